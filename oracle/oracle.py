@@ -1,0 +1,209 @@
+"""ctypes wrapper around oracle/liboracle.so (the plain-C restatement).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline leg -- never from the product package.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "liboracle.so")
+INT_MAX = 2**31 - 1
+
+
+def build(force=False):
+    srcs = [os.path.join(HERE, f) for f in ("ss_oracle.c", "ss_oracle.h", "ss_oracle_fsg.c")]
+    srcs = [s for s in srcs if os.path.exists(s)]
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
+        subprocess.check_call(["make", "-s", "-C", HERE, "liboracle"])
+    return LIB
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+class AlignOut(C.Structure):
+    _fields_ = [("rv", C.c_int32), ("best_score", C.c_int32), ("n_renorm", C.c_int32)]
+
+
+class Oracle:
+    def __init__(self, model_dir, logbase=1.0001, varfloor=1e-4, tmatfloor=1e-4, topn=4):
+        build()
+        self.lib = L = C.CDLL(LIB)
+        L.orc_model_load.restype = C.c_void_p
+        L.orc_model_load.argtypes = [C.c_char_p, C.c_double, C.c_float, C.c_double]
+        L.orc_model_free.argtypes = [C.c_void_p]
+        L.orc_ptm_new.restype = C.c_void_p
+        L.orc_ptm_new.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.orc_ptm_free.argtypes = [C.c_void_p]
+        L.orc_ptm_reset.argtypes = [C.c_void_p]
+        L.orc_logmath_log.restype = C.c_int32
+        L.orc_logmath_log.argtypes = [C.c_double, C.c_int, C.c_double]
+        h = L.orc_model_load(model_dir.encode(), logbase, varfloor, tmatfloor)
+        if not h:
+            raise RuntimeError("oracle model load failed: " + model_dir)
+        self.h = C.c_void_p(h)
+        self.topn = topn
+        dims = np.zeros(16, np.int32)
+        L.orc_model_dims(self.h, _p(dims, C.c_int32))
+        (self.n_mgau, self.n_feat, self.n_density, self.veclen, self.n_sen, self.n_sseq,
+         self.n_emit, self.n_tmat, self.n_ciphone, self.n_phone, self.sil) = [int(x) for x in dims[:11]]
+        self.D = self.n_feat * self.veclen
+        self._arrays = None
+
+    def close(self):
+        if self.h:
+            self.lib.orc_model_free(self.h)
+            self.h = None
+
+    def model_arrays(self):
+        if self._arrays is None:
+            mean = np.zeros((self.n_mgau, self.n_feat, self.n_density, self.veclen), np.float32)
+            var = np.zeros_like(mean)
+            det = np.zeros((self.n_mgau, self.n_feat, self.n_density), np.float32)
+            mixw = np.zeros((self.n_feat, self.n_density, self.n_sen), np.uint8)
+            sen2cb = np.zeros(self.n_sen, np.uint8)
+            tp = np.zeros((self.n_tmat, self.n_emit, self.n_emit + 1), np.uint8)
+            sseq = np.zeros((self.n_sseq, self.n_emit), np.uint16)
+            lut = np.zeros(256, np.uint8)
+            self.lib.orc_model_copy(self.h, _p(mean, C.c_float), _p(var, C.c_float), _p(det, C.c_float),
+                                    _p(mixw, C.c_uint8), _p(sen2cb, C.c_uint8), _p(tp, C.c_uint8),
+                                    _p(sseq, C.c_uint16), _p(lut, C.c_uint8))
+            self._arrays = dict(mean=mean, var=var, det=det, mixw=mixw, sen2cb=sen2cb, tp=tp,
+                                sseq=sseq, lut=lut)
+        return self._arrays
+
+    def phone_table(self):
+        ssid = np.zeros(self.n_phone, np.int32)
+        tmat = np.zeros(self.n_phone, np.int32)
+        ci = np.zeros(self.n_phone, np.int32)
+        self.lib.orc_phone_table(self.h, _p(ssid, C.c_int32), _p(tmat, C.c_int32), _p(ci, C.c_int32))
+        return ssid, tmat, ci
+
+    @staticmethod
+    def logadd_table8(base=1.0001, shift=10):
+        build()
+        L = C.CDLL(LIB)
+        out = np.zeros(256, np.uint8)
+        L.orc_logadd_table8.argtypes = [C.c_double, C.c_int, C.POINTER(C.c_uint8)]
+        rv = L.orc_logadd_table8(base, shift, _p(out, C.c_uint8))
+        return rv, out
+
+    # ---- scorer
+    def score_all(self, feat):
+        feat = np.ascontiguousarray(feat, np.float32)
+        T = feat.shape[0]
+        out = np.zeros((T, self.n_sen), np.int16)
+        self.lib.orc_ptm_score_all(self.h, self.topn, _p(feat, C.c_float), T, _p(out, C.c_int16))
+        return out
+
+    def topn_all(self, feat):
+        feat = np.ascontiguousarray(feat, np.float32)
+        T = feat.shape[0]
+        cw = np.zeros((T, self.n_mgau, self.n_feat, self.topn), np.uint8)
+        sc = np.zeros((T, self.n_mgau, self.n_feat, self.topn), np.int32)
+        self.lib.orc_ptm_topn_all(self.h, self.topn, _p(feat, C.c_float), T, _p(cw, C.c_uint8),
+                                  _p(sc, C.c_int32))
+        return cw, sc
+
+    def new_ptm(self):
+        return C.c_void_p(self.lib.orc_ptm_new(self.h, self.topn, 1))
+
+    def free_ptm(self, p):
+        self.lib.orc_ptm_free(p)
+
+    def frame_eval(self, ptm, feat, frame, active=None, compallsen=True, want_topn=False):
+        feat = np.ascontiguousarray(feat, np.float32).reshape(-1)
+        out = np.zeros(self.n_sen, np.int16)
+        if active is None:
+            active = np.zeros(1, np.uint8)
+            n_active = 0
+        else:
+            active = np.ascontiguousarray(active, np.uint8)
+            n_active = len(active)
+        topn = np.zeros((self.n_mgau, self.n_feat, self.topn, 2), np.int32) if want_topn else None
+        self.lib.orc_ptm_frame_eval(ptm, _p(out, C.c_int16), _p(active, C.c_uint8), n_active,
+                                    _p(feat, C.c_float), int(frame), int(compallsen),
+                                    _p(topn, C.c_int32))
+        return (out, topn) if want_topn else out
+
+    def flags2list(self, senones):
+        bits = np.zeros((self.n_sen + 31) // 32, np.uint32)
+        for s in senones:
+            bits[s >> 5] |= np.uint32(1 << (s & 31))
+        out = np.zeros(self.n_sen + 64, np.uint8)
+        n = self.lib.orc_flags2list(_p(bits, C.c_uint32), self.n_sen, _p(out, C.c_uint8))
+        return out[:n].copy()
+
+    # ---- HMM / aligner
+    def hmm_eval(self, n_emit, tp, senid, senscr, st):
+        tp = np.ascontiguousarray(tp, np.uint8)
+        senid = np.ascontiguousarray(senid, np.uint16)
+        senscr = np.ascontiguousarray(senscr, np.int16)
+        st = np.ascontiguousarray(st, np.int32).copy()
+        self.lib.orc_hmm_eval.restype = C.c_int32
+        best = self.lib.orc_hmm_eval(n_emit, _p(tp, C.c_uint8), _p(senid, C.c_uint16),
+                                     _p(senscr, C.c_int16), _p(st, C.c_int32))
+        return best, st
+
+    @staticmethod
+    def windows(start, dur):
+        """state_align_search_init's sf/ef rule (ref: state_align_search.c:464-471)."""
+        start = np.asarray(start, np.int32)
+        dur = np.asarray(dur, np.int32)
+        sf = np.where(start > 0, start, 0).astype(np.int32)
+        ef = np.where(dur > 0, start + dur, INT_MAX).astype(np.int32)
+        return sf, ef
+
+    def _al_common(self, n_phones, T, want_tokens):
+        ns = n_phones * self.n_emit
+        return (np.zeros(ns, np.int32), np.zeros(ns, np.int32), np.zeros(ns, np.int32),
+                np.zeros((T, ns, 2), np.int32) if want_tokens else None, AlignOut())
+
+    def state_align_dense(self, senscr, ssid, tmat, sf, ef, want_tokens=False):
+        senscr = np.ascontiguousarray(senscr, np.int16)
+        T = senscr.shape[0]
+        ssid, tmat, sf, ef = [np.ascontiguousarray(a, np.int32) for a in (ssid, tmat, sf, ef)]
+        n = len(ssid)
+        st, du, sc, tok, out = self._al_common(n, T, want_tokens)
+        self.lib.orc_state_align_dense(self.h, _p(senscr, C.c_int16), T, n, _p(ssid, C.c_int32),
+                                       _p(tmat, C.c_int32), _p(sf, C.c_int32), _p(ef, C.c_int32),
+                                       _p(st, C.c_int32), _p(du, C.c_int32), _p(sc, C.c_int32),
+                                       _p(tok, C.c_int32), C.byref(out))
+        return dict(rv=out.rv, best_score=out.best_score, n_renorm=out.n_renorm, start=st, dur=du,
+                    score=sc, tokens=tok)
+
+    def state_align(self, feat, ssid, tmat, sf, ef, init_active=None, compallsen=False,
+                    want_tokens=False, want_senscr=False):
+        feat = np.ascontiguousarray(feat, np.float32)
+        T = feat.shape[0]
+        ssid, tmat, sf, ef = [np.ascontiguousarray(a, np.int32) for a in (ssid, tmat, sf, ef)]
+        n = len(ssid)
+        st, du, sc, tok, out = self._al_common(n, T, want_tokens)
+        bits = None
+        if init_active is not None:
+            bits = np.zeros((self.n_sen + 31) // 32, np.uint32)
+            for s in init_active:
+                bits[s >> 5] |= np.uint32(1 << (s & 31))
+        senscr = np.zeros((T, self.n_sen), np.int16) if want_senscr else None
+        self.lib.orc_state_align(self.h, self.topn, _p(feat, C.c_float), T, n, _p(ssid, C.c_int32),
+                                 _p(tmat, C.c_int32), _p(sf, C.c_int32), _p(ef, C.c_int32),
+                                 _p(bits, C.c_uint32), int(compallsen), _p(st, C.c_int32),
+                                 _p(du, C.c_int32), _p(sc, C.c_int32), _p(tok, C.c_int32),
+                                 _p(senscr, C.c_int16), C.byref(out))
+        return dict(rv=out.rv, best_score=out.best_score, n_renorm=out.n_renorm, start=st, dur=du,
+                    score=sc, tokens=tok, senscr=senscr)
+
+    def propagate(self, start, dur, score):
+        n = len(start)
+        E = self.n_emit
+        ps, pd, pc = (np.zeros(n // E, np.int32) for _ in range(3))
+        self.lib.orc_propagate(n, E, _p(np.ascontiguousarray(start, np.int32), C.c_int32),
+                               _p(np.ascontiguousarray(dur, np.int32), C.c_int32),
+                               _p(np.ascontiguousarray(score, np.int32), C.c_int32),
+                               _p(ps, C.c_int32), _p(pd, C.c_int32), _p(pc, C.c_int32))
+        return ps, pd, pc

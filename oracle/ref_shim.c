@@ -157,9 +157,9 @@ ref_features_from_pcm(void *h, const int16 *pcm, long nsamp, float *out,
     ref_t *r = h;
     acmod_t *a = r->d->acmod;
     int nfr, t, f, D = 0, nf;
-    if (decoder_start_utt(r->d) < 0)
-        return -1;
-    /* Feed acmod directly so that no search consumes the frames. */
+    /* Feed acmod directly so that no search consumes the frames (and no
+     * grammar needs to be set). */
+    acmod_start_utt(a);
     {
         const int16 *p = pcm;
         size_t n = nsamp;

@@ -1,0 +1,119 @@
+/*
+ * ss_oracle.h -- CPU oracle: a plain-C restatement of the reference's
+ * acoustic-scoring + Viterbi-alignment hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline leg may load liboracle.so; the product
+ * (soundswallower_b200/) never links, imports or executes anything in oracle/.
+ *
+ * Parity status: PINNED.  Every function here is checked (tests/test_oracle_*.py)
+ * against the unmodified reference compiled as oracle/_ref/libssref.so and
+ * against golden vectors generated from it (tests/golden/, tools/make_golden.py),
+ * including the SURVEY.md Appendix-B goldens (hyp score -2761, the sha256 of the
+ * 278x5126 senone-score matrix, word/phone/state segmentations).
+ *
+ * All `ref:` citations are relative to ReadAlongs/SoundSwallower 0.6.1.
+ */
+#ifndef SS_ORACLE_H
+#define SS_ORACLE_H
+#include <stdint.h>
+
+#define ORC_WORST_SCORE ((int32_t)0xE0000000) /* ref: include/soundswallower/hmm.h:80 */
+#define ORC_TMAT_WORST (-255)                 /* ref: hmm.h:86 */
+#define ORC_SENSCR_SHIFT 10                   /* ref: hmm.h:69 */
+#define ORC_MAX_NEG_ASCR 96                   /* ref: tied_mgau_common.h:81 */
+#define ORC_MAX_NEG_MIXW 159                  /* ref: tied_mgau_common.h:80 */
+#define ORC_WORST_DIST INT32_MIN              /* ref: tied_mgau_common.h:60 */
+#define ORC_MAX_FEAT 8
+#define ORC_MAX_TOPN 8
+
+typedef struct orc_model_s {
+    /* gauden (ref: ms_gauden.h:83-92), flattened */
+    int32_t n_mgau, n_feat, n_density;
+    int32_t featlen[ORC_MAX_FEAT];
+    int32_t featoff[ORC_MAX_FEAT + 1]; /* offsets of each stream in a frame */
+    int32_t blk;                       /* sum of featlen */
+    float *mean;                       /* [mgau][feat][density][featlen[f]] (file order) */
+    float *var;                        /* same, after precompute */
+    float *det;                        /* [mgau][feat][density] */
+    int64_t *gau_off;                  /* [mgau][feat] offset into mean/var */
+    /* senones */
+    int32_t n_sen;
+    uint8_t *mixw;   /* [feat][density][n_sen], 4-bit clusters expanded */
+    uint8_t *sen2cb; /* [n_sen] */
+    /* mdef */
+    int32_t n_ciphone, n_phone, n_emit, n_ci_sen, n_tmat_mdef, n_sseq, n_ctx, n_cd_tree, sil;
+    uint16_t *sseq;   /* [n_sseq][n_emit] */
+    int32_t *ph_ssid; /* [n_phone] */
+    int32_t *ph_tmat;
+    int32_t *ph_ci;
+    char **ciname;
+    /* tmat */
+    int32_t n_tmat, n_state;
+    uint8_t *tp; /* [n_tmat][n_state][n_state+1] */
+    /* log math */
+    double logbase;
+    uint8_t lut8[256];
+    int32_t lmath_zero; /* shift-0 zero */
+} orc_model_t;
+
+/* ---- load-time (ref: logmath.c, ms_gauden.c, ptm_mgau.c read_sendump, bin_mdef.c, tmat.c) */
+int orc_logadd_table8(double base, int shift, uint8_t *out256);
+int32_t orc_logmath_log(double base, int shift, double p);
+orc_model_t *orc_model_load(const char *dir, double logbase, float varfloor, double tmatfloor);
+void orc_model_free(orc_model_t *m);
+int orc_model_dims(const orc_model_t *m, int32_t *out);
+int orc_model_copy(const orc_model_t *m, float *mean, float *var, float *det, uint8_t *mixw,
+                   uint8_t *sen2cb, uint8_t *tp, uint16_t *sseq, uint8_t *lut8);
+int orc_phone_table(const orc_model_t *m, int32_t *ssid, int32_t *tmat, int32_t *ci);
+
+/* ---- PTM scorer (ref: ptm_mgau.c) */
+typedef struct orc_ptm_s orc_ptm_t;
+orc_ptm_t *orc_ptm_new(const orc_model_t *m, int topn, int ds_ratio);
+void orc_ptm_free(orc_ptm_t *p);
+void orc_ptm_reset(orc_ptm_t *p);
+/* One frame_eval; `feat` = blk floats. active = delta list (ref acmod.c:947). If
+ * topn_out != NULL receives post-norm [mgau][feat][topn][2] = (cw, score). */
+int orc_ptm_frame_eval(orc_ptm_t *p, int16_t *senscr, const uint8_t *active, int32_t n_active,
+                       const float *feat, int32_t frame, int32_t compallsen, int32_t *topn_out);
+/* Whole-utterance compallsen scoring: out[T][n_sen]. Fresh history. */
+int orc_ptm_score_all(const orc_model_t *m, int topn, const float *feat, int T, int16_t *out);
+/* Raw (pre-norm) top-N for every frame, fresh history per call:
+ * cw[T][mgau][feat][topn] (u8), score[T][mgau][feat][topn] (i32) */
+int orc_ptm_topn_all(const orc_model_t *m, int topn, const float *feat, int T, uint8_t *cw,
+                     int32_t *score);
+
+/* ---- active list (ref: acmod.c:947-999) */
+int orc_flags2list(const uint32_t *bits, int n_sen, uint8_t *out);
+
+/* ---- HMM (ref: hmm.c:166-304, 482-567). st = score[5] hist[5] out_score out_hist */
+int32_t orc_hmm_eval(int n_emit, const uint8_t *tp, const uint16_t *senid, const int16_t *senscr,
+                     int32_t *st);
+
+/* ---- chain aligner (ref: state_align_search.c) */
+typedef struct orc_align_out_s {
+    int32_t rv;         /* 0 ok, -1 failed */
+    int32_t best_score; /* last frame's best */
+    int32_t n_renorm;
+} orc_align_out_t;
+/* Dense-score variant: senscr[T][n_sen] supplied ("given identical senone scores").
+ * phones: ssid[n], tmat[n], sf[n], ef[n] (ref state_align_search_init semantics already
+ * applied: sf=0 / ef=INT_MAX when unconstrained).
+ * Outputs: st_start/st_dur/st_score [n*n_emit]; tokens (optional) [T][n*n_emit][2]. */
+int orc_state_align_dense(const orc_model_t *m, const int16_t *senscr, int T, int n_phones,
+                          const int32_t *ssid, const int32_t *tmat, const int32_t *sf,
+                          const int32_t *ef, int32_t *st_start, int32_t *st_dur, int32_t *st_score,
+                          int32_t *tokens, orc_align_out_t *out);
+/* Full variant: scores computed frame by frame with the PTM scorer exactly as
+ * state_align_search_step does (activate -> acmod_score -> ...).
+ * init_active: optional bit vector (n_sen bits) the acmod starts with (pass 1
+ * leftovers), or NULL for empty.  compallsen selects the reference config key. */
+int orc_state_align(const orc_model_t *m, int topn, const float *feat, int T, int n_phones,
+                    const int32_t *ssid, const int32_t *tmat, const int32_t *sf, const int32_t *ef,
+                    const uint32_t *init_active, int compallsen, int32_t *st_start, int32_t *st_dur,
+                    int32_t *st_score, int32_t *tokens, int16_t *senscr_out, orc_align_out_t *out);
+/* ref: ps_alignment.c:317-355 (durations/scores summed upward) */
+int orc_propagate(int n_states, int n_emit, const int32_t *st_start, const int32_t *st_dur,
+                  const int32_t *st_score, int32_t *ph_start, int32_t *ph_dur, int32_t *ph_score);
+
+#endif
