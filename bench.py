@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py -- forced-alignment throughput of the B200 path (BASELINE.json metric:
+"forced-align audio-sec/sec", quoted on config #2: en-us senone scoring +
+state_align_search on 4096 synthetic 10 s utterances per GPU).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
+  python bench.py --impl reference [--gpus N] --steps K ...      the reference's CPU path
+
+One process per GPU (torchrun for N > 1); utterances are sharded across ranks with no
+collective on the data path (weak scaling: every rank aligns its own 4096 utterances).
+A step = one pass of the hot path over one batch:
+  * `value`: features resident in HBM, CUDA-event time of K1..backtrace on the launch stream;
+  * `e2e`  : the same batch through the C ABI with HOST buffers (pinned features in,
+             segmentations out), plan + H2D + kernels + D2H inside the timed region.
+Inputs (639 MB of features per rank) are larger than L2 and every step rewrites > 15 GB of
+intermediates, so no explicit L2 flush is needed between timed steps.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden", "align_en-us.npz")
+MODEL = os.path.join(ROOT, "soundswallower_b200", "model", "en-us")
+FRAMES = 1000          # 10 s utterances
+FRAME_RATE = 100.0     # frames per audio second (ref: config_defs.h "frate")
+
+
+# ------------------------------------------------------------------ workload
+def config2_template(g, frames=FRAMES):
+    """goforward features tiled 3x and padded with their trailing silence to `frames` frames;
+    chain = ("<sil> go forward ten meters") x3 + "<sil>": 16 words / 52 phones / 156 states,
+    word windows from the reference's first pass on the single sentence."""
+    import soundswallower_b200 as ssb
+    feat = g["feat"]                       # [278][39]
+    T1 = feat.shape[0]
+    words, phones = g["words"], g["phones"]
+    sil_tail = feat[int(words[-1, 1]):]    # trailing silence frames 211..277
+    reps = 3
+    base = np.concatenate([feat] * reps)
+    pad = frames - base.shape[0]
+    assert pad >= 0
+    tail = np.concatenate([sil_tail] * (pad // sil_tail.shape[0] + 1))[:pad]
+    base = np.concatenate([base, tail]).astype(np.float32)
+    n_ph_sentence = len(phones) - 1        # everything but the final silence
+    ssid, tmat, wstart, wdur = [], [], [], []
+    for k in range(reps):
+        for i in range(n_ph_sentence):
+            w = int(phones[i, 6])
+            s, d = int(words[w, 1]) + k * T1, int(words[w, 2])
+            if w == 0 and k > 0:           # leading silence merges with the previous trailing one
+                s = int(words[-1, 1]) + (k - 1) * T1
+                d = k * T1 + int(words[0, 2]) - s
+            ssid.append(int(phones[i, 1]))
+            tmat.append(int(phones[i, 2]))
+            wstart.append(s)
+            wdur.append(d)
+    s = int(words[-1, 1]) + (reps - 1) * T1
+    ssid.append(int(phones[-1, 1]))
+    tmat.append(int(phones[-1, 2]))
+    wstart.append(s)
+    wdur.append(frames - s)
+    sf, ef = ssb.windows(np.array(wstart, np.int32), np.array(wdur, np.int32))
+    chain = dict(ssid=np.array(ssid, np.int32), tmat=np.array(tmat, np.int32), sf=sf, ef=ef)
+    return base, chain
+
+
+def make_config2_batch(g, n_utts, noise=0.05, seed=1234, frames=FRAMES, out=None):
+    """Per-utterance additive N(0, noise^2) on the tiled features, Philox seed = seed + utt."""
+    base, chain = config2_template(g, frames)
+    feats = []
+    for u in range(n_utts):
+        rng = np.random.Generator(np.random.Philox(seed + u))
+        x = out[u] if out is not None else np.empty_like(base)
+        np.add(base, rng.standard_normal(base.shape, dtype=np.float32) * np.float32(noise), out=x)
+        feats.append(x)
+    return feats, [chain] * n_utts
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.stop = threading.Event()
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4)
+                          if len(r) > 3 + i and r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU legs (reference / oracle)
+_W = {}
+
+
+def _cpu_init(kind):
+    if kind == "reference":
+        from oracle.refshim import Ref
+        _W["ref"] = Ref(MODEL)
+    else:
+        from oracle.oracle import Oracle
+        _W["orc"] = Oracle(MODEL)
+    g = np.load(GOLDEN)
+    _W["g"] = g
+    _W["base"], _W["chain"] = config2_template(g)
+    words = g["words"]
+    T1 = g["feat"].shape[0]
+    wid, ws, wd = [], [], []
+    for k in range(3):
+        for w in range(len(words) - 1):
+            s, d = int(words[w, 1]) + k * T1, int(words[w, 2])
+            if w == 0 and k > 0:
+                s = int(words[-1, 1]) + (k - 1) * T1
+                d = k * T1 + int(words[0, 2]) - s
+            wid.append(int(words[w, 0]))
+            ws.append(s)
+            wd.append(d)
+    s = int(words[-1, 1]) + 2 * T1
+    wid.append(int(words[-1, 0]))
+    ws.append(s)
+    wd.append(FRAMES - s)
+    _W["words"] = (np.array(wid, np.int32), np.array(ws, np.int32), np.array(wd, np.int32))
+
+
+def _cpu_align(u):
+    """Second pass of the reference (re-score + chain Viterbi) on utterance u of the workload."""
+    rng = np.random.Generator(np.random.Philox(1234 + u))
+    base = _W["base"]
+    x = base + rng.standard_normal(base.shape, dtype=np.float32) * np.float32(0.05)
+    t0 = time.perf_counter()
+    if "ref" in _W:
+        wid, ws, wd = _W["words"]
+        r = _W["ref"].state_align(x, wid, ws, wd, clear_active=True)
+        ok = r["rv"] == 0
+        fp = int(r["states"][:, 2].astype(np.int64).sum())
+    else:
+        c = _W["chain"]
+        r = _W["orc"].state_align(x, c["ssid"], c["tmat"], c["sf"], c["ef"])
+        ok = r["rv"] == 0
+        fp = int(r["dur"].astype(np.int64).sum())
+    return time.perf_counter() - t0, ok, fp
+
+
+def cpu_kind():
+    from oracle import refshim
+    return "reference" if refshim.available() else "port"
+
+
+class CpuPool:
+    """`cores` worker processes, each with its own reference decoder (the reference is
+    single-threaded and not re-entrant)."""
+
+    def __init__(self, cores, kind):
+        import multiprocessing as mp
+        self.cores = cores
+        self.pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(kind,))
+        self.pool.map(_cpu_align, range(cores))  # warm the workers (model load, page-in)
+
+    def run(self, n_utts, first=0):
+        """Align `n_utts` utterances; returns (audio-s/s, all valid, wall seconds)."""
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_align, range(first, first + n_utts), chunksize=1)
+        wall = time.perf_counter() - t0
+        ok = all(r[1] for r in res) and all(r[2] == FRAMES for r in res)
+        return n_utts * FRAMES / FRAME_RATE / wall, ok, wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--utts", type=int, default=4096, help="utterances per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--compallsen", action="store_true", help="score every senone every frame")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    workload = ("config#2(i): en-us, %d x 10 s utterances per GPU, goforward features tiled 3x "
+                "+ N(0,0.05^2), 16 words / 52 phones / 156 states, word windows, "
+                "senone scoring (%s) + state_align_search" %
+                (args.utts, "compallsen" if args.compallsen else "active lists"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cores = host_cores()
+        kind = cpu_kind()
+        per_step = cores * 16
+        pool = CpuPool(cores, kind)
+        for _ in range(args.warmup):
+            pool.run(cores)
+        vals, oks = [], True
+        t_all = time.perf_counter()
+        for s in range(args.steps):
+            v, ok, _ = pool.run(per_step, first=s * per_step)
+            vals.append(v)
+            oks = oks and ok
+        wall = time.perf_counter() - t_all
+        pool.close()
+        v = float(np.mean(vals))
+        line = {"impl": "reference", "metric": "forced-align audio-sec/sec", "value": v,
+                "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+i32",
+                "data": "synthetic", "config": {"workload": workload, "sample_utts_per_step": per_step},
+                "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": kind,
+                                 "sample": "%d utterances (%.0f audio-s) per step, second pass "
+                                           "(re-score + state_align_search), all results valid=%s"
+                                           % (per_step, per_step * FRAMES / FRAME_RATE, oks)},
+                "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import soundswallower_b200 as ssb
+    from soundswallower_b200 import _build
+    _build.build_lib()
+    if not torch.cuda.is_available() or ssb.device_count() == 0:
+        raise SystemExit("bench.py needs a B200: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    g = np.load(GOLDEN)
+    model = ssb.AcousticModel(MODEL, device=local)
+    U = args.utts
+    # this rank's shard: utterances rank*U .. rank*U+U-1 of the global list
+    pinned = torch.empty((U, FRAMES, model.blk), dtype=torch.float32, pin_memory=True)
+    feat_np = pinned.numpy()
+    feats, chains = make_config2_batch(g, U, seed=1234 + rank * U, out=feat_np)
+    chain = chains[0]
+    frame_off = np.arange(U + 1, dtype=np.int64) * FRAMES
+    phone_off = np.arange(U + 1, dtype=np.int64) * len(chain["ssid"])
+    flat = {k: np.tile(chain[k], U) for k in ("ssid", "tmat", "sf", "ef")}
+    batch = ssb.StateAlignBatch(model)
+
+    def upload():
+        batch.upload_raw(feat_np.reshape(-1, model.blk), frame_off, phone_off, flat["ssid"],
+                         flat["tmat"], flat["sf"], flat["ef"], None, args.compallsen)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    upload()
+    for _ in range(args.warmup):
+        batch.run()
+    barrier()
+    kms = {k: 0.0 for k in ("gmm_topn", "senone_mix", "chain_viterbi", "backtrace", "total")}
+    launches = 0
+    with ClockSampler(local) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            batch.run()
+            launches += batch.n_launches()
+            ms = batch.kernel_ms()  # CUDA events on the launch stream; synchronises
+            for k in kms:
+                kms[k] += ms[k]
+        barrier()
+        wall_dev = time.perf_counter() - t0
+        clocks = clk.summary()
+    dev_ms = kms["total"] / args.steps
+    stats = batch.stats()
+    res = batch.download()
+    n_fail = int((res["rv"] != 0).sum())
+    h2d = feat_np.nbytes + sum(a.nbytes for a in flat.values()) + frame_off.nbytes + phone_off.nbytes
+    d2h = 3 * res["start"].nbytes + 3 * res["rv"].nbytes
+
+    # end to end through the public call, host buffers in and out
+    upload(); batch.run(); batch.download()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        upload()
+        batch.run()
+        res = batch.download()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+
+    audio_s = U * FRAMES / FRAME_RATE
+    t_dev = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(t_dev[0]), float(t_dev[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback"
+    # K1 algorithmic FLOPs: scanned codebook-frames x streams x densities x 2(2D+1)  
+    flop_per_cbframe = model.n_feat * model.n_density * 2 * (2 * model.veclen + 1)
+    k1_flops = stats["scanned_cb_frames"] * flop_per_cbframe
+    k1_ms = kms["gmm_topn"] / args.steps
+    achieved_tf = k1_flops / (k1_ms * 1e-3) / 1e12
+    # FP32-pipe view of the same kernel: 4 dependent-rounding FP32 ops per (density, dim)
+    fp32_ops = stats["scanned_cb_frames"] * model.n_feat * model.n_density * model.veclen * 4
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    fp32_peak = 148 * 128 * sm_mhz * 1e6
+    line = {
+        "metric": "forced-align audio-sec/sec", "value": world * audio_s / (dev_ms_max * 1e-3),
+        "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32+i32", "data": "synthetic",
+        "config": {"workload": workload, "utts_per_gpu": U, "frames_per_utt": FRAMES,
+                   "l2": "inputs (%.0f MB/rank) and per-step intermediates exceed the 126 MB L2; "
+                         "no flush needed" % (feat_np.nbytes / 1e6),
+                   "failed_alignments": n_fail},
+        "e2e": {"value": world * audio_s / (e2e_ms_max * 1e-3), "unit": "audio-s/s",
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_ms_max},
+        "gpu_launches": launches,
+        "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items()},
+        "clocks": clocks,
+        "roofline": {"kernel": "gmm_topn_kernel (K1: Gaussian eval + top-N)", "bound": "tensor",
+                     "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": peak_src,
+                     "note": "K1 runs bit-exact FP32 on the CUDA cores (no FMA contraction); "
+                             "fp32_pipe_frac is its share of 148 SM x 128 lanes at the sampled clock",
+                     "fp32_pipe_frac": fp32_ops / (k1_ms * 1e-3) / fp32_peak},
+        "senone_scores_per_s": stats["active_senone_frames"] / ((kms["gmm_topn"] + kms["senone_mix"]) / args.steps * 1e-3),
+        "dp_state_frames_per_s": stats["state_frames"] / (kms["chain_viterbi"] / args.steps * 1e-3),
+        "dp_hbm_frac_10B": stats["state_frames"] * 10 / (kms["chain_viterbi"] / args.steps * 1e-3) / 1e9
+                           / float(peaks.get("hbm_gbs", 6650.0)),
+        "wall_ms_per_step_device_loop": 1e3 * wall_dev / args.steps,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        kind = cpu_kind()
+        n = cores * 32
+        pool = CpuPool(cores, kind)
+        v, ok, wall = pool.run(n)
+        pool.close()
+        line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": kind,
+                                "sample": "%d utterances of the same workload (%.0f audio-s, %.1f s wall), "
+                                          "second pass of the reference (re-score + state_align_search), "
+                                          "valid=%s" % (n, n * FRAMES / FRAME_RATE, wall, ok)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,199 @@
+/*
+ * ssb200.h -- C ABI of libssb200.so: the B200 (sm_100a) acoustic-scoring and
+ * Viterbi-alignment hot path of SoundSwallower.
+ *
+ * Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ * Every entry point returns 0 (or a valid handle) on success and -1 / NULL on
+ * failure, like the reference's C API; ssb_last_error() holds the message the
+ * reference would have logged with E_ERROR.  There is NO CPU fallback: without a
+ * CUDA device (or without the sm_100a kernels) every compute call fails.
+ *
+ * `ref:` citations are relative to ReadAlongs/SoundSwallower 0.6.1.
+ *
+ * Two layers:
+ *   1. drop-in objects that keep the reference's static "plugin" layout
+ *      (ssb_mgau_t <-> mgau_t / mgaufuncs_t, ref: include/soundswallower/acmod.h:93-111);
+ *   2. additive *batched* entry points (many utterances per launch).  The
+ *      reference API is one frame at a time (ref: src/decoder.c:935-957) and would
+ *      serialise the GPU; the batched calls return exactly what a loop over the
+ *      per-utterance reference calls returns.
+ */
+#ifndef SSB200_H
+#define SSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSB_WORST_SCORE ((int32_t)0xE0000000) /* ref: hmm.h:80 */
+#define SSB_MAX_TOPN 4                        /* ref: config_defs.h "topn" default */
+#define SSB_MAX_FEAT 4
+#define SSB_MAX_CB 256 /* ref: ptm_mgau.c:754 */
+
+/* ------------------------------------------------------------------ */
+/* library                                                             */
+/* ------------------------------------------------------------------ */
+int ssb_version(void);
+const char *ssb_last_error(void);
+/* number of visible CUDA devices with compute capability 10.x; 0 if none */
+int ssb_device_count(void);
+
+/* ------------------------------------------------------------------ */
+/* model: loaders + packed device image                                */
+/* replaces: gauden_init_s3file + gauden_dist_precompute (ref: src/ms_gauden.c:105-258),
+ *           read_sendump / read_mixw (ref: src/ptm_mgau.c:456-692),
+ *           bin_mdef_read (ref: src/bin_mdef.c:333-520),
+ *           tmat_init_s3file (ref: src/tmat.c:125-225),
+ *           logmath_init (ref: src/logmath.c:61-163)                  */
+/* ------------------------------------------------------------------ */
+typedef struct ssb_config_s {
+    double logbase;  /* "logbase"   1.0001 */
+    float varfloor;  /* "varfloor"  1e-4   */
+    double mixwfloor; /* "mixwfloor" 1e-7   */
+    double tmatfloor; /* "tmatfloor" 1e-4   */
+    int32_t topn;    /* "topn"      4      */
+    int32_t ds;      /* "ds"        1      */
+    int32_t device;  /* CUDA ordinal; -1 = host arrays only (loader tests) */
+} ssb_config_t;
+void ssb_config_defaults(ssb_config_t *cfg);
+
+typedef struct ssb_model_s ssb_model_t;
+ssb_model_t *ssb_model_load(const char *hmmdir, const ssb_config_t *cfg);
+void ssb_model_free(ssb_model_t *m);
+/* out[0..10] = n_mgau n_feat n_density veclen(stream 0) n_sen n_sseq n_emit n_tmat
+ *              n_ciphone n_phone sil ; out[11..14] = featlen[0..3] ; out[15] = sum featlen */
+int ssb_model_dims(const ssb_model_t *m, int32_t *out16);
+/* host copies of the parsed tables (any pointer may be NULL):
+ * mean/var [mgau][feat][density][len]  det [mgau][feat][density]
+ * mixw [feat][density][n_sen]  sen2cb [n_sen]  tp [n_tmat][n_emit][n_emit+1]
+ * sseq [n_sseq][n_emit]  lut8 [256] */
+int ssb_model_copy(const ssb_model_t *m, float *mean, float *var, float *det, uint8_t *mixw,
+                   uint8_t *sen2cb, uint8_t *tp, uint16_t *sseq, uint8_t *lut8);
+/* per phone id: sequence id, transition matrix id, CI phone (ref: bin_mdef.h:160-175) */
+int ssb_model_phones(const ssb_model_t *m, int32_t *ssid, int32_t *tmat, int32_t *ci);
+
+/* ------------------------------------------------------------------ */
+/* scorer drop-in: same first members as mgau_t so that                 */
+/* acmod->mgau->frame_idx pokes (ref: src/acmod.c:367,748,760) and       */
+/* ps_mgau_frame_eval() dispatch (ref: acmod.h:113-114) work unchanged.  */
+/* ------------------------------------------------------------------ */
+typedef struct ssb_mgau_s ssb_mgau_t;
+typedef struct ssb_mgaufuncs_s {
+    const char *name;
+    int (*frame_eval)(ssb_mgau_t *mgau, int16_t *senscr, uint8_t *senone_active,
+                      int32_t n_senone_active, float **feat, int32_t frame, int32_t compallsen);
+    int (*transform)(ssb_mgau_t *mgau, void *mllr);
+    void (*free)(ssb_mgau_t *mgau);
+} ssb_mgaufuncs_t;
+struct ssb_mgau_s {
+    ssb_mgaufuncs_t *vt;
+    int frame_idx;
+    /* private state follows */
+};
+/* replaces ptm_mgau_init (ref: src/ptm_mgau.c:722-816); the model is borrowed */
+ssb_mgau_t *ssb_mgau_init(ssb_model_t *m);
+/* replaces ptm_mgau_frame_eval (ref: src/ptm_mgau.c:408-454): host buffers in, host
+ * senscr[n_sen] out, one frame, history kept on the device */
+int ssb_mgau_frame_eval(ssb_mgau_t *mgau, int16_t *senscr, uint8_t *senone_active,
+                        int32_t n_senone_active, float **feat, int32_t frame, int32_t compallsen);
+/* replaces ptm_mgau_reset_fast_hist (ref: src/ptm_mgau.c:694-720) */
+void ssb_mgau_reset(ssb_mgau_t *mgau);
+void ssb_mgau_free(ssb_mgau_t *mgau);
+
+/* ------------------------------------------------------------------ */
+/* batched path                                                        */
+/* ------------------------------------------------------------------ */
+/* One batch of independent utterances.  All arrays are host memory.
+ * Utterance u owns frames [frame_off[u], frame_off[u+1]) of `feat`
+ * ([frame][sum featlen] fp32, the layout of acmod's feat_buf, ref: src/feat.c:369-398)
+ * and phones [phone_off[u], phone_off[u+1]) of the chain arrays, which carry what
+ * state_align_search_init derives from the alignment (ref: src/state_align_search.c:429-474):
+ * ssid/tmat per phone, sf = window start (0 if none), ef = window end (INT32_MAX if none). */
+typedef struct ssb_align_in_s {
+    int32_t n_utts;
+    const float *feat;
+    const int64_t *frame_off;
+    const int64_t *phone_off;
+    const int32_t *ssid;
+    const int32_t *tmat;
+    const int32_t *sf;
+    const int32_t *ef;
+    /* optional [n_utts][(n_sen+31)/32]: senones already flagged active when pass 2
+     * starts (the reference never clears them, ref: src/state_align_search.c:186-188) */
+    const uint32_t *init_active;
+    int32_t compallsen; /* config key "compallsen" */
+} ssb_align_in_t;
+
+typedef struct ssb_align_out_s {
+    /* [total_phones * n_emit]: state start frame, duration, acoustic score
+     * (ref: src/state_align_search.c:215-268) */
+    int32_t *st_start;
+    int32_t *st_dur;
+    int32_t *st_score;
+    int32_t *utt_rv;     /* [n_utts] 0 ok, -1 "failed to reach final state" */
+    int32_t *utt_best;   /* [n_utts] best score of the last frame */
+    int32_t *utt_renorm; /* [n_utts] number of renormalisations */
+    /* optional debug outputs, NULL to skip */
+    int16_t *chain_scr; /* [sum_u T_u * n_states_u] senone score seen by each chain state */
+    int32_t *tokens;    /* [sum_u T_u * n_states_u * 2] {history id, score} */
+} ssb_align_out_t;
+
+/* Host-only (no device): the data-independent schedule the planner derives for one chain.
+ * enter[i] = first frame on which phone i is evaluated (== T: entered at the very end, never
+ * evaluated), -1 = never entered.  Phone i is then evaluated on [enter[i], max(enter[i], ef[i])].
+ * Restates the hmm_frame() bookkeeping of prune_hmms / phone_transition
+ * (ref: src/state_align_search.c:88-133) for window ends that do not decrease along the chain;
+ * returns -1 if they do. */
+int ssb_plan_chain(int32_t n_phones, int32_t n_frames, const int32_t *sf, const int32_t *ef,
+                   int32_t *enter);
+
+typedef struct ssb_batch_s ssb_batch_t;
+/* `stream` = a cudaStream_t (0 = the legacy default stream).  All kernels of the
+ * batch run on it, so a caller can bracket ssb_batch_run with its own events. */
+ssb_batch_t *ssb_batch_create(ssb_model_t *m, void *stream);
+void ssb_batch_free(ssb_batch_t *b);
+/* plan (active-senone epochs, offsets) + host->device copies */
+int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in);
+/* score + align on the device; asynchronous on the batch's stream */
+int ssb_batch_run(ssb_batch_t *b);
+/* device->host copies of the results; synchronises */
+int ssb_batch_download(ssb_batch_t *b, ssb_align_out_t *out);
+/* keep the whole token stack ({-1,-1} where the reference records nothing) so that
+ * ssb_batch_download can return it; off by default (only tokens of evaluated states
+ * are written).  Call before ssb_batch_run. */
+int ssb_batch_debug_tokens(ssb_batch_t *b, int on);
+/* CUDA-event durations (ms) of the kernels of the last ssb_batch_run:
+ * [0] gmm_topn [1] senone_mix [2] chain_viterbi [3] backtrace [4] whole run; synchronises */
+int ssb_batch_kernel_ms(ssb_batch_t *b, float *ms8);
+/* kernels launched by the last ssb_batch_run */
+int ssb_batch_n_launches(const ssb_batch_t *b);
+/* counters of the uploaded batch: [0] frames [1] state-frames [2] active senone-frames
+ * [3] scanned codebook-frames [4] device bytes held [5] largest active-senone union
+ * [6] longest chain (phones) */
+int ssb_batch_stats(const ssb_batch_t *b, int64_t *out8);
+
+/* upload + run + download in one call (the call a host program makes) */
+int ssb_align_batch(ssb_model_t *m, const ssb_align_in_t *in, ssb_align_out_t *out);
+
+/* Dense senone scoring of whole utterances with "compallsen" semantics
+ * (what acmod_score returns frame by frame, ref: src/acmod.c:822-860):
+ * senscr [total_frames][n_sen] int16, 0 = best.  senscr may be NULL to keep the
+ * result on the device only (throughput measurement); returns frames scored. */
+int64_t ssb_score_batch(ssb_model_t *m, const float *feat, const int64_t *frame_off,
+                        int32_t n_utts, int16_t *senscr);
+/* raw top-N of every (frame, codebook, stream), before normalisation:
+ * cw [frames][mgau][feat][topn] u8, score [..] int32 (ref: src/ptm_mgau.c:86-225) */
+int64_t ssb_topn_batch(ssb_model_t *m, const float *feat, const int64_t *frame_off,
+                       int32_t n_utts, uint8_t *cw, int32_t *score);
+
+/* single HMM step on the device (ref: src/hmm.c:482-567); st = score[5] hist[5]
+ * out_score out_hist, updated in place; returns best score via *best */
+int ssb_hmm_vit_eval(ssb_model_t *m, int32_t n_emit, int32_t tmatid, const uint16_t *senid,
+                     const int16_t *senscr, int32_t *st12, int32_t *best);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSB200_H */

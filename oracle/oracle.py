@@ -113,6 +113,13 @@ class Oracle:
     def new_ptm(self):
         return C.c_void_p(self.lib.orc_ptm_new(self.h, self.topn, 1))
 
+    def set_frame_idx(self, p, v):
+        self.lib.orc_ptm_set_frame_idx.argtypes = [C.c_void_p, C.c_int]
+        self.lib.orc_ptm_set_frame_idx(p, int(v))
+
+    def reset_ptm(self, p):
+        self.lib.orc_ptm_reset(p)
+
     def free_ptm(self, p):
         self.lib.orc_ptm_free(p)
 

@@ -825,6 +825,13 @@ orc_ptm_frame_eval(orc_ptm_t *p, int16_t *senscr, const uint8_t *active, int32_t
     return 0;
 }
 
+/* what acmod_advance / acmod_rewind do to mgau_t.frame_idx (ref: acmod.c:367,748,760) */
+void
+orc_ptm_set_frame_idx(orc_ptm_t *p, int frame_idx)
+{
+    p->frame_idx = frame_idx;
+}
+
 int
 orc_ptm_score_all(const orc_model_t *m, int topn, const float *feat, int T, int16_t *out)
 {

@@ -72,6 +72,7 @@ typedef struct orc_ptm_s orc_ptm_t;
 orc_ptm_t *orc_ptm_new(const orc_model_t *m, int topn, int ds_ratio);
 void orc_ptm_free(orc_ptm_t *p);
 void orc_ptm_reset(orc_ptm_t *p);
+void orc_ptm_set_frame_idx(orc_ptm_t *p, int frame_idx);
 /* One frame_eval; `feat` = blk floats. active = delta list (ref acmod.c:947). If
  * topn_out != NULL receives post-norm [mgau][feat][topn][2] = (cw, score). */
 int orc_ptm_frame_eval(orc_ptm_t *p, int16_t *senscr, const uint8_t *active, int32_t n_active,

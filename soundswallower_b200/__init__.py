@@ -1,0 +1,415 @@
+"""soundswallower_b200 -- B200 (sm_100a) acoustic scoring + Viterbi alignment.
+
+Python mirror of the reference interfaces for this one path, over the C ABI of
+libssb200.so (include/ssb200.h):
+
+  AcousticModel    the model tables acmod_load_am builds (ref: src/acmod.c:62-129)
+  PtmMgau          mgau_t / mgaufuncs_t, one frame per call (ref: include/soundswallower/acmod.h:93-119)
+  StateAlignBatch  state_align_search over a batch of utterances
+                   (ref: src/state_align_search.c:177-268, 429-474)
+  score_batch / topn_batch / hmm_vit_eval   the pieces, for tests and benchmarks
+
+numpy arrays in, numpy arrays out; all compute happens in the CUDA library.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import Config, SsbError
+
+INT_MAX = 2**31 - 1
+WORST_SCORE = -536870912  # ref: include/soundswallower/hmm.h:80
+MODEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "model")
+
+__all__ = ["AcousticModel", "PtmMgau", "StateAlignBatch", "align_batch", "score_batch",
+           "topn_batch", "hmm_vit_eval", "windows", "plan_chain", "propagate", "flags2list", "device_count",
+           "SsbError", "Config", "MODEL_DIR", "INT_MAX", "WORST_SCORE"]
+
+
+def _ptr(a, t=None):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.POINTER(t)) if t is not None else a.ctypes.data_as(C.c_void_p)
+
+
+def device_count():
+    return _lib.load().ssb_device_count()
+
+
+def model_path(name):
+    """Bundled model directory ("en-us", "fr-fr")."""
+    return os.path.join(MODEL_DIR, name)
+
+
+class AcousticModel:
+    """Parsed model directory + its packed image in HBM.
+
+    device=-1 parses only (loader tests on machines without a GPU); every compute
+    call on such a model fails -- there is no CPU path."""
+
+    def __init__(self, hmmdir, device=0, topn=4, ds=1, logbase=1.0001, varfloor=1e-4,
+                 mixwfloor=1e-7, tmatfloor=1e-4):
+        self.lib = L = _lib.load()
+        cfg = Config()
+        L.ssb_config_defaults(C.byref(cfg))
+        cfg.logbase, cfg.varfloor, cfg.mixwfloor, cfg.tmatfloor = logbase, varfloor, mixwfloor, tmatfloor
+        cfg.topn, cfg.ds, cfg.device = topn, ds, device
+        h = L.ssb_model_load(os.fsencode(hmmdir), C.byref(cfg))
+        if not h:
+            raise SsbError("ssb_model_load(%s): %s" % (hmmdir, _lib.last_error()))
+        self.h = C.c_void_p(h)
+        self.device = device
+        self.topn = topn
+        d = np.zeros(16, np.int32)
+        L.ssb_model_dims(self.h, _ptr(d, C.c_int32))
+        (self.n_mgau, self.n_feat, self.n_density, self.veclen, self.n_sen, self.n_sseq,
+         self.n_emit, self.n_tmat, self.n_ciphone, self.n_phone, self.sil) = [int(x) for x in d[:11]]
+        self.featlen = [int(x) for x in d[11:11 + self.n_feat]]
+        self.blk = int(d[15])
+        self._arrays = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ssb_model_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def arrays(self):
+        """Host copies of the parsed tables, in the reference's in-memory shapes."""
+        if self._arrays is None:
+            L = self.n_mgau, self.n_feat, self.n_density
+            if len(set(self.featlen)) == 1:
+                mean = np.zeros(L + (self.veclen,), np.float32)
+            else:
+                mean = np.zeros(self.n_mgau * self.n_density * self.blk, np.float32)
+            var = np.zeros_like(mean)
+            det = np.zeros(L, np.float32)
+            mixw = np.zeros((self.n_feat, self.n_density, self.n_sen), np.uint8)
+            sen2cb = np.zeros(self.n_sen, np.uint8)
+            tp = np.zeros((self.n_tmat, self.n_emit, self.n_emit + 1), np.uint8)
+            sseq = np.zeros((self.n_sseq, self.n_emit), np.uint16)
+            lut = np.zeros(256, np.uint8)
+            self.lib.ssb_model_copy(self.h, _ptr(mean), _ptr(var), _ptr(det), _ptr(mixw),
+                                    _ptr(sen2cb), _ptr(tp), _ptr(sseq), _ptr(lut))
+            self._arrays = dict(mean=mean, var=var, det=det, mixw=mixw, sen2cb=sen2cb, tp=tp,
+                                sseq=sseq, lut=lut)
+        return self._arrays
+
+    def phone_table(self):
+        ssid = np.zeros(self.n_phone, np.int32)
+        tmat = np.zeros(self.n_phone, np.int32)
+        ci = np.zeros(self.n_phone, np.int32)
+        self.lib.ssb_model_phones(self.h, _ptr(ssid), _ptr(tmat), _ptr(ci))
+        return ssid, tmat, ci
+
+
+def flags2list(senones, n_sen=None):
+    """acmod_flags2list (ref: src/acmod.c:947-999): sorted senone ids -> uint8 delta list,
+    gaps above 255 bridged with extra entries."""
+    out, last = [], 0
+    for s in sorted(set(int(x) for x in senones)):
+        delta = s - last
+        while delta > 255:
+            out.append(255)
+            delta -= 255
+        out.append(delta)
+        last = s
+    return np.asarray(out, np.uint8)
+
+
+class PtmMgau:
+    """The scorer object behind acmod_score: same layout ({vt, frame_idx} first) and the same
+    frame_eval contract as mgau_t / mgaufuncs_t (ref: acmod.h:93-119, src/ptm_mgau.c:408-454).
+    Calls go through the object's own vtable pointer, like ps_mgau_frame_eval() does."""
+
+    def __init__(self, model):
+        self.model = model
+        self.lib = model.lib
+        self.p = self.lib.ssb_mgau_init(model.h)
+        if not self.p:
+            raise SsbError("ssb_mgau_init: " + _lib.last_error())
+
+    @property
+    def name(self):
+        return self.p.contents.vt.contents.name.decode()
+
+    @property
+    def frame_idx(self):
+        return self.p.contents.frame_idx
+
+    @frame_idx.setter
+    def frame_idx(self, v):
+        self.p.contents.frame_idx = int(v)  # what acmod_advance / acmod_rewind poke
+
+    def reset(self):
+        self.lib.ssb_mgau_reset(self.p)
+
+    def frame_eval(self, feat, frame, senone_active=None, compallsen=False):
+        """feat: [blk] floats of one frame (streams concatenated).  senone_active: uint8
+        delta list as produced by flags2list.  Returns int16[n_sen]."""
+        m = self.model
+        feat = np.ascontiguousarray(feat, np.float32).reshape(-1)
+        assert feat.size == m.blk
+        ptrs = (C.POINTER(C.c_float) * m.n_feat)()
+        off = 0
+        for f in range(m.n_feat):
+            ptrs[f] = C.cast(feat.ctypes.data + 4 * off, C.POINTER(C.c_float))
+            off += m.featlen[f]
+        if senone_active is None:
+            act = np.zeros(1, np.uint8)
+            n_act = 0
+        else:
+            act = np.ascontiguousarray(senone_active, np.uint8)
+            n_act = len(act)
+        out = np.zeros(m.n_sen, np.int16)
+        fn = self.p.contents.vt.contents.frame_eval
+        rv = fn(C.cast(self.p, C.c_void_p), _ptr(out, C.c_int16), _ptr(act, C.c_uint8), n_act, ptrs,
+                int(frame), int(bool(compallsen)))
+        _lib.check(rv, "mgau frame_eval")
+        return out
+
+    def close(self):
+        if getattr(self, "p", None):
+            self.lib.ssb_mgau_free(self.p)
+            self.p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def windows(start, dur):
+    """state_align_search_init's window rule (ref: src/state_align_search.c:464-471)."""
+    start = np.asarray(start, np.int32)
+    dur = np.asarray(dur, np.int32)
+    sf = np.where(start > 0, start, 0).astype(np.int32)
+    ef = np.where(dur > 0, start.astype(np.int64) + dur, INT_MAX).astype(np.int32)
+    return sf, ef
+
+
+def plan_chain(n_frames, sf, ef):
+    """Host-only: the frame each phone of a chain is first evaluated on (-1 never)."""
+    sf = np.ascontiguousarray(sf, np.int32)
+    ef = np.ascontiguousarray(ef, np.int32)
+    enter = np.full(len(sf), -1, np.int32)
+    rv = _lib.load().ssb_plan_chain(len(sf), int(n_frames), _ptr(sf), _ptr(ef), _ptr(enter))
+    _lib.check(rv, "ssb_plan_chain")
+    return enter
+
+
+def propagate(start, dur, score, n_emit):
+    """alignment_propagate, states -> phones (ref: src/ps_alignment.c:317-341)."""
+    start = np.asarray(start).reshape(-1, n_emit)
+    dur = np.asarray(dur).reshape(-1, n_emit)
+    score = np.asarray(score).reshape(-1, n_emit)
+    return start[:, 0].copy(), dur.sum(1).astype(np.int32), score.sum(1).astype(np.int32)
+
+
+def _concat_i32(seq):
+    seq = [np.ascontiguousarray(a, np.int32).reshape(-1) for a in seq]
+    return np.concatenate(seq) if seq else np.zeros(0, np.int32)
+
+
+class StateAlignBatch:
+    """A batch of state_align_search problems resident on one GPU.
+
+    upload(feats, chains) -> run() -> download().  `chains` is a list of dicts with the
+    per-phone arrays state_align_search_init derives: ssid, tmat, sf, ef."""
+
+    def __init__(self, model, stream=None):
+        self.model = model
+        self.lib = model.lib
+        self.b = self.lib.ssb_batch_create(model.h, C.c_void_p(stream or 0))
+        if not self.b:
+            raise SsbError("ssb_batch_create: " + _lib.last_error())
+        self.b = C.c_void_p(self.b)
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "b", None):
+            self.lib.ssb_batch_free(self.b)
+            self.b = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload_raw(self, feat, frame_off, phone_off, ssid, tmat, sf, ef, init_active=None,
+                   compallsen=False):
+        """Flat arrays exactly as ssb_align_in_t takes them (feat may be pinned memory)."""
+        n_utts = len(frame_off) - 1
+        a = _lib.AlignIn()
+        a.n_utts = n_utts
+        a.feat = _ptr(feat, C.c_float)
+        a.frame_off = _ptr(frame_off, C.c_int64)
+        a.phone_off = _ptr(phone_off, C.c_int64)
+        a.ssid = _ptr(ssid, C.c_int32)
+        a.tmat = _ptr(tmat, C.c_int32)
+        a.sf = _ptr(sf, C.c_int32)
+        a.ef = _ptr(ef, C.c_int32)
+        a.init_active = _ptr(init_active, C.c_uint32) if init_active is not None else None
+        a.compallsen = int(bool(compallsen))
+        self._keep = (feat, frame_off, phone_off, ssid, tmat, sf, ef, init_active)
+        self.n_utts = n_utts
+        self.frame_off = np.asarray(frame_off)
+        self.phone_off = np.asarray(phone_off)
+        _lib.check(self.lib.ssb_batch_upload(self.b, C.byref(a)), "ssb_batch_upload")
+
+    def upload(self, feats, chains, init_active=None, compallsen=False):
+        m = self.model
+        feats = [np.ascontiguousarray(f, np.float32).reshape(-1, m.blk) for f in feats]
+        assert len(feats) == len(chains)
+        frame_off = np.zeros(len(feats) + 1, np.int64)
+        phone_off = np.zeros(len(feats) + 1, np.int64)
+        for i, (f, c) in enumerate(zip(feats, chains)):
+            frame_off[i + 1] = frame_off[i] + f.shape[0]
+            phone_off[i + 1] = phone_off[i] + len(c["ssid"])
+        feat = np.concatenate(feats) if feats else np.zeros((0, m.blk), np.float32)
+        ia = None
+        if init_active is not None:
+            nw = (m.n_sen + 31) // 32
+            ia = np.zeros((len(feats), nw), np.uint32)
+            for u, sens in enumerate(init_active):
+                for s in (sens or ()):
+                    ia[u, s >> 5] |= np.uint32(1 << (s & 31))
+        self.upload_raw(feat, frame_off, phone_off, _concat_i32([c["ssid"] for c in chains]),
+                        _concat_i32([c["tmat"] for c in chains]),
+                        _concat_i32([c["sf"] for c in chains]),
+                        _concat_i32([c["ef"] for c in chains]), ia, compallsen)
+
+    def debug_tokens(self, on=True):
+        self.lib.ssb_batch_debug_tokens(self.b, int(on))
+        self._tokens = bool(on)
+
+    def run(self):
+        _lib.check(self.lib.ssb_batch_run(self.b), "ssb_batch_run")
+
+    def download(self, want_chain_scr=False, want_tokens=False, init=None):
+        """Returns flat arrays; `per_utt()` splits them.  `init` = (start, dur, score) the
+        caller's pre-filled state entries (states off the best path keep them)."""
+        E = self.model.n_emit
+        ns = int(self.phone_off[-1]) * E
+        U = self.n_utts
+        if init is None:
+            st = [np.zeros(ns, np.int32) for _ in range(3)]
+        else:
+            st = [np.ascontiguousarray(a, np.int32).copy() for a in init]
+        rv, best, ren = (np.zeros(U, np.int32) for _ in range(3))
+        T = np.diff(self.frame_off)
+        npz = np.diff(self.phone_off)
+        nsf = int((T * npz * E).sum())
+        cs = np.zeros(nsf, np.int16) if want_chain_scr else None
+        tk = np.zeros((nsf, 2), np.int32) if want_tokens else None
+        o = _lib.AlignOut()
+        o.st_start, o.st_dur, o.st_score = (_ptr(a, C.c_int32) for a in st)
+        o.utt_rv, o.utt_best, o.utt_renorm = (_ptr(a, C.c_int32) for a in (rv, best, ren))
+        o.chain_scr = _ptr(cs, C.c_int16) if cs is not None else None
+        o.tokens = _ptr(tk, C.c_int32) if tk is not None else None
+        _lib.check(self.lib.ssb_batch_download(self.b, C.byref(o)), "ssb_batch_download")
+        return dict(start=st[0], dur=st[1], score=st[2], rv=rv, best_score=best, n_renorm=ren,
+                    chain_scr=cs, tokens=tk)
+
+    def per_utt(self, res):
+        E = self.model.n_emit
+        out = []
+        sf_off = 0
+        for u in range(self.n_utts):
+            p0, p1 = int(self.phone_off[u]) * E, int(self.phone_off[u + 1]) * E
+            T = int(self.frame_off[u + 1] - self.frame_off[u])
+            n = T * (p1 - p0)
+            d = dict(start=res["start"][p0:p1], dur=res["dur"][p0:p1], score=res["score"][p0:p1],
+                     rv=int(res["rv"][u]), best_score=int(res["best_score"][u]),
+                     n_renorm=int(res["n_renorm"][u]))
+            if res.get("chain_scr") is not None:
+                d["chain_scr"] = res["chain_scr"][sf_off:sf_off + n].reshape(T, p1 - p0)
+            if res.get("tokens") is not None:
+                d["tokens"] = res["tokens"][sf_off:sf_off + n].reshape(T, p1 - p0, 2)
+            sf_off += n
+            out.append(d)
+        return out
+
+    def kernel_ms(self):
+        ms = np.zeros(8, np.float32)
+        _lib.check(self.lib.ssb_batch_kernel_ms(self.b, _ptr(ms, C.c_float)), "ssb_batch_kernel_ms")
+        return dict(gmm_topn=float(ms[0]), senone_mix=float(ms[1]), chain_viterbi=float(ms[2]),
+                    backtrace=float(ms[3]), total=float(ms[4]))
+
+    def n_launches(self):
+        return int(self.lib.ssb_batch_n_launches(self.b))
+
+    def stats(self):
+        s = np.zeros(8, np.int64)
+        self.lib.ssb_batch_stats(self.b, _ptr(s, C.c_int64))
+        return dict(frames=int(s[0]), state_frames=int(s[1]), active_senone_frames=int(s[2]),
+                    scanned_cb_frames=int(s[3]), device_bytes=int(s[4]), max_union=int(s[5]),
+                    max_phones=int(s[6]))
+
+
+def align_batch(model, feats, chains, init_active=None, compallsen=False, want_chain_scr=False,
+                want_tokens=False):
+    """One-shot: upload + run + download; returns a list of per-utterance dicts
+    (start/dur/score per state, rv, best_score, n_renorm[, chain_scr, tokens])."""
+    b = StateAlignBatch(model)
+    try:
+        if want_tokens:
+            b.debug_tokens(True)
+        b.upload(feats, chains, init_active=init_active, compallsen=compallsen)
+        b.run()
+        return b.per_utt(b.download(want_chain_scr=want_chain_scr, want_tokens=want_tokens))
+    finally:
+        b.close()
+
+
+def score_batch(model, feats, want=True):
+    """acmod_score over whole utterances with compallsen semantics: list of int16 [T][n_sen]."""
+    feats = [np.ascontiguousarray(f, np.float32).reshape(-1, model.blk) for f in feats]
+    off = np.zeros(len(feats) + 1, np.int64)
+    for i, f in enumerate(feats):
+        off[i + 1] = off[i] + f.shape[0]
+    feat = np.concatenate(feats) if feats else np.zeros((0, model.blk), np.float32)
+    out = np.zeros((int(off[-1]), model.n_sen), np.int16) if want else None
+    n = model.lib.ssb_score_batch(model.h, _ptr(feat), _ptr(off), len(feats), _ptr(out))
+    _lib.check(int(n), "ssb_score_batch")
+    if not want:
+        return int(n)
+    return [out[off[i]:off[i + 1]] for i in range(len(feats))]
+
+
+def topn_batch(model, feats):
+    """Raw top-N (codeword ids, int32 scores) of every frame/codebook/stream."""
+    feats = [np.ascontiguousarray(f, np.float32).reshape(-1, model.blk) for f in feats]
+    off = np.zeros(len(feats) + 1, np.int64)
+    for i, f in enumerate(feats):
+        off[i + 1] = off[i] + f.shape[0]
+    feat = np.concatenate(feats) if feats else np.zeros((0, model.blk), np.float32)
+    G = int(off[-1])
+    cw = np.zeros((G, model.n_mgau, model.n_feat, model.topn), np.uint8)
+    sc = np.zeros((G, model.n_mgau, model.n_feat, model.topn), np.int32)
+    n = model.lib.ssb_topn_batch(model.h, _ptr(feat), _ptr(off), len(feats), _ptr(cw), _ptr(sc))
+    _lib.check(int(n), "ssb_topn_batch")
+    return ([cw[off[i]:off[i + 1]] for i in range(len(feats))],
+            [sc[off[i]:off[i + 1]] for i in range(len(feats))])
+
+
+def hmm_vit_eval(model, tmatid, senid, senscr, st):
+    """hmm_vit_eval on one HMM (ref: src/hmm.c:741-759).  st = score[5] hist[5] out_score
+    out_hist; returns (best, new st)."""
+    senid = np.ascontiguousarray(senid, np.uint16)
+    senscr = np.ascontiguousarray(senscr, np.int16)
+    st = np.ascontiguousarray(st, np.int32).copy()
+    best = C.c_int32(0)
+    rv = model.lib.ssb_hmm_vit_eval(model.h, model.n_emit, int(tmatid), _ptr(senid), _ptr(senscr),
+                                    _ptr(st), C.byref(best))
+    _lib.check(rv, "ssb_hmm_vit_eval")
+    return best.value, st

@@ -1,0 +1,129 @@
+"""ctypes binding of libssb200.so (the C ABI declared in include/ssb200.h).
+
+There is deliberately no fallback: if the shared library is missing this module
+raises, and if it loads but finds no B200 every compute call returns -1 and the
+wrappers raise SsbError with the library's message.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libssb200.so")
+
+
+class SsbError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    """ssb_config_t -- the reference config keys that reach the hot path
+    (ref: include/soundswallower/config_defs.h:78-257)."""
+    _fields_ = [("logbase", C.c_double), ("varfloor", C.c_float), ("mixwfloor", C.c_double),
+                ("tmatfloor", C.c_double), ("topn", C.c_int32), ("ds", C.c_int32),
+                ("device", C.c_int32)]
+
+
+class AlignIn(C.Structure):
+    _fields_ = [("n_utts", C.c_int32), ("feat", C.POINTER(C.c_float)),
+                ("frame_off", C.POINTER(C.c_int64)), ("phone_off", C.POINTER(C.c_int64)),
+                ("ssid", C.POINTER(C.c_int32)), ("tmat", C.POINTER(C.c_int32)),
+                ("sf", C.POINTER(C.c_int32)), ("ef", C.POINTER(C.c_int32)),
+                ("init_active", C.POINTER(C.c_uint32)), ("compallsen", C.c_int32)]
+
+
+class AlignOut(C.Structure):
+    _fields_ = [("st_start", C.POINTER(C.c_int32)), ("st_dur", C.POINTER(C.c_int32)),
+                ("st_score", C.POINTER(C.c_int32)), ("utt_rv", C.POINTER(C.c_int32)),
+                ("utt_best", C.POINTER(C.c_int32)), ("utt_renorm", C.POINTER(C.c_int32)),
+                ("chain_scr", C.POINTER(C.c_int16)), ("tokens", C.POINTER(C.c_int32))]
+
+
+MGAU_FRAME_EVAL = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int16), C.POINTER(C.c_uint8),
+                              C.c_int32, C.POINTER(C.POINTER(C.c_float)), C.c_int32, C.c_int32)
+
+
+class MgauFuncs(C.Structure):
+    """ssb_mgaufuncs_t == mgaufuncs_t (ref: include/soundswallower/acmod.h:93-106)."""
+    _fields_ = [("name", C.c_char_p), ("frame_eval", MGAU_FRAME_EVAL),
+                ("transform", C.c_void_p), ("free", C.c_void_p)]
+
+
+class MgauBase(C.Structure):
+    """ssb_mgau_t == mgau_t (ref: acmod.h:108-111): {vt, frame_idx}."""
+    _fields_ = [("vt", C.POINTER(MgauFuncs)), ("frame_idx", C.c_int)]
+
+
+# every symbol include/ssb200.h declares
+SYMBOLS = [
+    "ssb_version", "ssb_last_error", "ssb_device_count", "ssb_config_defaults",
+    "ssb_model_load", "ssb_model_free", "ssb_model_dims", "ssb_model_copy", "ssb_model_phones",
+    "ssb_mgau_init", "ssb_mgau_frame_eval", "ssb_mgau_reset", "ssb_mgau_free",
+    "ssb_plan_chain", "ssb_batch_create", "ssb_batch_free", "ssb_batch_upload", "ssb_batch_run",
+    "ssb_batch_download", "ssb_batch_debug_tokens", "ssb_batch_kernel_ms",
+    "ssb_batch_n_launches", "ssb_batch_stats", "ssb_align_batch", "ssb_score_batch",
+    "ssb_topn_batch", "ssb_hmm_vit_eval",
+]
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SsbError("libssb200.so is not built (run `python -m soundswallower_b200._build`); "
+                       "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    P = C.POINTER
+    L.ssb_version.restype = C.c_int
+    L.ssb_last_error.restype = C.c_char_p
+    L.ssb_device_count.restype = C.c_int
+    L.ssb_config_defaults.argtypes = [P(Config)]
+    L.ssb_config_defaults.restype = None
+    L.ssb_model_load.restype = vp
+    L.ssb_model_load.argtypes = [C.c_char_p, P(Config)]
+    L.ssb_model_free.argtypes = [vp]
+    L.ssb_model_free.restype = None
+    L.ssb_model_dims.argtypes = [vp, P(i32)]
+    L.ssb_model_copy.argtypes = [vp] + [vp] * 8
+    L.ssb_model_phones.argtypes = [vp, vp, vp, vp]
+    L.ssb_mgau_init.restype = P(MgauBase)
+    L.ssb_mgau_init.argtypes = [vp]
+    L.ssb_mgau_frame_eval.argtypes = [P(MgauBase), P(C.c_int16), P(C.c_uint8), i32,
+                                      P(P(C.c_float)), i32, i32]
+    L.ssb_mgau_reset.argtypes = [P(MgauBase)]
+    L.ssb_mgau_reset.restype = None
+    L.ssb_mgau_free.argtypes = [P(MgauBase)]
+    L.ssb_mgau_free.restype = None
+    L.ssb_plan_chain.argtypes = [i32, i32, vp, vp, vp]
+    L.ssb_batch_create.restype = vp
+    L.ssb_batch_create.argtypes = [vp, vp]
+    L.ssb_batch_free.argtypes = [vp]
+    L.ssb_batch_free.restype = None
+    L.ssb_batch_upload.argtypes = [vp, P(AlignIn)]
+    L.ssb_batch_run.argtypes = [vp]
+    L.ssb_batch_download.argtypes = [vp, P(AlignOut)]
+    L.ssb_batch_debug_tokens.argtypes = [vp, C.c_int]
+    L.ssb_batch_kernel_ms.argtypes = [vp, P(C.c_float)]
+    L.ssb_batch_n_launches.argtypes = [vp]
+    L.ssb_batch_stats.argtypes = [vp, P(i64)]
+    L.ssb_align_batch.argtypes = [vp, P(AlignIn), P(AlignOut)]
+    L.ssb_score_batch.restype = i64
+    L.ssb_score_batch.argtypes = [vp, vp, vp, i32, vp]
+    L.ssb_topn_batch.restype = i64
+    L.ssb_topn_batch.argtypes = [vp, vp, vp, i32, vp, vp]
+    L.ssb_hmm_vit_eval.argtypes = [vp, i32, i32, vp, vp, vp, P(i32)]
+    _lib = L
+    return L
+
+
+def last_error():
+    return load().ssb_last_error().decode("utf-8", "replace")
+
+
+def check(rv, what):
+    if rv is None or (isinstance(rv, int) and rv < 0):
+        raise SsbError("%s failed: %s" % (what, last_error()))
+    return rv

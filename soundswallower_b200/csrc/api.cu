@@ -1,0 +1,1263 @@
+// api.cu -- the C ABI of libssb200.so (include/ssb200.h): model image in HBM, the
+// mgau_t drop-in, the host-side planner of a batch and the kernel pipeline
+//   K1 gmm_topn -> K2 senone_mix -> K3 chain_viterbi -> backtrace.
+// No CPU fallback: every compute entry point needs a CUDA device.
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "device.cuh"
+
+namespace ssb {
+const char *last_error();
+int launch_senone_mix_active(const DevModel &m, const DevPlan &p, const int4 *tn_score,
+                             const uchar4 *tn_cw, int64_t n_frames, int max_union,
+                             int max_frames_per_utt, int16_t *chain_scr, cudaStream_t st);
+int launch_subtract_best(const DevModel &m, int16_t *dense, const int32_t *best, int64_t n,
+                         cudaStream_t st);
+int launch_gather_chain_best(const DevModel &m, const DevPlan &p, const int16_t *dense,
+                             const int32_t *best, int u0, int u1, int64_t g0, int16_t *chain_scr,
+                             cudaStream_t st);
+int launch_chain_viterbi(const DevModel &m, const DevPlan &p, const int16_t *chain_scr,
+                         int2 *tokens, int32_t *spill, int64_t spill_stride, int32_t *utt_best,
+                         int32_t *utt_renorm, int32_t *fin_hist, int32_t *fin_score,
+                         int max_phones, cudaStream_t st);
+}  // namespace ssb
+
+using namespace ssb;
+
+#define API_CUDA(call, rv)                                                                  \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            ssb::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,             \
+                           cudaGetErrorString(e_));                                         \
+            return rv;                                                                      \
+        }                                                                                   \
+    } while (0)
+
+// ------------------------------------------------------------------ small helpers
+namespace {
+
+// grow-only device buffer
+struct DBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap)
+            return 0;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+            p = nullptr;
+            return -1;
+        }
+        cap = want;
+        return 0;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const
+    {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+template <class T>
+int upload(DBuf &b, const std::vector<T> &v, cudaStream_t st)
+{
+    size_t bytes = v.size() * sizeof(T);
+    if (b.ensure(bytes ? bytes : 16) != 0)
+        return -1;
+    if (bytes)
+        SSB_CUDA(cudaMemcpyAsync(b.p, v.data(), bytes, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ model
+struct ssb_model_s {
+    HostModel h;
+    DevModel d;
+    int device = -1;
+    std::vector<void *> owned;
+    int sm_count = 0;
+};
+
+extern "C" int ssb_version(void) { return 100; }
+extern "C" const char *ssb_last_error(void) { return ssb::last_error(); }
+
+extern "C" int ssb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess
+            && major == 10)
+            ++ok;
+    }
+    return ok;
+}
+
+extern "C" void ssb_config_defaults(ssb_config_t *c)
+{
+    // ref: include/soundswallower/config_defs.h:78-257
+    c->logbase = 1.0001;
+    c->varfloor = 1e-4f;
+    c->mixwfloor = 1e-7;
+    c->tmatfloor = 1e-4;
+    c->topn = 4;
+    c->ds = 1;
+    c->device = 0;
+}
+
+template <class T>
+static const T *to_device(ssb_model_s *m, const std::vector<T> &v)
+{
+    void *p = nullptr;
+    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    if (cudaMalloc(&p, bytes) != cudaSuccess
+        || cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("model upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (p)
+            cudaFree(p);
+        return nullptr;
+    }
+    m->owned.push_back(p);
+    return reinterpret_cast<const T *>(p);
+}
+
+static int model_to_device(ssb_model_s *m)
+{
+    const HostModel &h = m->h;
+    DevModel &d = m->d;
+    int dev_major = 0;
+    API_CUDA(cudaSetDevice(m->device), -1);
+    API_CUDA(cudaDeviceGetAttribute(&dev_major, cudaDevAttrComputeCapabilityMajor, m->device), -1);
+    if (dev_major != 10) {
+        set_error("device %d has compute capability %d.x; libssb200 carries sm_100a code only",
+                  m->device, dev_major);
+        return -1;
+    }
+    API_CUDA(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device), -1);
+    std::memset(&d, 0, sizeof(d));
+    d.n_mgau = h.n_mgau;
+    d.n_feat = h.n_feat;
+    d.n_density = h.n_density;
+    d.n_sen = h.n_sen;
+    d.n_emit = h.n_emit;
+    d.n_tmat = h.n_tmat;
+    d.n_sseq = h.n_sseq;
+    d.blk = h.blk;
+    d.topn = h.cfg.topn;
+    d.ds = h.cfg.ds;
+    // packed Gaussian records: [det, mean[L], prec[L], 0-pad], codebook-major
+    int64_t off = 0;
+    for (int f = 0; f < h.n_feat; ++f) {
+        d.featlen[f] = h.featlen[f];
+        d.featoff[f] = h.featoff[f];
+        d.rec_len[f] = (1 + 2 * h.featlen[f] + 3) & ~3;
+        d.gau_base[f] = off;
+        off += (int64_t)h.n_density * d.rec_len[f];
+    }
+    d.gau_cb_stride = off;
+    std::vector<float> gau((size_t)off * h.n_mgau, 0.f);
+    for (int c = 0; c < h.n_mgau; ++c)
+        for (int f = 0; f < h.n_feat; ++f) {
+            const int L = h.featlen[f], RL = d.rec_len[f];
+            const float *mu = h.mean.data() + h.gau_off[c * h.n_feat + f];
+            const float *pv = h.var.data() + h.gau_off[c * h.n_feat + f];
+            const float *dt = h.det.data() + (size_t)(c * h.n_feat + f) * h.n_density;
+            float *dst = gau.data() + d.gau_base[f] + (int64_t)c * d.gau_cb_stride;
+            for (int k = 0; k < h.n_density; ++k) {
+                float *r = dst + (size_t)k * RL;
+                r[0] = dt[k];
+                for (int i = 0; i < L; ++i) {
+                    r[1 + i] = mu[k * L + i];
+                    r[1 + L + i] = pv[k * L + i];
+                }
+            }
+        }
+    // senones grouped by codebook
+    std::vector<int32_t> cb_off(h.n_mgau + 1, 0);
+    std::vector<uint16_t> cb_sen(h.n_sen);
+    for (int s = 0; s < h.n_sen; ++s)
+        cb_off[h.sen2cb[s] + 1]++;
+    int max_cb = 0;
+    for (int c = 0; c < h.n_mgau; ++c) {
+        max_cb = std::max(max_cb, cb_off[c + 1]);
+        cb_off[c + 1] += cb_off[c];
+    }
+    {
+        std::vector<int32_t> at(cb_off.begin(), cb_off.end() - 1);
+        for (int s = 0; s < h.n_sen; ++s)
+            cb_sen[at[h.sen2cb[s]]++] = (uint16_t)s;
+    }
+    d.max_cb_sen = max_cb;
+    std::vector<uint8_t> lut(h.lut8, h.lut8 + 256);
+    if (!(d.gau = to_device(m, gau)) || !(d.mixw = to_device(m, h.mixw))
+        || !(d.sen2cb = to_device(m, h.sen2cb)) || !(d.sseq = to_device(m, h.sseq))
+        || !(d.tp = to_device(m, h.tp)) || !(d.lut8 = to_device(m, lut))
+        || !(d.cb_sen_off = to_device(m, cb_off)) || !(d.cb_sen = to_device(m, cb_sen)))
+        return -1;
+    return 0;
+}
+
+extern "C" ssb_model_t *ssb_model_load(const char *hmmdir, const ssb_config_t *cfg)
+{
+    ssb_config_t c;
+    if (cfg)
+        c = *cfg;
+    else
+        ssb_config_defaults(&c);
+    if (c.topn < 1 || c.topn > SSB_MAX_TOPN) {
+        set_error("topn %d out of range 1..%d", c.topn, SSB_MAX_TOPN);
+        return nullptr;
+    }
+    if (c.ds < 1)
+        c.ds = 1;
+    std::unique_ptr<ssb_model_s> m(new ssb_model_s);
+    if (!m->h.load(hmmdir ? hmmdir : "", c))
+        return nullptr;
+    if (m->h.n_sen > 65535) {
+        set_error("%d senones exceed the 16-bit senone ids of the chain planner", m->h.n_sen);
+        return nullptr;
+    }
+    m->device = c.device;
+    if (c.device >= 0 && model_to_device(m.get()) != 0) {
+        for (void *p : m->owned)
+            cudaFree(p);
+        return nullptr;
+    }
+    return m.release();
+}
+
+extern "C" void ssb_model_free(ssb_model_t *m)
+{
+    if (!m)
+        return;
+    if (m->device >= 0)
+        cudaSetDevice(m->device);
+    for (void *p : m->owned)
+        cudaFree(p);
+    delete m;
+}
+
+extern "C" int ssb_model_dims(const ssb_model_t *m, int32_t *o)
+{
+    if (!m || !o)
+        return -1;
+    const HostModel &h = m->h;
+    int32_t v[16] = {h.n_mgau, h.n_feat, h.n_density, h.featlen[0], h.n_sen, h.n_sseq,
+                     h.n_emit, h.n_tmat, h.n_ciphone, h.n_phone, h.sil,
+                     h.featlen[0], h.featlen[1], h.featlen[2], h.featlen[3], h.blk};
+    std::memcpy(o, v, sizeof(v));
+    return 0;
+}
+
+extern "C" int ssb_model_copy(const ssb_model_t *m, float *mean, float *var, float *det,
+                              uint8_t *mixw, uint8_t *sen2cb, uint8_t *tp, uint16_t *sseq,
+                              uint8_t *lut8)
+{
+    if (!m)
+        return -1;
+    const HostModel &h = m->h;
+    if (mean)
+        std::memcpy(mean, h.mean.data(), h.mean.size() * 4);
+    if (var)
+        std::memcpy(var, h.var.data(), h.var.size() * 4);
+    if (det)
+        std::memcpy(det, h.det.data(), h.det.size() * 4);
+    if (mixw)
+        std::memcpy(mixw, h.mixw.data(), h.mixw.size());
+    if (sen2cb)
+        std::memcpy(sen2cb, h.sen2cb.data(), h.sen2cb.size());
+    if (tp)
+        std::memcpy(tp, h.tp.data(), h.tp.size());
+    if (sseq)
+        std::memcpy(sseq, h.sseq.data(), h.sseq.size() * 2);
+    if (lut8)
+        std::memcpy(lut8, h.lut8, 256);
+    return 0;
+}
+
+extern "C" int ssb_model_phones(const ssb_model_t *m, int32_t *ssid, int32_t *tmat, int32_t *ci)
+{
+    if (!m)
+        return -1;
+    const HostModel &h = m->h;
+    if (ssid)
+        std::memcpy(ssid, h.ph_ssid.data(), h.ph_ssid.size() * 4);
+    if (tmat)
+        std::memcpy(tmat, h.ph_tmat.data(), h.ph_tmat.size() * 4);
+    if (ci)
+        std::memcpy(ci, h.ph_ci.data(), h.ph_ci.size() * 4);
+    return 0;
+}
+
+static int need_device(const ssb_model_t *m)
+{
+    if (!m) {
+        set_error("NULL model");
+        return -1;
+    }
+    if (m->device < 0) {
+        set_error("model was loaded with device = -1 (host tables only); "
+                  "libssb200 has no CPU compute path");
+        return -1;
+    }
+    API_CUDA(cudaSetDevice(m->device), -1);
+    return 0;
+}
+
+// ------------------------------------------------------------------ active list decoding
+// ref: src/acmod.c:947-999 -- the list is uint8 deltas; a gap above 255 is bridged with
+// entries of 255 which make the scorer evaluate those in-between senones too.
+static void decode_active(const uint8_t *list, int n, std::vector<uint16_t> &out)
+{
+    out.clear();
+    int last = 0;
+    for (int i = 0; i < n; ++i) {
+        last += list[i];
+        out.push_back((uint16_t)last);
+    }
+}
+
+// senone ids the scorer evaluates for a flagged set (ascending `flags`), bridging included
+static void flags_to_eval_list(const std::vector<uint8_t> &flag, int n_sen,
+                               std::vector<uint16_t> &out)
+{
+    out.clear();
+    int last = 0;
+    for (int s = 0; s < n_sen; ++s) {
+        if (!flag[s])
+            continue;
+        int delta = s - last;
+        while (delta > 255) {
+            last += 255;
+            delta -= 255;
+            out.push_back((uint16_t)last);
+        }
+        out.push_back((uint16_t)s);
+        last = s;
+    }
+}
+
+// ------------------------------------------------------------------ mgau drop-in
+struct ssb_mgau_impl {
+    ssb_mgau_t base;  // must be first: {vt, frame_idx}
+    ssb_model_t *m;
+    FrameHist hist;
+    DBuf hs[2], hc[2], ha[2], x, senscr, act;
+    float *h_x = nullptr;
+    int16_t *h_senscr = nullptr;
+    uint16_t *h_act = nullptr;
+    uint8_t *h_cb = nullptr;
+    cudaStream_t st = nullptr;
+    std::vector<uint16_t> tmp;
+};
+
+static int mgau_frame_eval_vt(ssb_mgau_t *g, int16_t *senscr, uint8_t *act, int32_t n_act,
+                              float **feat, int32_t frame, int32_t compallsen)
+{
+    return ssb_mgau_frame_eval(g, senscr, act, n_act, feat, frame, compallsen);
+}
+static int mgau_transform_vt(ssb_mgau_t *, void *)
+{
+    // ref: src/ptm_mgau.c:818-825 (MLLR re-estimates means/variances); out of scope
+    set_error("MLLR transform is not supported by the B200 scorer");
+    return -1;
+}
+static void mgau_free_vt(ssb_mgau_t *g) { ssb_mgau_free(g); }
+static ssb_mgaufuncs_t g_mgau_funcs = {"ptm", mgau_frame_eval_vt, mgau_transform_vt, mgau_free_vt};
+
+static int mgau_reset_device(ssb_mgau_impl *g)
+{
+    const HostModel &h = g->m->h;
+    const int CS = h.n_mgau * h.n_feat;
+    std::vector<int4> s(CS, make_int4(INT32_MIN, INT32_MIN, INT32_MIN, INT32_MIN));
+    std::vector<uchar4> c(CS, make_uchar4(0, 1, 2, 3));
+    std::vector<uint8_t> a(h.n_mgau, 1);
+    for (int i = 0; i < 2; ++i) {
+        API_CUDA(cudaMemcpyAsync(g->hs[i].p, s.data(), CS * sizeof(int4), cudaMemcpyHostToDevice, g->st), -1);
+        API_CUDA(cudaMemcpyAsync(g->hc[i].p, c.data(), CS * sizeof(uchar4), cudaMemcpyHostToDevice, g->st), -1);
+        API_CUDA(cudaMemcpyAsync(g->ha[i].p, a.data(), h.n_mgau, cudaMemcpyHostToDevice, g->st), -1);
+    }
+    API_CUDA(cudaStreamSynchronize(g->st), -1);
+    return 0;
+}
+
+extern "C" ssb_mgau_t *ssb_mgau_init(ssb_model_t *m)
+{
+    if (need_device(m) != 0)
+        return nullptr;
+    const HostModel &h = m->h;
+    const int CS = h.n_mgau * h.n_feat;
+    ssb_mgau_impl *g = new ssb_mgau_impl;
+    g->base.vt = &g_mgau_funcs;
+    g->base.frame_idx = 0;
+    g->m = m;
+    bool ok = cudaStreamCreateWithFlags(&g->st, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i) {
+        ok = g->hs[i].ensure(CS * sizeof(int4)) == 0 && g->hc[i].ensure(CS * sizeof(uchar4)) == 0
+             && g->ha[i].ensure(h.n_mgau) == 0;
+        g->hist.score[i] = g->hs[i].as<int4>();
+        g->hist.cw[i] = g->hc[i].as<uchar4>();
+        g->hist.act[i] = g->ha[i].as<uint8_t>();
+    }
+    ok = ok && g->x.ensure(h.blk * sizeof(float)) == 0 && g->senscr.ensure(h.n_sen * 2) == 0
+         && g->act.ensure((size_t)h.n_sen * 2 + 16) == 0;
+    ok = ok && cudaMallocHost((void **)&g->h_x, h.blk * sizeof(float)) == cudaSuccess
+         && cudaMallocHost((void **)&g->h_senscr, h.n_sen * 2) == cudaSuccess
+         && cudaMallocHost((void **)&g->h_act, (size_t)h.n_sen * 2 + 16) == cudaSuccess
+         && cudaMallocHost((void **)&g->h_cb, h.n_mgau) == cudaSuccess;
+    if (!ok || mgau_reset_device(g) != 0) {
+        if (ok)
+            ;
+        else
+            set_error("ssb_mgau_init: device allocation failed: %s",
+                      cudaGetErrorString(cudaGetLastError()));
+        ssb_mgau_free(&g->base);
+        return nullptr;
+    }
+    return &g->base;
+}
+
+extern "C" void ssb_mgau_reset(ssb_mgau_t *gg)
+{
+    ssb_mgau_impl *g = reinterpret_cast<ssb_mgau_impl *>(gg);
+    if (!g)
+        return;
+    cudaSetDevice(g->m->device);
+    mgau_reset_device(g);
+    g->base.frame_idx = 0;
+}
+
+extern "C" void ssb_mgau_free(ssb_mgau_t *gg)
+{
+    ssb_mgau_impl *g = reinterpret_cast<ssb_mgau_impl *>(gg);
+    if (!g)
+        return;
+    cudaSetDevice(g->m->device);
+    for (int i = 0; i < 2; ++i) {
+        g->hs[i].release();
+        g->hc[i].release();
+        g->ha[i].release();
+    }
+    g->x.release();
+    g->senscr.release();
+    g->act.release();
+    if (g->h_x)
+        cudaFreeHost(g->h_x);
+    if (g->h_senscr)
+        cudaFreeHost(g->h_senscr);
+    if (g->h_act)
+        cudaFreeHost(g->h_act);
+    if (g->h_cb)
+        cudaFreeHost(g->h_cb);
+    if (g->st)
+        cudaStreamDestroy(g->st);
+    delete g;
+}
+
+extern "C" int ssb_mgau_frame_eval(ssb_mgau_t *gg, int16_t *senscr, uint8_t *senone_active,
+                                   int32_t n_act, float **feat, int32_t frame, int32_t compallsen)
+{
+    ssb_mgau_impl *g = reinterpret_cast<ssb_mgau_impl *>(gg);
+    if (!g || !senscr || !feat || frame < 0) {
+        set_error("ssb_mgau_frame_eval: bad arguments");
+        return -1;
+    }
+    if (need_device(g->m) != 0)
+        return -1;
+    const HostModel &h = g->m->h;
+    const DevModel &d = g->m->d;
+    const int slot = frame % 2, prev = slot ? slot - 1 : 1;
+    int n_list = 0;
+    if (!compallsen) {
+        decode_active(senone_active, n_act, g->tmp);
+        n_list = (int)g->tmp.size();
+        for (int i = 0; i < n_list; ++i) {
+            if (g->tmp[i] >= h.n_sen) {
+                set_error("active senone list runs past n_sen");
+                return -1;
+            }
+            g->h_act[i] = g->tmp[i];
+        }
+        if (n_list)
+            API_CUDA(cudaMemcpyAsync(g->act.p, g->h_act, n_list * 2, cudaMemcpyHostToDevice, g->st), -1);
+    }
+    const bool fresh = frame >= g->base.frame_idx;
+    if (fresh) {
+        // ptm_mgau_calc_cb_active (ref: src/ptm_mgau.c:297-321)
+        if (compallsen)
+            std::memset(g->h_cb, 1, h.n_mgau);
+        else {
+            std::memset(g->h_cb, 0, h.n_mgau);
+            for (int i = 0; i < n_list; ++i)
+                g->h_cb[h.sen2cb[g->tmp[i]]] = 1;
+        }
+        for (int f = 0; f < h.n_feat; ++f)
+            std::memcpy(g->h_x + h.featoff[f], feat[f], h.featlen[f] * sizeof(float));
+        API_CUDA(cudaMemcpyAsync(g->hist.act[slot], g->h_cb, h.n_mgau, cudaMemcpyHostToDevice, g->st), -1);
+        API_CUDA(cudaMemcpyAsync(g->x.p, g->h_x, h.blk * sizeof(float), cudaMemcpyHostToDevice, g->st), -1);
+        if (launch_frame_topn(d, g->hist, slot, prev, g->x.as<float>(), frame % h.cfg.ds == 0, g->st) != 0)
+            return -1;
+    }
+    if (launch_frame_senones(d, g->hist, slot, fresh ? 1 : 0, g->act.as<uint16_t>(), n_list,
+                             compallsen, g->senscr.as<int16_t>(), g->st) != 0)
+        return -1;
+    API_CUDA(cudaMemcpyAsync(g->h_senscr, g->senscr.p, h.n_sen * 2, cudaMemcpyDeviceToHost, g->st), -1);
+    API_CUDA(cudaStreamSynchronize(g->st), -1);
+    std::memcpy(senscr, g->h_senscr, h.n_sen * 2);
+    return 0;
+}
+
+// ------------------------------------------------------------------ batch
+struct ssb_batch_s {
+    ssb_model_t *m = nullptr;
+    cudaStream_t st = nullptr;
+    // plan (host)
+    int n_utts = 0;
+    int64_t n_frames = 0, n_phones = 0, n_states = 0, n_state_frames = 0;
+    int64_t n_active_sen_frames = 0, n_scanned_cb_frames = 0;
+    int max_phones = 0, max_union = 0, max_T = 0;
+    int compallsen = 0;
+    bool want_tokens_all = false;
+    std::vector<int64_t> frame_off, phone_off, scr_off;
+    std::vector<int32_t> enter;
+    // device
+    DBuf feat, tn_s, tn_c, chain_scr, tokens, spill;
+    DBuf d_frame_off, d_phone_off, d_scr_off, d_ssid, d_tmat, d_sf, d_ef, d_ep_off, d_ep_start,
+        d_ep_cbmask, d_ep_slot_off, d_ep_slot, d_us_off, d_usen, d_st_slot, d_enter;
+    DBuf st_start, st_dur, st_score, utt_rv, utt_best, utt_renorm, fin_hist, fin_score;
+    DBuf dense, best_tmp;
+    DevPlan plan;
+    int64_t spill_stride = 0;
+    // timing
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int n_launches = 0;
+    bool ran = false;
+    size_t bytes_held() const
+    {
+        const DBuf *all[] = {&feat, &tn_s, &tn_c, &chain_scr, &tokens, &spill, &d_frame_off,
+                             &d_phone_off, &d_scr_off, &d_ssid, &d_tmat, &d_sf, &d_ef, &d_ep_off,
+                             &d_ep_start, &d_ep_cbmask, &d_ep_slot_off, &d_ep_slot, &d_us_off,
+                             &d_usen, &d_st_slot, &d_enter, &st_start, &st_dur, &st_score, &utt_rv,
+                             &utt_best, &utt_renorm, &fin_hist, &fin_score, &dense, &best_tmp};
+        size_t n = 0;
+        for (const DBuf *b : all)
+            n += b->cap;
+        return n;
+    }
+    void release_all()
+    {
+        DBuf *all[] = {&feat, &tn_s, &tn_c, &chain_scr, &tokens, &spill, &d_frame_off,
+                       &d_phone_off, &d_scr_off, &d_ssid, &d_tmat, &d_sf, &d_ef, &d_ep_off,
+                       &d_ep_start, &d_ep_cbmask, &d_ep_slot_off, &d_ep_slot, &d_us_off, &d_usen,
+                       &d_st_slot, &d_enter, &st_start, &st_dur, &st_score, &utt_rv, &utt_best,
+                       &utt_renorm, &fin_hist, &fin_score, &dense, &best_tmp};
+        for (DBuf *b : all)
+            b->release();
+    }
+};
+
+extern "C" ssb_batch_t *ssb_batch_create(ssb_model_t *m, void *stream)
+{
+    if (need_device(m) != 0)
+        return nullptr;
+    ssb_batch_s *b = new ssb_batch_s;
+    b->m = m;
+    b->st = reinterpret_cast<cudaStream_t>(stream);
+    for (auto &e : b->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) {
+            set_error("cudaEventCreate failed");
+            ssb_batch_free(b);
+            return nullptr;
+        }
+    return b;
+}
+
+extern "C" void ssb_batch_free(ssb_batch_t *b)
+{
+    if (!b)
+        return;
+    cudaSetDevice(b->m->device);
+    cudaStreamSynchronize(b->st);
+    b->release_all();
+    for (auto &e : b->ev)
+        if (e)
+            cudaEventDestroy(e);
+    delete b;
+}
+
+// Data-independent schedule of one chain (see chain_viterbi.cu header):
+//   enter[0] = 0;  enter[i] = max(enter[i-1], sf[i], 1) if that is <= max(enter[i-1], ef[i-1])
+//   and <= T, else the phone (and every later one) is never entered (-1).
+static void plan_enter(int np, int T, const int32_t *sf, const int32_t *ef, int32_t *enter)
+{
+    for (int i = 0; i < np; ++i)
+        enter[i] = -1;
+    if (np == 0 || T == 0)
+        return;
+    enter[0] = 0;
+    for (int i = 1; i < np; ++i) {
+        // transitions happen at the end of a step, so the earliest entry frame is 1
+        int32_t e = std::max<int32_t>(std::max(enter[i - 1], sf[i]), 1);
+        int32_t last_prev = std::min<int32_t>(std::max(enter[i - 1], ef[i - 1]), T);
+        if (e > last_prev)
+            break;
+        enter[i] = e;
+    }
+}
+
+extern "C" int ssb_plan_chain(int32_t np, int32_t T, const int32_t *sf, const int32_t *ef,
+                              int32_t *enter)
+{
+    if (np < 0 || T < 0 || (np > 0 && (!sf || !ef || !enter))) {
+        set_error("ssb_plan_chain: bad arguments");
+        return -1;
+    }
+    for (int i = 1; i < np; ++i)
+        if (ef[i] < ef[i - 1]) {
+            set_error("phone %d: window ends must not decrease along the chain", i);
+            return -1;
+        }
+    plan_enter(np, T, sf, ef, enter);
+    return 0;
+}
+
+extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
+{
+    if (!b || !in || in->n_utts < 0 || (in->n_utts > 0 && (!in->frame_off || !in->phone_off))) {
+        set_error("ssb_batch_upload: bad arguments");
+        return -1;
+    }
+    if (need_device(b->m) != 0)
+        return -1;
+    const HostModel &h = b->m->h;
+    const int U = in->n_utts, E = h.n_emit, n_sen = h.n_sen;
+    const int nw = (n_sen + 31) / 32;
+    b->ran = false;
+    b->n_utts = U;
+    b->compallsen = in->compallsen ? 1 : 0;
+    if (U == 0) {
+        b->frame_off.assign(1, 0);
+        b->phone_off.assign(1, 0);
+    } else {
+        b->frame_off.assign(in->frame_off, in->frame_off + U + 1);
+        b->phone_off.assign(in->phone_off, in->phone_off + U + 1);
+    }
+    b->n_frames = b->frame_off[U] - b->frame_off[0];
+    b->n_phones = b->phone_off[U] - b->phone_off[0];
+    if (b->frame_off[0] != 0 || b->phone_off[0] != 0) {
+        set_error("frame_off[0] and phone_off[0] must be 0");
+        return -1;
+    }
+    b->n_states = b->n_phones * E;
+    b->scr_off.assign(U + 1, 0);
+    b->enter.assign((size_t)b->n_phones, -1);
+    b->max_phones = b->max_union = b->max_T = 0;
+    b->n_active_sen_frames = b->n_scanned_cb_frames = 0;
+
+    std::vector<int32_t> ep_off(U + 1, 0), ep_start, ep_slot_off(1, 0), us_off(U + 1, 0);
+    std::vector<uint32_t> ep_cbmask;
+    std::vector<uint16_t> ep_slot, usen, st_slot((size_t)b->n_states, 0);
+    std::vector<uint8_t> flag(n_sen), in_union(n_sen);
+    std::vector<uint16_t> list, slot_of(n_sen);
+    std::vector<std::pair<int32_t, int>> order;  // (enter frame, phone)
+    struct Ep {
+        int32_t start;
+        std::vector<uint16_t> sen;
+        uint32_t mask[8];
+    };
+    std::vector<Ep> eps;
+
+    for (int u = 0; u < U; ++u) {
+        const int64_t f0 = b->frame_off[u], p0 = b->phone_off[u];
+        const int64_t Tl = b->frame_off[u + 1] - f0, npl = b->phone_off[u + 1] - p0;
+        if (Tl < 0 || npl < 0 || Tl > INT32_MAX - 2 || npl * E > 0x7fffffff) {
+            set_error("utterance %d: offsets must be non-decreasing", u);
+            return -1;
+        }
+        const int T = (int)Tl, np = (int)npl;
+        b->max_phones = std::max(b->max_phones, np);
+        b->max_T = std::max(b->max_T, T);
+        b->scr_off[u + 1] = b->scr_off[u] + (int64_t)T * np * E;
+        const int32_t *ssid = in->ssid + p0, *tmat = in->tmat + p0, *sf = in->sf + p0,
+                      *ef = in->ef + p0;
+        for (int i = 0; i < np; ++i) {
+            if (ssid[i] < 0 || ssid[i] >= h.n_sseq || tmat[i] < 0 || tmat[i] >= h.n_tmat) {
+                set_error("utterance %d phone %d: ssid %d / tmat %d out of range", u, i, ssid[i],
+                          tmat[i]);
+                return -1;
+            }
+            if (i > 0 && ef[i] < ef[i - 1]) {
+                // the reference's own windows never decrease (phones inherit word windows,
+                // ref: src/ps_alignment.c:168-305); a decreasing one would make HMM activity
+                // depend on scores, which the planned schedule cannot express
+                set_error("utterance %d phone %d: window ends must not decrease along the chain",
+                          u, i);
+                return -1;
+            }
+        }
+        int32_t *enter = b->enter.data() + p0;
+        plan_enter(np, T, sf, ef, enter);
+        us_off[u + 1] = us_off[u];
+        ep_off[u + 1] = ep_off[u];
+        if (b->compallsen) {
+            b->n_active_sen_frames += (int64_t)T * n_sen;
+            b->n_scanned_cb_frames += (int64_t)T * h.n_mgau;
+            for (int i = 0; i < np * E; ++i)
+                st_slot[p0 * E + i] = 0;
+            continue;
+        }
+        // epochs: the active senone set only grows (ref: src/state_align_search.c:186-188)
+        std::fill(flag.begin(), flag.end(), 0);
+        std::fill(in_union.begin(), in_union.end(), 0);
+        if (in->init_active) {
+            const uint32_t *bits = in->init_active + (size_t)u * nw;
+            for (int s = 0; s < n_sen; ++s)
+                flag[s] = (bits[s >> 5] >> (s & 31)) & 1u;
+        }
+        order.clear();
+        for (int i = 0; i < np; ++i)
+            if (enter[i] >= 0 && enter[i] < T)
+                order.emplace_back(enter[i], i);
+        std::stable_sort(order.begin(), order.end());
+        eps.clear();
+        size_t k = 0;
+        while (k < order.size()) {
+            const int32_t start = order[k].first;
+            bool grew = eps.empty();
+            for (; k < order.size() && order[k].first == start; ++k) {
+                const int i = order[k].second;
+                for (int j = 0; j < E; ++j) {
+                    int s = h.sseq[(size_t)ssid[i] * E + j];
+                    if (s >= n_sen) {
+                        set_error("utterance %d phone %d: senone id %d out of range", u, i, s);
+                        return -1;
+                    }
+                    if (!flag[s]) {
+                        flag[s] = 1;
+                        grew = true;
+                    }
+                }
+            }
+            if (!grew)
+                continue;
+            Ep e;
+            e.start = start;
+            flags_to_eval_list(flag, n_sen, e.sen);
+            std::memset(e.mask, 0, sizeof(e.mask));
+            for (uint16_t s : e.sen) {
+                int cb = h.sen2cb[s];
+                e.mask[cb >> 5] |= 1u << (cb & 31);
+                in_union[s] = 1;
+            }
+            eps.push_back(std::move(e));
+        }
+        // union of everything ever evaluated for this utterance -> slots
+        int n_us = 0;
+        for (int s = 0; s < n_sen; ++s)
+            if (in_union[s]) {
+                slot_of[s] = (uint16_t)n_us++;
+                usen.push_back((uint16_t)s);
+            }
+        us_off[u + 1] = us_off[u] + n_us;
+        b->max_union = std::max(b->max_union, n_us);
+        for (size_t e = 0; e < eps.size(); ++e) {
+            ep_start.push_back(eps[e].start);
+            for (int w = 0; w < 8; ++w)
+                ep_cbmask.push_back(eps[e].mask[w]);
+            for (uint16_t s : eps[e].sen)
+                ep_slot.push_back(slot_of[s]);
+            ep_slot_off.push_back((int32_t)ep_slot.size());
+            const int32_t end = e + 1 < eps.size() ? eps[e + 1].start : T;
+            int ncb = 0;
+            for (int w = 0; w < 8; ++w)
+                ncb += __builtin_popcount(eps[e].mask[w]);
+            b->n_active_sen_frames += (int64_t)(end - eps[e].start) * eps[e].sen.size();
+            b->n_scanned_cb_frames += (int64_t)(end - eps[e].start) * ncb;
+        }
+        ep_off[u + 1] = ep_off[u] + (int32_t)eps.size();
+        // chain state -> union slot; states whose phone never becomes active read the
+        // always-zero slot n_us (the reference leaves such senone scores at 0 - best)
+        for (int i = 0; i < np; ++i)
+            for (int j = 0; j < E; ++j) {
+                int s = h.sseq[(size_t)ssid[i] * E + j];
+                st_slot[(p0 + i) * E + j] = in_union[s] ? slot_of[s] : (uint16_t)n_us;
+            }
+        if (ep_slot.size() > (size_t)INT32_MAX - 65536) {
+            set_error("active-list plan too large; split the batch");
+            return -1;
+        }
+    }
+    b->n_state_frames = b->scr_off[U];
+
+    // ---- device buffers
+    cudaStream_t st = b->st;
+    const int CS = h.n_mgau * h.n_feat;
+    const int64_t G = b->n_frames;
+    if (b->feat.ensure(std::max<size_t>((size_t)G * h.blk * sizeof(float), 16)) != 0
+        || b->tn_s.ensure(std::max<size_t>((size_t)G * CS * sizeof(int4), 16)) != 0
+        || b->tn_c.ensure(std::max<size_t>((size_t)G * CS * sizeof(uchar4), 16)) != 0
+        || b->chain_scr.ensure(std::max<size_t>((size_t)b->n_state_frames * 2, 16)) != 0
+        || b->tokens.ensure(std::max<size_t>((size_t)b->n_state_frames * sizeof(int2), 16)) != 0
+        || b->st_start.ensure(std::max<size_t>((size_t)b->n_states * 4, 16)) != 0
+        || b->st_dur.ensure(std::max<size_t>((size_t)b->n_states * 4, 16)) != 0
+        || b->st_score.ensure(std::max<size_t>((size_t)b->n_states * 4, 16)) != 0
+        || b->utt_rv.ensure(std::max<size_t>((size_t)U * 4, 16)) != 0
+        || b->utt_best.ensure(std::max<size_t>((size_t)U * 4, 16)) != 0
+        || b->utt_renorm.ensure(std::max<size_t>((size_t)U * 4, 16)) != 0
+        || b->fin_hist.ensure(std::max<size_t>((size_t)U * 4, 16)) != 0
+        || b->fin_score.ensure(std::max<size_t>((size_t)U * 4, 16)) != 0)
+        return -1;
+    // chains too long for shared memory keep their HMM state in HBM/L2
+    {
+        const size_t per_phone = (size_t)(2 * E + 2) * 4;
+        const int cap = (int)((200 * 1024) / per_phone);
+        b->spill_stride = 0;
+        if (b->max_phones > cap) {
+            b->spill_stride = (int64_t)b->max_phones * (2 * E + 2);
+            if (b->spill.ensure((size_t)b->spill_stride * 4 * U) != 0)
+                return -1;
+        }
+    }
+    if (G > 0 && in->feat)
+        API_CUDA(cudaMemcpyAsync(b->feat.p, in->feat, (size_t)G * h.blk * sizeof(float),
+                                 cudaMemcpyHostToDevice, st), -1);
+    else if (G > 0) {
+        set_error("ssb_batch_upload: feat is NULL");
+        return -1;
+    }
+    if (b->n_phones > 0 && (!in->ssid || !in->tmat || !in->sf || !in->ef)) {
+        set_error("ssb_batch_upload: chain arrays are NULL");
+        return -1;
+    }
+    std::vector<int32_t> v_ssid(in->ssid, in->ssid + b->n_phones),
+        v_tmat(in->tmat, in->tmat + b->n_phones), v_sf(in->sf, in->sf + b->n_phones),
+        v_ef(in->ef, in->ef + b->n_phones);
+    if (upload(b->d_frame_off, b->frame_off, st) || upload(b->d_phone_off, b->phone_off, st)
+        || upload(b->d_scr_off, b->scr_off, st) || upload(b->d_ssid, v_ssid, st)
+        || upload(b->d_tmat, v_tmat, st) || upload(b->d_sf, v_sf, st) || upload(b->d_ef, v_ef, st)
+        || upload(b->d_ep_off, ep_off, st) || upload(b->d_ep_start, ep_start, st)
+        || upload(b->d_ep_cbmask, ep_cbmask, st) || upload(b->d_ep_slot_off, ep_slot_off, st)
+        || upload(b->d_ep_slot, ep_slot, st) || upload(b->d_us_off, us_off, st)
+        || upload(b->d_usen, usen, st) || upload(b->d_st_slot, st_slot, st)
+        || upload(b->d_enter, b->enter, st))
+        return -1;
+    // the host vectors above die at return: make sure the copies have been staged
+    API_CUDA(cudaStreamSynchronize(st), -1);
+    DevPlan &p = b->plan;
+    p.n_utts = U;
+    p.frame_off = b->d_frame_off.as<int64_t>();
+    p.phone_off = b->d_phone_off.as<int64_t>();
+    p.scr_off = b->d_scr_off.as<int64_t>();
+    p.ssid = b->d_ssid.as<int32_t>();
+    p.tmat = b->d_tmat.as<int32_t>();
+    p.sf = b->d_sf.as<int32_t>();
+    p.ef = b->d_ef.as<int32_t>();
+    p.ep_off = b->d_ep_off.as<int32_t>();
+    p.ep_start = b->d_ep_start.as<int32_t>();
+    p.ep_cbmask = b->d_ep_cbmask.as<uint32_t>();
+    p.ep_slot_off = b->d_ep_slot_off.as<int32_t>();
+    p.ep_slot = b->d_ep_slot.as<uint16_t>();
+    p.us_off = b->d_us_off.as<int32_t>();
+    p.usen = b->d_usen.as<uint16_t>();
+    p.st_slot = b->d_st_slot.as<uint16_t>();
+    p.enter_plan = b->d_enter.as<int32_t>();
+    p.all_active = b->compallsen;
+    return 0;
+}
+
+// frames per dense slab in compallsen mode (whole utterances)
+static const int64_t kSlabFrames = 32768;
+
+extern "C" int ssb_batch_run(ssb_batch_t *b)
+{
+    if (!b) {
+        set_error("NULL batch");
+        return -1;
+    }
+    if (need_device(b->m) != 0)
+        return -1;
+    const DevModel &d = b->m->d;
+    const DevPlan &p = b->plan;
+    cudaStream_t st = b->st;
+    const int U = b->n_utts;
+    b->n_launches = 0;
+    API_CUDA(cudaEventRecord(b->ev[0], st), -1);
+    if (U > 0 && b->n_frames > 0) {
+        if (launch_gmm_topn(d, p, b->feat.as<float>(), b->n_frames, b->tn_s.as<int4>(),
+                            b->tn_c.as<uchar4>(), st) != 0)
+            return -1;
+        b->n_launches++;
+    }
+    API_CUDA(cudaEventRecord(b->ev[1], st), -1);
+    if (U > 0 && b->n_frames > 0 && b->n_states > 0) {
+        if (!b->compallsen) {
+            if (launch_senone_mix_active(d, p, b->tn_s.as<int4>(), b->tn_c.as<uchar4>(),
+                                         b->n_frames, b->max_union + 1, b->max_T,
+                                         b->chain_scr.as<int16_t>(), st) != 0)
+                return -1;
+            b->n_launches++;
+        } else {
+            int u0 = 0;
+            while (u0 < U) {
+                int u1 = u0 + 1;
+                while (u1 < U && b->frame_off[u1 + 1] - b->frame_off[u0] <= kSlabFrames)
+                    ++u1;
+                const int64_t g0 = b->frame_off[u0], n = b->frame_off[u1] - g0;
+                if (n > 0) {
+                    if (b->dense.ensure((size_t)n * d.n_sen * 2) != 0
+                        || b->best_tmp.ensure((size_t)n * (1 + SSB_MAX_FEAT) * 4) != 0)
+                        return -1;
+                    if (launch_senone_mix_all(d, b->tn_s.as<int4>(), b->tn_c.as<uchar4>(),
+                                              b->n_frames, g0, n, b->dense.as<int16_t>(),
+                                              b->best_tmp.as<int32_t>(), st) != 0
+                        || launch_gather_chain_best(d, p, b->dense.as<int16_t>(),
+                                                    b->best_tmp.as<int32_t>(), u0, u1, g0,
+                                                    b->chain_scr.as<int16_t>(), st) != 0)
+                        return -1;
+                    b->n_launches += 4;
+                }
+                u0 = u1;
+            }
+        }
+    }
+    API_CUDA(cudaEventRecord(b->ev[2], st), -1);
+    if (U > 0) {
+        if (b->want_tokens_all && b->n_state_frames > 0)
+            API_CUDA(cudaMemsetAsync(b->tokens.p, 0xff, (size_t)b->n_state_frames * sizeof(int2), st), -1);
+        if (launch_chain_viterbi(d, p, b->chain_scr.as<int16_t>(), b->tokens.as<int2>(),
+                                 b->spill.as<int32_t>(), b->spill_stride,
+                                 b->utt_best.as<int32_t>(), b->utt_renorm.as<int32_t>(),
+                                 b->fin_hist.as<int32_t>(), b->fin_score.as<int32_t>(),
+                                 b->max_phones, st) != 0)
+            return -1;
+        b->n_launches++;
+    }
+    API_CUDA(cudaEventRecord(b->ev[3], st), -1);
+    if (U > 0) {
+        // duration -1 marks "state not on the best path"
+        if (b->n_states > 0) {
+            API_CUDA(cudaMemsetAsync(b->st_dur.p, 0xff, (size_t)b->n_states * 4, st), -1);
+            // 0x80808080 marks "score never written" (the first state of an utterance)
+            API_CUDA(cudaMemsetAsync(b->st_score.p, 0x80, (size_t)b->n_states * 4, st), -1);
+        }
+        if (launch_backtrace(d, p, b->tokens.as<int2>(), b->fin_hist.as<int32_t>(),
+                             b->fin_score.as<int32_t>(), b->st_start.as<int32_t>(),
+                             b->st_dur.as<int32_t>(), b->st_score.as<int32_t>(),
+                             b->utt_rv.as<int32_t>(), st) != 0)
+            return -1;
+        b->n_launches++;
+    }
+    API_CUDA(cudaEventRecord(b->ev[4], st), -1);
+    b->ran = true;
+    return 0;
+}
+
+extern "C" int ssb_batch_download(ssb_batch_t *b, ssb_align_out_t *out)
+{
+    if (!b || !out) {
+        set_error("ssb_batch_download: bad arguments");
+        return -1;
+    }
+    if (!b->ran) {
+        set_error("ssb_batch_download: ssb_batch_run has not been called on this upload");
+        return -1;
+    }
+    if (need_device(b->m) != 0)
+        return -1;
+    cudaStream_t st = b->st;
+    const int U = b->n_utts;
+    const size_t ns = (size_t)b->n_states;
+    std::vector<int32_t> s_start, s_dur, s_score;
+    if (ns && (out->st_start || out->st_dur || out->st_score)) {
+        s_start.resize(ns);
+        s_dur.resize(ns);
+        s_score.resize(ns);
+        API_CUDA(cudaMemcpyAsync(s_start.data(), b->st_start.p, ns * 4, cudaMemcpyDeviceToHost, st), -1);
+        API_CUDA(cudaMemcpyAsync(s_dur.data(), b->st_dur.p, ns * 4, cudaMemcpyDeviceToHost, st), -1);
+        API_CUDA(cudaMemcpyAsync(s_score.data(), b->st_score.p, ns * 4, cudaMemcpyDeviceToHost, st), -1);
+    }
+    if (U && out->utt_rv)
+        API_CUDA(cudaMemcpyAsync(out->utt_rv, b->utt_rv.p, (size_t)U * 4, cudaMemcpyDeviceToHost, st), -1);
+    if (U && out->utt_best)
+        API_CUDA(cudaMemcpyAsync(out->utt_best, b->utt_best.p, (size_t)U * 4, cudaMemcpyDeviceToHost, st), -1);
+    if (U && out->utt_renorm)
+        API_CUDA(cudaMemcpyAsync(out->utt_renorm, b->utt_renorm.p, (size_t)U * 4, cudaMemcpyDeviceToHost, st), -1);
+    if (b->n_state_frames && out->chain_scr)
+        API_CUDA(cudaMemcpyAsync(out->chain_scr, b->chain_scr.p, (size_t)b->n_state_frames * 2,
+                                 cudaMemcpyDeviceToHost, st), -1);
+    if (b->n_state_frames && out->tokens) {
+        if (!b->want_tokens_all) {
+            set_error("token stack requested but the batch was not run with debug tokens "
+                      "(call ssb_batch_debug_tokens(b, 1) before ssb_batch_run)");
+            return -1;
+        }
+        API_CUDA(cudaMemcpyAsync(out->tokens, b->tokens.p, (size_t)b->n_state_frames * sizeof(int2),
+                                 cudaMemcpyDeviceToHost, st), -1);
+    }
+    API_CUDA(cudaStreamSynchronize(st), -1);
+    // states off the best path keep the caller's values, like the reference's alignment
+    // entries keep what alignment_populate put there (ref: src/state_align_search.c:236-263)
+    for (size_t i = 0; i < s_dur.size(); ++i) {
+        if (s_dur[i] < 0)
+            continue;
+        if (out->st_start)
+            out->st_start[i] = s_start[i];
+        if (out->st_dur)
+            out->st_dur[i] = s_dur[i];
+        // the first state of an utterance keeps its score (ref :256-261)
+        if (out->st_score && s_score[i] != (int32_t)0x80808080)
+            out->st_score[i] = s_score[i];
+    }
+    return 0;
+}
+
+extern "C" int ssb_batch_debug_tokens(ssb_batch_t *b, int on)
+{
+    if (!b)
+        return -1;
+    b->want_tokens_all = on != 0;
+    return 0;
+}
+
+extern "C" int ssb_batch_kernel_ms(ssb_batch_t *b, float *ms)
+{
+    if (!b || !ms || !b->ran) {
+        set_error("ssb_batch_kernel_ms: no completed run");
+        return -1;
+    }
+    API_CUDA(cudaEventSynchronize(b->ev[4]), -1);
+    for (int i = 0; i < 8; ++i)
+        ms[i] = 0.f;
+    for (int i = 0; i < 4; ++i)
+        API_CUDA(cudaEventElapsedTime(&ms[i], b->ev[i], b->ev[i + 1]), -1);
+    API_CUDA(cudaEventElapsedTime(&ms[4], b->ev[0], b->ev[4]), -1);
+    return 0;
+}
+
+extern "C" int ssb_batch_n_launches(const ssb_batch_t *b) { return b ? b->n_launches : -1; }
+
+extern "C" int ssb_batch_stats(const ssb_batch_t *b, int64_t *o)
+{
+    if (!b || !o)
+        return -1;
+    for (int i = 0; i < 8; ++i)
+        o[i] = 0;
+    o[0] = b->n_frames;
+    o[1] = b->n_state_frames;
+    o[2] = b->n_active_sen_frames;
+    o[3] = b->n_scanned_cb_frames;
+    o[4] = (int64_t)b->bytes_held();
+    o[5] = b->max_union;
+    o[6] = b->max_phones;
+    return 0;
+}
+
+extern "C" int ssb_align_batch(ssb_model_t *m, const ssb_align_in_t *in, ssb_align_out_t *out)
+{
+    ssb_batch_t *b = ssb_batch_create(m, nullptr);
+    if (!b)
+        return -1;
+    if (out && out->tokens)
+        ssb_batch_debug_tokens(b, 1);
+    int rv = ssb_batch_upload(b, in);
+    if (rv == 0)
+        rv = ssb_batch_run(b);
+    if (rv == 0)
+        rv = ssb_batch_download(b, out);
+    ssb_batch_free(b);
+    return rv;
+}
+
+// ------------------------------------------------------------------ dense scoring
+static int score_prepare(ssb_batch_t *b, const float *feat, const int64_t *frame_off, int32_t U)
+{
+    std::vector<int64_t> poff(U + 1, 0);
+    ssb_align_in_t in;
+    std::memset(&in, 0, sizeof(in));
+    in.n_utts = U;
+    in.feat = feat;
+    in.frame_off = frame_off;
+    in.phone_off = poff.data();
+    int32_t dummy = 0;
+    in.ssid = in.tmat = in.sf = in.ef = &dummy;
+    in.compallsen = 1;
+    return ssb_batch_upload(b, &in);
+}
+
+extern "C" int64_t ssb_score_batch(ssb_model_t *m, const float *feat, const int64_t *frame_off,
+                                   int32_t n_utts, int16_t *senscr)
+{
+    ssb_batch_t *b = ssb_batch_create(m, nullptr);
+    if (!b)
+        return -1;
+    int64_t rv = -1;
+    do {
+        if (score_prepare(b, feat, frame_off, n_utts) != 0)
+            break;
+        const DevModel &d = m->d;
+        const int64_t G = b->n_frames;
+        if (G == 0) {
+            rv = 0;
+            break;
+        }
+        if (launch_gmm_topn(d, b->plan, b->feat.as<float>(), G, b->tn_s.as<int4>(),
+                            b->tn_c.as<uchar4>(), b->st) != 0)
+            break;
+        bool ok = true;
+        for (int64_t g0 = 0; g0 < G && ok; g0 += kSlabFrames) {
+            const int64_t n = std::min(kSlabFrames, G - g0);
+            ok = b->dense.ensure((size_t)n * d.n_sen * 2) == 0
+                 && b->best_tmp.ensure((size_t)n * (1 + SSB_MAX_FEAT) * 4) == 0
+                 && launch_senone_mix_all(d, b->tn_s.as<int4>(), b->tn_c.as<uchar4>(), G, g0, n,
+                                          b->dense.as<int16_t>(), b->best_tmp.as<int32_t>(),
+                                          b->st) == 0
+                 && launch_subtract_best(d, b->dense.as<int16_t>(), b->best_tmp.as<int32_t>(), n,
+                                         b->st) == 0;
+            if (ok && senscr
+                && cudaMemcpyAsync(senscr + g0 * d.n_sen, b->dense.p, (size_t)n * d.n_sen * 2,
+                                   cudaMemcpyDeviceToHost, b->st) != cudaSuccess) {
+                set_error("senone score download failed: %s", cudaGetErrorString(cudaGetLastError()));
+                ok = false;
+            }
+        }
+        if (!ok)
+            break;
+        cudaError_t e = cudaStreamSynchronize(b->st);
+        if (e != cudaSuccess) {
+            set_error("ssb_score_batch: %s", cudaGetErrorString(e));
+            break;
+        }
+        rv = G;
+    } while (0);
+    ssb_batch_free(b);
+    return rv;
+}
+
+extern "C" int64_t ssb_topn_batch(ssb_model_t *m, const float *feat, const int64_t *frame_off,
+                                  int32_t n_utts, uint8_t *cw, int32_t *score)
+{
+    ssb_batch_t *b = ssb_batch_create(m, nullptr);
+    if (!b)
+        return -1;
+    int64_t rv = -1;
+    do {
+        if (score_prepare(b, feat, frame_off, n_utts) != 0)
+            break;
+        const DevModel &d = m->d;
+        const int64_t G = b->n_frames;
+        const int CS = d.n_mgau * d.n_feat, N = d.topn;
+        if (G == 0) {
+            rv = 0;
+            break;
+        }
+        if (launch_gmm_topn(d, b->plan, b->feat.as<float>(), G, b->tn_s.as<int4>(),
+                            b->tn_c.as<uchar4>(), b->st) != 0)
+            break;
+        std::vector<int4> hs((size_t)G * CS);
+        std::vector<uchar4> hc((size_t)G * CS);
+        if (cudaMemcpyAsync(hs.data(), b->tn_s.p, hs.size() * sizeof(int4), cudaMemcpyDeviceToHost, b->st) != cudaSuccess
+            || cudaMemcpyAsync(hc.data(), b->tn_c.p, hc.size() * sizeof(uchar4), cudaMemcpyDeviceToHost, b->st) != cudaSuccess
+            || cudaStreamSynchronize(b->st) != cudaSuccess) {
+            set_error("ssb_topn_batch: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        // device layout [cs][frame] -> [frame][cs][topn]
+        for (int64_t g = 0; g < G; ++g)
+            for (int cs = 0; cs < CS; ++cs) {
+                const int4 s = hs[(size_t)cs * G + g];
+                const uchar4 c = hc[(size_t)cs * G + g];
+                const int32_t sv[4] = {s.x, s.y, s.z, s.w};
+                const uint8_t cv[4] = {c.x, c.y, c.z, c.w};
+                for (int k = 0; k < N; ++k) {
+                    if (score)
+                        score[((size_t)g * CS + cs) * N + k] = sv[k];
+                    if (cw)
+                        cw[((size_t)g * CS + cs) * N + k] = cv[k];
+                }
+            }
+        rv = G;
+    } while (0);
+    ssb_batch_free(b);
+    return rv;
+}
+
+extern "C" int ssb_hmm_vit_eval(ssb_model_t *m, int32_t n_emit, int32_t tmatid,
+                                const uint16_t *senid, const int16_t *senscr, int32_t *st12,
+                                int32_t *best)
+{
+    if (need_device(m) != 0)
+        return -1;
+    if (!senid || !senscr || !st12 || tmatid < 0 || tmatid >= m->h.n_tmat
+        || n_emit != m->h.n_emit) {
+        set_error("ssb_hmm_vit_eval: bad arguments (n_emit must equal the model's %d)", m->h.n_emit);
+        return -1;
+    }
+    for (int j = 0; j < n_emit; ++j)
+        if (senid[j] >= m->h.n_sen) {
+            set_error("ssb_hmm_vit_eval: senone id out of range");
+            return -1;
+        }
+    DBuf a, s, t, o;
+    int rv = -1;
+    do {
+        if (a.ensure(16) || s.ensure((size_t)m->h.n_sen * 2) || t.ensure(48) || o.ensure(16))
+            break;
+        if (cudaMemcpy(a.p, senid, n_emit * 2, cudaMemcpyHostToDevice) != cudaSuccess
+            || cudaMemcpy(s.p, senscr, (size_t)m->h.n_sen * 2, cudaMemcpyHostToDevice) != cudaSuccess
+            || cudaMemcpy(t.p, st12, 48, cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("ssb_hmm_vit_eval: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        if (launch_hmm_eval(m->d, n_emit, tmatid, a.as<uint16_t>(), s.as<int16_t>(),
+                            t.as<int32_t>(), o.as<int32_t>(), nullptr) != 0)
+            break;
+        int32_t bb = 0;
+        if (cudaMemcpy(st12, t.p, 48, cudaMemcpyDeviceToHost) != cudaSuccess
+            || cudaMemcpy(&bb, o.p, 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            set_error("ssb_hmm_vit_eval: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        if (best)
+            *best = bb;
+        rv = 0;
+    } while (0);
+    a.release();
+    s.release();
+    t.release();
+    o.release();
+    return rv;
+}

@@ -1,0 +1,521 @@
+// chain_viterbi.cu -- K3: left-to-right chain Viterbi with token stack, and the
+// backtrace that turns the stack into state segmentations.
+//
+// Replaces state_align_search_start/step/finish and their helpers
+// (ref: src/state_align_search.c:46-268) together with hmm_vit_eval_3st_lr /
+// hmm_vit_eval_5st_lr (ref: src/hmm.c:166-304, 482-567), hmm_clear / hmm_enter /
+// hmm_normalize (ref: src/hmm.c:121-161).  Integer max-plus arithmetic only; every
+// tie-break, clamp and "stale" value of the reference is kept.
+//
+// What the reference decides frame by frame with `hmm_frame(hmm)` bookkeeping is
+// data independent when the window ends `ef` do not decrease along the chain (the
+// reference's own case: phones inherit their word's window, ref:
+// src/ps_alignment.c:168-305): phone i is evaluated on frames [enter[i], last[i]]
+// with  enter[i] = max(enter[i-1], sf[i], 1)  and  last[i] = max(enter[i], ef[i]).
+// The host planner computes enter[] once per utterance (api.cu: plan_utterance);
+// the kernel only moves scores.
+//
+// B200 mapping: one CTA per utterance -- a single warp for ordinary sentences, up
+// to 32 warps for book-length chains -- with the whole HMM state (score, history,
+// exit score/history per phone) resident in shared memory.  Only the band of
+// phones that is active on frame t is touched.  HBM traffic per state-frame is
+// one int16 senone score in (pre-gathered, coalesced) and one {history, score}
+// token out (the reference's own 8-byte record, ref: state_align_search.h:61-64).
+#include "device.cuh"
+
+namespace ssb {
+
+constexpr int32_t TMAT_WORST = -255;  // ref: include/soundswallower/hmm.h:86
+
+__device__ __forceinline__ int32_t clampw(int32_t x) { return x < WORST_SCORE ? WORST_SCORE : x; }
+
+// ref: src/hmm.c:482-567.  sc/hi: emitting-state scores/histories; ss: senone scores
+// (non-negative costs); tp: [3][4] uint8 costs.  Returns the HMM's best score.
+__device__ __forceinline__ int32_t hmm_step3(const uint8_t *__restrict__ tp, const int (&ss)[3],
+                                             int32_t (&sc)[3], int32_t (&hi)[3], int32_t &osc,
+                                             int32_t &ohi)
+{
+#define TP(i, j) (-(int32_t)tp[(i) * 4 + (j)])
+    int32_t s2 = sc[2] - ss[2], s1 = sc[1] - ss[1], s0 = sc[0] - ss[0];
+    int32_t t0, t1, t2 = INT32_MIN, best = WORST_SCORE;
+    if (s1 > WORST_SCORE) {
+        int32_t s3;
+        t1 = s2 + TP(2, 3);
+        if (TP(1, 3) > TMAT_WORST)
+            t2 = s1 + TP(1, 3);
+        if (t1 > t2) {
+            s3 = t1;
+            ohi = hi[2];
+        } else {
+            s3 = t2;
+            ohi = hi[1];
+        }
+        s3 = clampw(s3);
+        osc = s3;
+        best = s3;
+    }
+    t0 = s2 + TP(2, 2);
+    t1 = s1 + TP(1, 2);
+    if (TP(0, 2) > TMAT_WORST)
+        t2 = s0 + TP(0, 2);  // otherwise t2 keeps what the exit block left (ref :496,519)
+    if (t0 > t1) {
+        if (t2 > t0) {
+            s2 = t2;
+            hi[2] = hi[0];
+        } else
+            s2 = t0;
+    } else {
+        if (t2 > t1) {
+            s2 = t2;
+            hi[2] = hi[0];
+        } else {
+            s2 = t1;
+            hi[2] = hi[1];
+        }
+    }
+    s2 = clampw(s2);
+    best = max(best, s2);
+    sc[2] = s2;
+    t0 = s1 + TP(1, 1);
+    t1 = s0 + TP(0, 1);
+    if (t0 > t1)
+        s1 = t0;
+    else {
+        s1 = t1;
+        hi[1] = hi[0];
+    }
+    s1 = clampw(s1);
+    best = max(best, s1);
+    sc[1] = s1;
+    s0 = clampw(s0 + TP(0, 0));
+    best = max(best, s0);
+    sc[0] = s0;
+    return best;
+#undef TP
+}
+
+// ref: src/hmm.c:166-304
+__device__ __forceinline__ int32_t hmm_step5(const uint8_t *__restrict__ tp, const int (&ss)[5],
+                                             int32_t (&sc)[5], int32_t (&hi)[5], int32_t &osc,
+                                             int32_t &ohi)
+{
+#define TP(i, j) (-(int32_t)tp[(i) * 6 + (j)])
+    int32_t sv[5], t0, t1, t2, best = WORST_SCORE;
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+        sv[j] = sc[j] - ss[j];
+    if (sv[3] > WORST_SCORE) {
+        int32_t s5;
+        t1 = sv[4] + TP(4, 5);
+        t2 = sv[3] + TP(3, 5);
+        if (t1 > t2) {
+            s5 = t1;
+            ohi = hi[4];
+        } else {
+            s5 = t2;
+            ohi = hi[3];
+        }
+        s5 = clampw(s5);
+        osc = s5;
+        best = s5;
+    }
+    // states 4 and 3 only move when their skip source is alive (ref :191,:218); 2 always
+#pragma unroll
+    for (int j = 4; j >= 2; --j) {
+        if (j > 2 && !(sv[j - 2] > WORST_SCORE))
+            continue;
+        int32_t nv;
+        t0 = sv[j] + TP(j, j);
+        t1 = sv[j - 1] + TP(j - 1, j);
+        t2 = sv[j - 2] + TP(j - 2, j);
+        if (t0 > t1) {
+            if (t2 > t0) {
+                nv = t2;
+                hi[j] = hi[j - 2];
+            } else
+                nv = t0;
+        } else {
+            if (t2 > t1) {
+                nv = t2;
+                hi[j] = hi[j - 2];
+            } else {
+                nv = t1;
+                hi[j] = hi[j - 1];
+            }
+        }
+        nv = clampw(nv);
+        best = max(best, nv);
+        sc[j] = nv;
+    }
+    t0 = sv[1] + TP(1, 1);
+    t1 = sv[0] + TP(0, 1);
+    int32_t s1;
+    if (t0 > t1)
+        s1 = t0;
+    else {
+        s1 = t1;
+        hi[1] = hi[0];
+    }
+    s1 = clampw(s1);
+    best = max(best, s1);
+    sc[1] = s1;
+    int32_t s0 = clampw(sv[0] + TP(0, 0));
+    best = max(best, s0);
+    sc[0] = s0;
+    return best;
+#undef TP
+}
+
+template <int E>
+__device__ __forceinline__ int32_t hmm_step(const uint8_t *tp, const int (&ss)[E],
+                                            int32_t (&sc)[E], int32_t (&hi)[E], int32_t &osc,
+                                            int32_t &ohi)
+{
+    if constexpr (E == 3)
+        return hmm_step3(tp, ss, sc, hi, osc, ohi);
+    else
+        return hmm_step5(tp, ss, sc, hi, osc, ohi);
+}
+
+__device__ __forceinline__ int32_t block_max(int32_t v, int32_t *red, int nwarps)
+{
+    for (int o = 16; o > 0; o >>= 1)
+        v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (nwarps == 1)
+        return v;
+    if ((threadIdx.x & 31) == 0)
+        red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int32_t r = red[0];
+    for (int w = 1; w < nwarps; ++w)
+        r = max(r, red[w]);
+    __syncthreads();
+    return r;
+}
+
+__device__ __forceinline__ void cta_sync(int nwarps)
+{
+    if (nwarps == 1)
+        __syncwarp();
+    else
+        __syncthreads();
+}
+
+// Shared (or, for very long chains, global) state of one utterance's chain:
+//   sc[E][np] hi[E][np] osc[np] ohi[np]
+template <int E>
+__global__ void __launch_bounds__(1024)
+chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_scr,
+                     int2 *__restrict__ tokens, int32_t *__restrict__ spill,
+                     int64_t spill_stride, int32_t *__restrict__ utt_best,
+                     int32_t *__restrict__ utt_renorm, int32_t *__restrict__ fin_hist,
+                     int32_t *__restrict__ fin_score, int smem_phones)
+{
+    extern __shared__ int32_t sh[];
+    __shared__ int32_t red[32];
+    const int u = blockIdx.x;
+    const int nwarps = blockDim.x >> 5;
+    const int64_t g0 = p.frame_off[u];
+    const int T = (int)(p.frame_off[u + 1] - g0);
+    const int64_t ph0 = p.phone_off[u];
+    const int np = (int)(p.phone_off[u + 1] - ph0);
+    const int ns = np * E;
+    if (np == 0) {
+        if (threadIdx.x == 0) {
+            utt_best[u] = 0;
+            utt_renorm[u] = 0;
+            fin_hist[u] = -1;
+            fin_score[u] = WORST_SCORE;
+        }
+        return;
+    }
+    int32_t *st = np <= smem_phones ? sh : spill + (int64_t)u * spill_stride;
+    int32_t *sc = st;                   // [E][np]
+    int32_t *hi = st + (size_t)E * np;  // [E][np]
+    int32_t *osc = hi + (size_t)E * np;
+    int32_t *ohi = osc + np;
+    const int32_t *enter = p.enter_plan + ph0;
+    const int32_t *sf = p.sf + ph0, *ef = p.ef + ph0, *tmat = p.tmat + ph0;
+    const int16_t *scr = chain_scr + p.scr_off[u];
+    int2 *tok = tokens + p.scr_off[u];
+
+    // hmm_clear on every phone, hmm_enter(hmms, 0, 0, 0) (ref: state_align_search.c:46-55)
+    for (int i = threadIdx.x; i < np; i += blockDim.x) {
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            sc[j * np + i] = WORST_SCORE;
+            hi[j * np + i] = -1;
+        }
+        osc[i] = WORST_SCORE;
+        ohi[i] = -1;
+    }
+    cta_sync(nwarps);
+    if (threadIdx.x == 0) {
+        sc[0] = 0;
+        hi[0] = 0;
+    }
+    cta_sync(nwarps);
+
+    int32_t best = 0, n_renorm = 0;
+    int lo = 0, hiq = 0;  // phones [lo, hiq] are evaluated on frame t
+    for (int t = 0; t < T; ++t) {
+        const int nf = t + 1;
+        while (hiq + 1 < np && enter[hiq + 1] >= 0 && enter[hiq + 1] <= t)
+            ++hiq;
+        while (lo < hiq && max(enter[lo], ef[lo]) < t)
+            ++lo;
+        const bool lo_alive = max(enter[lo], ef[lo]) >= t;  // lo == hiq may have expired too
+        // renormalize_hmms (ref: state_align_search.c:57-64,193-197; hmm.c:150-161):
+        // every phone, alive or not, whose scores are above WORST_SCORE
+        if (best - 0x300000 < WORST_SCORE) {
+            for (int i = threadIdx.x; i < np; i += blockDim.x) {
+#pragma unroll
+                for (int j = 0; j < E; ++j)
+                    if (sc[j * np + i] > WORST_SCORE)
+                        sc[j * np + i] -= best;
+                if (osc[i] > WORST_SCORE)
+                    osc[i] -= best;
+            }
+            ++n_renorm;
+            cta_sync(nwarps);
+        }
+        // evaluate_hmms (ref :66-86)
+        int32_t lb = WORST_SCORE;
+        if (lo_alive) {
+            for (int i = lo + threadIdx.x; i <= hiq; i += blockDim.x) {
+                int32_t s[E], h[E], o_s = osc[i], o_h = ohi[i];
+                int ss[E];
+#pragma unroll
+                for (int j = 0; j < E; ++j) {
+                    s[j] = sc[j * np + i];
+                    h[j] = hi[j * np + i];
+                    ss[j] = scr[(int64_t)t * ns + i * E + j];
+                }
+                int32_t b = hmm_step<E>(m.tp + (size_t)tmat[i] * E * (E + 1), ss, s, h, o_s, o_h);
+                lb = max(lb, b);
+#pragma unroll
+                for (int j = 0; j < E; ++j) {
+                    sc[j * np + i] = s[j];
+                    hi[j * np + i] = h[j];
+                }
+                osc[i] = o_s;
+                ohi[i] = o_h;
+            }
+        }
+        cta_sync(nwarps);
+        best = block_max(lb, red, nwarps);
+        // prune_hmms + phone_transition + record_transitions (ref :88-175), one target phone
+        // per thread.  Targets: the evaluated band plus every phone the plan enters at nf
+        // (several when the reference's transition loop cascades along the chain).
+        const int first = lo_alive ? lo : hiq + 1;
+        int last_t = hiq;
+        while (last_t + 1 < np && enter[last_t + 1] == nf)
+            ++last_t;
+        for (int i = first + threadIdx.x; i <= last_t; i += blockDim.x) {
+            const bool was_active = i <= hiq;  // evaluated on frame t
+            bool now = was_active;             // hmm_frame(hmm) >= t after this step
+            if (i > 0) {
+                const int hprev = i - 1;
+                if (!was_active) {
+                    // first entry: unconditional, with whatever exit score the previous
+                    // phone holds (WORST_SCORE / -1 if it has never been evaluated)
+                    sc[i] = osc[hprev];
+                    hi[i] = ohi[hprev];
+                    now = true;
+                } else {
+                    const bool prev_eval = hprev >= first && hprev <= hiq;
+                    // hmm_frame(prev) == nf: kept by prune_hmms, or entered in this pass
+                    const bool prev_nf = (prev_eval && nf <= ef[hprev]) || enter[hprev] == nf;
+                    if (prev_nf && nf >= sf[i]) {
+                        const int32_t o = osc[hprev];
+                        if (o > sc[i]) {
+                            sc[i] = o;  // state 0
+                            hi[i] = ohi[hprev];
+                        }
+                    }
+                }
+            }
+            if (now) {
+#pragma unroll
+                for (int j = 0; j < E; ++j) {
+                    const int si = i * E + j;
+                    tok[(int64_t)t * ns + si] = make_int2(hi[j * np + i], sc[j * np + i]);
+                    hi[j * np + i] = si;
+                }
+            }
+        }
+        cta_sync(nwarps);
+    }
+    if (threadIdx.x == 0) {
+        utt_best[u] = best;
+        utt_renorm[u] = n_renorm;
+        fin_hist[u] = ohi[np - 1];
+        fin_score[u] = osc[np - 1];
+    }
+}
+
+int launch_chain_viterbi(const DevModel &m, const DevPlan &p, const int16_t *chain_scr,
+                         int2 *tokens, int32_t *spill, int64_t spill_stride, int32_t *utt_best,
+                         int32_t *utt_renorm, int32_t *fin_hist, int32_t *fin_score,
+                         int max_phones, cudaStream_t st)
+{
+    if (p.n_utts == 0)
+        return 0;
+    const int E = m.n_emit;
+    if (E != 3 && E != 5) {
+        // ref: src/hmm.c:741-759 also has an any-topology evaluator; the bundled models are 3-state
+        set_error("chain Viterbi supports 3- and 5-state HMMs, model has %d", E);
+        return -1;
+    }
+    // The evaluated band is usually a handful of phones (one word window); a single warp
+    // keeps every step warp-synchronous.  More warps only pay for unconstrained long chains.
+    int threads = max_phones <= 128 ? 32 : (max_phones < 4096 ? 128 : 512);
+    const size_t per_phone = (size_t)(2 * E + 2) * sizeof(int32_t);
+    int smem_phones = (int)((200 * 1024) / per_phone);
+    if (max_phones < smem_phones)
+        smem_phones = max_phones;
+    const size_t smem = per_phone * smem_phones;
+    if (E == 3) {
+        SSB_CUDA(cudaFuncSetAttribute(chain_viterbi_kernel<3>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        chain_viterbi_kernel<3><<<p.n_utts, threads, smem, st>>>(
+            m, p, chain_scr, tokens, spill, spill_stride, utt_best, utt_renorm, fin_hist,
+            fin_score, smem_phones);
+    } else {
+        SSB_CUDA(cudaFuncSetAttribute(chain_viterbi_kernel<5>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        chain_viterbi_kernel<5><<<p.n_utts, threads, smem, st>>>(
+            m, p, chain_scr, tokens, spill, spill_stride, utt_best, utt_renorm, fin_hist,
+            fin_score, smem_phones);
+    }
+    SSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------- backtrace
+// ref: src/state_align_search.c:215-268.  One thread per utterance; the walk is a
+// chain of dependent 8-byte loads, so the only parallelism is across utterances.
+// States that are not on the best path keep the sentinel duration -1 so the host
+// leaves the caller's entries untouched (the reference never writes them either).
+__global__ void backtrace_kernel(DevModel m, DevPlan p, const int2 *__restrict__ tokens,
+                                 const int32_t *__restrict__ fin_hist,
+                                 const int32_t *__restrict__ fin_score,
+                                 int32_t *__restrict__ st_start, int32_t *__restrict__ st_dur,
+                                 int32_t *__restrict__ st_score, int32_t *__restrict__ utt_rv)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= p.n_utts)
+        return;
+    const int T = (int)(p.frame_off[u + 1] - p.frame_off[u]);
+    const int64_t s0 = p.phone_off[u] * m.n_emit;
+    const int ns = (int)(p.phone_off[u + 1] - p.phone_off[u]) * m.n_emit;
+    const int2 *tok = tokens + p.scr_off[u];
+    if (ns == 0) {
+        utt_rv[u] = -1;
+        return;
+    }
+    int32_t last_id = fin_hist[u], last_score = fin_score[u];
+    if (last_id == -1) {
+        utt_rv[u] = -1;  // "Failed to reach final state in alignment"
+        return;
+    }
+    const int32_t *enter = p.enter_plan + p.phone_off[u];
+    const int32_t *ef = p.ef + p.phone_off[u];
+    int32_t cur_id = last_id, last_frame = T;
+    for (int cur_frame = T - 2; cur_frame >= 0; --cur_frame) {
+        // a token exists for (frame, state) only if the phone was evaluated on that frame or
+        // entered at its end; the reference reads {-1,-1} otherwise (its 0xff-filled stack)
+        const int ph = cur_id / m.n_emit;
+        const int32_t en = enter[ph];
+        if (en < 0 || en > cur_frame + 1 || (en <= cur_frame && cur_frame > max(en, ef[ph]))) {
+            utt_rv[u] = -1;
+            return;
+        }
+        const int2 tk = tok[(int64_t)cur_frame * ns + cur_id];
+        cur_id = tk.x;
+        if (cur_id == -1) {
+            utt_rv[u] = -1;
+            return;
+        }
+        if (cur_id != last_id) {
+            st_start[s0 + last_id] = cur_frame + 1;
+            st_dur[s0 + last_id] = last_frame - (cur_frame + 1);
+            st_score[s0 + last_id] = last_score - tk.y;
+            last_id = cur_id;
+            last_score = tk.y;
+            last_frame = cur_frame + 1;
+        }
+    }
+    // first state: score left alone by the reference (ref :256-261); report 0
+    st_start[s0] = 0;
+    st_dur[s0] = last_frame;
+    utt_rv[u] = 0;
+}
+
+int launch_backtrace(const DevModel &m, const DevPlan &p, const int2 *tokens,
+                     const int32_t *fin_hist, const int32_t *fin_score, int32_t *st_start,
+                     int32_t *st_dur, int32_t *st_score, int32_t *utt_rv, cudaStream_t st)
+{
+    if (p.n_utts == 0)
+        return 0;
+    backtrace_kernel<<<(p.n_utts + 63) / 64, 64, 0, st>>>(m, p, tokens, fin_hist, fin_score,
+                                                          st_start, st_dur, st_score, utt_rv);
+    SSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------- single HMM (vtable-level test hook)
+// ref: src/hmm.c:741-759 hmm_vit_eval on one non-multiplex HMM.
+__global__ void hmm_eval_kernel(DevModel m, int n_emit, int tmatid,
+                                const uint16_t *__restrict__ senid,
+                                const int16_t *__restrict__ senscr, int32_t *st12, int32_t *best)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0)
+        return;
+    const uint8_t *tp = m.tp + (size_t)tmatid * n_emit * (n_emit + 1);
+    if (n_emit == 3) {
+        int32_t s[3], h[3], o_s = st12[10], o_h = st12[11];
+        int ss[3];
+        for (int j = 0; j < 3; ++j) {
+            s[j] = st12[j];
+            h[j] = st12[5 + j];
+            ss[j] = senscr[senid[j]];
+        }
+        *best = hmm_step3(tp, ss, s, h, o_s, o_h);
+        for (int j = 0; j < 3; ++j) {
+            st12[j] = s[j];
+            st12[5 + j] = h[j];
+        }
+        st12[10] = o_s;
+        st12[11] = o_h;
+    } else {
+        int32_t s[5], h[5], o_s = st12[10], o_h = st12[11];
+        int ss[5];
+        for (int j = 0; j < 5; ++j) {
+            s[j] = st12[j];
+            h[j] = st12[5 + j];
+            ss[j] = senscr[senid[j]];
+        }
+        *best = hmm_step5(tp, ss, s, h, o_s, o_h);
+        for (int j = 0; j < 5; ++j) {
+            st12[j] = s[j];
+            st12[5 + j] = h[j];
+        }
+        st12[10] = o_s;
+        st12[11] = o_h;
+    }
+}
+
+int launch_hmm_eval(const DevModel &m, int n_emit, int tmatid, const uint16_t *senid,
+                    const int16_t *senscr, int32_t *st12, int32_t *best, cudaStream_t st)
+{
+    if (n_emit != 3 && n_emit != 5) {
+        set_error("hmm_vit_eval: %d emitting states not supported (3 or 5)", n_emit);
+        return -1;
+    }
+    hmm_eval_kernel<<<1, 32, 0, st>>>(m, n_emit, tmatid, senid, senscr, st12, best);
+    SSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ssb

@@ -1,0 +1,116 @@
+// device.cuh -- device-side model image and kernel launch prototypes.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "model.h"
+
+namespace ssb {
+
+#define SSB_CUDA(call)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            ssb::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,             \
+                           cudaGetErrorString(e_));                                         \
+            return -1;                                                                      \
+        }                                                                                   \
+    } while (0)
+
+constexpr int32_t WORST_SCORE = (int32_t)0xE0000000;
+constexpr int MAX_NEG_ASCR = 96;
+constexpr int SENSCR_SHIFT = 10;
+
+// Packed model in HBM.  Gaussians: one record per density,
+//   rec = [det, mean[0..L), prec[0..L), 0-pad]  (rec_len floats, multiple of 4)
+// so that a whole record is a run of aligned float4 loads.
+struct DevModel {
+    int32_t n_mgau, n_feat, n_density, n_sen, n_emit, n_tmat, n_sseq, blk, topn, ds;
+    int32_t featlen[SSB_MAX_FEAT];
+    int32_t featoff[SSB_MAX_FEAT];
+    int32_t rec_len[SSB_MAX_FEAT];   // floats per density record
+    int64_t gau_base[SSB_MAX_FEAT];  // float offset of stream f of codebook 0
+    int64_t gau_cb_stride;           // floats between consecutive codebooks
+    const float *gau;                // packed records
+    const uint8_t *mixw;             // [feat][density][n_sen]
+    const uint8_t *sen2cb;           // [n_sen]
+    const uint16_t *sseq;            // [n_sseq][n_emit]
+    const uint8_t *tp;               // [n_tmat][n_emit][n_emit+1]
+    const uint8_t *lut8;             // [256]
+    // senones grouped by codebook (for the dense scorer)
+    const int32_t *cb_sen_off;       // [n_mgau+1]
+    const uint16_t *cb_sen;          // [n_sen] senone ids sorted by (codebook, id)
+    int32_t max_cb_sen;
+};
+
+__host__ __device__ inline int64_t gau_offset(const DevModel &m, int cb, int f)
+{
+    return m.gau_base[f] + (int64_t)cb * m.gau_cb_stride;
+}
+
+// ---- active-set plan of one batch (mode "compallsen = no") ----
+// Utterance u has epochs [ep_off[u], ep_off[u+1]); epoch e starts at frame
+// ep_start[e] and activates union slots ep_slot[ep_slot_off[e] .. ep_slot_off[e+1])
+// of the utterance's senone union usen[us_off[u] .. us_off[u+1]).
+struct DevPlan {
+    int32_t n_utts;
+    const int64_t *frame_off;   // [U+1]
+    const int64_t *phone_off;   // [U+1]
+    const int64_t *scr_off;     // [U+1] offsets into chain_scr / tokens (state-frames)
+    const int32_t *ssid, *tmat, *sf, *ef;  // [total phones]
+    const int32_t *ep_off;      // [U+1]
+    const int32_t *ep_start;    // [n_epochs]
+    const uint32_t *ep_cbmask;  // [n_epochs][8]   256-bit active-codebook mask
+    const int32_t *ep_slot_off; // [n_epochs+1]
+    const uint16_t *ep_slot;    // union slots active in the epoch, ascending senone order
+    const int32_t *us_off;      // [U+1]
+    const uint16_t *usen;       // union senone ids (sorted) per utterance
+    const uint16_t *st_slot;    // [total states] union slot of each chain state
+    const int32_t *enter_plan;  // [total phones] planned first-entry frame (-1 never)
+    int32_t all_active;         // compallsen: every codebook scanned on every frame
+};
+
+// ---- kernel launchers (each returns 0 or -1 with the error set) ----
+// K1: stateful top-N of every (utterance, codebook, stream) chain.
+int launch_gmm_topn(const DevModel &m, const DevPlan &p, const float *feat, int64_t n_frames,
+                    int4 *tn_score, uchar4 *tn_cw, cudaStream_t st);
+// K2 (active lists): normalise, mix, subtract best, gather to chain states.
+// max_union counts the always-zero slot that inactive chain states read.
+int launch_senone_mix_active(const DevModel &m, const DevPlan &p, const int4 *tn_score,
+                             const uchar4 *tn_cw, int64_t n_frames, int max_union,
+                             int max_frames_per_utt, int16_t *chain_scr, cudaStream_t st);
+// K2 (dense, compallsen): all senones of frames [g0, g0+n) -> dense [n][n_sen] BEFORE the
+// best-score subtraction; best_tmp = [n] running minimum followed by [n][SSB_MAX_FEAT] norms
+int launch_senone_mix_all(const DevModel &m, const int4 *tn_score, const uchar4 *tn_cw,
+                          int64_t n_frames_total, int64_t g0, int64_t n, int16_t *dense,
+                          int32_t *best_tmp, cudaStream_t st);
+int launch_subtract_best(const DevModel &m, int16_t *dense, const int32_t *best, int64_t n,
+                         cudaStream_t st);
+// dense scores of frames [g0, ...) minus best -> chain states of utterances [u0, u1)
+int launch_gather_chain_best(const DevModel &m, const DevPlan &p, const int16_t *dense,
+                             const int32_t *best, int u0, int u1, int64_t g0, int16_t *chain_scr,
+                             cudaStream_t st);
+// K3: chain Viterbi + token stack; K3b: backtrace
+int launch_chain_viterbi(const DevModel &m, const DevPlan &p, const int16_t *chain_scr,
+                         int2 *tokens, int32_t *spill, int64_t spill_stride, int32_t *utt_best,
+                         int32_t *utt_renorm, int32_t *fin_hist, int32_t *fin_score,
+                         int max_phones, cudaStream_t st);
+int launch_backtrace(const DevModel &m, const DevPlan &p, const int2 *tokens,
+                     const int32_t *fin_hist, const int32_t *fin_score, int32_t *st_start,
+                     int32_t *st_dur, int32_t *st_score, int32_t *utt_rv, cudaStream_t st);
+// single-frame scorer behind the mgau vtable
+struct FrameHist {
+    int4 *score[2];    // [CS] per history slot
+    uchar4 *cw[2];
+    uint8_t *act[2];   // [n_mgau]
+};
+int launch_frame_topn(const DevModel &m, const FrameHist &h, int slot, int prev, const float *x,
+                      int do_scan, cudaStream_t st);
+int launch_frame_senones(const DevModel &m, const FrameHist &h, int slot, int do_norm,
+                         const uint16_t *act_sen, int n_act, int compallsen, int16_t *senscr,
+                         cudaStream_t st);
+int launch_hmm_eval(const DevModel &m, int n_emit, int tmatid, const uint16_t *senid,
+                    const int16_t *senscr, int32_t *st12, int32_t *best, cudaStream_t st);
+
+}  // namespace ssb

@@ -1,0 +1,518 @@
+// senone_mix.cu -- K2: codebook normalisation + mixture-weight log-sum.
+//
+// Replaces ptm_mgau_codebook_norm and ptm_mgau_senone_eval of the reference
+// (ref: src/ptm_mgau.c:264-295, 326-403) and fast_logmath_add
+// (ref: include/soundswallower/tied_mgau_common.h:100-117).  All integer work,
+// bit-exact:
+//   norm_f   = max over ACTIVE codebooks of (top-1 score >> 10)
+//   score_k  = min(96, norm_f - (raw_k >> 10))
+//   fden_f   = fold_k  a (+) b = min(a,b) - LUT[|a-b|]   over  mixw[f][cw_k][sen] + score_k
+//   senscr   = sum_f fden_f  - min over ACTIVE senones
+//
+// Two shapes:
+//  * senone_mix_active (the aligner's default mode): per utterance only the
+//    senones of its phone chain are active (plus the >255-gap bridging entries of
+//    acmod_flags2list, ref: src/acmod.c:947-999).  One CTA owns one utterance for a
+//    run of frames, stages the mixture-weight COLUMNS of that utterance's senones
+//    in shared memory once (3*128*W bytes), and emits the int16 score of every
+//    chain state -- 2 B per state-frame is all that reaches HBM.
+//  * senone_mix_all (compallsen): CTAs own a codebook, stage its ~47 KB weight
+//    slab, and stream frames.
+#include "device.cuh"
+
+namespace ssb {
+
+__device__ __forceinline__ int logadd8(int a, int b, const uint8_t *lut)
+{
+    int d = a - b, r = b;
+    if (d <= 0) {  // ref takes the (mlx > mly) branch only when strictly greater
+        d = -d;
+        r = a;
+    }
+    return r - lut[d];
+}
+
+constexpr int K2_THREADS = 256;
+constexpr int K2_F = 8;           // frames per tile
+constexpr int K2_CHUNK = 128;     // frames per CTA
+
+// ---------------------------------------------------------------- active lists
+template <bool STAGED>
+__global__ void __launch_bounds__(K2_THREADS)
+senone_mix_active_kernel(DevModel m, DevPlan p, const int4 *__restrict__ tn_s,
+                         const uchar4 *__restrict__ tn_c, int64_t G, int W,
+                         int16_t *__restrict__ chain_scr)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int u = blockIdx.y;
+    const int64_t g0 = p.frame_off[u];
+    const int T = (int)(p.frame_off[u + 1] - g0);
+    const int t_begin = blockIdx.x * K2_CHUNK;
+    if (t_begin >= T)
+        return;
+    const int t_end = min(T, t_begin + K2_CHUNK);
+    const int CS = m.n_mgau * m.n_feat;
+    const int ND = m.n_density, NF = m.n_feat, N = m.topn;
+    const int us0 = p.us_off[u], n_us = p.us_off[u + 1] - us0;
+    const int64_t ph0 = p.phone_off[u];
+    const int ns = (int)(p.phone_off[u + 1] - ph0) * m.n_emit;
+    const uint16_t *st_slot = p.st_slot + ph0 * m.n_emit;
+    const int e0 = p.ep_off[u], e1 = p.ep_off[u + 1];
+    if (ns == 0 || e0 == e1)
+        return;  // nothing to score for this utterance (uniform for the whole CTA)
+
+    // shared layout
+    uint8_t *lut = smem;                                        // 256
+    uchar4 *tile_s = reinterpret_cast<uchar4 *>(smem + 256);    // [F][CS]
+    uchar4 *tile_c = tile_s + K2_F * CS;                        // [F][CS]
+    int *norm = reinterpret_cast<int *>(tile_c + K2_F * CS);    // [F][SSB_MAX_FEAT]
+    int *best = norm + K2_F * SSB_MAX_FEAT;                     // [F]
+    int *ep_of = best + K2_F;                                   // [F]
+    int16_t *scr = reinterpret_cast<int16_t *>(ep_of + K2_F);   // [F][W]
+    uint8_t *ucb = reinterpret_cast<uint8_t *>(scr + K2_F * W); // [W] codebook of union slot
+    uint8_t *mw = ucb + ((W + 15) & ~15);                       // [NF*ND][W] staged columns
+
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        lut[i] = m.lut8[i];
+    for (int i = threadIdx.x; i < n_us; i += blockDim.x)
+        ucb[i] = m.sen2cb[p.usen[us0 + i]];
+    if (STAGED) {
+        const int rows = NF * ND;
+        for (int idx = threadIdx.x; idx < rows * n_us; idx += blockDim.x) {
+            int r = idx / n_us, j = idx - r * n_us;
+            mw[r * W + j] = m.mixw[(int64_t)r * m.n_sen + p.usen[us0 + j]];
+        }
+    }
+    __syncthreads();
+
+    for (int tt = t_begin; tt < t_end; tt += K2_F) {
+        const int nf = min(K2_F, t_end - tt);
+        // epoch of each frame of the tile; reset reducers
+        if (threadIdx.x < K2_F) {
+            int fr = threadIdx.x;
+            int e = e0;
+            if (fr < nf) {
+                while (e + 1 < e1 && p.ep_start[e + 1] <= tt + fr)
+                    ++e;
+            }
+            ep_of[fr] = e;
+            best[fr] = INT32_MAX;
+            for (int f = 0; f < NF; ++f)
+                norm[fr * SSB_MAX_FEAT + f] = WORST_SCORE;
+        }
+        for (int i = threadIdx.x; i < K2_F * W; i += blockDim.x)
+            scr[i] = 0;
+        __syncthreads();
+        // A: raw top-N of the active codebooks -> per-stream normaliser
+        constexpr int ITEMS = 4;  // (K2_F * CS) / K2_THREADS rounded up for CS <= 128
+        int4 rs[ITEMS];
+        uchar4 rc[ITEMS];
+        bool ok[ITEMS];
+#pragma unroll
+        for (int it = 0; it < ITEMS; ++it) {
+            int idx = threadIdx.x + it * K2_THREADS;
+            int fr = idx % K2_F, cs = idx / K2_F;
+            ok[it] = false;
+            if (cs < CS && fr < nf) {
+                int cb = cs / NF, f = cs - cb * NF;
+                int e = ep_of[fr];
+                if ((p.ep_cbmask[(int64_t)e * 8 + (cb >> 5)] >> (cb & 31)) & 1u) {
+                    int64_t g = (int64_t)cs * G + g0 + tt + fr;
+                    rs[it] = tn_s[g];
+                    rc[it] = tn_c[g];
+                    ok[it] = true;
+                    atomicMax(&norm[fr * SSB_MAX_FEAT + f], rs[it].x >> SENSCR_SHIFT);
+                }
+            }
+        }
+        __syncthreads();
+        // B: normalise, clamp, park in shared memory
+#pragma unroll
+        for (int it = 0; it < ITEMS; ++it) {
+            int idx = threadIdx.x + it * K2_THREADS;
+            int fr = idx % K2_F, cs = idx / K2_F;
+            if (ok[it]) {
+                int f = cs % NF;
+                int nm = norm[fr * SSB_MAX_FEAT + f];
+                uchar4 q;
+                q.x = (unsigned char)min(MAX_NEG_ASCR, nm - (rs[it].x >> SENSCR_SHIFT));
+                q.y = (unsigned char)min(MAX_NEG_ASCR, nm - (rs[it].y >> SENSCR_SHIFT));
+                q.z = (unsigned char)min(MAX_NEG_ASCR, nm - (rs[it].z >> SENSCR_SHIFT));
+                q.w = (unsigned char)min(MAX_NEG_ASCR, nm - (rs[it].w >> SENSCR_SHIFT));
+                tile_s[fr * CS + cs] = q;
+                tile_c[fr * CS + cs] = rc[it];
+            }
+        }
+        __syncthreads();
+        // C: one (frame, active senone) per thread
+        for (int fr = 0; fr < nf; ++fr) {
+            const int e = ep_of[fr];
+            const int sl0 = p.ep_slot_off[e], na = p.ep_slot_off[e + 1] - sl0;
+            int local_best = INT32_MAX;
+            for (int i = threadIdx.x; i < na; i += blockDim.x) {
+                const int slot = p.ep_slot[sl0 + i];
+                const int cb = ucb[slot];
+                int ascore = 0;
+                for (int f = 0; f < NF; ++f) {
+                    const uchar4 sv = tile_s[fr * CS + cb * NF + f];
+                    const uchar4 cv = tile_c[fr * CS + cb * NF + f];
+                    const int sc[4] = {sv.x, sv.y, sv.z, sv.w};
+                    const int cw[4] = {cv.x, cv.y, cv.z, cv.w};
+                    int fden = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (k < N) {
+                            int w;
+                            if (STAGED)
+                                w = mw[(f * ND + cw[k]) * W + slot];
+                            else
+                                w = m.mixw[(int64_t)(f * ND + cw[k]) * m.n_sen
+                                           + p.usen[us0 + slot]];
+                            int v = w + sc[k];
+                            fden = k == 0 ? v : logadd8(fden, v, lut);
+                        }
+                    }
+                    ascore += fden;
+                }
+                scr[fr * W + slot] = (int16_t)ascore;
+                local_best = min(local_best, ascore);
+            }
+            // warp-reduce then one shared atomic per warp
+            for (int o = 16; o > 0; o >>= 1)
+                local_best = min(local_best, __shfl_xor_sync(0xffffffffu, local_best, o));
+            if ((threadIdx.x & 31) == 0 && local_best != INT32_MAX)
+                atomicMin(&best[fr], local_best);
+        }
+        __syncthreads();
+        // D: gather to chain states, subtract the frame's best (ref :398-400)
+        {
+            int16_t *dst = chain_scr + p.scr_off[u] + (int64_t)tt * ns;
+            for (int idx = threadIdx.x; idx < nf * ns; idx += blockDim.x) {
+                int fr = idx / ns, si = idx - fr * ns;
+                dst[idx] = (int16_t)(scr[fr * W + st_slot[si]] - (int16_t)best[fr]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+static size_t k2_active_smem(const DevModel &m, int W, bool staged)
+{
+    int CS = m.n_mgau * m.n_feat;
+    size_t b = 256 + (size_t)2 * K2_F * CS * 4 + (size_t)K2_F * SSB_MAX_FEAT * 4 + K2_F * 4
+               + K2_F * 4 + (size_t)K2_F * W * 2 + ((W + 15) & ~15);
+    if (staged)
+        b += (size_t)m.n_feat * m.n_density * W;
+    return b + 16;
+}
+
+int launch_senone_mix_active(const DevModel &m, const DevPlan &p, const int4 *tn_score,
+                             const uchar4 *tn_cw, int64_t n_frames, int max_union,
+                             int max_frames_per_utt, int16_t *chain_scr, cudaStream_t st)
+{
+    if (p.n_utts == 0 || n_frames == 0)
+        return 0;
+    if (m.n_mgau * m.n_feat * K2_F > 4 * K2_THREADS) {
+        set_error("senone_mix: %d codebook-streams exceed the tile (max %d)",
+                  m.n_mgau * m.n_feat, 4 * K2_THREADS / K2_F);
+        return -1;
+    }
+    int W = (max_union + 3) & ~3;
+    if (W < 4)
+        W = 4;
+    bool staged = k2_active_smem(m, W, true) <= 200 * 1024;
+    size_t smem = k2_active_smem(m, W, staged);
+    dim3 grid((max_frames_per_utt + K2_CHUNK - 1) / K2_CHUNK, p.n_utts);
+    if (staged) {
+        SSB_CUDA(cudaFuncSetAttribute(senone_mix_active_kernel<true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        senone_mix_active_kernel<true>
+            <<<grid, K2_THREADS, smem, st>>>(m, p, tn_score, tn_cw, n_frames, W, chain_scr);
+    } else {
+        SSB_CUDA(cudaFuncSetAttribute(senone_mix_active_kernel<false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        senone_mix_active_kernel<false>
+            <<<grid, K2_THREADS, smem, st>>>(m, p, tn_score, tn_cw, n_frames, W, chain_scr);
+    }
+    SSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------- dense (compallsen)
+// per-frame, per-stream normaliser over ALL codebooks: norm[g][f]
+__global__ void norm_all_kernel(DevModel m, const int4 *__restrict__ tn_s, int64_t G, int64_t g0,
+                                int64_t n, int32_t *__restrict__ norm)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    for (int f = 0; f < m.n_feat; ++f) {
+        int nm = WORST_SCORE;
+        for (int cb = 0; cb < m.n_mgau; ++cb)
+            nm = max(nm, tn_s[(int64_t)(cb * m.n_feat + f) * G + g0 + i].x >> SENSCR_SHIFT);
+        norm[i * SSB_MAX_FEAT + f] = nm;
+    }
+}
+
+constexpr int K2A_F = 32;
+
+// grid: x = codebook, y = frame slices.  dense[(g-g0)][sen] receives the score BEFORE the
+// best-score subtraction; best[g-g0] the running minimum.
+__global__ void __launch_bounds__(K2_THREADS)
+senone_mix_all_kernel(DevModel m, const int4 *__restrict__ tn_s, const uchar4 *__restrict__ tn_c,
+                      int64_t G, int64_t g0, int64_t n, const int32_t *__restrict__ norm,
+                      int Wc, int staged, int16_t *__restrict__ dense, int32_t *__restrict__ best)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int cb = blockIdx.x;
+    const int ND = m.n_density, NF = m.n_feat, N = m.topn;
+    const int s0 = m.cb_sen_off[cb], ncs = m.cb_sen_off[cb + 1] - s0;
+    uint8_t *lut = smem;
+    uchar4 *tile_s = reinterpret_cast<uchar4 *>(smem + 256);  // [F][NF]
+    uchar4 *tile_c = tile_s + K2A_F * SSB_MAX_FEAT;
+    int *tbest = reinterpret_cast<int *>(tile_c + K2A_F * SSB_MAX_FEAT);  // [F]
+    uint8_t *mw = reinterpret_cast<uint8_t *>(tbest + K2A_F);             // [NF*ND][Wc]
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        lut[i] = m.lut8[i];
+    if (staged) {
+        const int rows = NF * ND;
+        for (int idx = threadIdx.x; idx < rows * ncs; idx += blockDim.x) {
+            int r = idx / ncs, j = idx - r * ncs;
+            mw[r * Wc + j] = m.mixw[(int64_t)r * m.n_sen + m.cb_sen[s0 + j]];
+        }
+    }
+    __syncthreads();
+    if (ncs == 0)
+        return;
+    for (int64_t base = (int64_t)blockIdx.y * K2A_F; base < n; base += (int64_t)gridDim.y * K2A_F) {
+        const int nf = (int)min((int64_t)K2A_F, n - base);
+        if (threadIdx.x < nf * NF) {
+            int fr = threadIdx.x / NF, f = threadIdx.x - fr * NF;
+            int64_t g = (int64_t)(cb * NF + f) * G + g0 + base + fr;
+            int4 rs = tn_s[g];
+            int nm = norm[(base + fr) * SSB_MAX_FEAT + f];
+            uchar4 q;
+            q.x = (unsigned char)min(MAX_NEG_ASCR, nm - (rs.x >> SENSCR_SHIFT));
+            q.y = (unsigned char)min(MAX_NEG_ASCR, nm - (rs.y >> SENSCR_SHIFT));
+            q.z = (unsigned char)min(MAX_NEG_ASCR, nm - (rs.z >> SENSCR_SHIFT));
+            q.w = (unsigned char)min(MAX_NEG_ASCR, nm - (rs.w >> SENSCR_SHIFT));
+            tile_s[fr * SSB_MAX_FEAT + f] = q;
+            tile_c[fr * SSB_MAX_FEAT + f] = tn_c[g];
+        }
+        if (threadIdx.x < K2A_F)
+            tbest[threadIdx.x] = INT32_MAX;
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nf * ncs; idx += blockDim.x) {
+            int fr = idx / ncs, j = idx - fr * ncs;
+            int sen = m.cb_sen[s0 + j];
+            int ascore = 0;
+            for (int f = 0; f < NF; ++f) {
+                const uchar4 sv = tile_s[fr * SSB_MAX_FEAT + f];
+                const uchar4 cv = tile_c[fr * SSB_MAX_FEAT + f];
+                const int sc[4] = {sv.x, sv.y, sv.z, sv.w};
+                const int cw[4] = {cv.x, cv.y, cv.z, cv.w};
+                int fden = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k < N) {
+                        int w = staged ? mw[(f * ND + cw[k]) * Wc + j]
+                                       : m.mixw[(int64_t)(f * ND + cw[k]) * m.n_sen + sen];
+                        int v = w + sc[k];
+                        fden = k == 0 ? v : logadd8(fden, v, lut);
+                    }
+                }
+                ascore += fden;
+            }
+            dense[(base + fr) * m.n_sen + sen] = (int16_t)ascore;
+            atomicMin(&tbest[fr], ascore);
+        }
+        __syncthreads();
+        if (threadIdx.x < nf && tbest[threadIdx.x] != INT32_MAX)
+            atomicMin(&best[base + threadIdx.x], tbest[threadIdx.x]);
+        __syncthreads();
+    }
+}
+
+__global__ void fill_i32_kernel(int32_t *p, int64_t n, int32_t v)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        p[i] = v;
+}
+
+__global__ void subtract_best_kernel(int16_t *__restrict__ dense, const int32_t *__restrict__ best,
+                                     int64_t n, int n_sen)
+{
+    int64_t row = blockIdx.x;
+    if (row >= n)
+        return;
+    int16_t b = (int16_t)best[row];
+    int16_t *r = dense + row * n_sen;
+    for (int i = threadIdx.x; i < n_sen; i += blockDim.x)
+        r[i] = (int16_t)(r[i] - b);
+}
+
+// best_tmp: [n] int32 followed by [n][SSB_MAX_FEAT] int32 normalisers
+int launch_senone_mix_all(const DevModel &m, const int4 *tn_score, const uchar4 *tn_cw,
+                          int64_t n_frames_total, int64_t g0, int64_t n, int16_t *dense,
+                          int32_t *best_tmp, cudaStream_t st)
+{
+    if (n == 0)
+        return 0;
+    int32_t *best = best_tmp, *norm = best_tmp + n;
+    fill_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(best, n, INT32_MAX);
+    norm_all_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(m, tn_score, n_frames_total, g0, n,
+                                                                 norm);
+    int Wc = (m.max_cb_sen + 3) & ~3;
+    size_t fixed = 256 + (size_t)2 * K2A_F * SSB_MAX_FEAT * 4 + K2A_F * 4;
+    size_t smem = fixed + (size_t)m.n_feat * m.n_density * Wc;
+    int staged = smem <= 200 * 1024;
+    if (!staged)
+        smem = fixed;
+    SSB_CUDA(cudaFuncSetAttribute(senone_mix_all_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t slices64 = (n + K2A_F - 1) / K2A_F;
+    int slices = slices64 > 16 ? 16 : (int)slices64;
+    dim3 grid(m.n_mgau, slices);
+    senone_mix_all_kernel<<<grid, K2_THREADS, smem, st>>>(m, tn_score, tn_cw, n_frames_total, g0, n,
+                                                          norm, Wc, staged, dense, best);
+    SSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_subtract_best(const DevModel &m, int16_t *dense, const int32_t *best, int64_t n,
+                         cudaStream_t st)
+{
+    if (n == 0)
+        return 0;
+    subtract_best_kernel<<<(unsigned)n, 256, 0, st>>>(dense, best, n, m.n_sen);
+    SSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// chain_scr[u][t][si] = dense[g][senone(si)] - best[g] for utterances [u0,u1) whose frames
+// lie in [g0, ...)
+__global__ void gather_chain_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ dense,
+                                    const int32_t *__restrict__ best, int u0, int64_t g0,
+                                    int16_t *__restrict__ chain_scr)
+{
+    const int u = u0 + blockIdx.y;
+    const int64_t f0 = p.frame_off[u];
+    const int T = (int)(p.frame_off[u + 1] - f0);
+    const int64_t ph0 = p.phone_off[u];
+    const int ns = (int)(p.phone_off[u + 1] - ph0) * m.n_emit;
+    const int E = m.n_emit;
+    for (int t = blockIdx.x; t < T; t += gridDim.x) {
+        const int64_t row = f0 + t - g0;
+        const int16_t b = (int16_t)best[row];
+        int16_t *dst = chain_scr + p.scr_off[u] + (int64_t)t * ns;
+        for (int si = threadIdx.x; si < ns; si += blockDim.x) {
+            int ph = si / E, j = si - ph * E;
+            int sen = m.sseq[(int64_t)p.ssid[ph0 + ph] * E + j];
+            dst[si] = (int16_t)(dense[row * m.n_sen + sen] - b);
+        }
+    }
+}
+
+int launch_gather_chain_best(const DevModel &m, const DevPlan &p, const int16_t *dense,
+                             const int32_t *best, int u0, int u1, int64_t g0, int16_t *chain_scr,
+                             cudaStream_t st)
+{
+    if (u1 <= u0)
+        return 0;
+    dim3 grid(64, u1 - u0);
+    gather_chain_kernel<<<grid, 128, 0, st>>>(m, p, dense, best, u0, g0, chain_scr);
+    SSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------- single frame (vtable)
+// One CTA.  Works on history slot `slot` in place like the reference does: active
+// codebooks are normalised in place when do_norm, and a senone whose codebook is not
+// active forces that codebook's entries to 96 (ref :353-364).
+__global__ void __launch_bounds__(512)
+frame_senones_kernel(DevModel m, FrameHist h, int slot, int do_norm,
+                     const uint16_t *__restrict__ act_sen, int n_act, int compallsen,
+                     int16_t *__restrict__ senscr)
+{
+    __shared__ int s_norm[SSB_MAX_FEAT];
+    __shared__ int s_best;
+    __shared__ uint8_t lut[256];
+    const int NF = m.n_feat, ND = m.n_density, N = m.topn;
+    int4 *hs = h.score[slot];
+    const uchar4 *hc = h.cw[slot];
+    const uint8_t *act = h.act[slot];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        lut[i] = m.lut8[i];
+    if (threadIdx.x < NF)
+        s_norm[threadIdx.x] = WORST_SCORE;
+    if (threadIdx.x == 0)
+        s_best = INT32_MAX;
+    for (int i = threadIdx.x; i < m.n_sen; i += blockDim.x)
+        senscr[i] = 0;
+    __syncthreads();
+    if (do_norm) {
+        for (int cs = threadIdx.x; cs < m.n_mgau * NF; cs += blockDim.x)
+            if (act[cs / NF])
+                atomicMax(&s_norm[cs % NF], hs[cs].x >> SENSCR_SHIFT);
+        __syncthreads();
+        for (int cs = threadIdx.x; cs < m.n_mgau * NF; cs += blockDim.x)
+            if (act[cs / NF]) {
+                int nm = s_norm[cs % NF];
+                int4 v = hs[cs];
+                v.x = min(MAX_NEG_ASCR, nm - (v.x >> SENSCR_SHIFT));
+                v.y = min(MAX_NEG_ASCR, nm - (v.y >> SENSCR_SHIFT));
+                v.z = min(MAX_NEG_ASCR, nm - (v.z >> SENSCR_SHIFT));
+                v.w = min(MAX_NEG_ASCR, nm - (v.w >> SENSCR_SHIFT));
+                hs[cs] = v;
+            }
+        __syncthreads();
+    }
+    const int n = compallsen ? m.n_sen : n_act;
+    // pass 1: knock out codebooks that are referenced but not active
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int sen = compallsen ? i : act_sen[i];
+        int cb = m.sen2cb[sen];
+        if (!act[cb])
+            for (int f = 0; f < NF; ++f)
+                hs[cb * NF + f] = make_int4(MAX_NEG_ASCR, MAX_NEG_ASCR, MAX_NEG_ASCR, MAX_NEG_ASCR);
+    }
+    __syncthreads();
+    int local_best = INT32_MAX;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int sen = compallsen ? i : act_sen[i];
+        int cb = m.sen2cb[sen];
+        int ascore = 0;
+        for (int f = 0; f < NF; ++f) {
+            int4 sv = hs[cb * NF + f];
+            uchar4 cv = hc[cb * NF + f];
+            const int sc[4] = {sv.x, sv.y, sv.z, sv.w};
+            const int cw[4] = {cv.x, cv.y, cv.z, cv.w};
+            int fden = 0;
+            for (int k = 0; k < N; ++k) {
+                int v = m.mixw[(int64_t)(f * ND + cw[k]) * m.n_sen + sen] + sc[k];
+                fden = k == 0 ? v : logadd8(fden, v, lut);
+            }
+            ascore += fden;
+        }
+        senscr[sen] = (int16_t)ascore;
+        local_best = min(local_best, ascore);
+    }
+    if (local_best != INT32_MAX)
+        atomicMin(&s_best, local_best);
+    __syncthreads();
+    const int16_t b = (int16_t)s_best;
+    for (int i = threadIdx.x; i < m.n_sen; i += blockDim.x)
+        senscr[i] = (int16_t)(senscr[i] - b);
+}
+
+int launch_frame_senones(const DevModel &m, const FrameHist &h, int slot, int do_norm,
+                         const uint16_t *act_sen, int n_act, int compallsen, int16_t *senscr,
+                         cudaStream_t st)
+{
+    frame_senones_kernel<<<1, 512, 0, st>>>(m, h, slot, do_norm, act_sen, n_act, compallsen, senscr);
+    SSB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ssb

@@ -1,0 +1,328 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the golden vectors.
+Integer work is compared bit for bit."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import soundswallower_b200 as ssb
+from conftest import chain_from_golden, model_features, random_chain
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+# ------------------------------------------------------------------ K1: Gaussian top-N
+@pytest.mark.parametrize("lang", ["en-us", "fr-fr"])
+def test_topn_matches_oracle_golden_audio(models, oracles, golden, lang):
+    m, o, g = models(lang), oracles(lang), golden[lang]
+    cw, sc = ssb.topn_batch(m, [g["feat"]])
+    ocw, osc = o.topn_all(g["feat"])
+    assert np.array_equal(sc[0], osc)
+    assert np.array_equal(cw[0], ocw)
+
+
+def test_topn_ragged_batch(models, oracles):
+    m, o = models("en-us"), oracles("en-us")
+    rs = np.random.RandomState(3)
+    arrays = o.model_arrays()
+    lens = [1, 0, 17, 5, 64, 2, 33] + [3] * 130  # > one CTA of utterances, an empty one
+    feats = [model_features(rs, arrays, T) for T in lens]
+    cw, sc = ssb.topn_batch(m, feats)
+    for u in (0, 1, 2, 4, 6, 7, 100, len(lens) - 1):
+        ocw, osc = o.topn_all(feats[u])
+        assert np.array_equal(sc[u], osc) and np.array_equal(cw[u], ocw), u
+
+
+@pytest.mark.parametrize("topn", [1, 2, 3])
+def test_topn_other_n(models, oracles, golden, topn):
+    from oracle.oracle import Oracle
+    from conftest import model_dir
+    m = models("en-us", topn=topn)
+    o = Oracle(model_dir("en-us"), topn=topn)
+    feat = golden["en-us"]["feat"][:40]
+    cw, sc = ssb.topn_batch(m, [feat])
+    ocw, osc = o.topn_all(feat)
+    assert np.array_equal(sc[0], osc) and np.array_equal(cw[0], ocw)
+    assert np.array_equal(ssb.score_batch(m, [feat])[0], o.score_all(feat))
+
+
+# ------------------------------------------------------------------ K1+K2 dense scores
+@pytest.mark.parametrize("lang", ["en-us", "fr-fr"])
+def test_dense_scores_golden(models, golden, lang):
+    m, g = models(lang), golden[lang]
+    d = ssb.score_batch(m, [g["feat"]])[0]
+    assert sha(d) == str(g["senscr_sha"])
+    assert np.array_equal(d[g["senscr_rows"]], g["senscr_sample"])
+
+
+def test_dense_scores_survey_sha(models, golden):
+    d = ssb.score_batch(models("en-us"), [golden["en-us"]["feat"]])[0]
+    assert sha(d) == "4129ae8da103a1aa3a6b44487596c1bb3563a84cc5929fc82c1fc9068951f26f"
+
+
+def test_dense_scores_synthetic(models, synthetic):
+    m = models("en-us")
+    feats = [synthetic["feat%d" % u] for u in range(4)]
+    out = ssb.score_batch(m, feats)
+    for u in range(4):
+        assert sha(out[u]) == str(synthetic["senscr_sha%d" % u]), u
+    # batch composition must not matter
+    out2 = ssb.score_batch(m, feats[::-1])
+    for u in range(4):
+        assert np.array_equal(out2[3 - u], out[u])
+
+
+def test_dense_scores_spanning_slabs(models, oracles):
+    """More frames than one dense slab (32768): only properties + spot rows vs the oracle."""
+    m, o = models("fr-fr"), oracles("fr-fr")
+    rs = np.random.RandomState(5)
+    base = model_features(rs, o.model_arrays(), 700)
+    feats = [base[rs.randint(0, 600):][:100] for _ in range(340)]  # 34000 frames
+    out = ssb.score_batch(m, feats)
+    for u in (0, 327, 328, 339):
+        assert np.array_equal(out[u], o.score_all(feats[u])), u
+    assert all((d.min(1) == 0).all() for d in out)
+
+
+# ------------------------------------------------------------------ mgau vtable (one frame per call)
+def test_mgau_vtable_compallsen_and_rewind(models, oracles, golden):
+    m, o, g = models("en-us"), oracles("en-us"), golden["en-us"]
+    mg = ssb.PtmMgau(m)
+    assert mg.name == "ptm" and mg.frame_idx == 0
+    p = o.new_ptm()
+    feat = g["feat"]
+    for t in range(12):
+        a = mg.frame_eval(feat[t], t, compallsen=True)
+        b = o.frame_eval(p, feat[t], t, compallsen=True)
+        assert np.array_equal(a, b), t
+        mg.frame_idx = t + 1
+        o.set_frame_idx(p, t + 1)
+    # re-scoring a frame that is already in the history does not recompute the codebooks
+    a = mg.frame_eval(feat[11], 11, compallsen=True)
+    b = o.frame_eval(p, feat[11], 11, compallsen=True)
+    assert np.array_equal(a, b)
+    # acmod_rewind: frame_idx back to 0, history kept (ref: src/acmod.c:730-751)
+    mg.frame_idx = 0
+    o.set_frame_idx(p, 0)
+    for t in range(3):
+        assert np.array_equal(mg.frame_eval(feat[t], t, compallsen=True),
+                              o.frame_eval(p, feat[t], t, compallsen=True))
+        mg.frame_idx = t + 1
+        o.set_frame_idx(p, t + 1)
+    mg.reset()
+    o.reset_ptm(p)
+    o.set_frame_idx(p, 0)
+    assert np.array_equal(mg.frame_eval(feat[5], 0, compallsen=True),
+                          o.frame_eval(p, feat[5], 0, compallsen=True))
+    o.free_ptm(p)
+    mg.close()
+
+
+def test_mgau_vtable_active_lists(models, oracles, golden):
+    m, o, g = models("en-us"), oracles("en-us"), golden["en-us"]
+    mg = ssb.PtmMgau(m)
+    p = o.new_ptm()
+    rs = np.random.RandomState(9)
+    feat = g["feat"]
+    sen = set()
+    for t in range(20):
+        # a growing active set with gaps above 255 (bridging entries)
+        sen |= set(int(x) for x in rs.randint(0, m.n_sen, 6))
+        lst = ssb.flags2list(sen)
+        assert np.array_equal(lst, o.flags2list(sorted(sen)))
+        a = mg.frame_eval(feat[t], t, senone_active=lst, compallsen=False)
+        b = o.frame_eval(p, feat[t], t, active=lst, compallsen=False)
+        assert np.array_equal(a, b), t
+        mg.frame_idx = t + 1
+        o.set_frame_idx(p, t + 1)
+    # empty active list: everything 0 - INT_MAX truncated, as the reference computes it
+    a = mg.frame_eval(feat[20], 20, senone_active=np.zeros(0, np.uint8), compallsen=False)
+    b = o.frame_eval(p, feat[20], 20, active=np.zeros(0, np.uint8), compallsen=False)
+    assert np.array_equal(a, b)
+    o.free_ptm(p)
+    mg.close()
+
+
+# ------------------------------------------------------------------ hmm_vit_eval
+def test_hmm_vit_eval_known_answers(models, synthetic):
+    m, s = models("en-us"), synthetic
+    for i in range(0, len(s["hmm_best"]), 3):
+        if len(set(s["hmm_senid"][i].tolist())) < 3:
+            continue
+        senscr = np.zeros(m.n_sen, np.int16)
+        senscr[s["hmm_senid"][i]] = s["hmm_senscr3"][i]
+        best, st = ssb.hmm_vit_eval(m, s["hmm_tmat"][i], s["hmm_senid"][i], senscr, s["hmm_st_in"][i])
+        assert best == int(s["hmm_best"][i]), i
+        assert np.array_equal(st, s["hmm_st_out"][i]), i
+
+
+# ------------------------------------------------------------------ chain alignment
+def _check_against_golden(r, g, mode):
+    st = g[mode + "_states"]
+    assert r["rv"] == 0 and r["best_score"] == int(g[mode + "_best"])
+    assert np.array_equal(r["start"], st[:, 1])
+    assert np.array_equal(r["dur"], st[:, 2])
+    assert np.array_equal(r["score"], st[:, 3])
+    assert np.array_equal(r["chain_scr"], g[mode + "_chain_scr"])
+    assert sha(r["tokens"]) == str(g[mode + "_tokens_sha"])
+
+
+@pytest.mark.parametrize("lang", ["en-us", "fr-fr"])
+@pytest.mark.parametrize("mode", ["win", "nowin", "win_call"])
+def test_align_golden(models, golden, lang, mode):
+    """Windowed / unwindowed, default (active-list) / compallsen scoring, vs the reference's
+    own state_align_search run on the same features (tools/make_golden.py)."""
+    m, g = models(lang), golden[lang]
+    chain = chain_from_golden(g, windows=mode != "nowin")
+    r = ssb.align_batch(m, [g["feat"]], [chain], compallsen=mode.endswith("call"),
+                        want_chain_scr=True, want_tokens=True)[0]
+    _check_against_golden(r, g, mode)
+    ps, pd, pc = ssb.propagate(r["start"], r["dur"], r["score"], m.n_emit)
+    ph = g[mode + "_phones"]
+    assert np.array_equal(ps, ph[:, 3]) and np.array_equal(pd, ph[:, 4]) and np.array_equal(pc, ph[:, 5])
+
+
+def test_align_reproduces_survey_appendix_b(models, golden):
+    m, g = models("en-us"), golden["en-us"]
+    r = ssb.align_batch(m, [g["feat"]], [chain_from_golden(g)])[0]
+    sen = m.arrays()["sseq"][g["phones"][:, 1]].reshape(-1)
+    got = ["%d:%d+%d:%d" % (sen[i], r["start"][i], r["dur"][i], r["score"][i]) for i in range(len(sen))]
+    assert got[:6] == ["96:0+44:0", "97:44+1:-37", "98:45+1:-30", "2085:46+3:-18", "2115:49+3:-18",
+                       "2138:52+2:-13"]
+    assert got[-3:] == ["96:211+61:-296", "97:272+1:-21", "98:273+5:-62"]
+
+
+def _random_batch(rs, o, n_utts, max_T=60, max_ph=14):
+    arrays = o.model_arrays()
+    feats, chains = [], []
+    for u in range(n_utts):
+        T = int(rs.randint(1, max_T))
+        npn = int(rs.randint(1, max_ph))
+        feats.append(model_features(rs, arrays, T))
+        chains.append(random_chain(rs, o, npn, T, windowed=u % 3 != 0))
+    return feats, chains
+
+
+@pytest.mark.parametrize("compallsen", [False, True])
+def test_align_random_ragged_batch(models, oracles, compallsen):
+    m, o = models("en-us"), oracles("en-us")
+    rs = np.random.RandomState(21 + compallsen)
+    feats, chains = _random_batch(rs, o, 40)
+    # edge cases: zero frames, one frame, chain longer than the utterance
+    feats[3] = feats[3][:0]
+    feats[5] = feats[5][:1]
+    chains[7] = random_chain(rs, o, 30, feats[7].shape[0], windowed=False)
+    res = ssb.align_batch(m, feats, chains, compallsen=compallsen, want_chain_scr=True,
+                          want_tokens=True)
+    n_ok = 0
+    for u, (f, c, r) in enumerate(zip(feats, chains, res)):
+        w = o.state_align(f, c["ssid"], c["tmat"], c["sf"], c["ef"], compallsen=compallsen,
+                          want_tokens=True, want_senscr=True)
+        assert r["rv"] == w["rv"], u
+        if f.shape[0]:
+            assert r["best_score"] == w["best_score"], u
+            sen = o.model_arrays()["sseq"][c["ssid"]].reshape(-1)
+            assert np.array_equal(r["chain_scr"], w["senscr"][:, sen]), u
+            assert np.array_equal(r["tokens"], w["tokens"]), u
+        if w["rv"] == 0:
+            n_ok += 1
+            assert np.array_equal(r["start"], w["start"]) and np.array_equal(r["dur"], w["dur"]), u
+            assert np.array_equal(r["score"], w["score"]), u
+    assert n_ok >= 10
+
+
+def test_align_init_active_senones(models, oracles, golden):
+    """Pass 2 starts with whatever pass 1 left flagged (ref: src/state_align_search.c:186-188)."""
+    m, o, g = models("en-us"), oracles("en-us"), golden["en-us"]
+    chain = chain_from_golden(g)
+    left = [5, 300, 301, 2999, 5100]
+    r = ssb.align_batch(m, [g["feat"]], [chain], init_active=[left], want_chain_scr=True)[0]
+    w = o.state_align(g["feat"], chain["ssid"], chain["tmat"], chain["sf"], chain["ef"],
+                      init_active=left, want_senscr=True)
+    sen = o.model_arrays()["sseq"][chain["ssid"]].reshape(-1)
+    assert np.array_equal(r["chain_scr"], w["senscr"][:, sen])
+    assert np.array_equal(r["start"], w["start"]) and np.array_equal(r["score"], w["score"])
+
+
+def test_align_states_off_path_keep_caller_values(models, golden):
+    m, g = models("en-us"), golden["en-us"]
+    chain = chain_from_golden(g)
+    b = ssb.StateAlignBatch(m)
+    # second utterance cannot reach its final state: 2 frames for 18 phones
+    b.upload([g["feat"], g["feat"][:2]], [chain, chain_from_golden(g, windows=False)])
+    b.run()
+    ns = 18 * 3
+    init = (np.full(2 * ns, 777, np.int32), np.full(2 * ns, 888, np.int32), np.full(2 * ns, 999, np.int32))
+    res = b.per_utt(b.download(init=init))
+    assert res[0]["rv"] == 0 and np.array_equal(res[0]["dur"], g["win_states"][:, 2])
+    assert res[1]["rv"] == -1 and (res[1]["dur"] == 888).all() and (res[1]["start"] == 777).all()
+    assert b.n_launches() == 4
+    ms = b.kernel_ms()
+    assert ms["total"] > 0
+    st = b.stats()
+    assert st["frames"] == 280 and st["state_frames"] == 280 * ns
+    b.close()
+
+
+def test_align_empty_batch(models):
+    m = models("en-us")
+    assert ssb.align_batch(m, [], []) == []
+    assert ssb.score_batch(m, []) == []
+
+
+def test_align_rejects_bad_chains(models, golden):
+    m, g = models("en-us"), golden["en-us"]
+    chain = chain_from_golden(g)
+    bad = dict(chain, ssid=chain["ssid"].copy())
+    bad["ssid"][3] = m.n_sseq
+    with pytest.raises(ssb.SsbError, match="out of range"):
+        ssb.align_batch(m, [g["feat"]], [bad])
+    bad = dict(chain, ef=chain["ef"].copy())
+    bad["ef"][4] = 10
+    with pytest.raises(ssb.SsbError, match="must not decrease"):
+        ssb.align_batch(m, [g["feat"]], [bad])
+
+
+# ------------------------------------------------------------------ BASELINE-size properties
+def test_config2_shape_properties(models, golden):
+    """BASELINE config #2 shape (1000-frame utterances, 52 phones / 156 states), 512 utterances:
+    size-independent invariants + identical utterances give identical alignments wherever
+    they sit in the batch + spot parity."""
+    from bench import make_config2_batch
+    m, g = models("en-us"), golden["en-us"]
+    feats, chains = make_config2_batch(g, n_utts=512, noise=0.05, seed=1234)
+    feats[400] = feats[7].copy()
+    b = ssb.StateAlignBatch(m)
+    b.upload(feats, chains)
+    b.run()
+    res = b.per_utt(b.download())
+    b.close()
+    for u, r in enumerate(res):
+        assert r["rv"] == 0, u
+        on = r["dur"] > 0
+        start, dur = r["start"][on], r["dur"][on]
+        assert start[0] == 0 and (start[1:] == start[:-1] + dur[:-1]).all(), u  # tiles, monotone
+        assert start[-1] + dur[-1] == 1000, u
+        # every state lies inside its word window
+        sf = np.repeat(chains[u]["sf"], 3)[on]
+        ef = np.repeat(chains[u]["ef"], 3)[on]
+        assert (start >= sf).all() and (start + dur <= ef).all(), u
+    assert np.array_equal(res[400]["start"], res[7]["start"])
+    assert np.array_equal(res[400]["score"], res[7]["score"])
+
+
+def test_config2_spot_parity_with_oracle(models, oracles, golden):
+    from bench import make_config2_batch
+    m, o, g = models("en-us"), oracles("en-us"), golden["en-us"]
+    feats, chains = make_config2_batch(g, n_utts=160, noise=0.05, seed=99)
+    res = ssb.align_batch(m, feats, chains)
+    for u in (0, 31, 32, 127, 128, 159):
+        c = chains[u]
+        w = o.state_align(feats[u], c["ssid"], c["tmat"], c["sf"], c["ef"])
+        assert w["rv"] == 0 == res[u]["rv"]
+        assert np.array_equal(res[u]["start"], w["start"]) and np.array_equal(res[u]["dur"], w["dur"])
+        assert np.array_equal(res[u]["score"], w["score"]) and res[u]["best_score"] == w["best_score"]

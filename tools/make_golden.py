@@ -1,0 +1,169 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libssref.so).
+
+Run in the build container, where /root/reference exists and `make -C oracle ref`
+has produced libssref.so.  The fixtures are small (features, chains, integer
+results, sha256 digests of the big matrices) and are committed; the GPU box only
+ever reads the fixtures.
+
+    python tools/make_golden.py
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.refshim import Ref, available  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+DATA = os.path.join(ROOT, "tests", "data")
+MODELS = os.path.join(ROOT, "soundswallower_b200", "model")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def phone_windows(words, phones):
+    """phones inherit their word's (start, duration) (ref: src/ps_alignment.c:168-305)."""
+    parent = phones[:, 6]
+    return words[parent, 1].astype(np.int32), words[parent, 2].astype(np.int32)
+
+
+def utterance(lang, raw, text):
+    hmm = os.path.join(MODELS, lang)
+    pcm = np.fromfile(os.path.join(DATA, raw), np.int16)
+    ref = Ref(hmm)
+    refc = Ref(hmm, compallsen=True)
+    g = {}
+    arrays = ref.model_arrays()
+    for k, v in arrays.items():
+        g["model_sha_" + k] = sha(v)
+    g["lut"] = arrays["lut"]
+    g["tp"] = arrays["tp"]
+    g["dims"] = np.array([ref.n_mgau, ref.n_feat, ref.n_density, ref.veclen, ref.n_sen, ref.n_sseq,
+                          ref.n_emit, ref.n_tmat, ref.n_ciphone, ref.n_phone, ref.sil], np.int32)
+    feat = ref.features_from_pcm(pcm)
+    g["feat"] = feat
+    g["mfcc_head"] = ref.mfcc_from_pcm(pcm)[:8]
+    # 2-pass alignment exactly as the CLI does it
+    al = ref.align_pcm(pcm, text)
+    g["segs"] = al["segs"]
+    g["words"] = al["words"]
+    g["phones"] = al["phones"]
+    g["states"] = al["states"]
+    g["hyp_score"] = np.int32(al["hyp_score"])
+    g["n_frames"] = np.int32(al["n_frames"])
+    wstart, wdur = phone_windows(al["words"], al["phones"])
+    g["ph_start"] = wstart
+    g["ph_dur"] = wdur
+    # dense senone scores, compallsen
+    dense = refc.score_all(feat)
+    g["senscr_sha"] = sha(dense)
+    g["senscr_rows"] = np.array([0, 1, 100, feat.shape[0] - 1], np.int32)
+    g["senscr_sample"] = dense[g["senscr_rows"]]
+    g["senscr_argmin"] = dense.argmin(1).astype(np.int32)
+    # raw top-N of the first frames (fresh history)
+    refc.reset_hist()
+    tn = []
+    for t in range(6):
+        _, topn = refc.frame_eval(feat[t], t, compallsen=True, want_topn=True)
+        tn.append(topn)
+    g["topn_norm_head"] = np.stack(tn)  # post-normalisation (cw, score)
+    wids = al["words"][:, 0]
+    chain_sen = arrays["sseq"][al["phones"][:, 1]].reshape(-1)
+    for name, r, kw in (("win", ref, dict(start=al["words"][:, 1], dur=al["words"][:, 2])),
+                        ("nowin", ref, dict()),
+                        ("win_call", refc, dict(start=al["words"][:, 1], dur=al["words"][:, 2]))):
+        res = r.state_align(feat, wids, clear_active=True, want_tokens=True, want_senscr=True, **kw)
+        g[name + "_rv"] = np.int32(res["rv"])
+        g[name + "_best"] = np.int32(res["best_score"])
+        g[name + "_states"] = res["states"]
+        g[name + "_phones"] = res["phones"]
+        g[name + "_words"] = res["words"]
+        g[name + "_tokens_sha"] = sha(res["tokens"])
+        g[name + "_tokens_head"] = res["tokens"][:4]
+        g[name + "_senscr_sha"] = sha(res["senscr"])
+        g[name + "_chain_scr"] = res["senscr"][:, chain_sen]
+    ref.close()
+    refc.close()
+    np.savez_compressed(os.path.join(OUT, "align_%s.npz" % lang), **g)
+    print(lang, "frames", feat.shape[0], "phones", len(al["phones"]), "hyp", al["hyp_score"])
+    return g
+
+
+def synthetic(lang="en-us", seed=20261017):
+    """Seeded random utterances through the reference: scoring in both modes plus
+    alignment of random phone chains (no dictionary involved)."""
+    hmm = os.path.join(MODELS, lang)
+    ref = Ref(hmm)
+    refc = Ref(hmm, compallsen=True)
+    rs = np.random.RandomState(seed)
+    arrays = ref.model_arrays()
+    mean = arrays["mean"]
+    g = {}
+    feats = []
+    lens = [1, 7, 40, 33]
+    for u, T in enumerate(lens):
+        # draw frames around randomly chosen Gaussians so the scores are in a realistic range
+        cb = rs.randint(0, ref.n_mgau, T)
+        dn = rs.randint(0, ref.n_density, T)
+        x = np.stack([np.concatenate([mean[cb[t], f, dn[t]] for f in range(ref.n_feat)]) for t in range(T)])
+        x = (x + rs.normal(0, 0.7, x.shape)).astype(np.float32)
+        feats.append(x)
+        g["feat%d" % u] = x
+        refc.reset_hist()
+        d = refc.score_all(x)
+        g["senscr_sha%d" % u] = sha(d)
+        g["senscr_head%d" % u] = d[:2, :64]
+    # hmm_vit_eval known answers
+    n_case = 256
+    st_in = np.zeros((n_case, 12), np.int32)
+    st_out = np.zeros((n_case, 12), np.int32)
+    best = np.zeros(n_case, np.int32)
+    senids = np.zeros((n_case, 3), np.uint16)
+    tmats = rs.randint(0, ref.n_tmat, n_case).astype(np.int32)
+    senscr = rs.randint(0, 400, (n_case, ref.n_sen)).astype(np.int16)
+    W = -536870912
+    for i in range(n_case):
+        st = np.full(12, W, np.int32)
+        st[5:10] = -1
+        st[11] = -1
+        k = rs.randint(0, 4)  # how many states are alive
+        for j in range(min(k, 3)):
+            st[j] = -int(rs.randint(0, 50000))
+            st[5 + j] = int(rs.randint(0, 200))
+        if rs.rand() < 0.15:
+            st[rs.randint(0, 3)] = W + int(rs.randint(0, 300))  # clamp region
+        if rs.rand() < 0.2 and k >= 2:
+            st[1] = st[0]  # provoke ties
+        if rs.rand() < 0.3:
+            st[10] = -int(rs.randint(0, 50000))
+            st[11] = int(rs.randint(0, 200))
+        senids[i] = rs.randint(0, ref.n_sen, 3)
+        st_in[i] = st
+        best[i], st_out[i] = ref.hmm_vit_eval(3, int(tmats[i]), senids[i], senscr[i], st)
+    g.update(hmm_st_in=st_in, hmm_st_out=st_out, hmm_best=best, hmm_senid=senids, hmm_tmat=tmats,
+             hmm_senscr_seed=np.int64(seed + 1))
+    # store the senscr rows only for the senones used (3 per case)
+    g["hmm_senscr3"] = np.take_along_axis(senscr, senids.astype(np.int64), 1)
+    ref.close()
+    refc.close()
+    np.savez_compressed(os.path.join(OUT, "synthetic_%s.npz" % lang), **g)
+    print("synthetic", lang, lens)
+
+
+def main():
+    if not available():
+        raise SystemExit("oracle/_ref/libssref.so missing: run `make -C oracle ref` first")
+    os.makedirs(OUT, exist_ok=True)
+    utterance("en-us", "goforward.raw", "go forward ten meters")
+    utterance("fr-fr", "goforward_fr.raw", "avance de dix mètres")
+    synthetic("en-us")
+
+
+if __name__ == "__main__":
+    main()
