@@ -188,6 +188,14 @@ int64_t ssb_score_batch(ssb_model_t *m, const float *feat, const int64_t *frame_
 int64_t ssb_topn_batch(ssb_model_t *m, const float *feat, const int64_t *frame_off,
                        int32_t n_utts, uint8_t *cw, int32_t *score);
 
+/* Verification hook of the tensor-core scorer (gmm_topn_tc.cu): ssb_topn_batch plus the TF32
+ * screening scores approx [frames][mgau][feat][n_density], their per-row error bound
+ * eps [frames][mgau][feat] (|approx - exact fp32 distance| <= eps is what makes the screening
+ * safe) and counters {exact evaluations of scan survivors, scanned (utterance, frame,
+ * codebook-stream) steps}.  Any of approx/eps/counters may be NULL, not all. */
+int64_t ssb_tc_probe(ssb_model_t *m, const float *feat, const int64_t *frame_off, int32_t n_utts,
+                     uint8_t *cw, int32_t *score, float *approx, float *eps, int64_t *counters);
+
 /* single HMM step on the device (ref: src/hmm.c:482-567); st = score[5] hist[5]
  * out_score out_hist, updated in place; returns best score via *best */
 int ssb_hmm_vit_eval(ssb_model_t *m, int32_t n_emit, int32_t tmatid, const uint16_t *senid,

@@ -24,7 +24,7 @@ WORST_SCORE = -536870912  # ref: include/soundswallower/hmm.h:80
 MODEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "model")
 
 __all__ = ["AcousticModel", "PtmMgau", "StateAlignBatch", "align_batch", "score_batch",
-           "topn_batch", "hmm_vit_eval", "windows", "plan_chain", "propagate", "flags2list", "device_count",
+           "topn_batch", "tc_probe", "hmm_vit_eval", "windows", "plan_chain", "propagate", "flags2list", "device_count",
            "SsbError", "Config", "MODEL_DIR", "INT_MAX", "WORST_SCORE"]
 
 
@@ -400,6 +400,27 @@ def topn_batch(model, feats):
     _lib.check(int(n), "ssb_topn_batch")
     return ([cw[off[i]:off[i + 1]] for i in range(len(feats))],
             [sc[off[i]:off[i + 1]] for i in range(len(feats))])
+
+
+def tc_probe(model, feats):
+    """Tensor-core scorer verification: returns (cw, score, approx, eps, counters) with
+    approx [frames][mgau][feat][n_density] the TF32 screening scores and eps
+    [frames][mgau][feat] their guaranteed error bound."""
+    feats = [np.ascontiguousarray(f, np.float32).reshape(-1, model.blk) for f in feats]
+    off = np.zeros(len(feats) + 1, np.int64)
+    for i, f in enumerate(feats):
+        off[i + 1] = off[i] + f.shape[0]
+    feat = np.concatenate(feats) if feats else np.zeros((0, model.blk), np.float32)
+    G = int(off[-1])
+    cw = np.zeros((G, model.n_mgau, model.n_feat, model.topn), np.uint8)
+    sc = np.zeros((G, model.n_mgau, model.n_feat, model.topn), np.int32)
+    approx = np.zeros((G, model.n_mgau, model.n_feat, model.n_density), np.float32)
+    eps = np.zeros((G, model.n_mgau, model.n_feat), np.float32)
+    cnt = np.zeros(2, np.int64)
+    n = model.lib.ssb_tc_probe(model.h, _ptr(feat), _ptr(off), len(feats), _ptr(cw), _ptr(sc),
+                               _ptr(approx), _ptr(eps), _ptr(cnt))
+    _lib.check(int(n), "ssb_tc_probe")
+    return cw, sc, approx, eps, dict(exact_evals=int(cnt[0]), scan_steps=int(cnt[1]))
 
 
 def hmm_vit_eval(model, tmatid, senid, senscr, st):

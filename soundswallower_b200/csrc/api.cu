@@ -4,11 +4,13 @@
 // No CPU fallback: every compute entry point needs a CUDA device.
 #include <algorithm>
 #include <climits>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "device.cuh"
@@ -222,6 +224,54 @@ static int model_to_device(ssb_model_s *m)
             cb_sen[at[h.sen2cb[s]]++] = (uint16_t)s;
     }
     d.max_cb_sen = max_cb;
+    // operands of the tensor-core screening GEMM (gmm_topn_tc.cu), double precision -> TF32
+    std::vector<float> gB, gAux;
+    bool tc_shape = h.n_density == 128;
+    for (int f = 0; f < h.n_feat; ++f)
+        tc_shape = tc_shape && h.featlen[f] == 13;
+    if (tc_shape) {
+        auto tf32 = [](double x) {
+            float v = (float)x;
+            uint32_t b;
+            std::memcpy(&b, &v, 4);
+            b = (b + 0x1000u) & 0xFFFFE000u;  // round to nearest (ties away), 10-bit mantissa
+            std::memcpy(&v, &b, 4);
+            return v;
+        };
+        const int CS = h.n_mgau * h.n_feat, L = 13, ND = 128, K = 32;
+        gB.assign((size_t)CS * ND * K, 0.f);
+        gAux.assign((size_t)CS * 48, 0.f);
+        for (int cs = 0; cs < CS; ++cs) {
+            const float *mu = h.mean.data() + h.gau_off[cs];
+            const float *pv = h.var.data() + h.gau_off[cs];
+            const float *dt = h.det.data() + (size_t)cs * ND;
+            float *B = gB.data() + (size_t)cs * ND * K;
+            float *aux = gAux.data() + (size_t)cs * 48;
+            for (int j = 0; j < L; ++j) {
+                double c = 0;
+                for (int n = 0; n < ND; ++n)
+                    c += mu[n * L + j];
+                aux[j] = (float)(c / ND);  // the value the kernel subtracts, in fp32
+            }
+            for (int n = 0; n < ND; ++n) {
+                double cst = dt[n];
+                for (int j = 0; j < L; ++j) {
+                    double mc = (double)mu[n * L + j] - (double)aux[j], v = pv[n * L + j];
+                    B[n * K + j] = tf32(2.0 * mc * v);
+                    B[n * K + L + j] = tf32(-v);
+                    cst -= mc * mc * v;
+                    aux[13 + j] = std::max(aux[13 + j], std::fabs(B[n * K + j]));
+                    aux[26 + j] = std::max(aux[26 + j], std::fabs(B[n * K + L + j]));
+                }
+                float hi = tf32(cst);
+                B[n * K + 26] = hi;
+                B[n * K + 27] = tf32(cst - (double)hi);
+                aux[39] = std::max(aux[39], (float)std::fabs(cst));
+            }
+        }
+        if (!(d.gB = to_device(m, gB)) || !(d.gAux = to_device(m, gAux)))
+            return -1;
+    }
     std::vector<uint8_t> lut(h.lut8, h.lut8 + 256);
     if (!(d.gau = to_device(m, gau)) || !(d.mixw = to_device(m, h.mixw))
         || !(d.sen2cb = to_device(m, h.sen2cb)) || !(d.sseq = to_device(m, h.sseq))
@@ -348,26 +398,6 @@ static void decode_active(const uint8_t *list, int n, std::vector<uint16_t> &out
     for (int i = 0; i < n; ++i) {
         last += list[i];
         out.push_back((uint16_t)last);
-    }
-}
-
-// senone ids the scorer evaluates for a flagged set (ascending `flags`), bridging included
-static void flags_to_eval_list(const std::vector<uint8_t> &flag, int n_sen,
-                               std::vector<uint16_t> &out)
-{
-    out.clear();
-    int last = 0;
-    for (int s = 0; s < n_sen; ++s) {
-        if (!flag[s])
-            continue;
-        int delta = s - last;
-        while (delta > 255) {
-            last += 255;
-            delta -= 255;
-            out.push_back((uint16_t)last);
-        }
-        out.push_back((uint16_t)s);
-        last = s;
     }
 }
 
@@ -655,6 +685,159 @@ extern "C" int ssb_plan_chain(int32_t np, int32_t T, const int32_t *sf, const in
     return 0;
 }
 
+// ---- host planner --------------------------------------------------------------------------
+// Per-utterance plan pieces produced by one worker for a contiguous range of utterances;
+// offsets are local to the piece and rebased when the pieces are concatenated.
+namespace {
+struct PlanPiece {
+    std::vector<int32_t> ep_count, ep_start, ep_slot_len, us_count;
+    std::vector<uint32_t> ep_cbmask;
+    std::vector<uint16_t> ep_slot, usen;
+    int max_union = 0;
+    int64_t active_sen_frames = 0, scanned_cb_frames = 0;
+    std::string error;
+};
+
+struct PlanScratch {
+    std::vector<uint8_t> mark, umark;   // [n_sen] active / in-union flags, reset sparsely
+    std::vector<uint16_t> act, uni, slot_of, ev;
+    std::vector<int32_t> ev_off;
+    explicit PlanScratch(int n_sen) : mark(n_sen, 0), umark(n_sen, 0), slot_of(n_sen, 0) {}
+};
+
+// senone ids the scorer evaluates for the sorted active set `act`: acmod_flags2list's uint8
+// delta list bridges gaps above 255 with real entries (ref: src/acmod.c:947-999)
+inline void eval_list_from_sorted(const std::vector<uint16_t> &act, std::vector<uint16_t> &out)
+{
+    int last = 0;
+    for (uint16_t s : act) {
+        int delta = (int)s - last;
+        while (delta > 255) {
+            last += 255;
+            delta -= 255;
+            out.push_back((uint16_t)last);
+        }
+        out.push_back(s);
+        last = s;
+    }
+}
+
+// Plans utterances [u0, u1).  enter[] and st_slot[] are written in place (disjoint ranges).
+void plan_range(const HostModel &h, const ssb_align_in_t *in, const std::vector<int64_t> &frame_off,
+                const std::vector<int64_t> &phone_off, int u0, int u1, int32_t *enter_all,
+                uint16_t *st_slot_all, PlanPiece &out)
+{
+    const int E = h.n_emit, n_sen = h.n_sen, nw = (n_sen + 31) / 32;
+    PlanScratch S(n_sen);
+    for (int u = u0; u < u1; ++u) {
+        const int64_t p0 = phone_off[u];
+        const int T = (int)(frame_off[u + 1] - frame_off[u]);
+        const int np = (int)(phone_off[u + 1] - p0);
+        const int32_t *ssid = in->ssid + p0, *sf = in->sf + p0, *ef = in->ef + p0;
+        int32_t *enter = enter_all + p0;
+        uint16_t *st_slot = st_slot_all + p0 * E;
+        plan_enter(np, T, sf, ef, enter);
+        if (in->compallsen) {
+            out.ep_count.push_back(0);
+            out.us_count.push_back(0);
+            out.active_sen_frames += (int64_t)T * n_sen;
+            out.scanned_cb_frames += (int64_t)T * h.n_mgau;
+            for (int i = 0; i < np * E; ++i)
+                st_slot[i] = 0;
+            continue;
+        }
+        // epochs: the active senone set only grows (ref: src/state_align_search.c:186-188)
+        S.act.clear();
+        S.uni.clear();
+        S.ev.clear();
+        S.ev_off.assign(1, 0);
+        if (in->init_active) {
+            const uint32_t *bits = in->init_active + (size_t)u * nw;
+            for (int w = 0; w < nw; ++w)
+                for (uint32_t x = bits[w]; x; x &= x - 1) {
+                    int s = w * 32 + __builtin_ctz(x);
+                    if (s < n_sen && !S.mark[s]) {
+                        S.mark[s] = 1;
+                        S.act.push_back((uint16_t)s);
+                    }
+                }
+        }
+        const size_t ep_first = out.ep_start.size();
+        int n_ep = 0;
+        // enter[] is non-decreasing over the entered prefix of the chain
+        int i = 0;
+        while (i < np && enter[i] >= 0 && enter[i] < T) {
+            const int32_t start = enter[i];
+            bool grew = n_ep == 0;
+            const size_t before = S.act.size();
+            for (; i < np && enter[i] == start; ++i)
+                for (int j = 0; j < E; ++j) {
+                    const int s = h.sseq[(size_t)ssid[i] * E + j];
+                    if (!S.mark[s]) {
+                        S.mark[s] = 1;
+                        S.act.push_back((uint16_t)s);
+                        grew = true;
+                    }
+                }
+            if (!grew)
+                continue;
+            if (S.act.size() != before || n_ep == 0)
+                std::sort(S.act.begin(), S.act.end());
+            const size_t e0 = S.ev.size();
+            eval_list_from_sorted(S.act, S.ev);
+            S.ev_off.push_back((int32_t)S.ev.size());
+            uint32_t mask[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (size_t k = e0; k < S.ev.size(); ++k) {
+                const uint16_t s = S.ev[k];
+                const int cb = h.sen2cb[s];
+                mask[cb >> 5] |= 1u << (cb & 31);
+                if (!S.umark[s]) {
+                    S.umark[s] = 1;
+                    S.uni.push_back(s);
+                }
+            }
+            out.ep_start.push_back(start);
+            for (int w = 0; w < 8; ++w)
+                out.ep_cbmask.push_back(mask[w]);
+            ++n_ep;
+        }
+        // union of everything ever evaluated for this utterance -> slots
+        std::sort(S.uni.begin(), S.uni.end());
+        const int n_us = (int)S.uni.size();
+        for (int k = 0; k < n_us; ++k)
+            S.slot_of[S.uni[k]] = (uint16_t)k;
+        out.usen.insert(out.usen.end(), S.uni.begin(), S.uni.end());
+        out.us_count.push_back(n_us);
+        out.max_union = std::max(out.max_union, n_us);
+        for (int e = 0; e < n_ep; ++e) {
+            const int32_t a0 = S.ev_off[e], a1 = S.ev_off[e + 1];
+            for (int32_t k = a0; k < a1; ++k)
+                out.ep_slot.push_back(S.slot_of[S.ev[k]]);
+            out.ep_slot_len.push_back(a1 - a0);
+            const int32_t end = e + 1 < n_ep ? out.ep_start[ep_first + e + 1] : T;
+            const int32_t len = end - out.ep_start[ep_first + e];
+            int ncb = 0;
+            for (int w = 0; w < 8; ++w)
+                ncb += __builtin_popcount(out.ep_cbmask[(ep_first + e) * 8 + w]);
+            out.active_sen_frames += (int64_t)len * (a1 - a0);
+            out.scanned_cb_frames += (int64_t)len * ncb;
+        }
+        out.ep_count.push_back(n_ep);
+        // chain state -> union slot; states whose phone never becomes active read the
+        // always-zero slot n_us (the reference leaves such senone scores at 0 - best)
+        for (int q = 0; q < np; ++q)
+            for (int j = 0; j < E; ++j) {
+                const int s = h.sseq[(size_t)ssid[q] * E + j];
+                st_slot[q * E + j] = S.umark[s] ? S.slot_of[s] : (uint16_t)n_us;
+            }
+        for (uint16_t s : S.act)
+            S.mark[s] = 0;
+        for (uint16_t s : S.uni)
+            S.umark[s] = 0;
+    }
+}
+}  // namespace
+
 extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
 {
     if (!b || !in || in->n_utts < 0 || (in->n_utts > 0 && (!in->frame_off || !in->phone_off))) {
@@ -664,8 +847,7 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
     if (need_device(b->m) != 0)
         return -1;
     const HostModel &h = b->m->h;
-    const int U = in->n_utts, E = h.n_emit, n_sen = h.n_sen;
-    const int nw = (n_sen + 31) / 32;
+    const int U = in->n_utts, E = h.n_emit;
     b->ran = false;
     b->n_utts = U;
     b->compallsen = in->compallsen ? 1 : 0;
@@ -682,28 +864,17 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
         set_error("frame_off[0] and phone_off[0] must be 0");
         return -1;
     }
+    if (b->n_phones > 0 && (!in->ssid || !in->tmat || !in->sf || !in->ef)) {
+        set_error("ssb_batch_upload: chain arrays are NULL");
+        return -1;
+    }
     b->n_states = b->n_phones * E;
     b->scr_off.assign(U + 1, 0);
-    b->enter.assign((size_t)b->n_phones, -1);
     b->max_phones = b->max_union = b->max_T = 0;
-    b->n_active_sen_frames = b->n_scanned_cb_frames = 0;
-
-    std::vector<int32_t> ep_off(U + 1, 0), ep_start, ep_slot_off(1, 0), us_off(U + 1, 0);
-    std::vector<uint32_t> ep_cbmask;
-    std::vector<uint16_t> ep_slot, usen, st_slot((size_t)b->n_states, 0);
-    std::vector<uint8_t> flag(n_sen), in_union(n_sen);
-    std::vector<uint16_t> list, slot_of(n_sen);
-    std::vector<std::pair<int32_t, int>> order;  // (enter frame, phone)
-    struct Ep {
-        int32_t start;
-        std::vector<uint16_t> sen;
-        uint32_t mask[8];
-    };
-    std::vector<Ep> eps;
-
+    // ---- validation + sizes
     for (int u = 0; u < U; ++u) {
-        const int64_t f0 = b->frame_off[u], p0 = b->phone_off[u];
-        const int64_t Tl = b->frame_off[u + 1] - f0, npl = b->phone_off[u + 1] - p0;
+        const int64_t p0 = b->phone_off[u];
+        const int64_t Tl = b->frame_off[u + 1] - b->frame_off[u], npl = b->phone_off[u + 1] - p0;
         if (Tl < 0 || npl < 0 || Tl > INT32_MAX - 2 || npl * E > 0x7fffffff) {
             set_error("utterance %d: offsets must be non-decreasing", u);
             return -1;
@@ -712,8 +883,7 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
         b->max_phones = std::max(b->max_phones, np);
         b->max_T = std::max(b->max_T, T);
         b->scr_off[u + 1] = b->scr_off[u] + (int64_t)T * np * E;
-        const int32_t *ssid = in->ssid + p0, *tmat = in->tmat + p0, *sf = in->sf + p0,
-                      *ef = in->ef + p0;
+        const int32_t *ssid = in->ssid + p0, *tmat = in->tmat + p0, *ef = in->ef + p0;
         for (int i = 0; i < np; ++i) {
             if (ssid[i] < 0 || ssid[i] >= h.n_sseq || tmat[i] < 0 || tmat[i] >= h.n_tmat) {
                 set_error("utterance %d phone %d: ssid %d / tmat %d out of range", u, i, ssid[i],
@@ -728,102 +898,16 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
                           u, i);
                 return -1;
             }
-        }
-        int32_t *enter = b->enter.data() + p0;
-        plan_enter(np, T, sf, ef, enter);
-        us_off[u + 1] = us_off[u];
-        ep_off[u + 1] = ep_off[u];
-        if (b->compallsen) {
-            b->n_active_sen_frames += (int64_t)T * n_sen;
-            b->n_scanned_cb_frames += (int64_t)T * h.n_mgau;
-            for (int i = 0; i < np * E; ++i)
-                st_slot[p0 * E + i] = 0;
-            continue;
-        }
-        // epochs: the active senone set only grows (ref: src/state_align_search.c:186-188)
-        std::fill(flag.begin(), flag.end(), 0);
-        std::fill(in_union.begin(), in_union.end(), 0);
-        if (in->init_active) {
-            const uint32_t *bits = in->init_active + (size_t)u * nw;
-            for (int s = 0; s < n_sen; ++s)
-                flag[s] = (bits[s >> 5] >> (s & 31)) & 1u;
-        }
-        order.clear();
-        for (int i = 0; i < np; ++i)
-            if (enter[i] >= 0 && enter[i] < T)
-                order.emplace_back(enter[i], i);
-        std::stable_sort(order.begin(), order.end());
-        eps.clear();
-        size_t k = 0;
-        while (k < order.size()) {
-            const int32_t start = order[k].first;
-            bool grew = eps.empty();
-            for (; k < order.size() && order[k].first == start; ++k) {
-                const int i = order[k].second;
-                for (int j = 0; j < E; ++j) {
-                    int s = h.sseq[(size_t)ssid[i] * E + j];
-                    if (s >= n_sen) {
-                        set_error("utterance %d phone %d: senone id %d out of range", u, i, s);
-                        return -1;
-                    }
-                    if (!flag[s]) {
-                        flag[s] = 1;
-                        grew = true;
-                    }
+            for (int j = 0; j < E; ++j)
+                if (h.sseq[(size_t)ssid[i] * E + j] >= h.n_sen) {
+                    set_error("utterance %d phone %d: senone id out of range", u, i);
+                    return -1;
                 }
-            }
-            if (!grew)
-                continue;
-            Ep e;
-            e.start = start;
-            flags_to_eval_list(flag, n_sen, e.sen);
-            std::memset(e.mask, 0, sizeof(e.mask));
-            for (uint16_t s : e.sen) {
-                int cb = h.sen2cb[s];
-                e.mask[cb >> 5] |= 1u << (cb & 31);
-                in_union[s] = 1;
-            }
-            eps.push_back(std::move(e));
-        }
-        // union of everything ever evaluated for this utterance -> slots
-        int n_us = 0;
-        for (int s = 0; s < n_sen; ++s)
-            if (in_union[s]) {
-                slot_of[s] = (uint16_t)n_us++;
-                usen.push_back((uint16_t)s);
-            }
-        us_off[u + 1] = us_off[u] + n_us;
-        b->max_union = std::max(b->max_union, n_us);
-        for (size_t e = 0; e < eps.size(); ++e) {
-            ep_start.push_back(eps[e].start);
-            for (int w = 0; w < 8; ++w)
-                ep_cbmask.push_back(eps[e].mask[w]);
-            for (uint16_t s : eps[e].sen)
-                ep_slot.push_back(slot_of[s]);
-            ep_slot_off.push_back((int32_t)ep_slot.size());
-            const int32_t end = e + 1 < eps.size() ? eps[e + 1].start : T;
-            int ncb = 0;
-            for (int w = 0; w < 8; ++w)
-                ncb += __builtin_popcount(eps[e].mask[w]);
-            b->n_active_sen_frames += (int64_t)(end - eps[e].start) * eps[e].sen.size();
-            b->n_scanned_cb_frames += (int64_t)(end - eps[e].start) * ncb;
-        }
-        ep_off[u + 1] = ep_off[u] + (int32_t)eps.size();
-        // chain state -> union slot; states whose phone never becomes active read the
-        // always-zero slot n_us (the reference leaves such senone scores at 0 - best)
-        for (int i = 0; i < np; ++i)
-            for (int j = 0; j < E; ++j) {
-                int s = h.sseq[(size_t)ssid[i] * E + j];
-                st_slot[(p0 + i) * E + j] = in_union[s] ? slot_of[s] : (uint16_t)n_us;
-            }
-        if (ep_slot.size() > (size_t)INT32_MAX - 65536) {
-            set_error("active-list plan too large; split the batch");
-            return -1;
         }
     }
     b->n_state_frames = b->scr_off[U];
 
-    // ---- device buffers
+    // ---- device buffers; the feature copy starts now and overlaps the planning below
     cudaStream_t st = b->st;
     const int CS = h.n_mgau * h.n_feat;
     const int64_t G = b->n_frames;
@@ -859,8 +943,48 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
         set_error("ssb_batch_upload: feat is NULL");
         return -1;
     }
-    if (b->n_phones > 0 && (!in->ssid || !in->tmat || !in->sf || !in->ef)) {
-        set_error("ssb_batch_upload: chain arrays are NULL");
+
+    // ---- plan: worker threads over contiguous utterance ranges, then concatenate
+    b->enter.assign((size_t)b->n_phones, -1);
+    std::vector<uint16_t> st_slot((size_t)b->n_states, 0);
+    int n_workers = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+    n_workers = std::max(1, std::min(n_workers, U / 64));
+    std::vector<PlanPiece> pieces(n_workers);
+    {
+        std::vector<std::thread> th;
+        for (int w = 0; w < n_workers; ++w) {
+            const int u0 = (int)((int64_t)U * w / n_workers), u1 = (int)((int64_t)U * (w + 1) / n_workers);
+            if (n_workers == 1)
+                plan_range(h, in, b->frame_off, b->phone_off, u0, u1, b->enter.data(), st_slot.data(), pieces[w]);
+            else
+                th.emplace_back(plan_range, std::cref(h), in, std::cref(b->frame_off),
+                                std::cref(b->phone_off), u0, u1, b->enter.data(), st_slot.data(),
+                                std::ref(pieces[w]));
+        }
+        for (auto &t : th)
+            t.join();
+    }
+    std::vector<int32_t> ep_off(1, 0), ep_start, ep_slot_off(1, 0), us_off(1, 0);
+    std::vector<uint32_t> ep_cbmask;
+    std::vector<uint16_t> ep_slot, usen;
+    b->n_active_sen_frames = b->n_scanned_cb_frames = 0;
+    for (const PlanPiece &pc : pieces) {
+        for (int32_t c : pc.ep_count)
+            ep_off.push_back(ep_off.back() + c);
+        for (int32_t c : pc.us_count)
+            us_off.push_back(us_off.back() + c);
+        for (int32_t c : pc.ep_slot_len)
+            ep_slot_off.push_back(ep_slot_off.back() + c);
+        ep_start.insert(ep_start.end(), pc.ep_start.begin(), pc.ep_start.end());
+        ep_cbmask.insert(ep_cbmask.end(), pc.ep_cbmask.begin(), pc.ep_cbmask.end());
+        ep_slot.insert(ep_slot.end(), pc.ep_slot.begin(), pc.ep_slot.end());
+        usen.insert(usen.end(), pc.usen.begin(), pc.usen.end());
+        b->max_union = std::max(b->max_union, pc.max_union);
+        b->n_active_sen_frames += pc.active_sen_frames;
+        b->n_scanned_cb_frames += pc.scanned_cb_frames;
+    }
+    if (ep_slot.size() > (size_t)INT32_MAX - 65536) {
+        set_error("active-list plan too large; split the batch");
         return -1;
     }
     std::vector<int32_t> v_ssid(in->ssid, in->ssid + b->n_phones),
@@ -1167,26 +1291,44 @@ extern "C" int64_t ssb_score_batch(ssb_model_t *m, const float *feat, const int6
     return rv;
 }
 
-extern "C" int64_t ssb_topn_batch(ssb_model_t *m, const float *feat, const int64_t *frame_off,
-                                  int32_t n_utts, uint8_t *cw, int32_t *score)
+static int64_t topn_impl(ssb_model_t *m, const float *feat, const int64_t *frame_off,
+                         int32_t n_utts, uint8_t *cw, int32_t *score, float *approx, float *eps,
+                         int64_t *counters)
 {
     ssb_batch_t *b = ssb_batch_create(m, nullptr);
     if (!b)
         return -1;
+    const bool probe = approx || eps || counters;
+    DBuf d_approx, d_eps, d_cnt;
     int64_t rv = -1;
     do {
         if (score_prepare(b, feat, frame_off, n_utts) != 0)
             break;
         const DevModel &d = m->d;
         const int64_t G = b->n_frames;
-        const int CS = d.n_mgau * d.n_feat, N = d.topn;
+        const int CS = d.n_mgau * d.n_feat, N = d.topn, ND = d.n_density;
         if (G == 0) {
             rv = 0;
             break;
         }
-        if (launch_gmm_topn(d, b->plan, b->feat.as<float>(), G, b->tn_s.as<int4>(),
-                            b->tn_c.as<uchar4>(), b->st) != 0)
-            break;
+        if (!probe) {
+            if (launch_gmm_topn(d, b->plan, b->feat.as<float>(), G, b->tn_s.as<int4>(),
+                                b->tn_c.as<uchar4>(), b->st) != 0)
+                break;
+        } else {
+            if (!tc_supported(d)) {
+                set_error("ssb_tc_probe: model shape not supported by the tensor-core scorer");
+                break;
+            }
+            if (d_approx.ensure((size_t)G * CS * ND * 4) || d_eps.ensure((size_t)G * CS * 4)
+                || d_cnt.ensure(16))
+                break;
+            cudaMemsetAsync(d_cnt.p, 0, 16, b->st);
+            if (launch_gmm_topn_tc(d, b->plan, b->feat.as<float>(), G, b->tn_s.as<int4>(),
+                                   b->tn_c.as<uchar4>(), d_approx.as<float>(), d_eps.as<float>(),
+                                   d_cnt.as<unsigned long long>(), b->st) != 0)
+                break;
+        }
         std::vector<int4> hs((size_t)G * CS);
         std::vector<uchar4> hc((size_t)G * CS);
         if (cudaMemcpyAsync(hs.data(), b->tn_s.p, hs.size() * sizeof(int4), cudaMemcpyDeviceToHost, b->st) != cudaSuccess
@@ -1209,10 +1351,55 @@ extern "C" int64_t ssb_topn_batch(ssb_model_t *m, const float *feat, const int64
                         cw[((size_t)g * CS + cs) * N + k] = cv[k];
                 }
             }
+        if (probe) {
+            std::vector<float> ha((size_t)G * CS * ND), he((size_t)G * CS);
+            unsigned long long hcnt[2] = {0, 0};
+            if (cudaMemcpy(ha.data(), d_approx.p, ha.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess
+                || cudaMemcpy(he.data(), d_eps.p, he.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess
+                || cudaMemcpy(hcnt, d_cnt.p, 16, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                set_error("ssb_tc_probe: %s", cudaGetErrorString(cudaGetLastError()));
+                break;
+            }
+            for (int64_t g = 0; g < G; ++g)
+                for (int cs = 0; cs < CS; ++cs) {
+                    if (approx)
+                        std::memcpy(approx + ((size_t)g * CS + cs) * ND,
+                                    ha.data() + ((size_t)cs * G + g) * ND, (size_t)ND * 4);
+                    if (eps)
+                        eps[(size_t)g * CS + cs] = he[(size_t)cs * G + g];
+                }
+            if (counters) {
+                counters[0] = (int64_t)hcnt[0];
+                counters[1] = (int64_t)hcnt[1];
+            }
+        }
         rv = G;
     } while (0);
+    d_approx.release();
+    d_eps.release();
+    d_cnt.release();
     ssb_batch_free(b);
     return rv;
+}
+
+extern "C" int64_t ssb_topn_batch(ssb_model_t *m, const float *feat, const int64_t *frame_off,
+                                  int32_t n_utts, uint8_t *cw, int32_t *score)
+{
+    return topn_impl(m, feat, frame_off, n_utts, cw, score, nullptr, nullptr, nullptr);
+}
+
+extern "C" int64_t ssb_tc_probe(ssb_model_t *m, const float *feat, const int64_t *frame_off,
+                                int32_t n_utts, uint8_t *cw, int32_t *score, float *approx,
+                                float *eps, int64_t *counters)
+{
+    static float dummy_eps;
+    if (!approx && !eps && !counters)
+        eps = &dummy_eps, (void)0;
+    if (eps == &dummy_eps) {
+        set_error("ssb_tc_probe: nothing requested");
+        return -1;
+    }
+    return topn_impl(m, feat, frame_off, n_utts, cw, score, approx, eps, counters);
 }
 
 extern "C" int ssb_hmm_vit_eval(ssb_model_t *m, int32_t n_emit, int32_t tmatid,

@@ -42,6 +42,11 @@ struct DevModel {
     const int32_t *cb_sen_off;       // [n_mgau+1]
     const uint16_t *cb_sen;          // [n_sen] senone ids sorted by (codebook, id)
     int32_t max_cb_sen;
+    // tensor-core screening operands (gmm_topn_tc.cu): per codebook-stream
+    //   gB   [cs][128][32] TF32-rounded rows [2 mu' v (13) | -v (13) | c_hi | c_lo | 0 x4]
+    //   gAux [cs][48]      centre[13] | max|2 mu' v|[13] | max v[13] | max|c|
+    const float *gB;
+    const float *gAux;
 };
 
 __host__ __device__ inline int64_t gau_offset(const DevModel &m, int cb, int f)
@@ -75,6 +80,12 @@ struct DevPlan {
 // K1: stateful top-N of every (utterance, codebook, stream) chain.
 int launch_gmm_topn(const DevModel &m, const DevPlan &p, const float *feat, int64_t n_frames,
                     int4 *tn_score, uchar4 *tn_cw, cudaStream_t st);
+// K1 on the tensor cores (tcgen05 TF32 screening + exact FP32 re-scoring); same results.
+// dbg_* may be NULL: approx [cs][frame][128], eps [cs][frame], counters [2].
+bool tc_supported(const DevModel &m);
+int launch_gmm_topn_tc(const DevModel &m, const DevPlan &p, const float *feat, int64_t n_frames,
+                       int4 *tn_score, uchar4 *tn_cw, float *dbg_approx, float *dbg_eps,
+                       unsigned long long *dbg_counters, cudaStream_t st);
 // K2 (active lists): normalise, mix, subtract best, gather to chain states.
 // max_union counts the always-zero slot that inactive chain states read.
 int launch_senone_mix_active(const DevModel &m, const DevPlan &p, const int4 *tn_score,

@@ -17,6 +17,9 @@
 // dependence of the reference (frame t needs frame t-1's list) costs nothing,
 // there are no cross-lane operations, and the FP32 pipe is the binding unit:
 // 4 dependent-free FP32 ops per (density, dimension).
+#include <cstdlib>
+#include <cstring>
+
 #include "device.cuh"
 
 namespace ssb {
@@ -279,6 +282,12 @@ int launch_gmm_topn(const DevModel &m, const DevPlan &p, const float *feat, int6
 {
     if (p.n_utts == 0 || n_frames == 0)
         return 0;
+    // default: tensor-core screening kernel (gmm_topn_tc.cu); SSB_K1=fp32 keeps the plain
+    // CUDA-core scan below (same results, used for A/B timing and as the generic-shape path)
+    const char *force = getenv("SSB_K1");
+    if (tc_supported(m) && !(force && strcmp(force, "fp32") == 0))
+        return launch_gmm_topn_tc(m, p, feat, n_frames, tn_score, tn_cw, nullptr, nullptr, nullptr,
+                                  st);
     bool all13 = true;
     for (int f = 0; f < m.n_feat; ++f)
         all13 = all13 && m.featlen[f] == 13;

@@ -33,24 +33,28 @@ __device__ __forceinline__ int logadd8(int a, int b, const uint8_t *lut)
 }
 
 constexpr int K2_THREADS = 256;
-constexpr int K2_F = 8;           // frames per tile
-constexpr int K2_CHUNK = 128;     // frames per CTA
+constexpr int K2_WARPS = K2_THREADS / 32;
+constexpr int K2_CS_PER_LANE = 4;  // codebook-streams per lane: CS <= 128
 
 // ---------------------------------------------------------------- active lists
+// CTA = (utterance, run of frames); the mixture-weight columns of the utterance's senone
+// union are staged once.  Then every WARP takes frames on its own (t = t_begin + warp,
+// +8, ...): lanes over codebook-streams for the normaliser, lanes over active senones for
+// the mixing, lanes over chain states for the gather -- only __syncwarp inside the loop.
 template <bool STAGED>
 __global__ void __launch_bounds__(K2_THREADS)
 senone_mix_active_kernel(DevModel m, DevPlan p, const int4 *__restrict__ tn_s,
-                         const uchar4 *__restrict__ tn_c, int64_t G, int W,
+                         const uchar4 *__restrict__ tn_c, int64_t G, int W, int chunk,
                          int16_t *__restrict__ chain_scr)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const int u = blockIdx.y;
     const int64_t g0 = p.frame_off[u];
     const int T = (int)(p.frame_off[u + 1] - g0);
-    const int t_begin = blockIdx.x * K2_CHUNK;
+    const int t_begin = blockIdx.x * chunk;
     if (t_begin >= T)
         return;
-    const int t_end = min(T, t_begin + K2_CHUNK);
+    const int t_end = min(T, t_begin + chunk);
     const int CS = m.n_mgau * m.n_feat;
     const int ND = m.n_density, NF = m.n_feat, N = m.topn;
     const int us0 = p.us_off[u], n_us = p.us_off[u + 1] - us0;
@@ -60,17 +64,16 @@ senone_mix_active_kernel(DevModel m, DevPlan p, const int4 *__restrict__ tn_s,
     const int e0 = p.ep_off[u], e1 = p.ep_off[u + 1];
     if (ns == 0 || e0 == e1)
         return;  // nothing to score for this utterance (uniform for the whole CTA)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // shared layout
-    uint8_t *lut = smem;                                        // 256
-    uchar4 *tile_s = reinterpret_cast<uchar4 *>(smem + 256);    // [F][CS]
-    uchar4 *tile_c = tile_s + K2_F * CS;                        // [F][CS]
-    int *norm = reinterpret_cast<int *>(tile_c + K2_F * CS);    // [F][SSB_MAX_FEAT]
-    int *best = norm + K2_F * SSB_MAX_FEAT;                     // [F]
-    int *ep_of = best + K2_F;                                   // [F]
-    int16_t *scr = reinterpret_cast<int16_t *>(ep_of + K2_F);   // [F][W]
-    uint8_t *ucb = reinterpret_cast<uint8_t *>(scr + K2_F * W); // [W] codebook of union slot
-    uint8_t *mw = ucb + ((W + 15) & ~15);                       // [NF*ND][W] staged columns
+    const int CSP = (CS + 3) & ~3;
+    uint8_t *lut = smem;                                                 // 256
+    uchar4 *wt_s = reinterpret_cast<uchar4 *>(smem + 256) + warp * CSP;  // [warps][CSP]
+    uchar4 *wt_c = reinterpret_cast<uchar4 *>(smem + 256) + (K2_WARPS + warp) * CSP;
+    int16_t *wscr = reinterpret_cast<int16_t *>(smem + 256 + (size_t)2 * K2_WARPS * CSP * 4) + warp * W;
+    uint8_t *ucb = smem + 256 + (size_t)2 * K2_WARPS * CSP * 4 + (size_t)K2_WARPS * W * 2;  // [W]
+    uint8_t *mw = ucb + ((W + 15) & ~15);                                // [NF*ND][W] staged columns
 
     for (int i = threadIdx.x; i < 256; i += blockDim.x)
         lut[i] = m.lut8[i];
@@ -85,122 +88,129 @@ senone_mix_active_kernel(DevModel m, DevPlan p, const int4 *__restrict__ tn_s,
     }
     __syncthreads();
 
-    for (int tt = t_begin; tt < t_end; tt += K2_F) {
-        const int nf = min(K2_F, t_end - tt);
-        // epoch of each frame of the tile; reset reducers
-        if (threadIdx.x < K2_F) {
-            int fr = threadIdx.x;
-            int e = e0;
-            if (fr < nf) {
-                while (e + 1 < e1 && p.ep_start[e + 1] <= tt + fr)
-                    ++e;
-            }
-            ep_of[fr] = e;
-            best[fr] = INT32_MAX;
-            for (int f = 0; f < NF; ++f)
-                norm[fr * SSB_MAX_FEAT + f] = WORST_SCORE;
+    int e = e0;
+    uint32_t okmask = 0;  // bit it: codebook of this lane's it-th codebook-stream is active
+    int sl0 = 0, na = 0;
+    bool fresh = true;
+    for (int t = t_begin + warp; t < t_end; t += K2_WARPS) {
+        while (e + 1 < e1 && p.ep_start[e + 1] <= t) {
+            ++e;
+            fresh = true;
         }
-        for (int i = threadIdx.x; i < K2_F * W; i += blockDim.x)
-            scr[i] = 0;
-        __syncthreads();
-        // A: raw top-N of the active codebooks -> per-stream normaliser
-        constexpr int ITEMS = 4;  // (K2_F * CS) / K2_THREADS rounded up for CS <= 128
-        int4 rs[ITEMS];
-        uchar4 rc[ITEMS];
-        bool ok[ITEMS];
+        if (fresh) {
+            okmask = 0;
 #pragma unroll
-        for (int it = 0; it < ITEMS; ++it) {
-            int idx = threadIdx.x + it * K2_THREADS;
-            int fr = idx % K2_F, cs = idx / K2_F;
-            ok[it] = false;
-            if (cs < CS && fr < nf) {
-                int cb = cs / NF, f = cs - cb * NF;
-                int e = ep_of[fr];
-                if ((p.ep_cbmask[(int64_t)e * 8 + (cb >> 5)] >> (cb & 31)) & 1u) {
-                    int64_t g = (int64_t)cs * G + g0 + tt + fr;
-                    rs[it] = tn_s[g];
-                    rc[it] = tn_c[g];
-                    ok[it] = true;
-                    atomicMax(&norm[fr * SSB_MAX_FEAT + f], rs[it].x >> SENSCR_SHIFT);
+            for (int it = 0; it < K2_CS_PER_LANE; ++it) {
+                const int cs = lane + 32 * it;
+                if (cs < CS) {
+                    const int cb = cs / NF;
+                    okmask |= ((p.ep_cbmask[(int64_t)e * 8 + (cb >> 5)] >> (cb & 31)) & 1u) << it;
                 }
             }
+            sl0 = p.ep_slot_off[e];
+            na = p.ep_slot_off[e + 1] - sl0;
+            fresh = false;
         }
-        __syncthreads();
-        // B: normalise, clamp, park in shared memory
+        // A: raw top-N of the active codebooks, per-stream normaliser over them
+        int4 rs[K2_CS_PER_LANE];
+        uchar4 rc[K2_CS_PER_LANE];
+        bool ok[K2_CS_PER_LANE];
+        int nm[SSB_MAX_FEAT];
 #pragma unroll
-        for (int it = 0; it < ITEMS; ++it) {
-            int idx = threadIdx.x + it * K2_THREADS;
-            int fr = idx % K2_F, cs = idx / K2_F;
+        for (int f = 0; f < SSB_MAX_FEAT; ++f)
+            nm[f] = WORST_SCORE;
+#pragma unroll
+        for (int it = 0; it < K2_CS_PER_LANE; ++it) {
+            const int cs = lane + 32 * it;
+            ok[it] = (okmask >> it) & 1u;
             if (ok[it]) {
-                int f = cs % NF;
-                int nm = norm[fr * SSB_MAX_FEAT + f];
-                uchar4 q;
-                q.x = (unsigned char)min(MAX_NEG_ASCR, nm - (rs[it].x >> SENSCR_SHIFT));
-                q.y = (unsigned char)min(MAX_NEG_ASCR, nm - (rs[it].y >> SENSCR_SHIFT));
-                q.z = (unsigned char)min(MAX_NEG_ASCR, nm - (rs[it].z >> SENSCR_SHIFT));
-                q.w = (unsigned char)min(MAX_NEG_ASCR, nm - (rs[it].w >> SENSCR_SHIFT));
-                tile_s[fr * CS + cs] = q;
-                tile_c[fr * CS + cs] = rc[it];
+                const int64_t g = (int64_t)cs * G + g0 + t;
+                rs[it] = tn_s[g];
+                rc[it] = tn_c[g];
             }
         }
-        __syncthreads();
-        // C: one (frame, active senone) per thread
-        for (int fr = 0; fr < nf; ++fr) {
-            const int e = ep_of[fr];
-            const int sl0 = p.ep_slot_off[e], na = p.ep_slot_off[e + 1] - sl0;
-            int local_best = INT32_MAX;
-            for (int i = threadIdx.x; i < na; i += blockDim.x) {
-                const int slot = p.ep_slot[sl0 + i];
-                const int cb = ucb[slot];
-                int ascore = 0;
-                for (int f = 0; f < NF; ++f) {
-                    const uchar4 sv = tile_s[fr * CS + cb * NF + f];
-                    const uchar4 cv = tile_c[fr * CS + cb * NF + f];
-                    const int sc[4] = {sv.x, sv.y, sv.z, sv.w};
-                    const int cw[4] = {cv.x, cv.y, cv.z, cv.w};
-                    int fden = 0;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (k < N) {
-                            int w;
-                            if (STAGED)
-                                w = mw[(f * ND + cw[k]) * W + slot];
-                            else
-                                w = m.mixw[(int64_t)(f * ND + cw[k]) * m.n_sen
-                                           + p.usen[us0 + slot]];
-                            int v = w + sc[k];
-                            fden = k == 0 ? v : logadd8(fden, v, lut);
-                        }
-                    }
-                    ascore += fden;
-                }
-                scr[fr * W + slot] = (int16_t)ascore;
-                local_best = min(local_best, ascore);
+        for (int it = 0; it < K2_CS_PER_LANE; ++it)
+            if (ok[it]) {
+                const int f = (lane + 32 * it) % NF;
+                const int v = rs[it].x >> SENSCR_SHIFT;
+#pragma unroll
+                for (int ff = 0; ff < SSB_MAX_FEAT; ++ff)
+                    if (ff == f)
+                        nm[ff] = max(nm[ff], v);
             }
-            // warp-reduce then one shared atomic per warp
+#pragma unroll
+        for (int f = 0; f < SSB_MAX_FEAT; ++f)
             for (int o = 16; o > 0; o >>= 1)
-                local_best = min(local_best, __shfl_xor_sync(0xffffffffu, local_best, o));
-            if ((threadIdx.x & 31) == 0 && local_best != INT32_MAX)
-                atomicMin(&best[fr], local_best);
+                nm[f] = max(nm[f], __shfl_xor_sync(0xffffffffu, nm[f], o));
+        // B: normalise, clamp, park in this warp's tile; clear the warp's score row
+#pragma unroll
+        for (int it = 0; it < K2_CS_PER_LANE; ++it)
+            if (ok[it]) {
+                const int cs = lane + 32 * it, f = cs % NF;
+                int n0 = nm[0];
+#pragma unroll
+                for (int ff = 1; ff < SSB_MAX_FEAT; ++ff)
+                    if (ff == f)
+                        n0 = nm[ff];
+                uchar4 q;
+                q.x = (unsigned char)min(MAX_NEG_ASCR, n0 - (rs[it].x >> SENSCR_SHIFT));
+                q.y = (unsigned char)min(MAX_NEG_ASCR, n0 - (rs[it].y >> SENSCR_SHIFT));
+                q.z = (unsigned char)min(MAX_NEG_ASCR, n0 - (rs[it].z >> SENSCR_SHIFT));
+                q.w = (unsigned char)min(MAX_NEG_ASCR, n0 - (rs[it].w >> SENSCR_SHIFT));
+                wt_s[cs] = q;
+                wt_c[cs] = rc[it];
+            }
+        for (int i = lane; i < W / 2; i += 32)
+            reinterpret_cast<uint32_t *>(wscr)[i] = 0u;
+        __syncwarp();
+        // C: active senones of this frame's epoch
+        int local_best = INT32_MAX;
+        for (int i = lane; i < na; i += 32) {
+            const int slot = p.ep_slot[sl0 + i];
+            const int cb = ucb[slot];
+            int ascore = 0;
+            for (int f = 0; f < NF; ++f) {
+                const uchar4 sv = wt_s[cb * NF + f];
+                const uchar4 cv = wt_c[cb * NF + f];
+                const int sc[4] = {sv.x, sv.y, sv.z, sv.w};
+                const int cw[4] = {cv.x, cv.y, cv.z, cv.w};
+                int fden = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k < N) {
+                        int w;
+                        if (STAGED)
+                            w = mw[(f * ND + cw[k]) * W + slot];
+                        else
+                            w = m.mixw[(int64_t)(f * ND + cw[k]) * m.n_sen + p.usen[us0 + slot]];
+                        int v = w + sc[k];
+                        fden = k == 0 ? v : logadd8(fden, v, lut);
+                    }
+                }
+                ascore += fden;
+            }
+            wscr[slot] = (int16_t)ascore;
+            local_best = min(local_best, ascore);
         }
-        __syncthreads();
+        for (int o = 16; o > 0; o >>= 1)
+            local_best = min(local_best, __shfl_xor_sync(0xffffffffu, local_best, o));
+        __syncwarp();
         // D: gather to chain states, subtract the frame's best (ref :398-400)
         {
-            int16_t *dst = chain_scr + p.scr_off[u] + (int64_t)tt * ns;
-            for (int idx = threadIdx.x; idx < nf * ns; idx += blockDim.x) {
-                int fr = idx / ns, si = idx - fr * ns;
-                dst[idx] = (int16_t)(scr[fr * W + st_slot[si]] - (int16_t)best[fr]);
-            }
+            const int16_t b16 = (int16_t)local_best;
+            int16_t *dst = chain_scr + p.scr_off[u] + (int64_t)t * ns;
+            for (int si = lane; si < ns; si += 32)
+                dst[si] = (int16_t)(wscr[st_slot[si]] - b16);
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
 static size_t k2_active_smem(const DevModel &m, int W, bool staged)
 {
-    int CS = m.n_mgau * m.n_feat;
-    size_t b = 256 + (size_t)2 * K2_F * CS * 4 + (size_t)K2_F * SSB_MAX_FEAT * 4 + K2_F * 4
-               + K2_F * 4 + (size_t)K2_F * W * 2 + ((W + 15) & ~15);
+    int CSP = (m.n_mgau * m.n_feat + 3) & ~3;
+    size_t b = 256 + (size_t)2 * K2_WARPS * CSP * 4 + (size_t)K2_WARPS * W * 2 + ((W + 15) & ~15);
     if (staged)
         b += (size_t)m.n_feat * m.n_density * W;
     return b + 16;
@@ -212,9 +222,9 @@ int launch_senone_mix_active(const DevModel &m, const DevPlan &p, const int4 *tn
 {
     if (p.n_utts == 0 || n_frames == 0)
         return 0;
-    if (m.n_mgau * m.n_feat * K2_F > 4 * K2_THREADS) {
-        set_error("senone_mix: %d codebook-streams exceed the tile (max %d)",
-                  m.n_mgau * m.n_feat, 4 * K2_THREADS / K2_F);
+    if (m.n_mgau * m.n_feat > 32 * K2_CS_PER_LANE) {
+        set_error("senone_mix: %d codebook-streams exceed the per-warp tile (max %d)",
+                  m.n_mgau * m.n_feat, 32 * K2_CS_PER_LANE);
         return -1;
     }
     int W = (max_union + 3) & ~3;
@@ -222,17 +232,24 @@ int launch_senone_mix_active(const DevModel &m, const DevPlan &p, const int4 *tn
         W = 4;
     bool staged = k2_active_smem(m, W, true) <= 200 * 1024;
     size_t smem = k2_active_smem(m, W, staged);
-    dim3 grid((max_frames_per_utt + K2_CHUNK - 1) / K2_CHUNK, p.n_utts);
+    // Frames per CTA: staging the mixture-weight columns costs ~NF*ND*W byte gathers per CTA, so
+    // a CTA keeps an utterance as long as the grid still fills the machine a few times over.
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int64_t want_ctas = (int64_t)sms * 12;
+    int chunk = (int)((n_frames + want_ctas - 1) / want_ctas);
+    chunk = (max(chunk, 64) + K2_WARPS - 1) / K2_WARPS * K2_WARPS;
+    dim3 grid((max_frames_per_utt + chunk - 1) / chunk, p.n_utts);
     if (staged) {
         SSB_CUDA(cudaFuncSetAttribute(senone_mix_active_kernel<true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         senone_mix_active_kernel<true>
-            <<<grid, K2_THREADS, smem, st>>>(m, p, tn_score, tn_cw, n_frames, W, chain_scr);
+            <<<grid, K2_THREADS, smem, st>>>(m, p, tn_score, tn_cw, n_frames, W, chunk, chain_scr);
     } else {
         SSB_CUDA(cudaFuncSetAttribute(senone_mix_active_kernel<false>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         senone_mix_active_kernel<false>
-            <<<grid, K2_THREADS, smem, st>>>(m, p, tn_score, tn_cw, n_frames, W, chain_scr);
+            <<<grid, K2_THREADS, smem, st>>>(m, p, tn_score, tn_cw, n_frames, W, chunk, chain_scr);
     }
     SSB_CUDA(cudaGetLastError());
     return 0;

@@ -326,3 +326,53 @@ def test_config2_spot_parity_with_oracle(models, oracles, golden):
         assert w["rv"] == 0 == res[u]["rv"]
         assert np.array_equal(res[u]["start"], w["start"]) and np.array_equal(res[u]["dur"], w["dur"])
         assert np.array_equal(res[u]["score"], w["score"]) and res[u]["best_score"] == w["best_score"]
+
+
+# ------------------------------------------------------------------ tensor-core screening
+def _exact_dist64(arrays, feat):
+    """det - sum (x - mu)^2 v in float64: [T][mgau][feat][density]."""
+    mean, var, det = (arrays[k].astype(np.float64) for k in ("mean", "var", "det"))
+    x = feat.astype(np.float64).reshape(feat.shape[0], 1, mean.shape[1], 1, mean.shape[3])
+    return det[None] - (((x - mean[None]) ** 2) * var[None]).sum(-1)
+
+
+@pytest.mark.parametrize("lang", ["en-us", "fr-fr"])
+def test_tc_screening_error_bound_holds(models, oracles, golden, lang):
+    """|TF32 GEMM score - exact score| <= eps for EVERY (frame, codebook, stream, density):
+    this inequality is what makes skipping non-survivors exact."""
+    m, o, g = models(lang), oracles(lang), golden[lang]
+    rs = np.random.RandomState(17)
+    feats = [g["feat"][:96], model_features(rs, o.model_arrays(), 64, noise=1.5),
+             (g["feat"][100:140] * 3.0).astype(np.float32)]  # far-off frames: large magnitudes
+    cw, sc, approx, eps, cnt = ssb.tc_probe(m, feats)
+    feat = np.concatenate(feats)
+    exact = _exact_dist64(o.model_arrays(), feat)
+    err = np.abs(approx.astype(np.float64) - exact)
+    ratio = err / eps[..., None]
+    assert np.isfinite(approx).all() and (eps > 0).all()
+    assert ratio.max() <= 1.0, ratio.max()
+    # the bound is not vacuous: a few output units (1024 raw) at most on real audio
+    assert np.median(eps[:96]) < 4096
+    # and the probe's top-N are the oracle's
+    off = 0
+    for f in feats:
+        ocw, osc = o.topn_all(f)
+        assert np.array_equal(sc[off:off + len(f)], osc) and np.array_equal(cw[off:off + len(f)], ocw)
+        off += len(f)
+    # screening really prunes: far fewer exact evaluations than a full scan
+    assert cnt["scan_steps"] == len(feat) * m.n_mgau * m.n_feat
+    assert cnt["exact_evals"] < 0.25 * cnt["scan_steps"] * m.n_density
+
+
+def test_tc_and_fp32_kernels_agree(models, oracles, golden, monkeypatch):
+    """SSB_K1=fp32 selects the plain CUDA-core scan; both kernels give identical lists."""
+    m, o, g = models("en-us"), oracles("en-us"), golden["en-us"]
+    rs = np.random.RandomState(23)
+    feats = [g["feat"][:50]] + [model_features(rs, o.model_arrays(), int(rs.randint(1, 30))) for _ in range(140)]
+    cw_tc, sc_tc = ssb.topn_batch(m, feats)
+    monkeypatch.setenv("SSB_K1", "fp32")
+    cw_fp, sc_fp = ssb.topn_batch(m, feats)
+    for a, b in zip(sc_tc, sc_fp):
+        assert np.array_equal(a, b)
+    for a, b in zip(cw_tc, cw_fp):
+        assert np.array_equal(a, b)
