@@ -191,10 +191,14 @@ int64_t ssb_topn_batch(ssb_model_t *m, const float *feat, const int64_t *frame_o
 /* Verification hook of the tensor-core scorer (gmm_topn_tc.cu): ssb_topn_batch plus the TF32
  * screening scores approx [frames][mgau][feat][n_density], their per-row error bound
  * eps [frames][mgau][feat] (|approx - exact fp32 distance| <= eps is what makes the screening
- * safe) and counters {exact evaluations of scan survivors, scanned (utterance, frame,
- * codebook-stream) steps}.  Any of approx/eps/counters may be NULL, not all. */
+ * safe) and counters[4] {exact evaluations of scan survivors, scanned (utterance, frame,
+ * codebook-stream) steps, steps that took the literal slow path, 0}.  Any of approx/eps/counters may be NULL, not all. */
 int64_t ssb_tc_probe(ssb_model_t *m, const float *feat, const int64_t *frame_off, int32_t n_utts,
                      uint8_t *cw, int32_t *score, float *approx, float *eps, int64_t *counters);
+/* eps above is [frames][mgau][feat][2]: the bound of the regular densities and the bound of
+ * the "hot" ones (outlier precisions, e.g. floored variances).  out[mgau*feat][4]: bit n of
+ * the 128-bit mask says density n of that codebook-stream is hot. */
+int ssb_tc_hot_mask(const ssb_model_t *m, uint32_t *out);
 
 /* single HMM step on the device (ref: src/hmm.c:482-567); st = score[5] hist[5]
  * out_score out_hist, updated in place; returns best score via *best */

@@ -404,8 +404,8 @@ def topn_batch(model, feats):
 
 def tc_probe(model, feats):
     """Tensor-core scorer verification: returns (cw, score, approx, eps, counters) with
-    approx [frames][mgau][feat][n_density] the TF32 screening scores and eps
-    [frames][mgau][feat] their guaranteed error bound."""
+    approx [frames][mgau][feat][n_density] the TF32 screening scores and eps (same shape)
+    their guaranteed error bound (regular or "hot" class bound, per density)."""
     feats = [np.ascontiguousarray(f, np.float32).reshape(-1, model.blk) for f in feats]
     off = np.zeros(len(feats) + 1, np.int64)
     for i, f in enumerate(feats):
@@ -415,12 +415,18 @@ def tc_probe(model, feats):
     cw = np.zeros((G, model.n_mgau, model.n_feat, model.topn), np.uint8)
     sc = np.zeros((G, model.n_mgau, model.n_feat, model.topn), np.int32)
     approx = np.zeros((G, model.n_mgau, model.n_feat, model.n_density), np.float32)
-    eps = np.zeros((G, model.n_mgau, model.n_feat), np.float32)
-    cnt = np.zeros(2, np.int64)
+    eps2 = np.zeros((G, model.n_mgau, model.n_feat, 2), np.float32)
+    cnt = np.zeros(4, np.int64)
     n = model.lib.ssb_tc_probe(model.h, _ptr(feat), _ptr(off), len(feats), _ptr(cw), _ptr(sc),
-                               _ptr(approx), _ptr(eps), _ptr(cnt))
+                               _ptr(approx), _ptr(eps2), _ptr(cnt))
     _lib.check(int(n), "ssb_tc_probe")
-    return cw, sc, approx, eps, dict(exact_evals=int(cnt[0]), scan_steps=int(cnt[1]))
+    # per-density bound: the regular one, or the hot one for densities flagged hot
+    words = np.zeros((model.n_mgau * model.n_feat, 4), np.uint32)
+    _lib.check(model.lib.ssb_tc_hot_mask(model.h, _ptr(words)), "ssb_tc_hot_mask")
+    hot = ((words[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool)
+    hot = hot.reshape(model.n_mgau, model.n_feat, 128)[:, :, :model.n_density]
+    eps = np.where(hot[None], eps2[..., 1:2], eps2[..., 0:1])
+    return cw, sc, approx, eps, dict(hot=hot, eps_regular=eps2[..., 0], exact_evals=int(cnt[0]), scan_steps=int(cnt[1]), slow_steps=int(cnt[2]))
 
 
 def hmm_vit_eval(model, tmatid, senid, senscr, st):

@@ -61,7 +61,7 @@ SYMBOLS = [
     "ssb_plan_chain", "ssb_batch_create", "ssb_batch_free", "ssb_batch_upload", "ssb_batch_run",
     "ssb_batch_download", "ssb_batch_debug_tokens", "ssb_batch_kernel_ms",
     "ssb_batch_n_launches", "ssb_batch_stats", "ssb_align_batch", "ssb_score_batch",
-    "ssb_topn_batch", "ssb_tc_probe", "ssb_hmm_vit_eval",
+    "ssb_topn_batch", "ssb_tc_probe", "ssb_tc_hot_mask", "ssb_hmm_vit_eval",
 ]
 
 _lib = None
@@ -116,6 +116,7 @@ def load():
     L.ssb_topn_batch.argtypes = [vp, vp, vp, i32, vp, vp]
     L.ssb_tc_probe.restype = i64
     L.ssb_tc_probe.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp]
+    L.ssb_tc_hot_mask.argtypes = [vp, vp]
     L.ssb_hmm_vit_eval.argtypes = [vp, i32, i32, vp, vp, vp, P(i32)]
     _lib = L
     return L

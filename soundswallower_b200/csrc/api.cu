@@ -106,6 +106,7 @@ struct ssb_model_s {
     DevModel d;
     int device = -1;
     std::vector<void *> owned;
+    std::vector<uint32_t> tc_hot;  // [cs][4] densities with their own screening error bound
     int sm_count = 0;
 };
 
@@ -225,7 +226,7 @@ static int model_to_device(ssb_model_s *m)
     }
     d.max_cb_sen = max_cb;
     // operands of the tensor-core screening GEMM (gmm_topn_tc.cu), double precision -> TF32
-    std::vector<float> gB, gAux;
+    std::vector<float> gB, gBlo, gAux;
     bool tc_shape = h.n_density == 128;
     for (int f = 0; f < h.n_feat; ++f)
         tc_shape = tc_shape && h.featlen[f] == 13;
@@ -240,18 +241,35 @@ static int model_to_device(ssb_model_s *m)
         };
         const int CS = h.n_mgau * h.n_feat, L = 13, ND = 128, K = 32;
         gB.assign((size_t)CS * ND * K, 0.f);
-        gAux.assign((size_t)CS * 48, 0.f);
+        gBlo.assign((size_t)CS * ND * K, 0.f);
+        gAux.assign((size_t)CS * SSB_TC_AUX, 0.f);
+        m->tc_hot.assign((size_t)CS * 4, 0u);
+        std::vector<float> col(ND);
         for (int cs = 0; cs < CS; ++cs) {
             const float *mu = h.mean.data() + h.gau_off[cs];
             const float *pv = h.var.data() + h.gau_off[cs];
             const float *dt = h.det.data() + (size_t)cs * ND;
             float *B = gB.data() + (size_t)cs * ND * K;
-            float *aux = gAux.data() + (size_t)cs * 48;
+            float *Bl = gBlo.data() + (size_t)cs * ND * K;
+            float *aux = gAux.data() + (size_t)cs * SSB_TC_AUX;
+            uint32_t *hot = m->tc_hot.data() + (size_t)cs * 4;
             for (int j = 0; j < L; ++j) {
                 double c = 0;
                 for (int n = 0; n < ND; ++n)
                     c += mu[n * L + j];
                 aux[j] = (float)(c / ND);  // the value the kernel subtracts, in fp32
+            }
+            // "hot" densities: a precision far above the codebook's typical one in some
+            // dimension (floored variances reach 5e7 against a median of ~60).  They would
+            // inflate the screening error bound of every other density, so they get their own.
+            for (int j = 0; j < L; ++j) {
+                for (int n = 0; n < ND; ++n)
+                    col[n] = pv[n * L + j];
+                std::nth_element(col.begin(), col.begin() + ND / 2, col.end());
+                const float lim = 16.f * col[ND / 2];
+                for (int n = 0; n < ND; ++n)
+                    if (pv[n * L + j] > lim)
+                        hot[n >> 5] |= 1u << (n & 31);
             }
             for (int n = 0; n < ND; ++n) {
                 double cst = dt[n];
@@ -259,9 +277,16 @@ static int model_to_device(ssb_model_s *m)
                     double mc = (double)mu[n * L + j] - (double)aux[j], v = pv[n * L + j];
                     B[n * K + j] = tf32(2.0 * mc * v);
                     B[n * K + L + j] = tf32(-v);
+                    Bl[n * K + j] = tf32(2.0 * mc * v - (double)B[n * K + j]);
+                    Bl[n * K + L + j] = tf32(-v - (double)B[n * K + L + j]);
                     cst -= mc * mc * v;
+                    // [13..38] maxima over all densities (v1 kernel); [40..65] over the regular
+                    // ones, [67..92] over the hot ones (v2 kernel)
+                    const int o = ((hot[n >> 5] >> (n & 31)) & 1u) ? 67 : 40;
                     aux[13 + j] = std::max(aux[13 + j], std::fabs(B[n * K + j]));
                     aux[26 + j] = std::max(aux[26 + j], std::fabs(B[n * K + L + j]));
+                    aux[o + j] = std::max(aux[o + j], std::fabs(B[n * K + j]));
+                    aux[o + 13 + j] = std::max(aux[o + 13 + j], std::fabs(B[n * K + L + j]));
                 }
                 float hi = tf32(cst);
                 B[n * K + 26] = hi;
@@ -269,7 +294,8 @@ static int model_to_device(ssb_model_s *m)
                 aux[39] = std::max(aux[39], (float)std::fabs(cst));
             }
         }
-        if (!(d.gB = to_device(m, gB)) || !(d.gAux = to_device(m, gAux)))
+        if (!(d.gB = to_device(m, gB)) || !(d.gBlo = to_device(m, gBlo))
+            || !(d.gAux = to_device(m, gAux)) || !(d.gHot = to_device(m, m->tc_hot)))
             return -1;
     }
     std::vector<uint8_t> lut(h.lut8, h.lut8 + 256);
@@ -585,7 +611,7 @@ struct ssb_batch_s {
     std::vector<int64_t> frame_off, phone_off, scr_off;
     std::vector<int32_t> enter;
     // device
-    DBuf feat, tn_s, tn_c, chain_scr, tokens, spill;
+    DBuf feat, featp, tn_s, tn_c, chain_scr, tokens, spill;
     DBuf d_frame_off, d_phone_off, d_scr_off, d_ssid, d_tmat, d_sf, d_ef, d_ep_off, d_ep_start,
         d_ep_cbmask, d_ep_slot_off, d_ep_slot, d_us_off, d_usen, d_st_slot, d_enter;
     DBuf st_start, st_dur, st_score, utt_rv, utt_best, utt_renorm, fin_hist, fin_score;
@@ -598,7 +624,7 @@ struct ssb_batch_s {
     bool ran = false;
     size_t bytes_held() const
     {
-        const DBuf *all[] = {&feat, &tn_s, &tn_c, &chain_scr, &tokens, &spill, &d_frame_off,
+        const DBuf *all[] = {&feat, &featp, &tn_s, &tn_c, &chain_scr, &tokens, &spill, &d_frame_off,
                              &d_phone_off, &d_scr_off, &d_ssid, &d_tmat, &d_sf, &d_ef, &d_ep_off,
                              &d_ep_start, &d_ep_cbmask, &d_ep_slot_off, &d_ep_slot, &d_us_off,
                              &d_usen, &d_st_slot, &d_enter, &st_start, &st_dur, &st_score, &utt_rv,
@@ -610,7 +636,7 @@ struct ssb_batch_s {
     }
     void release_all()
     {
-        DBuf *all[] = {&feat, &tn_s, &tn_c, &chain_scr, &tokens, &spill, &d_frame_off,
+        DBuf *all[] = {&feat, &featp, &tn_s, &tn_c, &chain_scr, &tokens, &spill, &d_frame_off,
                        &d_phone_off, &d_scr_off, &d_ssid, &d_tmat, &d_sf, &d_ef, &d_ep_off,
                        &d_ep_start, &d_ep_cbmask, &d_ep_slot_off, &d_ep_slot, &d_us_off, &d_usen,
                        &d_st_slot, &d_enter, &st_start, &st_dur, &st_score, &utt_rv, &utt_best,
@@ -912,6 +938,7 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
     const int CS = h.n_mgau * h.n_feat;
     const int64_t G = b->n_frames;
     if (b->feat.ensure(std::max<size_t>((size_t)G * h.blk * sizeof(float), 16)) != 0
+        || (tc_supported(b->m->d) && b->featp.ensure(std::max<size_t>(tc2_featp_bytes(b->m->d, G), 16)) != 0)
         || b->tn_s.ensure(std::max<size_t>((size_t)G * CS * sizeof(int4), 16)) != 0
         || b->tn_c.ensure(std::max<size_t>((size_t)G * CS * sizeof(uchar4), 16)) != 0
         || b->chain_scr.ensure(std::max<size_t>((size_t)b->n_state_frames * 2, 16)) != 0
@@ -1039,12 +1066,12 @@ extern "C" int ssb_batch_run(ssb_batch_t *b)
     cudaStream_t st = b->st;
     const int U = b->n_utts;
     b->n_launches = 0;
+    launch_count(true);
     API_CUDA(cudaEventRecord(b->ev[0], st), -1);
     if (U > 0 && b->n_frames > 0) {
         if (launch_gmm_topn(d, p, b->feat.as<float>(), b->n_frames, b->tn_s.as<int4>(),
-                            b->tn_c.as<uchar4>(), st) != 0)
+                            b->tn_c.as<uchar4>(), b->featp.as<float>(), st) != 0)
             return -1;
-        b->n_launches++;
     }
     API_CUDA(cudaEventRecord(b->ev[1], st), -1);
     if (U > 0 && b->n_frames > 0 && b->n_states > 0) {
@@ -1053,7 +1080,6 @@ extern "C" int ssb_batch_run(ssb_batch_t *b)
                                          b->n_frames, b->max_union + 1, b->max_T,
                                          b->chain_scr.as<int16_t>(), st) != 0)
                 return -1;
-            b->n_launches++;
         } else {
             int u0 = 0;
             while (u0 < U) {
@@ -1072,7 +1098,6 @@ extern "C" int ssb_batch_run(ssb_batch_t *b)
                                                     b->best_tmp.as<int32_t>(), u0, u1, g0,
                                                     b->chain_scr.as<int16_t>(), st) != 0)
                         return -1;
-                    b->n_launches += 4;
                 }
                 u0 = u1;
             }
@@ -1088,7 +1113,6 @@ extern "C" int ssb_batch_run(ssb_batch_t *b)
                                  b->fin_hist.as<int32_t>(), b->fin_score.as<int32_t>(),
                                  b->max_phones, st) != 0)
             return -1;
-        b->n_launches++;
     }
     API_CUDA(cudaEventRecord(b->ev[3], st), -1);
     if (U > 0) {
@@ -1103,8 +1127,8 @@ extern "C" int ssb_batch_run(ssb_batch_t *b)
                              b->st_dur.as<int32_t>(), b->st_score.as<int32_t>(),
                              b->utt_rv.as<int32_t>(), st) != 0)
             return -1;
-        b->n_launches++;
     }
+    b->n_launches = launch_count(true);
     API_CUDA(cudaEventRecord(b->ev[4], st), -1);
     b->ran = true;
     return 0;
@@ -1259,7 +1283,7 @@ extern "C" int64_t ssb_score_batch(ssb_model_t *m, const float *feat, const int6
             break;
         }
         if (launch_gmm_topn(d, b->plan, b->feat.as<float>(), G, b->tn_s.as<int4>(),
-                            b->tn_c.as<uchar4>(), b->st) != 0)
+                            b->tn_c.as<uchar4>(), b->featp.as<float>(), b->st) != 0)
             break;
         bool ok = true;
         for (int64_t g0 = 0; g0 < G && ok; g0 += kSlabFrames) {
@@ -1313,19 +1337,20 @@ static int64_t topn_impl(ssb_model_t *m, const float *feat, const int64_t *frame
         }
         if (!probe) {
             if (launch_gmm_topn(d, b->plan, b->feat.as<float>(), G, b->tn_s.as<int4>(),
-                                b->tn_c.as<uchar4>(), b->st) != 0)
+                                b->tn_c.as<uchar4>(), b->featp.as<float>(), b->st) != 0)
                 break;
         } else {
             if (!tc_supported(d)) {
                 set_error("ssb_tc_probe: model shape not supported by the tensor-core scorer");
                 break;
             }
-            if (d_approx.ensure((size_t)G * CS * ND * 4) || d_eps.ensure((size_t)G * CS * 4)
-                || d_cnt.ensure(16))
+            if (d_approx.ensure((size_t)G * CS * ND * 4) || d_eps.ensure((size_t)G * CS * 8)
+                || d_cnt.ensure(32))
                 break;
-            cudaMemsetAsync(d_cnt.p, 0, 16, b->st);
+            cudaMemsetAsync(d_cnt.p, 0, 32, b->st);
             if (launch_gmm_topn_tc(d, b->plan, b->feat.as<float>(), G, b->tn_s.as<int4>(),
-                                   b->tn_c.as<uchar4>(), d_approx.as<float>(), d_eps.as<float>(),
+                                   b->tn_c.as<uchar4>(), b->featp.as<float>(), d_approx.as<float>(),
+                                   d_eps.as<float>(),
                                    d_cnt.as<unsigned long long>(), b->st) != 0)
                 break;
         }
@@ -1352,11 +1377,11 @@ static int64_t topn_impl(ssb_model_t *m, const float *feat, const int64_t *frame
                 }
             }
         if (probe) {
-            std::vector<float> ha((size_t)G * CS * ND), he((size_t)G * CS);
-            unsigned long long hcnt[2] = {0, 0};
+            std::vector<float> ha((size_t)G * CS * ND), he((size_t)G * CS * 2);
+            unsigned long long hcnt[4] = {0, 0, 0, 0};
             if (cudaMemcpy(ha.data(), d_approx.p, ha.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess
                 || cudaMemcpy(he.data(), d_eps.p, he.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess
-                || cudaMemcpy(hcnt, d_cnt.p, 16, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                || cudaMemcpy(hcnt, d_cnt.p, 32, cudaMemcpyDeviceToHost) != cudaSuccess) {
                 set_error("ssb_tc_probe: %s", cudaGetErrorString(cudaGetLastError()));
                 break;
             }
@@ -1366,11 +1391,13 @@ static int64_t topn_impl(ssb_model_t *m, const float *feat, const int64_t *frame
                         std::memcpy(approx + ((size_t)g * CS + cs) * ND,
                                     ha.data() + ((size_t)cs * G + g) * ND, (size_t)ND * 4);
                     if (eps)
-                        eps[(size_t)g * CS + cs] = he[(size_t)cs * G + g];
+                        for (int q = 0; q < 2; ++q)
+                            eps[((size_t)g * CS + cs) * 2 + q] = he[((size_t)cs * G + g) * 2 + q];
                 }
             if (counters) {
                 counters[0] = (int64_t)hcnt[0];
                 counters[1] = (int64_t)hcnt[1];
+                counters[2] = (int64_t)hcnt[2];
             }
         }
         rv = G;
@@ -1386,6 +1413,16 @@ extern "C" int64_t ssb_topn_batch(ssb_model_t *m, const float *feat, const int64
                                   int32_t n_utts, uint8_t *cw, int32_t *score)
 {
     return topn_impl(m, feat, frame_off, n_utts, cw, score, nullptr, nullptr, nullptr);
+}
+
+extern "C" int ssb_tc_hot_mask(const ssb_model_t *m, uint32_t *out)
+{
+    if (!m || !out || m->tc_hot.empty()) {
+        set_error("ssb_tc_hot_mask: model has no tensor-core operands (device = -1 or unsupported shape)");
+        return -1;
+    }
+    std::memcpy(out, m->tc_hot.data(), m->tc_hot.size() * 4);
+    return 0;
 }
 
 extern "C" int64_t ssb_tc_probe(ssb_model_t *m, const float *feat, const int64_t *frame_off,

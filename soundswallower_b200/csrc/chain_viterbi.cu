@@ -389,6 +389,7 @@ int launch_chain_viterbi(const DevModel &m, const DevPlan &p, const int16_t *cha
             fin_score, smem_phones);
     }
     SSB_CUDA(cudaGetLastError());
+    note_launch();
     return 0;
 }
 
@@ -461,6 +462,7 @@ int launch_backtrace(const DevModel &m, const DevPlan &p, const int2 *tokens,
     backtrace_kernel<<<(p.n_utts + 63) / 64, 64, 0, st>>>(m, p, tokens, fin_hist, fin_score,
                                                           st_start, st_dur, st_score, utt_rv);
     SSB_CUDA(cudaGetLastError());
+    note_launch();
     return 0;
 }
 
@@ -515,6 +517,7 @@ int launch_hmm_eval(const DevModel &m, int n_emit, int tmatid, const uint16_t *s
     }
     hmm_eval_kernel<<<1, 32, 0, st>>>(m, n_emit, tmatid, senid, senscr, st12, best);
     SSB_CUDA(cudaGetLastError());
+    note_launch();
     return 0;
 }
 

@@ -44,10 +44,16 @@ struct DevModel {
     int32_t max_cb_sen;
     // tensor-core screening operands (gmm_topn_tc.cu): per codebook-stream
     //   gB   [cs][128][32] TF32-rounded rows [2 mu' v (13) | -v (13) | c_hi | c_lo | 0 x4]
-    //   gAux [cs][48]      centre[13] | max|2 mu' v|[13] | max v[13] | max|c|
+    //   gAux [cs][SSB_TC_AUX] centre[13] | max|2 mu' v|[13] | max v[13] | max|c| (all densities)
+    //                      | [40..65] the same maxima over regular densities | [67..92] over hot ones
+    //   gBlo [cs][128][32] TF32 residuals B - gB (3xTF32 split, v2 kernel)
+    //   gHot [cs][4]       bit n: density n is "hot" (outlier precision, own error bound)
     const float *gB;
+    const float *gBlo;
     const float *gAux;
+    const uint32_t *gHot;
 };
+constexpr int SSB_TC_AUX = 96;
 
 __host__ __device__ inline int64_t gau_offset(const DevModel &m, int cb, int f)
 {
@@ -78,14 +84,16 @@ struct DevPlan {
 
 // ---- kernel launchers (each returns 0 or -1 with the error set) ----
 // K1: stateful top-N of every (utterance, codebook, stream) chain.
+// featp: scratch of tc2_featp_bytes() for the tensor-core path (NULL: CUDA-core / v1 kernels)
 int launch_gmm_topn(const DevModel &m, const DevPlan &p, const float *feat, int64_t n_frames,
-                    int4 *tn_score, uchar4 *tn_cw, cudaStream_t st);
+                    int4 *tn_score, uchar4 *tn_cw, float *featp, cudaStream_t st);
+size_t tc2_featp_bytes(const DevModel &m, int64_t n_frames);
 // K1 on the tensor cores (tcgen05 TF32 screening + exact FP32 re-scoring); same results.
 // dbg_* may be NULL: approx [cs][frame][128], eps [cs][frame], counters [2].
 bool tc_supported(const DevModel &m);
 int launch_gmm_topn_tc(const DevModel &m, const DevPlan &p, const float *feat, int64_t n_frames,
-                       int4 *tn_score, uchar4 *tn_cw, float *dbg_approx, float *dbg_eps,
-                       unsigned long long *dbg_counters, cudaStream_t st);
+                       int4 *tn_score, uchar4 *tn_cw, float *featp, float *dbg_approx,
+                       float *dbg_eps, unsigned long long *dbg_counters, cudaStream_t st);
 // K2 (active lists): normalise, mix, subtract best, gather to chain states.
 // max_union counts the always-zero slot that inactive chain states read.
 int launch_senone_mix_active(const DevModel &m, const DevPlan &p, const int4 *tn_score,

@@ -274,11 +274,12 @@ static int launch_k1_n(const DevModel &m, const DevPlan &p, const float *feat, i
     }
 #undef SSB_K1
     SSB_CUDA(cudaGetLastError());
+    note_launch();
     return 0;
 }
 
 int launch_gmm_topn(const DevModel &m, const DevPlan &p, const float *feat, int64_t n_frames,
-                    int4 *tn_score, uchar4 *tn_cw, cudaStream_t st)
+                    int4 *tn_score, uchar4 *tn_cw, float *featp, cudaStream_t st)
 {
     if (p.n_utts == 0 || n_frames == 0)
         return 0;
@@ -286,8 +287,8 @@ int launch_gmm_topn(const DevModel &m, const DevPlan &p, const float *feat, int6
     // CUDA-core scan below (same results, used for A/B timing and as the generic-shape path)
     const char *force = getenv("SSB_K1");
     if (tc_supported(m) && !(force && strcmp(force, "fp32") == 0))
-        return launch_gmm_topn_tc(m, p, feat, n_frames, tn_score, tn_cw, nullptr, nullptr, nullptr,
-                                  st);
+        return launch_gmm_topn_tc(m, p, feat, n_frames, tn_score, tn_cw, featp, nullptr, nullptr,
+                                  nullptr, st);
     bool all13 = true;
     for (int f = 0; f < m.n_feat; ++f)
         all13 = all13 && m.featlen[f] == 13;
@@ -362,6 +363,7 @@ int launch_frame_topn(const DevModel &m, const FrameHist &h, int slot, int prev,
     frame_topn_kernel<<<m.n_mgau * m.n_feat, threads, m.n_density * sizeof(float), st>>>(
         m, h, slot, prev, x, do_scan);
     SSB_CUDA(cudaGetLastError());
+    note_launch();
     return 0;
 }
 

@@ -26,6 +26,16 @@ void set_error(const char *fmt, ...)
 
 const char *last_error() { return g_err; }
 
+static thread_local int g_launches = 0;
+void note_launch() { ++g_launches; }
+int launch_count(bool reset)
+{
+    int n = g_launches;
+    if (reset)
+        g_launches = 0;
+    return n;
+}
+
 // ---------------------------------------------------------------- log math
 LogMath::LogMath(double b) : base(b), inv_log_base(1.0 / std::log(b)) {}
 

@@ -11,6 +11,9 @@ namespace ssb {
 
 void set_error(const char *fmt, ...);
 const char *last_error();
+// kernels launched by this thread since the last reset (what ssb_batch_n_launches reports)
+void note_launch();
+int launch_count(bool reset);
 
 // Integer log domain helpers (ref: src/logmath.c:283-302).  shift-0 table-less use only.
 struct LogMath {

@@ -252,6 +252,7 @@ int launch_senone_mix_active(const DevModel &m, const DevPlan &p, const int4 *tn
             <<<grid, K2_THREADS, smem, st>>>(m, p, tn_score, tn_cw, n_frames, W, chunk, chain_scr);
     }
     SSB_CUDA(cudaGetLastError());
+    note_launch();
     return 0;
 }
 
@@ -394,6 +395,7 @@ int launch_senone_mix_all(const DevModel &m, const int4 *tn_score, const uchar4 
     senone_mix_all_kernel<<<grid, K2_THREADS, smem, st>>>(m, tn_score, tn_cw, n_frames_total, g0, n,
                                                           norm, Wc, staged, dense, best);
     SSB_CUDA(cudaGetLastError());
+    note_launch();
     return 0;
 }
 
@@ -404,6 +406,7 @@ int launch_subtract_best(const DevModel &m, int16_t *dense, const int32_t *best,
         return 0;
     subtract_best_kernel<<<(unsigned)n, 256, 0, st>>>(dense, best, n, m.n_sen);
     SSB_CUDA(cudaGetLastError());
+    note_launch();
     return 0;
 }
 
@@ -440,6 +443,7 @@ int launch_gather_chain_best(const DevModel &m, const DevPlan &p, const int16_t 
     dim3 grid(64, u1 - u0);
     gather_chain_kernel<<<grid, 128, 0, st>>>(m, p, dense, best, u0, g0, chain_scr);
     SSB_CUDA(cudaGetLastError());
+    note_launch();
     return 0;
 }
 
@@ -529,6 +533,7 @@ int launch_frame_senones(const DevModel &m, const FrameHist &h, int slot, int do
 {
     frame_senones_kernel<<<1, 512, 0, st>>>(m, h, slot, do_norm, act_sen, n_act, compallsen, senscr);
     SSB_CUDA(cudaGetLastError());
+    note_launch();
     return 0;
 }
 

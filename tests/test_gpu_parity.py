@@ -260,7 +260,7 @@ def test_align_states_off_path_keep_caller_values(models, golden):
     res = b.per_utt(b.download(init=init))
     assert res[0]["rv"] == 0 and np.array_equal(res[0]["dur"], g["win_states"][:, 2])
     assert res[1]["rv"] == -1 and (res[1]["dur"] == 888).all() and (res[1]["start"] == 777).all()
-    assert b.n_launches() == 4
+    assert b.n_launches() == 5  # pack_features, gmm_topn_tc2, senone_mix, chain_viterbi, backtrace
     ms = b.kernel_ms()
     assert ms["total"] > 0
     st = b.stats()
@@ -348,11 +348,12 @@ def test_tc_screening_error_bound_holds(models, oracles, golden, lang):
     feat = np.concatenate(feats)
     exact = _exact_dist64(o.model_arrays(), feat)
     err = np.abs(approx.astype(np.float64) - exact)
-    ratio = err / eps[..., None]
+    ratio = err / eps
     assert np.isfinite(approx).all() and (eps > 0).all()
     assert ratio.max() <= 1.0, ratio.max()
     # the bound is not vacuous: a few output units (1024 raw) at most on real audio
-    assert np.median(eps[:96]) < 4096
+    assert np.median(cnt["eps_regular"][:96]) < 1024
+    assert cnt["hot"].mean() < 0.05  # hot densities are the exception
     # and the probe's top-N are the oracle's
     off = 0
     for f in feats:

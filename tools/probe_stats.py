@@ -18,8 +18,10 @@ for lang in ("en-us", "fr-fr"):
     exact = det[None] - (((x - mean[None]) ** 2) * var[None]).sum(-1)
     err = np.abs(approx - exact)
     print(lang, "frames", len(feat), "exact evals per scan step: %.2f" % (cnt["exact_evals"] / cnt["scan_steps"]))
-    print("  eps percentiles (raw units) 10/50/90/99:", np.percentile(eps, [10, 50, 90, 99]).round(0))
-    print("  err/eps max %.3f  median %.4f" % ((err / eps[..., None]).max(), np.median(err / eps[..., None])))
+    print("  slow-path steps: %d of %d; hot densities: %d" % (cnt["slow_steps"], cnt["scan_steps"], cnt["hot"].sum()))
+    print("  eps (regular) percentiles (raw units) 10/50/90/99:", np.percentile(cnt["eps_regular"], [10, 50, 90, 99]).round(0))
+    print("  err/eps max %.3f  median %.4f" % ((err / eps).max(), np.median(err / eps)))
+    eps = cnt["eps_regular"]
     # how many densities lie within eps of the 4th best (the intrinsic survivor count)
     srt = np.sort(exact, -1)[..., ::-1]
     fourth = srt[..., 3]
