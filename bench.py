@@ -74,12 +74,13 @@ def config2_template(g, frames=FRAMES):
     return base, chain
 
 
-def make_config2_batch(g, n_utts, noise=0.05, seed=1234, frames=FRAMES, out=None):
-    """Per-utterance additive N(0, noise^2) on the tiled features, Philox seed = seed + utt."""
+def make_config2_batch(g, n_utts, noise=0.05, seed=1234, frames=FRAMES, out=None, ids=None):
+    """Per-utterance additive N(0, noise^2) on the tiled features, Philox seed = seed + utt
+    (utt = ids[u], the utterance's index in the global list, when a shard is generated)."""
     base, chain = config2_template(g, frames)
     feats = []
     for u in range(n_utts):
-        rng = np.random.Generator(np.random.Philox(seed + u))
+        rng = np.random.Generator(np.random.Philox(seed + (int(ids[u]) if ids is not None else u)))
         x = out[u] if out is not None else np.empty_like(base)
         np.add(base, rng.standard_normal(base.shape, dtype=np.float32) * np.float32(noise), out=x)
         feats.append(x)
@@ -283,10 +284,12 @@ def main():
     g = np.load(GOLDEN)
     model = ssb.AcousticModel(MODEL, device=local)
     U = args.utts
-    # this rank's shard: utterances rank*U .. rank*U+U-1 of the global list
+    # this rank's shard of the global list of world*U utterances: utt % n_gpu == rank
+    from soundswallower_b200 import shard
+    my_ids = shard.shard_indices(U * world, rank, world)
     pinned = torch.empty((U, FRAMES, model.blk), dtype=torch.float32, pin_memory=True)
     feat_np = pinned.numpy()
-    feats, chains = make_config2_batch(g, U, seed=1234 + rank * U, out=feat_np)
+    feats, chains = make_config2_batch(g, U, seed=1234, out=feat_np, ids=my_ids)
     chain = chains[0]
     frame_off = np.arange(U + 1, dtype=np.int64) * FRAMES
     phone_off = np.arange(U + 1, dtype=np.int64) * len(chain["ssid"])
@@ -339,9 +342,15 @@ def main():
 
     audio_s = U * FRAMES / FRAME_RATE
     t_dev = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    # the only exchange of the job: result summaries (failures, a checksum of all segmentations)
+    chk = torch.tensor([n_fail, int(res["start"].astype(np.int64).sum() % (1 << 40)),
+                        int(res["dur"].astype(np.int64).sum())], dtype=torch.int64, device="cuda")
     if dist is not None:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(chk, op=dist.ReduceOp.SUM)
     dev_ms_max, e2e_ms_max = float(t_dev[0]), float(t_dev[1])
+    n_fail = int(chk[0])
+    frames_covered = int(chk[2])
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -371,19 +380,30 @@ def main():
         "config": {"workload": workload, "utts_per_gpu": U, "frames_per_utt": FRAMES,
                    "l2": "inputs (%.0f MB/rank) and per-step intermediates exceed the 126 MB L2; "
                          "no flush needed" % (feat_np.nbytes / 1e6),
-                   "failed_alignments": n_fail},
+                   "failed_alignments": n_fail,
+                   "frames_covered_by_state_segments": frames_covered,
+                   "frames_total": world * U * FRAMES, "sharding": "utt % n_gpu, no data-path collective"},
         "e2e": {"value": world * audio_s / (e2e_ms_max * 1e-3), "unit": "audio-s/s",
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms_max},
         "gpu_launches": launches,
         "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items()},
         "clocks": clocks,
-        "roofline": {"kernel": "gmm_topn_kernel (K1: Gaussian eval + top-N)", "bound": "tensor",
+        "roofline": {"kernel": "gmm_topn_tc2_kernel (K1: tcgen05 3xTF32 screening GEMM in TMEM + exact "
+                               "FP32 survivors + top-N)" if not os.environ.get("SSB_K1") else
+                               "K1 variant SSB_K1=%s" % os.environ.get("SSB_K1"),
+                     "bound": "tensor",
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": peak_src,
-                     "note": "K1 runs bit-exact FP32 on the CUDA cores (no FMA contraction); "
-                             "fp32_pipe_frac is its share of 148 SM x 128 lanes at the sampled clock",
-                     "fp32_pipe_frac": fp32_ops / (k1_ms * 1e-3) / fp32_peak},
+                     "note": "achieved = ALGORITHMIC flops (SURVEY 8d: scanned codebook-frames x 3 streams x "
+                             "128 densities x 2(2*13+1)) / CUDA-event time of the kernel; the MMAs actually "
+                             "executed are 3 split products on K padded to 32 (mma_tflops_executed); the "
+                             "kernel is bound by the integer/FP32 epilogue (top-N selection + exact "
+                             "re-scoring), see DESIGN.md; scalar_equiv_fp32_frac = what the reference's "
+                             "scalar scan of the same densities would need of the FP32 lanes",
+                     "mma_tflops_executed": stats["scanned_cb_frames"] * model.n_feat * 3 * 2 * 128 * 32
+                                            / (k1_ms * 1e-3) / 1e12,
+                     "scalar_equiv_fp32_frac": fp32_ops / (k1_ms * 1e-3) / fp32_peak},
         "senone_scores_per_s": stats["active_senone_frames"] / ((kms["gmm_topn"] + kms["senone_mix"]) / args.steps * 1e-3),
         "dp_state_frames_per_s": stats["state_frames"] / (kms["chain_viterbi"] / args.steps * 1e-3),
         "dp_hbm_frac_10B": stats["state_frames"] * 10 / (kms["chain_viterbi"] / args.steps * 1e-3) / 1e9

@@ -44,11 +44,32 @@ struct Tc2Smem {
     float rec[TC_ND * TC_RL];                // 14 KB exact records
     float aux[SSB_TC_AUX];
     uint32_t hot[4];
-    uint64_t mbar;
+    uint64_t mbar[TC2_GROUPS];  // the two row groups run out of phase: own barriers, own MMAs
     uint32_t tmem_base;
-    int tmax;
-    int jump;
+    int tmax[TC2_GROUPS];
+    int jump[TC2_GROUPS];
 };
+
+// named barrier of one 128-thread row group (ids 1, 2; 0 is __syncthreads)
+__device__ __forceinline__ void group_sync(int grp)
+{
+    asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory");
+}
+__device__ __forceinline__ int group_sync_or(int grp, int pred)
+{
+    uint32_t r;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "bar.red.or.pred p, %2, 128, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(r)
+        : "r"(pred), "r"(grp + 1)
+        : "memory");
+    return (int)r;
+}
 
 __global__ void pack_features_kernel(DevModel m, const float *__restrict__ feat, int64_t G,
                                      float *__restrict__ featp)
@@ -81,6 +102,14 @@ __device__ __forceinline__ float max16(const float (&v)[32], int o, uint32_t exc
     float m0 = max3(w[0], w[1], w[2]), m1 = max3(w[3], w[4], w[5]), m2 = max3(w[6], w[7], w[8]);
     float m3 = max3(w[9], w[10], w[11]), m4 = max3(w[12], w[13], w[14]);
     return fmaxf(max3(m0, m1, m2), max3(m3, m4, w[15]));
+}
+
+__device__ __forceinline__ float max16_plain(const float (&v)[32], int o)
+{
+    float m0 = max3(v[o], v[o + 1], v[o + 2]), m1 = max3(v[o + 3], v[o + 4], v[o + 5]);
+    float m2 = max3(v[o + 6], v[o + 7], v[o + 8]), m3 = max3(v[o + 9], v[o + 10], v[o + 11]);
+    float m4 = max3(v[o + 12], v[o + 13], v[o + 14]);
+    return fmaxf(max3(m0, m1, m2), max3(m3, m4, v[o + 15]));
 }
 
 #define TC_CE(a, b)              \
@@ -182,9 +211,11 @@ gmm_topn_tc2_kernel(DevModel m, DevPlan p, const float *__restrict__ featp, int6
         for (int i = tid; i < TC2_GROUPS * 2 * 128 * TC_K / 4; i += TC2_THREADS)
             dA[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (tid == 0) {
-            mbar_init(&S.mbar, 1);
-            S.tmax = 0;
-            S.jump = INT32_MAX;
+            for (int g = 0; g < TC2_GROUPS; ++g) {
+                mbar_init(&S.mbar[g], 1);
+                S.tmax[g] = 0;
+                S.jump[g] = INT32_MAX;
+            }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
@@ -198,12 +229,12 @@ gmm_topn_tc2_kernel(DevModel m, DevPlan p, const float *__restrict__ featp, int6
     const bool has_utt = u < p.n_utts;
     const int64_t g0 = has_utt ? p.frame_off[u] : 0;
     const int T = has_utt ? (int)(p.frame_off[u + 1] - g0) : 0;
-    atomicMax(&S.tmax, T);
+    atomicMax(&S.tmax[grp], T);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = S.tmem_base;
-    const int Tmax = S.tmax;
+    const int Tmax = S.tmax[grp];
     const bool has_hot = (S.hot[0] | S.hot[1] | S.hot[2] | S.hot[3]) != 0u;
     // TMEM: lanes = rows of the group (a warp may only touch lanes 32*(warp%4)..+31), columns
     // [128*grp, 128*grp+128) = the group's accumulator
@@ -292,49 +323,46 @@ gmm_topn_tc2_kernel(DevModel m, DevPlan p, const float *__restrict__ featp, int6
         }
         fence_async_proxy();
         tc_fence_before();
-        const int any = __syncthreads_or(scan ? 1 : 0);
+        const int any = group_sync_or(grp, scan ? 1 : 0);
         if (!any) {
-            // nobody in this CTA scans this codebook on frame t: jump to the next frame on which
-            // the active set of one of its utterances grows
+            // nobody in this row group scans this codebook on frame t: jump to the next frame
+            // on which the active set of one of its utterances grows
             const int cand = (live && t_next < T) ? t_next : INT32_MAX;
             if (cand != INT32_MAX)
-                atomicMin(&S.jump, cand);
-            __syncthreads();
-            const int tj = S.jump;
-            __syncthreads();
-            if (tid == 0)
-                S.jump = INT32_MAX;
+                atomicMin(&S.jump[grp], cand);
+            group_sync(grp);
+            const int tj = S.jump[grp];
+            group_sync(grp);
+            if (row == 0)
+                S.jump[grp] = INT32_MAX;
             if (tj == INT32_MAX)
                 break;
             t = tj;
             continue;
         }
-        if (tid == 0) {
+        if (row == 0) {
             tc_fence_after();
             const uint64_t bhi = umma_desc_sw128(smem_u32(S.Bhi)), blo = umma_desc_sw128(smem_u32(S.Blo));
+            const uint64_t ahi = umma_desc_sw128(smem_u32(&S.A[grp][0][0]));
+            const uint64_t alo = umma_desc_sw128(smem_u32(&S.A[grp][1][0]));
+            const uint32_t d = tmem + (uint32_t)(grp * 128);
 #pragma unroll
-            for (int g = 0; g < TC2_GROUPS; ++g) {
-                const uint64_t ahi = umma_desc_sw128(smem_u32(&S.A[g][0][0]));
-                const uint64_t alo = umma_desc_sw128(smem_u32(&S.A[g][1][0]));
-                const uint32_t d = tmem + (uint32_t)(g * 128);
+            for (int k = 0; k < TC_K / 8; ++k)
+                umma_tf32(d, ahi + (uint64_t)(2 * k), bhi + (uint64_t)(2 * k), k > 0 ? 1u : 0u);
 #pragma unroll
-                for (int k = 0; k < TC_K / 8; ++k)
-                    umma_tf32(d, ahi + (uint64_t)(2 * k), bhi + (uint64_t)(2 * k), k > 0 ? 1u : 0u);
+            for (int k = 0; k < TC_K / 8; ++k)
+                umma_tf32(d, alo + (uint64_t)(2 * k), bhi + (uint64_t)(2 * k), 1u);
 #pragma unroll
-                for (int k = 0; k < TC_K / 8; ++k)
-                    umma_tf32(d, alo + (uint64_t)(2 * k), bhi + (uint64_t)(2 * k), 1u);
-#pragma unroll
-                for (int k = 0; k < TC_K / 8; ++k)
-                    umma_tf32(d, ahi + (uint64_t)(2 * k), blo + (uint64_t)(2 * k), 1u);
-            }
-            umma_commit(&S.mbar);
+            for (int k = 0; k < TC_K / 8; ++k)
+                umma_tf32(d, ahi + (uint64_t)(2 * k), blo + (uint64_t)(2 * k), 1u);
+            umma_commit(&S.mbar[grp]);
         }
         // next frame's features travel while the tensor core works
         if (scan && t + 1 < T) {
             load_x(xp + (int64_t)(t + 1) * xstride, xn);
             xn_t = t + 1;
         }
-        mbar_wait(&S.mbar, n_mma & 1u);
+        mbar_wait(&S.mbar[grp], n_mma & 1u);
         ++n_mma;
         tc_fence_after();
         // pass 1: N-th largest of the 8 group maxima (regular densities only, so that the N
@@ -344,8 +372,15 @@ gmm_topn_tc2_kernel(DevModel m, DevPlan p, const float *__restrict__ featp, int6
         for (int ch = 0; ch < TC_ND / 32; ++ch) {
             float v[32];
             tmem_ld32(tmem_row + (uint32_t)(ch * 32), v);
-            const uint32_t hot = has_hot ? S.hot[ch] : 0u;
-            const float a = max16(v, 0, hot & 0xffffu), b = max16(v, 16, hot >> 16);
+            float a, b;
+            if (has_hot) {  // block-uniform: only the few codebook-streams with hot densities
+                const uint32_t hot = S.hot[ch];
+                a = max16(v, 0, hot & 0xffffu);
+                b = max16(v, 16, hot >> 16);
+            } else {
+                a = max16_plain(v, 0);
+                b = max16_plain(v, 16);
+            }
             // gm[2*ch], gm[2*ch+1] without dynamic register indexing
 #pragma unroll
             for (int q = 0; q < 4; ++q)

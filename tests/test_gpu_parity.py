@@ -377,3 +377,69 @@ def test_tc_and_fp32_kernels_agree(models, oracles, golden, monkeypatch):
         assert np.array_equal(a, b)
     for a, b in zip(cw_tc, cw_fp):
         assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------ long chains (config #4 shape)
+def _tiled_fr(golden, reps):
+    """goforward_fr tiled `reps` times: features, chain (14 phones per sentence + final SIL),
+    word windows shifted per repetition (the long-form read-along shape of BASELINE config #4)."""
+    g = golden["fr-fr"]
+    feat, words, phones = g["feat"], g["words"], g["phones"]
+    T1 = feat.shape[0]
+    ssid, tmat, ws, wd = [], [], [], []
+    for k in range(reps):
+        for i in range(len(phones) - 1):
+            w = int(phones[i, 6])
+            s, d = int(words[w, 1]) + k * T1, int(words[w, 2])
+            if w == 0 and k > 0:
+                s = int(words[-1, 1]) + (k - 1) * T1
+                d = k * T1 + int(words[0, 2]) - s
+            ssid.append(int(phones[i, 1])); tmat.append(int(phones[i, 2])); ws.append(s); wd.append(d)
+    s = int(words[-1, 1]) + (reps - 1) * T1
+    ssid.append(int(phones[-1, 1])); tmat.append(int(phones[-1, 2])); ws.append(s); wd.append(reps * T1 - s)
+    sf, ef = ssb.windows(np.array(ws, np.int32), np.array(wd, np.int32))
+    x = np.concatenate([feat] * reps)
+    rs = np.random.RandomState(777)
+    x = (x + rs.normal(0, 0.05, x.shape)).astype(np.float32)
+    return x, dict(ssid=np.array(ssid, np.int32), tmat=np.array(tmat, np.int32), sf=sf, ef=ef)
+
+
+@pytest.mark.parametrize("windowed", [True, False])
+def test_long_chain_multiwarp(models, oracles, golden, windowed):
+    """169 phones / 507 states (> 128 phones: the multi-warp Viterbi kernel), 2868 frames."""
+    m, o = models("fr-fr"), oracles("fr-fr")
+    x, chain = _tiled_fr(golden, 12)
+    if not windowed:
+        chain = dict(chain, sf=chain["sf"] * 0, ef=chain["ef"] * 0 + ssb.INT_MAX)
+    r = ssb.align_batch(m, [x], [chain], want_chain_scr=True)[0]
+    w = o.state_align(x, chain["ssid"], chain["tmat"], chain["sf"], chain["ef"], want_senscr=True)
+    sen = o.model_arrays()["sseq"][chain["ssid"]].reshape(-1)
+    assert np.array_equal(r["chain_scr"], w["senscr"][:, sen])
+    assert r["rv"] == w["rv"] == 0 and r["best_score"] == w["best_score"]
+    for k in ("start", "dur", "score"):
+        assert np.array_equal(r[k], w[k]), k
+    on = r["dur"] > 0
+    assert r["start"][on][0] == 0 and (r["start"][on][1:] == (r["start"][on] + r["dur"][on])[:-1]).all()
+
+
+def test_very_long_chain_state_in_global_memory(models, oracles):
+    """6600 phones: more HMM state than fits in shared memory (spill path), 4 warps, windows of a
+    few frames per word.  Random triphones: the alignment may or may not reach the final state;
+    either way every score and the verdict must equal the oracle's."""
+    m, o = models("fr-fr"), oracles("fr-fr")
+    rs = np.random.RandomState(4242)
+    n_ph, T = 6600, 7000
+    ssid_t, tmat_t, _ = o.phone_table()
+    pid = rs.randint(0, len(ssid_t), n_ph)
+    word_of = np.arange(n_ph) // 3
+    n_words = int(word_of[-1]) + 1
+    edges = (np.arange(n_words + 1) * T) // n_words
+    sf, ef = ssb.windows(edges[:-1][word_of].astype(np.int32), np.diff(edges)[word_of].astype(np.int32))
+    chain = dict(ssid=ssid_t[pid].astype(np.int32), tmat=tmat_t[pid].astype(np.int32), sf=sf, ef=ef)
+    x = model_features(rs, o.model_arrays(), T)
+    r = ssb.align_batch(m, [x], [chain])[0]
+    w = o.state_align(x, chain["ssid"], chain["tmat"], chain["sf"], chain["ef"])
+    assert r["rv"] == w["rv"] and r["best_score"] == w["best_score"] and r["n_renorm"] == w["n_renorm"]
+    if w["rv"] == 0:
+        for k in ("start", "dur", "score"):
+            assert np.array_equal(r[k], w[k]), k
