@@ -279,6 +279,9 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # keep stdout to the one JSON line: NCCL prints its version banner there otherwise
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     g = np.load(GOLDEN)

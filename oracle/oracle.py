@@ -205,6 +205,57 @@ class Oracle:
         return dict(rv=out.rv, best_score=out.best_score, n_renorm=out.n_renorm, start=st, dur=du,
                     score=sc, tokens=tok, senscr=senscr)
 
+    # ---- FSG search
+    class _Fsg(C.Structure):
+        _fields_ = [(k, C.c_int32) for k in ("n_state", "start", "final", "n_link", "n_pnode",
+                                              "n_ciphone", "sil", "beam", "pbeam", "wbeam", "maxhmmpf")] + \
+                   [("link4", C.c_void_p), ("link_flag", C.c_void_p), ("arc_off", C.c_void_p),
+                    ("root", C.c_void_p), ("pnode8", C.c_void_p), ("ctxt", C.c_void_p)]
+
+    def _fsg_struct(self, G):
+        keep = dict(link=np.ascontiguousarray(G["link"], np.int32),
+                    link_flag=np.ascontiguousarray(G["link_flag"], np.uint8),
+                    arc_off=np.ascontiguousarray(G["arc_off"], np.int32),
+                    root=np.ascontiguousarray(G["root"], np.int32),
+                    pnode=np.ascontiguousarray(G["pnode"], np.int32),
+                    ctxt=np.ascontiguousarray(G["ctxt"], np.uint32))
+        f = self._Fsg()
+        f.n_state, f.start, f.final = int(G["n_state"]), int(G["start"]), int(G["final"])
+        f.n_link, f.n_pnode = len(keep["link"]), len(keep["pnode"])
+        f.n_ciphone, f.sil = int(G["n_ciphone"]), int(G["sil"])
+        f.beam, f.pbeam, f.wbeam, f.maxhmmpf = (int(G[k]) for k in ("beam", "pbeam", "wbeam", "maxhmmpf"))
+        f.link4, f.link_flag, f.arc_off = (keep[k].ctypes.data for k in ("link", "link_flag", "arc_off"))
+        f.root, f.pnode8, f.ctxt = (keep[k].ctypes.data for k in ("root", "pnode", "ctxt"))
+        return f, keep
+
+    def fsg_search(self, G, senscr, cap=1 << 16):
+        """Token passing over the flattened graph G (refshim.Ref.fsg_graph layout) on dense senone
+        scores [T][n_sen].  Returns history [n][9], counters, best exit, segs [n][5]
+        (link sf ef ascr lscr)."""
+        senscr = np.ascontiguousarray(senscr, np.int16)
+        T = senscr.shape[0]
+        f, keep = self._fsg_struct(G)
+        hist = np.zeros((cap, 9), np.int32)
+        out = np.zeros(8, np.int64)
+        L = self.lib
+        L.orc_fsg_search.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                     C.c_void_p]
+        rv = L.orc_fsg_search(self.h, C.byref(f), senscr.ctypes.data, T, hist.ctypes.data, cap,
+                              out.ctypes.data)
+        n = int(out[0])
+        hist = hist[:n].copy()
+        score = C.c_int32(0)
+        L.orc_fsg_find_exit.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        bp = L.orc_fsg_find_exit(C.byref(f), hist.ctypes.data, n, int(out[2]), 1, C.byref(score))
+        segs = np.zeros((4096, 5), np.int32)
+        ns = 0
+        if bp > 0:
+            L.orc_fsg_segs.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+            ns = L.orc_fsg_segs(C.byref(f), hist.ctypes.data, bp, segs.ctypes.data, 4096)
+        del keep
+        return dict(rv=rv, hist=hist, n_hmm_eval=int(out[1]), n_frames=int(out[2]), exit=bp,
+                    hyp_score=int(score.value), segs=segs[:max(ns, 0)].copy())
+
     def propagate(self, start, dur, score):
         n = len(start)
         E = self.n_emit

@@ -564,3 +564,211 @@ ref_hmm_vit_eval(void *h, int n_emit, int tmatid, const uint16 *senid,
     hmm_context_free(ctx);
     return best;
 }
+
+/* ------------------------------------------------------------------ */
+/* FSG search: flattened graph + history table (for the K4 oracle/kernel) */
+/* ------------------------------------------------------------------ */
+#include <soundswallower/fsg_history.h>
+#include <soundswallower/fsg_lextree.h>
+
+typedef struct {
+    fsg_link_t **link;
+    int n_link;
+    fsg_pnode_t **pnode;
+    int n_pnode;
+} fsg_index_t;
+
+static fsg_search_t *
+fsg_of(ref_t *r)
+{
+    search_module_t *s = r->d->search;
+    if (s == NULL || strcmp(s->type, PS_SEARCH_TYPE_FSG) != 0)
+        return NULL;
+    return (fsg_search_t *)s;
+}
+
+static void
+fsg_index_build(fsg_search_t *fs, fsg_index_t *ix)
+{
+    fsg_model_t *fsg = fs->fsg;
+    int s, n;
+    memset(ix, 0, sizeof(*ix));
+    for (n = 0, s = 0; s < fsg_model_n_state(fsg); ++s) {
+        fsg_arciter_t *it;
+        for (it = fsg_model_arcs(fsg, s); it; it = fsg_arciter_next(it))
+            ++n;
+    }
+    ix->link = ckd_calloc(n + 1, sizeof(*ix->link));
+    for (s = 0; s < fsg_model_n_state(fsg); ++s) {
+        fsg_arciter_t *it;
+        for (it = fsg_model_arcs(fsg, s); it; it = fsg_arciter_next(it))
+            ix->link[ix->n_link++] = fsg_arciter_get(it);
+    }
+    ix->pnode = ckd_calloc(fs->lextree->n_pnode + 1, sizeof(*ix->pnode));
+    for (s = 0; s < fsg_model_n_state(fsg); ++s) {
+        fsg_pnode_t *p;
+        for (p = fs->lextree->alloc_head[s]; p; p = p->alloc_next)
+            ix->pnode[ix->n_pnode++] = p;
+    }
+}
+
+static void
+fsg_index_free(fsg_index_t *ix)
+{
+    ckd_free(ix->link);
+    ckd_free(ix->pnode);
+}
+
+static int
+link_id(fsg_index_t *ix, fsg_link_t *l)
+{
+    int i;
+    if (l == NULL)
+        return -1;
+    for (i = 0; i < ix->n_link; ++i)
+        if (ix->link[i] == l)
+            return i;
+    return -2;
+}
+
+static int
+pnode_id(fsg_index_t *ix, fsg_pnode_t *p)
+{
+    int i;
+    if (p == NULL)
+        return -1;
+    for (i = 0; i < ix->n_pnode; ++i)
+        if (ix->pnode[i] == p)
+            return i;
+    return -2;
+}
+
+/* Select the grammar (align text or JSGF string) without decoding. */
+int
+ref_fsg_prepare(void *h, const char *align_text, const char *jsgf_string)
+{
+    ref_t *r = h;
+    if (align_text)
+        return decoder_set_align_text(r->d, align_text);
+    if (jsgf_string)
+        return decoder_set_jsgf_string(r->d, jsgf_string);
+    return -1;
+}
+
+/* out: n_state start final n_link n_pnode n_ciphone silcipid beam pbeam wbeam maxhmmpf wip pip */
+int
+ref_fsg_dims(void *h, int32 *out)
+{
+    ref_t *r = h;
+    fsg_search_t *fs = fsg_of(r);
+    fsg_index_t ix;
+    if (fs == NULL)
+        return -1;
+    fsg_index_build(fs, &ix);
+    out[0] = fsg_model_n_state(fs->fsg);
+    out[1] = fsg_model_start_state(fs->fsg);
+    out[2] = fsg_model_final_state(fs->fsg);
+    out[3] = ix.n_link;
+    out[4] = ix.n_pnode;
+    out[5] = bin_mdef_n_ciphone(r->d->acmod->mdef);
+    out[6] = bin_mdef_ciphone_id(r->d->acmod->mdef, "SIL");
+    out[7] = fs->beam_orig;
+    out[8] = fs->pbeam_orig;
+    out[9] = fs->wbeam_orig;
+    out[10] = config_int(search_module_config(fs), "maxhmmpf");
+    out[11] = fs->wip;
+    out[12] = fs->pip;
+    fsg_index_free(&ix);
+    return 0;
+}
+
+/* link4 [n_link][4] = from to logs2prob wid ; link_flag [n_link] bit0 = the word models no
+ * right context (filler or single-phone word, the test of fsg_search_pnode_exit), bit1 = filler;
+ * arc_off [n_state+1] into the link list (links are numbered in fsg_model_arcs order, state by
+ * state, so state s owns links arc_off[s]..arc_off[s+1]);
+ * root [n_state]; pnode8 [n_pnode][8] = ssid tmat logs2prob ci_ext leaf succ_or_link sibling ppos;
+ * ctxt [n_pnode][4]. */
+int
+ref_fsg_dump(void *h, int32 *link4, uint8 *link_flag, int32 *arc_off, int32 *root, int32 *pnode8,
+             uint32 *ctxt)
+{
+    ref_t *r = h;
+    fsg_search_t *fs = fsg_of(r);
+    fsg_model_t *fsg;
+    dict_t *dict = r->d->dict;
+    fsg_index_t ix;
+    int s, i, n;
+    if (fs == NULL)
+        return -1;
+    fsg = fs->fsg;
+    fsg_index_build(fs, &ix);
+    for (n = 0, s = 0; s < fsg_model_n_state(fsg); ++s) {
+        fsg_arciter_t *it;
+        arc_off[s] = n;
+        for (it = fsg_model_arcs(fsg, s); it; it = fsg_arciter_next(it))
+            ++n;
+        root[s] = pnode_id(&ix, fsg_lextree_root(fs->lextree, s));
+    }
+    arc_off[fsg_model_n_state(fsg)] = n;
+    for (i = 0; i < ix.n_link; ++i) {
+        fsg_link_t *l = ix.link[i];
+        int wid = fsg_link_wid(l);
+        link4[i * 4 + 0] = fsg_link_from_state(l);
+        link4[i * 4 + 1] = fsg_link_to_state(l);
+        link4[i * 4 + 2] = fsg_link_logs2prob(l);
+        link4[i * 4 + 3] = wid;
+        link_flag[i] = 0;
+        if (wid >= 0) {
+            int filler = fsg_model_is_filler(fsg, wid);
+            int single = dict_is_single_phone(dict, dict_wordid(dict, fsg_model_word_str(fsg, wid)));
+            link_flag[i] = (uint8)((filler || single) ? 1 : 0) | (uint8)(filler ? 2 : 0);
+        }
+    }
+    for (i = 0; i < ix.n_pnode; ++i) {
+        fsg_pnode_t *p = ix.pnode[i];
+        pnode8[i * 8 + 0] = p->hmm.ssid;
+        pnode8[i * 8 + 1] = p->hmm.tmatid;
+        pnode8[i * 8 + 2] = p->logs2prob;
+        pnode8[i * 8 + 3] = p->ci_ext;
+        pnode8[i * 8 + 4] = p->leaf;
+        pnode8[i * 8 + 5] = p->leaf ? link_id(&ix, p->next.fsglink) : pnode_id(&ix, p->next.succ);
+        pnode8[i * 8 + 6] = pnode_id(&ix, p->sibling);
+        pnode8[i * 8 + 7] = p->ppos;
+        memcpy(ctxt + i * 4, p->ctxt.bv, 4 * sizeof(uint32));
+    }
+    fsg_index_free(&ix);
+    return 0;
+}
+
+/* History table of the last decode: ent [n][9] = link score pred frame lc rc[4]. */
+int
+ref_fsg_history(void *h, int32 *ent, int max_ent, int32 *n_out)
+{
+    ref_t *r = h;
+    fsg_search_t *fs = fsg_of(r);
+    fsg_index_t ix;
+    int i, n;
+    int32 score = 0;
+    if (fs == NULL)
+        return -1;
+    n = fsg_history_n_entries(fs->history);
+    if (n > max_ent)
+        return -2;
+    fsg_index_build(fs, &ix);
+    for (i = 0; i < n; ++i) {
+        fsg_hist_entry_t *e = fsg_history_entry_get(fs->history, i);
+        ent[i * 9 + 0] = link_id(&ix, e->fsglink);
+        ent[i * 9 + 1] = e->score;
+        ent[i * 9 + 2] = e->pred;
+        ent[i * 9 + 3] = e->frame;
+        ent[i * 9 + 4] = e->lc;
+        memcpy(ent + i * 9 + 5, e->rc.bv, 4 * sizeof(int32));
+    }
+    fsg_index_free(&ix);
+    n_out[0] = n;
+    n_out[1] = fs->n_hmm_eval;
+    n_out[2] = fs->frame;
+    search_module_hyp(r->d->search, &score);
+    n_out[3] = score;
+    return n;
+}

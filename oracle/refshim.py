@@ -188,6 +188,39 @@ class Ref:
         r.update(rv=rv, best_score=int(n_out[6]), tokens=tokens, senscr=senscr)
         return r
 
+    def fsg_graph(self, align_text=None, jsgf=None):
+        """Select a grammar and return the flattened FSG + lextree the search runs on
+        (see ref_fsg_dump in ref_shim.c for the layouts)."""
+        L = self.lib
+        rv = L.ref_fsg_prepare(self.h, align_text.encode() if align_text else None,
+                               jsgf.encode() if jsgf else None)
+        assert rv == 0, rv
+        d = np.zeros(16, np.int32)
+        assert L.ref_fsg_dims(self.h, _p(d, C.c_int32)) == 0
+        (n_state, start, final, n_link, n_pnode, n_ci, sil, beam, pbeam, wbeam, maxhmmpf, wip,
+         pip) = [int(x) for x in d[:13]]
+        link4 = np.zeros((n_link, 4), np.int32)
+        flag = np.zeros(n_link, np.uint8)
+        arc_off = np.zeros(n_state + 1, np.int32)
+        root = np.zeros(n_state, np.int32)
+        pnode8 = np.zeros((n_pnode, 8), np.int32)
+        ctxt = np.zeros((n_pnode, 4), np.uint32)
+        rv = L.ref_fsg_dump(self.h, _p(link4, C.c_int32), _p(flag, C.c_uint8), _p(arc_off, C.c_int32),
+                            _p(root, C.c_int32), _p(pnode8, C.c_int32), _p(ctxt, C.c_uint32))
+        assert rv == 0, rv
+        return dict(n_state=n_state, start=start, final=final, n_ciphone=n_ci, sil=sil, beam=beam,
+                    pbeam=pbeam, wbeam=wbeam, maxhmmpf=maxhmmpf, wip=wip, pip=pip, link=link4,
+                    link_flag=flag, arc_off=arc_off, root=root, pnode=pnode8, ctxt=ctxt)
+
+    def fsg_history(self, max_ent=1 << 16):
+        """History table of the last fsg_decode: [n][9] = link score pred frame lc rc[4]."""
+        ent = np.zeros((max_ent, 9), np.int32)
+        n_out = np.zeros(8, np.int32)
+        n = self.lib.ref_fsg_history(self.h, _p(ent, C.c_int32), max_ent, _p(n_out, C.c_int32))
+        assert n >= 0, n
+        return dict(hist=ent[:n].copy(), n_hmm_eval=int(n_out[1]), n_frames=int(n_out[2]),
+                    hyp_score=int(n_out[3]))
+
     def fsg_decode(self, feat, align_text=None, jsgf=None):
         feat = np.ascontiguousarray(feat, np.float32)
         n_out = np.zeros(16, np.int32)

@@ -113,6 +113,24 @@ int orc_state_align(const orc_model_t *m, int topn, const float *feat, int T, in
                     const int32_t *ssid, const int32_t *tmat, const int32_t *sf, const int32_t *ef,
                     const uint32_t *init_active, int compallsen, int32_t *st_start, int32_t *st_dur,
                     int32_t *st_score, int32_t *tokens, int16_t *senscr_out, orc_align_out_t *out);
+/* ---- FSG token-passing search on a flattened lextree (ss_oracle_fsg.c; ref: fsg_search.c,
+ * fsg_history.c).  Array layouts = oracle/ref_shim.c:ref_fsg_dump. */
+typedef struct orc_fsg_s {
+    int32_t n_state, start, final, n_link, n_pnode, n_ciphone, sil;
+    int32_t beam, pbeam, wbeam, maxhmmpf;
+    const int32_t *link4;     /* [n_link][4] from to logs2prob wid; state s owns arc_off[s]..arc_off[s+1] */
+    const uint8_t *link_flag; /* bit0: word models no right context (filler / single phone) */
+    const int32_t *arc_off;   /* [n_state+1] */
+    const int32_t *root;      /* [n_state] first root pnode or -1 */
+    const int32_t *pnode8;    /* [n_pnode][8] ssid tmat logs2prob ci_ext leaf succ|link sibling ppos */
+    const uint32_t *ctxt;     /* [n_pnode][4] */
+} orc_fsg_t;
+int orc_fsg_search(const orc_model_t *m, const orc_fsg_t *g, const int16_t *senscr, int T,
+                   int32_t *hist9, int cap, int64_t *out);
+int orc_fsg_find_exit(const orc_fsg_t *g, const int32_t *hist9, int n_hist, int frame_idx, int final,
+                      int32_t *out_score);
+int orc_fsg_segs(const orc_fsg_t *g, const int32_t *hist9, int bpidx, int32_t *segs, int max_seg);
+
 /* ref: ps_alignment.c:317-355 (durations/scores summed upward) */
 int orc_propagate(int n_states, int n_emit, const int32_t *st_start, const int32_t *st_dur,
                   const int32_t *st_score, int32_t *ph_start, int32_t *ph_dur, int32_t *ph_score);

@@ -156,6 +156,30 @@ def synthetic(lang="en-us", seed=20261017):
     print("synthetic", lang, lens)
 
 
+def fsg(lang, raw_feat_key, text, gram):
+    """FSG search (first pass): the flattened graph the reference searches, and its complete
+    history table / segmentation on the test utterance with dense (compallsen) scores."""
+    hmm = os.path.join(MODELS, lang)
+    ref = Ref(hmm, compallsen=True)
+    feat = np.load(os.path.join(OUT, "align_%s.npz" % lang))["feat"]
+    jsgf = open(os.path.join(DATA, gram)).read()
+    g = {}
+    for name, kw in (("align", dict(align_text=text)), ("jsgf", dict(jsgf=jsgf))):
+        G = ref.fsg_graph(**kw)
+        for k, v in G.items():
+            g["%s_%s" % (name, k)] = np.asarray(v)
+        d = ref.fsg_decode(feat, **kw)
+        H = ref.fsg_history()
+        g[name + "_hist"] = H["hist"]
+        g[name + "_segs"] = d["segs"]
+        g[name + "_n_hmm_eval"] = np.int64(H["n_hmm_eval"])
+        g[name + "_hyp_score"] = np.int32(H["hyp_score"])
+        print(lang, name, "pnodes", len(G["pnode"]), "links", len(G["link"]), "hist", len(H["hist"]),
+              "hyp", H["hyp_score"])
+    ref.close()
+    np.savez_compressed(os.path.join(OUT, "fsg_%s.npz" % lang), **g)
+
+
 def main():
     if not available():
         raise SystemExit("oracle/_ref/libssref.so missing: run `make -C oracle ref` first")
@@ -163,6 +187,8 @@ def main():
     utterance("en-us", "goforward.raw", "go forward ten meters")
     utterance("fr-fr", "goforward_fr.raw", "avance de dix mètres")
     synthetic("en-us")
+    fsg("en-us", "goforward.raw", "go forward ten meters", "goforward.gram")
+    fsg("fr-fr", "goforward_fr.raw", "avance de dix mètres", "goforward_fr.gram")
 
 
 if __name__ == "__main__":
