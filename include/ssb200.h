@@ -200,6 +200,51 @@ int64_t ssb_tc_probe(ssb_model_t *m, const float *feat, const int64_t *frame_off
  * the 128-bit mask says density n of that codebook-stream is hot. */
 int ssb_tc_hot_mask(const ssb_model_t *m, uint32_t *out);
 
+/* ------------------------------------------------------------------ */
+/* FSG token-passing search (first pass / grammar decoding)            */
+/* replaces fsg_search_start/step/finish, fsg_history_*, and the backtrace behind
+ * fsg_search_hyp / fsg_search_seg_iter (ref: src/fsg_search.c:309-1142, src/fsg_history.c:129-232).
+ * The graph is prepared on the host by the caller: it is the reference's fsg_model_t +
+ * fsg_lextree_t flattened (INTEGRATION.md shows the loop over alloc_head / fsg_model_arcs).   */
+/* ------------------------------------------------------------------ */
+typedef struct ssb_fsg_graph_s {
+    int32_t n_state, start, final, n_link, n_pnode, n_ciphone, sil;
+    int32_t beam, pbeam, wbeam, maxhmmpf; /* log-domain beams of fsg_search_init; -1 = no maxhmmpf */
+    const int32_t *link4;     /* [n_link][4] from_state to_state logs2prob wid (-1: null arc); the
+                                 links of state s are arc_off[s]..arc_off[s+1], in fsg_model_arcs order */
+    const uint8_t *link_flag; /* [n_link] bit0: word gives no right context (filler or single phone) */
+    const int32_t *arc_off;   /* [n_state+1] */
+    const int32_t *root;      /* [n_state] first root pnode of the state's lextree, -1 if none */
+    const int32_t *pnode8;    /* [n_pnode][8] ssid tmatid logs2prob ci_ext leaf (succ | link) sibling ppos */
+    const uint32_t *ctxt;     /* [n_pnode][4] fsg_pnode_ctxt_t */
+} ssb_fsg_graph_t;
+
+typedef struct ssb_fsg_in_s {
+    int32_t n_utts;
+    const float *feat;        /* [frames][sum featlen], utterance u = frame_off[u]..frame_off[u+1] */
+    const int64_t *frame_off;
+    int32_t n_graphs;
+    const ssb_fsg_graph_t *graphs;
+    const int32_t *utt_graph; /* [n_utts] graph searched for each utterance */
+    int32_t hist_cap;         /* history entries kept per utterance (overflow: utt_rv = -2) */
+    int32_t max_seg;          /* segmentation entries returned per utterance */
+} ssb_fsg_in_t;
+
+typedef struct ssb_fsg_out_s {
+    int32_t *segs;       /* [n_utts][max_seg][5] link sf ef ascr lscr (fsg_seg_bp2itor) */
+    int32_t *n_seg;      /* [n_utts] entries used; < 0: -needed when max_seg is too small */
+    int32_t *hyp_score;  /* [n_utts] score of the best final exit (fsg_search_hyp) */
+    int32_t *exit_bp;    /* [n_utts] its history index; -1: "does not match the grammar", 0: no hypothesis */
+    int32_t *utt_rv;     /* [n_utts] 0, or -2 on history overflow */
+    int32_t *n_hist;     /* [n_utts] history entries created (optional) */
+    int64_t *n_hmm_eval; /* [n_utts] HMM evaluations (optional) */
+    int32_t *hist9;      /* optional [n_utts][hist_cap][9] link score pred frame lc rc[4] */
+    float *kernel_ms;    /* optional [4] gmm_topn, senone_mix, fsg_search, backtrace */
+    int32_t n_launches;  /* kernels launched (written by the call) */
+} ssb_fsg_out_t;
+/* Dense ("compallsen") senone scoring + search + backtrace of a batch of utterances. */
+int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out_t *out);
+
 /* single HMM step on the device (ref: src/hmm.c:482-567); st = score[5] hist[5]
  * out_score out_hist, updated in place; returns best score via *best */
 int ssb_hmm_vit_eval(ssb_model_t *m, int32_t n_emit, int32_t tmatid, const uint16_t *senid,

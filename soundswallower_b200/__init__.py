@@ -24,7 +24,7 @@ WORST_SCORE = -536870912  # ref: include/soundswallower/hmm.h:80
 MODEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "model")
 
 __all__ = ["AcousticModel", "PtmMgau", "StateAlignBatch", "align_batch", "score_batch",
-           "topn_batch", "tc_probe", "hmm_vit_eval", "windows", "plan_chain", "propagate", "flags2list", "device_count",
+           "topn_batch", "tc_probe", "fsg_batch", "hmm_vit_eval", "windows", "plan_chain", "propagate", "flags2list", "device_count",
            "SsbError", "Config", "MODEL_DIR", "INT_MAX", "WORST_SCORE"]
 
 
@@ -427,6 +427,69 @@ def tc_probe(model, feats):
     hot = hot.reshape(model.n_mgau, model.n_feat, 128)[:, :, :model.n_density]
     eps = np.where(hot[None], eps2[..., 1:2], eps2[..., 0:1])
     return cw, sc, approx, eps, dict(hot=hot, eps_regular=eps2[..., 0], exact_evals=int(cnt[0]), scan_steps=int(cnt[1]), slow_steps=int(cnt[2]))
+
+
+def fsg_batch(model, feats, graphs, utt_graph=None, hist_cap=4096, max_seg=256, want_hist=False):
+    """fsg_search over a batch (first pass / grammar decoding) on dense senone scores.
+
+    graphs: list of dicts with the flattened FSG + lextree (keys n_state start final n_ciphone
+    sil beam pbeam wbeam maxhmmpf link link_flag arc_off root pnode ctxt -- the reference's
+    fsg_model_t / fsg_lextree_t, see ssb_fsg_graph_t).  utt_graph[u] = graph of utterance u
+    (default: all use graph 0).  Returns a list of per-utterance dicts: segs [n][5] (link sf ef
+    ascr lscr), hyp_score, exit, rv, n_hist, n_hmm_eval[, hist [n_hist][9]] and, on the first
+    one, kernel_ms / n_launches of the call."""
+    feats = [np.ascontiguousarray(f, np.float32).reshape(-1, model.blk) for f in feats]
+    U = len(feats)
+    off = np.zeros(U + 1, np.int64)
+    for i, f in enumerate(feats):
+        off[i + 1] = off[i] + f.shape[0]
+    feat = np.concatenate(feats) if feats else np.zeros((0, model.blk), np.float32)
+    ug = np.zeros(U, np.int32) if utt_graph is None else np.ascontiguousarray(utt_graph, np.int32)
+    keep = []
+    garr = (_lib.FsgGraph * max(len(graphs), 1))()
+    for i, G in enumerate(graphs):
+        a = dict(link=np.ascontiguousarray(G["link"], np.int32).reshape(-1, 4),
+                 link_flag=np.ascontiguousarray(G["link_flag"], np.uint8),
+                 arc_off=np.ascontiguousarray(G["arc_off"], np.int32),
+                 root=np.ascontiguousarray(G["root"], np.int32),
+                 pnode=np.ascontiguousarray(G["pnode"], np.int32).reshape(-1, 8),
+                 ctxt=np.ascontiguousarray(G["ctxt"], np.uint32).reshape(-1, 4))
+        keep.append(a)
+        g = garr[i]
+        g.n_state, g.start, g.final = int(G["n_state"]), int(G["start"]), int(G["final"])
+        g.n_link, g.n_pnode = len(a["link"]), len(a["pnode"])
+        g.n_ciphone, g.sil = int(G["n_ciphone"]), int(G["sil"])
+        g.beam, g.pbeam, g.wbeam, g.maxhmmpf = (int(G[k]) for k in ("beam", "pbeam", "wbeam", "maxhmmpf"))
+        g.link4, g.link_flag, g.arc_off = (a[k].ctypes.data for k in ("link", "link_flag", "arc_off"))
+        g.root, g.pnode8, g.ctxt = (a[k].ctypes.data for k in ("root", "pnode", "ctxt"))
+    fin = _lib.FsgIn()
+    fin.n_utts, fin.feat, fin.frame_off = U, feat.ctypes.data, off.ctypes.data
+    fin.n_graphs, fin.graphs, fin.utt_graph = len(graphs), garr, ug.ctypes.data
+    fin.hist_cap, fin.max_seg = int(hist_cap), int(max_seg)
+    segs = np.zeros((U, max_seg, 5), np.int32)
+    n_seg, score, exit_bp, rv, n_hist = (np.zeros(U, np.int32) for _ in range(5))
+    n_eval = np.zeros(U, np.int64)
+    hist = np.zeros((U, hist_cap, 9), np.int32) if want_hist else None
+    ms = np.zeros(4, np.float32)
+    fo = _lib.FsgOut()
+    fo.segs, fo.n_seg, fo.hyp_score, fo.exit_bp = (a.ctypes.data for a in (segs, n_seg, score, exit_bp))
+    fo.utt_rv, fo.n_hist, fo.n_hmm_eval = rv.ctypes.data, n_hist.ctypes.data, n_eval.ctypes.data
+    fo.hist9 = hist.ctypes.data if hist is not None else None
+    fo.kernel_ms = ms.ctypes.data
+    _lib.check(model.lib.ssb_fsg_batch(model.h, C.byref(fin), C.byref(fo)), "ssb_fsg_batch")
+    out = []
+    for u in range(U):
+        d = dict(segs=segs[u, :max(int(n_seg[u]), 0)].copy(), n_seg=int(n_seg[u]), hyp_score=int(score[u]),
+                 exit=int(exit_bp[u]), rv=int(rv[u]), n_hist=int(n_hist[u]), n_hmm_eval=int(n_eval[u]))
+        if hist is not None:
+            d["hist"] = hist[u, :int(n_hist[u])].copy()
+        out.append(d)
+    if out:
+        out[0]["kernel_ms"] = dict(gmm_topn=float(ms[0]), senone_mix=float(ms[1]), fsg_search=float(ms[2]),
+                                   backtrace=float(ms[3]))
+        out[0]["n_launches"] = int(fo.n_launches)
+    del keep
+    return out
 
 
 def hmm_vit_eval(model, tmatid, senid, senscr, st):

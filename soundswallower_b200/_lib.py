@@ -38,6 +38,27 @@ class AlignOut(C.Structure):
                 ("chain_scr", C.POINTER(C.c_int16)), ("tokens", C.POINTER(C.c_int32))]
 
 
+class FsgGraph(C.Structure):
+    """ssb_fsg_graph_t: the reference's fsg_model_t + fsg_lextree_t flattened."""
+    _fields_ = [(k, C.c_int32) for k in ("n_state", "start", "final", "n_link", "n_pnode", "n_ciphone",
+                                          "sil", "beam", "pbeam", "wbeam", "maxhmmpf")] + \
+               [("link4", C.c_void_p), ("link_flag", C.c_void_p), ("arc_off", C.c_void_p),
+                ("root", C.c_void_p), ("pnode8", C.c_void_p), ("ctxt", C.c_void_p)]
+
+
+class FsgIn(C.Structure):
+    _fields_ = [("n_utts", C.c_int32), ("feat", C.c_void_p), ("frame_off", C.c_void_p),
+                ("n_graphs", C.c_int32), ("graphs", C.POINTER(FsgGraph)), ("utt_graph", C.c_void_p),
+                ("hist_cap", C.c_int32), ("max_seg", C.c_int32)]
+
+
+class FsgOut(C.Structure):
+    _fields_ = [("segs", C.c_void_p), ("n_seg", C.c_void_p), ("hyp_score", C.c_void_p),
+                ("exit_bp", C.c_void_p), ("utt_rv", C.c_void_p), ("n_hist", C.c_void_p),
+                ("n_hmm_eval", C.c_void_p), ("hist9", C.c_void_p), ("kernel_ms", C.c_void_p),
+                ("n_launches", C.c_int32)]
+
+
 MGAU_FRAME_EVAL = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int16), C.POINTER(C.c_uint8),
                               C.c_int32, C.POINTER(C.POINTER(C.c_float)), C.c_int32, C.c_int32)
 
@@ -61,7 +82,7 @@ SYMBOLS = [
     "ssb_plan_chain", "ssb_batch_create", "ssb_batch_free", "ssb_batch_upload", "ssb_batch_run",
     "ssb_batch_download", "ssb_batch_debug_tokens", "ssb_batch_kernel_ms",
     "ssb_batch_n_launches", "ssb_batch_stats", "ssb_align_batch", "ssb_score_batch",
-    "ssb_topn_batch", "ssb_tc_probe", "ssb_tc_hot_mask", "ssb_hmm_vit_eval",
+    "ssb_topn_batch", "ssb_tc_probe", "ssb_tc_hot_mask", "ssb_fsg_batch", "ssb_hmm_vit_eval",
 ]
 
 _lib = None
@@ -117,6 +138,7 @@ def load():
     L.ssb_tc_probe.restype = i64
     L.ssb_tc_probe.argtypes = [vp, vp, vp, i32, vp, vp, vp, vp, vp]
     L.ssb_tc_hot_mask.argtypes = [vp, vp]
+    L.ssb_fsg_batch.argtypes = [vp, P(FsgIn), P(FsgOut)]
     L.ssb_hmm_vit_eval.argtypes = [vp, i32, i32, vp, vp, vp, P(i32)]
     _lib = L
     return L

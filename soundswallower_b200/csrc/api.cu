@@ -1485,3 +1485,207 @@ extern "C" int ssb_hmm_vit_eval(ssb_model_t *m, int32_t n_emit, int32_t tmatid,
     o.release();
     return rv;
 }
+
+// ------------------------------------------------------------------ FSG search (K4)
+// frames per dense-score slab of the FSG path: whole utterances, <= ~12 GB of int16 scores
+static const int64_t kFsgSlabFrames = 1200000;
+
+extern "C" int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out_t *out)
+{
+    if (!in || !out || in->n_utts < 0 || in->n_graphs < 0 || in->hist_cap < 2 || in->max_seg < 1
+        || (in->n_utts > 0 && (!in->frame_off || !in->graphs || !in->utt_graph || in->n_graphs < 1))) {
+        set_error("ssb_fsg_batch: bad arguments");
+        return -1;
+    }
+    if (need_device(m) != 0)
+        return -1;
+    const HostModel &h = m->h;
+    const int U = in->n_utts;
+    if (U == 0)
+        return 0;
+    // ---- validate + concatenate the graphs
+    std::vector<DevFsg> hdr(in->n_graphs);
+    std::vector<int32_t> link4, arc_off, root, pnode8;
+    std::vector<uint8_t> link_flag;
+    std::vector<uint32_t> ctxt;
+    int tent_cap = 16;
+    for (int gi = 0; gi < in->n_graphs; ++gi) {
+        const ssb_fsg_graph_t &g = in->graphs[gi];
+        if (g.n_state < 1 || g.n_link < 0 || g.n_pnode < 0 || g.n_ciphone < 1 || g.n_ciphone > 128
+            || g.start < 0 || g.start >= g.n_state || g.final < 0 || g.final >= g.n_state
+            || g.sil < 0 || g.sil >= g.n_ciphone || !g.arc_off || !g.root
+            || (g.n_link && (!g.link4 || !g.link_flag)) || (g.n_pnode && (!g.pnode8 || !g.ctxt))) {
+            set_error("ssb_fsg_batch: graph %d is malformed", gi);
+            return -1;
+        }
+        if (g.arc_off[0] != 0 || g.arc_off[g.n_state] != g.n_link) {
+            set_error("ssb_fsg_batch: graph %d: arc_off must span the %d links", gi, g.n_link);
+            return -1;
+        }
+        for (int i = 0; i < g.n_link; ++i) {
+            const int32_t *l = g.link4 + i * 4;
+            if (l[0] < 0 || l[0] >= g.n_state || l[1] < 0 || l[1] >= g.n_state) {
+                set_error("ssb_fsg_batch: graph %d link %d: state out of range", gi, i);
+                return -1;
+            }
+        }
+        for (int i = 0; i < g.n_pnode; ++i) {
+            const int32_t *p = g.pnode8 + i * 8;
+            const bool leaf = p[4] != 0;
+            if (p[0] < 0 || p[0] >= h.n_sseq || p[1] < 0 || p[1] >= h.n_tmat || p[3] < 0
+                || p[3] >= g.n_ciphone || p[6] < -1 || p[6] >= g.n_pnode
+                || (leaf ? (p[5] < 0 || p[5] >= g.n_link) : (p[5] < -1 || p[5] >= g.n_pnode))) {
+                set_error("ssb_fsg_batch: graph %d pnode %d is malformed", gi, i);
+                return -1;
+            }
+        }
+        for (int s = 0; s < g.n_state; ++s)
+            if (g.root[s] < -1 || g.root[s] >= g.n_pnode || g.arc_off[s] > g.arc_off[s + 1]) {
+                set_error("ssb_fsg_batch: graph %d state %d is malformed", gi, s);
+                return -1;
+            }
+        DevFsg &d = hdr[gi];
+        d.n_state = g.n_state;
+        d.start = g.start;
+        d.final = g.final;
+        d.n_link = g.n_link;
+        d.n_pnode = g.n_pnode;
+        d.n_ciphone = g.n_ciphone;
+        d.sil = g.sil;
+        d.beam = g.beam;
+        d.pbeam = g.pbeam;
+        d.wbeam = g.wbeam;
+        d.maxhmmpf = g.maxhmmpf;
+        d.link_off = (int32_t)(link4.size() / 4);
+        d.arcoff_off = (int32_t)arc_off.size();
+        d.root_off = (int32_t)root.size();
+        d.pnode_off = (int32_t)(pnode8.size() / 8);
+        link4.insert(link4.end(), g.link4, g.link4 + (size_t)g.n_link * 4);
+        link_flag.insert(link_flag.end(), g.link_flag, g.link_flag + g.n_link);
+        arc_off.insert(arc_off.end(), g.arc_off, g.arc_off + g.n_state + 1);
+        root.insert(root.end(), g.root, g.root + g.n_state);
+        pnode8.insert(pnode8.end(), g.pnode8, g.pnode8 + (size_t)g.n_pnode * 8);
+        ctxt.insert(ctxt.end(), g.ctxt, g.ctxt + (size_t)g.n_pnode * 4);
+        tent_cap = std::max(tent_cap, g.n_pnode + g.n_link + 16);
+    }
+    std::vector<int64_t> ws_off(U + 1, 0);
+    std::vector<int32_t> utt_graph(in->utt_graph, in->utt_graph + U);
+    for (int u = 0; u < U; ++u) {
+        if (utt_graph[u] < 0 || utt_graph[u] >= in->n_graphs) {
+            set_error("ssb_fsg_batch: utterance %d names graph %d of %d", u, utt_graph[u], in->n_graphs);
+            return -1;
+        }
+        const DevFsg &d = hdr[utt_graph[u]];
+        ws_off[u + 1] = ws_off[u] + (int64_t)d.n_pnode * (FSG_PH + 2) + (int64_t)d.n_state * d.n_ciphone
+                        + tent_cap + (int64_t)tent_cap * FSG_TE;
+    }
+    ssb_batch_t *b = ssb_batch_create(m, nullptr);
+    if (!b)
+        return -1;
+    DBuf d_hdr, d_link4, d_flag, d_arc, d_root, d_pnode, d_ctxt, d_ug, d_wsoff, d_ws, d_hist, d_nhist,
+        d_neval, d_frames, d_rv, d_exit, d_score, d_segs, d_nseg;
+    int rv = -1;
+    do {
+        if (score_prepare(b, in->feat, in->frame_off, U) != 0)
+            break;
+        cudaStream_t st = b->st;
+        const DevModel &d = m->d;
+        const int64_t G = b->n_frames;
+        const size_t hist_ints = (size_t)U * in->hist_cap * 9;
+        if (upload(d_hdr, hdr, st) || upload(d_link4, link4, st) || upload(d_flag, link_flag, st)
+            || upload(d_arc, arc_off, st) || upload(d_root, root, st) || upload(d_pnode, pnode8, st)
+            || upload(d_ctxt, ctxt, st) || upload(d_ug, utt_graph, st) || upload(d_wsoff, ws_off, st)
+            || d_ws.ensure(std::max<size_t>((size_t)ws_off[U] * 4, 16)) || d_hist.ensure(hist_ints * 4)
+            || d_nhist.ensure((size_t)U * 4) || d_neval.ensure((size_t)U * 8) || d_frames.ensure((size_t)U * 4)
+            || d_rv.ensure((size_t)U * 4) || d_exit.ensure((size_t)U * 4) || d_score.ensure((size_t)U * 4)
+            || d_segs.ensure((size_t)U * in->max_seg * 5 * 4) || d_nseg.ensure((size_t)U * 4))
+            break;
+        DevFsgSet gs;
+        gs.graph = d_hdr.as<DevFsg>();
+        gs.link4 = d_link4.as<int32_t>();
+        gs.link_flag = d_flag.as<uint8_t>();
+        gs.arc_off = d_arc.as<int32_t>();
+        gs.root = d_root.as<int32_t>();
+        gs.pnode8 = d_pnode.as<int32_t>();
+        gs.ctxt = d_ctxt.as<uint32_t>();
+        launch_count(true);
+        cudaEventRecord(b->ev[0], st);
+        if (G > 0
+            && launch_gmm_topn(d, b->plan, b->feat.as<float>(), G, b->tn_s.as<int4>(),
+                               b->tn_c.as<uchar4>(), b->featp.as<float>(), st) != 0)
+            break;
+        cudaEventRecord(b->ev[1], st);
+        // dense senone scores slab by slab (whole utterances), searched as soon as they exist
+        bool ok = true;
+        float ms_mix = 0.f, ms_search = 0.f;
+        int u0 = 0;
+        while (u0 < U && ok) {
+            int u1 = u0 + 1;
+            while (u1 < U && b->frame_off[u1 + 1] - b->frame_off[u0] <= kFsgSlabFrames)
+                ++u1;
+            const int64_t g0 = b->frame_off[u0], n = b->frame_off[u1] - g0;
+            cudaEventRecord(b->ev[2], st);
+            if (n > 0)
+                ok = b->dense.ensure((size_t)n * d.n_sen * 2) == 0
+                     && b->best_tmp.ensure((size_t)n * (1 + SSB_MAX_FEAT) * 4) == 0
+                     && launch_senone_mix_all(d, b->tn_s.as<int4>(), b->tn_c.as<uchar4>(), G, g0, n,
+                                              b->dense.as<int16_t>(), b->best_tmp.as<int32_t>(), st) == 0
+                     && launch_subtract_best(d, b->dense.as<int16_t>(), b->best_tmp.as<int32_t>(), n, st) == 0;
+            cudaEventRecord(b->ev[3], st);
+            ok = ok
+                 && launch_fsg_search(d, gs, b->d_frame_off.as<int64_t>(), d_ug.as<int32_t>(),
+                                      d_wsoff.as<int64_t>(), d_ws.as<int32_t>(), b->dense.as<int16_t>(), g0,
+                                      u0, u1 - u0, d_hist.as<int32_t>(), in->hist_cap, tent_cap,
+                                      d_nhist.as<int32_t>(), d_neval.as<int64_t>(), d_frames.as<int32_t>(),
+                                      d_rv.as<int32_t>(), st) == 0;
+            cudaEventRecord(b->ev[4], st);
+            if (ok && cudaEventSynchronize(b->ev[4]) == cudaSuccess) {
+                float a = 0.f, c = 0.f;
+                cudaEventElapsedTime(&a, b->ev[2], b->ev[3]);
+                cudaEventElapsedTime(&c, b->ev[3], b->ev[4]);
+                ms_mix += a;
+                ms_search += c;
+            }
+            u0 = u1;
+        }
+        if (!ok)
+            break;
+        cudaEventRecord(b->ev[2], st);
+        if (launch_fsg_backtrace(gs, d_ug.as<int32_t>(), 0, U, d_hist.as<int32_t>(), in->hist_cap,
+                                 d_nhist.as<int32_t>(), d_frames.as<int32_t>(), d_exit.as<int32_t>(),
+                                 d_score.as<int32_t>(), d_segs.as<int32_t>(), in->max_seg,
+                                 d_nseg.as<int32_t>(), st) != 0)
+            break;
+        cudaEventRecord(b->ev[3], st);
+        struct { void *dst; DBuf *src; size_t bytes; } copies[] = {
+            {out->segs, &d_segs, (size_t)U * in->max_seg * 5 * 4}, {out->n_seg, &d_nseg, (size_t)U * 4},
+            {out->hyp_score, &d_score, (size_t)U * 4}, {out->exit_bp, &d_exit, (size_t)U * 4},
+            {out->utt_rv, &d_rv, (size_t)U * 4}, {out->n_hist, &d_nhist, (size_t)U * 4},
+            {out->n_hmm_eval, &d_neval, (size_t)U * 8}, {out->hist9, &d_hist, hist_ints * 4}};
+        for (auto &c : copies)
+            if (c.dst && cudaMemcpyAsync(c.dst, c.src->p, c.bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+                ok = false;
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (!ok || e != cudaSuccess) {
+            set_error("ssb_fsg_batch: %s", cudaGetErrorString(e != cudaSuccess ? e : cudaGetLastError()));
+            break;
+        }
+        if (out->kernel_ms) {
+            float k1 = 0.f, bt = 0.f;
+            cudaEventElapsedTime(&k1, b->ev[0], b->ev[1]);
+            cudaEventElapsedTime(&bt, b->ev[2], b->ev[3]);
+            out->kernel_ms[0] = k1;
+            out->kernel_ms[1] = ms_mix;
+            out->kernel_ms[2] = ms_search;
+            out->kernel_ms[3] = bt;
+        }
+        out->n_launches = launch_count(true);
+        rv = 0;
+    } while (0);
+    DBuf *all[] = {&d_hdr, &d_link4, &d_flag, &d_arc, &d_root, &d_pnode, &d_ctxt, &d_ug, &d_wsoff, &d_ws,
+                   &d_hist, &d_nhist, &d_neval, &d_frames, &d_rv, &d_exit, &d_score, &d_segs, &d_nseg};
+    for (DBuf *x : all)
+        x->release();
+    ssb_batch_free(b);
+    return rv;
+}

@@ -118,6 +118,31 @@ int launch_chain_viterbi(const DevModel &m, const DevPlan &p, const int16_t *cha
 int launch_backtrace(const DevModel &m, const DevPlan &p, const int2 *tokens,
                      const int32_t *fin_hist, const int32_t *fin_score, int32_t *st_start,
                      int32_t *st_dur, int32_t *st_score, int32_t *utt_rv, cudaStream_t st);
+// ---- K4: FSG token passing (fsg_search.cu) ----
+struct DevFsg {  // one grammar: sizes, beams, offsets into the concatenated arrays of DevFsgSet
+    int32_t n_state, start, final, n_link, n_pnode, n_ciphone, sil, beam, pbeam, wbeam, maxhmmpf;
+    int32_t link_off, arcoff_off, root_off, pnode_off;
+};
+struct DevFsgSet {
+    const DevFsg *graph;       // [n_graphs]
+    const int32_t *link4;      // concatenated [.][4]: from to logs2prob wid
+    const uint8_t *link_flag;  // concatenated
+    const int32_t *arc_off;    // concatenated, n_state+1 per graph (values local to the graph)
+    const int32_t *root;       // concatenated
+    const int32_t *pnode8;     // concatenated [.][8]: ssid tmat logs2prob ci_ext leaf succ|link sibling ppos
+    const uint32_t *ctxt;      // concatenated [.][4]
+};
+constexpr int FSG_PH = 14;  // ints of HMM state per pnode
+constexpr int FSG_TE = 10;  // ints per tentative history entry
+int launch_fsg_search(const DevModel &m, const DevFsgSet &gs, const int64_t *frame_off,
+                      const int32_t *utt_graph, const int64_t *ws_off, int32_t *ws,
+                      const int16_t *dense, int64_t g0, int u0, int n_utts, int32_t *hist,
+                      int hist_cap, int tent_cap, int32_t *n_hist, int64_t *n_eval, int32_t *frames,
+                      int32_t *rv, cudaStream_t st);
+int launch_fsg_backtrace(const DevFsgSet &gs, const int32_t *utt_graph, int u0, int n_utts,
+                         const int32_t *hist, int hist_cap, const int32_t *n_hist,
+                         const int32_t *frames, int32_t *exit_bp, int32_t *hyp_score, int32_t *segs,
+                         int max_seg, int32_t *n_seg, cudaStream_t st);
 // single-frame scorer behind the mgau vtable
 struct FrameHist {
     int4 *score[2];    // [CS] per history slot

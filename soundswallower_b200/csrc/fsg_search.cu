@@ -1,0 +1,490 @@
+// fsg_search.cu -- K4: FSG token passing over a flattened lextree, one warp per utterance.
+//
+// Replaces fsg_search_start / step / finish and their helpers (ref: src/fsg_search.c:309-851),
+// the history table (ref: src/fsg_history.c:129-232) and the backtrace behind
+// fsg_search_hyp / fsg_search_seg_iter (ref: src/fsg_search.c:853-924, 1030-1142).  The graph
+// (FSG + per-state phonetic lextrees with their cross-word context sets) is built on the host
+// by the caller -- fsg_lextree.c / fsg_model.c are graph preparation, not the per-frame path --
+// and arrives as flat arrays (include/ssb200.h: ssb_fsg_graph_t).  Senone scores are dense
+// ("compallsen" semantics), computed by K1 + K2 for the whole batch beforehand.
+//
+// The search is beam pruned and pointer chasing: a handful of HMMs (~5) are alive per frame
+// whatever the grammar size, history entries are inserted into per-(state, left-context)
+// lists whose order decides ties.  All of that is kept literally, so it runs sequentially on
+// lane 0; the warp's other lanes evaluate the active HMMs in parallel (the only data-parallel
+// piece) and the machine is filled by utterances: 4096 utterances = 4096 warps.  Integer
+// work: results are bit-exact (history table, scores, segmentation).
+#include "hmm_step.cuh"
+
+namespace ssb {
+
+struct FsgUtt {  // per-utterance view, set up once by every lane
+    const DevFsg *g;
+    const int32_t *link4, *arc_off, *root, *pnode8;
+    const uint8_t *link_flag;
+    const uint32_t *ctxt;
+    int32_t *phmm, *act, *nxt, *heads, *touched, *tent;
+    int32_t *hist;
+    int cap, tent_cap;
+    // lane-0 state
+    int n_act, n_nxt, n_hist, n_tent, n_touched, overflow;
+    int32_t frame, bestscore, bpidx_start, beam, pbeam, wbeam;
+    float beam_factor;
+};
+
+constexpr int PH = FSG_PH;  // phmm: score[5] hist[5] out_score out_hist frame bestscore
+constexpr int TE = FSG_TE;  // tentative entry: link score pred frame lc rc[4] next
+
+__device__ __forceinline__ void ph_clear(int32_t *h)
+{
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        h[i] = WORST_SCORE;
+        h[5 + i] = -1;
+    }
+    h[10] = WORST_SCORE;
+    h[11] = -1;
+    h[12] = -1;
+    h[13] = WORST_SCORE;
+}
+
+__device__ __forceinline__ void ph_enter(int32_t *h, int32_t score, int32_t hist, int32_t frame)
+{
+    h[0] = score;
+    h[5] = hist;
+    h[12] = frame;
+}
+
+__device__ void hist_append(FsgUtt &s, const int32_t *e9)
+{
+    if (s.n_hist >= s.cap) {
+        s.overflow = 1;
+        return;
+    }
+    int32_t *o = s.hist + (size_t)s.n_hist * 9;
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+        o[k] = e9[k];
+    ++s.n_hist;
+}
+
+// ref: src/fsg_history.c:129-202
+__device__ void entry_add(FsgUtt &s, int link, int32_t frame, int32_t score, int32_t pred, int32_t lc,
+                          const uint32_t *rc_in)
+{
+    uint32_t rc[4] = {rc_in[0], rc_in[1], rc_in[2], rc_in[3]};
+    if (frame < 0) {
+        int32_t e[9] = {link, score, pred, frame, lc, (int32_t)rc[0], (int32_t)rc[1], (int32_t)rc[2],
+                        (int32_t)rc[3]};
+        hist_append(s, e);
+        return;
+    }
+    const int hidx = s.link4[link * 4 + 1] * s.g->n_ciphone + lc;
+    int prev = -1, gn;
+    for (gn = s.heads[hidx]; gn >= 0; gn = s.tent[gn * TE + 9]) {
+        const int32_t *e = s.tent + gn * TE;
+        if (score > e[1])
+            break;
+        uint32_t left = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            left |= (rc[k] = ~(uint32_t)e[5 + k] & rc[k]);
+        if (left == 0)
+            return;
+        prev = gn;
+    }
+    if (s.n_tent >= s.tent_cap) {
+        s.overflow = 1;
+        return;
+    }
+    const int k = s.n_tent++;
+    int32_t *ne = s.tent + k * TE;
+    ne[0] = link;
+    ne[1] = score;
+    ne[2] = pred;
+    ne[3] = frame;
+    ne[4] = lc;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        ne[5 + q] = (int32_t)rc[q];
+    ne[9] = gn;
+    if (prev < 0) {
+        if (s.heads[hidx] < 0)
+            s.touched[s.n_touched++] = hidx;
+        s.heads[hidx] = k;
+    } else
+        s.tent[prev * TE + 9] = k;
+    prev = k;
+    while (gn >= 0) {
+        int32_t *e = s.tent + gn * TE;
+        uint32_t left = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t v = ~rc[q] & (uint32_t)e[5 + q];
+            e[5 + q] = (int32_t)v;
+            left |= v;
+        }
+        const int nx = e[9];
+        if (left == 0)
+            s.tent[prev * TE + 9] = nx;  // pruned
+        else
+            prev = gn;
+        gn = nx;
+    }
+}
+
+// ref: src/fsg_history.c:208-232 -- (state, left context) lists in ascending order
+__device__ void end_frame(FsgUtt &s)
+{
+    // insertion sort of the few touched list heads
+    for (int i = 1; i < s.n_touched; ++i) {
+        const int v = s.touched[i];
+        int j = i - 1;
+        for (; j >= 0 && s.touched[j] > v; --j)
+            s.touched[j + 1] = s.touched[j];
+        s.touched[j + 1] = v;
+    }
+    for (int i = 0; i < s.n_touched; ++i) {
+        const int hidx = s.touched[i];
+        for (int gn = s.heads[hidx]; gn >= 0; gn = s.tent[gn * TE + 9])
+            hist_append(s, s.tent + gn * TE);
+        s.heads[hidx] = -1;
+    }
+    s.n_touched = 0;
+    s.n_tent = 0;
+}
+
+// ref: src/fsg_search.c:543-591
+__device__ void null_prop(FsgUtt &s)
+{
+    const int32_t thresh = s.bestscore + s.wbeam;
+    const int n = s.n_hist;
+    for (int bp = s.bpidx_start; bp < n; ++bp) {
+        int32_t he[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+            he[k] = s.hist[(size_t)bp * 9 + k];
+        const int st = he[0] >= 0 ? s.link4[he[0] * 4 + 1] : s.g->start;
+        for (int a = s.arc_off[st]; a < s.arc_off[st + 1]; ++a) {
+            if (s.link4[a * 4 + 3] != -1)
+                continue;
+            const int32_t newscore = he[1] + (s.link4[a * 4 + 2] >> SENSCR_SHIFT);
+            if (newscore >= thresh)
+                entry_add(s, a, he[3], newscore, bp, he[4], reinterpret_cast<const uint32_t *>(he + 5));
+        }
+    }
+}
+
+// ref: src/fsg_search.c:597-662
+__device__ void word_trans(FsgUtt &s)
+{
+    const int32_t thresh = s.bestscore + s.beam, nf = s.frame + 1;
+    const int n = s.n_hist;
+    for (int bp = s.bpidx_start; bp < n; ++bp) {
+        const int32_t *he = s.hist + (size_t)bp * 9;
+        const int d = he[0] >= 0 ? s.link4[he[0] * 4 + 1] : s.g->start;
+        const int lc = he[4];
+        const int32_t score = he[1];
+        for (int root = s.root[d]; root >= 0; root = s.pnode8[root * 8 + 6]) {
+            const int rc = s.pnode8[root * 8 + 3];
+            if ((s.ctxt[root * 4 + (lc >> 5)] & (1u << (lc & 31)))
+                && ((uint32_t)he[5 + (rc >> 5)] & (1u << (rc & 31)))) {
+                const int32_t newscore = score + s.pnode8[root * 8 + 2];
+                int32_t *h = s.phmm + root * PH;
+                if (newscore > thresh && newscore > h[0]) {
+                    if (h[12] < nf)
+                        s.nxt[s.n_nxt++] = root;
+                    ph_enter(h, newscore, bp, nf);
+                }
+            }
+        }
+    }
+}
+
+// one warp per utterance; dense = senone scores of frames [g0, ...), row-major [frame][n_sen]
+__global__ void __launch_bounds__(128)
+fsg_search_kernel(DevModel m, DevFsgSet gs, const int64_t *__restrict__ frame_off,
+                  const int32_t *__restrict__ utt_graph, const int64_t *__restrict__ ws_off,
+                  int32_t *__restrict__ ws, const int16_t *__restrict__ dense, int64_t g0, int u0,
+                  int n_utts, int32_t *__restrict__ hist_all, int hist_cap, int tent_cap,
+                  int32_t *__restrict__ n_hist_out, int64_t *__restrict__ n_eval_out,
+                  int32_t *__restrict__ frames_out, int32_t *__restrict__ rv_out)
+{
+    const int lane = threadIdx.x & 31;
+    const int u = u0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (u >= u0 + n_utts)
+        return;
+    FsgUtt s;
+    const DevFsg *g = gs.graph + utt_graph[u];
+    s.g = g;
+    s.link4 = gs.link4 + (size_t)g->link_off * 4;
+    s.link_flag = gs.link_flag + g->link_off;
+    s.arc_off = gs.arc_off + g->arcoff_off;
+    s.root = gs.root + g->root_off;
+    s.pnode8 = gs.pnode8 + (size_t)g->pnode_off * 8;
+    s.ctxt = gs.ctxt + (size_t)g->pnode_off * 4;
+    int32_t *w = ws + ws_off[u];
+    const int NP = g->n_pnode, NH = g->n_state * g->n_ciphone;
+    s.phmm = w;
+    s.act = s.phmm + (size_t)NP * PH;
+    s.nxt = s.act + NP;
+    s.heads = s.nxt + NP;
+    s.touched = s.heads + NH;
+    s.tent = s.touched + tent_cap;
+    s.tent_cap = tent_cap;
+    s.hist = hist_all + (size_t)u * hist_cap * 9;
+    s.cap = hist_cap;
+    const int T = (int)(frame_off[u + 1] - frame_off[u]);
+    const int16_t *scr = dense + (frame_off[u] - g0) * m.n_sen;
+    const int E = m.n_emit;
+
+    for (int i = lane; i < NP; i += 32)
+        ph_clear(s.phmm + i * PH);
+    for (int i = lane; i < NH; i += 32)
+        s.heads[i] = -1;
+    __syncwarp();
+    s.n_act = s.n_nxt = s.n_hist = s.n_tent = s.n_touched = s.overflow = 0;
+    long long n_eval = 0;
+    if (lane == 0) {
+        // fsg_search_start (ref :746-798)
+        const uint32_t all[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        s.beam_factor = 1.0f;
+        s.beam = g->beam;
+        s.pbeam = g->pbeam;
+        s.wbeam = g->wbeam;
+        s.frame = -1;
+        s.bestscore = 0;
+        entry_add(s, -1, -1, 0, -1, g->sil, all);
+        s.bpidx_start = 0;
+        null_prop(s);
+        word_trans(s);
+        for (int i = 0; i < s.n_nxt; ++i)
+            s.act[i] = s.nxt[i];
+        s.n_act = s.n_nxt;
+        s.n_nxt = 0;
+        s.frame = 0;
+    }
+    __syncwarp();
+    for (int t = 0; t < T; ++t) {
+        const int n_act = __shfl_sync(0xffffffffu, s.n_act, 0);
+        const int16_t *ss = scr + (size_t)t * m.n_sen;
+        // fsg_search_hmm_eval (ref :330-398): the active HMMs in parallel
+        int32_t best = WORST_SCORE;
+        for (int i = lane; i < n_act; i += 32) {
+            const int pn = s.act[i];
+            int32_t *h = s.phmm + pn * PH;
+            const uint16_t *sid = m.sseq + (size_t)s.pnode8[pn * 8 + 0] * E;
+            int32_t sc[3] = {h[0], h[1], h[2]}, hi[3] = {h[5], h[6], h[7]}, o_s = h[10], o_h = h[11];
+            const int sv[3] = {ss[sid[0]], ss[sid[1]], ss[sid[2]]};
+            const int32_t b = hmm_step3(m.tp + (size_t)s.pnode8[pn * 8 + 1] * 12, sv, sc, hi, o_s, o_h);
+            h[0] = sc[0];
+            h[1] = sc[1];
+            h[2] = sc[2];
+            h[5] = hi[0];
+            h[6] = hi[1];
+            h[7] = hi[2];
+            h[10] = o_s;
+            h[11] = o_h;
+            h[13] = b;
+            best = max(best, b);
+        }
+        for (int o = 16; o > 0; o >>= 1)
+            best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+        __syncwarp();
+        if (lane == 0) {
+            s.bpidx_start = s.n_hist;
+            if (s.n_act > 0) {
+                n_eval += s.n_act;
+                if (g->maxhmmpf != -1 && s.n_act > g->maxhmmpf) {
+                    if (s.beam_factor > 0.1) {
+                        s.beam_factor *= 0.9f;
+                        s.beam = (int32_t)(g->beam * s.beam_factor);
+                        s.pbeam = (int32_t)(g->pbeam * s.beam_factor);
+                        s.wbeam = (int32_t)(g->wbeam * s.beam_factor);
+                    }
+                } else {
+                    s.beam_factor = 1.0f;
+                    s.beam = g->beam;
+                    s.pbeam = g->pbeam;
+                    s.wbeam = g->wbeam;
+                }
+                s.bestscore = best;
+            }
+            // fsg_search_hmm_prune_prop (ref :497-538); "prepended" lists are walked backwards
+            const int32_t thresh = s.bestscore + s.beam, phone_thresh = s.bestscore + s.pbeam,
+                          word_thresh = s.bestscore + s.wbeam;
+            const int32_t nf = s.frame + 1;
+            for (int i = s.n_act - 1; i >= 0; --i) {
+                const int pn = s.act[i];
+                int32_t *h = s.phmm + pn * PH;
+                if (h[13] >= thresh) {
+                    if (h[12] == s.frame) {
+                        h[12] = nf;
+                        s.nxt[s.n_nxt++] = pn;
+                    }
+                    if (!s.pnode8[pn * 8 + 4]) {
+                        if (h[10] >= phone_thresh) {
+                            // fsg_search_pnode_trans (ref :400-428)
+                            for (int child = s.pnode8[pn * 8 + 5]; child >= 0; child = s.pnode8[child * 8 + 6]) {
+                                const int32_t newscore = h[10] + s.pnode8[child * 8 + 2];
+                                int32_t *c = s.phmm + child * PH;
+                                if (newscore > thresh && newscore > c[0]) {
+                                    if (c[12] < nf)
+                                        s.nxt[s.n_nxt++] = child;
+                                    ph_enter(c, newscore, h[11], nf);
+                                }
+                            }
+                        }
+                    } else if (h[10] >= word_thresh) {
+                        // fsg_search_pnode_exit (ref :430-489)
+                        const uint32_t all[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+                        const int link = s.pnode8[pn * 8 + 5];
+                        const uint32_t *rc = (s.link_flag[link] & 1) ? all : s.ctxt + pn * 4;
+                        entry_add(s, link, s.frame, h[10], h[11], s.pnode8[pn * 8 + 3], rc);
+                    }
+                }
+            }
+            end_frame(s);
+            null_prop(s);
+            end_frame(s);
+            word_trans(s);
+            for (int i = s.n_act - 1; i >= 0; --i) {
+                int32_t *h = s.phmm + s.act[i] * PH;
+                if (h[12] == s.frame)
+                    ph_clear(h);
+            }
+            int32_t *tmp = s.act;
+            s.act = s.nxt;
+            s.nxt = tmp;
+            s.n_act = s.n_nxt;
+            s.n_nxt = 0;
+            ++s.frame;
+        }
+        // every lane follows the list swap
+        s.act = reinterpret_cast<int32_t *>(__shfl_sync(0xffffffffu, (unsigned long long)s.act, 0));
+        __syncwarp();
+    }
+    if (lane == 0) {
+        n_hist_out[u] = s.n_hist;
+        n_eval_out[u] = n_eval;
+        frames_out[u] = s.frame;
+        rv_out[u] = s.overflow ? -2 : 0;
+    }
+}
+
+// ref: src/fsg_search.c:853-924 (find_exit, final = TRUE) and :1030-1142 (segmentation).
+// One thread per utterance.  segs [u][max_seg][5] = link sf ef ascr lscr, first word first.
+__global__ void fsg_backtrace_kernel(DevFsgSet gs, const int32_t *__restrict__ utt_graph, int u0,
+                                     int n_utts, const int32_t *__restrict__ hist_all, int hist_cap,
+                                     const int32_t *__restrict__ n_hist, const int32_t *__restrict__ frames,
+                                     int32_t *__restrict__ exit_bp, int32_t *__restrict__ hyp_score,
+                                     int32_t *__restrict__ segs, int max_seg, int32_t *__restrict__ n_seg)
+{
+    const int u = u0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= u0 + n_utts)
+        return;
+    const DevFsg *g = gs.graph + utt_graph[u];
+    const int32_t *link4 = gs.link4 + (size_t)g->link_off * 4;
+    const int32_t *hist = hist_all + (size_t)u * hist_cap * 9;
+    const int frame_idx = frames[u];
+    int bpidx = n_hist[u] - 1, frm = frame_idx, last_frm = frame_idx, besthist = -1;
+    int32_t bestscore = INT32_MIN;
+    const int32_t *e = nullptr;
+    n_seg[u] = 0;
+    hyp_score[u] = 0;
+    while (bpidx > 0) {
+        e = hist + (size_t)bpidx * 9;
+        if (e[3] <= frame_idx) {
+            frm = last_frm = e[3];
+            break;
+        }
+        --bpidx;
+    }
+    if (bpidx <= 0) {
+        exit_bp[u] = bpidx;
+        return;
+    }
+    while (frm == last_frm) {
+        const int link = e[0];
+        const int32_t score = e[1];
+        if (link < 0)
+            break;
+        if (score == bestscore && link4[link * 4 + 1] == g->final)
+            besthist = bpidx;
+        else if (score > bestscore && link4[link * 4 + 1] == g->final) {
+            bestscore = score;
+            besthist = bpidx;
+        }
+        --bpidx;
+        if (bpidx < 0)
+            break;
+        e = hist + (size_t)bpidx * 9;
+        frm = e[3];
+    }
+    exit_bp[u] = besthist;
+    if (besthist == -1)
+        return;  // "Final result does not match the grammar"
+    hyp_score[u] = bestscore;
+    int n = 0;
+    for (int bp = besthist; bp > 0; bp = hist[(size_t)bp * 9 + 2])
+        ++n;
+    if (n > max_seg) {
+        n_seg[u] = -n;
+        return;
+    }
+    n_seg[u] = n;
+    int32_t *so = segs + (size_t)u * max_seg * 5;
+    int cur = n - 1;
+    for (int bp = besthist; bp > 0; bp = hist[(size_t)bp * 9 + 2], --cur) {
+        const int32_t *h = hist + (size_t)bp * 9;
+        const int32_t *ph = h[2] >= 0 ? hist + (size_t)h[2] * 9 : nullptr;
+        int32_t sf = ph ? ph[3] + 1 : 0;
+        const int32_t ef = h[3];
+        const int32_t lscr = link4[h[0] * 4 + 2] >> SENSCR_SHIFT;
+        if (sf > ef)
+            sf = ef;
+        so[cur * 5 + 0] = h[0];
+        so[cur * 5 + 1] = sf;
+        so[cur * 5 + 2] = ef;
+        so[cur * 5 + 3] = ph ? h[1] - ph[1] - lscr : h[1] - lscr;
+        so[cur * 5 + 4] = lscr;
+    }
+}
+
+int launch_fsg_search(const DevModel &m, const DevFsgSet &gs, const int64_t *frame_off,
+                      const int32_t *utt_graph, const int64_t *ws_off, int32_t *ws,
+                      const int16_t *dense, int64_t g0, int u0, int n_utts, int32_t *hist,
+                      int hist_cap, int tent_cap, int32_t *n_hist, int64_t *n_eval, int32_t *frames,
+                      int32_t *rv, cudaStream_t st)
+{
+    if (n_utts <= 0)
+        return 0;
+    if (m.n_emit != 3) {
+        set_error("FSG search supports 3-state HMMs, model has %d", m.n_emit);
+        return -1;
+    }
+    const int wpb = 4;
+    fsg_search_kernel<<<(n_utts + wpb - 1) / wpb, wpb * 32, 0, st>>>(
+        m, gs, frame_off, utt_graph, ws_off, ws, dense, g0, u0, n_utts, hist, hist_cap, tent_cap,
+        n_hist, n_eval, frames, rv);
+    SSB_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+int launch_fsg_backtrace(const DevFsgSet &gs, const int32_t *utt_graph, int u0, int n_utts,
+                         const int32_t *hist, int hist_cap, const int32_t *n_hist,
+                         const int32_t *frames, int32_t *exit_bp, int32_t *hyp_score, int32_t *segs,
+                         int max_seg, int32_t *n_seg, cudaStream_t st)
+{
+    if (n_utts <= 0)
+        return 0;
+    fsg_backtrace_kernel<<<(n_utts + 63) / 64, 64, 0, st>>>(gs, utt_graph, u0, n_utts, hist, hist_cap,
+                                                           n_hist, frames, exit_bp, hyp_score, segs,
+                                                           max_seg, n_seg);
+    SSB_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+}  // namespace ssb

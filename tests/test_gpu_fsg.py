@@ -1,0 +1,97 @@
+"""K4 (FSG token passing) through the C ABI against the golden history tables of the reference
+(tests/golden/fsg_*.npz) and against the oracle on ragged / multi-grammar batches."""
+import os
+
+import numpy as np
+import pytest
+
+import soundswallower_b200 as ssb
+from conftest import GOLDEN, model_features
+from test_oracle_fsg import graph_of
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fsg_golden():
+    return {lang: np.load(os.path.join(GOLDEN, "fsg_%s.npz" % lang)) for lang in ("en-us", "fr-fr")}
+
+
+@pytest.mark.parametrize("lang", ["en-us", "fr-fr"])
+@pytest.mark.parametrize("name", ["align", "jsgf"])
+def test_fsg_golden(models, golden, fsg_golden, lang, name):
+    m, g = models(lang), fsg_golden[lang]
+    r = ssb.fsg_batch(m, [golden[lang]["feat"]], [graph_of(g, name)], want_hist=True)[0]
+    assert r["rv"] == 0
+    assert np.array_equal(r["hist"], g[name + "_hist"])
+    assert r["n_hmm_eval"] == int(g[name + "_n_hmm_eval"])
+    assert r["hyp_score"] == int(g[name + "_hyp_score"])
+    assert np.array_equal(r["segs"][:, 1:], g[name + "_segs"][:, 1:])
+    assert r["n_launches"] >= 6 and r["kernel_ms"]["fsg_search"] > 0
+
+
+def test_fsg_ragged_two_grammars(models, oracles, golden, fsg_golden):
+    """Utterances of different lengths searching different graphs in one batch, some of which
+    do not match their grammar; every history table equals the oracle's."""
+    m, o = models("en-us"), oracles("en-us")
+    g, feat = fsg_golden["en-us"], golden["en-us"]["feat"]
+    graphs = [graph_of(g, "align"), graph_of(g, "jsgf")]
+    rs = np.random.RandomState(31)
+    feats, ug = [], []
+    for u in range(37):
+        k = int(rs.randint(0, 4))
+        if k == 0:
+            f = feat
+        elif k == 1:
+            f = feat[:int(rs.randint(1, 278))]           # truncated: may not reach the final state
+        elif k == 2:
+            f = (feat + rs.normal(0, 0.3, feat.shape)).astype(np.float32)
+        else:
+            f = model_features(rs, o.model_arrays(), int(rs.randint(1, 80)))  # noise
+        feats.append(f)
+        ug.append(u % 2)
+    feats[5] = feats[5][:0]  # an empty utterance
+    res = ssb.fsg_batch(m, feats, graphs, utt_graph=ug, want_hist=True)
+    n_match = 0
+    for u, (f, r) in enumerate(zip(feats, res)):
+        w = o.fsg_search(graphs[ug[u]], o.score_all(f) if len(f) else np.zeros((0, o.n_sen), np.int16))
+        assert r["rv"] == w["rv"] == 0, u
+        assert np.array_equal(r["hist"], w["hist"]), u
+        assert r["n_hmm_eval"] == w["n_hmm_eval"], u
+        assert r["exit"] == w["exit"], u
+        if w["exit"] > 0:
+            n_match += 1
+            assert r["hyp_score"] == w["hyp_score"], u
+            assert np.array_equal(r["segs"], w["segs"]), u
+    assert n_match >= 10
+
+
+def test_fsg_history_overflow_and_bad_graph(models, golden, fsg_golden):
+    m, g = models("en-us"), fsg_golden["en-us"]
+    feat = golden["en-us"]["feat"]
+    r = ssb.fsg_batch(m, [feat[:60]], [graph_of(g, "align")], hist_cap=16)[0]
+    assert r["rv"] == -2
+    bad = dict(graph_of(g, "align"))
+    bad["pnode"] = bad["pnode"].copy()
+    bad["pnode"][3, 0] = m.n_sseq + 5
+    with pytest.raises(ssb.SsbError, match="malformed"):
+        ssb.fsg_batch(m, [feat[:10]], [bad])
+
+
+def test_config3_shape(models, golden, fsg_golden):
+    """BASELINE config #3 shape at reduced width: 256 utterances x 279 frames on goforward.gram;
+    identical inputs give identical results wherever they sit, noisy copies keep the words."""
+    m, g = models("en-us"), fsg_golden["en-us"]
+    feat = golden["en-us"]["feat"]
+    rs = np.random.RandomState(8)
+    feats = [feat] + [(feat + rs.normal(0, 0.05, feat.shape)).astype(np.float32) for _ in range(255)]
+    feats[200] = feats[0]
+    res = ssb.fsg_batch(m, feats, [graph_of(g, "jsgf")])
+    assert np.array_equal(res[0]["segs"][:, 1:], g["jsgf_segs"][:, 1:])
+    assert np.array_equal(res[200]["segs"], res[0]["segs"]) and res[200]["hyp_score"] == res[0]["hyp_score"]
+    words = [s for s in res[0]["segs"][:, 0]]
+    for r in res:
+        assert r["rv"] == 0 and r["exit"] > 0
+        assert [s for s in r["segs"][:, 0]] == words            # same link sequence (same words)
+        sf, ef = r["segs"][:, 1], r["segs"][:, 2]
+        assert sf[0] == 0 and ef[-1] == 277 and (sf[1:] >= ef[:-1]).all()
