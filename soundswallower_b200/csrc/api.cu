@@ -20,11 +20,6 @@ const char *last_error();
 int launch_senone_mix_active(const DevModel &m, const DevPlan &p, const int4 *tn_score,
                              const uchar4 *tn_cw, int64_t n_frames, int max_union,
                              int max_frames_per_utt, int16_t *chain_scr, cudaStream_t st);
-int launch_subtract_best(const DevModel &m, int16_t *dense, const int32_t *best, int64_t n,
-                         cudaStream_t st);
-int launch_gather_chain_best(const DevModel &m, const DevPlan &p, const int16_t *dense,
-                             const int32_t *best, int u0, int u1, int64_t g0, int16_t *chain_scr,
-                             cudaStream_t st);
 int launch_chain_viterbi(const DevModel &m, const DevPlan &p, const int16_t *chain_scr,
                          int2 *tokens, int32_t *spill, int64_t spill_stride, int32_t *utt_best,
                          int32_t *utt_renorm, int32_t *fin_hist, int32_t *fin_score,
@@ -1088,15 +1083,12 @@ extern "C" int ssb_batch_run(ssb_batch_t *b)
                     ++u1;
                 const int64_t g0 = b->frame_off[u0], n = b->frame_off[u1] - g0;
                 if (n > 0) {
-                    if (b->dense.ensure((size_t)n * d.n_sen * 2) != 0
-                        || b->best_tmp.ensure((size_t)n * (1 + SSB_MAX_FEAT) * 4) != 0)
+                    if (b->dense.ensure((size_t)n * d.n_sen * 2) != 0)
                         return -1;
                     if (launch_senone_mix_all(d, b->tn_s.as<int4>(), b->tn_c.as<uchar4>(),
-                                              b->n_frames, g0, n, b->dense.as<int16_t>(),
-                                              b->best_tmp.as<int32_t>(), st) != 0
-                        || launch_gather_chain_best(d, p, b->dense.as<int16_t>(),
-                                                    b->best_tmp.as<int32_t>(), u0, u1, g0,
-                                                    b->chain_scr.as<int16_t>(), st) != 0)
+                                              b->n_frames, g0, n, b->dense.as<int16_t>(), st) != 0
+                        || launch_gather_chain(d, p, b->dense.as<int16_t>(), u0, u1, g0,
+                                               b->chain_scr.as<int16_t>(), st) != 0)
                         return -1;
                 }
                 u0 = u1;
@@ -1289,12 +1281,8 @@ extern "C" int64_t ssb_score_batch(ssb_model_t *m, const float *feat, const int6
         for (int64_t g0 = 0; g0 < G && ok; g0 += kSlabFrames) {
             const int64_t n = std::min(kSlabFrames, G - g0);
             ok = b->dense.ensure((size_t)n * d.n_sen * 2) == 0
-                 && b->best_tmp.ensure((size_t)n * (1 + SSB_MAX_FEAT) * 4) == 0
                  && launch_senone_mix_all(d, b->tn_s.as<int4>(), b->tn_c.as<uchar4>(), G, g0, n,
-                                          b->dense.as<int16_t>(), b->best_tmp.as<int32_t>(),
-                                          b->st) == 0
-                 && launch_subtract_best(d, b->dense.as<int16_t>(), b->best_tmp.as<int32_t>(), n,
-                                         b->st) == 0;
+                                          b->dense.as<int16_t>(), b->st) == 0;
             if (ok && senscr
                 && cudaMemcpyAsync(senscr + g0 * d.n_sen, b->dense.p, (size_t)n * d.n_sen * 2,
                                    cudaMemcpyDeviceToHost, b->st) != cudaSuccess) {
@@ -1627,10 +1615,8 @@ extern "C" int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out
             cudaEventRecord(b->ev[2], st);
             if (n > 0)
                 ok = b->dense.ensure((size_t)n * d.n_sen * 2) == 0
-                     && b->best_tmp.ensure((size_t)n * (1 + SSB_MAX_FEAT) * 4) == 0
                      && launch_senone_mix_all(d, b->tn_s.as<int4>(), b->tn_c.as<uchar4>(), G, g0, n,
-                                              b->dense.as<int16_t>(), b->best_tmp.as<int32_t>(), st) == 0
-                     && launch_subtract_best(d, b->dense.as<int16_t>(), b->best_tmp.as<int32_t>(), n, st) == 0;
+                                              b->dense.as<int16_t>(), st) == 0;
             cudaEventRecord(b->ev[3], st);
             ok = ok
                  && launch_fsg_search(d, gs, b->d_frame_off.as<int64_t>(), d_ug.as<int32_t>(),

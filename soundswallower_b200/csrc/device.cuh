@@ -99,17 +99,13 @@ int launch_gmm_topn_tc(const DevModel &m, const DevPlan &p, const float *feat, i
 int launch_senone_mix_active(const DevModel &m, const DevPlan &p, const int4 *tn_score,
                              const uchar4 *tn_cw, int64_t n_frames, int max_union,
                              int max_frames_per_utt, int16_t *chain_scr, cudaStream_t st);
-// K2 (dense, compallsen): all senones of frames [g0, g0+n) -> dense [n][n_sen] BEFORE the
-// best-score subtraction; best_tmp = [n] running minimum followed by [n][SSB_MAX_FEAT] norms
+// K2 (dense, compallsen): every senone of frames [g0, g0+n) -> dense [n][n_sen], best subtracted
 int launch_senone_mix_all(const DevModel &m, const int4 *tn_score, const uchar4 *tn_cw,
                           int64_t n_frames_total, int64_t g0, int64_t n, int16_t *dense,
-                          int32_t *best_tmp, cudaStream_t st);
-int launch_subtract_best(const DevModel &m, int16_t *dense, const int32_t *best, int64_t n,
-                         cudaStream_t st);
-// dense scores of frames [g0, ...) minus best -> chain states of utterances [u0, u1)
-int launch_gather_chain_best(const DevModel &m, const DevPlan &p, const int16_t *dense,
-                             const int32_t *best, int u0, int u1, int64_t g0, int16_t *chain_scr,
-                             cudaStream_t st);
+                          cudaStream_t st);
+// dense scores of frames [g0, ...) -> chain states of utterances [u0, u1)
+int launch_gather_chain(const DevModel &m, const DevPlan &p, const int16_t *dense, int u0, int u1,
+                        int64_t g0, int16_t *chain_scr, cudaStream_t st);
 // K3: chain Viterbi + token stack; K3b: backtrace
 int launch_chain_viterbi(const DevModel &m, const DevPlan &p, const int16_t *chain_scr,
                          int2 *tokens, int32_t *spill, int64_t spill_stride, int32_t *utt_best,

@@ -16,8 +16,9 @@
 //    run of frames, stages the mixture-weight COLUMNS of that utterance's senones
 //    in shared memory once (3*128*W bytes), and emits the int16 score of every
 //    chain state -- 2 B per state-frame is all that reaches HBM.
-//  * senone_mix_all (compallsen): CTAs own a codebook, stage its ~47 KB weight
-//    slab, and stream frames.
+//  * senone_dense (compallsen): CTAs own tiles of frames, keep the tile's raw scores in
+//    shared memory until the frame minimum is known, and read the mixture weights as
+//    coalesced 32-byte runs straight from L2 (neighbouring senones share their codebook).
 #include "device.cuh"
 
 namespace ssb {
@@ -257,164 +258,169 @@ int launch_senone_mix_active(const DevModel &m, const DevPlan &p, const int4 *tn
 }
 
 // ---------------------------------------------------------------- dense (compallsen)
-// per-frame, per-stream normaliser over ALL codebooks: norm[g][f]
-__global__ void norm_all_kernel(DevModel m, const int4 *__restrict__ tn_s, int64_t G, int64_t g0,
-                                int64_t n, int32_t *__restrict__ norm)
-{
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n)
-        return;
-    for (int f = 0; f < m.n_feat; ++f) {
-        int nm = WORST_SCORE;
-        for (int cb = 0; cb < m.n_mgau; ++cb)
-            nm = max(nm, tn_s[(int64_t)(cb * m.n_feat + f) * G + g0 + i].x >> SENSCR_SHIFT);
-        norm[i * SSB_MAX_FEAT + f] = nm;
-    }
-}
+// Every senone of every frame: what acmod_score returns with compallsen (ref: src/acmod.c:
+// 822-860), best score already subtracted.  CTA = tile of F frames.  Phase A parks the
+// normalised top-N of all codebook-streams of the tile in shared memory (normaliser = max over
+// ALL codebooks); phase B gives every thread a run of senone ids: neighbouring senones share
+// their codebook almost always (ids are grouped by phone), so a warp reads the same 12
+// mixture-weight rows at 32 consecutive bytes -- coalesced straight out of L2, no staging;
+// the raw scores of the tile stay in shared memory until the frame's minimum is known, then
+// one coalesced int16 row per frame goes to HBM (2 B per score is all the HBM traffic).
+constexpr int KD_THREADS = 256;
 
-constexpr int K2A_F = 32;
-
-// grid: x = codebook, y = frame slices.  dense[(g-g0)][sen] receives the score BEFORE the
-// best-score subtraction; best[g-g0] the running minimum.
-__global__ void __launch_bounds__(K2_THREADS)
-senone_mix_all_kernel(DevModel m, const int4 *__restrict__ tn_s, const uchar4 *__restrict__ tn_c,
-                      int64_t G, int64_t g0, int64_t n, const int32_t *__restrict__ norm,
-                      int Wc, int staged, int16_t *__restrict__ dense, int32_t *__restrict__ best)
+__global__ void __launch_bounds__(KD_THREADS)
+senone_dense_kernel(DevModel m, const int4 *__restrict__ tn_s, const uchar4 *__restrict__ tn_c,
+                    int64_t G, int64_t g0, int64_t n, int F, int16_t *__restrict__ dense)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    const int cb = blockIdx.x;
-    const int ND = m.n_density, NF = m.n_feat, N = m.topn;
-    const int s0 = m.cb_sen_off[cb], ncs = m.cb_sen_off[cb + 1] - s0;
-    uint8_t *lut = smem;
-    uchar4 *tile_s = reinterpret_cast<uchar4 *>(smem + 256);  // [F][NF]
-    uchar4 *tile_c = tile_s + K2A_F * SSB_MAX_FEAT;
-    int *tbest = reinterpret_cast<int *>(tile_c + K2A_F * SSB_MAX_FEAT);  // [F]
-    uint8_t *mw = reinterpret_cast<uint8_t *>(tbest + K2A_F);             // [NF*ND][Wc]
+    const int CS = m.n_mgau * m.n_feat, NF = m.n_feat, ND = m.n_density, N = m.topn;
+    const int n_sen = m.n_sen;
+    const int CSP = (CS + 3) & ~3;
+    uint8_t *lut = smem;                                          // 256
+    int *norm = reinterpret_cast<int *>(smem + 256);              // [F][SSB_MAX_FEAT]
+    int *best = norm + F * SSB_MAX_FEAT;                          // [F]
+    uchar4 *wt_s = reinterpret_cast<uchar4 *>(best + F);          // [F][CSP]
+    uchar4 *wt_c = wt_s + (size_t)F * CSP;                        // [F][CSP]
+    uint8_t *s2c = reinterpret_cast<uint8_t *>(wt_c + (size_t)F * CSP);  // [n_sen]
+    int16_t *scr = reinterpret_cast<int16_t *>(s2c + ((n_sen + 15) & ~15));  // [F][n_sen]
     for (int i = threadIdx.x; i < 256; i += blockDim.x)
         lut[i] = m.lut8[i];
-    if (staged) {
-        const int rows = NF * ND;
-        for (int idx = threadIdx.x; idx < rows * ncs; idx += blockDim.x) {
-            int r = idx / ncs, j = idx - r * ncs;
-            mw[r * Wc + j] = m.mixw[(int64_t)r * m.n_sen + m.cb_sen[s0 + j]];
+    for (int i = threadIdx.x; i < n_sen; i += blockDim.x)
+        s2c[i] = m.sen2cb[i];
+    for (int64_t base = (int64_t)blockIdx.x * F; base < n; base += (int64_t)gridDim.x * F) {
+        const int nf = (int)min((int64_t)F, n - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < F * SSB_MAX_FEAT; i += blockDim.x)
+            norm[i] = WORST_SCORE;
+        if (threadIdx.x < F)
+            best[threadIdx.x] = INT32_MAX;
+        __syncthreads();
+        // A: raw top-N -> per-stream normaliser over all codebooks
+        for (int idx = threadIdx.x; idx < nf * CS; idx += blockDim.x) {
+            const int fr = idx % nf, cs = idx / nf;
+            const int v = tn_s[(int64_t)cs * G + g0 + base + fr].x >> SENSCR_SHIFT;
+            atomicMax(&norm[fr * SSB_MAX_FEAT + cs % NF], v);
         }
-    }
-    __syncthreads();
-    if (ncs == 0)
-        return;
-    for (int64_t base = (int64_t)blockIdx.y * K2A_F; base < n; base += (int64_t)gridDim.y * K2A_F) {
-        const int nf = (int)min((int64_t)K2A_F, n - base);
-        if (threadIdx.x < nf * NF) {
-            int fr = threadIdx.x / NF, f = threadIdx.x - fr * NF;
-            int64_t g = (int64_t)(cb * NF + f) * G + g0 + base + fr;
-            int4 rs = tn_s[g];
-            int nm = norm[(base + fr) * SSB_MAX_FEAT + f];
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nf * CS; idx += blockDim.x) {
+            const int fr = idx % nf, cs = idx / nf;
+            const int64_t g = (int64_t)cs * G + g0 + base + fr;
+            const int4 rs = tn_s[g];
+            const int nm = norm[fr * SSB_MAX_FEAT + cs % NF];
             uchar4 q;
             q.x = (unsigned char)min(MAX_NEG_ASCR, nm - (rs.x >> SENSCR_SHIFT));
             q.y = (unsigned char)min(MAX_NEG_ASCR, nm - (rs.y >> SENSCR_SHIFT));
             q.z = (unsigned char)min(MAX_NEG_ASCR, nm - (rs.z >> SENSCR_SHIFT));
             q.w = (unsigned char)min(MAX_NEG_ASCR, nm - (rs.w >> SENSCR_SHIFT));
-            tile_s[fr * SSB_MAX_FEAT + f] = q;
-            tile_c[fr * SSB_MAX_FEAT + f] = tn_c[g];
+            wt_s[fr * CSP + cs] = q;
+            wt_c[fr * CSP + cs] = tn_c[g];
         }
-        if (threadIdx.x < K2A_F)
-            tbest[threadIdx.x] = INT32_MAX;
         __syncthreads();
-        for (int idx = threadIdx.x; idx < nf * ncs; idx += blockDim.x) {
-            int fr = idx / ncs, j = idx - fr * ncs;
-            int sen = m.cb_sen[s0 + j];
-            int ascore = 0;
-            for (int f = 0; f < NF; ++f) {
-                const uchar4 sv = tile_s[fr * SSB_MAX_FEAT + f];
-                const uchar4 cv = tile_c[fr * SSB_MAX_FEAT + f];
-                const int sc[4] = {sv.x, sv.y, sv.z, sv.w};
-                const int cw[4] = {cv.x, cv.y, cv.z, cv.w};
-                int fden = 0;
+        // B: every senone of every frame of the tile
+        for (int fr = 0; fr < nf; ++fr) {
+            int local_best = INT32_MAX;
+            for (int sen = threadIdx.x; sen < n_sen; sen += blockDim.x) {
+                const int cb = s2c[sen];
+                int ascore = 0;
+                if (NF == 3 && N == 4) {
+                    // the bundled shape: all 12 weight loads in flight before any arithmetic
+                    uchar4 sv[3], cv[3];
+                    int w[12];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (k < N) {
-                        int w = staged ? mw[(f * ND + cw[k]) * Wc + j]
-                                       : m.mixw[(int64_t)(f * ND + cw[k]) * m.n_sen + sen];
-                        int v = w + sc[k];
-                        fden = k == 0 ? v : logadd8(fden, v, lut);
+                    for (int f = 0; f < 3; ++f) {
+                        sv[f] = wt_s[fr * CSP + cb * 3 + f];
+                        cv[f] = wt_c[fr * CSP + cb * 3 + f];
+                    }
+                    const uint32_t base_s = (uint32_t)sen;
+#pragma unroll
+                    for (int f = 0; f < 3; ++f) {
+                        const uint8_t *row = m.mixw + (uint32_t)(f * ND) * (uint32_t)n_sen + base_s;
+                        w[4 * f + 0] = __ldg(row + (uint32_t)cv[f].x * (uint32_t)n_sen);
+                        w[4 * f + 1] = __ldg(row + (uint32_t)cv[f].y * (uint32_t)n_sen);
+                        w[4 * f + 2] = __ldg(row + (uint32_t)cv[f].z * (uint32_t)n_sen);
+                        w[4 * f + 3] = __ldg(row + (uint32_t)cv[f].w * (uint32_t)n_sen);
+                    }
+#pragma unroll
+                    for (int f = 0; f < 3; ++f) {
+                        int fden = w[4 * f] + sv[f].x;
+                        fden = logadd8(fden, w[4 * f + 1] + sv[f].y, lut);
+                        fden = logadd8(fden, w[4 * f + 2] + sv[f].z, lut);
+                        fden = logadd8(fden, w[4 * f + 3] + sv[f].w, lut);
+                        ascore += fden;
+                    }
+                } else {
+                    for (int f = 0; f < NF; ++f) {
+                        const uchar4 sv = wt_s[fr * CSP + cb * NF + f];
+                        const uchar4 cv = wt_c[fr * CSP + cb * NF + f];
+                        const int sc[4] = {sv.x, sv.y, sv.z, sv.w};
+                        const int cw[4] = {cv.x, cv.y, cv.z, cv.w};
+                        const uint8_t *row = m.mixw + (int64_t)f * ND * n_sen + sen;
+                        int fden = 0;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (k < N) {
+                                const int v = (int)__ldg(row + (int64_t)cw[k] * n_sen) + sc[k];
+                                fden = k == 0 ? v : logadd8(fden, v, lut);
+                            }
+                        }
+                        ascore += fden;
                     }
                 }
-                ascore += fden;
+                scr[(size_t)fr * n_sen + sen] = (int16_t)ascore;
+                local_best = min(local_best, ascore);
             }
-            dense[(base + fr) * m.n_sen + sen] = (int16_t)ascore;
-            atomicMin(&tbest[fr], ascore);
+            for (int o = 16; o > 0; o >>= 1)
+                local_best = min(local_best, __shfl_xor_sync(0xffffffffu, local_best, o));
+            if ((threadIdx.x & 31) == 0)
+                atomicMin(&best[fr], local_best);
         }
         __syncthreads();
-        if (threadIdx.x < nf && tbest[threadIdx.x] != INT32_MAX)
-            atomicMin(&best[base + threadIdx.x], tbest[threadIdx.x]);
-        __syncthreads();
+        // C: subtract the frame's best (ref: src/ptm_mgau.c:398-400), one coalesced row per frame
+        for (int fr = 0; fr < nf; ++fr) {
+            const int16_t b16 = (int16_t)best[fr];
+            int16_t *dst = dense + (base + fr) * n_sen;
+            for (int sen = threadIdx.x; sen < n_sen; sen += blockDim.x)
+                dst[sen] = (int16_t)(scr[(size_t)fr * n_sen + sen] - b16);
+        }
     }
 }
 
-__global__ void fill_i32_kernel(int32_t *p, int64_t n, int32_t v)
-{
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n)
-        p[i] = v;
-}
-
-__global__ void subtract_best_kernel(int16_t *__restrict__ dense, const int32_t *__restrict__ best,
-                                     int64_t n, int n_sen)
-{
-    int64_t row = blockIdx.x;
-    if (row >= n)
-        return;
-    int16_t b = (int16_t)best[row];
-    int16_t *r = dense + row * n_sen;
-    for (int i = threadIdx.x; i < n_sen; i += blockDim.x)
-        r[i] = (int16_t)(r[i] - b);
-}
-
-// best_tmp: [n] int32 followed by [n][SSB_MAX_FEAT] int32 normalisers
+// dense [n][n_sen] = final senone scores of frames [g0, g0 + n)
 int launch_senone_mix_all(const DevModel &m, const int4 *tn_score, const uchar4 *tn_cw,
                           int64_t n_frames_total, int64_t g0, int64_t n, int16_t *dense,
-                          int32_t *best_tmp, cudaStream_t st)
+                          cudaStream_t st)
 {
     if (n == 0)
         return 0;
-    int32_t *best = best_tmp, *norm = best_tmp + n;
-    fill_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(best, n, INT32_MAX);
-    norm_all_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(m, tn_score, n_frames_total, g0, n,
-                                                                 norm);
-    int Wc = (m.max_cb_sen + 3) & ~3;
-    size_t fixed = 256 + (size_t)2 * K2A_F * SSB_MAX_FEAT * 4 + K2A_F * 4;
-    size_t smem = fixed + (size_t)m.n_feat * m.n_density * Wc;
-    int staged = smem <= 200 * 1024;
-    if (!staged)
-        smem = fixed;
-    SSB_CUDA(cudaFuncSetAttribute(senone_mix_all_kernel,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t slices64 = (n + K2A_F - 1) / K2A_F;
-    int slices = slices64 > 16 ? 16 : (int)slices64;
-    dim3 grid(m.n_mgau, slices);
-    senone_mix_all_kernel<<<grid, K2_THREADS, smem, st>>>(m, tn_score, tn_cw, n_frames_total, g0, n,
-                                                          norm, Wc, staged, dense, best);
+    const int CSP = (m.n_mgau * m.n_feat + 3) & ~3;
+    const size_t fixed = 256 + ((m.n_sen + 15) & ~15) + 16;
+    auto need = [&](int F) {
+        return fixed + (size_t)F * (SSB_MAX_FEAT + 1) * 4 + (size_t)2 * F * CSP * 4 + (size_t)F * m.n_sen * 2;
+    };
+    int F = 8;
+    while (F > 1 && need(F) > 56 * 1024)
+        F >>= 1;
+    if (need(F) > 200 * 1024) {
+        set_error("dense senone scoring: %d senones do not fit the shared-memory tile", m.n_sen);
+        return -1;
+    }
+    const size_t smem = need(F);
+    SSB_CUDA(cudaFuncSetAttribute(senone_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int64_t tiles = (n + F - 1) / F;
+    const int grid = (int)(tiles < (int64_t)sms * 8 ? tiles : (int64_t)sms * 8);
+    senone_dense_kernel<<<grid, KD_THREADS, smem, st>>>(m, tn_score, tn_cw, n_frames_total, g0, n, F,
+                                                        dense);
     SSB_CUDA(cudaGetLastError());
     note_launch();
     return 0;
 }
 
-int launch_subtract_best(const DevModel &m, int16_t *dense, const int32_t *best, int64_t n,
-                         cudaStream_t st)
-{
-    if (n == 0)
-        return 0;
-    subtract_best_kernel<<<(unsigned)n, 256, 0, st>>>(dense, best, n, m.n_sen);
-    SSB_CUDA(cudaGetLastError());
-    note_launch();
-    return 0;
-}
-
-// chain_scr[u][t][si] = dense[g][senone(si)] - best[g] for utterances [u0,u1) whose frames
-// lie in [g0, ...)
+// chain_scr[u][t][si] = dense[g][senone(si)] for utterances [u0,u1) whose frames start at g0
 __global__ void gather_chain_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ dense,
-                                    const int32_t *__restrict__ best, int u0, int64_t g0,
-                                    int16_t *__restrict__ chain_scr)
+                                    int u0, int64_t g0, int16_t *__restrict__ chain_scr)
 {
     const int u = u0 + blockIdx.y;
     const int64_t f0 = p.frame_off[u];
@@ -424,24 +430,22 @@ __global__ void gather_chain_kernel(DevModel m, DevPlan p, const int16_t *__rest
     const int E = m.n_emit;
     for (int t = blockIdx.x; t < T; t += gridDim.x) {
         const int64_t row = f0 + t - g0;
-        const int16_t b = (int16_t)best[row];
         int16_t *dst = chain_scr + p.scr_off[u] + (int64_t)t * ns;
         for (int si = threadIdx.x; si < ns; si += blockDim.x) {
             int ph = si / E, j = si - ph * E;
             int sen = m.sseq[(int64_t)p.ssid[ph0 + ph] * E + j];
-            dst[si] = (int16_t)(dense[row * m.n_sen + sen] - b);
+            dst[si] = dense[row * m.n_sen + sen];
         }
     }
 }
 
-int launch_gather_chain_best(const DevModel &m, const DevPlan &p, const int16_t *dense,
-                             const int32_t *best, int u0, int u1, int64_t g0, int16_t *chain_scr,
-                             cudaStream_t st)
+int launch_gather_chain(const DevModel &m, const DevPlan &p, const int16_t *dense, int u0, int u1,
+                        int64_t g0, int16_t *chain_scr, cudaStream_t st)
 {
     if (u1 <= u0)
         return 0;
     dim3 grid(64, u1 - u0);
-    gather_chain_kernel<<<grid, 128, 0, st>>>(m, p, dense, best, u0, g0, chain_scr);
+    gather_chain_kernel<<<grid, 128, 0, st>>>(m, p, dense, u0, g0, chain_scr);
     SSB_CUDA(cudaGetLastError());
     note_launch();
     return 0;
