@@ -89,31 +89,63 @@ def make_config2_batch(g, n_utts, noise=0.05, seed=1234, frames=FRAMES, out=None
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    """SM clock + clock-event (throttle) reasons sampled every ~20 ms while the timed region runs,
+    through NVML (nvidia-ml-py); falls back to polling nvidia-smi when NVML is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.sm, self.reasons, self.sm_max = [], set(), None
         self.stop = threading.Event()
         self.th = threading.Thread(target=self._run, daemon=True)
 
-    def _run(self):
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20,
+                "hw_thermal_slowdown": 0x40}
+        while not self.stop.is_set():
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = int(get_reasons(h))
+            for name, bit in bits.items():
+                if r & bit:
+                    self.reasons.add(name)
+            self.stop.wait(0.02)
+        nv.nvmlShutdown()
+
+    def _run_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True,
                                      text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                r = [c.strip() for c in out.split(",")]
+                if len(r) >= 7:
+                    self.sm.append(float(r[0]))
+                    self.sm_max = float(r[1])
+                    for i in range(4):
+                        if r[3 + i].lower().startswith("active"):
+                            self.reasons.add(names[i])
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.05)
+
+    def _run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
 
     def __enter__(self):
         self.th.start()
+        time.sleep(0.03)
         return self
 
     def __exit__(self, *a):
@@ -121,13 +153,8 @@ class ClockSampler:
         self.th.join(timeout=6)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows for i in range(4)
-                          if len(r) > 3 + i and r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 # ------------------------------------------------------------------ CPU legs (reference / oracle)
@@ -336,10 +363,18 @@ def main():
     upload(); batch.run(); batch.download()
     barrier()
     t0 = time.perf_counter()
+    host_split = [0.0, 0.0, 0.0]  # seconds inside upload (plan + staging), run (launches), download
     for _ in range(args.steps):
+        ta = time.perf_counter()
         upload()
+        tb = time.perf_counter()
         batch.run()
+        tc = time.perf_counter()
         res = batch.download()
+        td = time.perf_counter()
+        host_split[0] += tb - ta
+        host_split[1] += tc - tb
+        host_split[2] += td - tc
     barrier()
     e2e_s = (time.perf_counter() - t0) / args.steps
 
@@ -388,7 +423,10 @@ def main():
                    "frames_total": world * U * FRAMES, "sharding": "utt % n_gpu, no data-path collective"},
         "e2e": {"value": world * audio_s / (e2e_ms_max * 1e-3), "unit": "audio-s/s",
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e_ms_max},
+                "ms_per_step": e2e_ms_max,
+                "host_call_ms": {"upload(plan+H2D issue)": 1e3 * host_split[0] / args.steps,
+                                 "run(launch)": 1e3 * host_split[1] / args.steps,
+                                 "download(wait+D2H+scatter)": 1e3 * host_split[2] / args.steps}},
         "gpu_launches": launches,
         "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items()},
         "clocks": clocks,

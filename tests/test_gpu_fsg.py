@@ -95,3 +95,33 @@ def test_config3_shape(models, golden, fsg_golden):
         assert [s for s in r["segs"][:, 0]] == words            # same link sequence (same words)
         sf, ef = r["segs"][:, 1], r["segs"][:, 2]
         assert sf[0] == 0 and ef[-1] == 277 and (sf[1:] >= ef[:-1]).all()
+
+
+@pytest.mark.parametrize("lang", ["en-us", "fr-fr"])
+def test_two_pass_alignment_on_gpu_equals_cli(models, golden, fsg_golden, lang):
+    """BASELINE config #1 on the GPU: pass 1 = FSG search of the alignment grammar (word
+    boundaries), pass 2 = chain Viterbi inside those windows.  The state segmentation must be the
+    one the reference's CLI produces (tests/golden/align_*.npz `states`).
+    Only the word -> phone expansion (alignment_populate, host graph preparation) comes from
+    the fixture."""
+    m, g, fg = models(lang), golden[lang], fsg_golden[lang]
+    feat = g["feat"]
+    p1 = ssb.fsg_batch(m, [feat], [graph_of(fg, "align")])[0]
+    assert p1["rv"] == 0 and p1["exit"] > 0
+    segs = p1["segs"]
+    # decoder_alignment: one alignment word per segment, start = sf, duration = ef - sf + 1
+    # (ref: src/decoder.c:753-768)
+    w_start, w_dur = segs[:, 1], segs[:, 2] - segs[:, 1] + 1
+    assert np.array_equal(w_start, g["words"][:, 1]) and np.array_equal(w_dur, g["words"][:, 2])
+    parent = g["phones"][:, 6]
+    sf, ef = ssb.windows(w_start[parent], w_dur[parent])
+    chain = dict(ssid=g["phones"][:, 1].astype(np.int32), tmat=g["phones"][:, 2].astype(np.int32),
+                 sf=sf, ef=ef)
+    p2 = ssb.align_batch(m, [feat], [chain])[0]
+    st = g["states"]  # the reference's full two-pass result
+    assert p2["rv"] == 0
+    assert np.array_equal(p2["start"], st[:, 1]) and np.array_equal(p2["dur"], st[:, 2])
+    assert np.array_equal(p2["score"], st[:, 3])
+    ps, pd, pc = ssb.propagate(p2["start"], p2["dur"], p2["score"], m.n_emit)
+    assert np.array_equal(ps, g["phones"][:, 3]) and np.array_equal(pd, g["phones"][:, 4])
+    assert np.array_equal(pc, g["phones"][:, 5])
