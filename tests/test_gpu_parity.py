@@ -443,3 +443,23 @@ def test_very_long_chain_state_in_global_memory(models, oracles):
     if w["rv"] == 0:
         for k in ("start", "dur", "score"):
             assert np.array_equal(r[k], w[k]), k
+
+
+def test_long_form_five_minute_prefix(models, oracles, golden):
+    """BASELINE config #4 shape on the prefix the CPU oracle can hold: fr-fr,
+    30 114 frames (5 min), 126 repetitions = 1765 phones / 5295 states, word windows.
+    Bit-exact against the oracle, plus the invariants used for the full hour."""
+    m, o = models("fr-fr"), oracles("fr-fr")
+    x, chain = _tiled_fr(golden, 126)
+    assert x.shape[0] > 30000 and len(chain["ssid"]) == 1765
+    r = ssb.align_batch(m, [x], [chain])[0]
+    w = o.state_align(x, chain["ssid"], chain["tmat"], chain["sf"], chain["ef"])
+    assert r["rv"] == w["rv"] == 0 and r["best_score"] == w["best_score"]
+    assert r["n_renorm"] == w["n_renorm"]
+    for k in ("start", "dur", "score"):
+        assert np.array_equal(r[k], w[k]), k
+    on = r["dur"] > 0
+    start, dur = r["start"][on], r["dur"][on]
+    assert start[0] == 0 and (start[1:] == start[:-1] + dur[:-1]).all() and start[-1] + dur[-1] == x.shape[0]
+    sf, ef = np.repeat(chain["sf"], 3)[on], np.repeat(chain["ef"], 3)[on]
+    assert (start >= sf).all() and (start + dur <= ef).all()

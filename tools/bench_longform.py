@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""BASELINE config #4: fr-fr long-form alignment of ONE utterance (default 1 hour = 360 000
+frames, 714 repetitions of "avance de dix metres" = 9 997 phones / 29 991 states, word windows,
+silence padding between repetitions).  No CPU oracle at this size (its token stack alone would
+be 86 GB): the result is checked through invariants (contiguous, monotone, inside the word
+windows, whole utterance covered); tests/test_gpu_parity.py::test_long_form_five_minute_prefix
+is the bit-exact check on a prefix.  Prints one JSON line."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import soundswallower_b200 as ssb  # noqa: E402
+
+
+def build(g, reps, frames_per_rep):
+    feat, words, phones = g["feat"], g["words"], g["phones"]
+    T1 = feat.shape[0]
+    extra = frames_per_rep - T1
+    sil = feat[int(words[-1, 1]):]
+    pad = np.concatenate([sil] * (extra // len(sil) + 1))[:extra]
+    one = np.concatenate([feat, pad])
+    rs = np.random.RandomState(777)
+    x = np.concatenate([one] * reps)
+    x = (x + rs.normal(0, 0.05, x.shape)).astype(np.float32)
+    ssid, tmat, ws, wd = [], [], [], []
+    P = frames_per_rep
+    for k in range(reps):
+        for i in range(len(phones) - 1):
+            w = int(phones[i, 6])
+            s, d = int(words[w, 1]) + k * P, int(words[w, 2])
+            if w == 0 and k > 0:  # leading silence merges with the previous trailing one + padding
+                s = int(words[-1, 1]) + (k - 1) * P
+                d = k * P + int(words[0, 2]) - s
+            ssid.append(int(phones[i, 1])); tmat.append(int(phones[i, 2])); ws.append(s); wd.append(d)
+    s = int(words[-1, 1]) + (reps - 1) * P
+    ssid.append(int(phones[-1, 1])); tmat.append(int(phones[-1, 2])); ws.append(s); wd.append(reps * P - s)
+    sf, ef = ssb.windows(np.array(ws, np.int32), np.array(wd, np.int32))
+    return x, dict(ssid=np.array(ssid, np.int32), tmat=np.array(tmat, np.int32), sf=sf, ef=ef)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=714)
+    ap.add_argument("--frames-per-rep", type=int, default=504)
+    args = ap.parse_args()
+    g = np.load(os.path.join(ROOT, "tests/golden/align_fr-fr.npz"))
+    x, chain = build(g, args.reps, args.frames_per_rep)
+    m = ssb.AcousticModel(os.path.join(ROOT, "soundswallower_b200/model/fr-fr"))
+    b = ssb.StateAlignBatch(m)
+    t0 = time.perf_counter()
+    b.upload([x], [chain])
+    b.run()
+    res = b.per_utt(b.download())[0]
+    wall = time.perf_counter() - t0
+    ms = b.kernel_ms()
+    st = b.stats()
+    on = res["dur"] > 0
+    start, dur = res["start"][on], res["dur"][on]
+    sf, ef = np.repeat(chain["sf"], 3)[on], np.repeat(chain["ef"], 3)[on]
+    ok = bool(res["rv"] == 0 and start[0] == 0 and (start[1:] == start[:-1] + dur[:-1]).all()
+              and start[-1] + dur[-1] == x.shape[0] and (start >= sf).all() and (start + dur <= ef).all())
+    audio_s = x.shape[0] / 100.0
+    print(json.dumps({"workload": "config#4: fr-fr long-form, 1 utterance, %d frames, %d phones / %d states"
+                                  % (x.shape[0], len(chain["ssid"]), 3 * len(chain["ssid"])),
+                      "invariants_ok": ok, "rv": res["rv"], "n_renorm": res["n_renorm"],
+                      "states_on_path": int(on.sum()), "kernel_ms": ms, "e2e_s": wall,
+                      "audio_s_per_s_device": audio_s / (ms["total"] * 1e-3), "audio_s_per_s_e2e": audio_s / wall,
+                      "device_bytes": st["device_bytes"], "state_frames": st["state_frames"],
+                      "note": "one utterance = one active thread per codebook-stream in K1 and one CTA in K3: "
+                              "this configuration does not fill the machine (SURVEY 8e)"}))
+
+
+if __name__ == "__main__":
+    main()
