@@ -110,12 +110,22 @@ ref_model_copy(void *h, float *mean, float *var, float *det, uint8 *mixw,
                 n += L;
                 det[nd++] = s->g->det[c][f][k];
             }
-    if (s->mixw_cb)
-        return -2; /* clustered sendump not dumped here */
     for (f = 0; f < s->g->n_feat; ++f)
-        for (k = 0; k < s->g->n_density; ++k)
-            memcpy(mixw + ((size_t)f * s->g->n_density + k) * s->n_sen,
-                   s->mixw[f][k], s->n_sen);
+        for (k = 0; k < s->g->n_density; ++k) {
+            uint8 *dst = mixw + ((size_t)f * s->g->n_density + k) * s->n_sen;
+            if (!s->mixw_cb) {
+                memcpy(dst, s->mixw[f][k], s->n_sen);
+                continue;
+            }
+            /* 4-bit clustered sendump: expand with the expression the scoring loop
+             * uses (ptm_mgau.c:375-378; the nibble is chosen by the low bit of the
+             * packed byte itself) */
+            for (i = 0; i < s->n_sen; ++i) {
+                int dcw = s->mixw[f][k][i / 2];
+                dcw = (dcw & 1) ? dcw >> 4 : dcw & 0x0f;
+                dst[i] = s->mixw_cb[dcw];
+            }
+        }
     memcpy(sen2cb, s->sen2cb, s->n_sen);
     for (i = 0; i < t->n_tmat; ++i)
         for (j = 0; j < t->n_state; ++j)

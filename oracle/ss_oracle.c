@@ -233,7 +233,7 @@ load_sendump(orc_model_t *m, const char *dir)
     const uint8_t *cb = NULL;
     int f, k, s;
     if (rd_open(&r, dir, "sendump") < 0)
-        return -1;
+        return -2; /* no sendump: the caller tries mixture_weights */
     n_feat = m->n_feat;
     n_density = m->n_density;
     n_sen = m->n_sen;
@@ -300,9 +300,10 @@ load_sendump(orc_model_t *m, const char *dir)
             if (k >= n_density)
                 continue;
             for (s = 0; s < n_sen; ++s) {
-                if (cb) { /* ref: ptm_mgau.c:375-378 nibble order */
+                if (cb) { /* ref: ptm_mgau.c:375-378: the nibble is selected by the low
+                           * bit of the packed byte, not by the senone's parity */
                     int dcw = row[s / 2];
-                    dcw = (s & 1) ? dcw >> 4 : dcw & 0x0f;
+                    dcw = (dcw & 1) ? dcw >> 4 : dcw & 0x0f;
                     dst[s] = cb[dcw];
                 } else
                     dst[s] = row[s];
@@ -312,6 +313,70 @@ load_sendump(orc_model_t *m, const char *dir)
     free(r.buf);
     return 0;
 fail:
+    free(r.buf);
+    return -1;
+}
+
+/* ref: ptm_mgau.c:611-692 (uncompressed mixture_weights, used when there is no sendump),
+ * vector.c:87-113.  The floor is the "mixwfloor" default of config_defs.h:218-221, held
+ * in a float32 by the caller (ptm_mgau.c:787). */
+static void
+sum_norm_f32(float *v, int n)
+{
+    double sum = 0.0, f;
+    int i;
+    for (i = 0; i < n; ++i)
+        sum += v[i];
+    if (sum != 0.0) {
+        f = 1.0 / sum;
+        for (i = 0; i < n; ++i)
+            v[i] = (float)(v[i] * f);
+    }
+}
+
+static int
+load_mixw_float(orc_model_t *m, const char *dir)
+{
+    rd_t r;
+    int32_t n_sen, n_feat, n_comp, n, i, f, c;
+    const float flr_f = 1e-7f;
+    const double flr = flr_f;
+    float *pdf = NULL;
+    if (rd_open(&r, dir, "mixture_weights") < 0)
+        return -1;
+    if (rd_s3_header(&r) < 0)
+        goto fail;
+    if (rd_u32(&r, &n_sen, 1) < 0 || rd_u32(&r, &n_feat, 1) < 0 || rd_u32(&r, &n_comp, 1) < 0
+        || rd_u32(&r, &n, 1) < 0)
+        goto fail;
+    if (n_feat != m->n_feat || n_comp != m->n_density || n_sen != m->n_sen
+        || n != n_sen * n_feat * n_comp)
+        goto fail;
+    m->mixw = calloc((size_t)n_feat * n_comp * n_sen, 1);
+    pdf = malloc(sizeof(float) * n_comp);
+    for (i = 0; i < n_sen; ++i)
+        for (f = 0; f < n_feat; ++f) {
+            if (rd_u32(&r, pdf, n_comp) < 0)
+                goto fail;
+            sum_norm_f32(pdf, n_comp);
+            for (c = 0; c < n_comp; ++c)
+                if (pdf[c] < flr)
+                    pdf[c] = (float)flr;
+            sum_norm_f32(pdf, n_comp);
+            for (c = 0; c < n_comp; ++c) {
+                int32_t q = -orc_logmath_log(m->logbase, ORC_SENSCR_SHIFT, pdf[c]);
+                if (q > 159 || q < 0) /* MAX_NEG_MIXW */
+                    q = 159;
+                m->mixw[((size_t)f * n_comp + c) * n_sen + i] = (uint8_t)q;
+            }
+        }
+    if (rd_verify(&r) < 0)
+        goto fail;
+    free(pdf);
+    free(r.buf);
+    return 0;
+fail:
+    free(pdf);
     free(r.buf);
     return -1;
 }
@@ -501,7 +566,9 @@ orc_model_load(const char *dir, double logbase, float varfloor, double tmatfloor
         goto fail;
     if (m->n_mgau != m->n_ciphone)
         goto fail; /* not PTM (ptm_mgau.c:760) */
-    if (load_sendump(m, dir) < 0)
+    if ((c = load_sendump(m, dir)) == -2)
+        c = load_mixw_float(m, dir);
+    if (c < 0)
         goto fail;
     if (load_tmat(m, dir, tmatfloor) < 0)
         goto fail;

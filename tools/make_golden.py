@@ -180,15 +180,44 @@ def fsg(lang, raw_feat_key, text, gram):
     np.savez_compressed(os.path.join(OUT, "fsg_%s.npz" % lang), **g)
 
 
+def loaders(lang="en-us"):
+    """Weight tables and scores of the reference for the mixture-weight formats the bundled
+    models do not use (tests/model_variants.py writes the files) -> loader_variants.json."""
+    import json
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import model_variants as mv
+    src = os.path.join(MODELS, lang)
+    base = Ref(src)
+    mixw = base.model_arrays()["mixw"]
+    feat = np.load(os.path.join(OUT, "synthetic_%s.npz" % lang))["feat1"]
+    base.close()
+    out = {"lang": lang, "n_frames": int(len(feat))}
+    with tempfile.TemporaryDirectory() as tmp:
+        mv.write_clustered_sendump(src, os.path.join(tmp, "clustered"), mixw)
+        mv.write_float_mixw(src, os.path.join(tmp, "floatmixw"), mixw)
+        for name in ("clustered", "floatmixw"):
+            r = Ref(os.path.join(tmp, name), compallsen=True)
+            out[name] = {"mixw": sha(r.model_arrays()["mixw"]),
+                         "senscr": sha(r.score_all(feat).astype(np.int16))}
+            r.close()
+    with open(os.path.join(OUT, "loader_variants.json"), "w") as fh:
+        json.dump(out, fh, indent=1, sort_keys=True)
+    print(out)
+
+
 def main():
     if not available():
         raise SystemExit("oracle/_ref/libssref.so missing: run `make -C oracle ref` first")
     os.makedirs(OUT, exist_ok=True)
+    if "--loaders" in sys.argv:
+        return loaders()
     utterance("en-us", "goforward.raw", "go forward ten meters")
     utterance("fr-fr", "goforward_fr.raw", "avance de dix mètres")
     synthetic("en-us")
     fsg("en-us", "goforward.raw", "go forward ten meters", "goforward.gram")
     fsg("fr-fr", "goforward_fr.raw", "avance de dix mètres", "goforward_fr.gram")
+    loaders()
 
 
 if __name__ == "__main__":
