@@ -113,7 +113,9 @@ void ssb_mgau_free(ssb_mgau_t *mgau);
  * ssid/tmat per phone, sf = window start (0 if none), ef = window end (INT32_MAX if none). */
 typedef struct ssb_align_in_s {
     int32_t n_utts;
-    const float *feat;
+    const float *feat;        /* [frames][sum featlen]; host memory, or device memory of the
+                               * model's GPU (e.g. ssb_frontend_feat_device) that is complete
+                               * when the call is made / ordered before the batch's stream */
     const int64_t *frame_off;
     const int64_t *phone_off;
     const int32_t *ssid;
@@ -249,6 +251,76 @@ int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out_t *out);
  * out_score out_hist, updated in place; returns best score via *best */
 int ssb_hmm_vit_eval(ssb_model_t *m, int32_t n_emit, int32_t tmatid, const uint16_t *senid,
                      const int16_t *senscr, int32_t *st12, int32_t *best);
+
+/* ------------------------------------------------------------------ frontend
+ * Batched PCM -> MFCC -> CMN -> dynamic features for whole utterances: what
+ * acmod_process_raw(full_utt=TRUE) obtains from fe_start / fe_process_int16 |
+ * fe_process_float32 / fe_end (ref: src/fe_interface.c:352-360, 578-713,
+ * src/fe_sigproc.c:238-738, src/fe_noise.c:266-327) followed by
+ * feat_s2mfc2feat_block_utt (ref: src/feat.c:978-1007, 589-632; src/cmn.c:159-229).
+ * Arithmetic types are the reference's: float64 up to the log mel spectrum, float32
+ * cepstra.  Everything except the natural logarithm is evaluated in the reference's
+ * operation order with IEEE operations. */
+enum { SSB_FE_DCT = 0, SSB_FE_LEGACY = 1, SSB_FE_HTK = 2 };   /* "transform" */
+enum { SSB_FE_CMN_NONE = 0, SSB_FE_CMN_BATCH = 1 };          /* "cmn": none | batch/current */
+enum { SSB_PCM_INT16 = 0, SSB_PCM_FLOAT32 = 1 };
+typedef struct ssb_fe_config_s {
+    int32_t samprate;      /* "samprate"      16000 */
+    int32_t frate;         /* "frate"         100 */
+    int32_t ncep;          /* "ncep"          13 */
+    int32_t nfft;          /* "nfft"          0 = smallest power of two >= window */
+    int32_t nfilt;         /* "nfilt"         40 */
+    int32_t lifter;        /* "lifter"        0 */
+    int32_t remove_dc;     /* "remove_dc"     no */
+    int32_t remove_noise;  /* "remove_noise"  no */
+    int32_t unit_area;     /* "unit_area"     yes */
+    int32_t round_filters; /* "round_filters" yes */
+    int32_t doublebw;      /* "doublebw"      no */
+    int32_t transform;     /* "transform"     legacy */
+    int32_t cmn;           /* "cmn"           batch (live CMN is a streaming mode: not offered) */
+    int32_t varnorm;       /* "varnorm"       no */
+    float wlen;            /* "wlen"          0.025625 */
+    float alpha;           /* "alpha"         0.97 */
+    float lowerf;          /* "lowerf"        133.33334 */
+    float upperf;          /* "upperf"        6855.4976 */
+} ssb_fe_config_t;
+/* defaults of include/soundswallower/config_defs.h:296-449 (non-web build) */
+void ssb_fe_config_defaults(ssb_fe_config_t *c);
+/* defaults overridden by <hmmdir>/feat_params.json, as decoder_init expands "hmm"
+ * (ref: src/decoder.c:100-160).  -1 when the file asks for something this frontend does
+ * not implement (feat other than 1s_c_d_dd, an svspec that is not three equal contiguous
+ * streams, lda, agc, dither, frequency warping, logspec/smoothspec, live CMN). */
+int ssb_fe_config_from_model(const char *hmmdir, ssb_fe_config_t *c);
+
+typedef struct ssb_frontend_s ssb_frontend_t;
+/* `stream` as in ssb_batch_create.  NULL (see ssb_last_error) for parameters fe_init
+ * refuses (ref: src/fe_interface.c:270-300). */
+ssb_frontend_t *ssb_frontend_create(const ssb_fe_config_t *c, int device, void *stream);
+void ssb_frontend_free(ssb_frontend_t *fe);
+/* out8: frame_size frame_shift fft_size nfilt ncep feat_dim(=3*ncep) n_filter_coeffs 0 */
+int ssb_frontend_dims(const ssb_frontend_t *fe, int32_t *out8);
+/* frames a whole-utterance call yields for n_samples samples (fe_process_int16 with a NULL
+ * output buffer, ref: src/fe_interface.c:379-391, minus the frame fe_end cannot fill when
+ * there is no sample at all) */
+int64_t ssb_frontend_n_frames(const ssb_frontend_t *fe, int64_t n_samples);
+/* host tables (parity tests): mel filters, DCT basis, lifter, half Hamming window */
+int ssb_frontend_tables(const ssb_frontend_t *fe, int32_t *spec_start, int32_t *filt_width,
+                        float *coeffs, float *mel_cosine, float *lifter, double *hamming);
+/* Upload the samples of n_utts utterances (utterance u = samp_off[u]..samp_off[u+1], int16
+ * or float32 in [-1,1) as for fe_process_float32) and compute their features on the device;
+ * asynchronous on the frontend's stream.  Returns the total number of frames. */
+int64_t ssb_frontend_run(ssb_frontend_t *fe, const void *pcm, int32_t encoding,
+                         const int64_t *samp_off, int32_t n_utts);
+/* frame_off [n_utts+1]; mfcc [frames][ncep] (before CMN) and feat [frames][3*ncep], either
+ * may be NULL; synchronises */
+int ssb_frontend_download(ssb_frontend_t *fe, int64_t *frame_off, float *mfcc, float *feat);
+/* device pointer to feat [frames][3*ncep] of the last run, valid until the next run: may be
+ * passed as `feat` of ssb_align_in_t / ssb_fsg_in_t / ssb_score_batch (those accept host or
+ * device memory) so that features never visit the host */
+const float *ssb_frontend_feat_device(const ssb_frontend_t *fe);
+/* CUDA-event durations (ms) of the last run: [0] mel spectrum [1] noise tracker
+ * [2] cepstrum [3] CMN sums [4] dynamic features [5] whole run incl. the upload */
+int ssb_frontend_kernel_ms(ssb_frontend_t *fe, float *ms8);
 
 #ifdef __cplusplus
 }

@@ -15,7 +15,7 @@ INT_MAX = 2**31 - 1
 
 
 def build(force=False):
-    srcs = [os.path.join(HERE, f) for f in ("ss_oracle.c", "ss_oracle.h", "ss_oracle_fsg.c")]
+    srcs = [os.path.join(HERE, f) for f in ("ss_oracle.c", "ss_oracle.h", "ss_oracle_fsg.c", "ss_oracle_fe.c")]
     srcs = [s for s in srcs if os.path.exists(s)]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", HERE, "liboracle"])
@@ -265,3 +265,104 @@ class Oracle:
                                _p(np.ascontiguousarray(score, np.int32), C.c_int32),
                                _p(ps, C.c_int32), _p(pd, C.c_int32), _p(pc, C.c_int32))
         return ps, pd, pc
+
+
+class FeCfg(C.Structure):
+    """orc_fe_cfg_t; defaults = config_defs.h as the non-web build has them."""
+    _fields_ = [(k, C.c_int32) for k in ("samprate", "frate", "ncep", "nfft", "nfilt", "lifter",
+                                          "remove_dc", "remove_noise", "unit_area", "round_filters",
+                                          "doublebw", "transform", "cmn", "varnorm")] + \
+               [(k, C.c_float) for k in ("wlen", "alpha", "lowerf", "upperf")]
+
+
+TRANSFORMS = {"dct": 0, "legacy": 1, "htk": 2}
+CMN_TYPES = {"none": 0, "batch": 1, "current": 1}
+
+
+def fe_config(model_dir=None, **kw):
+    """Frontend parameters: reference defaults, overridden by the model's feat_params.json
+    (ref: src/acmod.c / config.c expansion of -hmm), overridden by keywords."""
+    import json
+    d = dict(samprate=16000, frate=100, ncep=13, nfft=0, nfilt=40, lifter=0, remove_dc=0,
+             remove_noise=0, unit_area=1, round_filters=1, doublebw=0, transform="legacy",
+             cmn="batch", varnorm=0, wlen=0.025625, alpha=0.97, lowerf=133.33334, upperf=6855.4976)
+    if model_dir:
+        with open(os.path.join(model_dir, "feat_params.json")) as fh:
+            for k, v in json.load(fh).items():
+                if k in d:
+                    d[k] = v
+    d.update(kw)
+    c = FeCfg()
+    for k, _ in FeCfg._fields_:
+        v = d[k]
+        if k == "transform":
+            v = TRANSFORMS[v]
+        elif k == "cmn":
+            v = CMN_TYPES[v]
+        setattr(c, k, int(v) if k not in ("wlen", "alpha", "lowerf", "upperf") else float(v))
+    return c
+
+
+class OracleFrontend:
+    """PCM -> MFCC -> features through the C restatement (whole utterances)."""
+
+    def __init__(self, cfg):
+        build()
+        self.lib = L = C.CDLL(LIB)
+        L.orc_fe_new.restype = C.c_void_p
+        L.orc_fe_new.argtypes = [C.POINTER(FeCfg)]
+        L.orc_fe_free.argtypes = [C.c_void_p]
+        L.orc_fe_n_frames.restype = C.c_long
+        L.orc_fe_n_frames.argtypes = [C.c_void_p, C.c_long]
+        L.orc_fe_mfcc.restype = C.c_long
+        L.orc_fe_mfcc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
+        L.orc_fe_feat.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]
+        L.orc_fe_dims.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_fe_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        self.cfg = cfg
+        h = L.orc_fe_new(C.byref(cfg))
+        if not h:
+            raise RuntimeError("orc_fe_new: unsupported frontend parameters")
+        self.h = C.c_void_p(h)
+        d = np.zeros(4, np.int32)
+        L.orc_fe_dims(self.h, d.ctypes.data)
+        self.frame_size, self.frame_shift, self.fft_size, self.n_coeffs = [int(x) for x in d]
+
+    def close(self):
+        if self.h:
+            self.lib.orc_fe_free(self.h)
+            self.h = None
+
+    def n_frames(self, n_samples):
+        return int(self.lib.orc_fe_n_frames(self.h, n_samples))
+
+    def tables(self):
+        c = self.cfg
+        out = dict(spec_start=np.zeros(c.nfilt, np.int32), filt_width=np.zeros(c.nfilt, np.int32),
+                   coeffs=np.zeros(self.n_coeffs, np.float32),
+                   mel_cosine=np.zeros((c.ncep, c.nfilt), np.float32),
+                   lifter=np.zeros(c.ncep, np.float32), hamming=np.zeros(self.frame_size // 2))
+        self.lib.orc_fe_tables(self.h, *[out[k].ctypes.data for k in
+                                         ("spec_start", "filt_width", "coeffs", "mel_cosine", "lifter", "hamming")])
+        return out
+
+    def mfcc(self, pcm, want_melspec=False):
+        pcm = np.ascontiguousarray(pcm)
+        assert pcm.dtype in (np.int16, np.float32)
+        n = self.n_frames(len(pcm))
+        out = np.zeros((n, self.cfg.ncep), np.float32)
+        mel = np.zeros((n, self.cfg.nfilt), np.float64) if want_melspec else None
+        p16 = pcm.ctypes.data if pcm.dtype == np.int16 else None
+        p32 = pcm.ctypes.data if pcm.dtype == np.float32 else None
+        got = self.lib.orc_fe_mfcc(self.h, p16, p32, len(pcm), out.ctypes.data,
+                                   mel.ctypes.data if want_melspec else None)
+        assert got == n
+        return (out, mel) if want_melspec else out
+
+    def features(self, pcm):
+        """(mfcc before CMN, feat [T][3*ncep])"""
+        raw = self.mfcc(pcm)
+        work = raw.copy()
+        feat = np.zeros((len(raw), 3 * self.cfg.ncep), np.float32)
+        self.lib.orc_fe_feat(self.h, work.ctypes.data, len(raw), feat.ctypes.data)
+        return raw, feat

@@ -214,6 +214,31 @@ ref_mfcc_from_pcm(void *h, const int16 *pcm, long nsamp, float *out, int max_fra
     return nvec;
 }
 
+/* Same through the float32 entry point (samples in [-1, 1)). */
+int
+ref_mfcc_from_f32(void *h, const float *pcm, long nsamp, float *out, int max_frames)
+{
+    ref_t *r = h;
+    fe_t *fe = r->d->acmod->fe;
+    const float *p = pcm;
+    size_t n = nsamp;
+    int nfr, nvec, ncep = fe_get_output_size(fe), t;
+    mfcc_t **buf;
+    nfr = fe_process_float32(fe, NULL, &n, NULL, 0);
+    if (nfr > max_frames)
+        return -2;
+    buf = (mfcc_t **)ckd_calloc_2d(nfr > 0 ? nfr : 1, ncep, sizeof(mfcc_t));
+    fe_start(fe);
+    p = pcm;
+    n = nsamp;
+    nvec = fe_process_float32(fe, (float32 **)&p, &n, buf, nfr);
+    nvec += fe_end(fe, buf + nvec, nfr - nvec);
+    for (t = 0; t < nvec; ++t)
+        memcpy(out + (size_t)t * ncep, buf[t], ncep * sizeof(float));
+    ckd_free_2d(buf);
+    return nvec;
+}
+
 /* Load T frames of precomputed features into the acmod as a full utterance. */
 static int
 load_features(ref_t *r, const float *feat, int T)

@@ -77,7 +77,7 @@ class Ref:
 
     def features_from_pcm(self, pcm):
         pcm = np.ascontiguousarray(pcm, np.int16)
-        maxf = len(pcm) // 100 + 16
+        maxf = len(pcm) // 80 + 16
         out = np.zeros((maxf, self.D), np.float32)
         n = self.lib.ref_features_from_pcm(self.h, _p(pcm, C.c_int16), C.c_long(len(pcm)),
                                            _p(out, C.c_float), maxf)
@@ -86,9 +86,18 @@ class Ref:
 
     def mfcc_from_pcm(self, pcm, ncep=13):
         pcm = np.ascontiguousarray(pcm, np.int16)
-        maxf = len(pcm) // 100 + 16
+        maxf = len(pcm) // 80 + 16
         out = np.zeros((maxf, ncep), np.float32)
         n = self.lib.ref_mfcc_from_pcm(self.h, _p(pcm, C.c_int16), C.c_long(len(pcm)),
+                                       _p(out, C.c_float), maxf)
+        assert n >= 0, n
+        return out[:n].copy()
+
+    def mfcc_from_f32(self, pcm, ncep=13):
+        pcm = np.ascontiguousarray(pcm, np.float32)
+        maxf = len(pcm) // 80 + 16
+        out = np.zeros((maxf, ncep), np.float32)
+        n = self.lib.ref_mfcc_from_f32(self.h, _p(pcm, C.c_float), C.c_long(len(pcm)),
                                        _p(out, C.c_float), maxf)
         assert n >= 0, n
         return out[:n].copy()

@@ -135,4 +135,24 @@ int orc_fsg_segs(const orc_fsg_t *g, const int32_t *hist9, int bpidx, int32_t *s
 int orc_propagate(int n_states, int n_emit, const int32_t *st_start, const int32_t *st_dur,
                   const int32_t *st_score, int32_t *ph_start, int32_t *ph_dur, int32_t *ph_score);
 
+/* ---- acoustic frontend (ss_oracle_fe.c), whole utterances ---- */
+enum { ORC_FE_DCT = 0, ORC_FE_LEGACY = 1, ORC_FE_HTK = 2 };
+enum { ORC_FE_CMN_NONE = 0, ORC_FE_CMN_BATCH = 1 };
+typedef struct {
+    int32_t samprate, frate, ncep, nfft, nfilt, lifter;
+    int32_t remove_dc, remove_noise, unit_area, round_filters, doublebw;
+    int32_t transform, cmn, varnorm;
+    float wlen, alpha, lowerf, upperf;
+} orc_fe_cfg_t;
+typedef struct orc_fe_s orc_fe_t;
+orc_fe_t *orc_fe_new(const orc_fe_cfg_t *cfg);
+void orc_fe_free(orc_fe_t *fe);
+int orc_fe_dims(const orc_fe_t *fe, int32_t *out4); /* frame_size shift fft_size n_coeffs */
+int orc_fe_tables(const orc_fe_t *fe, int32_t *spec_start, int32_t *filt_width, float *coeffs,
+                  float *mel_cosine, float *lifter, double *hamming);
+long orc_fe_n_frames(const orc_fe_t *fe, long n_samples);
+long orc_fe_mfcc(const orc_fe_t *fe, const int16_t *pcm16, const float *pcm32, long n_samples,
+                 float *mfcc, double *melspec);
+int orc_fe_feat(const orc_fe_t *fe, float *mfcc, long nfr, float *feat);
+
 #endif

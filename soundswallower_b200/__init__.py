@@ -25,7 +25,7 @@ MODEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "model")
 
 __all__ = ["AcousticModel", "PtmMgau", "StateAlignBatch", "align_batch", "score_batch",
            "topn_batch", "tc_probe", "fsg_batch", "hmm_vit_eval", "windows", "plan_chain", "propagate", "flags2list", "device_count",
-           "SsbError", "Config", "MODEL_DIR", "INT_MAX", "WORST_SCORE"]
+           "Frontend", "DeviceFeatures", "SsbError", "Config", "MODEL_DIR", "INT_MAX", "WORST_SCORE"]
 
 
 def _ptr(a, t=None):
@@ -219,6 +219,16 @@ def _concat_i32(seq):
     return np.concatenate(seq) if seq else np.zeros(0, np.int32)
 
 
+class _DevPtr:
+    """A raw (host or device) address with whatever keeps it alive."""
+
+    def __init__(self, addr, keep):
+        self.addr, self.keep = addr, keep
+
+    def cast(self):
+        return C.cast(C.c_void_p(self.addr), C.POINTER(C.c_float))
+
+
 class StateAlignBatch:
     """A batch of state_align_search problems resident on one GPU.
 
@@ -251,7 +261,7 @@ class StateAlignBatch:
         n_utts = len(frame_off) - 1
         a = _lib.AlignIn()
         a.n_utts = n_utts
-        a.feat = _ptr(feat, C.c_float)
+        a.feat = feat.cast() if isinstance(feat, _DevPtr) else _ptr(feat, C.c_float)
         a.frame_off = _ptr(frame_off, C.c_int64)
         a.phone_off = _ptr(phone_off, C.c_int64)
         a.ssid = _ptr(ssid, C.c_int32)
@@ -268,18 +278,16 @@ class StateAlignBatch:
 
     def upload(self, feats, chains, init_active=None, compallsen=False):
         m = self.model
-        feats = [np.ascontiguousarray(f, np.float32).reshape(-1, m.blk) for f in feats]
         assert len(feats) == len(chains)
-        frame_off = np.zeros(len(feats) + 1, np.int64)
-        phone_off = np.zeros(len(feats) + 1, np.int64)
-        for i, (f, c) in enumerate(zip(feats, chains)):
-            frame_off[i + 1] = frame_off[i] + f.shape[0]
+        fptr, frame_off, keep = _flat_feats(m, feats)
+        feat = _DevPtr(fptr, keep)
+        phone_off = np.zeros(len(chains) + 1, np.int64)
+        for i, c in enumerate(chains):
             phone_off[i + 1] = phone_off[i] + len(c["ssid"])
-        feat = np.concatenate(feats) if feats else np.zeros((0, m.blk), np.float32)
         ia = None
         if init_active is not None:
             nw = (m.n_sen + 31) // 32
-            ia = np.zeros((len(feats), nw), np.uint32)
+            ia = np.zeros((len(chains), nw), np.uint32)
             for u, sens in enumerate(init_active):
                 for s in (sens or ()):
                     ia[u, s >> 5] |= np.uint32(1 << (s & 31))
@@ -373,17 +381,13 @@ def align_batch(model, feats, chains, init_active=None, compallsen=False, want_c
 
 def score_batch(model, feats, want=True):
     """acmod_score over whole utterances with compallsen semantics: list of int16 [T][n_sen]."""
-    feats = [np.ascontiguousarray(f, np.float32).reshape(-1, model.blk) for f in feats]
-    off = np.zeros(len(feats) + 1, np.int64)
-    for i, f in enumerate(feats):
-        off[i + 1] = off[i] + f.shape[0]
-    feat = np.concatenate(feats) if feats else np.zeros((0, model.blk), np.float32)
+    fptr, off, _keep_feat = _flat_feats(model, feats)
     out = np.zeros((int(off[-1]), model.n_sen), np.int16) if want else None
-    n = model.lib.ssb_score_batch(model.h, _ptr(feat), _ptr(off), len(feats), _ptr(out))
+    n = model.lib.ssb_score_batch(model.h, C.c_void_p(fptr), _ptr(off), len(off) - 1, _ptr(out))
     _lib.check(int(n), "ssb_score_batch")
     if not want:
         return int(n)
-    return [out[off[i]:off[i + 1]] for i in range(len(feats))]
+    return [out[off[i]:off[i + 1]] for i in range(len(off) - 1)]
 
 
 def topn_batch(model, feats):
@@ -438,12 +442,8 @@ def fsg_batch(model, feats, graphs, utt_graph=None, hist_cap=4096, max_seg=256, 
     (default: all use graph 0).  Returns a list of per-utterance dicts: segs [n][5] (link sf ef
     ascr lscr), hyp_score, exit, rv, n_hist, n_hmm_eval[, hist [n_hist][9]] and, on the first
     one, kernel_ms / n_launches of the call."""
-    feats = [np.ascontiguousarray(f, np.float32).reshape(-1, model.blk) for f in feats]
-    U = len(feats)
-    off = np.zeros(U + 1, np.int64)
-    for i, f in enumerate(feats):
-        off[i + 1] = off[i] + f.shape[0]
-    feat = np.concatenate(feats) if feats else np.zeros((0, model.blk), np.float32)
+    fptr, off, _keep_feat = _flat_feats(model, feats)
+    U = len(off) - 1
     ug = np.zeros(U, np.int32) if utt_graph is None else np.ascontiguousarray(utt_graph, np.int32)
     keep = []
     garr = (_lib.FsgGraph * max(len(graphs), 1))()
@@ -463,7 +463,7 @@ def fsg_batch(model, feats, graphs, utt_graph=None, hist_cap=4096, max_seg=256, 
         g.link4, g.link_flag, g.arc_off = (a[k].ctypes.data for k in ("link", "link_flag", "arc_off"))
         g.root, g.pnode8, g.ctxt = (a[k].ctypes.data for k in ("root", "pnode", "ctxt"))
     fin = _lib.FsgIn()
-    fin.n_utts, fin.feat, fin.frame_off = U, feat.ctypes.data, off.ctypes.data
+    fin.n_utts, fin.feat, fin.frame_off = U, fptr, off.ctypes.data
     fin.n_graphs, fin.graphs, fin.utt_graph = len(graphs), garr, ug.ctypes.data
     fin.hist_cap, fin.max_seg = int(hist_cap), int(max_seg)
     segs = np.zeros((U, max_seg, 5), np.int32)
@@ -503,3 +503,142 @@ def hmm_vit_eval(model, tmatid, senid, senscr, st):
                                     _ptr(st), C.byref(best))
     _lib.check(rv, "ssb_hmm_vit_eval")
     return best.value, st
+
+
+# ---------------------------------------------------------------------------- frontend
+TRANSFORMS = {"dct": 0, "legacy": 1, "htk": 2}
+CMN_TYPES = {"none": 0, "batch": 1, "current": 1}
+
+
+class DeviceFeatures:
+    """Features of a batch that stayed in HBM (Frontend.run): accepted wherever a list of
+    per-utterance feature arrays is (align_batch, fsg_batch, score_batch, StateAlignBatch)."""
+
+    def __init__(self, frontend, ptr, frame_off, dim):
+        self.frontend, self.ptr, self.frame_off, self.dim = frontend, ptr, frame_off, dim
+
+    def __len__(self):
+        return len(self.frame_off) - 1
+
+
+def _flat_feats(model, feats):
+    """(pointer value, frame_off, keep-alive) of host arrays or DeviceFeatures."""
+    if isinstance(feats, DeviceFeatures):
+        if feats.dim != model.blk:
+            raise SsbError("feature dimension %d does not match the model (%d)" % (feats.dim, model.blk))
+        return feats.ptr, np.ascontiguousarray(feats.frame_off, np.int64), feats
+    feats = [np.ascontiguousarray(f, np.float32).reshape(-1, model.blk) for f in feats]
+    off = np.zeros(len(feats) + 1, np.int64)
+    for i, f in enumerate(feats):
+        off[i + 1] = off[i] + f.shape[0]
+    feat = np.concatenate(feats) if feats else np.zeros((0, model.blk), np.float32)
+    return feat.ctypes.data, off, feat
+
+
+class Frontend:
+    """Batched fe_t + feat_t for whole utterances (ref: src/fe_interface.c, src/fe_sigproc.c,
+    src/fe_noise.c, src/cmn.c, src/feat.c): PCM -> MFCC -> CMN -> 1s_c_d_dd features.
+
+    Frontend(hmmdir) reads <hmmdir>/feat_params.json over the reference defaults, keywords
+    override single parameters (names = the reference's config keys)."""
+
+    def __init__(self, hmmdir=None, device=0, stream=None, **params):
+        self.lib = L = _lib.load()
+        cfg = _lib.FeConfig()
+        if hmmdir is not None:
+            _lib.check(L.ssb_fe_config_from_model(os.fsencode(hmmdir), C.byref(cfg)),
+                       "ssb_fe_config_from_model")
+        else:
+            L.ssb_fe_config_defaults(C.byref(cfg))
+        for k, v in params.items():
+            if k == "transform":
+                v = TRANSFORMS[v] if isinstance(v, str) else v
+            elif k == "cmn":
+                v = CMN_TYPES[v] if isinstance(v, str) else v
+            if not hasattr(cfg, k):
+                raise SsbError("unknown frontend parameter " + k)
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        h = L.ssb_frontend_create(C.byref(cfg), device, C.c_void_p(stream or 0))
+        if not h:
+            raise SsbError("ssb_frontend_create: " + _lib.last_error())
+        self.h = C.c_void_p(h)
+        d = np.zeros(8, np.int32)
+        L.ssb_frontend_dims(self.h, _ptr(d))
+        (self.frame_size, self.frame_shift, self.fft_size, self.nfilt, self.ncep, self.feat_dim,
+         self.n_coeffs) = [int(x) for x in d[:7]]
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ssb_frontend_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def n_frames(self, n_samples):
+        return int(self.lib.ssb_frontend_n_frames(self.h, int(n_samples)))
+
+    def tables(self):
+        out = dict(spec_start=np.zeros(self.nfilt, np.int32), filt_width=np.zeros(self.nfilt, np.int32),
+                   coeffs=np.zeros(self.n_coeffs, np.float32),
+                   mel_cosine=np.zeros((self.ncep, self.nfilt), np.float32),
+                   lifter=np.zeros(self.ncep, np.float32), hamming=np.zeros(self.frame_size // 2))
+        self.lib.ssb_frontend_tables(self.h, *[_ptr(out[k]) for k in
+                                               ("spec_start", "filt_width", "coeffs", "mel_cosine",
+                                                "lifter", "hamming")])
+        return out
+
+    def run(self, pcms):
+        """pcms: list of int16 (or float32 in [-1,1)) sample arrays, one per utterance.
+        Computes on the device and returns DeviceFeatures (nothing is copied back)."""
+        if len(pcms) and any(np.asarray(p).dtype != np.asarray(pcms[0]).dtype for p in pcms):
+            raise SsbError("all utterances of a batch must share one sample type")
+        dt = np.asarray(pcms[0]).dtype if len(pcms) else np.dtype(np.int16)
+        if dt not in (np.dtype(np.int16), np.dtype(np.float32)):
+            raise SsbError("samples must be int16 or float32")
+        pcms = [np.ascontiguousarray(p, dt).reshape(-1) for p in pcms]
+        off = np.zeros(len(pcms) + 1, np.int64)
+        for i, p in enumerate(pcms):
+            off[i + 1] = off[i] + len(p)
+        flat = np.concatenate(pcms) if pcms else np.zeros(0, dt)
+        return self.run_raw(flat, off)
+
+    def run_raw(self, pcm, samp_off):
+        """Flat samples + offsets exactly as ssb_frontend_run takes them (pcm may be pinned)."""
+        enc = 0 if pcm.dtype == np.int16 else 1
+        samp_off = np.ascontiguousarray(samp_off, np.int64)
+        n = self.lib.ssb_frontend_run(self.h, _ptr(pcm), enc, _ptr(samp_off), len(samp_off) - 1)
+        _lib.check(int(n), "ssb_frontend_run")
+        self._keep = (pcm, samp_off)
+        frame_off = np.zeros(len(samp_off), np.int64)
+        _lib.check(self.lib.ssb_frontend_download(self.h, _ptr(frame_off), None, None),
+                   "ssb_frontend_download")
+        ptr = self.lib.ssb_frontend_feat_device(self.h)
+        return DeviceFeatures(self, ptr, frame_off, self.feat_dim)
+
+    def download(self, want_mfcc=True):
+        """Per-utterance (mfcc [T][ncep] before CMN, feat [T][3*ncep]) of the last run."""
+        frame_off = np.zeros(len(self._keep[1]), np.int64)
+        self.lib.ssb_frontend_download(self.h, _ptr(frame_off), None, None)
+        G = int(frame_off[-1])
+        mfcc = np.zeros((G, self.ncep), np.float32) if want_mfcc else None
+        feat = np.zeros((G, self.feat_dim), np.float32)
+        _lib.check(self.lib.ssb_frontend_download(self.h, None, _ptr(mfcc), _ptr(feat)),
+                   "ssb_frontend_download")
+        sl = [slice(int(frame_off[u]), int(frame_off[u + 1])) for u in range(len(frame_off) - 1)]
+        return [(mfcc[s] if want_mfcc else None, feat[s]) for s in sl]
+
+    def features(self, pcms):
+        self.run(pcms)
+        return self.download()
+
+    def kernel_ms(self):
+        ms = np.zeros(8, np.float32)
+        _lib.check(self.lib.ssb_frontend_kernel_ms(self.h, _ptr(ms)), "ssb_frontend_kernel_ms")
+        return dict(melspec=float(ms[0]), noise=float(ms[1]), cepstrum=float(ms[2]),
+                    cmn=float(ms[3]), feat=float(ms[4]), total=float(ms[5]))

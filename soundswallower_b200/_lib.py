@@ -23,6 +23,15 @@ class Config(C.Structure):
                 ("device", C.c_int32)]
 
 
+class FeConfig(C.Structure):
+    """ssb_fe_config_t -- the frontend keys of the reference config
+    (ref: include/soundswallower/config_defs.h:296-449)."""
+    _fields_ = [(k, C.c_int32) for k in ("samprate", "frate", "ncep", "nfft", "nfilt", "lifter",
+                                          "remove_dc", "remove_noise", "unit_area", "round_filters",
+                                          "doublebw", "transform", "cmn", "varnorm")] + \
+               [(k, C.c_float) for k in ("wlen", "alpha", "lowerf", "upperf")]
+
+
 class AlignIn(C.Structure):
     _fields_ = [("n_utts", C.c_int32), ("feat", C.POINTER(C.c_float)),
                 ("frame_off", C.POINTER(C.c_int64)), ("phone_off", C.POINTER(C.c_int64)),
@@ -83,6 +92,10 @@ SYMBOLS = [
     "ssb_batch_download", "ssb_batch_debug_tokens", "ssb_batch_kernel_ms",
     "ssb_batch_n_launches", "ssb_batch_stats", "ssb_align_batch", "ssb_score_batch",
     "ssb_topn_batch", "ssb_tc_probe", "ssb_tc_hot_mask", "ssb_fsg_batch", "ssb_hmm_vit_eval",
+    "ssb_fe_config_defaults", "ssb_fe_config_from_model", "ssb_frontend_create",
+    "ssb_frontend_free", "ssb_frontend_dims", "ssb_frontend_n_frames", "ssb_frontend_tables",
+    "ssb_frontend_run", "ssb_frontend_download", "ssb_frontend_feat_device",
+    "ssb_frontend_kernel_ms",
 ]
 
 _lib = None
@@ -140,6 +153,23 @@ def load():
     L.ssb_tc_hot_mask.argtypes = [vp, vp]
     L.ssb_fsg_batch.argtypes = [vp, P(FsgIn), P(FsgOut)]
     L.ssb_hmm_vit_eval.argtypes = [vp, i32, i32, vp, vp, vp, P(i32)]
+    L.ssb_fe_config_defaults.restype = None
+    L.ssb_fe_config_defaults.argtypes = [P(FeConfig)]
+    L.ssb_fe_config_from_model.argtypes = [C.c_char_p, P(FeConfig)]
+    L.ssb_frontend_create.restype = vp
+    L.ssb_frontend_create.argtypes = [P(FeConfig), i32, vp]
+    L.ssb_frontend_free.restype = None
+    L.ssb_frontend_free.argtypes = [vp]
+    L.ssb_frontend_dims.argtypes = [vp, vp]
+    L.ssb_frontend_n_frames.restype = i64
+    L.ssb_frontend_n_frames.argtypes = [vp, i64]
+    L.ssb_frontend_tables.argtypes = [vp] + [vp] * 6
+    L.ssb_frontend_run.restype = i64
+    L.ssb_frontend_run.argtypes = [vp, vp, i32, vp, i32]
+    L.ssb_frontend_download.argtypes = [vp, vp, vp, vp]
+    L.ssb_frontend_feat_device.restype = vp
+    L.ssb_frontend_feat_device.argtypes = [vp]
+    L.ssb_frontend_kernel_ms.argtypes = [vp, vp]
     _lib = L
     return L
 

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "device.cuh"
+#include "host_util.cuh"
 
 namespace ssb {
 const char *last_error();
@@ -28,59 +29,8 @@ int launch_chain_viterbi(const DevModel &m, const DevPlan &p, const int16_t *cha
 
 using namespace ssb;
 
-#define API_CUDA(call, rv)                                                                  \
-    do {                                                                                    \
-        cudaError_t e_ = (call);                                                            \
-        if (e_ != cudaSuccess) {                                                            \
-            ssb::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,             \
-                           cudaGetErrorString(e_));                                         \
-            return rv;                                                                      \
-        }                                                                                   \
-    } while (0)
-
 // ------------------------------------------------------------------ small helpers
 namespace {
-
-// grow-only device buffer
-struct DBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    int ensure(size_t bytes)
-    {
-        if (bytes <= cap)
-            return 0;
-        if (p)
-            cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            e = cudaMalloc(&p, bytes);
-            want = bytes;
-        }
-        if (e != cudaSuccess) {
-            set_error("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
-            p = nullptr;
-            return -1;
-        }
-        cap = want;
-        return 0;
-    }
-    void release()
-    {
-        if (p)
-            cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-    template <class T>
-    T *as() const
-    {
-        return reinterpret_cast<T *>(p);
-    }
-};
 
 template <class T>
 int upload(DBuf &b, const std::vector<T> &v, cudaStream_t st)
@@ -960,7 +910,7 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
     }
     if (G > 0 && in->feat)
         API_CUDA(cudaMemcpyAsync(b->feat.p, in->feat, (size_t)G * h.blk * sizeof(float),
-                                 cudaMemcpyHostToDevice, st), -1);
+                                 cudaMemcpyDefault, st), -1);
     else if (G > 0) {
         set_error("ssb_batch_upload: feat is NULL");
         return -1;

@@ -29,6 +29,34 @@ def _link_shared(src, dst):
             os.symlink(os.path.abspath(s), os.path.join(dst, name))
 
 
+def write_frontend_variant(src, dst, **params):
+    """A model directory whose feat_params.json is the bundled one updated with `params`."""
+    import json
+    os.makedirs(dst, exist_ok=True)
+    with open(os.path.join(src, "feat_params.json")) as fh:
+        d = json.load(fh)
+    d.update(params)
+    with open(os.path.join(dst, "feat_params.json"), "w") as fh:
+        json.dump(d, fh)
+    for name in SHARED + ("sendump",):
+        s = os.path.join(src, name)
+        if name != "feat_params.json" and os.path.exists(s) and not os.path.exists(os.path.join(dst, name)):
+            os.symlink(os.path.abspath(s), os.path.join(dst, name))
+    return dst
+
+
+def synthetic_pcm(n, seed, samprate=16000):
+    """Speech-like test signal: gated harmonics + noise, int16."""
+    rs = np.random.RandomState(seed)
+    t = np.arange(n) / float(samprate)
+    f0 = 110 + 40 * np.sin(2 * np.pi * 0.7 * t + rs.uniform(0, 6))
+    ph = 2 * np.pi * np.cumsum(f0) / samprate
+    x = sum(np.sin(k * ph) / k for k in range(1, 12))
+    gate = (np.sin(2 * np.pi * 1.3 * t + rs.uniform(0, 6)) > -0.2).astype(float)
+    x = 6000 * x * gate / 3 + rs.normal(0, 120, n)
+    return np.clip(np.round(x), -32768, 32767).astype(np.int16)
+
+
 def _sendump_strings(fh, strings):
     for s in strings:
         b = s.encode() + b"\0"
@@ -88,3 +116,31 @@ def write_float_mixw(src, dst, mixw, logbase=1.0001, seed=11, chksum=True):
                 s = ((((s << 20) | (s >> 12)) & 0xffffffff) + w) & 0xffffffff
             fh.write(struct.pack("<I", s))
     return data
+
+
+DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+FE_LENGTHS = (0, 1, 100, 409, 410, 411, 569, 570, 571, 730, 5000)
+FE_CASES = [  # (tag, feat_params overrides, sample rate, input)
+    ("base", {}, 16000, "goforward.raw"),
+    ("fr", {}, 16000, "goforward_fr.raw"),
+    ("wav8k", {}, 8000, "sense_and_sensibility_01_austen_64kb-0880.wav"),
+    ("legacy", dict(transform="legacy"), 16000, "synth:20000:1"),
+    ("htk_dc", dict(transform="htk", remove_dc=True), 16000, "synth:12345:2"),
+    ("plain", dict(remove_noise=False, lifter=0, cmn="none"), 16000, "synth:9000:3"),
+    ("f40_varnorm", dict(nfilt=40, lowerf=133.33334, upperf=6855.4976, varnorm=True), 16000, "synth:16000:4"),
+    ("dbw_noround", dict(doublebw=True, lowerf=300, round_filters=False, unit_area=False), 16000, "synth:8000:5"),
+    ("nfft1024_wlen", dict(nfft=1024, wlen=0.02, frate=125, alpha=0.0), 16000, "synth:7777:6"),
+]
+
+
+def fe_input(spec, samprate):
+    """int16 samples of a frontend test case (file under tests/data, or synth:<n>:<seed>)."""
+    if spec.startswith("synth:"):
+        _, n, seed = spec.split(":")
+        return synthetic_pcm(int(n), int(seed), samprate)
+    path = os.path.join(DATA, spec)
+    if spec.endswith(".wav"):
+        import wave
+        w = wave.open(path)
+        return np.frombuffer(w.readframes(w.getnframes()), np.int16).copy()
+    return np.fromfile(path, np.int16)

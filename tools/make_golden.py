@@ -16,6 +16,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle.refshim import Ref, available  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -206,18 +207,48 @@ def loaders(lang="en-us"):
     print(out)
 
 
+def frontend():
+    """MFCCs and dynamic features of the reference frontend (fe_process_int16/float32 + fe_end,
+    feat_s2mfc2feat_live whole-utterance) for a few parameter sets -> frontend.npz."""
+    import tempfile
+    import model_variants as mv
+    src = os.path.join(MODELS, "en-us")
+    g = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for tag, params, sr, spec in mv.FE_CASES:
+            hmm = os.path.join(MODELS, "fr-fr") if tag == "fr" else src
+            d = mv.write_frontend_variant(hmm, os.path.join(tmp, tag), **params)
+            r = Ref(d, samprate=sr)
+            pcm = mv.fe_input(spec, sr)
+            g["mfcc_" + tag] = r.mfcc_from_pcm(pcm)
+            g["feat_" + tag] = r.features_from_pcm(pcm)
+            if tag in ("base", "plain"):
+                g["mfcc32_" + tag] = r.mfcc_from_f32((pcm.astype(np.float32) / 32768 * 0.7).astype(np.float32))
+            if tag == "base":  # ragged lengths around the framing boundaries
+                for n in mv.FE_LENGTHS:
+                    x = mv.synthetic_pcm(n, n)
+                    g["mfcc_len%d" % n] = r.mfcc_from_pcm(x)
+                    g["feat_len%d" % n] = r.features_from_pcm(x) if n else np.zeros((0, 39), np.float32)
+            r.close()
+            print("frontend", tag, g["mfcc_" + tag].shape)
+    np.savez_compressed(os.path.join(OUT, "frontend.npz"), **g)
+
+
 def main():
     if not available():
         raise SystemExit("oracle/_ref/libssref.so missing: run `make -C oracle ref` first")
     os.makedirs(OUT, exist_ok=True)
     if "--loaders" in sys.argv:
         return loaders()
+    if "--frontend" in sys.argv:
+        return frontend()
     utterance("en-us", "goforward.raw", "go forward ten meters")
     utterance("fr-fr", "goforward_fr.raw", "avance de dix mètres")
     synthetic("en-us")
     fsg("en-us", "goforward.raw", "go forward ten meters", "goforward.gram")
     fsg("fr-fr", "goforward_fr.raw", "avance de dix mètres", "goforward_fr.gram")
     loaders()
+    frontend()
 
 
 if __name__ == "__main__":
