@@ -182,6 +182,141 @@ fe_melspec_kernel(FeDev fe, const void *__restrict__ pcm, int enc,
     }
 }
 
+// Same arithmetic, register-resident start: for fft_size = 32 * R (R = 8, 16, 32) lane l owns the
+// R consecutive elements [l*R, l*R + R) of the bit-reversed frame.  Their source samples are
+// rev_LR(e) * 32 + rev5(l): each load instruction reads 32 consecutive samples across the warp,
+// and the first LR butterfly stages (spans up to R) never leave the registers.  Only the last
+// five stages go through shared memory, in a layout padded by one double per 16 so that both
+// the lane-contiguous hand-over and the strided butterflies are (nearly) conflict-free.
+__device__ __forceinline__ int fe_pad(int i) { return i + (i >> 4); }
+
+template <int LR>
+__global__ void __launch_bounds__(256)
+fe_melspec_reg_kernel(FeDev fe, const void *__restrict__ pcm, int enc,
+                      const int64_t *__restrict__ samp_off,
+                      const int64_t *__restrict__ frame_off, int n_utts, int64_t n_frames,
+                      double *__restrict__ mel)
+{
+    constexpr int R = 1 << LR, NN = 32 * R, M = 5 + LR, LDW = NN + NN / 16;
+    extern __shared__ double fe_sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t fr = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (fr >= n_frames)
+        return;
+    double *x = fe_sm + (size_t)warp * LDW;
+    const int fs = fe.frame_size, half = fs >> 1;
+    const int u = find_utt(frame_off, n_utts, fr);
+    const int64_t t = fr - frame_off[u];
+    const int64_t s0 = samp_off[u] + t * fe.frame_shift;
+    const int64_t left = samp_off[u + 1] - s0;
+    const int len = left < fs ? (int)left : fs;
+    const double alpha = (double)fe.alpha;
+    const int rl = (int)(__brev((unsigned)lane) >> 27);
+
+    double v[R];
+#pragma unroll
+    for (int e = 0; e < R; ++e) {
+        const int pos = (int)((__brev((unsigned)e) >> (32 - LR)) << 5) | rl;
+        double a = 0.0;
+        if (pos < len) {
+            const float s = pcm_sample(pcm, enc, s0 + pos);
+            if (fe.alpha != 0.0f) {
+                const float p = (pos > 0 || t > 0) ? pcm_sample(pcm, enc, s0 + pos - 1) : 0.0f;
+                a = __dsub_rn((double)s, __dmul_rn((double)p, alpha));
+            } else
+                a = (double)s;
+        }
+        if (pos < fs) {
+            const int k = pos < half ? pos : fs - 1 - pos;
+            if (k < half)
+                a = __dmul_rn(a, __ldg(fe.hamming + k));
+        }
+        v[e] = a;
+    }
+    // stages 0 .. LR-1 in registers (ref: fe_sigproc.c:482-550)
+#pragma unroll
+    for (int e = 0; e < R; e += 2) {
+        const double a = v[e], b = v[e + 1];
+        v[e] = __dadd_rn(a, b);
+        v[e + 1] = __dsub_rn(a, b);
+    }
+#pragma unroll
+    for (int k = 1; k < LR; ++k) {
+        const int h = 1 << k, q = h >> 1, tw = M - k - 1;
+#pragma unroll
+        for (int i = 0; i < R; i += 2 * h) {
+            const double a = v[i], b = v[i + h];
+            v[i] = __dadd_rn(a, b);
+            v[i + h] = __dsub_rn(a, b);
+            v[i + h + q] = -v[i + h + q];
+#pragma unroll
+            for (int j = 1; j < q; ++j) {
+                const int i1 = i + j, i2 = i + h - j, i3 = i + h + j, i4 = i + 2 * h - j;
+                const double cc = __ldg(fe.ccc + (j << tw)), ss = __ldg(fe.sss + (j << tw));
+                const double x1 = v[i1], x2 = v[i2], x3 = v[i3], x4 = v[i4];
+                const double t1 = __dadd_rn(__dmul_rn(x3, cc), __dmul_rn(x4, ss));
+                const double t2 = __dsub_rn(__dmul_rn(x3, ss), __dmul_rn(x4, cc));
+                v[i4] = __dsub_rn(x2, t2);
+                v[i3] = __dsub_rn(-x2, t2);
+                v[i2] = __dsub_rn(x1, t1);
+                v[i1] = __dadd_rn(x1, t1);
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < R; ++e)
+        x[fe_pad(lane * R + e)] = v[e];
+    __syncwarp();
+    // stages LR .. M-1 through shared memory
+#pragma unroll
+    for (int k = LR; k < M; ++k) {
+        const int h = 1 << k, q = h >> 1, tw = M - k - 1;
+#pragma unroll
+        for (int r = 0; r < R / 4; ++r) {
+            const int w = lane + 32 * r;
+            const int j = w & (q - 1), i = (w >> (k - 1)) << (k + 1);
+            if (j == 0) {
+                const int pa = fe_pad(i), pb = fe_pad(i + h), pc = fe_pad(i + h + q);
+                const double a = x[pa], b = x[pb];
+                x[pa] = __dadd_rn(a, b);
+                x[pb] = __dsub_rn(a, b);
+                x[pc] = -x[pc];
+            } else {
+                const int p1 = fe_pad(i + j), p2 = fe_pad(i + h - j), p3 = fe_pad(i + h + j),
+                          p4 = fe_pad(i + 2 * h - j);
+                const double cc = __ldg(fe.ccc + (j << tw)), ss = __ldg(fe.sss + (j << tw));
+                const double x1 = x[p1], x2 = x[p2], x3 = x[p3], x4 = x[p4];
+                const double t1 = __dadd_rn(__dmul_rn(x3, cc), __dmul_rn(x4, ss));
+                const double t2 = __dsub_rn(__dmul_rn(x3, ss), __dmul_rn(x4, cc));
+                x[p4] = __dsub_rn(x2, t2);
+                x[p3] = __dsub_rn(-x2, t2);
+                x[p2] = __dsub_rn(x1, t1);
+                x[p1] = __dadd_rn(x1, t1);
+            }
+        }
+        __syncwarp();
+    }
+    // power spectrum in place: bin j <= NN/2 overwrites x[j], its imaginary part x[NN-j] lives
+    // in the upper half which is only read
+    for (int j = lane; j <= NN / 2; j += 32) {
+        const double re = x[fe_pad(j)];
+        double pw = __dmul_rn(re, re);
+        if (j > 0) {
+            const double im = x[fe_pad(NN - j)];
+            pw = __dadd_rn(pw, __dmul_rn(im, im));
+        }
+        x[fe_pad(j)] = pw;
+    }
+    __syncwarp();
+    for (int f = lane; f < fe.nfilt; f += 32) {
+        const int ss = fe.spec_start[f], cs = fe.filt_start[f], wd = fe.filt_width[f];
+        double acc = 0.0;
+        for (int i = 0; i < wd; ++i)
+            acc = __dadd_rn(acc, __dmul_rn(x[fe_pad(ss + i)], (double)__ldg(fe.coeffs + cs + i)));
+        mel[fr * fe.nfilt + f] = acc;
+    }
+}
+
 // ------------------------------------------------------------------ noise tracker
 __device__ __forceinline__ double lower_envelope(double buf, double fl)
 {
@@ -643,6 +778,7 @@ struct ssb_frontend_s {
     int64_t n_frames = 0;
     cudaEvent_t ev[7] = {};
     bool have_ev = false, ran = false;
+    bool force_generic = false;  // SSB_FE=generic: the shared-memory-only mel spectrum kernel
 };
 
 extern "C" void ssb_fe_config_defaults(ssb_fe_config_t *c)
@@ -791,6 +927,10 @@ extern "C" ssb_frontend_t *ssb_frontend_create(const ssb_fe_config_t *c, int dev
     }
     fe->device = device;
     fe->st = (cudaStream_t)stream;
+    {
+        const char *env = getenv("SSB_FE");
+        fe->force_generic = env && std::strcmp(env, "generic") == 0;
+    }
     if (device < 0)  // tables only (host tests); every compute call fails
         return fe;
     const FeHost &h = fe->h;
@@ -991,10 +1131,29 @@ extern "C" int64_t ssb_frontend_run(ssb_frontend_t *fe, const void *pcm, int32_t
     API_CUDA(cudaEventRecord(fe->ev[1], st), -1);
     const int64_t *d_so = fe->samp_off.as<int64_t>(), *d_fo = fe->frame_off.as<int64_t>();
     if (G > 0) {
-        const int warps = std::max(1, std::min(8, kMelSmem / (2 * h.fft_size * 8)));
-        const int64_t blocks = (G + warps - 1) / warps;
-        fe_melspec_kernel<<<(unsigned)blocks, warps * 32, (size_t)warps * 2 * h.fft_size * 8, st>>>(
-            fe->d, fe->pcm.p, encoding, d_so, d_fo, U, G, fe->mel.as<double>());
+        const bool reg = !h.c.remove_dc && !fe->force_generic
+                         && (h.fft_size == 256 || h.fft_size == 512 || h.fft_size == 1024);
+        if (reg) {  // register-resident first stages
+            const int warps = h.fft_size == 1024 ? 4 : 8;
+            const int64_t blocks = (G + warps - 1) / warps;
+            const size_t smem = (size_t)warps * (h.fft_size + h.fft_size / 16) * 8;
+            double *mel = fe->mel.as<double>();
+            if (h.fft_size == 256)
+                fe_melspec_reg_kernel<3><<<(unsigned)blocks, warps * 32, smem, st>>>(
+                    fe->d, fe->pcm.p, encoding, d_so, d_fo, U, G, mel);
+            else if (h.fft_size == 512)
+                fe_melspec_reg_kernel<4><<<(unsigned)blocks, warps * 32, smem, st>>>(
+                    fe->d, fe->pcm.p, encoding, d_so, d_fo, U, G, mel);
+            else
+                fe_melspec_reg_kernel<5><<<(unsigned)blocks, warps * 32, smem, st>>>(
+                    fe->d, fe->pcm.p, encoding, d_so, d_fo, U, G, mel);
+        } else {  // any power of two up to 2048, per-frame DC removal
+            const int warps = std::max(1, std::min(8, kMelSmem / (2 * h.fft_size * 8)));
+            const int64_t blocks = (G + warps - 1) / warps;
+            fe_melspec_kernel<<<(unsigned)blocks, warps * 32, (size_t)warps * 2 * h.fft_size * 8,
+                                st>>>(fe->d, fe->pcm.p, encoding, d_so, d_fo, U, G,
+                                      fe->mel.as<double>());
+        }
         note_launch();
     }
     API_CUDA(cudaEventRecord(fe->ev[2], st), -1);

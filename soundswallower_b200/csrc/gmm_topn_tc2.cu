@@ -402,6 +402,10 @@ gmm_topn_tc2_kernel(DevModel m, DevPlan p, const float *__restrict__ featp, int6
             best.c[k] = -1;
         }
         int cnt = 0;
+        // survivor bitmasks of the four 32-column chunks first, then ONE loop over all
+        // survivors: the warp iterates max-over-lanes(total survivors) times instead of the
+        // sum over chunks of the per-chunk maxima
+        uint32_t mk0 = 0u, mk1 = 0u, mk2 = 0u, mk3 = 0u;
 #pragma unroll 1
         for (int ch = 0; ch < TC_ND / 32; ++ch) {
             float v[32];
@@ -435,15 +439,28 @@ gmm_topn_tc2_kernel(DevModel m, DevPlan p, const float *__restrict__ featp, int6
                     }
                     mask = (mask & ~hot) | (((uint32_t)h0 | ((uint32_t)h1 << 16)) & hot);
                 }
-                while (mask) {
-                    const int i = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const int cw = ch * 32 + i;
-                    const int32_t sc = __float2int_rz(exact_dist_s(rec_s + (uint32_t)(cw * TC_RL * 4), x));
-                    ++cnt;
-                    if (sc >= best.s[N])
-                        best.insert(sc, cw);
+                mk0 = ch == 0 ? mask : mk0;
+                mk1 = ch == 1 ? mask : mk1;
+                mk2 = ch == 2 ? mask : mk2;
+                mk3 = ch == 3 ? mask : mk3;
+            }
+        }
+        {
+            unsigned long long lo = (unsigned long long)mk0 | ((unsigned long long)mk1 << 32);
+            unsigned long long hi = (unsigned long long)mk2 | ((unsigned long long)mk3 << 32);
+            while (lo | hi) {  // ascending density index, as the chunked loop visited them
+                int cw;
+                if (lo) {
+                    cw = __ffsll((long long)lo) - 1;
+                    lo &= lo - 1;
+                } else {
+                    cw = 63 + __ffsll((long long)hi);
+                    hi &= hi - 1;
                 }
+                const int32_t sc = __float2int_rz(exact_dist_s(rec_s + (uint32_t)(cw * TC_RL * 4), x));
+                ++cnt;
+                if (sc >= best.s[N])
+                    best.insert(sc, cw);
             }
         }
         tc_fence_before();

@@ -128,6 +128,25 @@ def test_gpu_frontend_matches_reference(fe_golden, fe_dirs, tag):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["base", "wav8k", "nfft1024_wlen"])
+def test_gpu_generic_melspec_kernel_agrees(fe_golden, fe_dirs, tag, monkeypatch):
+    """SSB_FE=generic forces the shared-memory-only mel spectrum kernel (the one used for
+    remove_dc and for FFT sizes other than 256/512/1024): same bits as the register kernel."""
+    import soundswallower_b200 as ssb
+    d, sr, spec = fe_dirs[tag]
+    pcm = mv.fe_input(spec, sr)
+    fast = ssb.Frontend(d, device=0, samprate=sr)
+    a = fast.features([pcm])[0]
+    monkeypatch.setenv("SSB_FE", "generic")
+    slow = ssb.Frontend(d, device=0, samprate=sr)
+    b = slow.features([pcm])[0]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    close(a[0], fe_golden["mfcc_" + tag], "mfcc")
+    fast.close()
+    slow.close()
+
+
+@pytest.mark.gpu
 def test_gpu_frontend_ragged_batch(fe_golden, fe_dirs):
     """One batch holding every boundary length (incl. the empty utterance) plus real audio."""
     import soundswallower_b200 as ssb

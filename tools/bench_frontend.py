@@ -26,7 +26,9 @@ def main():
     base = np.fromfile(os.path.join(ROOT, "tests/data/goforward.raw"), np.int16)
     n = int(args.seconds * 16000)
     tile = np.tile(base, n // len(base) + 1)[:n].astype(np.int32)
-    pcm = np.empty((args.utts, n), np.int16)
+    import torch  # pinned host memory only (device plumbing, as in bench.py)
+    pinned = torch.empty((args.utts, n), dtype=torch.int16, pin_memory=True)
+    pcm = pinned.numpy()
     for u in range(args.utts):
         rng = np.random.Generator(np.random.Philox(1234 + u))
         pcm[u] = np.clip(tile + rng.integers(-40, 41, n), -32768, 32767)
