@@ -56,11 +56,20 @@ typedef struct ssb_config_s {
     int32_t topn;    /* "topn"      4      */
     int32_t ds;      /* "ds"        1      */
     int32_t device;  /* CUDA ordinal; -1 = host arrays only (loader tests) */
+    int32_t topn_beam[SSB_MAX_FEAT]; /* "topn_beam" per stream, 0 = off; semi-continuous
+                                      * models only (ref: src/s2_semi_mgau.c:184-202, 877-907) */
 } ssb_config_t;
 void ssb_config_defaults(ssb_config_t *cfg);
 
+/* Which of the reference's scorers the model directory selects, in acmod_load_am's order
+ * (ref: src/acmod.c:101-119): ptm_mgau when there is one codebook per CI phone
+ * (ref: src/ptm_mgau.c:722-816), s2_semi_mgau when there is a single codebook
+ * (ref: src/s2_semi_mgau.c:829-1058).  Fully continuous models (ms_mgau) are declined
+ * (NULL) so that a caller falls through to the reference's own scorer. */
+enum { SSB_SCORER_PTM = 0, SSB_SCORER_SEMI = 1 };
 typedef struct ssb_model_s ssb_model_t;
 ssb_model_t *ssb_model_load(const char *hmmdir, const ssb_config_t *cfg);
+int ssb_model_kind(const ssb_model_t *m);
 void ssb_model_free(ssb_model_t *m);
 /* out[0..10] = n_mgau n_feat n_density veclen(stream 0) n_sen n_sseq n_emit n_tmat
  *              n_ciphone n_phone sil ; out[11..14] = featlen[0..3] ; out[15] = sum featlen */

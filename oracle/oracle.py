@@ -60,6 +60,12 @@ class Oracle:
             self.lib.orc_model_free(self.h)
             self.h = None
 
+    def set_topn_beam(self, beam):
+        """s2_semi "topn_beam" (comma list in the reference's config), per stream."""
+        b = np.ascontiguousarray(beam, np.int32)
+        self.lib.orc_model_set_topn_beam.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        self.lib.orc_model_set_topn_beam(self.h, b.ctypes.data, len(b))
+
     def model_arrays(self):
         if self._arrays is None:
             mean = np.zeros((self.n_mgau, self.n_feat, self.n_density, self.veclen), np.float32)

@@ -27,6 +27,7 @@
 #include <soundswallower/fsg_search.h>
 #include <soundswallower/hmm.h>
 #include <soundswallower/ptm_mgau.h>
+#include <soundswallower/s2_semi_mgau.h>
 #include <soundswallower/search_module.h>
 #include <soundswallower/state_align_search.h>
 #include <soundswallower/tied_mgau_common.h>
@@ -75,13 +76,21 @@ ref_model_dims(void *h, int32 *out)
     ref_t *r = h;
     ptm_mgau_t *s = (ptm_mgau_t *)r->d->acmod->mgau;
     bin_mdef_t *m = r->d->acmod->mdef;
-    if (strcmp(r->d->acmod->mgau->vt->name, "ptm") != 0)
+    gauden_t *g;
+    int n_sen;
+    if (strcmp(r->d->acmod->mgau->vt->name, "ptm") == 0) {
+        g = s->g;
+        n_sen = s->n_sen;
+    } else if (strcmp(r->d->acmod->mgau->vt->name, "s2_semi") == 0) {
+        g = ((s2_semi_mgau_t *)r->d->acmod->mgau)->g;
+        n_sen = ((s2_semi_mgau_t *)r->d->acmod->mgau)->n_sen;
+    } else
         return -1;
-    out[0] = s->g->n_mgau;
-    out[1] = s->g->n_feat;
-    out[2] = s->g->n_density;
-    out[3] = s->g->featlen[0];
-    out[4] = s->n_sen;
+    out[0] = g->n_mgau;
+    out[1] = g->n_feat;
+    out[2] = g->n_density;
+    out[3] = g->featlen[0];
+    out[4] = n_sen;
     out[5] = m->n_sseq;
     out[6] = m->n_emit_state;
     out[7] = r->d->acmod->tmat->n_tmat;
@@ -97,36 +106,53 @@ ref_model_copy(void *h, float *mean, float *var, float *det, uint8 *mixw,
                uint8 *sen2cb, uint8 *tp, uint16 *sseq, uint8 *lut8)
 {
     ref_t *r = h;
-    ptm_mgau_t *s = (ptm_mgau_t *)r->d->acmod->mgau;
     bin_mdef_t *m = r->d->acmod->mdef;
     tmat_t *t = r->d->acmod->tmat;
     int i, j, k, c, f, n = 0, nd = 0;
-    for (c = 0; c < s->g->n_mgau; ++c)
-        for (f = 0; f < s->g->n_feat; ++f)
-            for (k = 0; k < s->g->n_density; ++k) {
-                int L = s->g->featlen[f];
-                memcpy(mean + n, s->g->mean[c][f][k], L * sizeof(float));
-                memcpy(var + n, s->g->var[c][f][k], L * sizeof(float));
+    int semi = strcmp(r->d->acmod->mgau->vt->name, "s2_semi") == 0;
+    gauden_t *g;
+    uint8 ***mw, *mw_cb;
+    logmath_t *lm8;
+    int n_sen;
+    if (semi) {
+        s2_semi_mgau_t *s = (s2_semi_mgau_t *)r->d->acmod->mgau;
+        g = s->g, mw = s->mixw, mw_cb = s->mixw_cb, lm8 = s->lmath_8b, n_sen = s->n_sen;
+    } else {
+        ptm_mgau_t *s = (ptm_mgau_t *)r->d->acmod->mgau;
+        g = s->g, mw = s->mixw, mw_cb = s->mixw_cb, lm8 = s->lmath_8b, n_sen = s->n_sen;
+    }
+    for (c = 0; c < g->n_mgau; ++c)
+        for (f = 0; f < g->n_feat; ++f)
+            for (k = 0; k < g->n_density; ++k) {
+                int L = g->featlen[f];
+                memcpy(mean + n, g->mean[c][f][k], L * sizeof(float));
+                memcpy(var + n, g->var[c][f][k], L * sizeof(float));
                 n += L;
-                det[nd++] = s->g->det[c][f][k];
+                det[nd++] = g->det[c][f][k];
             }
-    for (f = 0; f < s->g->n_feat; ++f)
-        for (k = 0; k < s->g->n_density; ++k) {
-            uint8 *dst = mixw + ((size_t)f * s->g->n_density + k) * s->n_sen;
-            if (!s->mixw_cb) {
-                memcpy(dst, s->mixw[f][k], s->n_sen);
+    for (f = 0; f < g->n_feat; ++f)
+        for (k = 0; k < g->n_density; ++k) {
+            uint8 *dst = mixw + ((size_t)f * g->n_density + k) * n_sen;
+            if (!mw_cb) {
+                memcpy(dst, mw[f][k], n_sen);
                 continue;
             }
-            /* 4-bit clustered sendump: expand with the expression the scoring loop
-             * uses (ptm_mgau.c:375-378; the nibble is chosen by the low bit of the
-             * packed byte itself) */
-            for (i = 0; i < s->n_sen; ++i) {
-                int dcw = s->mixw[f][k][i / 2];
-                dcw = (dcw & 1) ? dcw >> 4 : dcw & 0x0f;
-                dst[i] = s->mixw_cb[dcw];
+            /* 4-bit clustered sendump: expand with the expression the scoring loops use.
+             * ptm_mgau.c:375-378 chooses the nibble by the low bit of the packed byte
+             * itself; s2_semi_mgau.c:733-757 by the parity of the senone. */
+            for (i = 0; i < n_sen; ++i) {
+                int dcw = mw[f][k][i / 2];
+                if (semi)
+                    dcw = (i & 1) ? dcw >> 4 : dcw & 0x0f;
+                else
+                    dcw = (dcw & 1) ? dcw >> 4 : dcw & 0x0f;
+                dst[i] = mw_cb[dcw];
             }
         }
-    memcpy(sen2cb, s->sen2cb, s->n_sen);
+    if (semi)
+        memset(sen2cb, 0, n_sen);
+    else
+        memcpy(sen2cb, ((ptm_mgau_t *)r->d->acmod->mgau)->sen2cb, n_sen);
     for (i = 0; i < t->n_tmat; ++i)
         for (j = 0; j < t->n_state; ++j)
             for (k = 0; k < t->n_state + 1; ++k)
@@ -138,7 +164,7 @@ ref_model_copy(void *h, float *mean, float *var, float *det, uint8 *mixw,
         /* 8-bit log-add table of the scorer (logmath_init(base, 10, TRUE)) */
         int d;
         for (d = 0; d < 256; ++d)
-            lut8[d] = (uint8)(0 - fast_logmath_add(s->lmath_8b, 0, d));
+            lut8[d] = (uint8)(0 - fast_logmath_add(lm8, 0, d));
     }
     return 0;
 }

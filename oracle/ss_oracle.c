@@ -301,9 +301,13 @@ load_sendump(orc_model_t *m, const char *dir)
                 continue;
             for (s = 0; s < n_sen; ++s) {
                 if (cb) { /* ref: ptm_mgau.c:375-378: the nibble is selected by the low
-                           * bit of the packed byte, not by the senone's parity */
+                           * bit of the packed byte, not by the senone's parity; s2_semi
+                           * selects by senone parity (s2_semi_mgau.c:733-757, 795-824) */
                     int dcw = row[s / 2];
-                    dcw = (dcw & 1) ? dcw >> 4 : dcw & 0x0f;
+                    if (m->kind == ORC_KIND_SEMI)
+                        dcw = (s & 1) ? dcw >> 4 : dcw & 0x0f;
+                    else
+                        dcw = (dcw & 1) ? dcw >> 4 : dcw & 0x0f;
                     dst[s] = cb[dcw];
                 } else
                     dst[s] = row[s];
@@ -564,8 +568,15 @@ orc_model_load(const char *dir, double logbase, float varfloor, double tmatfloor
     gauden_precompute(m, varfloor);
     if (load_mdef(m, dir) < 0)
         goto fail;
-    if (m->n_mgau != m->n_ciphone)
-        goto fail; /* not PTM (ptm_mgau.c:760) */
+    /* acmod_load_am tries ptm_mgau (needs n_mgau == n_ciphone, ptm_mgau.c:760), then
+     * s2_semi_mgau (needs a single codebook, s2_semi_mgau.c:947-949) */
+    if (m->n_mgau == m->n_ciphone)
+        m->kind = ORC_KIND_PTM;
+    else if (m->n_mgau == 1) {
+        m->kind = ORC_KIND_SEMI;
+        memset(m->sen2cb, 0, m->n_sen);
+    } else
+        goto fail;
     if ((c = load_sendump(m, dir)) == -2)
         c = load_mixw_float(m, dir);
     if (c < 0)
@@ -660,6 +671,8 @@ struct orc_ptm_s {
     uint8_t *cb_active[2];
     int cur;
     int32_t frame_idx; /* mgau_t.frame_idx (acmod.h:110) */
+    int32_t topn_beam[ORC_MAX_FEAT]; /* s2_semi only */
+    uint8_t *topn_n[2];              /* s2_semi: entries inside the beam, [feat] per slot */
 };
 
 orc_ptm_t *
@@ -675,7 +688,9 @@ orc_ptm_new(const orc_model_t *m, int topn, int ds_ratio)
     for (i = 0; i < 2; ++i) {
         p->hist[i] = malloc(sizeof(topn_t) * m->n_mgau * m->n_feat * topn);
         p->cb_active[i] = malloc(m->n_mgau);
+        p->topn_n[i] = calloc(ORC_MAX_FEAT, 1);
     }
+    memcpy(p->topn_beam, m->topn_beam, sizeof(p->topn_beam));
     orc_ptm_reset(p);
     return p;
 }
@@ -689,6 +704,8 @@ orc_ptm_free(orc_ptm_t *p)
     free(p->hist[1]);
     free(p->cb_active[0]);
     free(p->cb_active[1]);
+    free(p->topn_n[0]);
+    free(p->topn_n[1]);
     free(p);
 }
 
@@ -782,6 +799,119 @@ scan_codebook(orc_ptm_t *p, topn_t *tn, int c, int f, const float *x)
     }
 }
 
+/* ref: s2_semi_mgau.c:110-169 (eval_cb of the semi-continuous scorer).  Unlike the PTM
+ * one its early-out is NOT result-neutral: a density is dropped when a partial sum (before the
+ * last dimension at the latest) is below the worst score as a float, otherwise its TRUNCATED
+ * score is compared with the worst as integers. */
+static void
+scan_codebook_semi(orc_ptm_t *p, topn_t *tn, int f, const float *x)
+{
+    const orc_model_t *m = p->m;
+    int L = m->featlen[f], cw, i, j, N = p->topn;
+    const float *mean = m->mean + m->gau_off[f];
+    const float *var = m->var + m->gau_off[f];
+    const float *det = m->det + (size_t)f * m->n_density;
+    for (cw = 0; cw < m->n_density; ++cw) {
+        float d = det[cw];
+        int32_t id;
+        for (j = 0; j < L && d >= tn[N - 1].score; ++j) {
+            float diff = x[j] - mean[cw * L + j];
+            float sq = diff * diff;
+            float c = sq * var[cw * L + j];
+            d = d - c;
+        }
+        if (j < L)
+            continue;
+        id = dist_to_int(d);
+        if (id < tn[N - 1].score)
+            continue;
+        for (i = 0; i < N; ++i)
+            if (tn[i].cw == cw)
+                break;
+        if (i < N)
+            continue;
+        for (i = N - 2; i >= 0 && id >= tn[i].score; --i)
+            tn[i + 1] = tn[i];
+        tn[i + 1].cw = cw;
+        tn[i + 1].score = id;
+    }
+}
+
+void
+orc_model_set_topn_beam(orc_model_t *m, const int32_t *beam, int n)
+{
+    int i, maxn = 0;
+    for (i = 0; i < n && i < ORC_MAX_FEAT; ++i)
+        if (beam[i] > maxn)
+            maxn = beam[i];
+    for (i = 0; i < ORC_MAX_FEAT; ++i)
+        m->topn_beam[i] = (uint8_t)(i < n ? beam[i] : maxn);
+}
+
+/* ref: s2_semi_mgau.c:829-875 and callees */
+static int
+semi_frame_eval(orc_ptm_t *p, int16_t *senscr, const uint8_t *active, int32_t n_active,
+                const float *feat, int32_t frame, int32_t compallsen, int32_t *topn_out)
+{
+    const orc_model_t *m = p->m;
+    int N = p->topn, f, k, i, lastsen;
+    int slot = frame % 2;
+    topn_t *cur = p->hist[slot];
+    uint8_t *nn = p->topn_n[slot];
+    memset(senscr, 0, sizeof(int16_t) * m->n_sen);
+    for (f = 0; f < m->n_feat; ++f) {
+        topn_t *tn = cur + f * N;
+        if (frame >= p->frame_idx) {
+            int32_t norm;
+            memcpy(tn, p->hist[slot ? slot - 1 : 1] + f * N, sizeof(topn_t) * N);
+            rescore_topn(p, tn, 0, f, feat + m->featoff[f]); /* :68-108, same as the PTM one */
+            if (frame % p->ds == 0)
+                scan_codebook_semi(p, tn, f, feat + m->featoff[f]);
+            /* mgau_norm (:184-202) */
+            norm = tn[0].score >> ORC_SENSCR_SHIFT;
+            for (k = 0; k < N; ++k) {
+                tn[k].score = -((tn[k].score >> ORC_SENSCR_SHIFT) - norm);
+                if (tn[k].score > ORC_MAX_NEG_ASCR)
+                    tn[k].score = ORC_MAX_NEG_ASCR;
+                if (p->topn_beam[f] && tn[k].score > p->topn_beam[f])
+                    break;
+            }
+            nn[f] = (uint8_t)k;
+        }
+        /* get_scores_{8b,4b}_feat[_all] (:204-827): no normalisation over senones, senones
+         * that are not listed stay 0 */
+        for (lastsen = i = 0; i < (compallsen ? m->n_sen : n_active); ++i) {
+            int sen = compallsen ? i : active[i] + lastsen;
+            int fden = 0;
+            lastsen = sen;
+            for (k = 0; k < nn[f]; ++k) {
+                int v = m->mixw[((size_t)f * m->n_density + tn[k].cw) * m->n_sen + sen] + tn[k].score;
+                if (k == 0)
+                    fden = v;
+                else {
+                    int d, r;
+                    if (fden > v) {
+                        d = fden - v;
+                        r = v;
+                    } else {
+                        d = v - fden;
+                        r = fden;
+                    }
+                    fden = r - m->lut8[d];
+                }
+            }
+            senscr[sen] = (int16_t)(senscr[sen] + fden);
+        }
+    }
+    p->cur = slot;
+    if (topn_out)
+        for (i = 0; i < m->n_feat * N; ++i) {
+            *topn_out++ = cur[i].cw;
+            *topn_out++ = cur[i].score;
+        }
+    return 0;
+}
+
 /* ref: ptm_mgau.c:408-454 and callees */
 int
 orc_ptm_frame_eval(orc_ptm_t *p, int16_t *senscr, const uint8_t *active, int32_t n_active,
@@ -794,6 +924,8 @@ orc_ptm_frame_eval(orc_ptm_t *p, int16_t *senscr, const uint8_t *active, int32_t
     uint8_t *act = p->cb_active[slot];
     int32_t best;
 
+    if (m->kind == ORC_KIND_SEMI)
+        return semi_frame_eval(p, senscr, active, n_active, feat, frame, compallsen, topn_out);
     if (frame >= p->frame_idx) {
         topn_t *prev = p->hist[slot ? slot - 1 : 1];
         memcpy(cur, prev, sizeof(topn_t) * m->n_mgau * m->n_feat * N);

@@ -55,7 +55,12 @@ typedef struct orc_model_s {
     double logbase;
     uint8_t lut8[256];
     int32_t lmath_zero; /* shift-0 zero */
+    /* which scorer acmod_load_am ends up with (ref: acmod.c:101-119): ptm_mgau when
+     * n_mgau == n_ciphone, s2_semi_mgau when there is a single codebook */
+    int32_t kind;
+    int32_t topn_beam[ORC_MAX_FEAT]; /* s2_semi "topn_beam" per stream, 0 = off */
 } orc_model_t;
+enum { ORC_KIND_PTM = 0, ORC_KIND_SEMI = 1 };
 
 /* ---- load-time (ref: logmath.c, ms_gauden.c, ptm_mgau.c read_sendump, bin_mdef.c, tmat.c) */
 int orc_logadd_table8(double base, int shift, uint8_t *out256);
@@ -73,6 +78,10 @@ orc_ptm_t *orc_ptm_new(const orc_model_t *m, int topn, int ds_ratio);
 void orc_ptm_free(orc_ptm_t *p);
 void orc_ptm_reset(orc_ptm_t *p);
 void orc_ptm_set_frame_idx(orc_ptm_t *p, int frame_idx);
+/* s2_semi only: per-stream "topn_beam" (ref: s2_semi_mgau.c:184-202, 877-907; missing
+ * entries repeat the largest given one like split_topn does); applies to scorers created
+ * afterwards */
+void orc_model_set_topn_beam(orc_model_t *m, const int32_t *beam, int n);
 /* One frame_eval; `feat` = blk floats. active = delta list (ref acmod.c:947). If
  * topn_out != NULL receives post-norm [mgau][feat][topn][2] = (cw, score). */
 int orc_ptm_frame_eval(orc_ptm_t *p, int16_t *senscr, const uint8_t *active, int32_t n_active,

@@ -50,12 +50,16 @@ class AcousticModel:
     call on such a model fails -- there is no CPU path."""
 
     def __init__(self, hmmdir, device=0, topn=4, ds=1, logbase=1.0001, varfloor=1e-4,
-                 mixwfloor=1e-7, tmatfloor=1e-4):
+                 mixwfloor=1e-7, tmatfloor=1e-4, topn_beam=None):
         self.lib = L = _lib.load()
         cfg = Config()
         L.ssb_config_defaults(C.byref(cfg))
         cfg.logbase, cfg.varfloor, cfg.mixwfloor, cfg.tmatfloor = logbase, varfloor, mixwfloor, tmatfloor
         cfg.topn, cfg.ds, cfg.device = topn, ds, device
+        if topn_beam is not None:  # "topn_beam" of semi-continuous models; missing entries
+            beam = [int(x) for x in (topn_beam.split(",") if isinstance(topn_beam, str) else topn_beam)]
+            for f in range(4):     # repeat the largest one (ref: src/s2_semi_mgau.c:877-907)
+                cfg.topn_beam[f] = beam[f] if f < len(beam) else max(beam)
         h = L.ssb_model_load(os.fsencode(hmmdir), C.byref(cfg))
         if not h:
             raise SsbError("ssb_model_load(%s): %s" % (hmmdir, _lib.last_error()))
@@ -68,6 +72,7 @@ class AcousticModel:
          self.n_emit, self.n_tmat, self.n_ciphone, self.n_phone, self.sil) = [int(x) for x in d[:11]]
         self.featlen = [int(x) for x in d[11:11 + self.n_feat]]
         self.blk = int(d[15])
+        self.kind = int(L.ssb_model_kind(self.h))   # 0 PTM, 1 semi-continuous
         self._arrays = None
 
     def close(self):

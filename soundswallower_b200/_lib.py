@@ -20,7 +20,7 @@ class Config(C.Structure):
     (ref: include/soundswallower/config_defs.h:78-257)."""
     _fields_ = [("logbase", C.c_double), ("varfloor", C.c_float), ("mixwfloor", C.c_double),
                 ("tmatfloor", C.c_double), ("topn", C.c_int32), ("ds", C.c_int32),
-                ("device", C.c_int32)]
+                ("device", C.c_int32), ("topn_beam", C.c_int32 * 4)]
 
 
 class FeConfig(C.Structure):
@@ -86,7 +86,7 @@ class MgauBase(C.Structure):
 # every symbol include/ssb200.h declares
 SYMBOLS = [
     "ssb_version", "ssb_last_error", "ssb_device_count", "ssb_config_defaults",
-    "ssb_model_load", "ssb_model_free", "ssb_model_dims", "ssb_model_copy", "ssb_model_phones",
+    "ssb_model_load", "ssb_model_kind", "ssb_model_free", "ssb_model_dims", "ssb_model_copy", "ssb_model_phones",
     "ssb_mgau_init", "ssb_mgau_frame_eval", "ssb_mgau_reset", "ssb_mgau_free",
     "ssb_plan_chain", "ssb_batch_create", "ssb_batch_free", "ssb_batch_upload", "ssb_batch_run",
     "ssb_batch_download", "ssb_batch_debug_tokens", "ssb_batch_kernel_ms",
@@ -153,6 +153,7 @@ def load():
     L.ssb_tc_hot_mask.argtypes = [vp, vp]
     L.ssb_fsg_batch.argtypes = [vp, P(FsgIn), P(FsgOut)]
     L.ssb_hmm_vit_eval.argtypes = [vp, i32, i32, vp, vp, vp, P(i32)]
+    L.ssb_model_kind.argtypes = [vp]
     L.ssb_fe_config_defaults.restype = None
     L.ssb_fe_config_defaults.argtypes = [P(FeConfig)]
     L.ssb_fe_config_from_model.argtypes = [C.c_char_p, P(FeConfig)]

@@ -56,6 +56,14 @@ struct ssb_model_s {
 };
 
 extern "C" int ssb_version(void) { return 100; }
+extern "C" int ssb_model_kind(const ssb_model_t *m)
+{
+    if (!m) {
+        set_error("ssb_model_kind: model is NULL");
+        return -1;
+    }
+    return m->h.kind;
+}
 extern "C" const char *ssb_last_error(void) { return ssb::last_error(); }
 
 extern "C" int ssb_device_count(void)
@@ -85,6 +93,8 @@ extern "C" void ssb_config_defaults(ssb_config_t *c)
     c->topn = 4;
     c->ds = 1;
     c->device = 0;
+    for (int f = 0; f < SSB_MAX_FEAT; ++f)
+        c->topn_beam[f] = 0;
 }
 
 template <class T>
@@ -127,6 +137,9 @@ static int model_to_device(ssb_model_s *m)
     d.blk = h.blk;
     d.topn = h.cfg.topn;
     d.ds = h.cfg.ds;
+    d.kind = h.kind;
+    for (int f = 0; f < SSB_MAX_FEAT; ++f)  // the reference keeps the beams in uint8
+        d.topn_beam[f] = h.kind == SSB_SCORER_SEMI ? (h.cfg.topn_beam[f] & 0xff) : 0;
     // packed Gaussian records: [det, mean[L], prec[L], 0-pad], codebook-major
     int64_t off = 0;
     for (int f = 0; f < h.n_feat; ++f) {
@@ -519,7 +532,7 @@ extern "C" int ssb_mgau_frame_eval(ssb_mgau_t *gg, int16_t *senscr, uint8_t *sen
     const bool fresh = frame >= g->base.frame_idx;
     if (fresh) {
         // ptm_mgau_calc_cb_active (ref: src/ptm_mgau.c:297-321)
-        if (compallsen)
+        if (compallsen || h.kind == SSB_SCORER_SEMI)  // s2_semi always scans its codebook
             std::memset(g->h_cb, 1, h.n_mgau);
         else {
             std::memset(g->h_cb, 0, h.n_mgau);

@@ -52,6 +52,10 @@ struct DevModel {
     const float *gBlo;
     const float *gAux;
     const uint32_t *gHot;
+    // scorer family (ssb200.h SSB_SCORER_*): PTM, or the single-codebook semi-continuous one
+    // (ref: src/s2_semi_mgau.c) with its per-stream top-N beam
+    int32_t kind;
+    int32_t topn_beam[SSB_MAX_FEAT];
 };
 constexpr int SSB_TC_AUX = 96;
 

@@ -58,6 +58,55 @@ __device__ __forceinline__ float gau_dist(const float *__restrict__ rec, const f
     return d;
 }
 
+// Same, also returning the partial sum before the last dimension: the semi-continuous
+// scorer's early-out tests the partial sums against the worst score (ref:
+// src/s2_semi_mgau.c:131-143); they decrease monotonically, so the last one decides.
+template <int L>
+__device__ __forceinline__ float gau_dist2(const float *__restrict__ rec, const float (&x)[L],
+                                           float &before_last)
+{
+    constexpr int RL = (1 + 2 * L + 3) & ~3;
+    float v[RL];
+    const float4 *r4 = reinterpret_cast<const float4 *>(rec);
+#pragma unroll
+    for (int i = 0; i < RL / 4; ++i) {
+        float4 q = r4[i];
+        v[4 * i] = q.x;
+        v[4 * i + 1] = q.y;
+        v[4 * i + 2] = q.z;
+        v[4 * i + 3] = q.w;
+    }
+    float d = v[0];
+    before_last = d;
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+        if (j == L - 1)
+            before_last = d;
+        float diff = __fsub_rn(x[j], v[1 + j]);
+        float sq = __fmul_rn(diff, diff);
+        float c = __fmul_rn(sq, v[1 + L + j]);
+        d = __fsub_rn(d, c);
+    }
+    return d;
+}
+
+__device__ __forceinline__ float gau_dist_rt2(const float *__restrict__ rec,
+                                              const float *__restrict__ x, int L,
+                                              float &before_last)
+{
+    float d = rec[0];
+    before_last = d;
+    for (int j = 0; j < L; ++j) {
+        if (j == L - 1)
+            before_last = d;
+        float diff = __fsub_rn(__ldg(x + j), rec[1 + j]);
+        float sq = __fmul_rn(diff, diff);
+        float c = __fmul_rn(sq, rec[1 + L + j]);
+        d = __fsub_rn(d, c);
+    }
+    return d;
+}
+
 // run-time length variant (models whose streams are not 13 wide)
 __device__ __forceinline__ float gau_dist_rt(const float *__restrict__ rec,
                                              const float *__restrict__ x, int L)
@@ -178,10 +227,12 @@ gmm_topn_kernel(DevModel m, DevPlan p, const float *__restrict__ feat, int64_t G
     int4 *so = out_s + (int64_t)cs * G + g0;
     uchar4 *co = out_c + (int64_t)cs * G + g0;
 
-    // active-codebook epochs of this utterance
+    // active-codebook epochs of this utterance (the semi-continuous scorer has no notion of
+    // an inactive codebook: it scans its only one on every frame)
+    const bool semi = m.kind == SSB_SCORER_SEMI;
     int e = 0, e_end = 0, t_next = INT32_MAX;
     bool active = true;
-    if (!p.all_active) {
+    if (!p.all_active && !semi) {
         e = p.ep_off[u];
         e_end = p.ep_off[u + 1];
         active = false;
@@ -227,7 +278,27 @@ gmm_topn_kernel(DevModel m, DevPlan p, const float *__restrict__ feat, int64_t G
             tn.settle(i);
         }
         // scan the codebook (ref: eval_cb)
-        if (active && (m.ds <= 1 || t % m.ds == 0)) {
+        if (semi && (m.ds <= 1 || t % m.ds == 0)) {
+            // ref: src/s2_semi_mgau.c:110-169 -- dropped when a partial sum falls below the
+            // worst score (as floats), else the TRUNCATED score is compared as an integer
+#pragma unroll 2
+            for (int cw = 0; cw < ND; ++cw) {
+                const float *r = rec + cw * RL;
+                float d, dp;
+                if (L > 0)
+                    d = gau_dist2<LX>(r, x, dp);
+                else
+                    d = gau_dist_rt2(r, xt, Lrt, dp);
+                if (dp < __int2float_rn(tn.s[N - 1]))
+                    continue;
+                const int32_t id = dist_to_int(d);
+                if (id < tn.s[N - 1])
+                    continue;
+                if (tn.has(cw))
+                    continue;
+                tn.insert(id, cw);
+            }
+        } else if (active && (m.ds <= 1 || t % m.ds == 0)) {
 #pragma unroll 2
             for (int cw = 0; cw < ND; ++cw) {
                 const float *r = rec + cw * RL;
@@ -243,7 +314,7 @@ gmm_topn_kernel(DevModel m, DevPlan p, const float *__restrict__ feat, int64_t G
                 tn.insert(dist_to_int(d), cw);
             }
         }
-        if (active)
+        if (active || semi)
             store_topn<N>(tn, so + t, co + t);
     }
 }
@@ -312,8 +383,16 @@ __global__ void frame_topn_kernel(DevModel m, FrameHist h, int slot, int prev,
     const int RL = m.rec_len[f], L = m.featlen[f], ND = m.n_density, N = m.topn;
     const float *rec = m.gau + gau_offset(m, cb, f);
     const float *xf = x + m.featoff[f];
-    for (int cw = threadIdx.x; cw < ND; cw += blockDim.x)
-        dist[cw] = gau_dist_rt(rec + (int64_t)cw * RL, xf, L);
+    const bool semi = m.kind == SSB_SCORER_SEMI;
+    float *part = dist + ND;  // semi only: partial sums before the last dimension
+    for (int cw = threadIdx.x; cw < ND; cw += blockDim.x) {
+        if (semi) {
+            float dp;
+            dist[cw] = gau_dist_rt2(rec + (int64_t)cw * RL, xf, L, dp);
+            part[cw] = dp;
+        } else
+            dist[cw] = gau_dist_rt(rec + (int64_t)cw * RL, xf, L);
+    }
     __syncthreads();
     if (threadIdx.x != 0)
         return;
@@ -331,10 +410,13 @@ __global__ void frame_topn_kernel(DevModel m, FrameHist h, int slot, int prev,
         s[j + 1] = v;
         c[j + 1] = cw;
     }
-    if (do_scan && h.act[slot][cb]) {
+    if (do_scan && (semi || h.act[slot][cb])) {
         for (int cw = 0; cw < ND; ++cw) {
             float d = dist[cw];
-            if (d < __int2float_rn(s[N - 1]))
+            if (semi) {  // ref: src/s2_semi_mgau.c:131-152
+                if (part[cw] < __int2float_rn(s[N - 1]) || dist_to_int(d) < s[N - 1])
+                    continue;
+            } else if (d < __int2float_rn(s[N - 1]))
                 continue;
             int i;
             for (i = 0; i < N; ++i)
@@ -360,7 +442,7 @@ int launch_frame_topn(const DevModel &m, const FrameHist &h, int slot, int prev,
                       int do_scan, cudaStream_t st)
 {
     int threads = m.n_density < 128 ? 128 : 256;
-    frame_topn_kernel<<<m.n_mgau * m.n_feat, threads, m.n_density * sizeof(float), st>>>(
+    frame_topn_kernel<<<m.n_mgau * m.n_feat, threads, 2 * m.n_density * sizeof(float), st>>>(
         m, h, slot, prev, x, do_scan);
     SSB_CUDA(cudaGetLastError());
     note_launch();

@@ -254,7 +254,7 @@ gmm_topn_tc_kernel(DevModel m, DevPlan p, const float *__restrict__ feat, int64_
 
 bool tc_supported(const DevModel &m)
 {
-    if (m.n_density != TC_ND || m.gB == nullptr)
+    if (m.n_density != TC_ND || m.gB == nullptr || m.kind != SSB_SCORER_PTM)
         return false;
     for (int f = 0; f < m.n_feat; ++f)
         if (m.featlen[f] != TC_L)

@@ -394,6 +394,14 @@ static bool read_sendump(HostModel &m, const std::string &path)
             return false;
         book = &f.bytes[f.at];
         f.at += n_clust;
+        // the reference's unrolled 4-bit loops keep weight + score in uint8 tables
+        // (ref: src/s2_semi_mgau.c:445-731): entries above MAX_NEG_MIXW would wrap there
+        for (int i = 0; i < n_clust; ++i)
+            if (m.kind == SSB_SCORER_SEMI && book[i] > 159) {
+                set_error("%s: cluster codebook entry %d > 159 overflows the reference's 8-bit "
+                          "weight tables", path.c_str(), book[i]);
+                return false;
+            }
     }
     const size_t stride = n_bits == 4 ? (size_t)(cols + 1) / 2 : (size_t)cols;
     if (f.left() < stride * rows * n_feat) {
@@ -412,8 +420,12 @@ static bool read_sendump(HostModel &m, const std::string &path)
                 continue;
             }
             for (int s = 0; s < n_sen; ++s) {
-                int b = src[s / 2];
-                dst[s] = book[(b & 1) ? b >> 4 : b & 0x0f];
+                // ptm_mgau picks the nibble by the low bit of the packed byte itself
+                // (ref: src/ptm_mgau.c:375-378), s2_semi by the senone's parity
+                // (ref: src/s2_semi_mgau.c:733-757, 795-824)
+                const int b = src[s / 2];
+                const bool high = m.kind == SSB_SCORER_SEMI ? (s & 1) : (b & 1);
+                dst[s] = book[high ? b >> 4 : b & 0x0f];
             }
         }
     return true;
@@ -553,9 +565,16 @@ bool HostModel::load(const std::string &dir, const ssb_config_t &c)
     precompute_gauden(*this);
     if (!read_mdef(*this, dir + "/mdef"))
         return false;
-    if (n_mgau != n_ciphone) {
-        // ref: src/ptm_mgau.c:760-764 -- the PTM scorer declines such models
-        set_error("%d codebooks but %d CI phones: not a PTM model", n_mgau, n_ciphone);
+    // acmod_load_am's order (ref: src/acmod.c:101-119): PTM needs one codebook per CI phone
+    // (ref: src/ptm_mgau.c:760-764), s2_semi a single codebook (ref: src/s2_semi_mgau.c:947-949)
+    if (n_mgau == n_ciphone)
+        kind = SSB_SCORER_PTM;
+    else if (n_mgau == 1) {
+        kind = SSB_SCORER_SEMI;
+        std::fill(sen2cb.begin(), sen2cb.end(), (uint8_t)0);
+    } else {
+        set_error("%d codebooks but %d CI phones: neither a PTM nor a semi-continuous model",
+                  n_mgau, n_ciphone);
         return false;
     }
     if (!read_sendump(*this, dir + "/sendump")) {

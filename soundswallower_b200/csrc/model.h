@@ -49,6 +49,7 @@ struct HostModel {
     std::vector<uint8_t> tp;             // [n_tmat][n_emit][n_emit+1]
     uint8_t lut8[256];
     ssb_config_t cfg;
+    int32_t kind = SSB_SCORER_PTM;
 
     bool load(const std::string &dir, const ssb_config_t &cfg);
 };

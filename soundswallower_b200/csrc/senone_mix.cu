@@ -33,6 +33,28 @@ __device__ __forceinline__ int logadd8(int a, int b, const uint8_t *lut)
     return r - lut[d];
 }
 
+// Normalised, clamped scores of one codebook-stream.  For the semi-continuous scorer the
+// entries from the first one beyond the stream's top-N beam onwards are not mixed in
+// (ref: src/s2_semi_mgau.c:184-202); they are parked as K2_UNUSED.
+constexpr int K2_UNUSED = 255;
+__device__ __forceinline__ uchar4 norm_scores(const DevModel &m, int f, int nm, int4 rs)
+{
+    int s[4] = {min(MAX_NEG_ASCR, nm - (rs.x >> SENSCR_SHIFT)), min(MAX_NEG_ASCR, nm - (rs.y >> SENSCR_SHIFT)),
+                min(MAX_NEG_ASCR, nm - (rs.z >> SENSCR_SHIFT)), min(MAX_NEG_ASCR, nm - (rs.w >> SENSCR_SHIFT))};
+    if (m.kind == SSB_SCORER_SEMI) {
+        const int beam = m.topn_beam[f];
+        bool cut = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            cut = cut || (beam != 0 && s[k] > beam);
+            if (cut)
+                s[k] = K2_UNUSED;
+        }
+    }
+    return make_uchar4((unsigned char)s[0], (unsigned char)s[1], (unsigned char)s[2],
+                       (unsigned char)s[3]);
+}
+
 constexpr int K2_THREADS = 256;
 constexpr int K2_WARPS = K2_THREADS / 32;
 constexpr int K2_CS_PER_LANE = 4;  // codebook-streams per lane: CS <= 128
@@ -154,12 +176,7 @@ senone_mix_active_kernel(DevModel m, DevPlan p, const int4 *__restrict__ tn_s,
                 for (int ff = 1; ff < SSB_MAX_FEAT; ++ff)
                     if (ff == f)
                         n0 = nm[ff];
-                uchar4 q;
-                q.x = (unsigned char)min(MAX_NEG_ASCR, n0 - (rs[it].x >> SENSCR_SHIFT));
-                q.y = (unsigned char)min(MAX_NEG_ASCR, n0 - (rs[it].y >> SENSCR_SHIFT));
-                q.z = (unsigned char)min(MAX_NEG_ASCR, n0 - (rs[it].z >> SENSCR_SHIFT));
-                q.w = (unsigned char)min(MAX_NEG_ASCR, n0 - (rs[it].w >> SENSCR_SHIFT));
-                wt_s[cs] = q;
+                wt_s[cs] = norm_scores(m, f, n0, rs[it]);
                 wt_c[cs] = rc[it];
             }
         for (int i = lane; i < W / 2; i += 32)
@@ -179,7 +196,7 @@ senone_mix_active_kernel(DevModel m, DevPlan p, const int4 *__restrict__ tn_s,
                 int fden = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (k < N) {
+                    if (k < N && sc[k] != K2_UNUSED) {
                         int w;
                         if (STAGED)
                             w = mw[(f * ND + cw[k]) * W + slot];
@@ -197,9 +214,10 @@ senone_mix_active_kernel(DevModel m, DevPlan p, const int4 *__restrict__ tn_s,
         for (int o = 16; o > 0; o >>= 1)
             local_best = min(local_best, __shfl_xor_sync(0xffffffffu, local_best, o));
         __syncwarp();
-        // D: gather to chain states, subtract the frame's best (ref :398-400)
+        // D: gather to chain states, subtract the frame's best (ref :398-400; the
+        // semi-continuous scorer does not normalise over senones)
         {
-            const int16_t b16 = (int16_t)local_best;
+            const int16_t b16 = m.kind == SSB_SCORER_SEMI ? (int16_t)0 : (int16_t)local_best;
             int16_t *dst = chain_scr + p.scr_off[u] + (int64_t)t * ns;
             for (int si = lane; si < ns; si += 32)
                 dst[si] = (int16_t)(wscr[st_slot[si]] - b16);
@@ -307,12 +325,7 @@ senone_dense_kernel(DevModel m, const int4 *__restrict__ tn_s, const uchar4 *__r
             const int64_t g = (int64_t)cs * G + g0 + base + fr;
             const int4 rs = tn_s[g];
             const int nm = norm[fr * SSB_MAX_FEAT + cs % NF];
-            uchar4 q;
-            q.x = (unsigned char)min(MAX_NEG_ASCR, nm - (rs.x >> SENSCR_SHIFT));
-            q.y = (unsigned char)min(MAX_NEG_ASCR, nm - (rs.y >> SENSCR_SHIFT));
-            q.z = (unsigned char)min(MAX_NEG_ASCR, nm - (rs.z >> SENSCR_SHIFT));
-            q.w = (unsigned char)min(MAX_NEG_ASCR, nm - (rs.w >> SENSCR_SHIFT));
-            wt_s[fr * CSP + cs] = q;
+            wt_s[fr * CSP + cs] = norm_scores(m, cs % NF, nm, rs);
             wt_c[fr * CSP + cs] = tn_c[g];
         }
         __syncthreads();
@@ -322,7 +335,7 @@ senone_dense_kernel(DevModel m, const int4 *__restrict__ tn_s, const uchar4 *__r
             for (int sen = threadIdx.x; sen < n_sen; sen += blockDim.x) {
                 const int cb = s2c[sen];
                 int ascore = 0;
-                if (NF == 3 && N == 4) {
+                if (NF == 3 && N == 4 && m.kind == SSB_SCORER_PTM) {
                     // the bundled shape: all 12 weight loads in flight before any arithmetic
                     uchar4 sv[3], cv[3];
                     int w[12];
@@ -358,7 +371,7 @@ senone_dense_kernel(DevModel m, const int4 *__restrict__ tn_s, const uchar4 *__r
                         int fden = 0;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            if (k < N) {
+                            if (k < N && sc[k] != K2_UNUSED) {
                                 const int v = (int)__ldg(row + (int64_t)cw[k] * n_sen) + sc[k];
                                 fden = k == 0 ? v : logadd8(fden, v, lut);
                             }
@@ -377,7 +390,7 @@ senone_dense_kernel(DevModel m, const int4 *__restrict__ tn_s, const uchar4 *__r
         __syncthreads();
         // C: subtract the frame's best (ref: src/ptm_mgau.c:398-400), one coalesced row per frame
         for (int fr = 0; fr < nf; ++fr) {
-            const int16_t b16 = (int16_t)best[fr];
+            const int16_t b16 = m.kind == SSB_SCORER_SEMI ? (int16_t)0 : (int16_t)best[fr];
             int16_t *dst = dense + (base + fr) * n_sen;
             for (int sen = threadIdx.x; sen < n_sen; sen += blockDim.x)
                 dst[sen] = (int16_t)(scr[(size_t)fr * n_sen + sen] - b16);
@@ -483,13 +496,8 @@ frame_senones_kernel(DevModel m, FrameHist h, int slot, int do_norm,
         __syncthreads();
         for (int cs = threadIdx.x; cs < m.n_mgau * NF; cs += blockDim.x)
             if (act[cs / NF]) {
-                int nm = s_norm[cs % NF];
-                int4 v = hs[cs];
-                v.x = min(MAX_NEG_ASCR, nm - (v.x >> SENSCR_SHIFT));
-                v.y = min(MAX_NEG_ASCR, nm - (v.y >> SENSCR_SHIFT));
-                v.z = min(MAX_NEG_ASCR, nm - (v.z >> SENSCR_SHIFT));
-                v.w = min(MAX_NEG_ASCR, nm - (v.w >> SENSCR_SHIFT));
-                hs[cs] = v;
+                const uchar4 q = norm_scores(m, cs % NF, s_norm[cs % NF], hs[cs]);
+                hs[cs] = make_int4(q.x, q.y, q.z, q.w);
             }
         __syncthreads();
     }
@@ -514,7 +522,7 @@ frame_senones_kernel(DevModel m, FrameHist h, int slot, int do_norm,
             const int sc[4] = {sv.x, sv.y, sv.z, sv.w};
             const int cw[4] = {cv.x, cv.y, cv.z, cv.w};
             int fden = 0;
-            for (int k = 0; k < N; ++k) {
+            for (int k = 0; k < N && sc[k] != K2_UNUSED; ++k) {
                 int v = m.mixw[(int64_t)(f * ND + cw[k]) * m.n_sen + sen] + sc[k];
                 fden = k == 0 ? v : logadd8(fden, v, lut);
             }
@@ -526,7 +534,8 @@ frame_senones_kernel(DevModel m, FrameHist h, int slot, int do_norm,
     if (local_best != INT32_MAX)
         atomicMin(&s_best, local_best);
     __syncthreads();
-    const int16_t b = (int16_t)s_best;
+    // ref: src/ptm_mgau.c:398-400; s2_semi leaves the sums as they are (and unlisted senones 0)
+    const int16_t b = m.kind == SSB_SCORER_SEMI ? (int16_t)0 : (int16_t)s_best;
     for (int i = threadIdx.x; i < m.n_sen; i += blockDim.x)
         senscr[i] = (int16_t)(senscr[i] - b);
 }

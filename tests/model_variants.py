@@ -65,6 +65,11 @@ def _sendump_strings(fh, strings):
 
 def write_clustered_sendump(src, dst, mixw, seed=7, n_clust=15):
     """4-bit clustered sendump.  Returns (codebook[16], packed[F][D][(S+1)//2])."""
+    _link_shared(src, dst)
+    return _write_clustered(dst, mixw, seed, n_clust)
+
+
+def _write_clustered(dst, mixw, seed=7, n_clust=15):
     n_feat, n_density, n_sen = mixw.shape
     rs = np.random.RandomState(seed)
     book = np.sort(rs.choice(np.arange(0, 160), 16, replace=False)).astype(np.uint8)
@@ -73,7 +78,6 @@ def write_clustered_sendump(src, dst, mixw, seed=7, n_clust=15):
     if n_sen & 1:
         code = np.concatenate([code, np.zeros(code.shape[:2] + (1,), np.uint8)], -1)
     packed = (code[..., 0::2] | (code[..., 1::2] << 4)).astype(np.uint8)
-    _link_shared(src, dst)
     with open(os.path.join(dst, "sendump"), "wb") as fh:
         _sendump_strings(fh, ["clustered test sendump", "header"])
         _sendump_strings(fh, ["feature_count %d" % n_feat, "mixture_count %d" % n_density,
@@ -144,3 +148,89 @@ def fe_input(spec, samprate):
         w = wave.open(path)
         return np.frombuffer(w.readframes(w.getnframes()), np.int16).copy()
     return np.fromfile(path, np.int16)
+
+
+# ---------------------------------------------------------------------- semi-continuous models
+def read_gauden(path):
+    """(n_mgau, n_feat, n_density, featlen, data) of a means / variances S3 file."""
+    blob = open(path, "rb").read()
+    pos = blob.index(b"endhdr\n") + 7
+    assert struct.unpack_from("<I", blob, pos)[0] == 0x11223344
+    pos += 4
+    n_mgau, n_feat, n_density = struct.unpack_from("<3i", blob, pos)
+    pos += 12
+    featlen = struct.unpack_from("<%di" % n_feat, blob, pos)
+    pos += 4 * n_feat
+    n = struct.unpack_from("<i", blob, pos)[0]
+    pos += 4
+    data = np.frombuffer(blob, "<f4", n, pos).reshape(n_mgau, n_density * sum(featlen))
+    return n_mgau, n_feat, n_density, featlen, data
+
+
+def _s3_checksum(words):
+    s = 0
+    for w in words.tolist():
+        s = ((((s << 20) | (s >> 12)) & 0xffffffff) + w) & 0xffffffff
+    return s
+
+
+def write_gauden(path, arr, featlen):
+    """arr [n_mgau][n_feat][n_density][L] (equal stream lengths) -> S3 file with checksum."""
+    n_mgau, n_feat, n_density, L = arr.shape
+    assert all(x == L for x in featlen)
+    words = np.concatenate([np.array([n_mgau, n_feat, n_density] + list(featlen) + [arr.size],
+                                     "<i4").view("<u4"),
+                            np.ascontiguousarray(arr, "<f4").view("<u4").ravel()])
+    with open(path, "wb") as fh:
+        fh.write(b"s3\nversion 1.0\nchksum0 yes\nendhdr\n" + struct.pack("<I", 0x11223344))
+        fh.write(words.tobytes())
+        fh.write(struct.pack("<I", _s3_checksum(words)))
+
+
+def write_semi_model(src, dst, n_sen, n_density=256, seed=3, clustered=False, topn_beam=None):
+    """A semi-continuous (single codebook) model directory for the s2_semi scorer: the bundled
+    model's mdef / transitions / feature parameters, `n_density` Gaussians per stream drawn from
+    its own codebooks, and seeded mixture weights for every senone (8-bit sendump, or the 4-bit
+    clustered one)."""
+    import json
+    rs = np.random.RandomState(seed)
+    os.makedirs(dst, exist_ok=True)
+    n_mgau, n_feat, nd, featlen, mean = read_gauden(os.path.join(src, "means"))
+    _, _, _, _, var = read_gauden(os.path.join(src, "variances"))
+    L = featlen[0]
+    mean = mean.reshape(n_mgau, n_feat, nd, L)
+    var = var.reshape(n_mgau, n_feat, nd, L)
+    pick_c, pick_d = rs.randint(0, n_mgau, (n_feat, n_density)), rs.randint(0, nd, (n_feat, n_density))
+    f_idx = np.arange(n_feat)[:, None]
+    write_gauden(os.path.join(dst, "means"), mean[pick_c, f_idx, pick_d][None], featlen)
+    write_gauden(os.path.join(dst, "variances"), var[pick_c, f_idx, pick_d][None], featlen)
+    with open(os.path.join(src, "feat_params.json")) as fh:
+        fp = json.load(fh)
+    if topn_beam is not None:
+        fp["topn_beam"] = topn_beam
+    with open(os.path.join(dst, "feat_params.json"), "w") as fh:
+        json.dump(fp, fh)
+    for name in ("mdef", "transition_matrices", "noisedict.txt", "dict.txt", "phoneset.json"):
+        s = os.path.join(src, name)
+        if os.path.exists(s) and not os.path.exists(os.path.join(dst, name)):
+            os.symlink(os.path.abspath(s), os.path.join(dst, name))
+    # senones: the mdef decides how many (n_sen of the source model)
+    mixw = np.minimum(159, (rs.gamma(2.0, 18.0, (n_feat, n_density, n_sen))).astype(np.int32)).astype(np.uint8)
+    if clustered:
+        _write_clustered(dst, mixw, seed + 1)
+    else:
+        with open(os.path.join(dst, "sendump"), "wb") as fh:
+            _sendump_strings(fh, ["semi test sendump", "header"])
+            _sendump_strings(fh, ["feature_count %d" % n_feat, "mixture_count %d" % n_density,
+                                  "model_count %d" % n_sen])
+            fh.write(struct.pack("<i", 0))
+            fh.write(struct.pack("<2i", n_density, n_sen))
+            fh.write(mixw.tobytes())
+    return dict(n_sen=n_sen, n_density=n_density, n_feat=n_feat)
+
+
+SEMI_CASES = [  # (tag, write_semi_model keywords, topn_beam as a list)
+    ("semi256", dict(n_density=256, seed=3), None),
+    ("semi4b", dict(n_density=128, seed=4, clustered=True), None),
+    ("beam64", dict(n_density=64, seed=5, topn_beam="40,0,25"), [40, 0, 25]),
+]

@@ -33,7 +33,8 @@ def test_struct_layouts_match_header():
     # mgau_t prefix: {vt pointer, int frame_idx} (ref: include/soundswallower/acmod.h:108-111)
     assert _lib.MgauBase.vt.offset == 0 and _lib.MgauBase.frame_idx.offset == C.sizeof(C.c_void_p)
     assert [f[0] for f in _lib.MgauFuncs._fields_] == ["name", "frame_eval", "transform", "free"]
-    assert C.sizeof(_lib.Config) == 48
+    assert C.sizeof(_lib.Config) == 64 and _lib.Config.topn_beam.offset == 44
+    assert C.sizeof(_lib.FeConfig) == 72
     assert C.sizeof(_lib.AlignIn) == 80 and C.sizeof(_lib.AlignOut) == 64
 
 

@@ -234,6 +234,46 @@ def frontend():
     np.savez_compressed(os.path.join(OUT, "frontend.npz"), **g)
 
 
+def semi(lang="en-us"):
+    """Semi-continuous (s2_semi_mgau) scoring and alignment through the reference on the
+    synthetic single-codebook models of tests/model_variants.py -> semi_<lang>.npz."""
+    import tempfile
+    import model_variants as mv
+    src = os.path.join(MODELS, lang)
+    ga = np.load(os.path.join(OUT, "align_%s.npz" % lang))
+    feat, words = ga["feat"], ga["words"]
+    g = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for tag, kw, _ in mv.SEMI_CASES:
+            d = os.path.join(tmp, tag)
+            mv.write_semi_model(src, d, int(ga["dims"][4]), **kw)
+            ref = Ref(d)
+            refc = Ref(d, compallsen=True)
+            assert ref.n_mgau == 1
+            arrays = ref.model_arrays()
+            g[tag + "_mixw_sha"] = sha(arrays["mixw"])
+            g[tag + "_det_sha"] = sha(arrays["det"])
+            dense = refc.score_all(feat)
+            g[tag + "_senscr_sha"] = sha(dense)
+            g[tag + "_senscr_rows"] = dense[[0, 1, 100, len(feat) - 1]]
+            chain_sen = arrays["sseq"][ga["phones"][:, 1]].reshape(-1)
+            for name, r, k2 in (("win", ref, dict(start=words[:, 1], dur=words[:, 2])),
+                                ("nowin", ref, dict()),
+                                ("win_call", refc, dict(start=words[:, 1], dur=words[:, 2]))):
+                res = r.state_align(feat, words[:, 0], clear_active=True, want_tokens=True,
+                                    want_senscr=True, **k2)
+                key = "%s_%s_" % (tag, name)
+                g[key + "rv"] = np.int32(res["rv"])
+                g[key + "best"] = np.int32(res["best_score"])
+                g[key + "states"] = res["states"]
+                g[key + "tokens_sha"] = sha(res["tokens"])
+                g[key + "chain_scr"] = res["senscr"][:, chain_sen]
+            ref.close()
+            refc.close()
+            print("semi", tag, dense.shape, int(dense.min()), int(dense.max()))
+    np.savez_compressed(os.path.join(OUT, "semi_%s.npz" % lang), **g)
+
+
 def main():
     if not available():
         raise SystemExit("oracle/_ref/libssref.so missing: run `make -C oracle ref` first")
@@ -242,6 +282,8 @@ def main():
         return loaders()
     if "--frontend" in sys.argv:
         return frontend()
+    if "--semi" in sys.argv:
+        return semi()
     utterance("en-us", "goforward.raw", "go forward ten meters")
     utterance("fr-fr", "goforward_fr.raw", "avance de dix mètres")
     synthetic("en-us")
@@ -249,6 +291,7 @@ def main():
     fsg("fr-fr", "goforward_fr.raw", "avance de dix mètres", "goforward_fr.gram")
     loaders()
     frontend()
+    semi()
 
 
 if __name__ == "__main__":
