@@ -64,9 +64,11 @@ void ssb_config_defaults(ssb_config_t *cfg);
 /* Which of the reference's scorers the model directory selects, in acmod_load_am's order
  * (ref: src/acmod.c:101-119): ptm_mgau when there is one codebook per CI phone
  * (ref: src/ptm_mgau.c:722-816), s2_semi_mgau when there is a single codebook
- * (ref: src/s2_semi_mgau.c:829-1058).  Fully continuous models (ms_mgau) are declined
- * (NULL) so that a caller falls through to the reference's own scorer. */
-enum { SSB_SCORER_PTM = 0, SSB_SCORER_SEMI = 1 };
+ * (ref: src/s2_semi_mgau.c:829-1058), else ms_mgau (ref: src/ms_mgau.c:279-368) -- offered for
+ * fully continuous models with one codebook per senone (the ".cont." map of
+ * src/ms_senone.c:262-275); other shapes and explicit "senmgau" maps are declined (NULL) so
+ * that a caller falls through to the reference's own scorer. */
+enum { SSB_SCORER_PTM = 0, SSB_SCORER_SEMI = 1, SSB_SCORER_CONT = 2 };
 typedef struct ssb_model_s ssb_model_t;
 ssb_model_t *ssb_model_load(const char *hmmdir, const ssb_config_t *cfg);
 int ssb_model_kind(const ssb_model_t *m);

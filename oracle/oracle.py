@@ -15,7 +15,7 @@ INT_MAX = 2**31 - 1
 
 
 def build(force=False):
-    srcs = [os.path.join(HERE, f) for f in ("ss_oracle.c", "ss_oracle.h", "ss_oracle_fsg.c", "ss_oracle_fe.c")]
+    srcs = [os.path.join(HERE, f) for f in ("ss_oracle.c", "ss_oracle.h", "ss_oracle_fsg.c", "ss_oracle_fe.c", "ss_oracle_cont.c")]
     srcs = [s for s in srcs if os.path.exists(s)]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", HERE, "liboracle"])

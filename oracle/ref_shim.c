@@ -26,6 +26,7 @@
 #include <soundswallower/feat.h>
 #include <soundswallower/fsg_search.h>
 #include <soundswallower/hmm.h>
+#include <soundswallower/ms_mgau.h>
 #include <soundswallower/ptm_mgau.h>
 #include <soundswallower/s2_semi_mgau.h>
 #include <soundswallower/search_module.h>
@@ -84,6 +85,9 @@ ref_model_dims(void *h, int32 *out)
     } else if (strcmp(r->d->acmod->mgau->vt->name, "s2_semi") == 0) {
         g = ((s2_semi_mgau_t *)r->d->acmod->mgau)->g;
         n_sen = ((s2_semi_mgau_t *)r->d->acmod->mgau)->n_sen;
+    } else if (strcmp(r->d->acmod->mgau->vt->name, "ms") == 0) {
+        g = ((ms_mgau_model_t *)r->d->acmod->mgau)->g;
+        n_sen = ((ms_mgau_model_t *)r->d->acmod->mgau)->s->n_sen;
     } else
         return -1;
     out[0] = g->n_mgau;
@@ -110,11 +114,18 @@ ref_model_copy(void *h, float *mean, float *var, float *det, uint8 *mixw,
     tmat_t *t = r->d->acmod->tmat;
     int i, j, k, c, f, n = 0, nd = 0;
     int semi = strcmp(r->d->acmod->mgau->vt->name, "s2_semi") == 0;
+    int cont = strcmp(r->d->acmod->mgau->vt->name, "ms") == 0;
     gauden_t *g;
     uint8 ***mw, *mw_cb;
     logmath_t *lm8;
     int n_sen;
-    if (semi) {
+    if (cont) {
+        /* ms_mgau: weights are senone->pdf[sen][feat][codeword] (n_gauden > 1) */
+        ms_mgau_model_t *s = (ms_mgau_model_t *)r->d->acmod->mgau;
+        if (s->s->n_gauden <= 1)
+            return -3;
+        g = s->g, mw = (uint8 ***)s->s->pdf, mw_cb = NULL, lm8 = s->s->lmath, n_sen = s->s->n_sen;
+    } else if (semi) {
         s2_semi_mgau_t *s = (s2_semi_mgau_t *)r->d->acmod->mgau;
         g = s->g, mw = s->mixw, mw_cb = s->mixw_cb, lm8 = s->lmath_8b, n_sen = s->n_sen;
     } else {
@@ -130,7 +141,10 @@ ref_model_copy(void *h, float *mean, float *var, float *det, uint8 *mixw,
                 n += L;
                 det[nd++] = g->det[c][f][k];
             }
-    for (f = 0; f < g->n_feat; ++f)
+    for (f = 0; cont && f < n_sen; ++f) /* [sen][feat][codeword] as stored */
+        for (k = 0; k < g->n_feat; ++k)
+            memcpy(mixw + ((size_t)f * g->n_feat + k) * g->n_density, mw[f][k], g->n_density);
+    for (f = 0; !cont && f < g->n_feat; ++f)
         for (k = 0; k < g->n_density; ++k) {
             uint8 *dst = mixw + ((size_t)f * g->n_density + k) * n_sen;
             if (!mw_cb) {
@@ -149,7 +163,7 @@ ref_model_copy(void *h, float *mean, float *var, float *det, uint8 *mixw,
                 dst[i] = mw_cb[dcw];
             }
         }
-    if (semi)
+    if (semi || cont)
         memset(sen2cb, 0, n_sen);
     else
         memcpy(sen2cb, ((ptm_mgau_t *)r->d->acmod->mgau)->sen2cb, n_sen);

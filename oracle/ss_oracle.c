@@ -385,6 +385,55 @@ fail:
     return -1;
 }
 
+/* ref: ms_senone.c:103-190 (senone_mixw_read): the continuous scorer's own quantisation --
+ * shift-0 log, rounded before the >> 10, clamped at 255 -- stored [sen][feat][density]. */
+static int
+load_mixw_cont(orc_model_t *m, const char *dir)
+{
+    rd_t r;
+    int32_t n_sen, n_feat, n_cw, n, i, f, c;
+    const float flr_f = 1e-7f;
+    const double flr = flr_f;
+    float *pdf = NULL;
+    if (rd_open(&r, dir, "mixture_weights") < 0)
+        return -1;
+    if (rd_s3_header(&r) < 0)
+        goto fail;
+    if (rd_u32(&r, &n_sen, 1) < 0 || rd_u32(&r, &n_feat, 1) < 0 || rd_u32(&r, &n_cw, 1) < 0
+        || rd_u32(&r, &n, 1) < 0)
+        goto fail;
+    if (n_feat != m->n_feat || n_cw != m->n_density || n_sen != m->n_sen
+        || n != n_sen * n_feat * n_cw)
+        goto fail;
+    m->mixw = calloc((size_t)n_feat * n_cw * n_sen, 1);
+    pdf = malloc(sizeof(float) * n_cw);
+    for (i = 0; i < n_sen; ++i)
+        for (f = 0; f < n_feat; ++f) {
+            if (rd_u32(&r, pdf, n_cw) < 0)
+                goto fail;
+            sum_norm_f32(pdf, n_cw);
+            for (c = 0; c < n_cw; ++c)
+                if (pdf[c] < flr)
+                    pdf[c] = (float)flr;
+            sum_norm_f32(pdf, n_cw);
+            for (c = 0; c < n_cw; ++c) {
+                int32_t p = -orc_logmath_log(m->logbase, 0, pdf[c]);
+                p += (1 << (ORC_SENSCR_SHIFT - 1)) - 1;
+                m->mixw[((size_t)i * n_feat + f) * n_cw + c]
+                    = (uint8_t)(p < (255 << ORC_SENSCR_SHIFT) ? p >> ORC_SENSCR_SHIFT : 255);
+            }
+        }
+    if (rd_verify(&r) < 0)
+        goto fail;
+    free(pdf);
+    free(r.buf);
+    return 0;
+fail:
+    free(pdf);
+    free(r.buf);
+    return -1;
+}
+
 /* ref: bin_mdef.c:333-520 */
 static int
 load_mdef(orc_model_t *m, const char *dir)
@@ -575,9 +624,13 @@ orc_model_load(const char *dir, double logbase, float varfloor, double tmatfloor
     else if (m->n_mgau == 1) {
         m->kind = ORC_KIND_SEMI;
         memset(m->sen2cb, 0, m->n_sen);
-    } else
+    } else if (m->n_mgau == m->n_sen)
+        m->kind = ORC_KIND_CONT; /* ms_mgau with the 1-to-1 senone-codebook map (ms_senone.c:262-275) */
+    else
         goto fail;
-    if ((c = load_sendump(m, dir)) == -2)
+    if (m->kind == ORC_KIND_CONT)
+        c = load_mixw_cont(m, dir);
+    else if ((c = load_sendump(m, dir)) == -2)
         c = load_mixw_float(m, dir);
     if (c < 0)
         goto fail;
@@ -926,6 +979,8 @@ orc_ptm_frame_eval(orc_ptm_t *p, int16_t *senscr, const uint8_t *active, int32_t
 
     if (m->kind == ORC_KIND_SEMI)
         return semi_frame_eval(p, senscr, active, n_active, feat, frame, compallsen, topn_out);
+    if (m->kind == ORC_KIND_CONT)
+        return orc_cont_frame_eval(m, p->topn, senscr, active, n_active, feat, compallsen);
     if (frame >= p->frame_idx) {
         topn_t *prev = p->hist[slot ? slot - 1 : 1];
         memcpy(cur, prev, sizeof(topn_t) * m->n_mgau * m->n_feat * N);

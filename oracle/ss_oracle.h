@@ -60,7 +60,7 @@ typedef struct orc_model_s {
     int32_t kind;
     int32_t topn_beam[ORC_MAX_FEAT]; /* s2_semi "topn_beam" per stream, 0 = off */
 } orc_model_t;
-enum { ORC_KIND_PTM = 0, ORC_KIND_SEMI = 1 };
+enum { ORC_KIND_PTM = 0, ORC_KIND_SEMI = 1, ORC_KIND_CONT = 2 };
 
 /* ---- load-time (ref: logmath.c, ms_gauden.c, ptm_mgau.c read_sendump, bin_mdef.c, tmat.c) */
 int orc_logadd_table8(double base, int shift, uint8_t *out256);
@@ -92,6 +92,12 @@ int orc_ptm_score_all(const orc_model_t *m, int topn, const float *feat, int T, 
  * cw[T][mgau][feat][topn] (u8), score[T][mgau][feat][topn] (i32) */
 int orc_ptm_topn_all(const orc_model_t *m, int topn, const float *feat, int T, uint8_t *cw,
                      int32_t *score);
+
+/* ---- continuous scorer (ss_oracle_cont.c; ref: ms_mgau.c:279-368, ms_gauden.c:342-457,
+ * ms_senone.c:315-362).  mixw is [sen][feat][density] for such models.  In active-list mode
+ * only the listed entries of senscr are written, like the reference. */
+int orc_cont_frame_eval(const orc_model_t *m, int topn, int16_t *senscr, const uint8_t *active,
+                        int32_t n_active, const float *feat, int32_t compallsen);
 
 /* ---- active list (ref: acmod.c:947-999) */
 int orc_flags2list(const uint32_t *bits, int n_sen, uint8_t *out);

@@ -25,6 +25,14 @@ int launch_chain_viterbi(const DevModel &m, const DevPlan &p, const int16_t *cha
                          int2 *tokens, int32_t *spill, int64_t spill_stride, int32_t *utt_best,
                          int32_t *utt_renorm, int32_t *fin_hist, int32_t *fin_score,
                          int max_phones, cudaStream_t st);
+// cont_score.cu: fully continuous models (ref: src/ms_mgau.c:279-368)
+int launch_cont_dense(const DevModel &m, const float *feat, int64_t g0, int64_t n, int16_t *dense,
+                      cudaStream_t st);
+int launch_cont_active(const DevModel &m, const DevPlan &p, const float *feat, int W,
+                       int max_frames_per_utt, int16_t *scratch, int16_t *chain_scr,
+                       cudaStream_t st);
+int launch_cont_frame(const DevModel &m, const float *x, const uint16_t *act_sen, int n_act,
+                      int compallsen, int16_t *raw, int16_t *senscr, cudaStream_t st);
 }  // namespace ssb
 
 using namespace ssb;
@@ -390,7 +398,7 @@ struct ssb_mgau_impl {
     ssb_mgau_t base;  // must be first: {vt, frame_idx}
     ssb_model_t *m;
     FrameHist hist;
-    DBuf hs[2], hc[2], ha[2], x, senscr, act;
+    DBuf hs[2], hc[2], ha[2], x, senscr, act, raw;
     float *h_x = nullptr;
     int16_t *h_senscr = nullptr;
     uint16_t *h_act = nullptr;
@@ -411,7 +419,12 @@ static int mgau_transform_vt(ssb_mgau_t *, void *)
     return -1;
 }
 static void mgau_free_vt(ssb_mgau_t *g) { ssb_mgau_free(g); }
-static ssb_mgaufuncs_t g_mgau_funcs = {"ptm", mgau_frame_eval_vt, mgau_transform_vt, mgau_free_vt};
+// one vtable per scorer family, named like the reference's (ptm_mgau.c:57, s2_semi_mgau.c:57,
+// ms_mgau.c:75)
+static ssb_mgaufuncs_t g_mgau_funcs[3] = {
+    {"ptm", mgau_frame_eval_vt, mgau_transform_vt, mgau_free_vt},
+    {"s2_semi", mgau_frame_eval_vt, mgau_transform_vt, mgau_free_vt},
+    {"ms", mgau_frame_eval_vt, mgau_transform_vt, mgau_free_vt}};
 
 static int mgau_reset_device(ssb_mgau_impl *g)
 {
@@ -436,7 +449,7 @@ extern "C" ssb_mgau_t *ssb_mgau_init(ssb_model_t *m)
     const HostModel &h = m->h;
     const int CS = h.n_mgau * h.n_feat;
     ssb_mgau_impl *g = new ssb_mgau_impl;
-    g->base.vt = &g_mgau_funcs;
+    g->base.vt = &g_mgau_funcs[h.kind];
     g->base.frame_idx = 0;
     g->m = m;
     bool ok = cudaStreamCreateWithFlags(&g->st, cudaStreamNonBlocking) == cudaSuccess;
@@ -448,7 +461,10 @@ extern "C" ssb_mgau_t *ssb_mgau_init(ssb_model_t *m)
         g->hist.act[i] = g->ha[i].as<uint8_t>();
     }
     ok = ok && g->x.ensure(h.blk * sizeof(float)) == 0 && g->senscr.ensure(h.n_sen * 2) == 0
-         && g->act.ensure((size_t)h.n_sen * 2 + 16) == 0;
+         && g->raw.ensure(h.n_sen * 2) == 0 && g->act.ensure((size_t)h.n_sen * 2 + 16) == 0;
+    // the continuous scorer only writes the listed senones: the rest of the buffer starts as
+    // the reference's calloc'ed senone_scores does
+    ok = ok && cudaMemset(g->senscr.p, 0, h.n_sen * 2) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&g->h_x, h.blk * sizeof(float)) == cudaSuccess
          && cudaMallocHost((void **)&g->h_senscr, h.n_sen * 2) == cudaSuccess
          && cudaMallocHost((void **)&g->h_act, (size_t)h.n_sen * 2 + 16) == cudaSuccess
@@ -489,6 +505,7 @@ extern "C" void ssb_mgau_free(ssb_mgau_t *gg)
     g->x.release();
     g->senscr.release();
     g->act.release();
+    g->raw.release();
     if (g->h_x)
         cudaFreeHost(g->h_x);
     if (g->h_senscr)
@@ -528,6 +545,18 @@ extern "C" int ssb_mgau_frame_eval(ssb_mgau_t *gg, int16_t *senscr, uint8_t *sen
         }
         if (n_list)
             API_CUDA(cudaMemcpyAsync(g->act.p, g->h_act, n_list * 2, cudaMemcpyHostToDevice, g->st), -1);
+    }
+    if (h.kind == SSB_SCORER_CONT) {  // stateless: no history slots, no codebook flags
+        for (int f = 0; f < h.n_feat; ++f)
+            std::memcpy(g->h_x + h.featoff[f], feat[f], h.featlen[f] * sizeof(float));
+        API_CUDA(cudaMemcpyAsync(g->x.p, g->h_x, h.blk * sizeof(float), cudaMemcpyHostToDevice, g->st), -1);
+        if (launch_cont_frame(d, g->x.as<float>(), g->act.as<uint16_t>(), n_list, compallsen,
+                              g->raw.as<int16_t>(), g->senscr.as<int16_t>(), g->st) != 0)
+            return -1;
+        API_CUDA(cudaMemcpyAsync(g->h_senscr, g->senscr.p, h.n_sen * 2, cudaMemcpyDeviceToHost, g->st), -1);
+        API_CUDA(cudaStreamSynchronize(g->st), -1);
+        std::memcpy(senscr, g->h_senscr, h.n_sen * 2);
+        return 0;
     }
     const bool fresh = frame >= g->base.frame_idx;
     if (fresh) {
@@ -603,6 +632,16 @@ struct ssb_batch_s {
             b->release();
     }
 };
+
+// final senone scores of frames [g0, g0+n) of the uploaded batch, "compallsen" semantics
+static int dense_scores(ssb_batch_t *b, int64_t g0, int64_t n, int16_t *dense)
+{
+    const DevModel &d = b->m->d;
+    if (d.kind == SSB_SCORER_CONT)
+        return launch_cont_dense(d, b->feat.as<float>(), g0, n, dense, b->st);
+    return launch_senone_mix_all(d, b->tn_s.as<int4>(), b->tn_c.as<uchar4>(), b->n_frames, g0, n,
+                                 dense, b->st);
+}
 
 extern "C" ssb_batch_t *ssb_batch_create(ssb_model_t *m, void *stream)
 {
@@ -893,7 +932,7 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
 
     // ---- device buffers; the feature copy starts now and overlaps the planning below
     cudaStream_t st = b->st;
-    const int CS = h.n_mgau * h.n_feat;
+    const int CS = h.kind == SSB_SCORER_CONT ? 0 : h.n_mgau * h.n_feat;  // no top-N stage
     const int64_t G = b->n_frames;
     if (b->feat.ensure(std::max<size_t>((size_t)G * h.blk * sizeof(float), 16)) != 0
         || (tc_supported(b->m->d) && b->featp.ensure(std::max<size_t>(tc2_featp_bytes(b->m->d, G), 16)) != 0)
@@ -1033,7 +1072,13 @@ extern "C" int ssb_batch_run(ssb_batch_t *b)
     }
     API_CUDA(cudaEventRecord(b->ev[1], st), -1);
     if (U > 0 && b->n_frames > 0 && b->n_states > 0) {
-        if (!b->compallsen) {
+        if (!b->compallsen && d.kind == SSB_SCORER_CONT) {
+            const int W = std::max(b->max_union, 1);
+            if (b->dense.ensure((size_t)b->n_frames * W * 2) != 0
+                || launch_cont_active(d, p, b->feat.as<float>(), W, b->max_T,
+                                      b->dense.as<int16_t>(), b->chain_scr.as<int16_t>(), st) != 0)
+                return -1;
+        } else if (!b->compallsen) {
             if (launch_senone_mix_active(d, p, b->tn_s.as<int4>(), b->tn_c.as<uchar4>(),
                                          b->n_frames, b->max_union + 1, b->max_T,
                                          b->chain_scr.as<int16_t>(), st) != 0)
@@ -1048,8 +1093,7 @@ extern "C" int ssb_batch_run(ssb_batch_t *b)
                 if (n > 0) {
                     if (b->dense.ensure((size_t)n * d.n_sen * 2) != 0)
                         return -1;
-                    if (launch_senone_mix_all(d, b->tn_s.as<int4>(), b->tn_c.as<uchar4>(),
-                                              b->n_frames, g0, n, b->dense.as<int16_t>(), st) != 0
+                    if (dense_scores(b, g0, n, b->dense.as<int16_t>()) != 0
                         || launch_gather_chain(d, p, b->dense.as<int16_t>(), u0, u1, g0,
                                                b->chain_scr.as<int16_t>(), st) != 0)
                         return -1;
@@ -1244,8 +1288,7 @@ extern "C" int64_t ssb_score_batch(ssb_model_t *m, const float *feat, const int6
         for (int64_t g0 = 0; g0 < G && ok; g0 += kSlabFrames) {
             const int64_t n = std::min(kSlabFrames, G - g0);
             ok = b->dense.ensure((size_t)n * d.n_sen * 2) == 0
-                 && launch_senone_mix_all(d, b->tn_s.as<int4>(), b->tn_c.as<uchar4>(), G, g0, n,
-                                          b->dense.as<int16_t>(), b->st) == 0;
+                 && dense_scores(b, g0, n, b->dense.as<int16_t>()) == 0;
             if (ok && senscr
                 && cudaMemcpyAsync(senscr + g0 * d.n_sen, b->dense.p, (size_t)n * d.n_sen * 2,
                                    cudaMemcpyDeviceToHost, b->st) != cudaSuccess) {
@@ -1578,8 +1621,7 @@ extern "C" int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out
             cudaEventRecord(b->ev[2], st);
             if (n > 0)
                 ok = b->dense.ensure((size_t)n * d.n_sen * 2) == 0
-                     && launch_senone_mix_all(d, b->tn_s.as<int4>(), b->tn_c.as<uchar4>(), G, g0, n,
-                                              b->dense.as<int16_t>(), st) == 0;
+                     && dense_scores(b, g0, n, b->dense.as<int16_t>()) == 0;
             cudaEventRecord(b->ev[3], st);
             ok = ok
                  && launch_fsg_search(d, gs, b->d_frame_off.as<int64_t>(), d_ug.as<int32_t>(),

@@ -352,8 +352,8 @@ static int launch_k1_n(const DevModel &m, const DevPlan &p, const float *feat, i
 int launch_gmm_topn(const DevModel &m, const DevPlan &p, const float *feat, int64_t n_frames,
                     int4 *tn_score, uchar4 *tn_cw, float *featp, cudaStream_t st)
 {
-    if (p.n_utts == 0 || n_frames == 0)
-        return 0;
+    if (p.n_utts == 0 || n_frames == 0 || m.kind == SSB_SCORER_CONT)
+        return 0;  // (the continuous scorer has no top-N stage: cont_score.cu)
     // default: tensor-core screening kernel (gmm_topn_tc.cu); SSB_K1=fp32 keeps the plain
     // CUDA-core scan below (same results, used for A/B timing and as the generic-shape path)
     const char *force = getenv("SSB_K1");

@@ -6,6 +6,10 @@
 // written from the format descriptions, array-based, with no mmap retention.
 #include "model.h"
 
+#include <sys/stat.h>
+
+#include <algorithm>
+
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -477,6 +481,61 @@ static bool read_mixw_float(HostModel &m, const std::string &path)
     return f.s3_trailer();
 }
 
+// ref: src/ms_senone.c:103-190 (senone_mixw_read): the continuous scorer's own quantisation
+// (shift-0 log, +511 before the >> 10, clamp 255), kept [sen][feat][density]
+static bool read_mixw_cont(HostModel &m, const std::string &path)
+{
+    Blob f;
+    if (!f.open(path) || !f.s3_header()) {
+        set_error("cannot read S3 file %s", path.c_str());
+        return false;
+    }
+    int32_t n_sen, n_feat, n_cw, n;
+    if (!f.i32(n_sen) || !f.i32(n_feat) || !f.i32(n_cw) || !f.i32(n) || n_feat != m.n_feat
+        || n_cw != m.n_density || n_sen != m.n_sen || n != n_sen * n_feat * n_cw) {
+        set_error("%s: dimensions do not match the model", path.c_str());
+        return false;
+    }
+    if (m.cfg.mixwfloor <= 0.0 || m.cfg.mixwfloor >= 1.0) {
+        set_error("mixwfloor (%e) not in range (0, 1)", m.cfg.mixwfloor);
+        return false;
+    }
+    LogMath lm(m.cfg.logbase);
+    const float flr_f = (float)m.cfg.mixwfloor;  // the reference holds it in a float32
+    const double flr = flr_f;
+    std::vector<float> pdf(n_cw);
+    m.mixw.assign((size_t)n_sen * n_feat * n_cw, 0);
+    auto sum_norm = [&]() {
+        double s = 0.0;
+        for (float x : pdf)
+            s += x;
+        if (s != 0.0) {
+            const double r = 1.0 / s;
+            for (float &x : pdf)
+                x = (float)(x * r);
+        }
+    };
+    for (int s = 0; s < n_sen; ++s)
+        for (int ft = 0; ft < n_feat; ++ft) {
+            if (!f.words(pdf.data(), n_cw))
+                return false;
+            sum_norm();
+            for (float &x : pdf)
+                if (x < flr)
+                    x = (float)flr;
+            sum_norm();
+            for (int c = 0; c < n_cw; ++c) {
+                int32_t p = -lm.log(pdf[c], 0) + ((1 << 9) - 1);
+                m.mixw[((size_t)s * n_feat + ft) * n_cw + c] = (uint8_t)(p < (255 << 10) ? p >> 10 : 255);
+            }
+        }
+    if (!f.s3_trailer()) {
+        set_error("%s: checksum mismatch", path.c_str());
+        return false;
+    }
+    return true;
+}
+
 // ---------------------------------------------------------------- tmat
 // ref: src/tmat.c:125-225: rows normalised, non-zero entries floored, renormalised,
 // then min(255, (-log_b p) >> 10); zero probability -> 255.
@@ -545,8 +604,8 @@ bool HostModel::load(const std::string &dir, const ssb_config_t &c)
     n_mgau = d1[0];
     n_feat = d1[1];
     n_density = d1[2];
-    if (n_mgau > SSB_MAX_CB || n_density > 256) {
-        set_error("at most %d codebooks of 256 densities are supported", SSB_MAX_CB);
+    if (n_density > 256) {
+        set_error("at most 256 densities per codebook are supported");
         return false;
     }
     blk = 0;
@@ -572,11 +631,28 @@ bool HostModel::load(const std::string &dir, const ssb_config_t &c)
     else if (n_mgau == 1) {
         kind = SSB_SCORER_SEMI;
         std::fill(sen2cb.begin(), sen2cb.end(), (uint8_t)0);
+    } else if (n_mgau == n_sen) {
+        // ms_mgau with one codebook per senone (ref: src/ms_senone.c:262-275, ".cont.")
+        kind = SSB_SCORER_CONT;
+        std::fill(sen2cb.begin(), sen2cb.end(), (uint8_t)0);
     } else {
-        set_error("%d codebooks but %d CI phones: neither a PTM nor a semi-continuous model",
-                  n_mgau, n_ciphone);
+        set_error("%d codebooks for %d CI phones / %d senones: not a PTM, semi-continuous or "
+                  "continuous model", n_mgau, n_ciphone, n_sen);
         return false;
     }
+    if (kind == SSB_SCORER_PTM && n_mgau > SSB_MAX_CB) {
+        set_error("at most %d codebooks are supported (ref: src/ptm_mgau.c:754)", SSB_MAX_CB);
+        return false;
+    }
+    if (kind == SSB_SCORER_CONT) {
+        struct stat sb;
+        if (stat((dir + "/senmgau").c_str(), &sb) == 0) {
+            set_error("%s/senmgau: explicit senone-to-codebook maps are not supported", dir.c_str());
+            return false;
+        }
+        if (!read_mixw_cont(*this, dir + "/mixture_weights"))
+            return false;
+    } else
     if (!read_sendump(*this, dir + "/sendump")) {
         if (!mixw.empty() || !read_mixw_float(*this, dir + "/mixture_weights"))
             return false;

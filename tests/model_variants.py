@@ -234,3 +234,49 @@ SEMI_CASES = [  # (tag, write_semi_model keywords, topn_beam as a list)
     ("semi4b", dict(n_density=128, seed=4, clustered=True), None),
     ("beam64", dict(n_density=64, seed=5, topn_beam="40,0,25"), [40, 0, 25]),
 ]
+
+
+# ---------------------------------------------------------------------- continuous models
+def write_cont_model(src, dst, n_sen, n_density=8, seed=9):
+    """A fully continuous model directory for the ms_mgau scorer: one codebook per senone with
+    `n_density` 39-dimensional Gaussians (a single feature stream: no svspec), drawn from the
+    bundled model's codebooks, and seeded float mixture weights."""
+    import json
+    rs = np.random.RandomState(seed)
+    os.makedirs(dst, exist_ok=True)
+    n_mgau, n_feat, nd, featlen, mean = read_gauden(os.path.join(src, "means"))
+    _, _, _, _, var = read_gauden(os.path.join(src, "variances"))
+    L = featlen[0]
+    mean = mean.reshape(n_mgau, n_feat, nd, L)
+    var = var.reshape(n_mgau, n_feat, nd, L)
+    pc = rs.randint(0, n_mgau, (n_sen, n_density, n_feat))
+    pd = rs.randint(0, nd, (n_sen, n_density, n_feat))
+    fi = np.arange(n_feat)
+    mu = mean[pc, fi, pd].reshape(n_sen, 1, n_density, n_feat * L)
+    vv = var[pc, fi, pd].reshape(n_sen, 1, n_density, n_feat * L)
+    write_gauden(os.path.join(dst, "means"), mu, [n_feat * L])
+    write_gauden(os.path.join(dst, "variances"), vv, [n_feat * L])
+    w = rs.gamma(0.7, 1.0, (n_sen, 1, n_density)).astype(np.float32)
+    w[rs.uniform(size=w.shape) < 0.05] = 0.0
+    words = np.concatenate([np.array([n_sen, 1, n_density, w.size], "<i4").view("<u4"),
+                            w.astype("<f4").view("<u4").ravel()])
+    with open(os.path.join(dst, "mixture_weights"), "wb") as fh:
+        fh.write(b"s3\nversion 1.0\nchksum0 yes\nendhdr\n" + struct.pack("<I", 0x11223344))
+        fh.write(words.tobytes())
+        fh.write(struct.pack("<I", _s3_checksum(words)))
+    with open(os.path.join(src, "feat_params.json")) as fh:
+        fp = json.load(fh)
+    fp.pop("svspec", None)
+    with open(os.path.join(dst, "feat_params.json"), "w") as fh:
+        json.dump(fp, fh)
+    for name in ("mdef", "transition_matrices", "noisedict.txt", "dict.txt", "phoneset.json"):
+        s = os.path.join(src, name)
+        if os.path.exists(s) and not os.path.exists(os.path.join(dst, name)):
+            os.symlink(os.path.abspath(s), os.path.join(dst, name))
+    return dict(n_sen=n_sen, n_density=n_density)
+
+
+CONT_CASES = [  # (tag, write_cont_model keywords)
+    ("cont8", dict(n_density=8, seed=9)),
+    ("cont3", dict(n_density=3, seed=10)),   # fewer densities than topn: the unsorted "all" list
+]

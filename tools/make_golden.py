@@ -274,6 +274,48 @@ def semi(lang="en-us"):
     np.savez_compressed(os.path.join(OUT, "semi_%s.npz" % lang), **g)
 
 
+def cont(lang="en-us"):
+    """Fully continuous (ms_mgau) scoring and alignment through the reference on the synthetic
+    one-codebook-per-senone models of tests/model_variants.py -> cont_<lang>.npz."""
+    import tempfile
+    import model_variants as mv
+    src = os.path.join(MODELS, lang)
+    ga = np.load(os.path.join(OUT, "align_%s.npz" % lang))
+    feat, words = ga["feat"], ga["words"]
+    g = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for tag, kw in mv.CONT_CASES:
+            d = os.path.join(tmp, tag)
+            mv.write_cont_model(src, d, int(ga["dims"][4]), **kw)
+            ref = Ref(d)
+            refc = Ref(d, compallsen=True)
+            assert ref.n_mgau == ref.n_sen
+            arrays = ref.model_arrays()
+            g[tag + "_mixw_sha"] = sha(arrays["mixw"])
+            g[tag + "_det_sha"] = sha(arrays["det"])
+            dense = refc.score_all(feat)
+            g[tag + "_senscr_sha"] = sha(dense)
+            g[tag + "_senscr_rows"] = dense[[0, 1, 100, len(feat) - 1]]
+            chain_sen = arrays["sseq"][ga["phones"][:, 1]].reshape(-1)
+            for name, r, k2 in (("win", ref, dict(start=words[:, 1], dur=words[:, 2])),
+                                ("nowin", ref, dict()),
+                                ("win_call", refc, dict(start=words[:, 1], dur=words[:, 2]))):
+                res = r.state_align(feat, words[:, 0], clear_active=True, want_tokens=True,
+                                    want_senscr=True, **k2)
+                key = "%s_%s_" % (tag, name)
+                g[key + "rv"] = np.int32(res["rv"])
+                g[key + "best"] = np.int32(res["best_score"])
+                g[key + "states"] = res["states"]
+                g[key + "tokens_sha"] = sha(res["tokens"])
+                g[key + "tokens"] = res["tokens"]
+                if name == "win_call":   # (with active lists the reference's buffer keeps stale
+                    g[key + "chain_scr"] = res["senscr"][:, chain_sen]   # values of other senones)
+            ref.close()
+            refc.close()
+            print("cont", tag, dense.shape, int(dense.min()), int(dense.max()))
+    np.savez_compressed(os.path.join(OUT, "cont_%s.npz" % lang), **g)
+
+
 def main():
     if not available():
         raise SystemExit("oracle/_ref/libssref.so missing: run `make -C oracle ref` first")
@@ -284,6 +326,8 @@ def main():
         return frontend()
     if "--semi" in sys.argv:
         return semi()
+    if "--cont" in sys.argv:
+        return cont()
     utterance("en-us", "goforward.raw", "go forward ten meters")
     utterance("fr-fr", "goforward_fr.raw", "avance de dix mètres")
     synthetic("en-us")
@@ -292,6 +336,7 @@ def main():
     loaders()
     frontend()
     semi()
+    cont()
 
 
 if __name__ == "__main__":
