@@ -263,6 +263,28 @@ int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out_t *out);
 int ssb_hmm_vit_eval(ssb_model_t *m, int32_t n_emit, int32_t tmatid, const uint16_t *senid,
                      const int16_t *senscr, int32_t *st12, int32_t *best);
 
+/* ------------------------------------------------------------------ lexicon (host only)
+ * Graph preparation for the chain aligner: pronunciation dictionary + context-dependent phone
+ * lookup + the word -> phone-chain expansion.  Word ids are the reference's (main dictionary
+ * in file order, then the filler dictionary, then <s> </s> <sil> when missing). */
+typedef struct ssb_lexicon_s ssb_lexicon_t;
+/* replaces dict_init (ref: src/dict.c:134-366) + dict2pid_build (ref: src/dict2pid.c:372-480);
+ * either path may be NULL.  The model is borrowed. */
+ssb_lexicon_t *ssb_lexicon_load(const ssb_model_t *m, const char *dictfile, const char *fdictfile);
+void ssb_lexicon_free(ssb_lexicon_t *lx);
+int32_t ssb_lexicon_size(const ssb_lexicon_t *lx);
+int32_t ssb_lexicon_wordid(const ssb_lexicon_t *lx, const char *word);   /* dict_wordid; -1 */
+const char *ssb_lexicon_wordstr(const ssb_lexicon_t *lx, int32_t wid);
+/* CI phones of a word; returns the pronunciation length */
+int32_t ssb_lexicon_pron(const ssb_lexicon_t *lx, int32_t wid, int32_t *ciphones, int32_t max);
+int32_t ssb_lexicon_is_filler(const ssb_lexicon_t *lx, int32_t wid);     /* dict_filler_word */
+/* replaces alignment_populate (ref: src/ps_alignment.c:133-248): per phone of the word
+ * sequence its senone-sequence id, transition matrix, CI phone and parent word index (any
+ * output may be NULL).  Returns the number of phones, -1 on error. */
+int32_t ssb_chain_populate(const ssb_lexicon_t *lx, const int32_t *wids, int32_t n_words,
+                           int32_t *ssid, int32_t *tmat, int32_t *cipid, int32_t *parent,
+                           int32_t max_phones);
+
 /* ------------------------------------------------------------------ frontend
  * Batched PCM -> MFCC -> CMN -> dynamic features for whole utterances: what
  * acmod_process_raw(full_utt=TRUE) obtains from fe_start / fe_process_int16 |

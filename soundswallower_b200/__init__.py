@@ -25,7 +25,7 @@ MODEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "model")
 
 __all__ = ["AcousticModel", "PtmMgau", "StateAlignBatch", "align_batch", "score_batch",
            "topn_batch", "tc_probe", "fsg_batch", "hmm_vit_eval", "windows", "plan_chain", "propagate", "flags2list", "device_count",
-           "Frontend", "DeviceFeatures", "SsbError", "Config", "MODEL_DIR", "INT_MAX", "WORST_SCORE"]
+           "Frontend", "DeviceFeatures", "Lexicon", "SsbError", "Config", "MODEL_DIR", "INT_MAX", "WORST_SCORE"]
 
 
 def _ptr(a, t=None):
@@ -647,3 +647,70 @@ class Frontend:
         _lib.check(self.lib.ssb_frontend_kernel_ms(self.h, _ptr(ms)), "ssb_frontend_kernel_ms")
         return dict(melspec=float(ms[0]), noise=float(ms[1]), cepstrum=float(ms[2]),
                     cmn=float(ms[3]), feat=float(ms[4]), total=float(ms[5]))
+
+
+# ---------------------------------------------------------------------------- lexicon
+class Lexicon:
+    """dict_t + dict2pid_t of the reference (ref: src/dict.c, src/dict2pid.c): word ids,
+    pronunciations and the word -> phone-chain expansion of alignment_populate
+    (ref: src/ps_alignment.c:133-248).  Host only.  Defaults to the model directory's
+    dict.txt / noisedict.txt like `decoder_init` expands them (ref: src/decoder.c:122-123)."""
+
+    def __init__(self, model, dictfile=None, fdictfile=None, hmmdir=None):
+        self.model = model
+        self.lib = model.lib
+        if hmmdir is not None:
+            dictfile = dictfile or os.path.join(hmmdir, "dict.txt")
+            fd = os.path.join(hmmdir, "noisedict.txt")
+            fdictfile = fdictfile or (fd if os.path.exists(fd) else None)
+        h = self.lib.ssb_lexicon_load(model.h, os.fsencode(dictfile) if dictfile else None,
+                                      os.fsencode(fdictfile) if fdictfile else None)
+        if not h:
+            raise SsbError("ssb_lexicon_load: " + _lib.last_error())
+        self.h = C.c_void_p(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ssb_lexicon_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(self.lib.ssb_lexicon_size(self.h))
+
+    def wordid(self, word):
+        return int(self.lib.ssb_lexicon_wordid(self.h, word.encode("utf-8")))
+
+    def wordstr(self, wid):
+        s = self.lib.ssb_lexicon_wordstr(self.h, int(wid))
+        return s.decode("utf-8") if s is not None else None
+
+    def pron(self, wid):
+        out = np.zeros(64, np.int32)
+        n = int(self.lib.ssb_lexicon_pron(self.h, int(wid), _ptr(out), 64))
+        return out[:n]
+
+    def is_filler(self, wid):
+        return bool(self.lib.ssb_lexicon_is_filler(self.h, int(wid)))
+
+    def populate(self, wids, start=None, dur=None):
+        """Phone chain of a word sequence: dict(ssid, tmat, ci, parent[, sf, ef]) -- with
+        word windows (start, dur) the sf/ef arrays state_align_search_init derives."""
+        wids = np.ascontiguousarray(wids, np.int32)
+        n = int(self.lib.ssb_chain_populate(self.h, _ptr(wids), len(wids), None, None, None, None, 0))
+        _lib.check(n, "ssb_chain_populate")
+        ssid, tmat, ci, parent = (np.zeros(n, np.int32) for _ in range(4))
+        _lib.check(int(self.lib.ssb_chain_populate(self.h, _ptr(wids), len(wids), _ptr(ssid), _ptr(tmat),
+                                                   _ptr(ci), _ptr(parent), n)), "ssb_chain_populate")
+        out = dict(ssid=ssid, tmat=tmat, ci=ci, parent=parent)
+        if start is not None:
+            start, dur = np.asarray(start, np.int32), np.asarray(dur, np.int32)
+            out["sf"], out["ef"] = windows(start[parent], dur[parent])
+        else:
+            out["sf"], out["ef"] = windows(np.zeros(n, np.int32), np.zeros(n, np.int32))
+        return out

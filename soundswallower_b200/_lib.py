@@ -96,6 +96,8 @@ SYMBOLS = [
     "ssb_frontend_free", "ssb_frontend_dims", "ssb_frontend_n_frames", "ssb_frontend_tables",
     "ssb_frontend_run", "ssb_frontend_download", "ssb_frontend_feat_device",
     "ssb_frontend_kernel_ms",
+    "ssb_lexicon_load", "ssb_lexicon_free", "ssb_lexicon_size", "ssb_lexicon_wordid",
+    "ssb_lexicon_wordstr", "ssb_lexicon_pron", "ssb_lexicon_is_filler", "ssb_chain_populate",
 ]
 
 _lib = None
@@ -154,6 +156,17 @@ def load():
     L.ssb_fsg_batch.argtypes = [vp, P(FsgIn), P(FsgOut)]
     L.ssb_hmm_vit_eval.argtypes = [vp, i32, i32, vp, vp, vp, P(i32)]
     L.ssb_model_kind.argtypes = [vp]
+    L.ssb_lexicon_load.restype = vp
+    L.ssb_lexicon_load.argtypes = [vp, C.c_char_p, C.c_char_p]
+    L.ssb_lexicon_free.restype = None
+    L.ssb_lexicon_free.argtypes = [vp]
+    L.ssb_lexicon_size.argtypes = [vp]
+    L.ssb_lexicon_wordid.argtypes = [vp, C.c_char_p]
+    L.ssb_lexicon_wordstr.restype = C.c_char_p
+    L.ssb_lexicon_wordstr.argtypes = [vp, i32]
+    L.ssb_lexicon_pron.argtypes = [vp, i32, vp, i32]
+    L.ssb_lexicon_is_filler.argtypes = [vp, i32]
+    L.ssb_chain_populate.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32]
     L.ssb_fe_config_defaults.restype = None
     L.ssb_fe_config_defaults.argtypes = [P(FeConfig)]
     L.ssb_fe_config_from_model.argtypes = [C.c_char_p, P(FeConfig)]

@@ -63,6 +63,9 @@ struct ssb_model_s {
     int sm_count = 0;
 };
 
+namespace ssb {
+const HostModel *model_host(const ssb_model_t *m) { return m ? &m->h : nullptr; }  // lexicon.cpp
+}
 extern "C" int ssb_version(void) { return 100; }
 extern "C" int ssb_model_kind(const ssb_model_t *m)
 {

@@ -278,7 +278,22 @@ static bool read_mdef(HostModel &m, const std::string &path)
         p = e + 1;
     }
     p = names + (((p - names) + 3) & ~(size_t)3);
-    p += (size_t)n_cd_tree * 8;  // cd_tree_t {int16,int16,int32}: graph-prep only
+    if (f.bytes.size() < p + (size_t)n_cd_tree * 8)
+        return false;
+    m.cd_tree.resize(n_cd_tree);  // cd_tree_t {int16 ctx, int16 n_down, int32 pid|down}
+    for (int i = 0; i < n_cd_tree; ++i, p += 8) {
+        uint16_t a, b;
+        uint32_t c;
+        std::memcpy(&a, &f.bytes[p], 2);
+        std::memcpy(&b, &f.bytes[p + 2], 2);
+        std::memcpy(&c, &f.bytes[p + 4], 4);
+        if (f.swapped) {
+            a = (uint16_t)((a >> 8) | (a << 8));
+            b = (uint16_t)((b >> 8) | (b << 8));
+            c = Blob::flip(c);
+        }
+        m.cd_tree[i] = {(int16_t)a, (int16_t)b, (int32_t)c};
+    }
     if (f.bytes.size() < p + (size_t)m.n_phone * 12 + 4) {
         set_error("%s: truncated phone table", path.c_str());
         return false;
@@ -294,6 +309,8 @@ static bool read_mdef(HostModel &m, const std::string &path)
         m.ph_tmat[i] = (int32_t)(f.swapped ? Blob::flip(b) : b);
         // info bytes: CI entries {reserved, filler}; CD entries {wpos, base ci, lc, rc}
         m.ph_ci[i] = i < m.n_ciphone ? i : f.bytes[p + 9];
+        if (i < m.n_ciphone)
+            m.ci_filler.push_back(f.bytes[p + 8]);
     }
     f.at = p;
     int32_t sseq_size;

@@ -44,6 +44,14 @@ struct HostModel {
     std::vector<uint16_t> sseq;          // [n_sseq][n_emit]
     std::vector<int32_t> ph_ssid, ph_tmat, ph_ci;
     std::vector<std::string> ciname;
+    // triphone lookup (graph preparation, lexicon.cpp): the mdef's context tree
+    // {ctx, n_down, pid | down} and the filler flag of every CI phone (ref: bin_mdef.h:92-125)
+    struct CdNode {
+        int16_t ctx, n_down;
+        int32_t c;
+    };
+    std::vector<CdNode> cd_tree;
+    std::vector<uint8_t> ci_filler;
     // transitions
     int32_t n_tmat = 0;
     std::vector<uint8_t> tp;             // [n_tmat][n_emit][n_emit+1]

@@ -1,0 +1,90 @@
+"""Host-side graph preparation (first half): dictionary, triphone lookup and
+alignment_populate.  tests/golden/lexicon.npz holds word ids and phone chains the compiled
+reference produced (tools/make_golden.py --lexicon)."""
+import os
+
+import numpy as np
+import pytest
+
+import soundswallower_b200 as ssb
+from conftest import GOLDEN, chain_from_golden, model_dir
+
+
+@pytest.fixture(scope="module")
+def lex_golden():
+    return np.load(os.path.join(GOLDEN, "lexicon.npz"))
+
+
+@pytest.fixture(scope="module")
+def lexicons():
+    out = {}
+    for lang in ("en-us", "fr-fr"):
+        m = ssb.AcousticModel(model_dir(lang), device=-1)
+        out[lang] = (m, ssb.Lexicon(m, hmmdir=model_dir(lang)))
+    return out
+
+
+@pytest.mark.parametrize("lang", ["en-us", "fr-fr"])
+def test_word_ids_match_reference(lex_golden, lexicons, lang):
+    _, lx = lexicons[lang]
+    assert len(lx) == int(lex_golden[lang + "_size"])
+    for wid, s in zip(lex_golden[lang + "_probe_wid"], lex_golden[lang + "_probe_str"]):
+        assert lx.wordstr(int(wid)) == str(s) and lx.wordid(str(s)) == int(wid)
+    assert lx.wordid("no such word") == -1 and lx.wordstr(len(lx)) is None
+    assert lx.is_filler(lx.wordid("<sil>")) and not lx.is_filler(lx.wordid("<s>"))
+    assert not lx.is_filler(0)
+
+
+@pytest.mark.parametrize("lang", ["en-us", "fr-fr"])
+def test_populate_matches_reference(lex_golden, lexicons, lang):
+    _, lx = lexicons[lang]
+    off, wids, ph = lex_golden[lang + "_wid_off"], lex_golden[lang + "_wids"], lex_golden[lang + "_phones"]
+    p0 = 0
+    for i, n in enumerate(lex_golden[lang + "_n_phones"]):
+        c = lx.populate(wids[off[i]:off[i + 1]])
+        want = ph[p0:p0 + n]
+        p0 += n
+        assert len(c["ssid"]) == n
+        assert np.array_equal(c["ci"], want[:, 0]) and np.array_equal(c["ssid"], want[:, 1])
+        assert np.array_equal(c["tmat"], want[:, 2]) and np.array_equal(c["parent"], want[:, 3])
+
+
+@pytest.mark.parametrize("lang,text", [("en-us", "go forward ten meters"),
+                                       ("fr-fr", "avance de dix mètres")])
+def test_text_to_chain_equals_the_golden_alignment_chain(lexicons, golden, lang, text):
+    """<sil> words </sil> as decoder_alignment receives them: the chain equals the one the
+    reference's CLI aligned (tests/golden/align_*.npz), windows included."""
+    _, lx = lexicons[lang]
+    g = golden[lang]
+    wids = g["words"][:, 0]
+    # (pass 1 may have chosen alternate pronunciations: "de(2)", "mètres(4)")
+    assert [lx.wordstr(int(w)).split("(")[0] for w in wids] == ["<sil>"] + text.split() + ["<sil>"]
+    c = lx.populate(wids, g["words"][:, 1], g["words"][:, 2])
+    want = chain_from_golden(g)
+    for k in ("ssid", "tmat", "sf", "ef"):
+        assert np.array_equal(c[k], want[k]), k
+
+
+def test_populate_errors(lexicons):
+    _, lx = lexicons["en-us"]
+    with pytest.raises(ssb.SsbError):
+        lx.populate([len(lx) + 5])
+    assert len(lx.populate([])["ssid"]) == 0
+    m = lexicons["en-us"][0]
+    with pytest.raises(ssb.SsbError):
+        ssb.Lexicon(m, dictfile="/nonexistent/dict.txt")
+
+
+def test_reference_agrees_when_present(lexicons):
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("oracle/_ref/libssref.so not built here")
+    rs = np.random.RandomState(5)
+    for lang in ("en-us", "fr-fr"):
+        _, lx = lexicons[lang]
+        r = refshim.Ref(model_dir(lang))
+        for _ in range(150):
+            wids = rs.randint(0, len(lx), rs.randint(1, 20)).astype(np.int32)
+            a, b = r.populate(wids)["phones"], lx.populate(wids)
+            assert np.array_equal(a[:, 1], b["ssid"]) and np.array_equal(a[:, 2], b["tmat"])
+        r.close()

@@ -316,6 +316,35 @@ def cont(lang="en-us"):
     np.savez_compressed(os.path.join(OUT, "cont_%s.npz" % lang), **g)
 
 
+def lexicon():
+    """Word ids and alignment_populate phone chains of the reference for seeded random word
+    sequences (both bundled dictionaries) -> lexicon.npz."""
+    g = {}
+    for lang in ("en-us", "fr-fr"):
+        ref = Ref(os.path.join(MODELS, lang))
+        rs = np.random.RandomState(77)
+        n = ref.wordid("<sil>") + 1
+        while ref.wordstr(n) is not None:
+            n += 1
+        g[lang + "_size"] = np.int32(n)
+        probe = np.unique(np.concatenate([rs.randint(0, n, 48), np.arange(n - 8, n)])).astype(np.int32)
+        g[lang + "_probe_wid"] = probe
+        g[lang + "_probe_str"] = np.array([ref.wordstr(int(w)) for w in probe])
+        seqs, off, ph = [], [0], []
+        for _ in range(200):
+            wids = rs.randint(0, n, rs.randint(1, 14)).astype(np.int32)
+            seqs.append(wids)
+            off.append(off[-1] + len(wids))
+            ph.append(ref.populate(wids)["phones"][:, [0, 1, 2, 6]])
+        g[lang + "_wids"] = np.concatenate(seqs)
+        g[lang + "_wid_off"] = np.array(off, np.int32)
+        g[lang + "_phones"] = np.concatenate(ph).astype(np.int32)   # ci ssid tmat parent
+        g[lang + "_n_phones"] = np.array([len(p) for p in ph], np.int32)
+        ref.close()
+        print("lexicon", lang, n, len(g[lang + "_phones"]))
+    np.savez_compressed(os.path.join(OUT, "lexicon.npz"), **g)
+
+
 def main():
     if not available():
         raise SystemExit("oracle/_ref/libssref.so missing: run `make -C oracle ref` first")
@@ -328,6 +357,8 @@ def main():
         return semi()
     if "--cont" in sys.argv:
         return cont()
+    if "--lexicon" in sys.argv:
+        return lexicon()
     utterance("en-us", "goforward.raw", "go forward ten meters")
     utterance("fr-fr", "goforward_fr.raw", "avance de dix mètres")
     synthetic("en-us")
@@ -337,6 +368,7 @@ def main():
     frontend()
     semi()
     cont()
+    lexicon()
 
 
 if __name__ == "__main__":
