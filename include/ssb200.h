@@ -72,6 +72,8 @@ enum { SSB_SCORER_PTM = 0, SSB_SCORER_SEMI = 1, SSB_SCORER_CONT = 2 };
 typedef struct ssb_model_s ssb_model_t;
 ssb_model_t *ssb_model_load(const char *hmmdir, const ssb_config_t *cfg);
 int ssb_model_kind(const ssb_model_t *m);
+/* bin_mdef_ciphone_str (ref: src/bin_mdef.c:590-595); NULL when out of range */
+const char *ssb_model_ciphone_str(const ssb_model_t *m, int32_t ci);
 void ssb_model_free(ssb_model_t *m);
 /* out[0..10] = n_mgau n_feat n_density veclen(stream 0) n_sen n_sseq n_emit n_tmat
  *              n_ciphone n_phone sil ; out[11..14] = featlen[0..3] ; out[15] = sum featlen */
@@ -284,6 +286,30 @@ int32_t ssb_lexicon_is_filler(const ssb_lexicon_t *lx, int32_t wid);     /* dict
 int32_t ssb_chain_populate(const ssb_lexicon_t *lx, const int32_t *wids, int32_t n_words,
                            int32_t *ssid, int32_t *tmat, int32_t *cipid, int32_t *parent,
                            int32_t max_phones);
+
+/* Alignment grammar + lextree on the host: what decoder_set_align_text builds
+ * (ref: src/decoder.c:685-735: one state per word boundary, one link per word), augmented as
+ * fsg_search_init does (silence / filler self-loops on every state, alternate pronunciations;
+ * ref: src/fsg_search.c:83-168, 171-260) and expanded by fsg_lextree_init
+ * (ref: src/fsg_lextree.c:226-716), flattened to ssb_fsg_graph_t with the reference's link
+ * and node order. */
+typedef struct ssb_fsg_config_s {
+    double beam, pbeam, wbeam;        /* "beam" 1e-48, "pbeam" 1e-48, "wbeam" 7e-29 */
+    float lw, wip, pip;               /* "lw" 6.5, "wip" 0.65, "pip" 1.0 */
+    float silprob, fillprob;          /* "silprob" 0.005, "fillprob" 1e-8 */
+    int32_t maxhmmpf;                 /* "maxhmmpf" 30000 */
+    int32_t fsgusefiller, fsgusealtpron; /* yes, yes */
+} ssb_fsg_config_t;
+void ssb_fsg_config_defaults(ssb_fsg_config_t *c);
+typedef struct ssb_fsg_built_s ssb_fsg_built_t;
+/* NULL with "Unknown word ..." when a word of `text` is not in the dictionary */
+ssb_fsg_built_t *ssb_fsg_build_align(const ssb_lexicon_t *lx, const char *text,
+                                     const ssb_fsg_config_t *cfg);
+/* the graph (arrays owned by the object) and its vocabulary: link4[.][3] indexes these words */
+const ssb_fsg_graph_t *ssb_fsg_built_graph(const ssb_fsg_built_t *b);
+int32_t ssb_fsg_built_n_words(const ssb_fsg_built_t *b);
+const char *ssb_fsg_built_word(const ssb_fsg_built_t *b, int32_t fsg_wid, int32_t *dict_wid);
+void ssb_fsg_built_free(ssb_fsg_built_t *b);
 
 /* ------------------------------------------------------------------ frontend
  * Batched PCM -> MFCC -> CMN -> dynamic features for whole utterances: what

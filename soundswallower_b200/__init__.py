@@ -25,7 +25,7 @@ MODEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "model")
 
 __all__ = ["AcousticModel", "PtmMgau", "StateAlignBatch", "align_batch", "score_batch",
            "topn_batch", "tc_probe", "fsg_batch", "hmm_vit_eval", "windows", "plan_chain", "propagate", "flags2list", "device_count",
-           "Frontend", "DeviceFeatures", "Lexicon", "SsbError", "Config", "MODEL_DIR", "INT_MAX", "WORST_SCORE"]
+           "Frontend", "DeviceFeatures", "Lexicon", "align_texts", "SsbError", "Config", "MODEL_DIR", "INT_MAX", "WORST_SCORE"]
 
 
 def _ptr(a, t=None):
@@ -106,6 +106,10 @@ class AcousticModel:
             self._arrays = dict(mean=mean, var=var, det=det, mixw=mixw, sen2cb=sen2cb, tp=tp,
                                 sseq=sseq, lut=lut)
         return self._arrays
+
+    def ciname(self, ci):
+        s = self.lib.ssb_model_ciphone_str(self.h, int(ci))
+        return s.decode("utf-8") if s is not None else None
 
     def phone_table(self):
         ssid = np.zeros(self.n_phone, np.int32)
@@ -714,3 +718,106 @@ class Lexicon:
         else:
             out["sf"], out["ef"] = windows(np.zeros(n, np.int32), np.zeros(n, np.int32))
         return out
+
+
+def _lexicon_align_graph(self, text, **cfg):
+    """decoder_set_align_text + fsg_search_init + fsg_lextree_init (ref: src/decoder.c:685-735,
+    src/fsg_search.c:171-260, src/fsg_lextree.c:226-716): the flattened alignment grammar of
+    `text` in the form fsg_batch takes, plus `words` (the grammar's vocabulary: link[:, 3]
+    indexes it) and `dict_wid`."""
+    c = _lib.FsgConfig()
+    self.lib.ssb_fsg_config_defaults(C.byref(c))
+    for k, v in cfg.items():
+        if not hasattr(c, k):
+            raise SsbError("unknown search parameter " + k)
+        setattr(c, k, v)
+    b = self.lib.ssb_fsg_build_align(self.h, text.encode("utf-8"), C.byref(c))
+    if not b:
+        raise SsbError("ssb_fsg_build_align: " + _lib.last_error())
+    b = C.c_void_p(b)
+    try:
+        g = self.lib.ssb_fsg_built_graph(b).contents
+
+        def arr(ptr, shape, dt):
+            n = int(np.prod(shape))
+            if n == 0:
+                return np.zeros(shape, dt)
+            buf = (C.c_char * (n * np.dtype(dt).itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dt).reshape(shape).copy()
+        out = dict(n_state=g.n_state, start=g.start, final=g.final, n_ciphone=g.n_ciphone, sil=g.sil,
+                   beam=g.beam, pbeam=g.pbeam, wbeam=g.wbeam, maxhmmpf=g.maxhmmpf,
+                   link=arr(g.link4, (g.n_link, 4), np.int32),
+                   link_flag=arr(g.link_flag, (g.n_link,), np.uint8),
+                   arc_off=arr(g.arc_off, (g.n_state + 1,), np.int32),
+                   root=arr(g.root, (g.n_state,), np.int32),
+                   pnode=arr(g.pnode8, (g.n_pnode, 8), np.int32),
+                   ctxt=arr(g.ctxt, (g.n_pnode, 4), np.uint32))
+        words, dwids = [], []
+        for i in range(int(self.lib.ssb_fsg_built_n_words(b))):
+            dw = C.c_int32(-1)
+            words.append(self.lib.ssb_fsg_built_word(b, i, C.byref(dw)).decode("utf-8"))
+            dwids.append(dw.value)
+        out["words"], out["dict_wid"] = words, np.array(dwids, np.int32)
+        return out
+    finally:
+        self.lib.ssb_fsg_built_free(b)
+
+
+Lexicon.align_graph = _lexicon_align_graph
+
+
+# ---------------------------------------------------------------------------- two-pass alignment
+def align_texts(model, lexicon, feats, texts, **search_cfg):
+    """The reference's forced alignment of `soundswallower --align` for a batch of
+    (utterance, transcript) pairs, both passes on the GPU:
+
+      pass 1  decoder_set_align_text + search_module_forward (ref: src/decoder.c:685-735,
+              935-957): grammar search of the transcript -> word segmentation;
+      pass 2  decoder_alignment (ref: src/decoder.c:737-798): the words of pass 1 with their
+              frame windows -> alignment_populate -> state_align_search -> backtrace ->
+              alignment_propagate.
+
+    feats: list of feature arrays, or DeviceFeatures from Frontend.run (audio never leaves the
+    GPU).  Returns per utterance None when the transcript does not match the audio (pass 1
+    has no final exit), else dict(words=[(word, start, dur, score)], phones=[(phone, start,
+    dur, score, word index)], states=int32 [n][5] (senone, start, dur, score, phone index),
+    hyp_score)."""
+    graphs = [lexicon.align_graph(t, **search_cfg) for t in texts]
+    p1 = fsg_batch(model, feats, graphs, utt_graph=np.arange(len(texts), dtype=np.int32))
+    chains, metas = [], []
+    for g, r in zip(graphs, p1):
+        if r["rv"] != 0 or r["exit"] <= 0:
+            chains.append(dict(ssid=np.zeros(0, np.int32), tmat=np.zeros(0, np.int32),
+                               sf=np.zeros(0, np.int32), ef=np.zeros(0, np.int32)))
+            metas.append(None)
+            continue
+        segs = r["segs"]
+        fw = g["link"][segs[:, 0], 3]
+        keep = fw >= 0                      # null transitions carry no word
+        wids = g["dict_wid"][fw[keep]]
+        start, dur = segs[keep, 1], segs[keep, 2] - segs[keep, 1] + 1
+        c = lexicon.populate(wids, start, dur)
+        chains.append(c)
+        metas.append((wids, start, dur, c, int(r["hyp_score"])))
+    p2 = align_batch(model, feats, chains)
+    arrays = model.arrays()
+    E = model.n_emit
+    out = []
+    for meta, r in zip(metas, p2):
+        if meta is None or r["rv"] != 0:
+            out.append(None)
+            continue
+        wids, wstart, wdur, c, hyp = meta
+        ps, pd, pc = propagate(r["start"], r["dur"], r["score"], E)
+        parent = c["parent"]
+        words = []
+        for i, w in enumerate(wids):   # alignment_propagate, phones -> words
+            sel = parent == i
+            words.append((lexicon.wordstr(int(w)), int(ps[sel][0]), int(pd[sel].sum()), int(pc[sel].sum())))
+        phones = [(model.ciname(int(c["ci"][i])), int(ps[i]), int(pd[i]), int(pc[i]), int(parent[i]))
+                  for i in range(len(ps))]
+        sen = arrays["sseq"][c["ssid"]].reshape(-1).astype(np.int32)
+        states = np.stack([sen, r["start"], r["dur"], r["score"],
+                           np.repeat(np.arange(len(ps), dtype=np.int32), E)], 1).astype(np.int32)
+        out.append(dict(words=words, phones=phones, states=states, hyp_score=hyp))
+    return out

@@ -32,6 +32,15 @@ class FeConfig(C.Structure):
                [(k, C.c_float) for k in ("wlen", "alpha", "lowerf", "upperf")]
 
 
+class FsgConfig(C.Structure):
+    """ssb_fsg_config_t -- the search keys of the reference config
+    (ref: include/soundswallower/config_defs.h:79-159)."""
+    _fields_ = [("beam", C.c_double), ("pbeam", C.c_double), ("wbeam", C.c_double),
+                ("lw", C.c_float), ("wip", C.c_float), ("pip", C.c_float),
+                ("silprob", C.c_float), ("fillprob", C.c_float), ("maxhmmpf", C.c_int32),
+                ("fsgusefiller", C.c_int32), ("fsgusealtpron", C.c_int32)]
+
+
 class AlignIn(C.Structure):
     _fields_ = [("n_utts", C.c_int32), ("feat", C.POINTER(C.c_float)),
                 ("frame_off", C.POINTER(C.c_int64)), ("phone_off", C.POINTER(C.c_int64)),
@@ -86,7 +95,7 @@ class MgauBase(C.Structure):
 # every symbol include/ssb200.h declares
 SYMBOLS = [
     "ssb_version", "ssb_last_error", "ssb_device_count", "ssb_config_defaults",
-    "ssb_model_load", "ssb_model_kind", "ssb_model_free", "ssb_model_dims", "ssb_model_copy", "ssb_model_phones",
+    "ssb_model_load", "ssb_model_kind", "ssb_model_ciphone_str", "ssb_model_free", "ssb_model_dims", "ssb_model_copy", "ssb_model_phones",
     "ssb_mgau_init", "ssb_mgau_frame_eval", "ssb_mgau_reset", "ssb_mgau_free",
     "ssb_plan_chain", "ssb_batch_create", "ssb_batch_free", "ssb_batch_upload", "ssb_batch_run",
     "ssb_batch_download", "ssb_batch_debug_tokens", "ssb_batch_kernel_ms",
@@ -98,6 +107,8 @@ SYMBOLS = [
     "ssb_frontend_kernel_ms",
     "ssb_lexicon_load", "ssb_lexicon_free", "ssb_lexicon_size", "ssb_lexicon_wordid",
     "ssb_lexicon_wordstr", "ssb_lexicon_pron", "ssb_lexicon_is_filler", "ssb_chain_populate",
+    "ssb_fsg_config_defaults", "ssb_fsg_build_align", "ssb_fsg_built_graph",
+    "ssb_fsg_built_n_words", "ssb_fsg_built_word", "ssb_fsg_built_free",
 ]
 
 _lib = None
@@ -156,6 +167,8 @@ def load():
     L.ssb_fsg_batch.argtypes = [vp, P(FsgIn), P(FsgOut)]
     L.ssb_hmm_vit_eval.argtypes = [vp, i32, i32, vp, vp, vp, P(i32)]
     L.ssb_model_kind.argtypes = [vp]
+    L.ssb_model_ciphone_str.restype = C.c_char_p
+    L.ssb_model_ciphone_str.argtypes = [vp, i32]
     L.ssb_lexicon_load.restype = vp
     L.ssb_lexicon_load.argtypes = [vp, C.c_char_p, C.c_char_p]
     L.ssb_lexicon_free.restype = None
@@ -167,6 +180,17 @@ def load():
     L.ssb_lexicon_pron.argtypes = [vp, i32, vp, i32]
     L.ssb_lexicon_is_filler.argtypes = [vp, i32]
     L.ssb_chain_populate.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32]
+    L.ssb_fsg_config_defaults.restype = None
+    L.ssb_fsg_config_defaults.argtypes = [P(FsgConfig)]
+    L.ssb_fsg_build_align.restype = vp
+    L.ssb_fsg_build_align.argtypes = [vp, C.c_char_p, P(FsgConfig)]
+    L.ssb_fsg_built_graph.restype = P(FsgGraph)
+    L.ssb_fsg_built_graph.argtypes = [vp]
+    L.ssb_fsg_built_n_words.argtypes = [vp]
+    L.ssb_fsg_built_word.restype = C.c_char_p
+    L.ssb_fsg_built_word.argtypes = [vp, i32, P(i32)]
+    L.ssb_fsg_built_free.restype = None
+    L.ssb_fsg_built_free.argtypes = [vp]
     L.ssb_fe_config_defaults.restype = None
     L.ssb_fe_config_defaults.argtypes = [P(FeConfig)]
     L.ssb_fe_config_from_model.argtypes = [C.c_char_p, P(FeConfig)]

@@ -67,6 +67,12 @@ namespace ssb {
 const HostModel *model_host(const ssb_model_t *m) { return m ? &m->h : nullptr; }  // lexicon.cpp
 }
 extern "C" int ssb_version(void) { return 100; }
+extern "C" const char *ssb_model_ciphone_str(const ssb_model_t *m, int32_t ci)
+{
+    if (!m || ci < 0 || ci >= (int32_t)m->h.ciname.size())
+        return nullptr;
+    return m->h.ciname[ci].c_str();
+}
 extern "C" int ssb_model_kind(const ssb_model_t *m)
 {
     if (!m) {

@@ -401,3 +401,509 @@ extern "C" int32_t ssb_chain_populate(const ssb_lexicon_t *lx, const int32_t *wi
     }
     return n;
 }
+
+// ====================================================================== grammar graphs
+// The alignment grammar of decoder_set_align_text (ref: src/decoder.c:685-735), augmented as
+// fsg_search_init does (silence / filler self-loops on every state, alternate pronunciations;
+// ref: src/fsg_search.c:83-168, src/fsg_model.c:359-449), and its lextree
+// (ref: src/fsg_lextree.c:83-716), flattened to the arrays ssb_fsg_graph_t takes.
+//
+// Link order and node order are part of the search's tie-breaking, so they are reproduced:
+// the reference keeps the arcs of a state in a 101-bucket hash table keyed by destination
+// state (binary key spelt as two letters per byte, ref: src/hash_table.c:171-223), every
+// bucket chain grows behind its head, every (from, to) list grows at the front; lextree nodes
+// are numbered state by state, newest first (the alloc_head lists).
+namespace {
+
+struct FLink {
+    int32_t from, to, logp, wid;
+};
+
+struct ArcTable {  // the hash table of one state: to_state -> list of links (front = newest)
+    struct Ent {
+        int32_t to;
+        std::vector<int> links;  // indices into the link pool, front = most recently added
+    };
+    std::vector<std::vector<Ent>> bucket;
+    ArcTable() : bucket(101) {}
+    static unsigned hash(int32_t to)
+    {
+        unsigned char b[4];
+        std::memcpy(b, &to, 4);
+        unsigned h = 0;
+        int s = 0;
+        for (int i = 0; i < 4; ++i)
+            for (int half = 0; half < 2; ++half) {
+                const unsigned char c = half == 0 ? (unsigned char)('A' + (b[i] & 15))
+                                                  : (unsigned char)('J' + (b[i] >> 4));
+                h += (unsigned)c << s;
+                s += 5;
+                if (s >= 25)
+                    s -= 24;
+            }
+        return h % 101u;
+    }
+    Ent *find(int32_t to)
+    {
+        for (Ent &e : bucket[hash(to)])
+            if (e.to == to)
+                return &e;
+        return nullptr;
+    }
+    Ent *enter(int32_t to)
+    {
+        std::vector<Ent> &bk = bucket[hash(to)];
+        Ent e{to, {}};
+        if (bk.empty()) {
+            bk.push_back(e);
+            return &bk[0];
+        }
+        bk.insert(bk.begin() + 1, e);  // behind the head, in front of older collisions
+        return &bk[1];
+    }
+};
+
+struct PNode {
+    int32_t ssid, tmat, logs2prob, ci_ext, leaf, next, sibling, ppos;
+    uint32_t ctxt[4];
+};
+
+struct FsgWork {
+    const ssb_lexicon_s *lx;
+    ssb_fsg_config_t cfg;
+    int n_state = 0;
+    std::vector<std::string> vocab;
+    std::vector<uint8_t> silword, altword;
+    std::vector<FLink> pool;
+    std::vector<ArcTable> trans;
+
+    int word_add(const std::string &w)
+    {
+        for (size_t i = 0; i < vocab.size(); ++i)
+            if (vocab[i] == w)
+                return (int)i;
+        vocab.push_back(w);
+        silword.push_back(0);
+        altword.push_back(0);
+        return (int)vocab.size() - 1;
+    }
+    // ref: src/fsg_model.c:62-95
+    void trans_add(int from, int to, int logp, int wid)
+    {
+        ArcTable::Ent *e = trans[from].find(to);
+        if (e)
+            for (int li : e->links)
+                if (pool[li].wid == wid) {
+                    if (pool[li].logp < logp)
+                        pool[li].logp = logp;
+                    return;
+                }
+        if (!e)
+            e = trans[from].enter(to);
+        pool.push_back({from, to, logp, wid});
+        e->links.insert(e->links.begin(), (int)pool.size() - 1);
+    }
+    // ref: src/fsg_model.c:359-386
+    void add_silence(const std::string &w, float prob)
+    {
+        LogMath lm(lx->h->cfg.logbase);
+        const int wid = word_add(w);
+        const int logp = (int32_t)((float)lm.log((double)prob, 0) * cfg.lw);
+        silword[wid] = 1;
+        for (int s = 0; s < n_state; ++s)
+            trans_add(s, s, logp, wid);
+    }
+    // ref: src/fsg_model.c:388-449
+    void add_alt(const std::string &base, const std::string &alt)
+    {
+        int basewid = -1;
+        for (size_t i = 0; i < vocab.size(); ++i)
+            if (vocab[i] == base) {
+                basewid = (int)i;
+                break;
+            }
+        if (basewid < 0)
+            return;
+        const int altwid = word_add(alt);
+        altword[altwid] = 1;
+        if (silword[basewid])
+            silword[altwid] = 1;
+        for (int s = 0; s < n_state; ++s)
+            for (auto &bk : trans[s].bucket)
+                for (ArcTable::Ent &e : bk) {
+                    const std::vector<int> old = e.links;  // the walk does not see its own additions
+                    for (int li : old)
+                        if (pool[li].wid == basewid) {
+                            pool.push_back({pool[li].from, pool[li].to, pool[li].logp, altwid});
+                            e.links.insert(e.links.begin(), (int)pool.size() - 1);
+                        }
+                }
+    }
+    // links of state s in fsg_model_arcs order (no null transitions in these grammars)
+    std::vector<int> arcs(int s) const
+    {
+        std::vector<int> out;
+        for (const auto &bk : trans[s].bucket)
+            for (const ArcTable::Ent &e : bk)
+                out.insert(out.end(), e.links.begin(), e.links.end());
+        return out;
+    }
+};
+
+}  // namespace
+
+struct ssb_fsg_built_s {
+    ssb_fsg_graph_t g;
+    std::vector<int32_t> link4, arc_off, root, pnode8, dictwid;
+    std::vector<uint8_t> link_flag;
+    std::vector<uint32_t> ctxt;
+    std::vector<std::string> vocab;
+};
+
+extern "C" void ssb_fsg_config_defaults(ssb_fsg_config_t *c)
+{
+    // ref: include/soundswallower/config_defs.h:79-159
+    c->beam = 1e-48;
+    c->pbeam = 1e-48;
+    c->wbeam = 7e-29;
+    c->lw = 6.5f;
+    c->wip = 0.65f;
+    c->pip = 1.0f;
+    c->silprob = 0.005f;
+    c->fillprob = 1e-8f;
+    c->maxhmmpf = 30000;
+    c->fsgusefiller = 1;
+    c->fsgusealtpron = 1;
+}
+
+static ssb_fsg_built_t *fsg_finish(FsgWork &W, int start, int final);
+
+extern "C" ssb_fsg_built_t *ssb_fsg_build_align(const ssb_lexicon_t *lx, const char *text,
+                                                const ssb_fsg_config_t *cfg)
+{
+    if (!lx || !text) {
+        set_error("ssb_fsg_build_align: bad arguments");
+        return nullptr;
+    }
+    FsgWork W;
+    W.lx = lx;
+    if (cfg)
+        W.cfg = *cfg;
+    else
+        ssb_fsg_config_defaults(&W.cfg);
+    // words separated by blanks (ref: src/decoder.c:693-707)
+    std::vector<std::string> words;
+    const std::string t(text);
+    for (size_t i = 0; i < t.size();) {
+        while (i < t.size() && std::strchr(" \t\n\r", t[i]))
+            ++i;
+        size_t j = i;
+        while (j < t.size() && !std::strchr(" \t\n\r", t[j]))
+            ++j;
+        if (j > i)
+            words.emplace_back(t, i, j - i);
+        i = j;
+    }
+    for (const std::string &w : words)
+        if (!lx->id.count(w)) {
+            set_error("Unknown word %s", w.c_str());
+            return nullptr;
+        }
+    W.n_state = (int)words.size() + 1;
+    W.trans.resize(W.n_state);
+    for (size_t i = 0; i < words.size(); ++i)
+        W.trans_add((int)i, (int)i + 1, 0, W.word_add(words[i]));
+    return fsg_finish(W, 0, (int)words.size());
+}
+
+// fsg_search_init's augmentation + fsg_lextree_init, then the flattening
+static ssb_fsg_built_t *fsg_finish(FsgWork &W, int start, int final)
+{
+    const ssb_lexicon_s *lx = W.lx;
+    const HostModel &h = *lx->h;
+    const int n_ci = h.n_ciphone, sil = h.sil, NS = W.n_state;
+    if (sil < 0 || n_ci > 128) {
+        set_error("the grammar search needs a SIL phone and at most 128 CI phones");
+        return nullptr;
+    }
+    LogMath lm(h.cfg.logbase);
+    if (W.cfg.fsgusefiller) {  // ref: src/fsg_search.c:83-118
+        W.add_silence("<sil>", W.cfg.silprob);
+        for (int32_t wid = lx->filler_start; wid < lx->filler_end; ++wid) {
+            if (wid == lx->startwid || wid == lx->finishwid)
+                continue;
+            W.add_silence(lx->word[wid].str, W.cfg.fillprob);
+        }
+    }
+    if (W.cfg.fsgusealtpron) {  // ref: src/fsg_search.c:141-168
+        const int n_word = (int)W.vocab.size();
+        for (int i = 0; i < n_word; ++i) {
+            auto it = lx->id.find(W.vocab[i]);
+            if (it == lx->id.end())
+                continue;
+            const std::string base = W.vocab[i];
+            for (int32_t a = lx->word[it->second].alt; a >= 0; a = lx->word[a].alt)
+                W.add_alt(base, lx->word[a].str);
+        }
+    }
+    const int wip = (int32_t)((float)lm.log((double)W.cfg.wip, 0) * W.cfg.lw) >> 10;
+    const int pip = (int32_t)((float)lm.log((double)W.cfg.pip, 0) * W.cfg.lw) >> 10;
+
+    auto *B = new ssb_fsg_built_s();
+    // ---- links in arc order
+    std::vector<std::vector<int>> arcs(NS);
+    std::vector<int> link_id(W.pool.size(), -1);
+    B->arc_off.assign(NS + 1, 0);
+    std::vector<int32_t> dictwid_of_word(W.vocab.size());
+    for (size_t i = 0; i < W.vocab.size(); ++i)
+        dictwid_of_word[i] = lx->id.at(W.vocab[i]);
+    for (int s = 0; s < NS; ++s) {
+        arcs[s] = W.arcs(s);
+        B->arc_off[s] = (int32_t)(B->link4.size() / 4);
+        for (int li : arcs[s]) {
+            const FLink &l = W.pool[li];
+            link_id[li] = (int)(B->link4.size() / 4);
+            B->link4.insert(B->link4.end(), {l.from, l.to, l.logp, l.wid});
+            const bool filler = W.silword[l.wid];
+            const bool single = lx->word[dictwid_of_word[l.wid]].ph.size() == 1;
+            B->link_flag.push_back((uint8_t)(((filler || single) ? 1 : 0) | (filler ? 2 : 0)));
+        }
+    }
+    B->arc_off[NS] = (int32_t)(B->link4.size() / 4);
+    // ---- left / right context sets of every state (ref: src/fsg_lextree.c:83-214)
+    std::vector<std::vector<uint8_t>> lcb(NS, std::vector<uint8_t>(n_ci, 0)), rcb = lcb;
+    for (int s = 0; s < NS; ++s)
+        for (int li : arcs[s]) {
+            const FLink &l = W.pool[li];
+            if (W.silword[l.wid]) {
+                rcb[l.from][sil] = 1;
+                lcb[l.to][sil] = 1;
+            } else {
+                const Word &w = lx->word[dictwid_of_word[l.wid]];
+                rcb[l.from][w.ph[0]] = 1;
+                lcb[l.to][w.ph.back()] = 1;
+            }
+        }
+    std::vector<std::vector<int>> lcl(NS), rcl(NS);
+    for (int s = 0; s < NS; ++s) {
+        lcb[s][sil] = rcb[s][sil] = 1;
+        for (int i = 0; i < n_ci; ++i) {
+            if (lcb[s][i])
+                lcl[s].push_back(i);
+            if (rcb[s][i])
+                rcl[s].push_back(i);
+        }
+    }
+    // ---- lextree, state by state (ref: src/fsg_lextree.c:352-716)
+    std::vector<PNode> all;       // final numbering
+    B->root.assign(NS, -1);
+    for (int s = 0; s < NS; ++s) {
+        std::vector<PNode> nd;    // allocation order; ids are local until the state is done
+        int root = -1;
+        struct Shared {
+            int ci, rc;
+            std::vector<int> lc_nodes;  // front = newest
+        };
+        std::vector<Shared> shared;  // front = newest
+        auto alloc = [&](int ssid, int tmat, int prob, int ci_ext, int leaf, int next, int sibling,
+                         int ppos) {
+            nd.push_back({ssid, tmat, prob, ci_ext, leaf, next, sibling, ppos, {0, 0, 0, 0}});
+            return (int)nd.size() - 1;
+        };
+        auto add_ctxt = [&](int p, int c) { nd[p].ctxt[c >> 5] |= 1u << (c & 31); };
+        for (int li : arcs[s]) {
+            const FLink &l = W.pool[li];
+            const int32_t dw = dictwid_of_word[l.wid];
+            const Word &w = lx->word[dw];
+            const int pronlen = (int)w.ph.size();
+            const std::vector<int> &lclist = lcl[s], &rclist = rcl[l.to];
+            const int lprob = l.logp >> 10;
+            if (pronlen == 1) {
+                const int ci = w.ph[0];
+                if (!ssb_lexicon_is_filler(lx, dw)) {
+                    std::vector<int> mine;  // front = newest
+                    for (int lc : lclist) {
+                        const int ssid = lx->lrdiph_rc[lx->at(ci, lc, sil)];
+                        int found = -1;
+                        for (int p : mine)
+                            if (nd[p].ssid == ssid) {
+                                found = p;
+                                break;
+                            }
+                        if (found >= 0) {
+                            add_ctxt(found, lc);
+                            continue;
+                        }
+                        const int p = alloc(ssid, h.ph_tmat[ci], lprob + wip + pip, ci, 1, -2 - li,
+                                            root, 0);
+                        add_ctxt(p, lc);
+                        root = p;
+                        mine.insert(mine.begin(), p);
+                    }
+                } else {
+                    const int p = alloc(h.ph_ssid[ci], h.ph_tmat[ci], lprob + wip + pip, sil, 1,
+                                        -2 - li, root, 0);
+                    for (int k = 0; k < 4; ++k)
+                        nd[p].ctxt[k] = 0xffffffffu;
+                    root = p;
+                }
+                continue;
+            }
+            std::vector<int> lc_nodes;  // front = newest
+            int pred = -1;
+            for (int p = 0; p < pronlen; ++p) {
+                const int ci = w.ph[p];
+                if (p == 0) {
+                    const int rc = w.ph[1];
+                    int hit = -1;
+                    for (size_t k = 0; k < shared.size(); ++k)
+                        if (shared[k].ci == ci && shared[k].rc == rc) {
+                            hit = (int)k;
+                            break;
+                        }
+                    if (hit >= 0) {
+                        lc_nodes = shared[hit].lc_nodes;
+                        pred = lc_nodes.front();
+                        continue;
+                    }
+                    // the reference's ssid -> node scan keeps the LAST node it looked at when
+                    // nothing matches, so once a node exists every further left context is
+                    // folded into it (ref: src/fsg_lextree.c:504-536)
+                    std::vector<int> map;
+                    for (int lc : lclist) {
+                        const int ssid = lx->ldiph_lc[lx->at(ci, rc, lc)];
+                        int pn = map.empty() ? -1 : map[0];
+                        for (size_t j = 0; j < map.size(); ++j) {
+                            pn = map[j];
+                            if (nd[pn].ssid == ssid)
+                                break;
+                        }
+                        if (pn < 0) {
+                            pn = alloc(ssid, h.ph_tmat[w.ph[0]], wip + pip, w.ph[0], 0, -1, root, 0);
+                            root = pn;
+                            lc_nodes.insert(lc_nodes.begin(), pn);
+                            map.push_back(pn);
+                        }
+                        add_ctxt(pn, lc);
+                    }
+                    shared.insert(shared.begin(), Shared{ci, rc, lc_nodes});
+                    pred = root;
+                } else if (p != pronlen - 1) {
+                    const int ssid = lx->ssid_of(lx->phone_id_nearest(ci, w.ph[p - 1], w.ph[p + 1],
+                                                                      POS_INTERNAL));
+                    int pn = nd[pred].next;
+                    const int youngest = pn;
+                    while (pn >= 0 && (nd[pn].ssid != ssid || nd[pn].leaf))
+                        pn = nd[pn].sibling;
+                    if (pn >= 0) {
+                        pred = pn;
+                        continue;
+                    }
+                    pn = alloc(ssid, h.ph_tmat[ci], pip, ci, 0, -1, youngest, p);
+                    if (p == 1)
+                        for (int r : lc_nodes) {
+                            pred = r;
+                            nd[r].next = pn;
+                        }
+                    else
+                        nd[pred].next = pn;
+                    pred = pn;
+                } else {
+                    const int lc = w.ph[p - 1];
+                    std::vector<std::pair<int, int>> map;  // ssid -> node
+                    std::vector<int> rc_nodes;             // front = newest
+                    for (int rc : rclist) {
+                        const int ssid = lx->rdiph_rc[lx->at(ci, lc, rc)];
+                        int pn = -1;
+                        for (auto &e : map)
+                            if (e.first == ssid)
+                                pn = e.second;
+                        if (pn < 0) {
+                            pn = alloc(ssid, h.ph_tmat[ci], lprob + pip, ci, 1, -2 - li,
+                                       rc_nodes.empty() ? -1 : rc_nodes.front(), p);
+                            rc_nodes.insert(rc_nodes.begin(), pn);
+                            map.emplace_back(ssid, pn);
+                        }
+                        add_ctxt(pn, rc);
+                    }
+                    auto hook = [&](int pr) {  // true: appended to an existing chain
+                        if (nd[pr].next < 0) {
+                            nd[pr].next = rc_nodes.front();
+                            return false;
+                        }
+                        int succ = nd[pr].next;
+                        while (nd[succ].sibling >= 0)
+                            succ = nd[succ].sibling;
+                        nd[succ].sibling = rc_nodes.front();
+                        return true;
+                    };
+                    if (p == 1) {
+                        for (int r : lc_nodes) {
+                            pred = r;
+                            if (hook(r))
+                                break;
+                        }
+                    } else
+                        hook(pred);
+                }
+            }
+        }
+        // number the state's nodes newest first; leaf `next` (-2 - li) becomes a link id
+        const int base = (int)all.size(), n = (int)nd.size();
+        auto gid = [&](int local) { return local < 0 ? -1 : base + (n - 1 - local); };
+        for (int k = n - 1; k >= 0; --k) {
+            PNode q = nd[k];
+            q.next = q.leaf ? link_id[-2 - q.next] : gid(q.next);
+            q.sibling = gid(q.sibling);
+            all.push_back(q);
+        }
+        B->root[s] = gid(root);
+    }
+    for (const PNode &q : all) {
+        B->pnode8.insert(B->pnode8.end(),
+                         {q.ssid, q.tmat, q.logs2prob, q.ci_ext, q.leaf, q.next, q.sibling, q.ppos});
+        B->ctxt.insert(B->ctxt.end(), q.ctxt, q.ctxt + 4);
+    }
+    B->vocab = W.vocab;
+    B->dictwid = dictwid_of_word;
+    ssb_fsg_graph_t &g = B->g;
+    g.n_state = NS;
+    g.start = start;
+    g.final = final;
+    g.n_link = (int32_t)B->link_flag.size();
+    g.n_pnode = (int32_t)all.size();
+    g.n_ciphone = n_ci;
+    g.sil = sil;
+    g.beam = (int32_t)lm.log(W.cfg.beam, 0) >> 10;
+    g.pbeam = (int32_t)lm.log(W.cfg.pbeam, 0) >> 10;
+    g.wbeam = (int32_t)lm.log(W.cfg.wbeam, 0) >> 10;
+    g.maxhmmpf = W.cfg.maxhmmpf;
+    g.link4 = B->link4.data();
+    g.link_flag = B->link_flag.data();
+    g.arc_off = B->arc_off.data();
+    g.root = B->root.data();
+    g.pnode8 = B->pnode8.data();
+    g.ctxt = B->ctxt.data();
+    return B;
+}
+
+extern "C" const ssb_fsg_graph_t *ssb_fsg_built_graph(const ssb_fsg_built_t *b)
+{
+    return b ? &b->g : nullptr;
+}
+
+extern "C" int32_t ssb_fsg_built_n_words(const ssb_fsg_built_t *b)
+{
+    return b ? (int32_t)b->vocab.size() : -1;
+}
+
+extern "C" const char *ssb_fsg_built_word(const ssb_fsg_built_t *b, int32_t fsg_wid, int32_t *dict_wid)
+{
+    if (!b || fsg_wid < 0 || fsg_wid >= (int32_t)b->vocab.size())
+        return nullptr;
+    if (dict_wid)
+        *dict_wid = b->dictwid[fsg_wid];
+    return b->vocab[fsg_wid].c_str();
+}
+
+extern "C" void ssb_fsg_built_free(ssb_fsg_built_t *b) { delete b; }

@@ -213,3 +213,33 @@ def test_audio_to_alignment_on_gpu_equals_cli(models, golden, lang):
     assert np.array_equal(p2["start"], st[:, 1]) and np.array_equal(p2["dur"], st[:, 2])
     assert np.array_equal(p2["score"], st[:, 3])
     fe.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lang,raw,text", [("en-us", "goforward.raw", "go forward ten meters"),
+                                           ("fr-fr", "goforward_fr.raw", "avance de dix mètres")])
+def test_cli_alignment_from_audio_and_text(models, golden, lang, raw, text):
+    """BASELINE config #1 with nothing but the audio, the transcript and the model directory:
+    frontend -> alignment grammar (host) -> grammar search -> word windows -> phone chain
+    (host) -> chain Viterbi -> propagate.  Words, phones and states equal the reference CLI's
+    (tests/golden/align_*.npz = SURVEY Appendix A/B)."""
+    import soundswallower_b200 as ssb
+    m, g = models(lang), golden[lang]
+    lx = ssb.Lexicon(m, hmmdir=model_dir(lang))
+    fe = ssb.Frontend(model_dir(lang), device=0, samprate=16000)
+    pcm = mv.fe_input(raw, 16000)
+    dev = fe.run([pcm, pcm[:len(pcm) // 3]])          # the truncated copy cannot match
+    res = ssb.align_texts(m, lx, dev, [text, text])
+    assert res[1] is None
+    r = res[0]
+    # (pass 1 runs on dense "compallsen" scores: same search decisions and word boundaries as
+    # the CLI's default mode, but its path score is normalised over all senones, so hyp_score
+    # is the compallsen=yes one -- tests/test_gpu_fsg.py pins that value)
+    gw = g["words"]
+    assert [w[0] for w in r["words"]] == [lx.wordstr(int(w)) for w in gw[:, 0]]
+    assert [list(w[1:]) for w in r["words"]] == gw[:, 1:4].tolist()
+    gp = g["phones"]
+    assert [m.ciname(int(c)) for c in gp[:, 0]] == [p[0] for p in r["phones"]]
+    assert [list(p[1:]) for p in r["phones"]] == gp[:, [3, 4, 5, 6]].tolist()
+    assert np.array_equal(r["states"], g["states"])
+    fe.close()

@@ -88,3 +88,53 @@ def test_reference_agrees_when_present(lexicons):
             a, b = r.populate(wids)["phones"], lx.populate(wids)
             assert np.array_equal(a[:, 1], b["ssid"]) and np.array_equal(a[:, 2], b["tmat"])
         r.close()
+
+
+# ------------------------------------------------------------------ alignment grammar + lextree
+GRAPH_KEYS = ("link", "link_flag", "arc_off", "root", "pnode", "ctxt")
+GRAPH_DIMS = ("n_state", "start", "final", "n_ciphone", "sil", "beam", "pbeam", "wbeam", "maxhmmpf")
+
+
+@pytest.mark.parametrize("lang,text", [("en-us", "go forward ten meters"),
+                                       ("fr-fr", "avance de dix mètres")])
+def test_align_graph_equals_the_reference_graph(lexicons, lang, text):
+    """decoder_set_align_text + fsg_search_init + fsg_lextree_init, flattened: identical --
+    link order, node order, context sets -- to the graph the reference searched
+    (tests/golden/fsg_*.npz, dumped by oracle/ref_shim.c:ref_fsg_dump)."""
+    from test_oracle_fsg import graph_of
+    _, lx = lexicons[lang]
+    want = graph_of(np.load(os.path.join(GOLDEN, "fsg_%s.npz" % lang)), "align")
+    got = lx.align_graph(text)
+    for k in GRAPH_DIMS:
+        assert int(got[k]) == int(want[k]), k
+    for k in GRAPH_KEYS:
+        assert np.array_equal(got[k], np.asarray(want[k]).reshape(got[k].shape)), k
+    assert got["words"][:len(text.split())] == text.split()
+    with pytest.raises(ssb.SsbError, match="Unknown word"):
+        lx.align_graph("go forward xyzzyplugh")
+
+
+def test_align_graphs_agree_with_reference_when_present(lexicons):
+    """Random transcripts (1 to 150 words, repeated words, words with alternate
+    pronunciations, single-phone words) against the compiled reference."""
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("oracle/_ref/libssref.so not built here")
+    rs = np.random.RandomState(3)
+    for lang in ("en-us", "fr-fr"):
+        _, lx = lexicons[lang]
+        r = refshim.Ref(model_dir(lang))
+        n_main = lx.wordid("<sil>") - 2
+        for it in range(40):
+            ws = []
+            while len(ws) < int(rs.choice([1, 2, 3, 5, 8, 13, 40, 150])):
+                w = lx.wordstr(int(rs.randint(0, n_main)))
+                if "(" not in w and w[0] not in "<[":
+                    ws.append(w)
+            if it % 7 == 0:
+                ws += ws[:2]
+            text = " ".join(ws)
+            got, want = lx.align_graph(text), r.fsg_graph(align_text=text)
+            assert all(int(got[k]) == int(want[k]) for k in GRAPH_DIMS), text
+            assert all(np.array_equal(got[k], want[k]) for k in GRAPH_KEYS), text
+        r.close()
