@@ -186,11 +186,31 @@ int ssb_batch_kernel_ms(ssb_batch_t *b, float *ms8);
 int ssb_batch_n_launches(const ssb_batch_t *b);
 /* counters of the uploaded batch: [0] frames [1] state-frames [2] active senone-frames
  * [3] scanned codebook-frames [4] device bytes held [5] largest active-senone union
- * [6] longest chain (phones) */
+ * [6] longest chain (phones) [7] host microseconds the last upload spent planning */
 int ssb_batch_stats(const ssb_batch_t *b, int64_t *out8);
 
-/* upload + run + download in one call (the call a host program makes) */
+/* upload + run + download in one call (the call a host program makes).  A batch of at least
+ * two chunks (see ssb_pipeline_create) is routed through a temporary pipeline. */
 int ssb_align_batch(ssb_model_t *m, const ssb_align_in_t *in, ssb_align_out_t *out);
+
+/* The same call for callers that keep coming back (a server, a long file list): device
+ * buffers are kept between calls and a large batch is cut into chunks of whole utterances
+ * (about `chunk_frames` frames each, 0 = 1 024 000 or $SSB_PIPE_CHUNK_FRAMES) that travel through
+ * `n_lanes` (0 = 4 or $SSB_PIPE_LANES) batches, each on its own stream and host thread, so that
+ * planning, host->device and device->host copies of one chunk overlap the kernels of another.
+ * Utterances are independent (ref: one decoder_t per utterance, src/decoder.c:737-798), so the
+ * results are those of ssb_batch_upload/run/download on the whole batch, utterance by
+ * utterance.  `in->feat` should be pinned host memory for the copies to overlap. */
+typedef struct ssb_pipeline_s ssb_pipeline_t;
+ssb_pipeline_t *ssb_pipeline_create(ssb_model_t *m, int32_t n_lanes, int64_t chunk_frames);
+int ssb_pipeline_align(ssb_pipeline_t *p, const ssb_align_in_t *in, ssb_align_out_t *out);
+int ssb_pipeline_n_launches(const ssb_pipeline_t *p); /* kernels launched by the last call */
+int ssb_pipeline_n_chunks(const ssb_pipeline_t *p);   /* chunks of the last call */
+/* timeline of the last call, 8 doubles per chunk: lane, first utterance, ms since the call
+ * started at which the chunk's upload began / its upload returned / its download returned,
+ * CUDA-event ms of its top-N kernel and of all its kernels, 0; returns chunks written */
+int ssb_pipeline_trace(const ssb_pipeline_t *p, double *out, int32_t max_chunks);
+void ssb_pipeline_free(ssb_pipeline_t *p);
 
 /* Dense senone scoring of whole utterances with "compallsen" semantics
  * (what acmod_score returns frame by frame, ref: src/acmod.c:822-860):

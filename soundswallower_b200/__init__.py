@@ -264,9 +264,7 @@ class StateAlignBatch:
         except Exception:
             pass
 
-    def upload_raw(self, feat, frame_off, phone_off, ssid, tmat, sf, ef, init_active=None,
-                   compallsen=False):
-        """Flat arrays exactly as ssb_align_in_t takes them (feat may be pinned memory)."""
+    def _align_in(self, feat, frame_off, phone_off, ssid, tmat, sf, ef, init_active, compallsen):
         n_utts = len(frame_off) - 1
         a = _lib.AlignIn()
         a.n_utts = n_utts
@@ -283,6 +281,12 @@ class StateAlignBatch:
         self.n_utts = n_utts
         self.frame_off = np.asarray(frame_off)
         self.phone_off = np.asarray(phone_off)
+        return a
+
+    def upload_raw(self, feat, frame_off, phone_off, ssid, tmat, sf, ef, init_active=None,
+                   compallsen=False):
+        """Flat arrays exactly as ssb_align_in_t takes them (feat may be pinned memory)."""
+        a = self._align_in(feat, frame_off, phone_off, ssid, tmat, sf, ef, init_active, compallsen)
         _lib.check(self.lib.ssb_batch_upload(self.b, C.byref(a)), "ssb_batch_upload")
 
     def upload(self, feats, chains, init_active=None, compallsen=False):
@@ -312,9 +316,7 @@ class StateAlignBatch:
     def run(self):
         _lib.check(self.lib.ssb_batch_run(self.b), "ssb_batch_run")
 
-    def download(self, want_chain_scr=False, want_tokens=False, init=None):
-        """Returns flat arrays; `per_utt()` splits them.  `init` = (start, dur, score) the
-        caller's pre-filled state entries (states off the best path keep them)."""
+    def _align_out(self, want_chain_scr, want_tokens, init):
         E = self.model.n_emit
         ns = int(self.phone_off[-1]) * E
         U = self.n_utts
@@ -333,9 +335,15 @@ class StateAlignBatch:
         o.utt_rv, o.utt_best, o.utt_renorm = (_ptr(a, C.c_int32) for a in (rv, best, ren))
         o.chain_scr = _ptr(cs, C.c_int16) if cs is not None else None
         o.tokens = _ptr(tk, C.c_int32) if tk is not None else None
+        return o, dict(start=st[0], dur=st[1], score=st[2], rv=rv, best_score=best, n_renorm=ren,
+                       chain_scr=cs, tokens=tk)
+
+    def download(self, want_chain_scr=False, want_tokens=False, init=None):
+        """Returns flat arrays; `per_utt()` splits them.  `init` = (start, dur, score) the
+        caller's pre-filled state entries (states off the best path keep them)."""
+        o, res = self._align_out(want_chain_scr, want_tokens, init)
         _lib.check(self.lib.ssb_batch_download(self.b, C.byref(o)), "ssb_batch_download")
-        return dict(start=st[0], dur=st[1], score=st[2], rv=rv, best_score=best, n_renorm=ren,
-                    chain_scr=cs, tokens=tk)
+        return res
 
     def per_utt(self, res):
         E = self.model.n_emit
@@ -370,22 +378,79 @@ class StateAlignBatch:
         self.lib.ssb_batch_stats(self.b, _ptr(s, C.c_int64))
         return dict(frames=int(s[0]), state_frames=int(s[1]), active_senone_frames=int(s[2]),
                     scanned_cb_frames=int(s[3]), device_bytes=int(s[4]), max_union=int(s[5]),
-                    max_phones=int(s[6]))
+                    max_phones=int(s[6]), plan_us=int(s[7]))
+
+
+class _AlignCall(StateAlignBatch):
+    """Argument marshalling only: upload()/upload_raw() keep the ssb_align_in_t for a later call."""
+
+    def __init__(self, model):
+        self.model = model
+        self.lib = model.lib
+        self.b = None
+        self._keep = None
+        self._in = None
+
+    def upload_raw(self, feat, frame_off, phone_off, ssid, tmat, sf, ef, init_active=None,
+                   compallsen=False):
+        self._in = self._align_in(feat, frame_off, phone_off, ssid, tmat, sf, ef, init_active,
+                                  compallsen)
+
+    def run(self):
+        raise SsbError("not a resident batch: use align()")
+
+    def align(self, want_chain_scr=False, want_tokens=False, init=None):
+        """ssb_align_batch: upload + run + download in one C call."""
+        o, res = self._align_out(want_chain_scr, want_tokens, init)
+        _lib.check(self.lib.ssb_align_batch(self.model.h, C.byref(self._in), C.byref(o)),
+                   "ssb_align_batch")
+        return res
+
+
+class AlignPipeline(_AlignCall):
+    """ssb_pipeline_*: the batch cut into chunks of whole utterances that travel through a few
+    lanes (stream + host thread each), so that planning and copies overlap the kernels.  Same
+    upload()/upload_raw() arguments as StateAlignBatch; align() = upload + run + download."""
+
+    def __init__(self, model, n_lanes=0, chunk_frames=0):
+        _AlignCall.__init__(self, model)
+        self.p = self.lib.ssb_pipeline_create(model.h, int(n_lanes), int(chunk_frames))
+        if not self.p:
+            raise SsbError("ssb_pipeline_create: " + _lib.last_error())
+        self.p = C.c_void_p(self.p)
+
+    def close(self):
+        if getattr(self, "p", None):
+            self.lib.ssb_pipeline_free(self.p)
+            self.p = None
+
+    def align(self, want_chain_scr=False, want_tokens=False, init=None):
+        """Runs the uploaded arguments through the pipeline; returns download()'s dict."""
+        o, res = self._align_out(want_chain_scr, want_tokens, init)
+        _lib.check(self.lib.ssb_pipeline_align(self.p, C.byref(self._in), C.byref(o)),
+                   "ssb_pipeline_align")
+        return res
+
+    def n_launches(self):
+        return int(self.lib.ssb_pipeline_n_launches(self.p))
+
+    def n_chunks(self):
+        return int(self.lib.ssb_pipeline_n_chunks(self.p))
+
+    def trace(self):
+        """[chunk][lane, first utt, upload start, upload end, download end, top-N ms, kernels ms, 0]"""
+        t = np.zeros((max(self.n_chunks(), 1), 8), np.float64)
+        n = self.lib.ssb_pipeline_trace(self.p, _ptr(t, C.c_double), t.shape[0])
+        return t[:max(int(n), 0)]
 
 
 def align_batch(model, feats, chains, init_active=None, compallsen=False, want_chain_scr=False,
                 want_tokens=False):
     """One-shot: upload + run + download; returns a list of per-utterance dicts
     (start/dur/score per state, rv, best_score, n_renorm[, chain_scr, tokens])."""
-    b = StateAlignBatch(model)
-    try:
-        if want_tokens:
-            b.debug_tokens(True)
-        b.upload(feats, chains, init_active=init_active, compallsen=compallsen)
-        b.run()
-        return b.per_utt(b.download(want_chain_scr=want_chain_scr, want_tokens=want_tokens))
-    finally:
-        b.close()
+    b = _AlignCall(model)
+    b.upload(feats, chains, init_active=init_active, compallsen=compallsen)
+    return b.per_utt(b.align(want_chain_scr=want_chain_scr, want_tokens=want_tokens))
 
 
 def score_batch(model, feats, want=True):

@@ -99,7 +99,9 @@ SYMBOLS = [
     "ssb_mgau_init", "ssb_mgau_frame_eval", "ssb_mgau_reset", "ssb_mgau_free",
     "ssb_plan_chain", "ssb_batch_create", "ssb_batch_free", "ssb_batch_upload", "ssb_batch_run",
     "ssb_batch_download", "ssb_batch_debug_tokens", "ssb_batch_kernel_ms",
-    "ssb_batch_n_launches", "ssb_batch_stats", "ssb_align_batch", "ssb_score_batch",
+    "ssb_batch_n_launches", "ssb_batch_stats", "ssb_align_batch", "ssb_pipeline_create",
+    "ssb_pipeline_align", "ssb_pipeline_n_launches", "ssb_pipeline_n_chunks", "ssb_pipeline_trace", "ssb_pipeline_free",
+    "ssb_score_batch",
     "ssb_topn_batch", "ssb_tc_probe", "ssb_tc_hot_mask", "ssb_fsg_batch", "ssb_hmm_vit_eval",
     "ssb_fe_config_defaults", "ssb_fe_config_from_model", "ssb_frontend_create",
     "ssb_frontend_free", "ssb_frontend_dims", "ssb_frontend_n_frames", "ssb_frontend_tables",
@@ -157,6 +159,14 @@ def load():
     L.ssb_batch_n_launches.argtypes = [vp]
     L.ssb_batch_stats.argtypes = [vp, P(i64)]
     L.ssb_align_batch.argtypes = [vp, P(AlignIn), P(AlignOut)]
+    L.ssb_pipeline_create.restype = vp
+    L.ssb_pipeline_create.argtypes = [vp, i32, i64]
+    L.ssb_pipeline_align.argtypes = [vp, P(AlignIn), P(AlignOut)]
+    L.ssb_pipeline_n_launches.argtypes = [vp]
+    L.ssb_pipeline_n_chunks.argtypes = [vp]
+    L.ssb_pipeline_trace.argtypes = [vp, vp, i32]
+    L.ssb_pipeline_free.restype = None
+    L.ssb_pipeline_free.argtypes = [vp]
     L.ssb_score_batch.restype = i64
     L.ssb_score_batch.argtypes = [vp, vp, vp, i32, vp]
     L.ssb_topn_batch.restype = i64

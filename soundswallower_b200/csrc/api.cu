@@ -3,12 +3,16 @@
 //   K1 gmm_topn -> K2 senone_mix -> K3 chain_viterbi -> backtrace.
 // No CPU fallback: every compute entry point needs a CUDA device.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <climits>
+#include <condition_variable>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -601,6 +605,7 @@ struct ssb_batch_s {
     int n_utts = 0;
     int64_t n_frames = 0, n_phones = 0, n_states = 0, n_state_frames = 0;
     int64_t n_active_sen_frames = 0, n_scanned_cb_frames = 0;
+    int64_t plan_us = 0;  // host time of the last upload's planning + staging calls
     int max_phones = 0, max_union = 0, max_T = 0;
     int compallsen = 0;
     bool want_tokens_all = false;
@@ -978,6 +983,7 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
     }
 
     // ---- plan: worker threads over contiguous utterance ranges, then concatenate
+    const auto t_plan0 = std::chrono::steady_clock::now();
     b->enter.assign((size_t)b->n_phones, -1);
     std::vector<uint16_t> st_slot((size_t)b->n_states, 0);
     int n_workers = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
@@ -1032,6 +1038,8 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
         || upload(b->d_usen, usen, st) || upload(b->d_st_slot, st_slot, st)
         || upload(b->d_enter, b->enter, st))
         return -1;
+    b->plan_us = (int64_t)std::chrono::duration<double, std::micro>(
+                     std::chrono::steady_clock::now() - t_plan0).count();
     // the host vectors above die at return: make sure the copies have been staged
     API_CUDA(cudaStreamSynchronize(st), -1);
     DevPlan &p = b->plan;
@@ -1239,11 +1247,254 @@ extern "C" int ssb_batch_stats(const ssb_batch_t *b, int64_t *o)
     o[4] = (int64_t)b->bytes_held();
     o[5] = b->max_union;
     o[6] = b->max_phones;
+    o[7] = b->plan_us;
+    return 0;
+}
+
+// ------------------------------------------------------------------ pipeline
+// Utterances are independent, so a large batch is cut into chunks of whole utterances and the
+// chunks travel through `n_lanes` batches, each on its own stream and driven by its own host
+// thread: while one chunk is on the SMs the next one is being planned and copied in and the
+// previous one copied out.  Results are those of one big batch, utterance by utterance.
+struct ssb_pipeline_s {
+    ssb_model_t *m = nullptr;
+    int n_lanes = 0;
+    int64_t chunk_frames = 0;
+    std::vector<ssb_batch_t *> lane;
+    std::vector<cudaStream_t> st;
+    int n_launches = 0, n_chunks = 0;
+    // per chunk of the last call: lane, first utterance, then ms since the call started at
+    // which upload began / upload returned / download returned, and the chunk's kernel ms
+    std::vector<double> trace;
+};
+
+extern "C" void ssb_pipeline_free(ssb_pipeline_t *p)
+{
+    if (!p)
+        return;
+    cudaSetDevice(p->m->device);
+    for (ssb_batch_t *b : p->lane)
+        ssb_batch_free(b);
+    for (cudaStream_t s : p->st)
+        if (s)
+            cudaStreamDestroy(s);
+    delete p;
+}
+
+extern "C" ssb_pipeline_t *ssb_pipeline_create(ssb_model_t *m, int32_t n_lanes, int64_t chunk_frames)
+{
+    if (need_device(m) != 0)
+        return nullptr;
+    if (n_lanes <= 0) {
+        const char *e = getenv("SSB_PIPE_LANES");
+        n_lanes = e ? atoi(e) : 4;
+    }
+    if (chunk_frames <= 0) {
+        const char *e = getenv("SSB_PIPE_CHUNK_FRAMES");
+        chunk_frames = e ? atoll(e) : 1024000;
+    }
+    n_lanes = std::max(1, std::min(n_lanes, 8));
+    ssb_pipeline_s *p = new ssb_pipeline_s;
+    p->m = m;
+    p->n_lanes = n_lanes;
+    p->chunk_frames = std::max<int64_t>(chunk_frames, 1);
+    for (int i = 0; i < n_lanes; ++i) {
+        cudaStream_t s = nullptr;
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) {
+            set_error("cudaStreamCreate failed");
+            ssb_pipeline_free(p);
+            return nullptr;
+        }
+        p->st.push_back(s);
+        ssb_batch_t *b = ssb_batch_create(m, s);
+        if (!b) {
+            ssb_pipeline_free(p);
+            return nullptr;
+        }
+        p->lane.push_back(b);
+    }
+    return p;
+}
+
+extern "C" int ssb_pipeline_n_launches(const ssb_pipeline_t *p) { return p ? p->n_launches : -1; }
+extern "C" int ssb_pipeline_n_chunks(const ssb_pipeline_t *p) { return p ? p->n_chunks : -1; }
+extern "C" int ssb_pipeline_trace(const ssb_pipeline_t *p, double *out, int32_t max_chunks)
+{
+    if (!p || !out)
+        return -1;
+    const int n = std::min<int>(max_chunks, p->n_chunks);
+    for (int i = 0; i < n * 8; ++i)
+        out[i] = p->trace[i];
+    return n;
+}
+
+extern "C" int ssb_pipeline_align(ssb_pipeline_t *p, const ssb_align_in_t *in, ssb_align_out_t *out)
+{
+    if (!p || !in || !out || in->n_utts < 0 || (in->n_utts > 0 && (!in->frame_off || !in->phone_off))) {
+        set_error("ssb_pipeline_align: bad arguments");
+        return -1;
+    }
+    if (need_device(p->m) != 0)
+        return -1;
+    const HostModel &h = p->m->h;
+    const int U = in->n_utts, E = h.n_emit;
+    p->n_launches = 0;
+    p->n_chunks = 0;
+    if (U == 0)
+        return 0;
+    if (in->frame_off[0] != 0 || in->phone_off[0] != 0) {
+        set_error("frame_off[0] and phone_off[0] must be 0");
+        return -1;
+    }
+    // chunk boundaries (whole utterances, about chunk_frames frames each; a multiple of 256
+    // utterances where that many fit, the row count of one top-N CTA) and where each chunk's
+    // per-state-frame debug outputs start
+    std::vector<int> cut(1, 0);
+    std::vector<int64_t> scr0(1, 0);
+    {
+        int64_t scr = 0;
+        int u0 = 0;
+        for (int u = 0; u < U; ++u) {
+            const int64_t T = in->frame_off[u + 1] - in->frame_off[u];
+            const int64_t np = in->phone_off[u + 1] - in->phone_off[u];
+            if (T < 0 || np < 0) {
+                set_error("utterance %d: offsets must be non-decreasing", u);
+                return -1;
+            }
+            scr += T * np * E;
+            const int64_t fr = in->frame_off[u + 1] - in->frame_off[u0];
+            const int nu = u + 1 - u0;
+            if (u + 1 == U || (fr >= p->chunk_frames && (nu < 256 || nu % 256 == 0))
+                || fr >= 2 * p->chunk_frames) {
+                cut.push_back(u + 1);
+                scr0.push_back(scr);
+                u0 = u + 1;
+            }
+        }
+    }
+    const int n_chunks = (int)cut.size() - 1;
+    p->n_chunks = n_chunks;
+    const int nw = (h.n_sen + 31) / 32;
+    p->trace.assign((size_t)n_chunks * 8, 0.0);
+    const auto t_call = std::chrono::steady_clock::now();
+    auto now_ms = [&]() {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
+    };
+    std::atomic<int> next(0), failed(0), launches(0);
+    std::string err;
+    std::mutex err_mu, up_mu;
+    std::condition_variable up_cv;
+    int up_turn = 0;
+    auto work = [&](int li) {
+        cudaSetDevice(p->m->device);
+        ssb_batch_t *b = p->lane[li];
+        ssb_batch_debug_tokens(b, out->tokens ? 1 : 0);
+        std::vector<int64_t> fo, po;
+        for (;;) {
+            const int c = next.fetch_add(1);
+            if (c >= n_chunks || failed.load())
+                break;
+            const int u0 = cut[c], u1 = cut[c + 1];
+            const int64_t f0 = in->frame_off[u0], p0 = in->phone_off[u0];
+            fo.resize(u1 - u0 + 1);
+            po.resize(u1 - u0 + 1);
+            for (int u = u0; u <= u1; ++u) {
+                fo[u - u0] = in->frame_off[u] - f0;
+                po[u - u0] = in->phone_off[u] - p0;
+            }
+            ssb_align_in_t ci = *in;
+            ci.n_utts = u1 - u0;
+            ci.feat = in->feat ? in->feat + f0 * h.blk : nullptr;
+            ci.frame_off = fo.data();
+            ci.phone_off = po.data();
+            ci.ssid = in->ssid ? in->ssid + p0 : nullptr;
+            ci.tmat = in->tmat ? in->tmat + p0 : nullptr;
+            ci.sf = in->sf ? in->sf + p0 : nullptr;
+            ci.ef = in->ef ? in->ef + p0 : nullptr;
+            ci.init_active = in->init_active ? in->init_active + (size_t)u0 * nw : nullptr;
+            ssb_align_out_t co = *out;
+            co.st_start = out->st_start ? out->st_start + p0 * E : nullptr;
+            co.st_dur = out->st_dur ? out->st_dur + p0 * E : nullptr;
+            co.st_score = out->st_score ? out->st_score + p0 * E : nullptr;
+            co.utt_rv = out->utt_rv ? out->utt_rv + u0 : nullptr;
+            co.utt_best = out->utt_best ? out->utt_best + u0 : nullptr;
+            co.utt_renorm = out->utt_renorm ? out->utt_renorm + u0 : nullptr;
+            co.chain_scr = out->chain_scr ? out->chain_scr + scr0[c] : nullptr;
+            co.tokens = out->tokens ? out->tokens + 2 * scr0[c] : nullptr;
+            double *tr = &p->trace[(size_t)c * 8];
+            tr[0] = li;
+            tr[1] = u0;
+            int rv;
+            {
+                // one chunk on the PCIe link at a time, in chunk order: the first chunk reaches
+                // the SMs after 1/n of the copy time, and the lanes stay out of phase
+                std::unique_lock<std::mutex> lk(up_mu);
+                up_cv.wait(lk, [&] { return up_turn == c || failed.load(); });
+                tr[2] = now_ms();
+                rv = ssb_batch_upload(b, &ci);
+                ++up_turn;
+                lk.unlock();
+                up_cv.notify_all();
+            }
+            tr[3] = now_ms();
+            if (rv == 0)
+                rv = ssb_batch_run(b);
+            if (rv == 0)
+                rv = ssb_batch_download(b, &co);
+            tr[4] = now_ms();
+            if (rv == 0) {
+                float ms[8];
+                if (ssb_batch_kernel_ms(b, ms) == 0) {
+                    tr[5] = ms[0];
+                    tr[6] = ms[4];
+                }
+            }
+            if (rv != 0) {
+                std::lock_guard<std::mutex> lk(err_mu);
+                if (!failed.exchange(1))
+                    err = ssb::last_error();
+                up_cv.notify_all();
+                break;
+            }
+            launches.fetch_add(b->n_launches);
+        }
+    };
+    const int n_thr = std::min(p->n_lanes, n_chunks);
+    if (n_thr <= 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < n_thr; ++i)
+            th.emplace_back(work, i);
+        for (auto &t : th)
+            t.join();
+    }
+    p->n_launches = launches.load();
+    if (failed.load()) {
+        set_error("%s", err.c_str());
+        return -1;
+    }
     return 0;
 }
 
 extern "C" int ssb_align_batch(ssb_model_t *m, const ssb_align_in_t *in, ssb_align_out_t *out)
 {
+    // a batch of several chunks goes through the pipeline (copies overlap the kernels)
+    if (in && out && in->n_utts > 1 && in->frame_off) {
+        const char *e = getenv("SSB_PIPE_CHUNK_FRAMES");
+        const int64_t chunk = e ? atoll(e) : 1024000;
+        if (in->frame_off[in->n_utts] >= 2 * chunk) {
+            ssb_pipeline_t *p = ssb_pipeline_create(m, 0, 0);
+            if (!p)
+                return -1;
+            const int rv = ssb_pipeline_align(p, in, out);
+            std::string keep = rv ? ssb::last_error() : "";
+            ssb_pipeline_free(p);
+            if (rv)
+                set_error("%s", keep.c_str());
+            return rv;
+        }
+    }
     ssb_batch_t *b = ssb_batch_create(m, nullptr);
     if (!b)
         return -1;

@@ -235,6 +235,60 @@ def test_align_random_ragged_batch(models, oracles, compallsen):
     assert n_ok >= 10
 
 
+@pytest.mark.parametrize("compallsen", [False, True])
+def test_pipeline_equals_oracle_and_single_batch(models, oracles, compallsen):
+    """ssb_pipeline_align: chunks of whole utterances through 3 lanes (own stream + host thread
+    each) give, utterance by utterance, the oracle's answer and the one-batch answer, debug
+    outputs (chain scores, token stacks) and init_active slices included; lanes are reused
+    across calls."""
+    m, o = models("en-us"), oracles("en-us")
+    rs = np.random.RandomState(77 + compallsen)
+    feats, chains = _random_batch(rs, o, 37)
+    feats[0] = feats[0][:0]
+    feats[36] = feats[36][:1]
+    init = [sorted(set(int(x) for x in rs.randint(0, m.n_sen, size=rs.randint(0, 5))))
+            for _ in range(37)]
+    one = ssb.align_batch(m, feats, chains, init_active=init, compallsen=compallsen,
+                          want_chain_scr=True, want_tokens=True)
+    pipe = ssb.AlignPipeline(m, n_lanes=3, chunk_frames=150)
+    for rep in range(2):
+        pipe.upload(feats, chains, init_active=init, compallsen=compallsen)
+        got = pipe.per_utt(pipe.align(want_chain_scr=True, want_tokens=True))
+        assert pipe.n_chunks() >= 6 and pipe.n_launches() >= 4 * pipe.n_chunks()
+        for u, (a, b) in enumerate(zip(got, one)):
+            assert a["rv"] == b["rv"] and a["best_score"] == b["best_score"], u
+            assert a["n_renorm"] == b["n_renorm"], u
+            for k in ("start", "dur", "score", "chain_scr", "tokens"):
+                assert np.array_equal(a[k], b[k]), (u, k)
+    pipe.close()
+    n_ok = 0
+    for u, (f, c, r) in enumerate(zip(feats, chains, got)):
+        w = o.state_align(f, c["ssid"], c["tmat"], c["sf"], c["ef"], compallsen=compallsen,
+                          init_active=init[u], want_tokens=True)
+        assert r["rv"] == w["rv"], u
+        if f.shape[0]:
+            assert np.array_equal(r["tokens"], w["tokens"]), u
+        if w["rv"] == 0:
+            n_ok += 1
+            assert np.array_equal(r["start"], w["start"]) and np.array_equal(r["dur"], w["dur"]), u
+            assert np.array_equal(r["score"], w["score"]), u
+    assert n_ok >= 8
+
+
+def test_align_batch_routes_large_batches_through_pipeline(models, oracles, monkeypatch):
+    m, o = models("en-us"), oracles("en-us")
+    rs = np.random.RandomState(5)
+    feats, chains = _random_batch(rs, o, 20)
+    one = ssb.align_batch(m, feats, chains)
+    monkeypatch.setenv("SSB_PIPE_CHUNK_FRAMES", "64")
+    monkeypatch.setenv("SSB_PIPE_LANES", "2")
+    got = ssb.align_batch(m, feats, chains)
+    for a, b in zip(got, one):
+        assert a["rv"] == b["rv"] and a["best_score"] == b["best_score"]
+        for k in ("start", "dur", "score"):
+            assert np.array_equal(a[k], b[k])
+
+
 def test_align_init_active_senones(models, oracles, golden):
     """Pass 2 starts with whatever pass 1 left flagged (ref: src/state_align_search.c:186-188)."""
     m, o, g = models("en-us"), oracles("en-us"), golden["en-us"]
