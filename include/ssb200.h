@@ -300,6 +300,7 @@ const char *ssb_lexicon_wordstr(const ssb_lexicon_t *lx, int32_t wid);
 /* CI phones of a word; returns the pronunciation length */
 int32_t ssb_lexicon_pron(const ssb_lexicon_t *lx, int32_t wid, int32_t *ciphones, int32_t max);
 int32_t ssb_lexicon_is_filler(const ssb_lexicon_t *lx, int32_t wid);     /* dict_filler_word */
+int32_t ssb_lexicon_basewid(const ssb_lexicon_t *lx, int32_t wid);       /* dict_basewid */
 /* replaces alignment_populate (ref: src/ps_alignment.c:133-248): per phone of the word
  * sequence its senone-sequence id, transition matrix, CI phone and parent word index (any
  * output may be NULL).  Returns the number of phones, -1 on error. */
@@ -329,7 +330,79 @@ ssb_fsg_built_t *ssb_fsg_build_align(const ssb_lexicon_t *lx, const char *text,
 const ssb_fsg_graph_t *ssb_fsg_built_graph(const ssb_fsg_built_t *b);
 int32_t ssb_fsg_built_n_words(const ssb_fsg_built_t *b);
 const char *ssb_fsg_built_word(const ssb_fsg_built_t *b, int32_t fsg_wid, int32_t *dict_wid);
+int32_t ssb_fsg_built_is_filler(const ssb_fsg_built_t *b, int32_t fsg_wid); /* fsg_model_is_filler */
 void ssb_fsg_built_free(ssb_fsg_built_t *b);
+
+/* ------------------------------------------------------------------ search-module drop-in
+ * Objects with the layout and the vtable of the reference's search_module_t / seg_iter_t
+ * (ref: include/soundswallower/search_module.h:72-113, 157-174) for the two searches on the
+ * path: state_align_search (ref: src/state_align_search.c:46-474) and fsg_search
+ * (ref: src/fsg_search.c:171-260, 664-851, 945-1142).  search_module_forward's loop
+ * (ref: src/decoder.c:935-957) and decoder_end_utt / decoder_hyp / decoder_seg_iter work on
+ * them unchanged through the macros of search_module.h.  step() collects the frame's feature
+ * vector; finish() runs the utterance through the batched kernels; hyp / seg_iter / the
+ * alignment entries are then served from the results. */
+typedef struct ssb_search_s ssb_search_t;
+typedef struct ssb_seg_iter_s ssb_seg_iter_t;
+typedef struct ssb_searchfuncs_s { /* searchfuncs_t, ref: search_module.h:72-84 */
+    int (*start)(ssb_search_t *search);
+    int (*step)(ssb_search_t *search, int frame_idx); /* aligner: 0, grammar search: 1, error < 0 */
+    int (*finish)(ssb_search_t *search);              /* aligner: -1 "Failed to reach final state" */
+    int (*reinit)(ssb_search_t *search, void *dict, void *d2p);
+    void (*free)(ssb_search_t *search);
+    void *(*lattice)(ssb_search_t *search);           /* NULL: no lattice on this path */
+    const char *(*hyp)(ssb_search_t *search, int32_t *out_score);
+    int32_t (*prob)(ssb_search_t *search);            /* NULL, as for the reference's aligner */
+    ssb_seg_iter_t *(*seg_iter)(ssb_search_t *search);
+} ssb_searchfuncs_t;
+struct ssb_search_s { /* search_module_t field for field, ref: search_module.h:89-113 */
+    ssb_searchfuncs_t *vt;
+    char *type; /* "state_align" | "fsg" */
+    char *name;
+    void *config;
+    void *acmod; /* handed back to the feature source */
+    void *dict;  /* the ssb_lexicon_t */
+    void *d2p;
+    char *hyp_str;
+    void *dag;
+    void *last_link;
+    int32_t post;
+    int32_t n_words;
+    int32_t start_wid, silence_wid, finish_wid;
+};
+typedef struct ssb_segfuncs_s { /* ps_segfuncs_t, ref: search_module.h:157-160 */
+    ssb_seg_iter_t *(*seg_next)(ssb_seg_iter_t *seg); /* frees the iterator and returns NULL at the end */
+    void (*seg_free)(ssb_seg_iter_t *seg);
+} ssb_segfuncs_t;
+struct ssb_seg_iter_s { /* seg_iter_t, ref: search_module.h:165-174 */
+    ssb_segfuncs_t *vt;
+    ssb_search_t *search;
+    const char *word;
+    int32_t sf, ef;
+    int32_t ascr, lscr, prob;
+};
+/* The frame's feature vector ([sum featlen] fp32, what acmod_score scores for frame_idx,
+ * ref: src/acmod.c:822-860); NULL when the frame is not available.  With a NULL source the
+ * search reads the frames given to ssb_search_feed. */
+typedef const float *(*ssb_feat_source_fn)(void *acmod, int frame_idx);
+/* replaces state_align_search_init (ref: src/state_align_search.c:429-474) for the alignment
+ * whose word level is (wids, wstart, wdur) -- pass 1's words with their frame windows, 0/0 =
+ * no window; the phone and state levels are populated as alignment_populate does. */
+ssb_search_t *ssb_state_align_search_init(const char *name, ssb_model_t *m, const ssb_lexicon_t *lx,
+                                          const int32_t *wids, const int32_t *wstart,
+                                          const int32_t *wdur, int32_t n_words,
+                                          ssb_feat_source_fn src, void *acmod);
+/* replaces fsg_search_init (ref: src/fsg_search.c:171-260); consumes `fsg` like the reference */
+ssb_search_t *ssb_fsg_search_init(const char *name, ssb_model_t *m, const ssb_lexicon_t *lx,
+                                  ssb_fsg_built_t *fsg, ssb_feat_source_fn src, void *acmod);
+/* appends frames to the search's own feature buffer (the NULL-source case); returns the
+ * number of frames held */
+int ssb_search_feed(ssb_search_t *search, const float *feat, int32_t n_frames);
+/* alignment_words / alignment_phones / alignment_states of the aligner's alignment
+ * (level 0 / 1 / 2, ref: src/ps_alignment.c:357-420): [n][5] = id (word id | CI phone |
+ * senone), start, duration, score, parent; returns the number of entries at that level */
+int32_t ssb_search_alignment(const ssb_search_t *search, int32_t level, int32_t *out5,
+                             int32_t max_entries);
 
 /* ------------------------------------------------------------------ frontend
  * Batched PCM -> MFCC -> CMN -> dynamic features for whole utterances: what

@@ -831,6 +831,130 @@ def _lexicon_align_graph(self, text, **cfg):
 Lexicon.align_graph = _lexicon_align_graph
 
 
+# ---------------------------------------------------------------------------- search drop-in
+class Search:
+    """A search object behind the reference's search_module_t interface
+    (ref: include/soundswallower/search_module.h:72-113): every method below goes through the
+    object's own vtable, the way the search_module_* macros do.  Features come either from a
+    `source(frame_idx) -> 39 floats or None` callable (the part acmod plays in the reference)
+    or from feed()."""
+
+    def __init__(self, model, lexicon, ptr, source=None, cb=None):
+        if not ptr:
+            raise SsbError("search init: " + _lib.last_error())
+        self.model, self.lexicon = model, lexicon
+        self.ptr = C.c_void_p(ptr)
+        self.base = C.cast(self.ptr, C.POINTER(_lib.SearchBase)).contents
+        self.vt = self.base.vt.contents
+        self._cb, self._source = cb, source
+
+    @staticmethod
+    def _make_source(model, source):
+        if source is None:
+            return None, None
+        hold = {}
+
+        def get(_ctx, frame_idx):
+            x = source(int(frame_idx))
+            if x is None:
+                return None
+            hold["x"] = np.ascontiguousarray(x, np.float32).reshape(model.blk)
+            return hold["x"].ctypes.data
+        return _lib.FEAT_SOURCE_FN(get), hold
+
+    type = property(lambda self: self.base.type.decode())
+    name = property(lambda self: self.base.name.decode())
+
+    def feed(self, feat):
+        feat = np.ascontiguousarray(feat, np.float32).reshape(-1, self.model.blk)
+        return _lib.check(int(self.model.lib.ssb_search_feed(self.ptr, _ptr(feat), len(feat))),
+                          "ssb_search_feed")
+
+    def start(self):
+        return int(self.vt.start(self.ptr))
+
+    def step(self, frame_idx):
+        return int(self.vt.step(self.ptr, int(frame_idx)))
+
+    def finish(self):
+        return int(self.vt.finish(self.ptr))
+
+    def forward(self, feat):
+        """search_module_forward over a whole utterance (ref: src/decoder.c:935-957)."""
+        self.feed(feat)
+        n = 0
+        for t in range(len(feat)):
+            if self.step(t) < 0:
+                raise SsbError("search step: " + _lib.last_error())
+            n += 1
+        return n
+
+    def hyp(self):
+        """(hypothesis string or None, score)"""
+        sc = C.c_int32(0)
+        h = self.vt.hyp(self.ptr, C.byref(sc))
+        return (h.decode("utf-8") if h is not None else None), int(sc.value)
+
+    def seg(self):
+        """[(word, sf, ef, ascr, lscr)] through seg_iter / seg_next."""
+        out = []
+        it = self.vt.seg_iter(self.ptr)
+        while it:
+            s = C.cast(C.c_void_p(it), C.POINTER(_lib.SegIter)).contents
+            out.append((s.word.decode("utf-8"), int(s.sf), int(s.ef), int(s.ascr), int(s.lscr)))
+            it = s.vt.contents.seg_next(it)
+        return out
+
+    def alignment(self, level):
+        """alignment_words/phones/states: int32 [n][5] id start duration score parent."""
+        lvl = {"words": 0, "phones": 1, "states": 2}[level]
+        n = _lib.check(int(self.model.lib.ssb_search_alignment(self.ptr, lvl, None, 0)), "ssb_search_alignment")
+        out = np.zeros((n, 5), np.int32)
+        self.model.lib.ssb_search_alignment(self.ptr, lvl, _ptr(out), n)
+        return out
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.vt.free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def state_align_search(model, lexicon, wids, wstart=None, wdur=None, name="_state_align", source=None):
+    """state_align_search_init (ref: src/state_align_search.c:429-474)."""
+    wids = np.ascontiguousarray(wids, np.int32)
+    ws = np.ascontiguousarray(wstart if wstart is not None else np.zeros(len(wids)), np.int32)
+    wd = np.ascontiguousarray(wdur if wdur is not None else np.zeros(len(wids)), np.int32)
+    cb, hold = Search._make_source(model, source)
+    p = model.lib.ssb_state_align_search_init(name.encode(), model.h, lexicon.h, _ptr(wids), _ptr(ws),
+                                              _ptr(wd), len(wids), C.cast(cb, C.c_void_p) if cb else None,
+                                              None)
+    return Search(model, lexicon, p, hold, cb)
+
+
+def fsg_search(model, lexicon, text, name="_default", source=None, **cfg):
+    """decoder_set_align_text + fsg_search_init (ref: src/decoder.c:685-735,
+    src/fsg_search.c:171-260) for the alignment grammar of `text`."""
+    c = _lib.FsgConfig()
+    model.lib.ssb_fsg_config_defaults(C.byref(c))
+    for k, v in cfg.items():
+        if not hasattr(c, k):
+            raise SsbError("unknown search parameter " + k)
+        setattr(c, k, v)
+    b = model.lib.ssb_fsg_build_align(lexicon.h, text.encode("utf-8"), C.byref(c))
+    if not b:
+        raise SsbError("ssb_fsg_build_align: " + _lib.last_error())
+    cb, hold = Search._make_source(model, source)
+    p = model.lib.ssb_fsg_search_init(name.encode(), model.h, lexicon.h, C.c_void_p(b),
+                                      C.cast(cb, C.c_void_p) if cb else None, None)
+    return Search(model, lexicon, p, hold, cb)
+
+
 # ---------------------------------------------------------------------------- two-pass alignment
 def align_texts(model, lexicon, feats, texts, **search_cfg):
     """The reference's forced alignment of `soundswallower --align` for a batch of

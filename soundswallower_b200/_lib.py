@@ -92,6 +92,42 @@ class MgauBase(C.Structure):
     _fields_ = [("vt", C.POINTER(MgauFuncs)), ("frame_idx", C.c_int)]
 
 
+SEARCH_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
+SEARCH_STEP_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int)
+SEARCH_HYP_FN = C.CFUNCTYPE(C.c_char_p, C.c_void_p, C.POINTER(C.c_int32))
+SEARCH_SEG_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p)
+SEARCH_FREE_FN = C.CFUNCTYPE(None, C.c_void_p)
+FEAT_SOURCE_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int)
+
+
+class SearchFuncs(C.Structure):
+    """ssb_searchfuncs_t == searchfuncs_t (ref: include/soundswallower/search_module.h:72-84)."""
+    _fields_ = [("start", SEARCH_FN), ("step", SEARCH_STEP_FN), ("finish", SEARCH_FN),
+                ("reinit", C.c_void_p), ("free", SEARCH_FREE_FN), ("lattice", C.c_void_p),
+                ("hyp", SEARCH_HYP_FN), ("prob", C.c_void_p), ("seg_iter", SEARCH_SEG_FN)]
+
+
+class SearchBase(C.Structure):
+    """ssb_search_t == search_module_t (ref: search_module.h:89-113)."""
+    _fields_ = [("vt", C.POINTER(SearchFuncs)), ("type", C.c_char_p), ("name", C.c_char_p),
+                ("config", C.c_void_p), ("acmod", C.c_void_p), ("dict", C.c_void_p),
+                ("d2p", C.c_void_p), ("hyp_str", C.c_char_p), ("dag", C.c_void_p),
+                ("last_link", C.c_void_p), ("post", C.c_int32), ("n_words", C.c_int32),
+                ("start_wid", C.c_int32), ("silence_wid", C.c_int32), ("finish_wid", C.c_int32)]
+
+
+class SegFuncs(C.Structure):
+    """ssb_segfuncs_t == ps_segfuncs_t (ref: search_module.h:157-160)."""
+    _fields_ = [("seg_next", SEARCH_SEG_FN), ("seg_free", SEARCH_FREE_FN)]
+
+
+class SegIter(C.Structure):
+    """ssb_seg_iter_t == seg_iter_t (ref: search_module.h:165-174)."""
+    _fields_ = [("vt", C.POINTER(SegFuncs)), ("search", C.c_void_p), ("word", C.c_char_p),
+                ("sf", C.c_int32), ("ef", C.c_int32), ("ascr", C.c_int32), ("lscr", C.c_int32),
+                ("prob", C.c_int32)]
+
+
 # every symbol include/ssb200.h declares
 SYMBOLS = [
     "ssb_version", "ssb_last_error", "ssb_device_count", "ssb_config_defaults",
@@ -101,7 +137,8 @@ SYMBOLS = [
     "ssb_batch_download", "ssb_batch_debug_tokens", "ssb_batch_kernel_ms",
     "ssb_batch_n_launches", "ssb_batch_stats", "ssb_align_batch", "ssb_pipeline_create",
     "ssb_pipeline_align", "ssb_pipeline_n_launches", "ssb_pipeline_n_chunks", "ssb_pipeline_trace", "ssb_pipeline_free",
-    "ssb_score_batch",
+    "ssb_score_batch", "ssb_lexicon_basewid", "ssb_fsg_built_is_filler",
+    "ssb_state_align_search_init", "ssb_fsg_search_init", "ssb_search_feed", "ssb_search_alignment",
     "ssb_topn_batch", "ssb_tc_probe", "ssb_tc_hot_mask", "ssb_fsg_batch", "ssb_hmm_vit_eval",
     "ssb_fe_config_defaults", "ssb_fe_config_from_model", "ssb_frontend_create",
     "ssb_frontend_free", "ssb_frontend_dims", "ssb_frontend_n_frames", "ssb_frontend_tables",
@@ -189,6 +226,14 @@ def load():
     L.ssb_lexicon_wordstr.argtypes = [vp, i32]
     L.ssb_lexicon_pron.argtypes = [vp, i32, vp, i32]
     L.ssb_lexicon_is_filler.argtypes = [vp, i32]
+    L.ssb_lexicon_basewid.argtypes = [vp, i32]
+    L.ssb_fsg_built_is_filler.argtypes = [vp, i32]
+    L.ssb_state_align_search_init.restype = vp
+    L.ssb_state_align_search_init.argtypes = [C.c_char_p, vp, vp, vp, vp, vp, i32, vp, vp]
+    L.ssb_fsg_search_init.restype = vp
+    L.ssb_fsg_search_init.argtypes = [C.c_char_p, vp, vp, vp, vp, vp]
+    L.ssb_search_feed.argtypes = [vp, vp, i32]
+    L.ssb_search_alignment.argtypes = [vp, i32, vp, i32]
     L.ssb_chain_populate.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32]
     L.ssb_fsg_config_defaults.restype = None
     L.ssb_fsg_config_defaults.argtypes = [P(FsgConfig)]

@@ -318,6 +318,14 @@ extern "C" int32_t ssb_lexicon_pron(const ssb_lexicon_t *lx, int32_t wid, int32_
     return (int32_t)w.ph.size();
 }
 
+extern "C" int32_t ssb_lexicon_basewid(const ssb_lexicon_t *lx, int32_t wid)
+{
+    // dict_basewid: the first pronunciation of "word(2)" is "word"
+    if (!lx || wid < 0 || wid >= (int32_t)lx->word.size())
+        return -1;
+    return lx->word[wid].basewid;
+}
+
 extern "C" int32_t ssb_lexicon_is_filler(const ssb_lexicon_t *lx, int32_t wid)
 {
     // ref: src/dict.c:381-393
@@ -558,6 +566,7 @@ struct ssb_fsg_built_s {
     std::vector<uint8_t> link_flag;
     std::vector<uint32_t> ctxt;
     std::vector<std::string> vocab;
+    std::vector<uint8_t> silword;  // fsg_model_is_filler (ref: include/soundswallower/fsg_model.h)
 };
 
 extern "C" void ssb_fsg_config_defaults(ssb_fsg_config_t *c)
@@ -865,6 +874,7 @@ static ssb_fsg_built_t *fsg_finish(FsgWork &W, int start, int final)
         B->ctxt.insert(B->ctxt.end(), q.ctxt, q.ctxt + 4);
     }
     B->vocab = W.vocab;
+    B->silword = W.silword;
     B->dictwid = dictwid_of_word;
     ssb_fsg_graph_t &g = B->g;
     g.n_state = NS;
@@ -904,6 +914,13 @@ extern "C" const char *ssb_fsg_built_word(const ssb_fsg_built_t *b, int32_t fsg_
     if (dict_wid)
         *dict_wid = b->dictwid[fsg_wid];
     return b->vocab[fsg_wid].c_str();
+}
+
+extern "C" int32_t ssb_fsg_built_is_filler(const ssb_fsg_built_t *b, int32_t fsg_wid)
+{
+    if (!b || fsg_wid < 0 || fsg_wid >= (int32_t)b->silword.size())
+        return -1;
+    return b->silword[fsg_wid];
 }
 
 extern "C" void ssb_fsg_built_free(ssb_fsg_built_t *b) { delete b; }
