@@ -350,9 +350,9 @@ typedef struct ssb_searchfuncs_s { /* searchfuncs_t, ref: search_module.h:72-84 
     int (*finish)(ssb_search_t *search);              /* aligner: -1 "Failed to reach final state" */
     int (*reinit)(ssb_search_t *search, void *dict, void *d2p);
     void (*free)(ssb_search_t *search);
-    void *(*lattice)(ssb_search_t *search);           /* NULL: no lattice on this path */
+    void *(*lattice)(ssb_search_t *search);           /* aligner: NULL pointer; grammar search: returns NULL */
     const char *(*hyp)(ssb_search_t *search, int32_t *out_score);
-    int32_t (*prob)(ssb_search_t *search);            /* NULL, as for the reference's aligner */
+    int32_t (*prob)(ssb_search_t *search);            /* aligner: NULL pointer; grammar search: 0 (no bestpath) */
     ssb_seg_iter_t *(*seg_iter)(ssb_search_t *search);
 } ssb_searchfuncs_t;
 struct ssb_search_s { /* search_module_t field for field, ref: search_module.h:89-113 */

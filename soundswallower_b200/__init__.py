@@ -767,6 +767,10 @@ class Lexicon:
     def is_filler(self, wid):
         return bool(self.lib.ssb_lexicon_is_filler(self.h, int(wid)))
 
+    def basewid(self, wid):
+        """dict_basewid: the id of "word" for "word(2)"."""
+        return int(self.lib.ssb_lexicon_basewid(self.h, int(wid)))
+
     def populate(self, wids, start=None, dur=None):
         """Phone chain of a word sequence: dict(ssid, tmat, ci, parent[, sf, ef]) -- with
         word windows (start, dur) the sf/ef arrays state_align_search_init derives."""
@@ -1010,3 +1014,6 @@ def align_texts(model, lexicon, feats, texts, **search_cfg):
                            np.repeat(np.arange(len(ps), dtype=np.int32), E)], 1).astype(np.int32)
         out.append(dict(words=words, phones=phones, states=states, hyp_score=hyp))
     return out
+
+
+from .decoder import (Alignment, AlignmentEntry, Decoder, Hyp, Seg, get_audio_data)  # noqa: E402

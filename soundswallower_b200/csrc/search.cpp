@@ -386,10 +386,15 @@ void search_free(ssb_search_t *s)
     delete S;
 }
 
+// bestpath is off by default, so fsg_search_prob is 0 and there is no lattice
+// (ref: src/fsg_search.c:1145-1170)
+int32_t fsg_prob(ssb_search_t *) { return 0; }
+void *fsg_lattice(ssb_search_t *) { return nullptr; }
+
 ssb_searchfuncs_t g_align_funcs = {search_start, search_step, align_finish, search_reinit, search_free,
                                    nullptr, align_hyp, nullptr, search_seg_iter};
 ssb_searchfuncs_t g_fsg_funcs = {search_start, search_step, fsg_finish, search_reinit, search_free,
-                                 nullptr, fsg_hyp, nullptr, search_seg_iter};
+                                 fsg_lattice, fsg_hyp, fsg_prob, search_seg_iter};
 
 SearchImpl *new_search(int kind, const char *type, const char *name, ssb_model_t *m,
                        const ssb_lexicon_t *lx, ssb_feat_source_fn src, void *acmod)

@@ -42,7 +42,7 @@ def test_host_side_protocol(host):
     assert s.base.n_words == len(lx)
     assert [s.base.start_wid, s.base.finish_wid, s.base.silence_wid] == \
         [lx.wordid(w) for w in ("<s>", "</s>", "<sil>")]
-    assert s.vt.lattice is None and s.vt.prob is None       # as for the reference's aligner
+    assert s.vt.lattice and s.vt.prob                        # fsg_search_lattice / fsg_search_prob
     assert s.start() == 0
     assert s.step(0) == -1 and "not been fed" in _lib.last_error()
     s.feed(np.zeros((3, m.blk), np.float32))
@@ -62,6 +62,7 @@ def test_aligner_entries_before_the_search(host):
     wids = [lx.wordid(w) for w in ("<sil>", "go", "the(2)", "<sil>")]
     a = ssb.state_align_search(m, lx, wids, [0, 10, 20, 50], [10, 10, 30, 5])
     assert a.type == "state_align"
+    assert not a.vt.lattice and not a.vt.prob                # NULL in the reference's vtable too
     w, p, st = a.alignment("words"), a.alignment("phones"), a.alignment("states")
     assert w[:, 0].tolist() == wids and w[:, 1].tolist() == [0, 10, 20, 50]
     c = lx.populate(wids)
