@@ -263,6 +263,12 @@ typedef struct ssb_fsg_in_s {
     const int32_t *utt_graph; /* [n_utts] graph searched for each utterance */
     int32_t hist_cap;         /* history entries kept per utterance (overflow: utt_rv = -2) */
     int32_t max_seg;          /* segmentation entries returned per utterance */
+    /* config key "compallsen" negated: 0 = every senone is scored on every frame (compallsen =
+     * yes), 1 = the reference's default: only the senones of the active HMMs are scored, frame
+     * by frame inside the search (fsg_search_sen_active + acmod_score with an active list, ref:
+     * src/fsg_search.c:309-328, 686-690) -- path scores then equal the default CLI's.  PTM
+     * models with 128 densities only. */
+    int32_t active_lists;
 } ssb_fsg_in_t;
 
 typedef struct ssb_fsg_out_s {
@@ -276,6 +282,12 @@ typedef struct ssb_fsg_out_s {
     int32_t *hist9;      /* optional [n_utts][hist_cap][9] link score pred frame lc rc[4] */
     float *kernel_ms;    /* optional [4] gmm_topn, senone_mix, fsg_search, backtrace */
     int32_t n_launches;  /* kernels launched (written by the call) */
+    /* active_lists = 1 only, optional: acmod's active-senone flags as the last frame left them,
+     * [n_utts][(n_sen+31)/32] -- hand them to ssb_align_in_t.init_active for the second pass,
+     * which never clears them (ref: src/state_align_search.c:186-188); and the number of
+     * senones evaluated per utterance (fsgs->n_sen_eval) */
+    uint32_t *final_active;
+    int64_t *n_sen_eval;
 } ssb_fsg_out_t;
 /* Dense ("compallsen") senone scoring + search + backtrace of a batch of utterances. */
 int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out_t *out);

@@ -262,6 +262,36 @@ class Oracle:
         return dict(rv=rv, hist=hist, n_hmm_eval=int(out[1]), n_frames=int(out[2]), exit=bp,
                     hyp_score=int(score.value), segs=segs[:max(ns, 0)].copy())
 
+    def fsg_search_active(self, G, feat, topn=4, cap=1 << 16):
+        """The same search in the reference's default mode (compallsen = no): scores computed
+        frame by frame for the active HMMs' senones.  Adds `active` (acmod's flags after the
+        last frame, uint32 words) and n_sen_eval."""
+        feat = np.ascontiguousarray(feat, np.float32)
+        T = feat.shape[0]
+        f, keep = self._fsg_struct(G)
+        hist = np.zeros((cap, 9), np.int32)
+        out = np.zeros(8, np.int64)
+        active = np.zeros((self.n_sen + 31) // 32, np.uint32)
+        L = self.lib
+        L.orc_fsg_search_active.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                            C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        rv = L.orc_fsg_search_active(self.h, topn, C.byref(f), feat.ctypes.data, T, hist.ctypes.data,
+                                     cap, out.ctypes.data, active.ctypes.data)
+        n = int(out[0])
+        hist = hist[:n].copy()
+        score = C.c_int32(0)
+        L.orc_fsg_find_exit.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        bp = L.orc_fsg_find_exit(C.byref(f), hist.ctypes.data, n, int(out[2]), 1, C.byref(score))
+        segs = np.zeros((4096, 5), np.int32)
+        ns = 0
+        if bp > 0:
+            L.orc_fsg_segs.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+            ns = L.orc_fsg_segs(C.byref(f), hist.ctypes.data, bp, segs.ctypes.data, 4096)
+        del keep
+        return dict(rv=rv, hist=hist, n_hmm_eval=int(out[1]), n_frames=int(out[2]), exit=bp,
+                    hyp_score=int(score.value), segs=segs[:max(ns, 0)].copy(), active=active,
+                    n_sen_eval=int(out[3]))
+
     def propagate(self, start, dur, score):
         n = len(start)
         E = self.n_emit

@@ -607,6 +607,23 @@ ref_fsg_decode(void *h, const float *feat, int T, const char *align_text,
     return n;
 }
 
+/* acmod's active-senone flags as they stand (after an fsg decode in the default mode: the
+ * senones of the last frame's active HMMs); out = (n_sen+31)/32 words.  Also the number of
+ * senones the last grammar search evaluated (fsgs->n_sen_eval) when it is an fsg search. */
+int
+ref_active_bits(void *h, uint32 *out, int32 *n_sen_eval)
+{
+    ref_t *r = h;
+    acmod_t *a = r->d->acmod;
+    int n_sen = bin_mdef_n_sen(a->mdef), i;
+    for (i = 0; i < (n_sen + 31) / 32; ++i)
+        out[i] = a->senone_active_vec[i];
+    if (n_sen_eval && r->d->search
+        && 0 == strcmp(search_module_type(r->d->search), PS_SEARCH_TYPE_FSG))
+        *n_sen_eval = ((fsg_search_t *)r->d->search)->n_sen_eval;
+    return 0;
+}
+
 /* One hmm_vit_eval on caller-provided state (3- or 5-state, non-mpx).
  * st: score[5] history[5] out_score out_history (12 int32), in/out. */
 int

@@ -241,6 +241,13 @@ class Ref:
         assert rv >= 0, rv
         return dict(segs=segs[:rv].copy(), hyp_score=int(n_out[4]), n_frames=int(n_out[5]))
 
+    def active_bits(self):
+        """(acmod's active-senone flags as uint32 words, senones evaluated by the last fsg search)"""
+        out = np.zeros((self.n_sen + 31) // 32, np.uint32)
+        n = C.c_int32(0)
+        assert self.lib.ref_active_bits(self.h, _p(out, C.c_uint32), C.byref(n)) == 0
+        return out, int(n.value)
+
     def hmm_vit_eval(self, n_emit, tmatid, senid, senscr, st):
         senid = np.ascontiguousarray(senid, np.uint16)
         senscr = np.ascontiguousarray(senscr, np.int16)

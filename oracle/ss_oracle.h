@@ -142,6 +142,8 @@ typedef struct orc_fsg_s {
 } orc_fsg_t;
 int orc_fsg_search(const orc_model_t *m, const orc_fsg_t *g, const int16_t *senscr, int T,
                    int32_t *hist9, int cap, int64_t *out);
+int orc_fsg_search_active(const orc_model_t *m, int topn, const orc_fsg_t *g, const float *feat, int T,
+                          int32_t *hist9, int cap, int64_t *out, uint32_t *active_out);
 int orc_fsg_find_exit(const orc_fsg_t *g, const int32_t *hist9, int n_hist, int frame_idx, int final,
                       int32_t *out_score);
 int orc_fsg_segs(const orc_fsg_t *g, const int32_t *hist9, int bpidx, int32_t *segs, int max_seg);

@@ -51,6 +51,14 @@ typedef struct {
     float beam_factor;
     int64_t n_hmm_eval;
     int overflow;
+    /* active-list mode (the reference's default, compallsen = no): scores are computed frame
+     * by frame for the senones of the active HMMs only (ref: src/fsg_search.c:309-328, 686-690) */
+    orc_ptm_t *ptm;
+    const float *feat;
+    uint32_t *bits;   /* acmod's senone_active_vec; left as the last frame set it */
+    uint8_t *list;
+    int16_t *scr;
+    int64_t n_sen_eval;
 } fs_t;
 
 #define PN(g, i, k) ((g)->pnode8[(i) * 8 + (k)])
@@ -275,8 +283,23 @@ fsg_run(const orc_model_t *m, const orc_fsg_t *g, const int16_t *senscr, int T, 
     s->n_nxt = 0;
     s->frame = 0;
     for (t = 0; t < T; ++t) {
-        const int16_t *ss = senscr + (size_t)t * m->n_sen;
+        const int16_t *ss = senscr ? senscr + (size_t)t * m->n_sen : s->scr;
         int32_t thresh, phone_thresh, word_thresh;
+        if (!senscr) {
+            /* fsg_search_sen_active (ref :309-328): acmod_clear_active, then acmod_activate_hmm
+             * for every HMM of the active list; acmod_score -> acmod_flags2list -> frame_eval
+             * (ref: src/acmod.c:822-860, 889-999) */
+            int n_list, k;
+            memset(s->bits, 0, sizeof(uint32_t) * ((m->n_sen + 31) / 32));
+            for (i = 0; i < s->n_act; ++i) {
+                const uint16_t *sid = m->sseq + (size_t)PN(g, s->act[i], 0) * E;
+                for (k = 0; k < E; ++k)
+                    s->bits[sid[k] >> 5] |= 1u << (sid[k] & 31);
+            }
+            n_list = orc_flags2list(s->bits, m->n_sen, s->list);
+            orc_ptm_frame_eval(s->ptm, s->scr, s->list, n_list, s->feat + (size_t)t * m->blk, t, 0, NULL);
+            s->n_sen_eval += n_list;
+        }
         s->bpidx_start = s->n_hist;
         /* fsg_search_hmm_eval (ref :330-398) */
         if (s->n_act > 0) {
@@ -448,6 +471,51 @@ orc_fsg_search(const orc_model_t *m, const orc_fsg_t *g, const int16_t *senscr, 
     out[0] = s.n_hist;
     out[1] = s.n_hmm_eval;
     out[2] = s.frame;
+    free(s.hist);
+    return rv;
+}
+
+/* The same search in the reference's default mode (compallsen = no): senone scores are
+ * computed frame by frame by the PTM scorer for the active HMMs' senones only.  `active_out`
+ * (optional, (n_sen+31)/32 words) receives acmod's active-senone flags as the last frame left
+ * them -- what a following state_align_search starts with (ref: src/state_align_search.c:
+ * 186-188 never clears them).  out[3] = senones evaluated (fsgs->n_sen_eval). */
+int
+orc_fsg_search_active(const orc_model_t *m, int topn, const orc_fsg_t *g, const float *feat, int T,
+                      int32_t *hist9, int cap, int64_t *out, uint32_t *active_out)
+{
+    fs_t s;
+    int i, rv, nw = (m->n_sen + 31) / 32;
+    if (m->kind != ORC_KIND_PTM)
+        return -1;
+    memset(&s, 0, sizeof(s));
+    s.hist = malloc(sizeof(hent_t) * (cap > 0 ? cap : 1));
+    s.cap = cap;
+    s.ptm = orc_ptm_new(m, topn, 1);
+    s.feat = feat;
+    s.bits = calloc(nw, sizeof(uint32_t));
+    s.list = malloc(m->n_sen + 16);
+    s.scr = calloc(m->n_sen, sizeof(int16_t));
+    rv = fsg_run(m, g, NULL, T, &s);
+    for (i = 0; i < s.n_hist; ++i) {
+        int32_t *o = hist9 + (size_t)i * 9;
+        o[0] = s.hist[i].link;
+        o[1] = s.hist[i].score;
+        o[2] = s.hist[i].pred;
+        o[3] = s.hist[i].frame;
+        o[4] = s.hist[i].lc;
+        memcpy(o + 5, s.hist[i].rc, 16);
+    }
+    out[0] = s.n_hist;
+    out[1] = s.n_hmm_eval;
+    out[2] = s.frame;
+    out[3] = s.n_sen_eval;
+    if (active_out)
+        memcpy(active_out, s.bits, sizeof(uint32_t) * nw);
+    orc_ptm_free(s.ptm);
+    free(s.bits);
+    free(s.list);
+    free(s.scr);
     free(s.hist);
     return rv;
 }

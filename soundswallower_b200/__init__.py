@@ -507,7 +507,8 @@ def tc_probe(model, feats):
     return cw, sc, approx, eps, dict(hot=hot, eps_regular=eps2[..., 0], exact_evals=int(cnt[0]), scan_steps=int(cnt[1]), slow_steps=int(cnt[2]))
 
 
-def fsg_batch(model, feats, graphs, utt_graph=None, hist_cap=4096, max_seg=256, want_hist=False):
+def fsg_batch(model, feats, graphs, utt_graph=None, hist_cap=4096, max_seg=256, want_hist=False,
+              compallsen=True):
     """fsg_search over a batch (first pass / grammar decoding) on dense senone scores.
 
     graphs: list of dicts with the flattened FSG + lextree (keys n_state start final n_ciphone
@@ -515,7 +516,12 @@ def fsg_batch(model, feats, graphs, utt_graph=None, hist_cap=4096, max_seg=256, 
     fsg_model_t / fsg_lextree_t, see ssb_fsg_graph_t).  utt_graph[u] = graph of utterance u
     (default: all use graph 0).  Returns a list of per-utterance dicts: segs [n][5] (link sf ef
     ascr lscr), hyp_score, exit, rv, n_hist, n_hmm_eval[, hist [n_hist][9]] and, on the first
-    one, kernel_ms / n_launches of the call."""
+    one, kernel_ms / n_launches of the call.
+
+    compallsen=False is the reference's default mode: only the senones of the active HMMs are
+    scored, frame by frame inside the search; each result then also carries `active` (acmod's
+    active-senone flags after the last frame, uint32 words: the second pass' init_active) and
+    n_sen_eval."""
     fptr, off, _keep_feat = _flat_feats(model, feats)
     U = len(off) - 1
     ug = np.zeros(U, np.int32) if utt_graph is None else np.ascontiguousarray(utt_graph, np.int32)
@@ -540,6 +546,7 @@ def fsg_batch(model, feats, graphs, utt_graph=None, hist_cap=4096, max_seg=256, 
     fin.n_utts, fin.feat, fin.frame_off = U, fptr, off.ctypes.data
     fin.n_graphs, fin.graphs, fin.utt_graph = len(graphs), garr, ug.ctypes.data
     fin.hist_cap, fin.max_seg = int(hist_cap), int(max_seg)
+    fin.active_lists = 0 if compallsen else 1
     segs = np.zeros((U, max_seg, 5), np.int32)
     n_seg, score, exit_bp, rv, n_hist = (np.zeros(U, np.int32) for _ in range(5))
     n_eval = np.zeros(U, np.int64)
@@ -550,6 +557,11 @@ def fsg_batch(model, feats, graphs, utt_graph=None, hist_cap=4096, max_seg=256, 
     fo.utt_rv, fo.n_hist, fo.n_hmm_eval = rv.ctypes.data, n_hist.ctypes.data, n_eval.ctypes.data
     fo.hist9 = hist.ctypes.data if hist is not None else None
     fo.kernel_ms = ms.ctypes.data
+    nw = (model.n_sen + 31) // 32
+    fact = np.zeros((U, nw), np.uint32) if not compallsen else None
+    nsen = np.zeros(U, np.int64) if not compallsen else None
+    fo.final_active = fact.ctypes.data if fact is not None else None
+    fo.n_sen_eval = nsen.ctypes.data if nsen is not None else None
     _lib.check(model.lib.ssb_fsg_batch(model.h, C.byref(fin), C.byref(fo)), "ssb_fsg_batch")
     out = []
     for u in range(U):
@@ -557,6 +569,8 @@ def fsg_batch(model, feats, graphs, utt_graph=None, hist_cap=4096, max_seg=256, 
                  exit=int(exit_bp[u]), rv=int(rv[u]), n_hist=int(n_hist[u]), n_hmm_eval=int(n_eval[u]))
         if hist is not None:
             d["hist"] = hist[u, :int(n_hist[u])].copy()
+        if fact is not None:
+            d["active"], d["n_sen_eval"] = fact[u].copy(), int(nsen[u])
         out.append(d)
     if out:
         out[0]["kernel_ms"] = dict(gmm_topn=float(ms[0]), senone_mix=float(ms[1]), fsg_search=float(ms[2]),

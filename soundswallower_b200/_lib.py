@@ -67,14 +67,14 @@ class FsgGraph(C.Structure):
 class FsgIn(C.Structure):
     _fields_ = [("n_utts", C.c_int32), ("feat", C.c_void_p), ("frame_off", C.c_void_p),
                 ("n_graphs", C.c_int32), ("graphs", C.POINTER(FsgGraph)), ("utt_graph", C.c_void_p),
-                ("hist_cap", C.c_int32), ("max_seg", C.c_int32)]
+                ("hist_cap", C.c_int32), ("max_seg", C.c_int32), ("active_lists", C.c_int32)]
 
 
 class FsgOut(C.Structure):
     _fields_ = [("segs", C.c_void_p), ("n_seg", C.c_void_p), ("hyp_score", C.c_void_p),
                 ("exit_bp", C.c_void_p), ("utt_rv", C.c_void_p), ("n_hist", C.c_void_p),
                 ("n_hmm_eval", C.c_void_p), ("hist9", C.c_void_p), ("kernel_ms", C.c_void_p),
-                ("n_launches", C.c_int32)]
+                ("n_launches", C.c_int32), ("final_active", C.c_void_p), ("n_sen_eval", C.c_void_p)]
 
 
 MGAU_FRAME_EVAL = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int16), C.POINTER(C.c_uint8),

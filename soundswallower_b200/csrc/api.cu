@@ -617,7 +617,7 @@ struct ssb_batch_s {
         d_ep_cbmask, d_ep_slot_off, d_ep_slot, d_us_off, d_usen, d_st_slot, d_enter;
     DBuf st_start, st_dur, st_score, utt_rv, utt_best, utt_renorm, fin_hist, fin_score;
     DBuf dense, best_tmp;
-    DevPlan plan;
+    DevPlan plan{};
     int64_t spill_stride = 0;
     // timing
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -1061,6 +1061,8 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
     p.st_slot = b->d_st_slot.as<uint16_t>();
     p.enter_plan = b->d_enter.as<int32_t>();
     p.all_active = b->compallsen;
+    p.tie_bits = nullptr;
+    p.tie_w = 0;
     return 0;
 }
 
@@ -1833,11 +1835,23 @@ extern "C" int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out
         ws_off[u + 1] = ws_off[u] + (int64_t)d.n_pnode * (FSG_PH + 2) + (int64_t)d.n_state * d.n_ciphone
                         + tent_cap + (int64_t)tent_cap * FSG_TE;
     }
+    // mode "compallsen = no": scores are computed inside the search kernel
+    const bool active = in->active_lists != 0;
+    std::vector<int64_t> aws_off(U + 1, 0);
+    if (active) {
+        if (!tc_supported(m->d) || (getenv("SSB_K1") && *getenv("SSB_K1"))) {
+            set_error("ssb_fsg_batch: active lists need the tensor-core top-N kernel (a PTM model "
+                      "with 128 densities, SSB_K1 unset); use active_lists = 0 (compallsen)");
+            return -1;
+        }
+        for (int u = 0; u < U; ++u)
+            aws_off[u + 1] = aws_off[u] + (int64_t)fsg_active_ws_ints(m->d, hdr[utt_graph[u]].n_pnode);
+    }
     ssb_batch_t *b = ssb_batch_create(m, nullptr);
     if (!b)
         return -1;
     DBuf d_hdr, d_link4, d_flag, d_arc, d_root, d_pnode, d_ctxt, d_ug, d_wsoff, d_ws, d_hist, d_nhist,
-        d_neval, d_frames, d_rv, d_exit, d_score, d_segs, d_nseg;
+        d_neval, d_frames, d_rv, d_exit, d_score, d_segs, d_nseg, d_awsoff, d_aws, d_tie, d_fact, d_nsen;
     int rv = -1;
     do {
         if (score_prepare(b, in->feat, in->frame_off, U) != 0)
@@ -1862,10 +1876,23 @@ extern "C" int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out
         gs.root = d_root.as<int32_t>();
         gs.pnode8 = d_pnode.as<int32_t>();
         gs.ctxt = d_ctxt.as<uint32_t>();
+        const int nw_sen = (h.n_sen + 31) / 32;
+        const int64_t tie_w = (G + 31) / 32 + 1;
+        DevPlan plan = b->plan;
+        if (active) {
+            const size_t tie_bytes = (size_t)h.n_mgau * h.n_feat * tie_w * 4;
+            if (upload(d_awsoff, aws_off, st) || d_aws.ensure(std::max<size_t>((size_t)aws_off[U] * 4, 16))
+                || d_tie.ensure(tie_bytes) || d_fact.ensure((size_t)U * nw_sen * 4)
+                || d_nsen.ensure((size_t)U * 8)
+                || cudaMemsetAsync(d_tie.p, 0, tie_bytes, st) != cudaSuccess)
+                break;
+            plan.tie_bits = d_tie.as<uint32_t>();
+            plan.tie_w = tie_w;
+        }
         launch_count(true);
         cudaEventRecord(b->ev[0], st);
         if (G > 0
-            && launch_gmm_topn(d, b->plan, b->feat.as<float>(), G, b->tn_s.as<int4>(),
+            && launch_gmm_topn(d, plan, b->feat.as<float>(), G, b->tn_s.as<int4>(),
                                b->tn_c.as<uchar4>(), b->featp.as<float>(), st) != 0)
             break;
         cudaEventRecord(b->ev[1], st);
@@ -1873,6 +1900,21 @@ extern "C" int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out
         bool ok = true;
         float ms_mix = 0.f, ms_search = 0.f;
         int u0 = 0;
+        if (active) {
+            cudaEventRecord(b->ev[3], st);
+            ok = launch_fsg_search_active(d, gs, b->d_frame_off.as<int64_t>(), d_ug.as<int32_t>(),
+                                          d_wsoff.as<int64_t>(), d_ws.as<int32_t>(), b->feat.as<float>(),
+                                          b->tn_s.as<int4>(), b->tn_c.as<uchar4>(), d_tie.as<uint32_t>(),
+                                          G, tie_w, d_awsoff.as<int64_t>(), d_aws.as<int32_t>(),
+                                          d_fact.as<uint32_t>(), d_nsen.as<int64_t>(), U,
+                                          d_hist.as<int32_t>(), in->hist_cap, tent_cap,
+                                          d_nhist.as<int32_t>(), d_neval.as<int64_t>(),
+                                          d_frames.as<int32_t>(), d_rv.as<int32_t>(), st) == 0;
+            cudaEventRecord(b->ev[4], st);
+            if (ok && cudaEventSynchronize(b->ev[4]) == cudaSuccess)
+                cudaEventElapsedTime(&ms_search, b->ev[3], b->ev[4]);
+            u0 = U;
+        }
         while (u0 < U && ok) {
             int u1 = u0 + 1;
             while (u1 < U && b->frame_off[u1 + 1] - b->frame_off[u0] <= kFsgSlabFrames)
@@ -1912,7 +1954,9 @@ extern "C" int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out
             {out->segs, &d_segs, (size_t)U * in->max_seg * 5 * 4}, {out->n_seg, &d_nseg, (size_t)U * 4},
             {out->hyp_score, &d_score, (size_t)U * 4}, {out->exit_bp, &d_exit, (size_t)U * 4},
             {out->utt_rv, &d_rv, (size_t)U * 4}, {out->n_hist, &d_nhist, (size_t)U * 4},
-            {out->n_hmm_eval, &d_neval, (size_t)U * 8}, {out->hist9, &d_hist, hist_ints * 4}};
+            {out->n_hmm_eval, &d_neval, (size_t)U * 8}, {out->hist9, &d_hist, hist_ints * 4},
+            {active ? (void *)out->final_active : nullptr, &d_fact, (size_t)U * nw_sen * 4},
+            {active ? (void *)out->n_sen_eval : nullptr, &d_nsen, (size_t)U * 8}};
         for (auto &c : copies)
             if (c.dst && cudaMemcpyAsync(c.dst, c.src->p, c.bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess)
                 ok = false;
@@ -1934,7 +1978,8 @@ extern "C" int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out
         rv = 0;
     } while (0);
     DBuf *all[] = {&d_hdr, &d_link4, &d_flag, &d_arc, &d_root, &d_pnode, &d_ctxt, &d_ug, &d_wsoff, &d_ws,
-                   &d_hist, &d_nhist, &d_neval, &d_frames, &d_rv, &d_exit, &d_score, &d_segs, &d_nseg};
+                   &d_hist, &d_nhist, &d_neval, &d_frames, &d_rv, &d_exit, &d_score, &d_segs, &d_nseg,
+                   &d_awsoff, &d_aws, &d_tie, &d_fact, &d_nsen};
     for (DBuf *x : all)
         x->release();
     ssb_batch_free(b);

@@ -84,6 +84,11 @@ struct DevPlan {
     const uint16_t *st_slot;    // [total states] union slot of each chain state
     const int32_t *enter_plan;  // [total phones] planned first-entry frame (-1 never)
     int32_t all_active;         // compallsen: every codebook scanned on every frame
+    // optional (K4 with active lists): bit (global frame) of word row cs is set by the top-N
+    // kernel when the step's integer scores tie, i.e. when the reference's list depends on the
+    // list it carried in; [n_mgau*n_feat][tie_w] words, zeroed by the caller
+    uint32_t *tie_bits;
+    int64_t tie_w;
 };
 
 // ---- kernel launchers (each returns 0 or -1 with the error set) ----
@@ -139,6 +144,16 @@ int launch_fsg_search(const DevModel &m, const DevFsgSet &gs, const int64_t *fra
                       const int16_t *dense, int64_t g0, int u0, int n_utts, int32_t *hist,
                       int hist_cap, int tent_cap, int32_t *n_hist, int64_t *n_eval, int32_t *frames,
                       int32_t *rv, cudaStream_t st);
+// the same search in the reference's default mode: senone scores computed inside the kernel for
+// the active HMMs' senones, from K1's dense top-N lists (+ tie flags) and the mixture weights
+size_t fsg_active_ws_ints(const DevModel &m, int n_pnode);
+int launch_fsg_search_active(const DevModel &m, const DevFsgSet &gs, const int64_t *frame_off,
+                             const int32_t *utt_graph, const int64_t *ws_off, int32_t *ws,
+                             const float *feat, const int4 *tn_s, const uchar4 *tn_c,
+                             const uint32_t *tie, int64_t G, int64_t tie_w, const int64_t *aws_off,
+                             int32_t *aws, uint32_t *final_active, int64_t *n_sen_eval, int n_utts,
+                             int32_t *hist, int hist_cap, int tent_cap, int32_t *n_hist,
+                             int64_t *n_eval, int32_t *frames, int32_t *rv, cudaStream_t st);
 int launch_fsg_backtrace(const DevFsgSet &gs, const int32_t *utt_graph, int u0, int n_utts,
                          const int32_t *hist, int hist_cap, const int32_t *n_hist,
                          const int32_t *frames, int32_t *exit_bp, int32_t *hyp_score, int32_t *segs,

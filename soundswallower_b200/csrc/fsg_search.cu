@@ -5,8 +5,16 @@
 // fsg_search_hyp / fsg_search_seg_iter (ref: src/fsg_search.c:853-924, 1030-1142).  The graph
 // (FSG + per-state phonetic lextrees with their cross-word context sets) is built on the host
 // by the caller -- fsg_lextree.c / fsg_model.c are graph preparation, not the per-frame path --
-// and arrives as flat arrays (include/ssb200.h: ssb_fsg_graph_t).  Senone scores are dense
-// ("compallsen" semantics), computed by K1 + K2 for the whole batch beforehand.
+// and arrives as flat arrays (include/ssb200.h: ssb_fsg_graph_t).  Senone scores: either dense
+// ("compallsen = yes", computed by K1 + K2' for the whole batch beforehand), or -- the
+// reference's default -- computed inside this kernel frame by frame for the senones of the
+// active HMMs only (fsg_search_sen_active + acmod_score with an active list, ref:
+// src/fsg_search.c:309-328, 686-690; src/acmod.c:822-999; src/ptm_mgau.c:264-403): the beam
+// decides the active set, the active set decides the normalisers, so scoring and search cannot
+// be separated there.  What CAN be computed beforehand is the Gaussian top-N of every
+// (frame, codebook, stream): the reference's list after a scan is "the N best, sorted" whatever
+// list it carried in, unless integer scores tie -- K1 flags those steps and they are replayed
+// here literally from the list this search carried (see replay_tie).
 //
 // The search is beam pruned and pointer chasing: a handful of HMMs (~5) are alive per frame
 // whatever the grammar size, history entries are inserted into per-(state, left-context)
@@ -14,7 +22,10 @@
 // lane 0; the warp's other lanes evaluate the active HMMs in parallel (the only data-parallel
 // piece) and the machine is filled by utterances: 4096 utterances = 4096 warps.  Integer
 // work: results are bit-exact (history table, scores, segmentation).
+#include <cstring>
+
 #include "hmm_step.cuh"
+#include "tc_common.cuh"
 
 namespace ssb {
 
@@ -201,9 +212,312 @@ __device__ void word_trans(FsgUtt &s)
     }
 }
 
+// ---------------------------------------------------------------- active-list scoring
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(FULL, v, o);
+        if (lane >= o)
+            v += n;
+    }
+    return v;
+}
+
+struct FsgScore {            // per-utterance view of the scoring state (every lane holds it)
+    const float *feat;       // the utterance's features [T][blk]
+    const int4 *tn_s;        // dense top-N of K1, [cs][G]; g0 = the utterance's first frame
+    const uchar4 *tn_c;
+    const uint32_t *tie;     // [cs][tie_w] bit (global frame): integer scores tie on that step
+    int64_t G, g0, tie_w;
+    uint32_t *bits;          // acmod's senone_active_vec
+    uint16_t *srt, *ev;      // active senones ascending; the evaluated list (with bridging entries)
+    int16_t *scr;            // [n_sen] raw senone scores of the frame (listed entries only)
+    int4 *cur_s;             // [CS] raw top-N scores of the frame (scanned codebooks only)
+    uchar4 *cur_c;           // [CS] codewords of the last scan = the list the reference carries
+    uchar4 *cur_n;           // [CS] normalised scores of the frame
+    float *sd;               // shared, [128]: exact distances of one codebook-stream
+    const uint8_t *lut;      // shared, [256]
+};
+
+__device__ __forceinline__ float fsg_gau_dist(const float *__restrict__ rec, const float *__restrict__ x, int L)
+{
+    // the reference's operation order, no contraction (ref: src/ptm_mgau.c:63-68, 150-225)
+    float d = rec[0];
+    for (int j = 0; j < L; ++j) {
+        const float diff = __fsub_rn(x[j], rec[1 + j]);
+        const float sq = __fmul_rn(diff, diff);
+        const float c = __fmul_rn(sq, rec[1 + L + j]);
+        d = __fsub_rn(d, c);
+    }
+    return d;
+}
+
+// A step on which integer scores tie: the reference's result depends on the list it carried in
+// (ref: src/ptm_mgau.c:70-84, 139-148: eval_topn re-scores the carried codewords in their
+// order, eval_cb inserts newcomers in front of equals).  Replayed literally: all densities in
+// parallel, the insertion procedure on lane 0.
+template <int N>
+__device__ void replay_tie(const DevModel &m, const FsgScore &q, int cs, int t, int lane)
+{
+    const int cb = cs / m.n_feat, f = cs - cb * m.n_feat;
+    const int RL = m.rec_len[f], L = m.featlen[f], ND = m.n_density;
+    const float *rec = m.gau + gau_offset(m, cb, f);
+    const float *x = q.feat + (int64_t)t * m.blk + m.featoff[f];
+    for (int n = lane; n < ND; n += 32)
+        q.sd[n] = fsg_gau_dist(rec + (int64_t)n * RL, x, L);
+    __syncwarp();
+    if (lane == 0) {
+        TcTopN<N> tn;
+        const uchar4 c = q.cur_c[cs];
+        const int cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            tn.c[k] = cc[k];
+            tn.s[k] = INT32_MIN;
+        }
+#pragma unroll 1
+        for (int i = 0; i < N; ++i) {
+            int32_t ci = tn.c[0];
+#pragma unroll
+            for (int k = 1; k < N; ++k)
+                if (k == i)
+                    ci = tn.c[k];
+            const int32_t sc = __float2int_rz(q.sd[ci]);
+#pragma unroll
+            for (int k = 0; k < N; ++k)
+                if (k == i)
+                    tn.s[k] = sc;
+            tn.settle(i);
+        }
+#pragma unroll 1
+        for (int cw = 0; cw < ND; ++cw) {
+            const float d = q.sd[cw];
+            if (d < __int2float_rn(tn.s[N - 1]))
+                continue;
+            if (tn.has(cw))
+                continue;
+            tn.insert(__float2int_rz(d), cw);
+        }
+        int4 sv = make_int4(INT32_MIN, INT32_MIN, INT32_MIN, INT32_MIN);
+        uchar4 cv = make_uchar4(0, 0, 0, 0);
+        sv.x = tn.s[0];
+        cv.x = (unsigned char)tn.c[0];
+        if (N > 1) {
+            sv.y = tn.s[N > 1 ? 1 : 0];
+            cv.y = (unsigned char)tn.c[N > 1 ? 1 : 0];
+        }
+        if (N > 2) {
+            sv.z = tn.s[N > 2 ? 2 : 0];
+            cv.z = (unsigned char)tn.c[N > 2 ? 2 : 0];
+        }
+        if (N > 3) {
+            sv.w = tn.s[N > 3 ? 3 : 0];
+            cv.w = (unsigned char)tn.c[N > 3 ? 3 : 0];
+        }
+        q.cur_s[cs] = sv;
+        q.cur_c[cs] = cv;
+    }
+    __syncwarp();
+}
+
+// Scores of frame t for the senones of the `n_act` active HMMs (+ the bridging entries of the
+// uint8 delta list).  Returns the best (smallest) raw score; the value the search sees for
+// senone s is (int16)(scr[s] - best) (ref: src/ptm_mgau.c:398-400).
+__device__ int score_active_frame(const DevModel &m, const FsgUtt &s, const FsgScore &q, int t,
+                                  int n_act, int lane, int &n_ev_out)
+{
+    const int nw = (m.n_sen + 31) >> 5, E = m.n_emit, NF = m.n_feat, CS = m.n_mgau * NF, N = m.topn;
+    // fsg_search_sen_active: acmod_clear_active + acmod_activate_hmm (ref :309-328)
+    for (int w = lane; w < nw; w += 32)
+        q.bits[w] = 0u;
+    __syncwarp();
+    for (int i = lane; i < n_act; i += 32) {
+        const uint16_t *sid = m.sseq + (size_t)s.pnode8[s.act[i] * 8 + 0] * E;
+        for (int j = 0; j < E; ++j)
+            atomicOr(&q.bits[sid[j] >> 5], 1u << (sid[j] & 31));
+    }
+    __syncwarp();
+    // acmod_flags2list (ref: src/acmod.c:947-999): ascending, gaps above 255 bridged
+    const int per = (nw + 31) >> 5;
+    int cnt = 0;
+    for (int k = 0; k < per; ++k) {
+        const int w = lane * per + k;
+        if (w < nw)
+            cnt += __popc(q.bits[w]);
+    }
+    int off = warp_incl_scan(cnt, lane);
+    const int n_srt = __shfl_sync(FULL, off, 31);
+    off -= cnt;
+    for (int k = 0; k < per; ++k) {
+        const int w = lane * per + k;
+        if (w < nw)
+            for (uint32_t x = q.bits[w]; x; x &= x - 1)
+                q.srt[off++] = (uint16_t)(w * 32 + __ffs((int)x) - 1);
+    }
+    __syncwarp();
+    int n_ev = 0;
+    for (int k0 = 0; k0 < n_srt; k0 += 32) {
+        const int k = k0 + lane;
+        int c = 0, sen = 0, prev = 0;
+        if (k < n_srt) {
+            sen = q.srt[k];
+            prev = k ? q.srt[k - 1] : 0;
+            const int delta = sen - prev;
+            c = (delta > 255 ? (delta - 1) / 255 : 0) + 1;
+        }
+        const int pos = warp_incl_scan(c, lane);
+        if (k < n_srt) {
+            int o = n_ev + pos - c;
+            for (int b = 1; b < c; ++b)
+                q.ev[o++] = (uint16_t)(prev + 255 * b);
+            q.ev[o] = (uint16_t)sen;
+        }
+        n_ev += __shfl_sync(FULL, pos, 31);
+    }
+    __syncwarp();
+    n_ev_out = n_ev;
+    if (n_ev == 0)
+        return 0;
+    // ptm_mgau_calc_cb_active (ref: src/ptm_mgau.c:297-321)
+    unsigned long long cbm0 = 0ull, cbm1 = 0ull;  // up to 128 codebooks
+    for (int i = lane; i < n_ev; i += 32) {
+        const int cb = m.sen2cb[q.ev[i]];
+        if (cb < 64)
+            cbm0 |= 1ull << cb;
+        else
+            cbm1 |= 1ull << (cb - 64);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cbm0 |= __shfl_xor_sync(FULL, cbm0, o);
+        cbm1 |= __shfl_xor_sync(FULL, cbm1, o);
+    }
+    // the scanned codebooks' top-N lists of this frame
+    const int64_t g = q.g0 + t;
+    bool any_tie = false;
+    for (int cs = lane; cs < CS; cs += 32) {
+        const int cb = cs / NF;
+        const bool on = cb < 64 ? (cbm0 >> cb) & 1ull : (cbm1 >> (cb - 64)) & 1ull;
+        if (!on)
+            continue;
+        const bool tie = (q.tie[(int64_t)cs * q.tie_w + (g >> 5)] >> (g & 31)) & 1u;
+        if (tie) {
+            any_tie = true;
+            continue;
+        }
+        q.cur_s[cs] = q.tn_s[(int64_t)cs * q.G + g];
+        q.cur_c[cs] = q.tn_c[(int64_t)cs * q.G + g];
+    }
+    if (__any_sync(FULL, any_tie)) {
+        for (int cs = 0; cs < CS; ++cs) {  // warp-uniform walk; ties are rare
+            const int cb = cs / NF;
+            const bool on = cb < 64 ? (cbm0 >> cb) & 1ull : (cbm1 >> (cb - 64)) & 1ull;
+            if (!on || !((q.tie[(int64_t)cs * q.tie_w + (g >> 5)] >> (g & 31)) & 1u))
+                continue;
+            switch (N) {
+            case 1: replay_tie<1>(m, q, cs, t, lane); break;
+            case 2: replay_tie<2>(m, q, cs, t, lane); break;
+            case 3: replay_tie<3>(m, q, cs, t, lane); break;
+            default: replay_tie<4>(m, q, cs, t, lane); break;
+            }
+        }
+    }
+    __syncwarp();
+    // ptm_mgau_codebook_norm (ref :264-295): per stream, over the active codebooks
+    int nm[SSB_MAX_FEAT];
+#pragma unroll
+    for (int f = 0; f < SSB_MAX_FEAT; ++f)
+        nm[f] = WORST_SCORE;
+    for (int cs = lane; cs < CS; cs += 32) {
+        const int cb = cs / NF, f = cs - cb * NF;
+        const bool on = cb < 64 ? (cbm0 >> cb) & 1ull : (cbm1 >> (cb - 64)) & 1ull;
+        if (!on)
+            continue;
+        const int v = q.cur_s[cs].x >> SENSCR_SHIFT;
+#pragma unroll
+        for (int ff = 0; ff < SSB_MAX_FEAT; ++ff)
+            if (ff == f)
+                nm[ff] = max(nm[ff], v);
+    }
+#pragma unroll
+    for (int f = 0; f < SSB_MAX_FEAT; ++f)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            nm[f] = max(nm[f], __shfl_xor_sync(FULL, nm[f], o));
+    for (int cs = lane; cs < CS; cs += 32) {
+        const int cb = cs / NF, f = cs - cb * NF;
+        const bool on = cb < 64 ? (cbm0 >> cb) & 1ull : (cbm1 >> (cb - 64)) & 1ull;
+        if (!on)
+            continue;
+        int nf = nm[0];
+#pragma unroll
+        for (int ff = 1; ff < SSB_MAX_FEAT; ++ff)
+            if (ff == f)
+                nf = nm[ff];
+        const int4 r = q.cur_s[cs];
+        q.cur_n[cs] = make_uchar4((unsigned char)min(MAX_NEG_ASCR, nf - (r.x >> SENSCR_SHIFT)),
+                                  (unsigned char)min(MAX_NEG_ASCR, nf - (r.y >> SENSCR_SHIFT)),
+                                  (unsigned char)min(MAX_NEG_ASCR, nf - (r.z >> SENSCR_SHIFT)),
+                                  (unsigned char)min(MAX_NEG_ASCR, nf - (r.w >> SENSCR_SHIFT)));
+    }
+    __syncwarp();
+    // ptm_mgau_senone_eval (ref :326-403)
+    int best = INT32_MAX;
+    const int ND = m.n_density;
+    for (int i = lane; i < n_ev; i += 32) {
+        const int sen = q.ev[i];
+        const int cb = m.sen2cb[sen];
+        int ascore = 0;
+        for (int f = 0; f < NF; ++f) {
+            const uchar4 sv = q.cur_n[cb * NF + f];
+            const uchar4 cv = q.cur_c[cb * NF + f];
+            const int sc[4] = {sv.x, sv.y, sv.z, sv.w};
+            const int cw[4] = {cv.x, cv.y, cv.z, cv.w};
+            int fden = 0;
+            for (int k = 0; k < N; ++k) {
+                const int v = m.mixw[(int64_t)(f * ND + cw[k]) * m.n_sen + sen] + sc[k];
+                if (k == 0)
+                    fden = v;
+                else {
+                    int d = fden - v, r = v;
+                    if (d <= 0) {
+                        d = -d;
+                        r = fden;
+                    }
+                    fden = r - q.lut[d];
+                }
+            }
+            ascore += fden;
+        }
+        q.scr[sen] = (int16_t)ascore;
+        best = min(best, ascore);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        best = min(best, __shfl_xor_sync(FULL, best, o));
+    __syncwarp();
+    return best;
+}
+
 // one warp per utterance; dense = senone scores of frames [g0, ...), row-major [frame][n_sen]
+struct FsgActiveArgs {       // mode "compallsen = no"
+    const float *feat;       // [G][blk]
+    const int4 *tn_s;
+    const uchar4 *tn_c;
+    const uint32_t *tie;
+    int64_t G, tie_w;
+    const int64_t *aws_off;  // [U+1] offsets (int32 units) into aws
+    int32_t *aws;            // scoring workspace
+    uint32_t *final_active;  // [U][(n_sen+31)/32] or null
+    int64_t *n_sen_eval;     // [U] or null
+};
+
+template <bool ACTIVE>
 __global__ void __launch_bounds__(128)
-fsg_search_kernel(DevModel m, DevFsgSet gs, const int64_t *__restrict__ frame_off,
+fsg_search_kernel(DevModel m, DevFsgSet gs, FsgActiveArgs aa, const int64_t *__restrict__ frame_off,
                   const int32_t *__restrict__ utt_graph, const int64_t *__restrict__ ws_off,
                   int32_t *__restrict__ ws, const int16_t *__restrict__ dense, int64_t g0, int u0,
                   int n_utts, int32_t *__restrict__ hist_all, int hist_cap, int tent_cap,
@@ -214,6 +528,13 @@ fsg_search_kernel(DevModel m, DevFsgSet gs, const int64_t *__restrict__ frame_of
     const int u = u0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (u >= u0 + n_utts)
         return;
+    __shared__ float sh_sd[4][128];
+    __shared__ uint8_t sh_lut[256];
+    if (ACTIVE) {  // every warp fills the table with the same bytes: no block barrier needed
+        for (int i = lane; i < 256; i += 32)
+            sh_lut[i] = m.lut8[i];
+        __syncwarp();
+    }
     FsgUtt s;
     const DevFsg *g = gs.graph + utt_graph[u];
     s.g = g;
@@ -235,8 +556,42 @@ fsg_search_kernel(DevModel m, DevFsgSet gs, const int64_t *__restrict__ frame_of
     s.hist = hist_all + (size_t)u * hist_cap * 9;
     s.cap = hist_cap;
     const int T = (int)(frame_off[u + 1] - frame_off[u]);
-    const int16_t *scr = dense + (frame_off[u] - g0) * m.n_sen;
+    const int16_t *scr = ACTIVE ? nullptr : dense + (frame_off[u] - g0) * m.n_sen;
     const int E = m.n_emit;
+    FsgScore q;
+    long long n_sen_eval = 0;
+    if (ACTIVE) {
+        const int nw = (m.n_sen + 31) >> 5, CS = m.n_mgau * m.n_feat;
+        const int cap_ev = (3 * NP + m.n_sen / 255 + 8 + 1) & ~1;
+        int32_t *a = aa.aws + aa.aws_off[u];
+        q.feat = aa.feat + frame_off[u] * m.blk;
+        q.tn_s = aa.tn_s;
+        q.tn_c = aa.tn_c;
+        q.tie = aa.tie;
+        q.G = aa.G;
+        q.g0 = frame_off[u];
+        q.tie_w = aa.tie_w;
+        q.cur_s = reinterpret_cast<int4 *>(a);              // 16-byte aligned first
+        a += 4 * CS;
+        q.cur_c = reinterpret_cast<uchar4 *>(a);
+        a += CS;
+        q.cur_n = reinterpret_cast<uchar4 *>(a);
+        a += CS;
+        q.bits = reinterpret_cast<uint32_t *>(a);
+        a += nw;
+        q.srt = reinterpret_cast<uint16_t *>(a);
+        a += cap_ev / 2;
+        q.ev = reinterpret_cast<uint16_t *>(a);
+        a += cap_ev / 2;
+        q.scr = reinterpret_cast<int16_t *>(a);
+        q.sd = sh_sd[threadIdx.x >> 5];
+        q.lut = sh_lut;
+        // the list a codebook carries before its first scan (ref: src/ptm_mgau.c:694-720)
+        for (int i = lane; i < CS; i += 32)
+            q.cur_c[i] = make_uchar4(0, 1, 2, 3);
+        for (int i = lane; i < nw; i += 32)
+            q.bits[i] = 0u;
+    }
 
     for (int i = lane; i < NP; i += 32)
         ph_clear(s.phmm + i * PH);
@@ -267,7 +622,13 @@ fsg_search_kernel(DevModel m, DevFsgSet gs, const int64_t *__restrict__ frame_of
     __syncwarp();
     for (int t = 0; t < T; ++t) {
         const int n_act = __shfl_sync(0xffffffffu, s.n_act, 0);
-        const int16_t *ss = scr + (size_t)t * m.n_sen;
+        const int16_t *ss = ACTIVE ? q.scr : scr + (size_t)t * m.n_sen;
+        int sbest = 0;
+        if (ACTIVE) {
+            int n_ev = 0;
+            sbest = score_active_frame(m, s, q, t, n_act, lane, n_ev);
+            n_sen_eval += n_ev;
+        }
         // fsg_search_hmm_eval (ref :330-398): the active HMMs in parallel
         int32_t best = WORST_SCORE;
         for (int i = lane; i < n_act; i += 32) {
@@ -275,7 +636,9 @@ fsg_search_kernel(DevModel m, DevFsgSet gs, const int64_t *__restrict__ frame_of
             int32_t *h = s.phmm + pn * PH;
             const uint16_t *sid = m.sseq + (size_t)s.pnode8[pn * 8 + 0] * E;
             int32_t sc[3] = {h[0], h[1], h[2]}, hi[3] = {h[5], h[6], h[7]}, o_s = h[10], o_h = h[11];
-            const int sv[3] = {ss[sid[0]], ss[sid[1]], ss[sid[2]]};
+            const int sv[3] = {ACTIVE ? (int)(int16_t)(ss[sid[0]] - sbest) : (int)ss[sid[0]],
+                               ACTIVE ? (int)(int16_t)(ss[sid[1]] - sbest) : (int)ss[sid[1]],
+                               ACTIVE ? (int)(int16_t)(ss[sid[2]] - sbest) : (int)ss[sid[2]]};
             const int32_t b = hmm_step3(m.tp + (size_t)s.pnode8[pn * 8 + 1] * 12, sv, sc, hi, o_s, o_h);
             h[0] = sc[0];
             h[1] = sc[1];
@@ -369,6 +732,16 @@ fsg_search_kernel(DevModel m, DevFsgSet gs, const int64_t *__restrict__ frame_of
         n_eval_out[u] = n_eval;
         frames_out[u] = s.frame;
         rv_out[u] = s.overflow ? -2 : 0;
+        if (ACTIVE && aa.n_sen_eval)
+            aa.n_sen_eval[u] = n_sen_eval;
+    }
+    if (ACTIVE && aa.final_active) {
+        // acmod's flags as the last frame left them: what the second pass starts from
+        // (ref: src/state_align_search.c:186-188 never clears them)
+        const int nw = (m.n_sen + 31) >> 5;
+        __syncwarp();
+        for (int i = lane; i < nw; i += 32)
+            aa.final_active[(size_t)u * nw + i] = q.bits[i];
     }
 }
 
@@ -464,8 +837,53 @@ int launch_fsg_search(const DevModel &m, const DevFsgSet &gs, const int64_t *fra
         return -1;
     }
     const int wpb = 4;
-    fsg_search_kernel<<<(n_utts + wpb - 1) / wpb, wpb * 32, 0, st>>>(
-        m, gs, frame_off, utt_graph, ws_off, ws, dense, g0, u0, n_utts, hist, hist_cap, tent_cap,
+    FsgActiveArgs none;
+    memset(&none, 0, sizeof none);
+    fsg_search_kernel<false><<<(n_utts + wpb - 1) / wpb, wpb * 32, 0, st>>>(
+        m, gs, none, frame_off, utt_graph, ws_off, ws, dense, g0, u0, n_utts, hist, hist_cap, tent_cap,
+        n_hist, n_eval, frames, rv);
+    SSB_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+size_t fsg_active_ws_ints(const DevModel &m, int n_pnode)
+{
+    const size_t nw = (m.n_sen + 31) / 32, CS = (size_t)m.n_mgau * m.n_feat;
+    const size_t cap_ev = (3 * (size_t)n_pnode + m.n_sen / 255 + 8 + 1) & ~(size_t)1;
+    size_t n = 4 * CS + CS + CS + nw + cap_ev / 2 + cap_ev / 2 + ((size_t)m.n_sen + 1) / 2;
+    return (n + 3) & ~(size_t)3;  // keeps every utterance's int4 block 16-byte aligned
+}
+
+int launch_fsg_search_active(const DevModel &m, const DevFsgSet &gs, const int64_t *frame_off,
+                             const int32_t *utt_graph, const int64_t *ws_off, int32_t *ws,
+                             const float *feat, const int4 *tn_s, const uchar4 *tn_c,
+                             const uint32_t *tie, int64_t G, int64_t tie_w, const int64_t *aws_off,
+                             int32_t *aws, uint32_t *final_active, int64_t *n_sen_eval, int n_utts,
+                             int32_t *hist, int hist_cap, int tent_cap, int32_t *n_hist,
+                             int64_t *n_eval, int32_t *frames, int32_t *rv, cudaStream_t st)
+{
+    if (n_utts <= 0)
+        return 0;
+    if (m.n_emit != 3 || m.kind != SSB_SCORER_PTM || m.n_density > 128 || m.n_mgau > 128) {
+        set_error("FSG search with active lists needs a PTM model with 3-state HMMs, at most 128 "
+                  "densities and 128 codebooks");
+        return -1;
+    }
+    FsgActiveArgs aa;
+    aa.feat = feat;
+    aa.tn_s = tn_s;
+    aa.tn_c = tn_c;
+    aa.tie = tie;
+    aa.G = G;
+    aa.tie_w = tie_w;
+    aa.aws_off = aws_off;
+    aa.aws = aws;
+    aa.final_active = final_active;
+    aa.n_sen_eval = n_sen_eval;
+    const int wpb = 4;
+    fsg_search_kernel<true><<<(n_utts + wpb - 1) / wpb, wpb * 32, 0, st>>>(
+        m, gs, aa, frame_off, utt_graph, ws_off, ws, nullptr, 0, 0, n_utts, hist, hist_cap, tent_cap,
         n_hist, n_eval, frames, rv);
     SSB_CUDA(cudaGetLastError());
     note_launch();

@@ -485,6 +485,8 @@ gmm_topn_tc2_kernel(DevModel m, DevPlan p, const float *__restrict__ featp, int6
                 // re-score + stable sort only), then eval_topn + eval_cb on frame t.
                 if (DEBUG)
                     ++n_slow;
+                if (p.tie_bits)
+                    atomicOr(&p.tie_bits[(int64_t)cs * p.tie_w + ((g0 + t) >> 5)], 1u << ((g0 + t) & 31));
 #pragma unroll 1
                 for (int tt = t_last + 1; tt <= t; ++tt) {
                     float xx[TC_L];

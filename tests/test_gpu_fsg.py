@@ -125,3 +125,95 @@ def test_two_pass_alignment_on_gpu_equals_cli(models, golden, fsg_golden, lang):
     ps, pd, pc = ssb.propagate(p2["start"], p2["dur"], p2["score"], m.n_emit)
     assert np.array_equal(ps, g["phones"][:, 3]) and np.array_equal(pd, g["phones"][:, 4])
     assert np.array_equal(pc, g["phones"][:, 5])
+
+
+# ---- the reference's default mode: active lists, scoring inside the search kernel
+from test_oracle_fsg import ACTIVE_CASES, TEXT, active_case  # noqa: E402
+from conftest import model_dir  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def active_golden():
+    return {lang: np.load(os.path.join(GOLDEN, "fsg_active_%s.npz" % lang)) for lang in ("en-us", "fr-fr")}
+
+
+@pytest.mark.parametrize("lang", ["en-us", "fr-fr"])
+@pytest.mark.parametrize("name", ACTIVE_CASES)
+def test_fsg_active_lists_golden(models, golden, fsg_golden, active_golden, lang, name):
+    """History table, counters, hypothesis score (App. B: -2761 / -4236), segmentation and the
+    flags left in acmod, all equal to the unmodified reference run with its default config."""
+    m, a = models(lang), active_golden[lang]
+    G, feat = active_case(lang, name, golden[lang]["feat"], fsg_golden[lang], a)
+    r = ssb.fsg_batch(m, [feat], [G], want_hist=True, compallsen=False)[0]
+    assert r["rv"] == 0
+    assert np.array_equal(r["hist"], a[name + "_hist"])
+    assert r["n_hmm_eval"] == int(a[name + "_n_hmm_eval"])
+    assert r["n_sen_eval"] == int(a[name + "_n_sen_eval"])
+    assert np.array_equal(r["active"], a[name + "_active"])
+    assert r["hyp_score"] == int(a[name + "_hyp_score"])
+    assert np.array_equal(r["segs"][:, 1:], a[name + "_segs"][:, 1:])
+
+
+@pytest.mark.parametrize("lang,name", [("fr-fr", "trunc"), ("en-us", "noisy"), ("fr-fr", "tiled")])
+def test_second_pass_starts_from_the_flags_pass_one_left(models, golden, fsg_golden, active_golden, lang, name):
+    """decoder_alignment after a default-mode first pass: the aligner never clears acmod's flags
+    (ref: src/state_align_search.c:186-188), so the senones of pass 1's last frame stay active
+    throughout pass 2 and move its normalisers.  fr-fr/trunc leaves 29 of them."""
+    m, a = models(lang), active_golden[lang]
+    lx = ssb.Lexicon(m, hmmdir=model_dir(lang))
+    G, feat = active_case(lang, name, golden[lang]["feat"], fsg_golden[lang], a)
+    p1 = ssb.fsg_batch(m, [feat], [G], compallsen=False)[0]
+    segs = a[name + "_segs"]
+    segs = segs[segs[:, 0] >= 0]
+    chain = lx.populate(segs[:, 0], segs[:, 1], segs[:, 2] - segs[:, 1] + 1)
+    left = [int(w * 32 + b) for w, x in enumerate(p1["active"]) for b in range(32) if (int(x) >> b) & 1]
+    r = ssb.align_batch(m, [feat], [chain], init_active=[left])[0]
+    want = a[name + "_p2_states"]
+    assert r["rv"] == int(a[name + "_p2_rv"]) == 0
+    assert np.array_equal(np.stack([r["start"], r["dur"], r["score"]], 1), want[:, 1:4])
+    if name == "trunc":   # the flags matter: without them the scores differ
+        r0 = ssb.align_batch(m, [feat], [chain])[0]
+        assert len(left) == 29 and not np.array_equal(r0["score"], want[:, 3])
+
+
+def test_fsg_active_lists_ragged_batch_vs_oracle(models, oracles, golden, fsg_golden):
+    """Many utterances, two grammars, every length: the data-dependent active sets, the bridging
+    entries of the delta list and the tie replays all have to agree with the oracle."""
+    m, o = models("en-us"), oracles("en-us")
+    g, feat = fsg_golden["en-us"], golden["en-us"]["feat"]
+    graphs = [graph_of(g, "align"), graph_of(g, "jsgf")]
+    rs = np.random.RandomState(77)
+    feats, ug = [], []
+    for u in range(48):
+        k = int(rs.randint(0, 4))
+        if k == 0:
+            f = (feat + rs.normal(0, 0.05, feat.shape)).astype(np.float32)
+        elif k == 1:
+            f = feat[:int(rs.randint(1, 278))]
+        elif k == 2:
+            f = (feat + rs.normal(0, 0.3, feat.shape)).astype(np.float32)
+        else:
+            f = model_features(rs, o.model_arrays(), int(rs.randint(1, 80)))
+        feats.append(f)
+        ug.append(u % 2)
+    feats[7] = feats[7][:0]
+    res = ssb.fsg_batch(m, feats, graphs, utt_graph=ug, want_hist=True, compallsen=False)
+    n_match = 0
+    for u, (f, r) in enumerate(zip(feats, res)):
+        w = o.fsg_search_active(graphs[ug[u]], f if len(f) else np.zeros((0, 39), np.float32))
+        assert r["rv"] == w["rv"] == 0, u
+        assert np.array_equal(r["hist"], w["hist"]), u
+        assert r["n_hmm_eval"] == w["n_hmm_eval"] and r["n_sen_eval"] == w["n_sen_eval"], u
+        assert np.array_equal(r["active"], w["active"]), u
+        assert r["exit"] == w["exit"], u
+        if w["exit"] > 0:
+            n_match += 1
+            assert r["hyp_score"] == w["hyp_score"] and np.array_equal(r["segs"], w["segs"]), u
+    assert n_match >= 10
+
+
+def test_fsg_active_lists_need_the_ptm_tensor_core_path(models, golden, fsg_golden, monkeypatch):
+    m, g = models("en-us"), fsg_golden["en-us"]
+    monkeypatch.setenv("SSB_K1", "fp32")
+    with pytest.raises(ssb.SsbError, match="active lists need"):
+        ssb.fsg_batch(m, [golden["en-us"]["feat"][:20]], [graph_of(g, "align")], compallsen=False)

@@ -181,6 +181,55 @@ def fsg(lang, raw_feat_key, text, gram):
     np.savez_compressed(os.path.join(OUT, "fsg_%s.npz" % lang), **g)
 
 
+def fsg_active_cases(lang, text, feat, jsgf):
+    """(name, grammar selection, features) of the default-mode fixtures; the noisy case is
+    regenerated from its seed by the tests."""
+    rs = np.random.RandomState(1)
+    return [("align", dict(align_text=text), feat), ("jsgf", dict(jsgf=jsgf), feat),
+            ("trunc", dict(align_text=text), feat[:150]),
+            ("noisy", dict(align_text=text), feat + rs.randn(*feat.shape).astype(np.float32) * np.float32(0.3)),
+            ("tiled", dict(align_text=" ".join([text] * 2)), np.concatenate([feat, feat]))]
+
+
+def fsg_active(lang, text, gram):
+    """The same searches in the reference's DEFAULT mode (compallsen = no: only the senones of
+    the active HMMs are scored, frame by frame): history table, segmentation, hypothesis score,
+    senones evaluated, the active-senone flags the search leaves in acmod, and the second pass
+    (decoder_alignment) that starts from those flags -> fsg_active_<lang>.npz."""
+    hmm = os.path.join(MODELS, lang)
+    ref = Ref(hmm, compallsen=False)
+    feat = np.load(os.path.join(OUT, "align_%s.npz" % lang))["feat"]
+    jsgf = open(os.path.join(DATA, gram)).read()
+    g = {}
+    for name, kw, f in fsg_active_cases(lang, text, feat, jsgf):
+        G = ref.fsg_graph(**kw)
+        if name == "tiled":
+            for k, v in G.items():
+                g["%s_%s" % (name, k)] = np.asarray(v)
+        d = ref.fsg_decode(f, **kw)
+        H = ref.fsg_history()
+        bits, n_sen_eval = ref.active_bits()
+        g[name + "_hist"] = H["hist"]
+        g[name + "_segs"] = d["segs"]
+        g[name + "_n_hmm_eval"] = np.int64(H["n_hmm_eval"])
+        g[name + "_n_sen_eval"] = np.int64(n_sen_eval)
+        g[name + "_hyp_score"] = np.int32(d["hyp_score"])
+        g[name + "_active"] = bits
+        # second pass exactly as decoder_alignment runs it: pass 1's words (null transitions
+        # dropped) with their windows, acmod's flags left as pass 1 set them
+        segs = d["segs"][d["segs"][:, 0] >= 0]
+        if len(segs):
+            a = ref.state_align(f, segs[:, 0], segs[:, 1], segs[:, 2] - segs[:, 1] + 1, clear_active=False)
+            g[name + "_p2_rv"] = np.int32(a["rv"])
+            for k in ("words", "phones", "states"):
+                g["%s_p2_%s" % (name, k)] = a[k]
+        print(lang, name, "hist", len(H["hist"]), "hyp", d["hyp_score"], "n_sen_eval", n_sen_eval,
+              "flags left", int(sum(bin(int(x)).count("1") for x in bits)),
+              "pass 2 rv", int(g.get(name + "_p2_rv", -9)))
+    ref.close()
+    np.savez_compressed(os.path.join(OUT, "fsg_active_%s.npz" % lang), **g)
+
+
 def loaders(lang="en-us"):
     """Weight tables and scores of the reference for the mixture-weight formats the bundled
     models do not use (tests/model_variants.py writes the files) -> loader_variants.json."""
@@ -359,11 +408,16 @@ def main():
         return cont()
     if "--lexicon" in sys.argv:
         return lexicon()
+    if "--fsg-active" in sys.argv:
+        fsg_active("en-us", "go forward ten meters", "goforward.gram")
+        return fsg_active("fr-fr", "avance de dix mètres", "goforward_fr.gram")
     utterance("en-us", "goforward.raw", "go forward ten meters")
     utterance("fr-fr", "goforward_fr.raw", "avance de dix mètres")
     synthetic("en-us")
     fsg("en-us", "goforward.raw", "go forward ten meters", "goforward.gram")
     fsg("fr-fr", "goforward_fr.raw", "avance de dix mètres", "goforward_fr.gram")
+    fsg_active("en-us", "go forward ten meters", "goforward.gram")
+    fsg_active("fr-fr", "avance de dix mètres", "goforward_fr.gram")
     loaders()
     frontend()
     semi()
