@@ -289,8 +289,11 @@ typedef struct ssb_fsg_out_s {
     uint32_t *final_active;
     int64_t *n_sen_eval;
 } ssb_fsg_out_t;
-/* Dense ("compallsen") senone scoring + search + backtrace of a batch of utterances. */
+/* Senone scoring + search + backtrace of a batch of utterances, with dense ("compallsen")
+ * scores or, with in->active_lists, the reference's default active-list scoring. */
 int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out_t *out);
+/* 1 when in->active_lists = 1 is available for this model (PTM, 128 densities, on a device) */
+int ssb_model_fsg_active_ok(const ssb_model_t *m);
 
 /* single HMM step on the device (ref: src/hmm.c:482-567); st = score[5] hist[5]
  * out_score out_hist, updated in place; returns best score via *best */
@@ -410,6 +413,13 @@ ssb_search_t *ssb_fsg_search_init(const char *name, ssb_model_t *m, const ssb_le
 /* appends frames to the search's own feature buffer (the NULL-source case); returns the
  * number of frames held */
 int ssb_search_feed(ssb_search_t *search, const float *feat, int32_t n_frames);
+/* acmod's active-senone flags ((n_sen+31)/32 words): after finish() of a grammar search in the
+ * default mode, what its last frame left (ssb_search_final_active; all zero in compallsen mode);
+ * before start() of the aligner, what it starts from (ssb_search_set_init_active) -- in the
+ * reference both live in the one acmod the two searches share, and the aligner never clears
+ * them (ref: src/state_align_search.c:186-188). */
+int ssb_search_final_active(const ssb_search_t *search, uint32_t *bits);
+int ssb_search_set_init_active(ssb_search_t *search, const uint32_t *bits);
 /* alignment_words / alignment_phones / alignment_states of the aligner's alignment
  * (level 0 / 1 / 2, ref: src/ps_alignment.c:357-420): [n][5] = id (word id | CI phone |
  * senone), start, duration, score, parent; returns the number of entries at that level */

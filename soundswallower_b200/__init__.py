@@ -86,6 +86,11 @@ class AcousticModel:
         except Exception:
             pass
 
+    @property
+    def fsg_active_ok(self):
+        """The grammar search can run in the reference's default (active-list) mode."""
+        return bool(self.lib.ssb_model_fsg_active_ok(self.h))
+
     def arrays(self):
         """Host copies of the parsed tables, in the reference's in-memory shapes."""
         if self._arrays is None:
@@ -923,6 +928,18 @@ class Search:
             it = s.vt.contents.seg_next(it)
         return out
 
+    def final_active(self):
+        """acmod's active-senone flags as the grammar search left them (uint32 words)."""
+        out = np.zeros((self.model.n_sen + 31) // 32, np.uint32)
+        _lib.check(self.model.lib.ssb_search_final_active(self.ptr, _ptr(out)), "ssb_search_final_active")
+        return out
+
+    def set_init_active(self, bits):
+        """The flags the aligner finds in acmod when it starts (it never clears them)."""
+        bits = np.ascontiguousarray(bits, np.uint32) if bits is not None else None
+        _lib.check(self.model.lib.ssb_search_set_init_active(self.ptr, _ptr(bits) if bits is not None else None),
+                   "ssb_search_set_init_active")
+
     def alignment(self, level):
         """alignment_words/phones/states: int32 [n][5] id start duration score parent."""
         lvl = {"words": 0, "phones": 1, "states": 2}[level]
@@ -974,6 +991,16 @@ def fsg_search(model, lexicon, text, name="_default", source=None, **cfg):
 
 
 # ---------------------------------------------------------------------------- two-pass alignment
+def _left_active(p1):
+    """Per utterance the senones whose acmod flags the first pass left set."""
+    out = []
+    for r in p1:
+        bits = r.get("active")
+        out.append([] if bits is None else
+                   [int(w * 32 + b) for w in np.nonzero(bits)[0] for b in range(32) if (int(bits[w]) >> b) & 1])
+    return out
+
+
 def align_texts(model, lexicon, feats, texts, **search_cfg):
     """The reference's forced alignment of `soundswallower --align` for a batch of
     (utterance, transcript) pairs, both passes on the GPU:
@@ -990,7 +1017,11 @@ def align_texts(model, lexicon, feats, texts, **search_cfg):
     dur, score, word index)], states=int32 [n][5] (senone, start, dur, score, phone index),
     hyp_score)."""
     graphs = [lexicon.align_graph(t, **search_cfg) for t in texts]
-    p1 = fsg_batch(model, feats, graphs, utt_graph=np.arange(len(texts), dtype=np.int32))
+    # the reference's default mode (compallsen = no) wherever the model allows it: pass-1 path
+    # scores are then the CLI's, and pass 2 starts from the flags pass 1 left in acmod
+    active = model.fsg_active_ok
+    p1 = fsg_batch(model, feats, graphs, utt_graph=np.arange(len(texts), dtype=np.int32),
+                   compallsen=not active)
     chains, metas = [], []
     for g, r in zip(graphs, p1):
         if r["rv"] != 0 or r["exit"] <= 0:
@@ -1006,7 +1037,7 @@ def align_texts(model, lexicon, feats, texts, **search_cfg):
         c = lexicon.populate(wids, start, dur)
         chains.append(c)
         metas.append((wids, start, dur, c, int(r["hyp_score"])))
-    p2 = align_batch(model, feats, chains)
+    p2 = align_batch(model, feats, chains, init_active=_left_active(p1) if active else None)
     arrays = model.arrays()
     E = model.n_emit
     out = []

@@ -138,7 +138,8 @@ SYMBOLS = [
     "ssb_batch_n_launches", "ssb_batch_stats", "ssb_align_batch", "ssb_pipeline_create",
     "ssb_pipeline_align", "ssb_pipeline_n_launches", "ssb_pipeline_n_chunks", "ssb_pipeline_trace", "ssb_pipeline_free",
     "ssb_score_batch", "ssb_lexicon_basewid", "ssb_fsg_built_is_filler",
-    "ssb_state_align_search_init", "ssb_fsg_search_init", "ssb_search_feed", "ssb_search_alignment",
+    "ssb_state_align_search_init", "ssb_fsg_search_init", "ssb_search_feed", "ssb_search_alignment", "ssb_search_final_active",
+    "ssb_search_set_init_active", "ssb_model_fsg_active_ok",
     "ssb_topn_batch", "ssb_tc_probe", "ssb_tc_hot_mask", "ssb_fsg_batch", "ssb_hmm_vit_eval",
     "ssb_fe_config_defaults", "ssb_fe_config_from_model", "ssb_frontend_create",
     "ssb_frontend_free", "ssb_frontend_dims", "ssb_frontend_n_frames", "ssb_frontend_tables",
@@ -234,6 +235,9 @@ def load():
     L.ssb_fsg_search_init.argtypes = [C.c_char_p, vp, vp, vp, vp, vp]
     L.ssb_search_feed.argtypes = [vp, vp, i32]
     L.ssb_search_alignment.argtypes = [vp, i32, vp, i32]
+    L.ssb_search_final_active.argtypes = [vp, vp]
+    L.ssb_search_set_init_active.argtypes = [vp, vp]
+    L.ssb_model_fsg_active_ok.argtypes = [vp]
     L.ssb_chain_populate.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32]
     L.ssb_fsg_config_defaults.restype = None
     L.ssb_fsg_config_defaults.argtypes = [P(FsgConfig)]

@@ -1746,6 +1746,11 @@ extern "C" int ssb_hmm_vit_eval(ssb_model_t *m, int32_t n_emit, int32_t tmatid,
 // frames per dense-score slab of the FSG path: whole utterances, <= ~12 GB of int16 scores
 static const int64_t kFsgSlabFrames = 1200000;
 
+extern "C" int ssb_model_fsg_active_ok(const ssb_model_t *m)
+{
+    return m && m->device >= 0 && tc_supported(m->d) && !(getenv("SSB_K1") && *getenv("SSB_K1"));
+}
+
 extern "C" int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out_t *out)
 {
     if (!in || !out || in->n_utts < 0 || in->n_graphs < 0 || in->hist_cap < 2 || in->max_seg < 1
@@ -1839,7 +1844,7 @@ extern "C" int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out
     const bool active = in->active_lists != 0;
     std::vector<int64_t> aws_off(U + 1, 0);
     if (active) {
-        if (!tc_supported(m->d) || (getenv("SSB_K1") && *getenv("SSB_K1"))) {
+        if (!ssb_model_fsg_active_ok(m)) {
             set_error("ssb_fsg_batch: active lists need the tensor-core top-N kernel (a PTM model "
                       "with 128 densities, SSB_K1 unset); use active_lists = 0 (compallsen)");
             return -1;

@@ -52,6 +52,9 @@ struct SearchImpl {
     std::vector<int32_t> segs;  // [n][5] link sf ef ascr lscr
     int32_t n_seg = 0, hyp_score = 0, exit_bp = 0, n_hist = 0;
     std::vector<std::string> seg_word_store;
+    // acmod's active-senone flags: left by the grammar search / found by the aligner
+    std::vector<uint32_t> flags;
+    int n_sen = 0;
 };
 
 struct SegImpl {
@@ -113,6 +116,7 @@ int align_finish(ssb_search_t *s)
     in.tmat = S->tmat.data();
     in.sf = S->sf.data();
     in.ef = S->ef.data();
+    in.init_active = S->flags.empty() ? nullptr : S->flags.data();
     std::vector<int32_t> st(ns), du(ns), sc(ns);
     for (int i = 0; i < ns; ++i) {
         st[i] = S->state[i].start;
@@ -298,6 +302,9 @@ int fsg_finish(ssb_search_t *s)
         in.utt_graph = &utt_graph;
         in.hist_cap = std::max(4096, 8 * S->n_frames);
         in.max_seg = max_seg;
+        // the reference's default (compallsen = no) wherever the model allows it
+        in.active_lists = ssb_model_fsg_active_ok(S->m);
+        S->flags.assign((size_t)(S->n_sen + 31) / 32, 0u);
         S->segs.assign((size_t)max_seg * 5, 0);
         int32_t n_seg = 0, score = 0, exit_bp = 0, rv = 0, n_hist = 0;
         ssb_fsg_out_t out;
@@ -308,6 +315,7 @@ int fsg_finish(ssb_search_t *s)
         out.exit_bp = &exit_bp;
         out.utt_rv = &rv;
         out.n_hist = &n_hist;
+        out.final_active = S->flags.data();
         if (ssb_fsg_batch(S->m, &in, &out) != 0)
             return -1;
         if (rv != 0) {
@@ -413,6 +421,7 @@ SearchImpl *new_search(int kind, const char *type, const char *name, ssb_model_t
     S->src_ctx = acmod;
     S->blk = h->blk;
     S->n_emit = h->n_emit;
+    S->n_sen = h->n_sen;
     S->type_s = type;
     S->name_s = name ? name : "";
     // search_module_init (ref: src/decoder.c:1276-1307)
@@ -499,6 +508,34 @@ extern "C" int ssb_search_feed(ssb_search_t *s, const float *feat, int32_t n_fra
     SearchImpl *S = impl(s);
     S->feat.insert(S->feat.end(), feat, feat + (size_t)n_frames * S->blk);
     return (int)(S->feat.size() / S->blk);
+}
+
+extern "C" int ssb_search_final_active(const ssb_search_t *s, uint32_t *bits)
+{
+    if (!s || !bits) {
+        set_error("ssb_search_final_active: bad arguments");
+        return -1;
+    }
+    const SearchImpl *S = reinterpret_cast<const SearchImpl *>(s);
+    const size_t nw = (size_t)(S->n_sen + 31) / 32;
+    for (size_t i = 0; i < nw; ++i)
+        bits[i] = i < S->flags.size() ? S->flags[i] : 0u;
+    return 0;
+}
+
+extern "C" int ssb_search_set_init_active(ssb_search_t *s, const uint32_t *bits)
+{
+    if (!s) {
+        set_error("NULL search");
+        return -1;
+    }
+    SearchImpl *S = impl(s);
+    const size_t nw = (size_t)(S->n_sen + 31) / 32;
+    if (bits)
+        S->flags.assign(bits, bits + nw);
+    else
+        S->flags.clear();
+    return 0;
 }
 
 extern "C" int32_t ssb_search_alignment(const ssb_search_t *s, int32_t level, int32_t *out5,

@@ -7,17 +7,18 @@ cannot fill a GPU.
 
 Scope: forced alignment (`set_align_text`) and grammar decoding with a flattened grammar
 (`set_fsg_graph`); JSGF parsing, add_word, VAD and the config parser stay with the caller.
-One mode difference from the reference's defaults: the first pass scores every senone on every
-frame ("compallsen"), so its *path scores* (Seg.ascore of the first pass, Hyp.score) are those
-of the reference run with compallsen=yes; word boundaries, and with them everything
-`alignment` returns, are the default mode's.
+Both passes run in the reference's default mode (compallsen = no: only the senones of the
+active HMMs are scored, and the second pass starts from the flags the first one left), so
+Hyp.score, Seg.ascore and the alignment are the default CLI's, bit for bit.  Models the
+active-list search does not cover (semi-continuous, continuous) fall back to compallsen = yes.
 """
 import collections
 import wave
 
 import numpy as np
 
-from . import (AcousticModel, Frontend, Lexicon, SsbError, align_batch, fsg_batch, propagate)
+from . import (AcousticModel, Frontend, Lexicon, SsbError, _left_active, align_batch, fsg_batch,
+               propagate)
 
 Seg = collections.namedtuple("Seg", ["text", "start", "duration", "ascore", "lscore"])
 Hyp = collections.namedtuple("Hyp", ["text", "score", "prob"])
@@ -204,7 +205,9 @@ class Decoder:
         feats = self.frontend.run(pcms)
         n = [int(feats.frame_off[i + 1] - feats.frame_off[i]) for i in range(len(pcms))]
         self._feats = feats
-        p1 = fsg_batch(self.model, feats, graphs, utt_graph=np.arange(len(graphs), dtype=np.int32))
+        # the reference's default mode (compallsen = no) wherever the model allows it
+        p1 = fsg_batch(self.model, feats, graphs, utt_graph=np.arange(len(graphs), dtype=np.int32),
+                       compallsen=not self.model.fsg_active_ok)
         return [_Result(self, n[i], graphs[i], p1[i]) for i in range(len(pcms))]
 
     @property
@@ -251,7 +254,9 @@ class Decoder:
             c = lx.populate(wids, start, dur)
             chains.append(c)
             metas.append((wids, c))
-        p2 = align_batch(m, feats, chains)
+        # the aligner starts from the flags the first pass left in acmod
+        # (ref: src/state_align_search.c:186-188 never clears them)
+        p2 = align_batch(m, feats, chains, init_active=_left_active([r.p1 for r in results]))
         sseq = m.arrays()["sseq"]
         for r, meta, a in zip(results, metas, p2):
             if meta is None or a["rv"] != 0:

@@ -41,7 +41,7 @@ def test_result_json_formatting_matches_the_cli(golden):
     no GPU needed, the numbers are the reference's."""
     d = ssb.Decoder(model_dir("en-us"), device=-1)
     g = golden["en-us"]
-    fg = np.load(os.path.join(os.path.dirname(__file__), "golden", "fsg_en-us.npz"))
+    fg = np.load(os.path.join(os.path.dirname(__file__), "golden", "fsg_active_en-us.npz"))
     d.set_align_text(TEXT["en-us"])
     graph = d._graph
     # pass-1 segmentation rows -> link ids of the alignment grammar
@@ -64,7 +64,9 @@ def test_result_json_formatting_matches_the_cli(golden):
     assert [len(p["w"]) for w in two["w"] for p in w["w"]] == [3] * 18
     zero = json.loads(d.dumps(align_level=0))
     assert [w["t"] for w in zero["w"]] == ["<sil>", "go", "forward", "ten", "meters", "<sil>"]
-    assert zero["w"][1] == {"b": 0.46, "d": 0.18, "p": round(1.0001 ** -413, 3), "t": "go"}
+    assert zero["w"][1] == {"b": 0.46, "d": 0.18, "p": round(1.0001 ** -133, 3), "t": "go"}
+    assert zero["w"][0]["p"] == round(1.0001 ** (-230 - 337), 3)      # App. B: <sil> 0 45 -230 -337
+    assert abs(d.hyp.score - 1.0001 ** -2761) < 1e-12
     assert [s.text for s in d.seg] == [w["t"] for w in zero["w"]]
     assert [w.name for w in d.alignment] == [w["t"] for w in zero["w"]]
     assert [p.name for p in list(d.alignment.words())[2]] == ["F", "AO", "R", "W", "ER", "D"]
@@ -103,6 +105,12 @@ def test_cli_json_from_audio():
     assert d.n_frames == 279
     assert d.dumps(align_level=1) == CLI_JSON
     assert d.hyp.text == TEXT["en-us"]
+    assert abs(d.hyp.score - 1.0001 ** -2761) < 1e-12               # decoder_hyp of the default CLI
+    word_level = json.loads(d.dumps(align_level=0))                   # App. B word ascr / lscr
+    assert [(w["t"], w["p"]) for w in word_level["w"]] == [
+        ("<sil>", round(1.0001 ** -567, 3)), ("go", round(1.0001 ** -133, 3)),
+        ("forward", round(1.0001 ** -369, 3)), ("ten", round(1.0001 ** -468, 3)),
+        ("meters", round(1.0001 ** -563, 3)), ("<sil>", round(1.0001 ** -661, 3))]
     text, seg = d.decode_file(os.path.join(DATA, "goforward.raw"))
     assert text == TEXT["en-us"]
     seg = list(seg)

@@ -87,7 +87,8 @@ def test_two_pass_through_the_vtables(models, golden, lang):
     """decoder_set_align_text -> search_module_forward -> hyp / seg_iter, then
     decoder_alignment -> state_align_search -> alignment entries: the reference's CLI result."""
     m, g = models(lang), golden[lang]
-    fg = np.load(os.path.join(os.path.dirname(__file__), "golden", "fsg_%s.npz" % lang))
+    # the reference's default mode (compallsen = no): App. B's -2761 / -4236
+    fg = np.load(os.path.join(os.path.dirname(__file__), "golden", "fsg_active_%s.npz" % lang))
     lx = ssb.Lexicon(m, hmmdir=model_dir(lang))
     feat = g["feat"]
     p1 = ssb.fsg_search(m, lx, TEXT[lang])
@@ -95,7 +96,7 @@ def test_two_pass_through_the_vtables(models, golden, lang):
     assert p1.forward(feat) == len(feat)
     assert p1.finish() == 0
     hyp, score = p1.hyp()
-    assert hyp == TEXT[lang] and score == int(fg["align_hyp_score"])
+    assert hyp == TEXT[lang] and score == int(fg["align_hyp_score"]) == {"en-us": -2761, "fr-fr": -4236}[lang]
     seg = p1.seg()
     want = fg["align_segs"]
     assert [lx.wordid(s[0]) for s in seg] == want[:, 0].tolist()
@@ -103,6 +104,8 @@ def test_two_pass_through_the_vtables(models, golden, lang):
     # pass 2 on pass 1's words and windows
     wids = [lx.wordid(s[0]) for s in seg]
     p2 = ssb.state_align_search(m, lx, wids, [s[1] for s in seg], [s[2] - s[1] + 1 for s in seg])
+    assert np.array_equal(p1.final_active(), fg["align_active"])
+    p2.set_init_active(p1.final_active())      # the acmod the two searches share
     assert p2.start() == 0 and p2.forward(feat) == len(feat) and p2.finish() == 0
     assert np.array_equal(p2.alignment("words")[:, :4], g["words"])
     ph = p2.alignment("phones")

@@ -20,6 +20,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--utts", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--active", action="store_true",
+                    help="the reference's default mode: active lists, scoring inside the search kernel")
     args = ap.parse_args()
     g = np.load(os.path.join(ROOT, "tests/golden/fsg_en-us.npz"))
     feat = np.load(os.path.join(ROOT, "tests/golden/align_en-us.npz"))["feat"]
@@ -29,11 +31,11 @@ def main():
         rng = np.random.Generator(np.random.Philox(1234 + u))
         feats.append(feat + rng.standard_normal(feat.shape, dtype=np.float32) * np.float32(0.05))
     graph = graph_of(g, "jsgf")
-    ssb.fsg_batch(m, feats[:64], [graph])  # warm-up
+    ssb.fsg_batch(m, feats[:64], [graph], compallsen=not args.active)  # warm-up
     best = None
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        res = ssb.fsg_batch(m, feats, [graph], hist_cap=2048, max_seg=32)
+        res = ssb.fsg_batch(m, feats, [graph], hist_cap=2048, max_seg=32, compallsen=not args.active)
         wall = time.perf_counter() - t0
         ms = res[0]["kernel_ms"]
         if best is None or wall < best[0]:
@@ -43,6 +45,8 @@ def main():
     dev_ms = sum(ms.values())
     n_ok = sum(1 for r in res if r["exit"] > 0 and r["rv"] == 0)
     print(json.dumps({"workload": "config#3: goforward.gram decode, %d x %d frames, en-us" % (args.utts, feat.shape[0]),
+                      "mode": "active lists (compallsen=no, the reference default)" if args.active else "dense (compallsen=yes)",
+                      "senones_per_frame": (float(np.mean([r["n_sen_eval"] for r in res])) / feat.shape[0]) if args.active else float(m.n_sen),
                       "kernel_ms": ms, "device_ms": dev_ms, "audio_s_per_s_device": audio_s / (dev_ms * 1e-3),
                       "e2e_ms": wall * 1e3, "audio_s_per_s_e2e": audio_s / wall, "decoded": n_ok,
                       "hmm_evals_per_frame": float(np.mean([r["n_hmm_eval"] for r in res])) / feat.shape[0],
