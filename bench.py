@@ -425,6 +425,20 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    # DRAM traffic of the dominant kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of
+    # one `ncu --set full` capture of this very launch shape (tools/profile_gpu.sh r1h 4096)
+    traffic = None
+    try:
+        if U == 4096 and not args.compallsen:
+            vals = {}
+            for ln in open(os.path.join(ROOT, "profiles", "prof_gmm_topn_r1h.txt")):
+                f = ln.split()
+                if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    vals[f[0]] = float(f[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[2]]
+            if len(vals) == 2:
+                traffic = sum(vals.values())
+    except Exception:
+        traffic = None
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback"
     # K1 algorithmic FLOPs: scanned codebook-frames x streams x densities x 2(2D+1)  
@@ -466,7 +480,9 @@ def main():
                                "K1 variant SSB_K1=%s" % os.environ.get("SSB_K1"),
                      "bound": "tensor",
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved_tf / peak_tf, "traffic": traffic,
+                     "traffic_source": "profiles/prof_gmm_topn_r1h.txt (ncu --set full, same launch shape), bytes per launch",
+                     "peak_source": peak_src,
                      "note": "achieved = ALGORITHMIC flops (SURVEY 8d: scanned codebook-frames x 3 streams x "
                              "128 densities x 2(2*13+1)) / CUDA-event time of the kernel; the MMAs actually "
                              "executed are 3 split products on K padded to 32 (mma_tflops_executed); the "

@@ -64,7 +64,9 @@ constexpr int K2_CS_PER_LANE = 4;  // codebook-streams per lane: CS <= 128
 // union are staged once.  Then every WARP takes frames on its own (t = t_begin + warp,
 // +8, ...): lanes over codebook-streams for the normaliser, lanes over active senones for
 // the mixing, lanes over chain states for the gather -- only __syncwarp inside the loop.
-template <bool STAGED>
+// PTM4 = the bundled models' case fixed at compile time (PTM scorer, top-4): no unused-entry test
+// and no trip-count test in the innermost loop (they cost 2.8 of 11 ms on config #2).
+template <bool STAGED, bool PTM4>
 __global__ void __launch_bounds__(K2_THREADS)
 senone_mix_active_kernel(DevModel m, DevPlan p, const int4 *__restrict__ tn_s,
                          const uchar4 *__restrict__ tn_c, int64_t G, int W, int chunk,
@@ -176,7 +178,13 @@ senone_mix_active_kernel(DevModel m, DevPlan p, const int4 *__restrict__ tn_s,
                 for (int ff = 1; ff < SSB_MAX_FEAT; ++ff)
                     if (ff == f)
                         n0 = nm[ff];
-                wt_s[cs] = norm_scores(m, f, n0, rs[it]);
+                if (PTM4)
+                    wt_s[cs] = make_uchar4((unsigned char)min(MAX_NEG_ASCR, n0 - (rs[it].x >> SENSCR_SHIFT)),
+                                           (unsigned char)min(MAX_NEG_ASCR, n0 - (rs[it].y >> SENSCR_SHIFT)),
+                                           (unsigned char)min(MAX_NEG_ASCR, n0 - (rs[it].z >> SENSCR_SHIFT)),
+                                           (unsigned char)min(MAX_NEG_ASCR, n0 - (rs[it].w >> SENSCR_SHIFT)));
+                else
+                    wt_s[cs] = norm_scores(m, f, n0, rs[it]);
                 wt_c[cs] = rc[it];
             }
         for (int i = lane; i < W / 2; i += 32)
@@ -196,7 +204,7 @@ senone_mix_active_kernel(DevModel m, DevPlan p, const int4 *__restrict__ tn_s,
                 int fden = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (k < N && sc[k] != K2_UNUSED) {
+                    if (PTM4 || (k < N && sc[k] != K2_UNUSED)) {
                         int w;
                         if (STAGED)
                             w = mw[(f * ND + cw[k]) * W + slot];
@@ -217,7 +225,7 @@ senone_mix_active_kernel(DevModel m, DevPlan p, const int4 *__restrict__ tn_s,
         // D: gather to chain states, subtract the frame's best (ref :398-400; the
         // semi-continuous scorer does not normalise over senones)
         {
-            const int16_t b16 = m.kind == SSB_SCORER_SEMI ? (int16_t)0 : (int16_t)local_best;
+            const int16_t b16 = (!PTM4 && m.kind == SSB_SCORER_SEMI) ? (int16_t)0 : (int16_t)local_best;
             int16_t *dst = chain_scr + p.scr_off[u] + (int64_t)t * ns;
             for (int si = lane; si < ns; si += 32)
                 dst[si] = (int16_t)(wscr[st_slot[si]] - b16);
@@ -259,17 +267,20 @@ int launch_senone_mix_active(const DevModel &m, const DevPlan &p, const int4 *tn
     int chunk = (int)((n_frames + want_ctas - 1) / want_ctas);
     chunk = (max(chunk, 64) + K2_WARPS - 1) / K2_WARPS * K2_WARPS;
     dim3 grid((max_frames_per_utt + chunk - 1) / chunk, p.n_utts);
+    const bool ptm4 = m.kind == SSB_SCORER_PTM && m.topn == 4;
+#define SSB_K2(ST, P4)                                                                              \
+    do {                                                                                            \
+        SSB_CUDA(cudaFuncSetAttribute(senone_mix_active_kernel<ST, P4>,                             \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        senone_mix_active_kernel<ST, P4>                                                            \
+            <<<grid, K2_THREADS, smem, st>>>(m, p, tn_score, tn_cw, n_frames, W, chunk, chain_scr); \
+    } while (0)
     if (staged) {
-        SSB_CUDA(cudaFuncSetAttribute(senone_mix_active_kernel<true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        senone_mix_active_kernel<true>
-            <<<grid, K2_THREADS, smem, st>>>(m, p, tn_score, tn_cw, n_frames, W, chunk, chain_scr);
+        if (ptm4) SSB_K2(true, true); else SSB_K2(true, false);
     } else {
-        SSB_CUDA(cudaFuncSetAttribute(senone_mix_active_kernel<false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        senone_mix_active_kernel<false>
-            <<<grid, K2_THREADS, smem, st>>>(m, p, tn_score, tn_cw, n_frames, W, chunk, chain_scr);
+        if (ptm4) SSB_K2(false, true); else SSB_K2(false, false);
     }
+#undef SSB_K2
     SSB_CUDA(cudaGetLastError());
     note_launch();
     return 0;

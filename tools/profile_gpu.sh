@@ -17,3 +17,9 @@ for K in gmm_topn senone_mix_active chain_viterbi; do
   echo "ncu ${K} rc=$?"
 done
 ls -la gpurun_out
+# K4 in the reference's default mode (config #3)
+ncu --set full --clock-control none --import-source on -k regex:fsg_search_kernel -s 1 -c 1 -f \
+    -o gpurun_out/prof_fsg_search_active_${TAG} \
+    python tools/bench_fsg.py --active --steps 1 --utts ${UTTS} > gpurun_out/prof_fsg_search_active_${TAG}.stdout 2>&1
+echo "ncu fsg_search rc=$?"
+ls -la gpurun_out
