@@ -383,9 +383,12 @@ def main():
 
     pipe = ssb.AlignPipeline(model)
 
+    def pipe_args(pp):
+        pp.upload_raw(feat_np.reshape(-1, model.blk), frame_off, phone_off, flat["ssid"],
+                      flat["tmat"], flat["sf"], flat["ef"], None, args.compallsen)
+
     def pipe_once():
-        pipe.upload_raw(feat_np.reshape(-1, model.blk), frame_off, phone_off, flat["ssid"],
-                        flat["tmat"], flat["sf"], flat["ef"], None, args.compallsen)
+        pipe_args(pipe)
         return pipe.align()
 
     for _ in range(2):
@@ -395,7 +398,7 @@ def main():
     for _ in range(args.steps):
         res = pipe_once()
     barrier()
-    e2e_s = (time.perf_counter() - t0) / args.steps
+    e2e_call_s = (time.perf_counter() - t0) / args.steps
     pipe_chunks, pipe_launches = pipe.n_chunks(), pipe.n_launches()
     if os.environ.get("SSB_PIPE_TRACE") and rank == 0:
         for row in pipe.trace():
@@ -403,6 +406,33 @@ def main():
                   % tuple(row[:7]), file=sys.stderr)
     pipe_same = all(np.array_equal(res[k], res_one[k]) for k in ("start", "dur", "score", "rv", "best_score"))
     pipe.close()
+
+    # (c) a stream of batches, the headline: every step is one whole batch submitted through
+    # ssb_pipeline_submit / collected through ssb_pipeline_collect, two in flight -- batch i+1 is
+    # planned and copied in while batch i computes (kernels of different batches never share the
+    # GPU); every step's H2D and D2H happen inside the timed region
+    stream = ssb.AlignPipeline(model, n_lanes=2, chunk_frames=1 << 40, overlap_kernels=False)
+
+    def stream_run(n):
+        tickets, out = [], None
+        for _ in range(n):
+            pipe_args(stream)
+            tickets.append(stream.submit())
+            if len(tickets) > 1:
+                out = stream.collect(tickets.pop(0))
+        while tickets:
+            out = stream.collect(tickets.pop(0))
+        return out
+
+    stream_run(3)
+    barrier()
+    t0 = time.perf_counter()
+    res = stream_run(args.steps)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    stream_launches = stream.n_launches()
+    stream_same = all(np.array_equal(res[k], res_one[k]) for k in ("start", "dur", "score", "rv", "best_score"))
+    stream.close()
 
     audio_s = U * FRAMES / FRAME_RATE
     t_dev = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -464,10 +494,14 @@ def main():
         "e2e": {"value": world * audio_s / (e2e_ms_max * 1e-3), "unit": "audio-s/s",
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms_max,
-                "path": "ssb_pipeline_align: %d chunks of whole utterances through 4 lanes (stream + host "
-                        "thread each), pinned host features in, segmentations out; %d kernel launches per "
-                        "step; results identical to the single resident batch: %s"
-                        % (pipe_chunks, pipe_launches, pipe_same),
+                "path": "ssb_pipeline_submit/collect: a stream of whole batches, two in flight (batch i+1 is "
+                        "planned and copied in while batch i computes; kernels of different batches never "
+                        "overlap), pinned host features in, segmentations out, %d kernel launches per step; "
+                        "results identical to the single resident batch: %s" % (stream_launches, stream_same),
+                "single_call_ms_per_step": e2e_call_s * 1e3,
+                "single_call_path": "ssb_pipeline_align on one batch: %d chunks of whole utterances through 4 "
+                                    "lanes (stream + host thread each), %d launches; identical results: %s"
+                                    % (pipe_chunks, pipe_launches, pipe_same),
                 "single_batch_ms_per_step": e2e_one_s * 1e3,
                 "single_batch_host_call_ms": {"upload(plan+H2D issue)": 1e3 * host_split[0] / args.steps,
                                  "run(launch)": 1e3 * host_split[1] / args.steps,

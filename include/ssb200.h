@@ -204,8 +204,18 @@ int ssb_align_batch(ssb_model_t *m, const ssb_align_in_t *in, ssb_align_out_t *o
 typedef struct ssb_pipeline_s ssb_pipeline_t;
 ssb_pipeline_t *ssb_pipeline_create(ssb_model_t *m, int32_t n_lanes, int64_t chunk_frames);
 int ssb_pipeline_align(ssb_pipeline_t *p, const ssb_align_in_t *in, ssb_align_out_t *out);
-int ssb_pipeline_n_launches(const ssb_pipeline_t *p); /* kernels launched by the last call */
-int ssb_pipeline_n_chunks(const ssb_pipeline_t *p);   /* chunks of the last call */
+/* The two halves of ssb_pipeline_align, for a stream of batches: submit returns a ticket (< 0 on
+ * error) at once, collect waits for that batch.  The arrays behind `in` and `out` must stay
+ * valid until the batch is collected; batches are processed in submission order and several
+ * may be in flight.  With ssb_pipeline_set_overlap(p, 0) the kernels of different chunks never
+ * share the GPU (only planning and copies overlap them) -- the setting for whole batches as
+ * chunks (chunk_frames >= the batch), where batch i+1 is planned and uploaded while batch i
+ * computes; the default, 1, lets kernels of different chunks overlap (chunks of one batch). */
+int64_t ssb_pipeline_submit(ssb_pipeline_t *p, const ssb_align_in_t *in, ssb_align_out_t *out);
+int ssb_pipeline_collect(ssb_pipeline_t *p, int64_t ticket);
+int ssb_pipeline_set_overlap(ssb_pipeline_t *p, int32_t overlap_kernels);
+int ssb_pipeline_n_launches(const ssb_pipeline_t *p); /* kernels launched for the last collected batch */
+int ssb_pipeline_n_chunks(const ssb_pipeline_t *p);   /* chunks of the last collected batch */
 /* timeline of the last call, 8 doubles per chunk: lane, first utterance, ms since the call
  * started at which the chunk's upload began / its upload returned / its download returned,
  * CUDA-event ms of its top-N kernel and of all its kernels, 0; returns chunks written */

@@ -417,12 +417,28 @@ class AlignPipeline(_AlignCall):
     lanes (stream + host thread each), so that planning and copies overlap the kernels.  Same
     upload()/upload_raw() arguments as StateAlignBatch; align() = upload + run + download."""
 
-    def __init__(self, model, n_lanes=0, chunk_frames=0):
+    def __init__(self, model, n_lanes=0, chunk_frames=0, overlap_kernels=True):
         _AlignCall.__init__(self, model)
         self.p = self.lib.ssb_pipeline_create(model.h, int(n_lanes), int(chunk_frames))
         if not self.p:
             raise SsbError("ssb_pipeline_create: " + _lib.last_error())
         self.p = C.c_void_p(self.p)
+        self.lib.ssb_pipeline_set_overlap(self.p, int(bool(overlap_kernels)))
+        self._inflight = {}
+
+    def submit(self, want_chain_scr=False, want_tokens=False, init=None):
+        """ssb_pipeline_submit of the uploaded arguments: returns a ticket at once; the arrays
+        are kept alive here until collect(ticket) returns the result dict."""
+        o, res = self._align_out(want_chain_scr, want_tokens, init)
+        t = int(self.lib.ssb_pipeline_submit(self.p, C.byref(self._in), C.byref(o)))
+        _lib.check(t, "ssb_pipeline_submit")
+        self._inflight[t] = (self._in, self._keep, o, res)
+        return t
+
+    def collect(self, ticket):
+        _in, _keep, _o, res = self._inflight.pop(ticket)
+        _lib.check(self.lib.ssb_pipeline_collect(self.p, int(ticket)), "ssb_pipeline_collect")
+        return res
 
     def close(self):
         if getattr(self, "p", None):

@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -1255,25 +1257,143 @@ extern "C" int ssb_batch_stats(const ssb_batch_t *b, int64_t *o)
 
 // ------------------------------------------------------------------ pipeline
 // Utterances are independent, so a large batch is cut into chunks of whole utterances and the
-// chunks travel through `n_lanes` batches, each on its own stream and driven by its own host
+// chunks travel through `n_lanes` batches, each on its own stream and driven by its own worker
 // thread: while one chunk is on the SMs the next one is being planned and copied in and the
 // previous one copied out.  Results are those of one big batch, utterance by utterance.
+// Batches are submitted and collected separately, so consecutive batches overlap as well: with
+// whole batches as chunks and kernels kept apart (overlap_kernels = 0) batch i+1 is planned
+// and uploaded while batch i computes.
+namespace {
+struct PipeJob {
+    int64_t ticket = -1, seq = -1;
+    int chunk = 0, u0 = 0;
+    ssb_align_in_t in;
+    ssb_align_out_t out;
+    std::vector<int64_t> fo, po;
+};
+struct PipeTicket {
+    int n_chunks = 0, n_done = 0, launches = 0;
+    bool failed = false;
+    std::string err;
+    std::vector<double> trace;
+    std::chrono::steady_clock::time_point t0;
+};
+}  // namespace
+
 struct ssb_pipeline_s {
     ssb_model_t *m = nullptr;
     int n_lanes = 0;
     int64_t chunk_frames = 0;
+    bool overlap_kernels = true;
     std::vector<ssb_batch_t *> lane;
     std::vector<cudaStream_t> st;
+    std::vector<std::thread> workers;
+    std::mutex mu, compute_mu;
+    std::condition_variable cv_job, cv_done, cv_up;
+    std::deque<std::unique_ptr<PipeJob>> jobs;
+    std::map<int64_t, PipeTicket> tickets;
+    int64_t next_ticket = 0, next_seq = 0, up_turn = 0;
+    bool stop = false;
+    // of the last collected batch
     int n_launches = 0, n_chunks = 0;
-    // per chunk of the last call: lane, first utterance, then ms since the call started at
-    // which upload began / upload returned / download returned, and the chunk's kernel ms
     std::vector<double> trace;
 };
+
+static void pipe_worker(ssb_pipeline_s *p, int li)
+{
+    cudaSetDevice(p->m->device);
+    ssb_batch_t *b = p->lane[li];
+    for (;;) {
+        std::unique_ptr<PipeJob> job;
+        {
+            std::unique_lock<std::mutex> lk(p->mu);
+            p->cv_job.wait(lk, [&] { return p->stop || !p->jobs.empty(); });
+            if (p->jobs.empty())
+                return;  // stop requested and nothing left
+            job = std::move(p->jobs.front());
+            p->jobs.pop_front();
+        }
+        double tr[8] = {(double)li, (double)job->u0, 0, 0, 0, 0, 0, 0};
+        std::chrono::steady_clock::time_point t0;
+        bool skip;
+        {
+            std::unique_lock<std::mutex> lk(p->mu);
+            PipeTicket &tk = p->tickets[job->ticket];
+            t0 = tk.t0;
+            skip = tk.failed;
+        }
+        auto now_ms = [&]() {
+            return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        };
+        int rv = 0;
+        {
+            // one chunk on the PCIe link at a time, in submission order: the first chunk
+            // reaches the SMs after 1/n of the copy time and the lanes stay out of phase
+            std::unique_lock<std::mutex> lk(p->mu);
+            p->cv_up.wait(lk, [&] { return p->up_turn == job->seq; });
+            lk.unlock();
+            tr[2] = now_ms();
+            if (!skip) {
+                ssb_batch_debug_tokens(b, job->out.tokens ? 1 : 0);
+                rv = ssb_batch_upload(b, &job->in);
+            }
+            lk.lock();
+            ++p->up_turn;
+            lk.unlock();
+            p->cv_up.notify_all();
+        }
+        tr[3] = now_ms();
+        if (!skip && rv == 0) {
+            if (p->overlap_kernels) {
+                rv = ssb_batch_run(b);
+            } else {
+                std::lock_guard<std::mutex> g(p->compute_mu);
+                rv = ssb_batch_run(b);
+                if (rv == 0 && cudaStreamSynchronize(b->st) != cudaSuccess) {
+                    set_error("pipeline: kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
+                    rv = -1;
+                }
+            }
+        }
+        if (!skip && rv == 0)
+            rv = ssb_batch_download(b, &job->out);
+        tr[4] = now_ms();
+        if (!skip && rv == 0) {
+            float ms[8];
+            if (ssb_batch_kernel_ms(b, ms) == 0) {
+                tr[5] = ms[0];
+                tr[6] = ms[4];
+            }
+        }
+        {
+            std::lock_guard<std::mutex> lk(p->mu);
+            PipeTicket &tk = p->tickets[job->ticket];
+            if (rv != 0 && !tk.failed) {
+                tk.failed = true;
+                tk.err = ssb::last_error();
+            }
+            if (!skip && rv == 0)
+                tk.launches += b->n_launches;
+            for (int k = 0; k < 8; ++k)
+                tk.trace[(size_t)job->chunk * 8 + k] = tr[k];
+            ++tk.n_done;
+        }
+        p->cv_done.notify_all();
+    }
+}
 
 extern "C" void ssb_pipeline_free(ssb_pipeline_t *p)
 {
     if (!p)
         return;
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        p->stop = true;
+    }
+    p->cv_job.notify_all();
+    for (auto &t : p->workers)
+        if (t.joinable())
+            t.join();
     cudaSetDevice(p->m->device);
     for (ssb_batch_t *b : p->lane)
         ssb_batch_free(b);
@@ -1315,7 +1435,18 @@ extern "C" ssb_pipeline_t *ssb_pipeline_create(ssb_model_t *m, int32_t n_lanes, 
         }
         p->lane.push_back(b);
     }
+    for (int i = 0; i < n_lanes; ++i)
+        p->workers.emplace_back(pipe_worker, p, i);
     return p;
+}
+
+extern "C" int ssb_pipeline_set_overlap(ssb_pipeline_t *p, int32_t overlap_kernels)
+{
+    if (!p)
+        return -1;
+    std::lock_guard<std::mutex> lk(p->mu);
+    p->overlap_kernels = overlap_kernels != 0;
+    return 0;
 }
 
 extern "C" int ssb_pipeline_n_launches(const ssb_pipeline_t *p) { return p ? p->n_launches : -1; }
@@ -1330,21 +1461,17 @@ extern "C" int ssb_pipeline_trace(const ssb_pipeline_t *p, double *out, int32_t 
     return n;
 }
 
-extern "C" int ssb_pipeline_align(ssb_pipeline_t *p, const ssb_align_in_t *in, ssb_align_out_t *out)
+extern "C" int64_t ssb_pipeline_submit(ssb_pipeline_t *p, const ssb_align_in_t *in, ssb_align_out_t *out)
 {
     if (!p || !in || !out || in->n_utts < 0 || (in->n_utts > 0 && (!in->frame_off || !in->phone_off))) {
-        set_error("ssb_pipeline_align: bad arguments");
+        set_error("ssb_pipeline_submit: bad arguments");
         return -1;
     }
     if (need_device(p->m) != 0)
         return -1;
     const HostModel &h = p->m->h;
     const int U = in->n_utts, E = h.n_emit;
-    p->n_launches = 0;
-    p->n_chunks = 0;
-    if (U == 0)
-        return 0;
-    if (in->frame_off[0] != 0 || in->phone_off[0] != 0) {
+    if (U > 0 && (in->frame_off[0] != 0 || in->phone_off[0] != 0)) {
         set_error("frame_off[0] and phone_off[0] must be 0");
         return -1;
     }
@@ -1375,108 +1502,91 @@ extern "C" int ssb_pipeline_align(ssb_pipeline_t *p, const ssb_align_in_t *in, s
         }
     }
     const int n_chunks = (int)cut.size() - 1;
-    p->n_chunks = n_chunks;
     const int nw = (h.n_sen + 31) / 32;
-    p->trace.assign((size_t)n_chunks * 8, 0.0);
-    const auto t_call = std::chrono::steady_clock::now();
-    auto now_ms = [&]() {
-        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
-    };
-    std::atomic<int> next(0), failed(0), launches(0);
-    std::string err;
-    std::mutex err_mu, up_mu;
-    std::condition_variable up_cv;
-    int up_turn = 0;
-    auto work = [&](int li) {
-        cudaSetDevice(p->m->device);
-        ssb_batch_t *b = p->lane[li];
-        ssb_batch_debug_tokens(b, out->tokens ? 1 : 0);
-        std::vector<int64_t> fo, po;
-        for (;;) {
-            const int c = next.fetch_add(1);
-            if (c >= n_chunks || failed.load())
-                break;
-            const int u0 = cut[c], u1 = cut[c + 1];
-            const int64_t f0 = in->frame_off[u0], p0 = in->phone_off[u0];
-            fo.resize(u1 - u0 + 1);
-            po.resize(u1 - u0 + 1);
-            for (int u = u0; u <= u1; ++u) {
-                fo[u - u0] = in->frame_off[u] - f0;
-                po[u - u0] = in->phone_off[u] - p0;
-            }
-            ssb_align_in_t ci = *in;
-            ci.n_utts = u1 - u0;
-            ci.feat = in->feat ? in->feat + f0 * h.blk : nullptr;
-            ci.frame_off = fo.data();
-            ci.phone_off = po.data();
-            ci.ssid = in->ssid ? in->ssid + p0 : nullptr;
-            ci.tmat = in->tmat ? in->tmat + p0 : nullptr;
-            ci.sf = in->sf ? in->sf + p0 : nullptr;
-            ci.ef = in->ef ? in->ef + p0 : nullptr;
-            ci.init_active = in->init_active ? in->init_active + (size_t)u0 * nw : nullptr;
-            ssb_align_out_t co = *out;
-            co.st_start = out->st_start ? out->st_start + p0 * E : nullptr;
-            co.st_dur = out->st_dur ? out->st_dur + p0 * E : nullptr;
-            co.st_score = out->st_score ? out->st_score + p0 * E : nullptr;
-            co.utt_rv = out->utt_rv ? out->utt_rv + u0 : nullptr;
-            co.utt_best = out->utt_best ? out->utt_best + u0 : nullptr;
-            co.utt_renorm = out->utt_renorm ? out->utt_renorm + u0 : nullptr;
-            co.chain_scr = out->chain_scr ? out->chain_scr + scr0[c] : nullptr;
-            co.tokens = out->tokens ? out->tokens + 2 * scr0[c] : nullptr;
-            double *tr = &p->trace[(size_t)c * 8];
-            tr[0] = li;
-            tr[1] = u0;
-            int rv;
-            {
-                // one chunk on the PCIe link at a time, in chunk order: the first chunk reaches
-                // the SMs after 1/n of the copy time, and the lanes stay out of phase
-                std::unique_lock<std::mutex> lk(up_mu);
-                up_cv.wait(lk, [&] { return up_turn == c || failed.load(); });
-                tr[2] = now_ms();
-                rv = ssb_batch_upload(b, &ci);
-                ++up_turn;
-                lk.unlock();
-                up_cv.notify_all();
-            }
-            tr[3] = now_ms();
-            if (rv == 0)
-                rv = ssb_batch_run(b);
-            if (rv == 0)
-                rv = ssb_batch_download(b, &co);
-            tr[4] = now_ms();
-            if (rv == 0) {
-                float ms[8];
-                if (ssb_batch_kernel_ms(b, ms) == 0) {
-                    tr[5] = ms[0];
-                    tr[6] = ms[4];
-                }
-            }
-            if (rv != 0) {
-                std::lock_guard<std::mutex> lk(err_mu);
-                if (!failed.exchange(1))
-                    err = ssb::last_error();
-                up_cv.notify_all();
-                break;
-            }
-            launches.fetch_add(b->n_launches);
+    std::vector<std::unique_ptr<PipeJob>> jobs;
+    for (int c = 0; c < n_chunks; ++c) {
+        std::unique_ptr<PipeJob> j(new PipeJob);
+        const int u0 = cut[c], u1 = cut[c + 1];
+        const int64_t f0 = in->frame_off[u0], p0 = in->phone_off[u0];
+        j->chunk = c;
+        j->u0 = u0;
+        j->fo.resize(u1 - u0 + 1);
+        j->po.resize(u1 - u0 + 1);
+        for (int u = u0; u <= u1; ++u) {
+            j->fo[u - u0] = in->frame_off[u] - f0;
+            j->po[u - u0] = in->phone_off[u] - p0;
         }
-    };
-    const int n_thr = std::min(p->n_lanes, n_chunks);
-    if (n_thr <= 1) {
-        work(0);
-    } else {
-        std::vector<std::thread> th;
-        for (int i = 0; i < n_thr; ++i)
-            th.emplace_back(work, i);
-        for (auto &t : th)
-            t.join();
+        j->in = *in;
+        j->in.n_utts = u1 - u0;
+        j->in.feat = in->feat ? in->feat + f0 * h.blk : nullptr;
+        j->in.frame_off = j->fo.data();
+        j->in.phone_off = j->po.data();
+        j->in.ssid = in->ssid ? in->ssid + p0 : nullptr;
+        j->in.tmat = in->tmat ? in->tmat + p0 : nullptr;
+        j->in.sf = in->sf ? in->sf + p0 : nullptr;
+        j->in.ef = in->ef ? in->ef + p0 : nullptr;
+        j->in.init_active = in->init_active ? in->init_active + (size_t)u0 * nw : nullptr;
+        j->out = *out;
+        j->out.st_start = out->st_start ? out->st_start + p0 * E : nullptr;
+        j->out.st_dur = out->st_dur ? out->st_dur + p0 * E : nullptr;
+        j->out.st_score = out->st_score ? out->st_score + p0 * E : nullptr;
+        j->out.utt_rv = out->utt_rv ? out->utt_rv + u0 : nullptr;
+        j->out.utt_best = out->utt_best ? out->utt_best + u0 : nullptr;
+        j->out.utt_renorm = out->utt_renorm ? out->utt_renorm + u0 : nullptr;
+        j->out.chain_scr = out->chain_scr ? out->chain_scr + scr0[c] : nullptr;
+        j->out.tokens = out->tokens ? out->tokens + 2 * scr0[c] : nullptr;
+        jobs.push_back(std::move(j));
     }
-    p->n_launches = launches.load();
-    if (failed.load()) {
-        set_error("%s", err.c_str());
+    int64_t ticket;
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        ticket = p->next_ticket++;
+        PipeTicket &tk = p->tickets[ticket];
+        tk.n_chunks = n_chunks;
+        tk.trace.assign((size_t)n_chunks * 8, 0.0);
+        tk.t0 = std::chrono::steady_clock::now();
+        for (auto &j : jobs) {
+            j->ticket = ticket;
+            j->seq = p->next_seq++;
+            p->jobs.push_back(std::move(j));
+        }
+    }
+    p->cv_job.notify_all();
+    return ticket;
+}
+
+extern "C" int ssb_pipeline_collect(ssb_pipeline_t *p, int64_t ticket)
+{
+    if (!p) {
+        set_error("NULL pipeline");
+        return -1;
+    }
+    std::unique_lock<std::mutex> lk(p->mu);
+    auto it = p->tickets.find(ticket);
+    if (it == p->tickets.end()) {
+        set_error("ssb_pipeline_collect: unknown ticket %lld", (long long)ticket);
+        return -1;
+    }
+    p->cv_done.wait(lk, [&] { return it->second.n_done >= it->second.n_chunks; });
+    PipeTicket tk = std::move(it->second);
+    p->tickets.erase(it);
+    p->n_launches = tk.launches;
+    p->n_chunks = tk.n_chunks;
+    p->trace = std::move(tk.trace);
+    lk.unlock();
+    if (tk.failed) {
+        set_error("%s", tk.err.c_str());
         return -1;
     }
     return 0;
+}
+
+extern "C" int ssb_pipeline_align(ssb_pipeline_t *p, const ssb_align_in_t *in, ssb_align_out_t *out)
+{
+    const int64_t t = ssb_pipeline_submit(p, in, out);
+    if (t < 0)
+        return -1;
+    return ssb_pipeline_collect(p, t);
 }
 
 extern "C" int ssb_align_batch(ssb_model_t *m, const ssb_align_in_t *in, ssb_align_out_t *out)

@@ -275,6 +275,41 @@ def test_pipeline_equals_oracle_and_single_batch(models, oracles, compallsen):
     assert n_ok >= 8
 
 
+def test_pipeline_stream_of_batches(models, oracles):
+    """ssb_pipeline_submit / collect: three different batches in flight through two lanes, whole
+    batches as chunks, kernels kept apart; every batch equals its own one-shot result."""
+    m, o = models("en-us"), oracles("en-us")
+    rs = np.random.RandomState(9)
+    batches = [_random_batch(rs, o, n) for n in (11, 1, 17, 6)]
+    pipe = ssb.AlignPipeline(m, n_lanes=2, chunk_frames=1 << 40, overlap_kernels=False)
+    tickets = []
+    for feats, chains in batches:
+        pipe.upload(feats, chains)
+        tickets.append((pipe.submit(want_chain_scr=True), pipe.n_utts, pipe.frame_off, pipe.phone_off))
+    for (t, n_utts, fo, po), (feats, chains) in zip(tickets, batches):
+        res = pipe.collect(t)
+        assert pipe.n_chunks() == 1
+        pipe.n_utts, pipe.frame_off, pipe.phone_off = n_utts, fo, po
+        got = pipe.per_utt(res)
+        one = ssb.align_batch(m, feats, chains, want_chain_scr=True)
+        for u, (a, b) in enumerate(zip(got, one)):
+            assert a["rv"] == b["rv"] and a["best_score"] == b["best_score"], u
+            for k in ("start", "dur", "score", "chain_scr"):
+                assert np.array_equal(a[k], b[k]), (u, k)
+    # an error in one batch is reported by its collect and does not poison the next one
+    feats, chains = batches[0]
+    bad = [dict(c) for c in chains]
+    bad[3] = dict(bad[3], ssid=bad[3]["ssid"] + 10 ** 6)
+    pipe.upload(feats, bad)
+    t_bad = pipe.submit()
+    pipe.upload(feats, chains)
+    t_ok = pipe.submit()
+    with pytest.raises(ssb.SsbError, match="out of range"):
+        pipe.collect(t_bad)
+    assert pipe.collect(t_ok)["rv"].shape == (len(feats),)
+    pipe.close()
+
+
 def test_align_batch_routes_large_batches_through_pipeline(models, oracles, monkeypatch):
     m, o = models("en-us"), oracles("en-us")
     rs = np.random.RandomState(5)
