@@ -238,6 +238,7 @@ struct FsgScore {            // per-utterance view of the scoring state (every l
     int4 *cur_s;             // [CS] raw top-N scores of the frame (scanned codebooks only)
     uchar4 *cur_c;           // [CS] codewords of the last scan = the list the reference carries
     uchar4 *cur_n;           // [CS] normalised scores of the frame
+    int32_t *last_t;         // [CS] frame of the codebook-stream's last scan (-1: never)
     float *sd;               // shared, [128]: exact distances of one codebook-stream
     const uint8_t *lut;      // shared, [256]
 };
@@ -257,8 +258,11 @@ __device__ __forceinline__ float fsg_gau_dist(const float *__restrict__ rec, con
 
 // A step on which integer scores tie: the reference's result depends on the list it carried in
 // (ref: src/ptm_mgau.c:70-84, 139-148: eval_topn re-scores the carried codewords in their
-// order, eval_cb inserts newcomers in front of equals).  Replayed literally: all densities in
-// parallel, the insertion procedure on lane 0.
+// order, eval_cb inserts newcomers in front of equals).  Replayed literally.  eval_topn runs for
+// EVERY codebook on every frame (ref :234-237), scanned or not, so the carried list has been
+// re-scored and stably re-sorted on each frame since the last scan: lane 0 first catches it up
+// through those frames, then all densities of frame t are evaluated across the warp and lane 0
+// runs the insertion procedure.
 template <int N>
 __device__ void replay_tie(const DevModel &m, const FsgScore &q, int cs, int t, int lane)
 {
@@ -277,6 +281,24 @@ __device__ void replay_tie(const DevModel &m, const FsgScore &q, int cs, int t, 
         for (int k = 0; k < N; ++k) {
             tn.c[k] = cc[k];
             tn.s[k] = INT32_MIN;
+        }
+#pragma unroll 1
+        for (int tt = q.last_t[cs] + 1; tt < t; ++tt) {  // eval_topn of the frames in between
+            const float *xx = q.feat + (int64_t)tt * m.blk + m.featoff[f];
+#pragma unroll 1
+            for (int i = 0; i < N; ++i) {
+                int32_t ci = tn.c[0];
+#pragma unroll
+                for (int k = 1; k < N; ++k)
+                    if (k == i)
+                        ci = tn.c[k];
+                const int32_t sc = __float2int_rz(fsg_gau_dist(rec + (int64_t)ci * RL, xx, L));
+#pragma unroll
+                for (int k = 0; k < N; ++k)
+                    if (k == i)
+                        tn.s[k] = sc;
+                tn.settle(i);
+            }
         }
 #pragma unroll 1
         for (int i = 0; i < N; ++i) {
@@ -319,6 +341,7 @@ __device__ void replay_tie(const DevModel &m, const FsgScore &q, int cs, int t, 
         }
         q.cur_s[cs] = sv;
         q.cur_c[cs] = cv;
+        q.last_t[cs] = t;
     }
     __syncwarp();
 }
@@ -410,6 +433,7 @@ __device__ int score_active_frame(const DevModel &m, const FsgUtt &s, const FsgS
         }
         q.cur_s[cs] = q.tn_s[(int64_t)cs * q.G + g];
         q.cur_c[cs] = q.tn_c[(int64_t)cs * q.G + g];
+        q.last_t[cs] = t;
     }
     if (__any_sync(FULL, any_tie)) {
         for (int cs = 0; cs < CS; ++cs) {  // warp-uniform walk; ties are rare
@@ -577,6 +601,8 @@ fsg_search_kernel(DevModel m, DevFsgSet gs, FsgActiveArgs aa, const int64_t *__r
         a += CS;
         q.cur_n = reinterpret_cast<uchar4 *>(a);
         a += CS;
+        q.last_t = a;
+        a += CS;
         q.bits = reinterpret_cast<uint32_t *>(a);
         a += nw;
         q.srt = reinterpret_cast<uint16_t *>(a);
@@ -587,8 +613,10 @@ fsg_search_kernel(DevModel m, DevFsgSet gs, FsgActiveArgs aa, const int64_t *__r
         q.sd = sh_sd[threadIdx.x >> 5];
         q.lut = sh_lut;
         // the list a codebook carries before its first scan (ref: src/ptm_mgau.c:694-720)
-        for (int i = lane; i < CS; i += 32)
+        for (int i = lane; i < CS; i += 32) {
             q.cur_c[i] = make_uchar4(0, 1, 2, 3);
+            q.last_t[i] = -1;
+        }
         for (int i = lane; i < nw; i += 32)
             q.bits[i] = 0u;
     }
@@ -851,7 +879,7 @@ size_t fsg_active_ws_ints(const DevModel &m, int n_pnode)
 {
     const size_t nw = (m.n_sen + 31) / 32, CS = (size_t)m.n_mgau * m.n_feat;
     const size_t cap_ev = (3 * (size_t)n_pnode + m.n_sen / 255 + 8 + 1) & ~(size_t)1;
-    size_t n = 4 * CS + CS + CS + nw + cap_ev / 2 + cap_ev / 2 + ((size_t)m.n_sen + 1) / 2;
+    size_t n = 4 * CS + CS + CS + CS + nw + cap_ev / 2 + cap_ev / 2 + ((size_t)m.n_sen + 1) / 2;
     return (n + 3) & ~(size_t)3;  // keeps every utterance's int4 block 16-byte aligned
 }
 

@@ -217,3 +217,55 @@ def test_fsg_active_lists_need_the_ptm_tensor_core_path(models, golden, fsg_gold
     monkeypatch.setenv("SSB_K1", "fp32")
     with pytest.raises(ssb.SsbError, match="active lists need"):
         ssb.fsg_batch(m, [golden["en-us"]["feat"][:20]], [graph_of(g, "align")], compallsen=False)
+
+
+def _tie_heavy(feat, kind):
+    """Inputs on which integer Gaussian scores tie massively: far from every mean the float
+    distances are coarser than 1 (or clamp at INT32_MIN), so the reference's carried-list rules
+    (eval_topn's stable re-sort on every frame, eval_cb's newcomer-before-equals) decide."""
+    f = feat.copy()
+    if kind == "x300":
+        f *= np.float32(300)
+    elif kind == "x3000":
+        f *= np.float32(3000)
+    elif kind == "every5th":
+        f[::5] *= np.float32(300)
+    elif kind == "bursts":
+        f[40:60] *= np.float32(3000)
+        f[120:123] *= np.float32(100)
+        f[200:] *= np.float32(30)
+    return f
+
+
+@pytest.mark.parametrize("kind", ["x300", "x3000", "every5th", "bursts"])
+def test_fsg_active_lists_when_scores_tie(models, oracles, golden, fsg_golden, kind):
+    m, o = models("en-us"), oracles("en-us")
+    g, feat = fsg_golden["en-us"], golden["en-us"]["feat"]
+    graphs = [graph_of(g, "align"), graph_of(g, "jsgf")]
+    feats = [_tie_heavy(feat, kind), _tie_heavy(feat[:150], kind), _tie_heavy(feat[30:], kind)]
+    res = ssb.fsg_batch(m, feats, graphs, utt_graph=[0, 1, 0], want_hist=True, compallsen=False)
+    for u, (f, r) in enumerate(zip(feats, res)):
+        w = o.fsg_search_active(graphs[[0, 1, 0][u]], f)
+        assert r["rv"] == w["rv"] == 0, u
+        assert np.array_equal(r["hist"], w["hist"]), u
+        assert r["n_sen_eval"] == w["n_sen_eval"] and np.array_equal(r["active"], w["active"]), u
+        assert r["exit"] == w["exit"] and (w["exit"] <= 0 or r["hyp_score"] == w["hyp_score"]), u
+
+
+@pytest.mark.parametrize("kind", ["x300", "x3000", "every5th", "bursts"])
+def test_dense_and_aligner_when_scores_tie(models, oracles, golden, kind):
+    """The same inputs through K1's own slow path: dense scores (every codebook scanned on
+    every frame) and the aligner's planned active sets (codebooks join over time)."""
+    from conftest import chain_from_golden
+    m, o, g = models("en-us"), oracles("en-us"), golden["en-us"]
+    f = _tie_heavy(g["feat"], kind)
+    assert np.array_equal(ssb.score_batch(m, [f[:120]])[0], o.score_all(f[:120]))
+    chain = chain_from_golden(g)
+    for c in (chain, dict(chain, sf=chain["sf"] * 0, ef=chain["ef"] * 0 + ssb.INT_MAX)):
+        r = ssb.align_batch(m, [f], [c], want_chain_scr=True)[0]
+        w = o.state_align(f, c["ssid"], c["tmat"], c["sf"], c["ef"], want_senscr=True)
+        sen = o.model_arrays()["sseq"][c["ssid"]].reshape(-1)
+        assert np.array_equal(r["chain_scr"], w["senscr"][:, sen])
+        assert r["rv"] == w["rv"] and r["best_score"] == w["best_score"]
+        if w["rv"] == 0:
+            assert np.array_equal(r["start"], w["start"]) and np.array_equal(r["score"], w["score"])
