@@ -37,6 +37,9 @@ int launch_cont_dense(const DevModel &m, const float *feat, int64_t g0, int64_t 
 int launch_cont_active(const DevModel &m, const DevPlan &p, const float *feat, int W,
                        int max_frames_per_utt, int16_t *scratch, int16_t *chain_scr,
                        cudaStream_t st);
+int launch_topn_fixup(const DevModel &m, const DevPlan &p, const int32_t *seg_utts, int n_seg_utts,
+                      const float *feat, int64_t n_frames, int4 *tn_s, uchar4 *tn_c,
+                      const uint32_t *tie, int64_t tie_w, cudaStream_t st);
 int launch_cont_frame(const DevModel &m, const float *x, const uint16_t *act_sen, int n_act,
                       int compallsen, int16_t *raw, int16_t *senscr, cudaStream_t st);
 }  // namespace ssb
@@ -44,6 +47,24 @@ int launch_cont_frame(const DevModel &m, const float *x, const uint16_t *act_sen
 using namespace ssb;
 
 // ------------------------------------------------------------------ small helpers
+namespace ssb {
+cudaError_t raise_dyn_smem_limit(const void *kernel, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> limit;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    size_t &cur = limit[std::make_pair(dev, kernel)];
+    if (bytes <= cur)
+        return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess)
+        cur = bytes;
+    return e;
+}
+}  // namespace ssb
+
 namespace {
 
 template <class T>
@@ -621,6 +642,12 @@ struct ssb_batch_s {
     DBuf dense, best_tmp;
     DevPlan plan{};
     int64_t spill_stride = 0;
+    // K1 over time (topn_fixup.cu): long utterances of a small batch cut into segments
+    bool k1_seg = false;
+    DevPlan k1_plan{};
+    DBuf d_k1_frame_off, d_k1_ep_off, d_k1_ep_start, d_k1_ep_cbmask, d_seg_utts, d_k1_tie;
+    int n_seg_utts = 0, n_k1_rows = 0;
+    int64_t k1_tie_w = 0;
     // timing
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int n_launches = 0;
@@ -631,7 +658,9 @@ struct ssb_batch_s {
                              &d_phone_off, &d_scr_off, &d_ssid, &d_tmat, &d_sf, &d_ef, &d_ep_off,
                              &d_ep_start, &d_ep_cbmask, &d_ep_slot_off, &d_ep_slot, &d_us_off,
                              &d_usen, &d_st_slot, &d_enter, &st_start, &st_dur, &st_score, &utt_rv,
-                             &utt_best, &utt_renorm, &fin_hist, &fin_score, &dense, &best_tmp};
+                             &utt_best, &utt_renorm, &fin_hist, &fin_score, &dense, &best_tmp,
+                             &d_k1_frame_off, &d_k1_ep_off, &d_k1_ep_start, &d_k1_ep_cbmask,
+                             &d_seg_utts, &d_k1_tie};
         size_t n = 0;
         for (const DBuf *b : all)
             n += b->cap;
@@ -643,7 +672,8 @@ struct ssb_batch_s {
                        &d_phone_off, &d_scr_off, &d_ssid, &d_tmat, &d_sf, &d_ef, &d_ep_off,
                        &d_ep_start, &d_ep_cbmask, &d_ep_slot_off, &d_ep_slot, &d_us_off, &d_usen,
                        &d_st_slot, &d_enter, &st_start, &st_dur, &st_score, &utt_rv, &utt_best,
-                       &utt_renorm, &fin_hist, &fin_score, &dense, &best_tmp};
+                       &utt_renorm, &fin_hist, &fin_score, &dense, &best_tmp, &d_k1_frame_off,
+                       &d_k1_ep_off, &d_k1_ep_start, &d_k1_ep_cbmask, &d_seg_utts, &d_k1_tie};
         for (DBuf *b : all)
             b->release();
     }
@@ -1065,6 +1095,113 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
     p.all_active = b->compallsen;
     p.tie_bits = nullptr;
     p.tie_w = 0;
+
+    // ---- K1 over time: with few utterances the top-N kernel (thread = utterance) has no rows
+    // to fill its CTAs with, so long utterances are cut into segments that are scored
+    // independently; the steps whose result depends on the carried list (ties) are replayed
+    // afterwards (topn_fixup.cu).  $SSB_K1_SEG forces a segment length (tests).
+    b->k1_seg = false;
+    b->n_seg_utts = 0;
+    {
+        const char *force = getenv("SSB_K1_SEG");
+        const char *k1 = getenv("SSB_K1");
+        int64_t seg = 0;
+        if (tc_supported(b->m->d) && !(k1 && *k1) && h.cfg.ds <= 1 && U > 0 && G > 0) {
+            if (force && atoll(force) > 0)
+                seg = atoll(force);
+            else if (U <= 512 && b->max_T >= 8192)
+                seg = std::min<int64_t>(4096, std::max<int64_t>(512, G / 2048));
+        }
+        if (seg > 0) {
+            std::vector<int64_t> kfo(1, 0);
+            std::vector<int32_t> kep_off(1, 0), kep_start, seg_utts;
+            std::vector<uint32_t> kep_mask;
+            for (int u = 0; u < U; ++u) {
+                const int64_t f0 = b->frame_off[u];
+                const int T = (int)(b->frame_off[u + 1] - f0);
+                const bool cut = T > 2 * seg;
+                if (cut)
+                    seg_utts.push_back(u);
+                const int64_t step = cut ? seg : std::max(T, 1);
+                for (int64_t s0 = 0; s0 < std::max(T, 1); s0 += step) {
+                    const int64_t s1 = std::min<int64_t>(T, s0 + step);
+                    kfo.push_back(f0 + s1);
+                    if (!b->compallsen) {
+                        // the parent's epoch in force at s0, then those starting inside the segment
+                        int last = -1;
+                        for (int e = ep_off[u]; e < ep_off[u + 1] && ep_start[e] <= s0; ++e)
+                            last = e;
+                        if (last >= 0) {
+                            kep_start.push_back(0);
+                            kep_mask.insert(kep_mask.end(), ep_cbmask.begin() + (size_t)last * 8,
+                                            ep_cbmask.begin() + (size_t)last * 8 + 8);
+                        }
+                        for (int e = std::max(last + 1, ep_off[u]); e < ep_off[u + 1]; ++e)
+                            if (ep_start[e] > s0 && ep_start[e] < s1) {
+                                kep_start.push_back((int32_t)(ep_start[e] - s0));
+                                kep_mask.insert(kep_mask.end(), ep_cbmask.begin() + (size_t)e * 8,
+                                                ep_cbmask.begin() + (size_t)e * 8 + 8);
+                            }
+                    }
+                    kep_off.push_back((int32_t)kep_start.size());
+                }
+            }
+            if (!seg_utts.empty()) {
+                if (kep_start.empty()) {  // keep the uploads non-empty
+                    kep_start.push_back(0);
+                    kep_mask.assign(8, 0u);
+                }
+                b->k1_tie_w = (G + 31) / 32 + 1;
+                if (upload(b->d_k1_frame_off, kfo, st) || upload(b->d_k1_ep_off, kep_off, st)
+                    || upload(b->d_k1_ep_start, kep_start, st) || upload(b->d_k1_ep_cbmask, kep_mask, st)
+                    || upload(b->d_seg_utts, seg_utts, st)
+                    || b->d_k1_tie.ensure((size_t)CS * b->k1_tie_w * 4 + 16) != 0)
+                    return -1;
+                API_CUDA(cudaStreamSynchronize(st), -1);
+                b->k1_seg = true;
+                b->n_seg_utts = (int)seg_utts.size();
+                b->n_k1_rows = (int)kfo.size() - 1;
+                b->k1_plan = p;
+                b->k1_plan.n_utts = b->n_k1_rows;
+                b->k1_plan.frame_off = b->d_k1_frame_off.as<int64_t>();
+                b->k1_plan.ep_off = b->d_k1_ep_off.as<int32_t>();
+                b->k1_plan.ep_start = b->d_k1_ep_start.as<int32_t>();
+                b->k1_plan.ep_cbmask = b->d_k1_ep_cbmask.as<uint32_t>();
+            }
+        }
+    }
+    return 0;
+}
+
+// K1 for the uploaded batch.  `tie` (optional, zeroed by the caller, [CS][tie_w] words) receives
+// the tie flags; when the batch's long utterances were cut into segments the flagged steps are
+// replayed afterwards unless the caller does that itself (`fixup` = false: the grammar search in
+// its default mode never reads them).
+static int batch_topn(ssb_batch_t *b, uint32_t *tie, int64_t tie_w, bool fixup)
+{
+    const DevModel &d = b->m->d;
+    cudaStream_t st = b->st;
+    const int64_t G = b->n_frames;
+    if (b->n_utts == 0 || G == 0)
+        return 0;
+    DevPlan p = b->k1_seg ? b->k1_plan : b->plan;
+    if (b->k1_seg && !tie) {
+        tie = b->d_k1_tie.as<uint32_t>();
+        tie_w = b->k1_tie_w;
+        if (cudaMemsetAsync(tie, 0, (size_t)d.n_mgau * d.n_feat * tie_w * 4, st) != cudaSuccess) {
+            set_error("cudaMemsetAsync failed");
+            return -1;
+        }
+    }
+    p.tie_bits = tie;
+    p.tie_w = tie_w;
+    if (launch_gmm_topn(d, p, b->feat.as<float>(), G, b->tn_s.as<int4>(), b->tn_c.as<uchar4>(),
+                        b->featp.as<float>(), st) != 0)
+        return -1;
+    if (b->k1_seg && fixup)
+        return launch_topn_fixup(d, b->plan, b->d_seg_utts.as<int32_t>(), b->n_seg_utts,
+                                 b->feat.as<float>(), G, b->tn_s.as<int4>(), b->tn_c.as<uchar4>(),
+                                 tie, tie_w, st);
     return 0;
 }
 
@@ -1087,8 +1224,7 @@ extern "C" int ssb_batch_run(ssb_batch_t *b)
     launch_count(true);
     API_CUDA(cudaEventRecord(b->ev[0], st), -1);
     if (U > 0 && b->n_frames > 0) {
-        if (launch_gmm_topn(d, p, b->feat.as<float>(), b->n_frames, b->tn_s.as<int4>(),
-                            b->tn_c.as<uchar4>(), b->featp.as<float>(), st) != 0)
+        if (batch_topn(b, nullptr, 0, true) != 0)
             return -1;
     }
     API_CUDA(cudaEventRecord(b->ev[1], st), -1);
@@ -1653,8 +1789,7 @@ extern "C" int64_t ssb_score_batch(ssb_model_t *m, const float *feat, const int6
             rv = 0;
             break;
         }
-        if (launch_gmm_topn(d, b->plan, b->feat.as<float>(), G, b->tn_s.as<int4>(),
-                            b->tn_c.as<uchar4>(), b->featp.as<float>(), b->st) != 0)
+        if (batch_topn(b, nullptr, 0, true) != 0)
             break;
         bool ok = true;
         for (int64_t g0 = 0; g0 < G && ok; g0 += kSlabFrames) {
@@ -1702,8 +1837,7 @@ static int64_t topn_impl(ssb_model_t *m, const float *feat, const int64_t *frame
             break;
         }
         if (!probe) {
-            if (launch_gmm_topn(d, b->plan, b->feat.as<float>(), G, b->tn_s.as<int4>(),
-                                b->tn_c.as<uchar4>(), b->featp.as<float>(), b->st) != 0)
+            if (batch_topn(b, nullptr, 0, true) != 0)
                 break;
         } else {
             if (!tc_supported(d)) {
@@ -2006,9 +2140,8 @@ extern "C" int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out
         }
         launch_count(true);
         cudaEventRecord(b->ev[0], st);
-        if (G > 0
-            && launch_gmm_topn(d, plan, b->feat.as<float>(), G, b->tn_s.as<int4>(),
-                               b->tn_c.as<uchar4>(), b->featp.as<float>(), st) != 0)
+        // (the default-mode search replays tie steps from its own carried lists: no fix-up pass)
+        if (G > 0 && batch_topn(b, plan.tie_bits, plan.tie_w, !active) != 0)
             break;
         cudaEventRecord(b->ev[1], st);
         // dense senone scores slab by slab (whole utterances), searched as soon as they exist

@@ -224,14 +224,12 @@ int launch_chain_viterbi(const DevModel &m, const DevPlan &p, const int16_t *cha
         smem_phones = max_phones;
     const size_t smem = per_phone * smem_phones;
     if (E == 3) {
-        SSB_CUDA(cudaFuncSetAttribute(chain_viterbi_kernel<3>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SSB_DYN_SMEM((chain_viterbi_kernel<3>), smem);
         chain_viterbi_kernel<3><<<p.n_utts, threads, smem, st>>>(
             m, p, chain_scr, tokens, spill, spill_stride, utt_best, utt_renorm, fin_hist,
             fin_score, smem_phones);
     } else {
-        SSB_CUDA(cudaFuncSetAttribute(chain_viterbi_kernel<5>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SSB_DYN_SMEM((chain_viterbi_kernel<5>), smem);
         chain_viterbi_kernel<5><<<p.n_utts, threads, smem, st>>>(
             m, p, chain_scr, tokens, spill, spill_stride, utt_best, utt_renorm, fin_hist,
             fin_score, smem_phones);

@@ -18,6 +18,13 @@ namespace ssb {
         }                                                                                   \
     } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is state of the (device, kernel) pair, shared by
+// every host thread: several batches launch the same kernel with different sizes (the lanes of
+// ssb_pipeline_*), so the limit is only ever raised, under a lock (api.cu).
+cudaError_t raise_dyn_smem_limit(const void *kernel, size_t bytes);
+#define SSB_DYN_SMEM(kernel, bytes) \
+    SSB_CUDA(ssb::raise_dyn_smem_limit(reinterpret_cast<const void *>(&kernel), (bytes)))
+
 constexpr int32_t WORST_SCORE = (int32_t)0xE0000000;
 constexpr int MAX_NEG_ASCR = 96;
 constexpr int SENSCR_SHIFT = 10;

@@ -330,8 +330,7 @@ static int launch_k1_n(const DevModel &m, const DevPlan &p, const float *feat, i
     dim3 grid(m.n_mgau * m.n_feat, (p.n_utts + K1_THREADS - 1) / K1_THREADS);
 #define SSB_K1(NN)                                                                          \
     case NN:                                                                                \
-        SSB_CUDA(cudaFuncSetAttribute(gmm_topn_kernel<L, NN>,                               \
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        SSB_DYN_SMEM((gmm_topn_kernel<L, NN>), smem); \
         gmm_topn_kernel<L, NN><<<grid, K1_THREADS, smem, st>>>(m, p, feat, G, s, c);        \
         break;
     switch (m.topn) {

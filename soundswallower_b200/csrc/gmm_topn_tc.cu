@@ -282,8 +282,7 @@ int launch_gmm_topn_tc(const DevModel &m, const DevPlan &p, const float *feat, i
     dim3 grid(m.n_mgau * m.n_feat, (p.n_utts + TC_THREADS - 1) / TC_THREADS);
 #define SSB_TC(NN, DBG)                                                                         \
     do {                                                                                        \
-        SSB_CUDA(cudaFuncSetAttribute(gmm_topn_tc_kernel<NN, DBG>,                              \
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        SSB_DYN_SMEM((gmm_topn_tc_kernel<NN, DBG>), smem); \
         gmm_topn_tc_kernel<NN, DBG><<<grid, TC_THREADS, smem, st>>>(m, p, feat, n_frames, m.gB, \
                                                                     m.gAux, tn_score, tn_cw, dbg); \
     } while (0)

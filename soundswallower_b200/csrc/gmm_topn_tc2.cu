@@ -565,8 +565,7 @@ int launch_gmm_topn_tc2(const DevModel &m, const DevPlan &p, const float *feat, 
     dim3 grid(m.n_mgau * m.n_feat, (p.n_utts + TC2_THREADS - 1) / TC2_THREADS);
 #define SSB_TC2(NN, DBG)                                                                        \
     do {                                                                                        \
-        SSB_CUDA(cudaFuncSetAttribute(gmm_topn_tc2_kernel<NN, DBG>,                             \
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        SSB_DYN_SMEM((gmm_topn_tc2_kernel<NN, DBG>), smem); \
         gmm_topn_tc2_kernel<NN, DBG><<<grid, TC2_THREADS, smem, st>>>(m, p, featp, n_frames,    \
                                                                       tn_score, tn_cw, dbg);    \
     } while (0)

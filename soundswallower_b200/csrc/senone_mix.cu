@@ -270,8 +270,7 @@ int launch_senone_mix_active(const DevModel &m, const DevPlan &p, const int4 *tn
     const bool ptm4 = m.kind == SSB_SCORER_PTM && m.topn == 4;
 #define SSB_K2(ST, P4)                                                                              \
     do {                                                                                            \
-        SSB_CUDA(cudaFuncSetAttribute(senone_mix_active_kernel<ST, P4>,                             \
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        SSB_DYN_SMEM((senone_mix_active_kernel<ST, P4>), smem);     \
         senone_mix_active_kernel<ST, P4>                                                            \
             <<<grid, K2_THREADS, smem, st>>>(m, p, tn_score, tn_cw, n_frames, W, chunk, chain_scr); \
     } while (0)
@@ -429,8 +428,7 @@ int launch_senone_mix_all(const DevModel &m, const int4 *tn_score, const uchar4 
         return -1;
     }
     const size_t smem = need(F);
-    SSB_CUDA(cudaFuncSetAttribute(senone_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
+    SSB_DYN_SMEM((senone_dense_kernel), smem);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     const int64_t tiles = (n + F - 1) / F;

@@ -1,6 +1,7 @@
 """Parity of the CUDA path (through the C ABI) with the oracle and the golden vectors.
 Integer work is compared bit for bit."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -349,7 +350,8 @@ def test_align_states_off_path_keep_caller_values(models, golden):
     res = b.per_utt(b.download(init=init))
     assert res[0]["rv"] == 0 and np.array_equal(res[0]["dur"], g["win_states"][:, 2])
     assert res[1]["rv"] == -1 and (res[1]["dur"] == 888).all() and (res[1]["start"] == 777).all()
-    assert b.n_launches() == 5  # pack_features, gmm_topn_tc2, senone_mix, chain_viterbi, backtrace
+    # pack_features, gmm_topn_tc2, senone_mix, chain_viterbi, backtrace (+ topn_fixup when segmented)
+    assert b.n_launches() == (6 if os.environ.get("SSB_K1_SEG") else 5)
     ms = b.kernel_ms()
     assert ms["total"] > 0
     st = b.stats()
@@ -552,3 +554,45 @@ def test_long_form_five_minute_prefix(models, oracles, golden):
     assert start[0] == 0 and (start[1:] == start[:-1] + dur[:-1]).all() and start[-1] + dur[-1] == x.shape[0]
     sf, ef = np.repeat(chain["sf"], 3)[on], np.repeat(chain["ef"], 3)[on]
     assert (start >= sf).all() and (start + dur <= ef).all()
+
+
+# ---- K1 over time: long utterances of small batches are scored in independent segments and
+# ---- the tie steps replayed afterwards (csrc/topn_fixup.cu); $SSB_K1_SEG forces it everywhere
+@pytest.mark.parametrize("seg", [5, 37])
+def test_segmented_topn_equals_oracle(models, oracles, golden, monkeypatch, seg):
+    m, o = models("en-us"), oracles("en-us")
+    feat = golden["en-us"]["feat"]
+    rs = np.random.RandomState(seg)
+    feats = [feat, feat[:101], (feat[50:] * np.float32(300)).astype(np.float32)]
+    f4 = feat.copy()
+    f4[::7] *= np.float32(3000)         # tie steps sprinkled over segment boundaries
+    feats.append(f4)
+    monkeypatch.setenv("SSB_K1_SEG", str(seg))
+    cw, sc = ssb.topn_batch(m, feats)
+    dense = ssb.score_batch(m, feats)
+    for u, f in enumerate(feats):
+        wcw, wsc = o.topn_all(f)
+        assert np.array_equal(cw[u], wcw) and np.array_equal(sc[u], wsc), u
+        assert np.array_equal(dense[u], o.score_all(f)), u
+
+
+@pytest.mark.parametrize("seg", [5, 37])
+def test_segmented_aligner_equals_oracle(models, oracles, golden, monkeypatch, seg):
+    """Active sets that grow over time: the segment that a codebook's first scan falls into, and
+    the carried list that eval_topn has been re-sorting since the utterance began."""
+    m, o, g = models("en-us"), oracles("en-us"), golden["en-us"]
+    chain = chain_from_golden(g)
+    nowin = dict(chain, sf=chain["sf"] * 0, ef=chain["ef"] * 0 + ssb.INT_MAX)
+    f_tie = g["feat"].copy()
+    f_tie[::5] *= np.float32(300)
+    f_all = (g["feat"] * np.float32(3000)).astype(np.float32)
+    cases = [(g["feat"], chain), (g["feat"], nowin), (f_tie, chain), (f_tie, nowin), (f_all, nowin)]
+    monkeypatch.setenv("SSB_K1_SEG", str(seg))
+    res = ssb.align_batch(m, [c[0] for c in cases], [c[1] for c in cases], want_chain_scr=True)
+    for u, ((f, c), r) in enumerate(zip(cases, res)):
+        w = o.state_align(f, c["ssid"], c["tmat"], c["sf"], c["ef"], want_senscr=True)
+        sen = o.model_arrays()["sseq"][c["ssid"]].reshape(-1)
+        assert np.array_equal(r["chain_scr"], w["senscr"][:, sen]), u
+        assert r["rv"] == w["rv"] and r["best_score"] == w["best_score"], u
+        if w["rv"] == 0:
+            assert np.array_equal(r["start"], w["start"]) and np.array_equal(r["score"], w["score"]), u
