@@ -240,17 +240,21 @@ int launch_chain_viterbi(const DevModel &m, const DevPlan &p, const int16_t *cha
 }
 
 // ---------------------------------------------------------------- backtrace
-// ref: src/state_align_search.c:215-268.  One thread per utterance; the walk is a
-// chain of dependent 8-byte loads, so the only parallelism is across utterances.
-// States that are not on the best path keep the sentinel duration -1 so the host
-// leaves the caller's entries untouched (the reference never writes them either).
-__global__ void backtrace_kernel(DevModel m, DevPlan p, const int2 *__restrict__ tokens,
-                                 const int32_t *__restrict__ fin_hist,
-                                 const int32_t *__restrict__ fin_score,
-                                 int32_t *__restrict__ st_start, int32_t *__restrict__ st_dur,
-                                 int32_t *__restrict__ st_score, int32_t *__restrict__ utt_rv)
+// ref: src/state_align_search.c:215-268.  The walk t = T-2 .. 0 is a chain of dependent 8-byte
+// loads, cur = tokens[t][cur.id] -- but the id changes only ~once per state (every 6-12 frames),
+// so one WARP per utterance reads the tokens of 32 consecutive frames at the current state's
+// column speculatively and consumes them up to the first frame on which the stored id differs
+// (or the token is missing): one memory latency per state run instead of one per frame.
+// States that are not on the best path keep the sentinel duration -1 so the host leaves the
+// caller's entries untouched (the reference never writes them either).
+__global__ void __launch_bounds__(128)
+backtrace_kernel(DevModel m, DevPlan p, const int2 *__restrict__ tokens,
+                 const int32_t *__restrict__ fin_hist, const int32_t *__restrict__ fin_score,
+                 int32_t *__restrict__ st_start, int32_t *__restrict__ st_dur,
+                 int32_t *__restrict__ st_score, int32_t *__restrict__ utt_rv)
 {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (u >= p.n_utts)
         return;
     const int T = (int)(p.frame_off[u + 1] - p.frame_off[u]);
@@ -258,45 +262,65 @@ __global__ void backtrace_kernel(DevModel m, DevPlan p, const int2 *__restrict__
     const int ns = (int)(p.phone_off[u + 1] - p.phone_off[u]) * m.n_emit;
     const int2 *tok = tokens + p.scr_off[u];
     if (ns == 0) {
-        utt_rv[u] = -1;
+        if (lane == 0)
+            utt_rv[u] = -1;
         return;
     }
     int32_t last_id = fin_hist[u], last_score = fin_score[u];
     if (last_id == -1) {
-        utt_rv[u] = -1;  // "Failed to reach final state in alignment"
+        if (lane == 0)
+            utt_rv[u] = -1;  // "Failed to reach final state in alignment"
         return;
     }
     const int32_t *enter = p.enter_plan + p.phone_off[u];
     const int32_t *ef = p.ef + p.phone_off[u];
     int32_t cur_id = last_id, last_frame = T;
-    for (int cur_frame = T - 2; cur_frame >= 0; --cur_frame) {
+    int cur_frame = T - 2;
+    while (cur_frame >= 0) {
+        const int fr = cur_frame - lane;
         // a token exists for (frame, state) only if the phone was evaluated on that frame or
         // entered at its end; the reference reads {-1,-1} otherwise (its 0xff-filled stack)
         const int ph = cur_id / m.n_emit;
-        const int32_t en = enter[ph];
-        if (en < 0 || en > cur_frame + 1 || (en <= cur_frame && cur_frame > max(en, ef[ph]))) {
-            utt_rv[u] = -1;
+        const int32_t en = enter[ph], efp = ef[ph];
+        int2 tk = make_int2(cur_id, 0);
+        bool event = false;
+        if (fr >= 0) {
+            const bool missing = en < 0 || en > fr + 1 || (en <= fr && fr > max(en, efp));
+            if (missing)
+                tk.x = -1;
+            else
+                tk = tok[(int64_t)fr * ns + cur_id];
+            event = tk.x != cur_id;
+        }
+        const unsigned ev = __ballot_sync(0xffffffffu, event);
+        if (ev == 0u) {  // 32 more frames in the same state (or the beginning of the utterance)
+            cur_frame -= 32;
+            continue;
+        }
+        const int k = __ffs((int)ev) - 1;
+        const int32_t nid = __shfl_sync(0xffffffffu, tk.x, k), nsc = __shfl_sync(0xffffffffu, tk.y, k);
+        const int f = cur_frame - k;
+        if (nid == -1) {
+            if (lane == 0)
+                utt_rv[u] = -1;
             return;
         }
-        const int2 tk = tok[(int64_t)cur_frame * ns + cur_id];
-        cur_id = tk.x;
-        if (cur_id == -1) {
-            utt_rv[u] = -1;
-            return;
+        if (lane == 0) {
+            st_start[s0 + last_id] = f + 1;
+            st_dur[s0 + last_id] = last_frame - (f + 1);
+            st_score[s0 + last_id] = last_score - nsc;
         }
-        if (cur_id != last_id) {
-            st_start[s0 + last_id] = cur_frame + 1;
-            st_dur[s0 + last_id] = last_frame - (cur_frame + 1);
-            st_score[s0 + last_id] = last_score - tk.y;
-            last_id = cur_id;
-            last_score = tk.y;
-            last_frame = cur_frame + 1;
-        }
+        last_id = cur_id = nid;
+        last_score = nsc;
+        last_frame = f + 1;
+        cur_frame = f - 1;
     }
-    // first state: score left alone by the reference (ref :256-261); report 0
-    st_start[s0] = 0;
-    st_dur[s0] = last_frame;
-    utt_rv[u] = 0;
+    if (lane == 0) {
+        // first state: score left alone by the reference (ref :256-261); report 0
+        st_start[s0] = 0;
+        st_dur[s0] = last_frame;
+        utt_rv[u] = 0;
+    }
 }
 
 int launch_backtrace(const DevModel &m, const DevPlan &p, const int2 *tokens,
@@ -305,8 +329,8 @@ int launch_backtrace(const DevModel &m, const DevPlan &p, const int2 *tokens,
 {
     if (p.n_utts == 0)
         return 0;
-    backtrace_kernel<<<(p.n_utts + 63) / 64, 64, 0, st>>>(m, p, tokens, fin_hist, fin_score,
-                                                          st_start, st_dur, st_score, utt_rv);
+    backtrace_kernel<<<(p.n_utts + 3) / 4, 128, 0, st>>>(m, p, tokens, fin_hist, fin_score,
+                                                         st_start, st_dur, st_score, utt_rv);
     SSB_CUDA(cudaGetLastError());
     note_launch();
     return 0;
