@@ -553,10 +553,10 @@ fsg_search_kernel(DevModel m, DevFsgSet gs, FsgActiveArgs aa, const int64_t *__r
     if (u >= u0 + n_utts)
         return;
     __shared__ float sh_sd[4][128];
-    __shared__ uint8_t sh_lut[256];
-    if (ACTIVE) {  // every warp fills the table with the same bytes: no block barrier needed
+    __shared__ uint8_t sh_lut[4][256];
+    if (ACTIVE) {  // a private copy per warp: warps are independent, no block barrier anywhere
         for (int i = lane; i < 256; i += 32)
-            sh_lut[i] = m.lut8[i];
+            sh_lut[threadIdx.x >> 5][i] = m.lut8[i];
         __syncwarp();
     }
     FsgUtt s;
@@ -611,7 +611,7 @@ fsg_search_kernel(DevModel m, DevFsgSet gs, FsgActiveArgs aa, const int64_t *__r
         a += cap_ev / 2;
         q.scr = reinterpret_cast<int16_t *>(a);
         q.sd = sh_sd[threadIdx.x >> 5];
-        q.lut = sh_lut;
+        q.lut = sh_lut[threadIdx.x >> 5];
         // the list a codebook carries before its first scan (ref: src/ptm_mgau.c:694-720)
         for (int i = lane; i < CS; i += 32) {
             q.cur_c[i] = make_uchar4(0, 1, 2, 3);
