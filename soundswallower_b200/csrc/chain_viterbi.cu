@@ -106,13 +106,21 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
 
     int32_t best = 0, n_renorm = 0;
     int lo = 0, hiq = 0;  // phones [lo, hiq] are evaluated on frame t
+    // the two plan values the band bookkeeping looks at on every frame, kept in registers:
+    // the entry frame of the next phone (-1: none / never) and the last frame of phone lo
+    int nx_en = np > 1 ? enter[1] : -1;
+    int lo_end = max(enter[0], ef[0]);
     for (int t = 0; t < T; ++t) {
         const int nf = t + 1;
-        while (hiq + 1 < np && enter[hiq + 1] >= 0 && enter[hiq + 1] <= t)
+        while (nx_en >= 0 && nx_en <= t) {
             ++hiq;
-        while (lo < hiq && max(enter[lo], ef[lo]) < t)
+            nx_en = hiq + 1 < np ? enter[hiq + 1] : -1;
+        }
+        while (lo < hiq && lo_end < t) {
             ++lo;
-        const bool lo_alive = max(enter[lo], ef[lo]) >= t;  // lo == hiq may have expired too
+            lo_end = max(enter[lo], ef[lo]);
+        }
+        const bool lo_alive = lo_end >= t;  // lo == hiq may have expired too
         // renormalize_hmms (ref: state_align_search.c:57-64,193-197; hmm.c:150-161):
         // every phone, alive or not, whose scores are above WORST_SCORE
         if (best - 0x300000 < WORST_SCORE) {
@@ -129,6 +137,8 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
         }
         // evaluate_hmms (ref :66-86)
         int32_t lb = WORST_SCORE;
+        const int16_t *scr_t = scr + (int64_t)t * ns;
+        int2 *tok_t = tok + (int64_t)t * ns;
         if (lo_alive) {
             for (int i = lo + threadIdx.x; i <= hiq; i += blockDim.x) {
                 int32_t s[E], h[E], o_s = osc[i], o_h = ohi[i];
@@ -137,8 +147,10 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
                 for (int j = 0; j < E; ++j) {
                     s[j] = sc[j * np + i];
                     h[j] = hi[j * np + i];
-                    ss[j] = scr[(int64_t)t * ns + i * E + j];
                 }
+#pragma unroll
+                for (int j = 0; j < E; ++j)
+                    ss[j] = scr_t[i * E + j];
                 int32_t b = hmm_step<E>(m.tp + (size_t)tmat[i] * E * (E + 1), ss, s, h, o_s, o_h);
                 lb = max(lb, b);
 #pragma unroll
@@ -157,8 +169,11 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
         // (several when the reference's transition loop cascades along the chain).
         const int first = lo_alive ? lo : hiq + 1;
         int last_t = hiq;
-        while (last_t + 1 < np && enter[last_t + 1] == nf)
+        if (nx_en == nf) {
             ++last_t;
+            while (last_t + 1 < np && enter[last_t + 1] == nf)
+                ++last_t;
+        }
         for (int i = first + threadIdx.x; i <= last_t; i += blockDim.x) {
             const bool was_active = i <= hiq;  // evaluated on frame t
             bool now = was_active;             // hmm_frame(hmm) >= t after this step
@@ -187,7 +202,7 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
 #pragma unroll
                 for (int j = 0; j < E; ++j) {
                     const int si = i * E + j;
-                    tok[(int64_t)t * ns + si] = make_int2(hi[j * np + i], sc[j * np + i]);
+                    tok_t[si] = make_int2(hi[j * np + i], sc[j * np + i]);
                     hi[j * np + i] = si;
                 }
             }
