@@ -170,6 +170,15 @@ __device__ __forceinline__ void load_x(const float *__restrict__ p, float4 (&q)[
         q[i] = __ldg(p4 + i);
 }
 
+// the same 13 values straight from the caller's [frame][sum featlen] rows (4-byte aligned only)
+__device__ __forceinline__ void load_x_raw(const float *__restrict__ p, float4 (&q)[4])
+{
+    q[0] = make_float4(__ldg(p + 0), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+    q[1] = make_float4(__ldg(p + 4), __ldg(p + 5), __ldg(p + 6), __ldg(p + 7));
+    q[2] = make_float4(__ldg(p + 8), __ldg(p + 9), __ldg(p + 10), __ldg(p + 11));
+    q[3] = make_float4(__ldg(p + 12), 0.f, 0.f, 0.f);
+}
+
 __device__ __forceinline__ void unpack_x(const float4 (&q)[4], float (&x)[TC_L])
 {
     x[0] = q[0].x; x[1] = q[0].y; x[2] = q[0].z; x[3] = q[0].w;
@@ -178,7 +187,7 @@ __device__ __forceinline__ void unpack_x(const float4 (&q)[4], float (&x)[TC_L])
     x[12] = q[3].x;
 }
 
-template <int N, bool DEBUG>
+template <int N, bool DEBUG, bool RAW>
 __global__ void __launch_bounds__(TC2_THREADS, 2)
 gmm_topn_tc2_kernel(DevModel m, DevPlan p, const float *__restrict__ featp, int64_t G,
                     int4 *__restrict__ out_s, uchar4 *__restrict__ out_c, TcDebug dbg)
@@ -241,8 +250,9 @@ gmm_topn_tc2_kernel(DevModel m, DevPlan p, const float *__restrict__ featp, int6
     const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(grp * 128);
     const uint32_t rec_s = smem_u32(S.rec);
 
-    const int64_t xstride = (int64_t)m.n_feat * TC2_XP;
-    const float *xp = featp + (g0 * m.n_feat + f) * TC2_XP;
+    // RAW: featp is the caller's feature array itself (no re-packing pass)
+    const int64_t xstride = RAW ? (int64_t)m.blk : (int64_t)m.n_feat * TC2_XP;
+    const float *xp = RAW ? featp + g0 * m.blk + m.featoff[f] : featp + (g0 * m.n_feat + f) * TC2_XP;
     int4 *so = out_s + (int64_t)cs * G + g0;
     uchar4 *co = out_c + (int64_t)cs * G + g0;
     float4 *myAhi = reinterpret_cast<float4 *>(&S.A[grp][0][0]) + (row >> 3) * 64 + (row & 7) * 8;
@@ -280,8 +290,12 @@ gmm_topn_tc2_kernel(DevModel m, DevPlan p, const float *__restrict__ featp, int6
         float x[TC_L];
         float eps = 0.f, eps_hot = 0.f;
         if (scan) {
-            if (xn_t != t)
-                load_x(xp + (int64_t)t * xstride, xn);
+            if (xn_t != t) {
+                if (RAW)
+                    load_x_raw(xp + (int64_t)t * xstride, xn);
+                else
+                    load_x(xp + (int64_t)t * xstride, xn);
+            }
             unpack_x(xn, x);
             // A rows (hi, lo): [x' (13), x'^2 (13), 1, 1, 0 x4] / [x'_lo, x'^2_lo, 0 ...]
             float hi[TC_K], lo[TC_K];
@@ -359,7 +373,10 @@ gmm_topn_tc2_kernel(DevModel m, DevPlan p, const float *__restrict__ featp, int6
         }
         // next frame's features travel while the tensor core works
         if (scan && t + 1 < T) {
-            load_x(xp + (int64_t)(t + 1) * xstride, xn);
+            if (RAW)
+                load_x_raw(xp + (int64_t)(t + 1) * xstride, xn);
+            else
+                load_x(xp + (int64_t)(t + 1) * xstride, xn);
             xn_t = t + 1;
         }
         mbar_wait(&S.mbar[grp], n_mma & 1u);
@@ -492,7 +509,10 @@ gmm_topn_tc2_kernel(DevModel m, DevPlan p, const float *__restrict__ featp, int6
                     float xx[TC_L];
                     if (tt < t) {
                         float4 q[4];
-                        load_x(xp + (int64_t)tt * xstride, q);
+                        if (RAW)
+                            load_x_raw(xp + (int64_t)tt * xstride, q);
+                        else
+                            load_x(xp + (int64_t)tt * xstride, q);
                         unpack_x(q, xx);
                     } else {
 #pragma unroll
@@ -555,19 +575,31 @@ int launch_gmm_topn_tc2(const DevModel &m, const DevPlan &p, const float *feat, 
                         int4 *tn_score, uchar4 *tn_cw, float *featp, TcDebug dbg, cudaStream_t st)
 {
     const bool debug = dbg.approx != nullptr || dbg.counters != nullptr;
-    {
+    // SSB_K1_PACK=1 keeps the re-packing pass ([frame][stream][16], four aligned 16-byte loads
+    // per step); the default reads the caller's rows directly (13 scalar loads per step, one
+    // launch and 786 MB of scratch traffic less)
+    const char *pk = getenv("SSB_K1_PACK");
+    const bool raw = !(pk && *pk == '1');
+    if (!raw) {
         const int64_t n = n_frames * m.n_feat * TC2_XP;
         pack_features_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m, feat, n_frames, featp);
         SSB_CUDA(cudaGetLastError());
         note_launch();
     }
+    const float *src = raw ? feat : featp;
     const size_t smem = sizeof(Tc2Smem) + 1024;
     dim3 grid(m.n_mgau * m.n_feat, (p.n_utts + TC2_THREADS - 1) / TC2_THREADS);
-#define SSB_TC2(NN, DBG)                                                                        \
-    do {                                                                                        \
-        SSB_DYN_SMEM((gmm_topn_tc2_kernel<NN, DBG>), smem); \
-        gmm_topn_tc2_kernel<NN, DBG><<<grid, TC2_THREADS, smem, st>>>(m, p, featp, n_frames,    \
-                                                                      tn_score, tn_cw, dbg);    \
+#define SSB_TC2(NN, DBG)                                                                          \
+    do {                                                                                          \
+        if (raw) {                                                                                \
+            SSB_DYN_SMEM((gmm_topn_tc2_kernel<NN, DBG, true>), smem);                             \
+            gmm_topn_tc2_kernel<NN, DBG, true><<<grid, TC2_THREADS, smem, st>>>(m, p, src, n_frames, \
+                                                                                tn_score, tn_cw, dbg); \
+        } else {                                                                                  \
+            SSB_DYN_SMEM((gmm_topn_tc2_kernel<NN, DBG, false>), smem);                            \
+            gmm_topn_tc2_kernel<NN, DBG, false><<<grid, TC2_THREADS, smem, st>>>(m, p, src, n_frames, \
+                                                                                 tn_score, tn_cw, dbg); \
+        }                                                                                         \
     } while (0)
     switch (m.topn) {
     case 1:
@@ -594,6 +626,9 @@ int launch_gmm_topn_tc2(const DevModel &m, const DevPlan &p, const float *feat, 
 
 size_t tc2_featp_bytes(const DevModel &m, int64_t n_frames)
 {
+    const char *pk = getenv("SSB_K1_PACK");
+    if (!(pk && *pk == '1'))
+        return 16;  // the kernel reads the caller's rows directly; the pointer only has to exist
     return (size_t)n_frames * m.n_feat * TC2_XP * sizeof(float);
 }
 

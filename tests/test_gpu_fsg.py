@@ -27,7 +27,7 @@ def test_fsg_golden(models, golden, fsg_golden, lang, name):
     assert r["n_hmm_eval"] == int(g[name + "_n_hmm_eval"])
     assert r["hyp_score"] == int(g[name + "_hyp_score"])
     assert np.array_equal(r["segs"][:, 1:], g[name + "_segs"][:, 1:])
-    assert r["n_launches"] >= 5 and r["kernel_ms"]["fsg_search"] > 0
+    assert r["n_launches"] >= 4 and r["kernel_ms"]["fsg_search"] > 0
 
 
 def test_fsg_ragged_two_grammars(models, oracles, golden, fsg_golden):

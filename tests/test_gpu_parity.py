@@ -350,8 +350,9 @@ def test_align_states_off_path_keep_caller_values(models, golden):
     res = b.per_utt(b.download(init=init))
     assert res[0]["rv"] == 0 and np.array_equal(res[0]["dur"], g["win_states"][:, 2])
     assert res[1]["rv"] == -1 and (res[1]["dur"] == 888).all() and (res[1]["start"] == 777).all()
-    # pack_features, gmm_topn_tc2, senone_mix, chain_viterbi, backtrace (+ topn_fixup when segmented)
-    assert b.n_launches() == (6 if os.environ.get("SSB_K1_SEG") else 5)
+    # gmm_topn_tc2, senone_mix, chain_viterbi, backtrace (+ pack_features with SSB_K1_PACK=1,
+    # + topn_fixup when segmented)
+    assert b.n_launches() == 4 + bool(os.environ.get("SSB_K1_SEG")) + (os.environ.get("SSB_K1_PACK") == "1")
     ms = b.kernel_ms()
     assert ms["total"] > 0
     st = b.stats()
