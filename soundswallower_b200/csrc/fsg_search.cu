@@ -349,10 +349,13 @@ __device__ void replay_tie(const DevModel &m, const FsgScore &q, int cs, int t, 
 // Scores of frame t for the senones of the `n_act` active HMMs (+ the bridging entries of the
 // uint8 delta list).  Returns the best (smallest) raw score; the value the search sees for
 // senone s is (int16)(scr[s] - best) (ref: src/ptm_mgau.c:398-400).
+// FIX = the bundled models' shape at compile time (3 streams, top-4, 128 densities).
+template <bool FIX>
 __device__ int score_active_frame(const DevModel &m, const FsgUtt &s, const FsgScore &q, int t,
                                   int n_act, int lane, int &n_ev_out)
 {
-    const int nw = (m.n_sen + 31) >> 5, E = m.n_emit, NF = m.n_feat, CS = m.n_mgau * NF, N = m.topn;
+    const int NF = FIX ? 3 : m.n_feat, N = FIX ? 4 : m.topn;
+    const int nw = (m.n_sen + 31) >> 5, E = m.n_emit, CS = m.n_mgau * NF;
     // fsg_search_sen_active: acmod_clear_active + acmod_activate_hmm (ref :309-328)
     for (int w = lane; w < nw; w += 32)
         q.bits[w] = 0u;
@@ -490,7 +493,7 @@ __device__ int score_active_frame(const DevModel &m, const FsgUtt &s, const FsgS
     __syncwarp();
     // ptm_mgau_senone_eval (ref :326-403)
     int best = INT32_MAX;
-    const int ND = m.n_density;
+    const int ND = FIX ? 128 : m.n_density;
     for (int i = lane; i < n_ev; i += 32) {
         const int sen = q.ev[i];
         const int cb = m.sen2cb[sen];
@@ -539,7 +542,7 @@ struct FsgActiveArgs {       // mode "compallsen = no"
     int64_t *n_sen_eval;     // [U] or null
 };
 
-template <bool ACTIVE>
+template <bool ACTIVE, bool FIX>
 __global__ void __launch_bounds__(128)
 fsg_search_kernel(DevModel m, DevFsgSet gs, FsgActiveArgs aa, const int64_t *__restrict__ frame_off,
                   const int32_t *__restrict__ utt_graph, const int64_t *__restrict__ ws_off,
@@ -654,7 +657,7 @@ fsg_search_kernel(DevModel m, DevFsgSet gs, FsgActiveArgs aa, const int64_t *__r
         int sbest = 0;
         if (ACTIVE) {
             int n_ev = 0;
-            sbest = score_active_frame(m, s, q, t, n_act, lane, n_ev);
+            sbest = score_active_frame<FIX>(m, s, q, t, n_act, lane, n_ev);
             n_sen_eval += n_ev;
         }
         // fsg_search_hmm_eval (ref :330-398): the active HMMs in parallel
@@ -867,7 +870,7 @@ int launch_fsg_search(const DevModel &m, const DevFsgSet &gs, const int64_t *fra
     const int wpb = 4;
     FsgActiveArgs none;
     memset(&none, 0, sizeof none);
-    fsg_search_kernel<false><<<(n_utts + wpb - 1) / wpb, wpb * 32, 0, st>>>(
+    fsg_search_kernel<false, false><<<(n_utts + wpb - 1) / wpb, wpb * 32, 0, st>>>(
         m, gs, none, frame_off, utt_graph, ws_off, ws, dense, g0, u0, n_utts, hist, hist_cap, tent_cap,
         n_hist, n_eval, frames, rv);
     SSB_CUDA(cudaGetLastError());
@@ -910,9 +913,14 @@ int launch_fsg_search_active(const DevModel &m, const DevFsgSet &gs, const int64
     aa.final_active = final_active;
     aa.n_sen_eval = n_sen_eval;
     const int wpb = 4;
-    fsg_search_kernel<true><<<(n_utts + wpb - 1) / wpb, wpb * 32, 0, st>>>(
-        m, gs, aa, frame_off, utt_graph, ws_off, ws, nullptr, 0, 0, n_utts, hist, hist_cap, tent_cap,
-        n_hist, n_eval, frames, rv);
+    if (m.n_feat == 3 && m.topn == 4 && m.n_density == 128)
+        fsg_search_kernel<true, true><<<(n_utts + wpb - 1) / wpb, wpb * 32, 0, st>>>(
+            m, gs, aa, frame_off, utt_graph, ws_off, ws, nullptr, 0, 0, n_utts, hist, hist_cap, tent_cap,
+            n_hist, n_eval, frames, rv);
+    else
+        fsg_search_kernel<true, false><<<(n_utts + wpb - 1) / wpb, wpb * 32, 0, st>>>(
+            m, gs, aa, frame_off, utt_graph, ws_off, ws, nullptr, 0, 0, n_utts, hist, hist_cap, tent_cap,
+            n_hist, n_eval, frames, rv);
     SSB_CUDA(cudaGetLastError());
     note_launch();
     return 0;

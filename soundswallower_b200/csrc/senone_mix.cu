@@ -64,8 +64,9 @@ constexpr int K2_CS_PER_LANE = 4;  // codebook-streams per lane: CS <= 128
 // union are staged once.  Then every WARP takes frames on its own (t = t_begin + warp,
 // +8, ...): lanes over codebook-streams for the normaliser, lanes over active senones for
 // the mixing, lanes over chain states for the gather -- only __syncwarp inside the loop.
-// PTM4 = the bundled models' case fixed at compile time (PTM scorer, top-4): no unused-entry test
-// and no trip-count test in the innermost loop (they cost 2.8 of 11 ms on config #2).
+// PTM4 = the bundled models' case fixed at compile time (PTM scorer, top-4, 3 streams x 128): no
+// unused-entry test and no trip-count test in the innermost loop (they cost 2.8 of 11 ms on
+// config #2), no runtime divisions by the stream count.
 template <bool STAGED, bool PTM4>
 __global__ void __launch_bounds__(K2_THREADS)
 senone_mix_active_kernel(DevModel m, DevPlan p, const int4 *__restrict__ tn_s,
@@ -80,8 +81,11 @@ senone_mix_active_kernel(DevModel m, DevPlan p, const int4 *__restrict__ tn_s,
     if (t_begin >= T)
         return;
     const int t_end = min(T, t_begin + chunk);
-    const int CS = m.n_mgau * m.n_feat;
-    const int ND = m.n_density, NF = m.n_feat, N = m.topn;
+    // PTM4 also fixes the stream count at 3 (the launcher checks): `% NF`, `/ NF` and the loops
+    // over streams are compile-time then
+    const int NF = PTM4 ? 3 : m.n_feat;
+    const int CS = m.n_mgau * NF;
+    const int ND = PTM4 ? 128 : m.n_density, N = m.topn;
     const int us0 = p.us_off[u], n_us = p.us_off[u + 1] - us0;
     const int64_t ph0 = p.phone_off[u];
     const int ns = (int)(p.phone_off[u + 1] - ph0) * m.n_emit;
@@ -267,7 +271,7 @@ int launch_senone_mix_active(const DevModel &m, const DevPlan &p, const int4 *tn
     int chunk = (int)((n_frames + want_ctas - 1) / want_ctas);
     chunk = (max(chunk, 64) + K2_WARPS - 1) / K2_WARPS * K2_WARPS;
     dim3 grid((max_frames_per_utt + chunk - 1) / chunk, p.n_utts);
-    const bool ptm4 = m.kind == SSB_SCORER_PTM && m.topn == 4;
+    const bool ptm4 = m.kind == SSB_SCORER_PTM && m.topn == 4 && m.n_feat == 3 && m.n_density == 128;
 #define SSB_K2(ST, P4)                                                                              \
     do {                                                                                            \
         SSB_DYN_SMEM((senone_mix_active_kernel<ST, P4>), smem);     \
