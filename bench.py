@@ -456,12 +456,12 @@ def main():
     except Exception:
         pass
     # DRAM traffic of the dominant kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of
-    # one `ncu --set full` capture of this very launch shape (tools/profile_gpu.sh r1h 4096)
+    # one `ncu --set full` capture of this very launch shape (tools/profile_r1j.sh)
     traffic = None
     try:
         if U == 4096 and not args.compallsen:
             vals = {}
-            for ln in open(os.path.join(ROOT, "profiles", "prof_gmm_topn_r1h.txt")):
+            for ln in open(os.path.join(ROOT, "profiles", "prof_gmm_topn_r1j.txt")):
                 f = ln.split()
                 if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                     vals[f[0]] = float(f[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[2]]
@@ -515,7 +515,7 @@ def main():
                      "bound": "tensor",
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf, "traffic": traffic,
-                     "traffic_source": "profiles/prof_gmm_topn_r1h.txt (ncu --set full, same launch shape), bytes per launch",
+                     "traffic_source": "profiles/prof_gmm_topn_r1j.txt (ncu --set full, same launch shape), bytes per launch",
                      "peak_source": peak_src,
                      "note": "achieved = ALGORITHMIC flops (SURVEY 8d: scanned codebook-frames x 3 streams x "
                              "128 densities x 2(2*13+1)) / CUDA-event time of the kernel; the MMAs actually "
