@@ -436,6 +436,34 @@ int ssb_search_set_init_active(ssb_search_t *search, const uint32_t *bits);
 int32_t ssb_search_alignment(const ssb_search_t *search, int32_t level, int32_t *out5,
                              int32_t max_entries);
 
+/* ------------------------------------------------------------------ batched two-pass alignment
+ * `soundswallower --align` for a batch: decoder_set_align_text + search_module_forward (pass 1,
+ * the reference's default active-list mode where the model allows it), decoder_alignment
+ * (pass 2, starting from the acmod flags pass 1 left), alignment_propagate and
+ * decoder_result_json (ref: src/decoder.c:685-798, 935-957, 1339-1593; src/ps_alignment.c:
+ * 317-355).  `feat` is host or device memory (ssb_frontend_feat_device), `texts[u]` the
+ * whitespace-separated transcript of utterance u, `cfg` NULL for the reference's defaults,
+ * align_level 0 = first pass only, >= 1 = both passes, frate 0 = 100 frames/s.
+ * NULL with "Unknown word ..." when a transcript has a word the dictionary lacks. */
+typedef struct ssb_text_align_s ssb_text_align_t;
+ssb_text_align_t *ssb_align_texts(ssb_model_t *m, const ssb_lexicon_t *lx, const float *feat,
+                                  const int64_t *frame_off, const char *const *texts, int32_t n_utts,
+                                  const ssb_fsg_config_t *cfg, int32_t align_level, int32_t frate);
+void ssb_text_align_free(ssb_text_align_t *r);
+/* 0 ok, -1 no hypothesis ("Final result does not match the grammar"), -2 "Failed to reach final
+ * state in alignment"; hyp_score = decoder_hyp's score, n_frames = decoder_n_frames */
+int32_t ssb_text_align_status(const ssb_text_align_t *r, int32_t u, int32_t *hyp_score, int32_t *n_frames);
+const char *ssb_text_align_hyp(const ssb_text_align_t *r, int32_t u);   /* decoder_hyp; NULL if none */
+/* level 0 / 1 / 2 = alignment_words / phones / states: [n][5] id start duration score parent;
+ * level 3 = the first pass' seg_iter: [n][5] fsg word id (-1 null) sf ef ascr lscr.  Returns n. */
+int32_t ssb_text_align_entries(const ssb_text_align_t *r, int32_t u, int32_t level, int32_t *out5,
+                               int32_t max_entries);
+/* decoder_result_json(d, start, align_level) of utterance u: the line the reference CLI prints;
+ * owned by the result object, valid until the next call for the same utterance; NULL where the
+ * reference returns NULL */
+const char *ssb_text_align_json(ssb_text_align_t *r, int32_t u, double start, int32_t align_level);
+int ssb_text_align_kernel_ms(const ssb_text_align_t *r, float *ms4); /* pass 1: top-N, mix, search, backtrace */
+
 /* ------------------------------------------------------------------ frontend
  * Batched PCM -> MFCC -> CMN -> dynamic features for whole utterances: what
  * acmod_process_raw(full_utt=TRUE) obtains from fe_start / fe_process_int16 |

@@ -1077,4 +1077,67 @@ def align_texts(model, lexicon, feats, texts, **search_cfg):
     return out
 
 
+class TextAlignment:
+    """ssb_align_texts: `soundswallower --align` for a batch in one C call -- both passes on the
+    GPU, chains and JSON on the host in C++.  status(u) / hyp(u) / entries(u, level) / json(u)."""
+
+    def __init__(self, model, lexicon, feats, texts, align_level=1, frate=0, **search_cfg):
+        self.model, self.lexicon = model, lexicon
+        self.lib = model.lib
+        c = None
+        if search_cfg:
+            c = _lib.FsgConfig()
+            self.lib.ssb_fsg_config_defaults(C.byref(c))
+            for k, v in search_cfg.items():
+                if not hasattr(c, k):
+                    raise SsbError("unknown search parameter " + k)
+                setattr(c, k, v)
+        fptr, off, keep = _flat_feats(model, feats)
+        arr = (C.c_char_p * max(len(texts), 1))(*[t.encode("utf-8") for t in texts])
+        self.n = len(texts)
+        r = self.lib.ssb_align_texts(model.h, lexicon.h, C.c_void_p(fptr), _ptr(off), arr, self.n,
+                                     C.byref(c) if c is not None else None, int(align_level), int(frate))
+        if not r:
+            raise SsbError("ssb_align_texts: " + _lib.last_error())
+        self.r = C.c_void_p(r)
+        del keep
+
+    def close(self):
+        if getattr(self, "r", None):
+            self.lib.ssb_text_align_free(self.r)
+            self.r = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def status(self, u):
+        """(rv, hyp_score, n_frames): rv 0 ok, -1 no hypothesis, -2 second pass failed."""
+        sc, nf = C.c_int32(0), C.c_int32(0)
+        rv = int(self.lib.ssb_text_align_status(self.r, int(u), C.byref(sc), C.byref(nf)))
+        return rv, int(sc.value), int(nf.value)
+
+    def hyp(self, u):
+        h = self.lib.ssb_text_align_hyp(self.r, int(u))
+        return h.decode("utf-8") if h is not None else None
+
+    def entries(self, u, level):
+        lvl = {"words": 0, "phones": 1, "states": 2, "seg": 3}[level]
+        n = _lib.check(int(self.lib.ssb_text_align_entries(self.r, int(u), lvl, None, 0)), "ssb_text_align_entries")
+        out = np.zeros((n, 5), np.int32)
+        self.lib.ssb_text_align_entries(self.r, int(u), lvl, _ptr(out), n)
+        return out
+
+    def json(self, u, start=0., align_level=1):
+        j = self.lib.ssb_text_align_json(self.r, int(u), float(start), int(align_level))
+        return j.decode("utf-8") if j is not None else None
+
+    def kernel_ms(self):
+        ms = np.zeros(4, np.float32)
+        self.lib.ssb_text_align_kernel_ms(self.r, _ptr(ms))
+        return dict(gmm_topn=float(ms[0]), senone_mix=float(ms[1]), fsg_search=float(ms[2]), backtrace=float(ms[3]))
+
+
 from .decoder import (Alignment, AlignmentEntry, Decoder, Hyp, Seg, get_audio_data)  # noqa: E402

@@ -139,7 +139,9 @@ SYMBOLS = [
     "ssb_pipeline_align", "ssb_pipeline_submit", "ssb_pipeline_collect", "ssb_pipeline_set_overlap", "ssb_pipeline_n_launches", "ssb_pipeline_n_chunks", "ssb_pipeline_trace", "ssb_pipeline_free",
     "ssb_score_batch", "ssb_lexicon_basewid", "ssb_fsg_built_is_filler",
     "ssb_state_align_search_init", "ssb_fsg_search_init", "ssb_search_feed", "ssb_search_alignment", "ssb_search_final_active",
-    "ssb_search_set_init_active", "ssb_model_fsg_active_ok",
+    "ssb_search_set_init_active", "ssb_model_fsg_active_ok", "ssb_align_texts", "ssb_text_align_free",
+    "ssb_text_align_status", "ssb_text_align_hyp", "ssb_text_align_entries", "ssb_text_align_json",
+    "ssb_text_align_kernel_ms",
     "ssb_topn_batch", "ssb_tc_probe", "ssb_tc_hot_mask", "ssb_fsg_batch", "ssb_hmm_vit_eval",
     "ssb_fe_config_defaults", "ssb_fe_config_from_model", "ssb_frontend_create",
     "ssb_frontend_free", "ssb_frontend_dims", "ssb_frontend_n_frames", "ssb_frontend_tables",
@@ -242,6 +244,17 @@ def load():
     L.ssb_search_final_active.argtypes = [vp, vp]
     L.ssb_search_set_init_active.argtypes = [vp, vp]
     L.ssb_model_fsg_active_ok.argtypes = [vp]
+    L.ssb_align_texts.restype = vp
+    L.ssb_align_texts.argtypes = [vp, vp, vp, vp, P(C.c_char_p), i32, vp, i32, i32]
+    L.ssb_text_align_free.restype = None
+    L.ssb_text_align_free.argtypes = [vp]
+    L.ssb_text_align_status.argtypes = [vp, i32, P(i32), P(i32)]
+    L.ssb_text_align_hyp.restype = C.c_char_p
+    L.ssb_text_align_hyp.argtypes = [vp, i32]
+    L.ssb_text_align_entries.argtypes = [vp, i32, i32, vp, i32]
+    L.ssb_text_align_json.restype = C.c_char_p
+    L.ssb_text_align_json.argtypes = [vp, i32, C.c_double, i32]
+    L.ssb_text_align_kernel_ms.argtypes = [vp, vp]
     L.ssb_chain_populate.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32]
     L.ssb_fsg_config_defaults.restype = None
     L.ssb_fsg_config_defaults.argtypes = [P(FsgConfig)]

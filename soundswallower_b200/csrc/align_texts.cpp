@@ -1,0 +1,404 @@
+// align_texts.cpp -- `soundswallower --align` for a batch: transcripts + features in, the
+// word / phone / state alignment of every utterance and the reference's JSON line out, both
+// passes batched on the GPU (the result surface).
+//
+//   pass 1  decoder_set_align_text + search_module_forward      ref: src/decoder.c:685-735, 935-957
+//           -> ssb_fsg_build_align per transcript, ssb_fsg_batch in the reference's default mode
+//   pass 2  decoder_alignment                                   ref: src/decoder.c:737-798
+//           -> pass 1's words (null transitions dropped) with their frame windows,
+//              ssb_chain_populate (alignment_populate), ssb_align_batch starting from the
+//              acmod flags pass 1 left, alignment_propagate      ref: src/ps_alignment.c:317-355
+//   JSON    decoder_result_json                                  ref: src/decoder.c:1339-1593
+// Host code only: every number comes out of the batched kernels.
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "model.h"
+
+namespace ssb {
+const HostModel *model_host(const ssb_model_t *m);  // api.cu
+}
+using namespace ssb;
+
+namespace {
+struct Ent {
+    int32_t id, start, dur, score, parent;
+};
+struct UttResult {
+    int32_t rv = -1;  // 0 ok, -1 no hypothesis (transcript does not match), -2 second pass failed
+    int32_t hyp_score = 0, n_frames = 0;
+    std::string hyp;
+    std::vector<Ent> seg;  // pass 1: id = fsg word id (-1 null), start = sf, dur = ef, score = ascr, parent = lscr
+    std::vector<std::string> seg_word;
+    std::vector<Ent> word, phone, state;
+    std::string json;
+};
+}  // namespace
+
+struct ssb_text_align_s {
+    ssb_model_t *m = nullptr;
+    const ssb_lexicon_t *lx = nullptr;
+    double logbase = 1.0001;
+    int frate = 100;
+    std::vector<UttResult> utt;
+    float kernel_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+static void hyp_item(std::string &out, double b, double d, double p, const char *t)
+{
+    char buf[160];
+    snprintf(buf, sizeof buf, "{\"b\":%.3f,\"d\":%.3f,\"p\":%.3f,\"t\":\"", b, d, p);  // HYP_FORMAT
+    out += buf;
+    out += t ? t : "";
+    out += '"';
+}
+
+extern "C" void ssb_text_align_free(ssb_text_align_t *r) { delete r; }
+
+extern "C" ssb_text_align_t *ssb_align_texts(ssb_model_t *m, const ssb_lexicon_t *lx, const float *feat,
+                                             const int64_t *frame_off, const char *const *texts,
+                                             int32_t n_utts, const ssb_fsg_config_t *cfg,
+                                             int32_t align_level, int32_t frate)
+{
+    const HostModel *h = model_host(m);
+    if (!h || !lx || n_utts < 0 || (n_utts > 0 && (!frame_off || !texts))) {
+        set_error("ssb_align_texts: bad arguments");
+        return nullptr;
+    }
+    std::unique_ptr<ssb_text_align_s> R(new ssb_text_align_s);
+    R->m = m;
+    R->lx = lx;
+    R->logbase = h->cfg.logbase;
+    R->frate = frate > 0 ? frate : 100;
+    R->utt.resize(n_utts);
+    const int U = n_utts, E = h->n_emit, nw = (h->n_sen + 31) / 32;
+    if (U == 0)
+        return R.release();
+
+    // ---- pass 1: one alignment grammar per distinct transcript
+    std::vector<ssb_fsg_built_t *> built;
+    std::vector<std::string> built_text;
+    std::vector<int32_t> utt_graph(U, 0);
+    struct Guard {
+        std::vector<ssb_fsg_built_t *> &b;
+        ~Guard()
+        {
+            for (auto *x : b)
+                ssb_fsg_built_free(x);
+        }
+    } guard{built};
+    for (int u = 0; u < U; ++u) {
+        const std::string t = texts[u] ? texts[u] : "";
+        int gi = -1;
+        for (size_t k = 0; k < built_text.size(); ++k)
+            if (built_text[k] == t) {
+                gi = (int)k;
+                break;
+            }
+        if (gi < 0) {
+            ssb_fsg_built_t *b = ssb_fsg_build_align(lx, t.c_str(), cfg);
+            if (!b)  // "Unknown word ..."
+                return nullptr;
+            built.push_back(b);
+            built_text.push_back(t);
+            gi = (int)built.size() - 1;
+        }
+        utt_graph[u] = gi;
+    }
+    std::vector<ssb_fsg_graph_t> graphs;
+    for (auto *b : built)
+        graphs.push_back(*ssb_fsg_built_graph(b));
+    int max_T = 0;
+    for (int u = 0; u < U; ++u)
+        max_T = std::max<int64_t>(max_T, frame_off[u + 1] - frame_off[u]);
+    int max_seg = 256;
+    ssb_fsg_in_t fin;
+    std::vector<int32_t> segs, n_seg(U), hyp_score(U), exit_bp(U), rv1(U);
+    std::vector<uint32_t> flags((size_t)U * nw, 0u);
+    float ms1[4] = {0, 0, 0, 0};
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        memset(&fin, 0, sizeof fin);
+        fin.n_utts = U;
+        fin.feat = feat;
+        fin.frame_off = frame_off;
+        fin.n_graphs = (int32_t)graphs.size();
+        fin.graphs = graphs.data();
+        fin.utt_graph = utt_graph.data();
+        fin.hist_cap = std::max(4096, 8 * max_T);
+        fin.max_seg = max_seg;
+        fin.active_lists = ssb_model_fsg_active_ok(m);
+        segs.assign((size_t)U * max_seg * 5, 0);
+        ssb_fsg_out_t fo;
+        memset(&fo, 0, sizeof fo);
+        fo.segs = segs.data();
+        fo.n_seg = n_seg.data();
+        fo.hyp_score = hyp_score.data();
+        fo.exit_bp = exit_bp.data();
+        fo.utt_rv = rv1.data();
+        fo.kernel_ms = ms1;
+        fo.final_active = flags.data();
+        if (ssb_fsg_batch(m, &fin, &fo) != 0)
+            return nullptr;
+        int need = 0;  // a segmentation longer than max_seg comes back as -length: ask again
+        for (int u = 0; u < U; ++u)
+            need = std::max(need, -n_seg[u]);
+        if (need <= max_seg)
+            break;
+        max_seg = need;
+    }
+    for (int k = 0; k < 4; ++k)
+        R->kernel_ms[k] = ms1[k];
+
+    // ---- decoder_alignment: words of pass 1 -> chains
+    std::vector<int64_t> phone_off(U + 1, 0);
+    std::vector<int32_t> ssid, tmat, sf, ef, st_start, st_dur, st_score;
+    std::vector<std::vector<int32_t>> ci_u(U), parent_u(U), wid_u(U);
+    for (int u = 0; u < U; ++u) {
+        UttResult &r = R->utt[u];
+        r.n_frames = (int32_t)(frame_off[u + 1] - frame_off[u]) + 1;  // decoder_n_frames (ref :1247-1250)
+        r.hyp_score = hyp_score[u];
+        const ssb_fsg_built_t *b = built[utt_graph[u]];
+        const ssb_fsg_graph_t &g = graphs[utt_graph[u]];
+        phone_off[u + 1] = phone_off[u];
+        if (rv1[u] != 0 || exit_bp[u] <= 0 || n_seg[u] <= 0)
+            continue;  // no hypothesis: "does not match the grammar"
+        std::vector<int32_t> wstart, wdur;
+        for (int i = 0; i < n_seg[u]; ++i) {
+            const int32_t *sg = &segs[((size_t)u * max_seg + i) * 5];
+            const int32_t fw = g.link4[(size_t)sg[0] * 4 + 3];
+            r.seg.push_back(Ent{fw, sg[1], sg[2], sg[3], sg[4]});
+            int32_t dw = -1;
+            const char *ws = fw >= 0 ? ssb_fsg_built_word(b, fw, &dw) : "(NULL)";
+            r.seg_word.push_back(ws ? ws : "");
+            if (fw < 0)
+                continue;  // null transitions carry no word (ref: src/decoder.c:757-766)
+            if (!ssb_fsg_built_is_filler(b, fw)) {
+                if (!r.hyp.empty())
+                    r.hyp += ' ';
+                const int32_t base = ssb_lexicon_basewid(lx, dw);
+                r.hyp += ssb_lexicon_wordstr(lx, base >= 0 ? base : dw);
+            }
+            wid_u[u].push_back(dw);
+            wstart.push_back(sg[1]);
+            wdur.push_back(sg[2] - sg[1] + 1);
+        }
+        r.rv = 0;
+        if (!align_level || wid_u[u].empty())
+            continue;
+        const int nwd = (int)wid_u[u].size();
+        const int32_t np = ssb_chain_populate(lx, wid_u[u].data(), nwd, nullptr, nullptr, nullptr, nullptr, 0);
+        if (np < 0)
+            return nullptr;
+        const size_t p0 = ssid.size();
+        ssid.resize(p0 + np);
+        tmat.resize(p0 + np);
+        ci_u[u].resize(np);
+        parent_u[u].resize(np);
+        if (np > 0
+            && ssb_chain_populate(lx, wid_u[u].data(), nwd, &ssid[p0], &tmat[p0], ci_u[u].data(),
+                                  parent_u[u].data(), np) != np)
+            return nullptr;
+        for (int i = 0; i < nwd; ++i)
+            r.word.push_back(Ent{wid_u[u][i], wstart[i], wdur[i], 0, -1});
+        for (int i = 0; i < np; ++i) {
+            const Ent &w = r.word[parent_u[u][i]];
+            // ref: src/state_align_search.c:464-471
+            sf.push_back(w.start > 0 ? w.start : 0);
+            ef.push_back(w.dur > 0 ? w.start + w.dur : INT_MAX);
+            r.phone.push_back(Ent{ci_u[u][i], w.start, w.dur, 0, parent_u[u][i]});
+            for (int j = 0; j < E; ++j) {
+                // what alignment_populate leaves in the state entries (ref: src/ps_alignment.c:237-240)
+                r.state.push_back(Ent{h->sseq[(size_t)ssid[p0 + i] * E + j], w.start, w.dur, 0, i});
+                st_start.push_back(w.start);
+                st_dur.push_back(w.dur);
+                st_score.push_back(0);
+            }
+        }
+        phone_off[u + 1] = phone_off[u] + np;
+    }
+
+    // ---- pass 2
+    if (align_level && phone_off[U] > 0) {
+        std::vector<int32_t> rv2(U, 0), best(U, 0), ren(U, 0);
+        ssb_align_in_t ain;
+        memset(&ain, 0, sizeof ain);
+        ain.n_utts = U;
+        ain.feat = feat;
+        ain.frame_off = frame_off;
+        ain.phone_off = phone_off.data();
+        ain.ssid = ssid.data();
+        ain.tmat = tmat.data();
+        ain.sf = sf.data();
+        ain.ef = ef.data();
+        ain.init_active = fin.active_lists ? flags.data() : nullptr;  // the acmod both passes share
+        ssb_align_out_t ao;
+        memset(&ao, 0, sizeof ao);
+        ao.st_start = st_start.data();
+        ao.st_dur = st_dur.data();
+        ao.st_score = st_score.data();
+        ao.utt_rv = rv2.data();
+        ao.utt_best = best.data();
+        ao.utt_renorm = ren.data();
+        if (ssb_align_batch(m, &ain, &ao) != 0)
+            return nullptr;
+        for (int u = 0; u < U; ++u) {
+            UttResult &r = R->utt[u];
+            if (r.rv != 0 || r.state.empty())
+                continue;
+            if (rv2[u] != 0) {
+                r.rv = -2;  // "Failed to reach final state in alignment"
+                continue;
+            }
+            const size_t s0 = (size_t)phone_off[u] * E;
+            for (size_t i = 0; i < r.state.size(); ++i) {
+                r.state[i].start = st_start[s0 + i];
+                r.state[i].dur = st_dur[s0 + i];
+                r.state[i].score = st_score[s0 + i];
+            }
+            int last = -1;  // alignment_propagate (ref: src/ps_alignment.c:317-355)
+            for (const Ent &e : r.state) {
+                Ent &p = r.phone[e.parent];
+                if (e.parent != last) {
+                    p.start = e.start;
+                    p.dur = 0;
+                    p.score = 0;
+                }
+                p.dur += e.dur;
+                p.score += e.score;
+                last = e.parent;
+            }
+            last = -1;
+            for (const Ent &p : r.phone) {
+                Ent &w = r.word[p.parent];
+                if (p.parent != last) {
+                    w.start = p.start;
+                    w.dur = 0;
+                    w.score = 0;
+                }
+                w.dur += p.dur;
+                w.score += p.score;
+                last = p.parent;
+            }
+        }
+    }
+    return R.release();
+}
+
+extern "C" int32_t ssb_text_align_status(const ssb_text_align_t *r, int32_t u, int32_t *hyp_score,
+                                         int32_t *n_frames)
+{
+    if (!r || u < 0 || u >= (int32_t)r->utt.size())
+        return INT32_MIN;
+    if (hyp_score)
+        *hyp_score = r->utt[u].hyp_score;
+    if (n_frames)
+        *n_frames = r->utt[u].n_frames;
+    return r->utt[u].rv;
+}
+
+extern "C" const char *ssb_text_align_hyp(const ssb_text_align_t *r, int32_t u)
+{
+    if (!r || u < 0 || u >= (int32_t)r->utt.size() || r->utt[u].rv == -1 || r->utt[u].hyp.empty())
+        return nullptr;
+    return r->utt[u].hyp.c_str();
+}
+
+extern "C" int32_t ssb_text_align_entries(const ssb_text_align_t *r, int32_t u, int32_t level,
+                                          int32_t *out5, int32_t max_entries)
+{
+    if (!r || u < 0 || u >= (int32_t)r->utt.size() || level < 0 || level > 3) {
+        set_error("ssb_text_align_entries: bad arguments");
+        return -1;
+    }
+    const UttResult &x = r->utt[u];
+    const std::vector<Ent> &v = level == 0 ? x.word : (level == 1 ? x.phone : (level == 2 ? x.state : x.seg));
+    if (out5)
+        for (int i = 0; i < (int)v.size() && i < max_entries; ++i) {
+            out5[i * 5] = v[i].id;
+            out5[i * 5 + 1] = v[i].start;
+            out5[i * 5 + 2] = v[i].dur;
+            out5[i * 5 + 3] = v[i].score;
+            out5[i * 5 + 4] = v[i].parent;
+        }
+    return (int32_t)v.size();
+}
+
+extern "C" const char *ssb_text_align_json(ssb_text_align_t *r, int32_t u, double start, int32_t align_level)
+{
+    if (!r || u < 0 || u >= (int32_t)r->utt.size()) {
+        set_error("ssb_text_align_json: bad arguments");
+        return nullptr;
+    }
+    UttResult &x = r->utt[u];
+    if (x.rv == -1 || (align_level && (x.rv != 0 || x.word.empty())))
+        return nullptr;  // decoder_result_json returns NULL without an alignment (ref :1511-1515)
+    const HostModel *h = model_host(r->m);
+    const double base = r->logbase, fr = r->frate;
+    auto P = [&](int32_t score) { return pow(base, (double)score); };  // logmath_exp
+    std::string &o = x.json;
+    o.clear();
+    hyp_item(o, start, x.n_frames / fr, P(0), x.hyp.c_str());  // fsg_search_prob = 0 (no bestpath)
+    o += ",\"w\":[";
+    bool first = true;
+    if (align_level) {
+        size_t pi = 0;
+        for (size_t wi = 0; wi < x.word.size(); ++wi) {
+            const Ent &w = x.word[wi];
+            if (!first)
+                o += ',';
+            first = false;
+            hyp_item(o, start + w.start / fr, w.dur / fr, P(w.score), ssb_lexicon_wordstr(r->lx, w.id));
+            o += ",\"w\":[";
+            bool pf = true;
+            for (; pi < x.phone.size() && x.phone[pi].parent == (int32_t)wi; ++pi) {
+                const Ent &p = x.phone[pi];
+                if (!pf)
+                    o += ',';
+                pf = false;
+                hyp_item(o, start + p.start / fr, p.dur / fr, P(p.score), ssb_model_ciphone_str(r->m, p.id));
+                if (align_level > 1) {
+                    o += ",\"w\":[";
+                    for (int j = 0; j < h->n_emit; ++j) {
+                        const Ent &s = x.state[pi * h->n_emit + j];
+                        char name[16];
+                        snprintf(name, sizeof name, "%u", (unsigned)s.id);  // alignment_iter_name of a state
+                        if (j)
+                            o += ',';
+                        hyp_item(o, start + s.start / fr, s.dur / fr, P(s.score), name);
+                        o += '}';
+                    }
+                    o += ']';
+                }
+                o += '}';
+            }
+            o += "]}";
+        }
+    } else {
+        for (size_t i = 0; i < x.seg.size(); ++i) {
+            const Ent &s = x.seg[i];  // start = sf, dur = ef, score = ascr, parent = lscr
+            if (!first)
+                o += ',';
+            first = false;
+            hyp_item(o, start + s.start / fr, (s.dur + 1 - s.start) / fr, P(s.score + s.parent),
+                     x.seg_word[i].c_str());
+            o += '}';
+        }
+    }
+    o += "]}\n";
+    return o.c_str();
+}
+
+extern "C" int ssb_text_align_kernel_ms(const ssb_text_align_t *r, float *ms4)
+{
+    if (!r || !ms4)
+        return -1;
+    for (int k = 0; k < 4; ++k)
+        ms4[k] = r->kernel_ms[k];
+    return 0;
+}

@@ -179,3 +179,49 @@ def test_decode_file_8khz_wav():
     assert ph[0].start == 0 and all(a.start + a.duration == b.start for a, b in zip(ph, ph[1:]))
     assert ph[-1].start + ph[-1].duration == d.n_frames - 1
     d.close()
+
+
+# ---- ssb_align_texts: the same thing for a batch in one C call
+def test_align_texts_unknown_word_and_no_cpu_path():
+    m = ssb.AcousticModel(model_dir("en-us"), device=-1)
+    lx = ssb.Lexicon(m, hmmdir=model_dir("en-us"))
+    with pytest.raises(ssb.SsbError, match="Unknown word"):
+        ssb.TextAlignment(m, lx, [np.zeros((5, 39), np.float32)], ["go xyzzyq"])
+    with pytest.raises(ssb.SsbError, match="no CPU compute path"):
+        ssb.TextAlignment(m, lx, [np.zeros((5, 39), np.float32)], ["go forward"])
+    assert ssb.TextAlignment(m, lx, [], []).n == 0
+
+
+@pytest.mark.gpu
+def test_align_texts_c_call_equals_cli_and_decoder(golden):
+    m = ssb.AcousticModel(model_dir("en-us"))
+    lx = ssb.Lexicon(m, hmmdir=model_dir("en-us"))
+    fe = ssb.Frontend(model_dir("en-us"))
+    pcm = np.frombuffer(open(os.path.join(DATA, "goforward.raw"), "rb").read(), np.int16)
+    rs = np.random.RandomState(3)
+    pcms = [pcm, pcm[:40000], (pcm + rs.randint(-40, 40, len(pcm))).astype(np.int16), pcm[:9000], pcm]
+    texts = [TEXT["en-us"], "go forward ten", TEXT["en-us"], TEXT["en-us"], "go forward ten meters"]
+    ta = ssb.TextAlignment(m, lx, fe.run(pcms), texts, align_level=2)
+    assert ta.json(0, align_level=1) == CLI_JSON and ta.json(4, align_level=1) == CLI_JSON
+    assert ta.status(0) == (0, -2761, 279) and ta.hyp(0) == TEXT["en-us"]
+    g = golden["en-us"]
+    assert np.array_equal(ta.entries(0, "words")[:, :4], g["words"])
+    assert np.array_equal(ta.entries(0, "states"), g["states"])
+    assert np.array_equal(ta.entries(0, "phones")[:, [0, 1, 2, 3, 4]], g["phones"][:, [0, 3, 4, 5, 6]])
+    seg = ta.entries(0, "seg")     # App. B: word sf ef ascr lscr of the default CLI
+    assert seg[:, 1:].tolist() == [[0, 45, -230, -337], [46, 63, -133, 0], [64, 116, -369, 0],
+                                   [117, 152, -468, 0], [153, 210, -563, 0], [211, 277, -324, -337]]
+    d = ssb.Decoder(model_dir("en-us"))
+    n_ok = 0
+    for u, (p, t) in enumerate(zip(pcms, texts)):
+        d.set_align_text(t)
+        d.start_utt(); d.process_raw(p.tobytes(), full_utt=True); d.end_utt()
+        if d.hyp.text is None:
+            assert ta.status(u)[0] == -1 and ta.json(u) is None and ta.hyp(u) is None
+            continue
+        n_ok += 1
+        assert ta.hyp(u) == d.hyp.text
+        for lvl in (0, 1, 2):
+            assert ta.json(u, start=1.5, align_level=lvl) == d.dumps(start_time=1.5, align_level=lvl), (u, lvl)
+    assert n_ok >= 4 and ta.kernel_ms()["fsg_search"] > 0
+    d.close()
