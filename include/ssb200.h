@@ -462,6 +462,9 @@ int32_t ssb_text_align_entries(const ssb_text_align_t *r, int32_t u, int32_t lev
  * owned by the result object, valid until the next call for the same utterance; NULL where the
  * reference returns NULL */
 const char *ssb_text_align_json(ssb_text_align_t *r, int32_t u, double start, int32_t align_level);
+/* renders the JSON line of every utterance with up to 16 host threads; ssb_text_align_json
+ * with the same (start, align_level) then returns the stored lines */
+int ssb_text_align_render(ssb_text_align_t *r, double start, int32_t align_level);
 int ssb_text_align_kernel_ms(const ssb_text_align_t *r, float *ms4); /* pass 1: top-N, mix, search, backtrace */
 
 /* ------------------------------------------------------------------ frontend

@@ -1130,6 +1130,10 @@ class TextAlignment:
         self.lib.ssb_text_align_entries(self.r, int(u), lvl, _ptr(out), n)
         return out
 
+    def render(self, start=0., align_level=1):
+        """All JSON lines at once (host threads); json(u, same arguments) then just returns them."""
+        _lib.check(self.lib.ssb_text_align_render(self.r, float(start), int(align_level)), "ssb_text_align_render")
+
     def json(self, u, start=0., align_level=1):
         j = self.lib.ssb_text_align_json(self.r, int(u), float(start), int(align_level))
         return j.decode("utf-8") if j is not None else None

@@ -141,7 +141,7 @@ SYMBOLS = [
     "ssb_state_align_search_init", "ssb_fsg_search_init", "ssb_search_feed", "ssb_search_alignment", "ssb_search_final_active",
     "ssb_search_set_init_active", "ssb_model_fsg_active_ok", "ssb_align_texts", "ssb_text_align_free",
     "ssb_text_align_status", "ssb_text_align_hyp", "ssb_text_align_entries", "ssb_text_align_json",
-    "ssb_text_align_kernel_ms",
+    "ssb_text_align_kernel_ms", "ssb_text_align_render",
     "ssb_topn_batch", "ssb_tc_probe", "ssb_tc_hot_mask", "ssb_fsg_batch", "ssb_hmm_vit_eval",
     "ssb_fe_config_defaults", "ssb_fe_config_from_model", "ssb_frontend_create",
     "ssb_frontend_free", "ssb_frontend_dims", "ssb_frontend_n_frames", "ssb_frontend_tables",
@@ -255,6 +255,7 @@ def load():
     L.ssb_text_align_json.restype = C.c_char_p
     L.ssb_text_align_json.argtypes = [vp, i32, C.c_double, i32]
     L.ssb_text_align_kernel_ms.argtypes = [vp, vp]
+    L.ssb_text_align_render.argtypes = [vp, C.c_double, i32]
     L.ssb_chain_populate.argtypes = [vp, vp, i32, vp, vp, vp, vp, i32]
     L.ssb_fsg_config_defaults.restype = None
     L.ssb_fsg_config_defaults.argtypes = [P(FsgConfig)]

@@ -17,6 +17,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "model.h"
@@ -38,6 +39,9 @@ struct UttResult {
     std::vector<std::string> seg_word;
     std::vector<Ent> word, phone, state;
     std::string json;
+    bool json_ok = false;   // json holds the line for (json_start, json_level)
+    double json_start = 0;
+    int json_level = -1;
 };
 }  // namespace
 
@@ -338,6 +342,8 @@ extern "C" const char *ssb_text_align_json(ssb_text_align_t *r, int32_t u, doubl
     UttResult &x = r->utt[u];
     if (x.rv == -1 || (align_level && (x.rv != 0 || x.word.empty())))
         return nullptr;  // decoder_result_json returns NULL without an alignment (ref :1511-1515)
+    if (x.json_ok && x.json_start == start && x.json_level == align_level)
+        return x.json.c_str();  // rendered by ssb_text_align_render
     const HostModel *h = model_host(r->m);
     const double base = r->logbase, fr = r->frate;
     auto P = [&](int32_t score) { return pow(base, (double)score); };  // logmath_exp
@@ -391,7 +397,34 @@ extern "C" const char *ssb_text_align_json(ssb_text_align_t *r, int32_t u, doubl
         }
     }
     o += "]}\n";
+    x.json_ok = true;
+    x.json_start = start;
+    x.json_level = align_level;
     return o.c_str();
+}
+
+extern "C" int ssb_text_align_render(ssb_text_align_t *r, double start, int32_t align_level)
+{
+    if (!r) {
+        set_error("NULL result");
+        return -1;
+    }
+    const int U = (int)r->utt.size();
+    const int nt = std::max(1, std::min<int>({16, (int)std::thread::hardware_concurrency(), U / 64}));
+    auto work = [&](int t) {
+        for (int u = t; u < U; u += nt)
+            ssb_text_align_json(r, u, start, align_level);
+    };
+    if (nt == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t)
+            th.emplace_back(work, t);
+        for (auto &x : th)
+            x.join();
+    }
+    return 0;
 }
 
 extern "C" int ssb_text_align_kernel_ms(const ssb_text_align_t *r, float *ms4)

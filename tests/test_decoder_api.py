@@ -224,4 +224,8 @@ def test_align_texts_c_call_equals_cli_and_decoder(golden):
         for lvl in (0, 1, 2):
             assert ta.json(u, start=1.5, align_level=lvl) == d.dumps(start_time=1.5, align_level=lvl), (u, lvl)
     assert n_ok >= 4 and ta.kernel_ms()["fsg_search"] > 0
+    one_by_one = [ta.json(u, start=2.0, align_level=2) for u in range(len(pcms))]
+    ta2 = ssb.TextAlignment(m, lx, fe.run(pcms), texts, align_level=2)
+    ta2.render(start=2.0, align_level=2)      # the same lines, rendered by host threads
+    assert [ta2.json(u, start=2.0, align_level=2) for u in range(len(pcms))] == one_by_one
     d.close()
