@@ -139,6 +139,11 @@ typedef struct ssb_align_in_s {
      * starts (the reference never clears them, ref: src/state_align_search.c:186-188) */
     const uint32_t *init_active;
     int32_t compallsen; /* config key "compallsen" */
+    /* optional [n_utts][n_mgau*n_feat][4]: the top-N codewords the scorer carries when pass 2
+     * starts -- ptm_mgau's lists are not reset between passes, frame 0 copies history slot 1 as
+     * the first pass left it (ref: src/ptm_mgau.c:426-440).  They only matter on frames whose
+     * integer Gaussian scores tie.  ssb_fsg_out_t.final_topn provides them; NULL = initial lists. */
+    const uint8_t *init_topn;
 } ssb_align_in_t;
 
 typedef struct ssb_align_out_s {
@@ -298,6 +303,10 @@ typedef struct ssb_fsg_out_s {
      * senones evaluated per utterance (fsgs->n_sen_eval) */
     uint32_t *final_active;
     int64_t *n_sen_eval;
+    /* optional (PTM / semi-continuous models): [n_utts][n_mgau*n_feat][4], the top-N codewords
+     * the scorer is left carrying (history slot 1 = after the last odd frame): the second pass'
+     * ssb_align_in_t.init_topn */
+    uint8_t *final_topn;
 } ssb_fsg_out_t;
 /* Senone scoring + search + backtrace of a batch of utterances, with dense ("compallsen")
  * scores or, with in->active_lists, the reference's default active-list scoring. */
@@ -430,6 +439,10 @@ int ssb_search_feed(ssb_search_t *search, const float *feat, int32_t n_frames);
  * them (ref: src/state_align_search.c:186-188). */
 int ssb_search_final_active(const ssb_search_t *search, uint32_t *bits);
 int ssb_search_set_init_active(ssb_search_t *search, const uint32_t *bits);
+/* likewise the scorer's carried top-N codewords ([n_mgau*n_feat][4] bytes; returns that row
+ * count): ptm_mgau's lists are not reset between the passes either */
+int ssb_search_final_topn(const ssb_search_t *search, uint8_t *cw);
+int ssb_search_set_init_topn(ssb_search_t *search, const uint8_t *cw);
 /* alignment_words / alignment_phones / alignment_states of the aligner's alignment
  * (level 0 / 1 / 2, ref: src/ps_alignment.c:357-420): [n][5] = id (word id | CI phone |
  * senone), start, duration, score, parent; returns the number of entries at that level */

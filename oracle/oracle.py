@@ -191,7 +191,7 @@ class Oracle:
                     score=sc, tokens=tok)
 
     def state_align(self, feat, ssid, tmat, sf, ef, init_active=None, compallsen=False,
-                    want_tokens=False, want_senscr=False):
+                    want_tokens=False, want_senscr=False, init_topn=None):
         feat = np.ascontiguousarray(feat, np.float32)
         T = feat.shape[0]
         ssid, tmat, sf, ef = [np.ascontiguousarray(a, np.int32) for a in (ssid, tmat, sf, ef)]
@@ -203,11 +203,12 @@ class Oracle:
             for s in init_active:
                 bits[s >> 5] |= np.uint32(1 << (s & 31))
         senscr = np.zeros((T, self.n_sen), np.int16) if want_senscr else None
-        self.lib.orc_state_align(self.h, self.topn, _p(feat, C.c_float), T, n, _p(ssid, C.c_int32),
-                                 _p(tmat, C.c_int32), _p(sf, C.c_int32), _p(ef, C.c_int32),
-                                 _p(bits, C.c_uint32), int(compallsen), _p(st, C.c_int32),
-                                 _p(du, C.c_int32), _p(sc, C.c_int32), _p(tok, C.c_int32),
-                                 _p(senscr, C.c_int16), C.byref(out))
+        it = np.ascontiguousarray(init_topn, np.uint8) if init_topn is not None else None
+        self.lib.orc_state_align2(self.h, self.topn, _p(feat, C.c_float), T, n, _p(ssid, C.c_int32),
+                                  _p(tmat, C.c_int32), _p(sf, C.c_int32), _p(ef, C.c_int32),
+                                  _p(bits, C.c_uint32), int(compallsen), _p(st, C.c_int32),
+                                  _p(du, C.c_int32), _p(sc, C.c_int32), _p(tok, C.c_int32),
+                                  _p(senscr, C.c_int16), C.byref(out), _p(it, C.c_uint8))
         return dict(rv=out.rv, best_score=out.best_score, n_renorm=out.n_renorm, start=st, dur=du,
                     score=sc, tokens=tok, senscr=senscr)
 
@@ -273,10 +274,11 @@ class Oracle:
         out = np.zeros(8, np.int64)
         active = np.zeros((self.n_sen + 31) // 32, np.uint32)
         L = self.lib
-        L.orc_fsg_search_active.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
-                                            C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
-        rv = L.orc_fsg_search_active(self.h, topn, C.byref(f), feat.ctypes.data, T, hist.ctypes.data,
-                                     cap, out.ctypes.data, active.ctypes.data)
+        carried = np.zeros((self.n_mgau * self.n_feat, topn), np.uint8)
+        L.orc_fsg_search_active2.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                             C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        rv = L.orc_fsg_search_active2(self.h, topn, C.byref(f), feat.ctypes.data, T, hist.ctypes.data,
+                                      cap, out.ctypes.data, active.ctypes.data, carried.ctypes.data)
         n = int(out[0])
         hist = hist[:n].copy()
         score = C.c_int32(0)
@@ -290,7 +292,7 @@ class Oracle:
         del keep
         return dict(rv=rv, hist=hist, n_hmm_eval=int(out[1]), n_frames=int(out[2]), exit=bp,
                     hyp_score=int(score.value), segs=segs[:max(ns, 0)].copy(), active=active,
-                    n_sen_eval=int(out[3]))
+                    n_sen_eval=int(out[3]), carried=carried)
 
     def propagate(self, start, dur, score):
         n = len(start)

@@ -779,6 +779,29 @@ orc_ptm_reset(orc_ptm_t *p)
     p->frame_idx = 0;
 }
 
+/* The codewords of history slot 1: what frame 0 of a following utterance copies in (ptm_mgau.c:
+ * 426-440: lastf = hist[n_fast_hist - 1] when fast_eval_idx == 0; the lists are not reset between
+ * utterances or passes).  Scores are irrelevant: eval_topn re-scores every entry first. */
+void
+orc_ptm_get_carried(const orc_ptm_t *p, uint8_t *cw)
+{
+    int j, k, CS = p->m->n_mgau * p->m->n_feat;
+    for (j = 0; j < CS; ++j)
+        for (k = 0; k < p->topn; ++k)
+            cw[j * p->topn + k] = (uint8_t)p->hist[1][j * p->topn + k].cw;
+}
+
+void
+orc_ptm_set_carried(orc_ptm_t *p, const uint8_t *cw)
+{
+    int j, k, CS = p->m->n_mgau * p->m->n_feat;
+    for (j = 0; j < CS; ++j)
+        for (k = 0; k < p->topn; ++k) {
+            p->hist[1][j * p->topn + k].cw = cw[j * p->topn + k];
+            p->hist[1][j * p->topn + k].score = ORC_WORST_DIST;
+        }
+}
+
 /* The fp32 distance, in the reference's op order (ptm_mgau.c:63-68,106-127):
  * per dimension: diff = x - mu; sq = diff*diff; c = sq*var; d = d - c. */
 static float
@@ -1488,6 +1511,19 @@ orc_state_align(const orc_model_t *m, int topn, const float *feat, int T, int n_
                 const uint32_t *init_active, int compallsen, int32_t *st_start, int32_t *st_dur,
                 int32_t *st_score, int32_t *tokens, int16_t *senscr_out, orc_align_out_t *out)
 {
+    return orc_state_align2(m, topn, feat, T, n_phones, ssid, tmat, sf, ef, init_active, compallsen,
+                            st_start, st_dur, st_score, tokens, senscr_out, out, NULL);
+}
+
+/* init_topn: the scorer's carried top-N codewords ([mgau*feat][topn]) when the pass starts --
+ * after a first pass on the same decoder they are what that pass left (orc_ptm_get_carried). */
+int
+orc_state_align2(const orc_model_t *m, int topn, const float *feat, int T, int n_phones,
+                 const int32_t *ssid, const int32_t *tmat, const int32_t *sf, const int32_t *ef,
+                 const uint32_t *init_active, int compallsen, int32_t *st_start, int32_t *st_dur,
+                 int32_t *st_score, int32_t *tokens, int16_t *senscr_out, orc_align_out_t *out,
+                 const uint8_t *init_topn)
+{
     chain_t c;
     orc_ptm_t *p = orc_ptm_new(m, topn, 1);
     int t, i, j, E = m->n_emit, ns = n_phones * E, nw = (m->n_sen + 31) / 32;
@@ -1496,6 +1532,8 @@ orc_state_align(const orc_model_t *m, int topn, const float *feat, int T, int n_
     int16_t *senscr = malloc(sizeof(int16_t) * m->n_sen);
     if (init_active)
         memcpy(bits, init_active, nw * sizeof(uint32_t));
+    if (init_topn)
+        orc_ptm_set_carried(p, init_topn);
     chain_init(&c, m, n_phones, ssid, tmat, sf, ef, T);
     for (t = 0; t < T; ++t) {
         int n_active = 0;

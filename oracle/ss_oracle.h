@@ -128,6 +128,13 @@ int orc_state_align(const orc_model_t *m, int topn, const float *feat, int T, in
                     const int32_t *ssid, const int32_t *tmat, const int32_t *sf, const int32_t *ef,
                     const uint32_t *init_active, int compallsen, int32_t *st_start, int32_t *st_dur,
                     int32_t *st_score, int32_t *tokens, int16_t *senscr_out, orc_align_out_t *out);
+int orc_state_align2(const orc_model_t *m, int topn, const float *feat, int T, int n_phones,
+                     const int32_t *ssid, const int32_t *tmat, const int32_t *sf, const int32_t *ef,
+                     const uint32_t *init_active, int compallsen, int32_t *st_start, int32_t *st_dur,
+                     int32_t *st_score, int32_t *tokens, int16_t *senscr_out, orc_align_out_t *out,
+                     const uint8_t *init_topn);
+void orc_ptm_get_carried(const orc_ptm_t *p, uint8_t *cw);
+void orc_ptm_set_carried(orc_ptm_t *p, const uint8_t *cw);
 /* ---- FSG token-passing search on a flattened lextree (ss_oracle_fsg.c; ref: fsg_search.c,
  * fsg_history.c).  Array layouts = oracle/ref_shim.c:ref_fsg_dump. */
 typedef struct orc_fsg_s {
@@ -144,6 +151,9 @@ int orc_fsg_search(const orc_model_t *m, const orc_fsg_t *g, const int16_t *sens
                    int32_t *hist9, int cap, int64_t *out);
 int orc_fsg_search_active(const orc_model_t *m, int topn, const orc_fsg_t *g, const float *feat, int T,
                           int32_t *hist9, int cap, int64_t *out, uint32_t *active_out);
+int orc_fsg_search_active2(const orc_model_t *m, int topn, const orc_fsg_t *g, const float *feat, int T,
+                           int32_t *hist9, int cap, int64_t *out, uint32_t *active_out,
+                           uint8_t *carried_out);
 int orc_fsg_find_exit(const orc_fsg_t *g, const int32_t *hist9, int n_hist, int frame_idx, int final,
                       int32_t *out_score);
 int orc_fsg_segs(const orc_fsg_t *g, const int32_t *hist9, int bpidx, int32_t *segs, int max_seg);

@@ -484,6 +484,16 @@ int
 orc_fsg_search_active(const orc_model_t *m, int topn, const orc_fsg_t *g, const float *feat, int T,
                       int32_t *hist9, int cap, int64_t *out, uint32_t *active_out)
 {
+    return orc_fsg_search_active2(m, topn, g, feat, T, hist9, cap, out, active_out, NULL);
+}
+
+/* carried_out (optional, [mgau*feat][topn]): the scorer's carried top-N codewords after the
+ * search -- what a second pass on the same decoder starts from (orc_ptm_get_carried). */
+int
+orc_fsg_search_active2(const orc_model_t *m, int topn, const orc_fsg_t *g, const float *feat, int T,
+                       int32_t *hist9, int cap, int64_t *out, uint32_t *active_out,
+                       uint8_t *carried_out)
+{
     fs_t s;
     int i, rv, nw = (m->n_sen + 31) / 32;
     if (m->kind != ORC_KIND_PTM)
@@ -512,6 +522,8 @@ orc_fsg_search_active(const orc_model_t *m, int topn, const orc_fsg_t *g, const 
     out[3] = s.n_sen_eval;
     if (active_out)
         memcpy(active_out, s.bits, sizeof(uint32_t) * nw);
+    if (carried_out)
+        orc_ptm_get_carried(s.ptm, carried_out);
     orc_ptm_free(s.ptm);
     free(s.bits);
     free(s.list);

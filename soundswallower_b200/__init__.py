@@ -269,7 +269,8 @@ class StateAlignBatch:
         except Exception:
             pass
 
-    def _align_in(self, feat, frame_off, phone_off, ssid, tmat, sf, ef, init_active, compallsen):
+    def _align_in(self, feat, frame_off, phone_off, ssid, tmat, sf, ef, init_active, compallsen,
+                  init_topn=None):
         n_utts = len(frame_off) - 1
         a = _lib.AlignIn()
         a.n_utts = n_utts
@@ -282,19 +283,24 @@ class StateAlignBatch:
         a.ef = _ptr(ef, C.c_int32)
         a.init_active = _ptr(init_active, C.c_uint32) if init_active is not None else None
         a.compallsen = int(bool(compallsen))
-        self._keep = (feat, frame_off, phone_off, ssid, tmat, sf, ef, init_active)
+        if init_topn is not None:
+            init_topn = np.ascontiguousarray(init_topn, np.uint8)
+            assert init_topn.size == n_utts * self.model.n_mgau * self.model.n_feat * 4
+        a.init_topn = _ptr(init_topn, C.c_uint8) if init_topn is not None else None
+        self._keep = (feat, frame_off, phone_off, ssid, tmat, sf, ef, init_active, init_topn)
         self.n_utts = n_utts
         self.frame_off = np.asarray(frame_off)
         self.phone_off = np.asarray(phone_off)
         return a
 
     def upload_raw(self, feat, frame_off, phone_off, ssid, tmat, sf, ef, init_active=None,
-                   compallsen=False):
+                   compallsen=False, init_topn=None):
         """Flat arrays exactly as ssb_align_in_t takes them (feat may be pinned memory)."""
-        a = self._align_in(feat, frame_off, phone_off, ssid, tmat, sf, ef, init_active, compallsen)
+        a = self._align_in(feat, frame_off, phone_off, ssid, tmat, sf, ef, init_active, compallsen,
+                           init_topn)
         _lib.check(self.lib.ssb_batch_upload(self.b, C.byref(a)), "ssb_batch_upload")
 
-    def upload(self, feats, chains, init_active=None, compallsen=False):
+    def upload(self, feats, chains, init_active=None, compallsen=False, init_topn=None):
         m = self.model
         assert len(feats) == len(chains)
         fptr, frame_off, keep = _flat_feats(m, feats)
@@ -312,7 +318,9 @@ class StateAlignBatch:
         self.upload_raw(feat, frame_off, phone_off, _concat_i32([c["ssid"] for c in chains]),
                         _concat_i32([c["tmat"] for c in chains]),
                         _concat_i32([c["sf"] for c in chains]),
-                        _concat_i32([c["ef"] for c in chains]), ia, compallsen)
+                        _concat_i32([c["ef"] for c in chains]), ia, compallsen,
+                        None if init_topn is None else np.stack([np.asarray(t, np.uint8).reshape(-1, 4)
+                                                                 for t in init_topn]))
 
     def debug_tokens(self, on=True):
         self.lib.ssb_batch_debug_tokens(self.b, int(on))
@@ -397,9 +405,9 @@ class _AlignCall(StateAlignBatch):
         self._in = None
 
     def upload_raw(self, feat, frame_off, phone_off, ssid, tmat, sf, ef, init_active=None,
-                   compallsen=False):
+                   compallsen=False, init_topn=None):
         self._in = self._align_in(feat, frame_off, phone_off, ssid, tmat, sf, ef, init_active,
-                                  compallsen)
+                                  compallsen, init_topn)
 
     def run(self):
         raise SsbError("not a resident batch: use align()")
@@ -466,11 +474,13 @@ class AlignPipeline(_AlignCall):
 
 
 def align_batch(model, feats, chains, init_active=None, compallsen=False, want_chain_scr=False,
-                want_tokens=False):
+                want_tokens=False, init_topn=None):
     """One-shot: upload + run + download; returns a list of per-utterance dicts
-    (start/dur/score per state, rv, best_score, n_renorm[, chain_scr, tokens])."""
+    (start/dur/score per state, rv, best_score, n_renorm[, chain_scr, tokens]).
+    init_active / init_topn: per utterance what a first pass left in the shared acmod (the
+    active-senone flags and the scorer's carried top-N codewords: fsg_batch's `active`, `carried`)."""
     b = _AlignCall(model)
-    b.upload(feats, chains, init_active=init_active, compallsen=compallsen)
+    b.upload(feats, chains, init_active=init_active, compallsen=compallsen, init_topn=init_topn)
     return b.per_utt(b.align(want_chain_scr=want_chain_scr, want_tokens=want_tokens))
 
 
@@ -583,6 +593,9 @@ def fsg_batch(model, feats, graphs, utt_graph=None, hist_cap=4096, max_seg=256, 
     nsen = np.zeros(U, np.int64) if not compallsen else None
     fo.final_active = fact.ctypes.data if fact is not None else None
     fo.n_sen_eval = nsen.ctypes.data if nsen is not None else None
+    CS = model.n_mgau * model.n_feat
+    ftopn = np.zeros((U, CS, 4), np.uint8) if model.kind != 2 else None
+    fo.final_topn = ftopn.ctypes.data if ftopn is not None else None
     _lib.check(model.lib.ssb_fsg_batch(model.h, C.byref(fin), C.byref(fo)), "ssb_fsg_batch")
     out = []
     for u in range(U):
@@ -592,6 +605,8 @@ def fsg_batch(model, feats, graphs, utt_graph=None, hist_cap=4096, max_seg=256, 
             d["hist"] = hist[u, :int(n_hist[u])].copy()
         if fact is not None:
             d["active"], d["n_sen_eval"] = fact[u].copy(), int(nsen[u])
+        if ftopn is not None:
+            d["carried"] = ftopn[u].copy()   # the scorer's top-N codewords after the search
         out.append(d)
     if out:
         out[0]["kernel_ms"] = dict(gmm_topn=float(ms[0]), senone_mix=float(ms[1]), fsg_search=float(ms[2]),
@@ -956,6 +971,17 @@ class Search:
         _lib.check(self.model.lib.ssb_search_set_init_active(self.ptr, _ptr(bits) if bits is not None else None),
                    "ssb_search_set_init_active")
 
+    def final_topn(self):
+        """The scorer's carried top-N codewords as the grammar search left them, uint8 [CS][4]."""
+        out = np.zeros((self.model.n_mgau * self.model.n_feat, 4), np.uint8)
+        _lib.check(self.model.lib.ssb_search_final_topn(self.ptr, _ptr(out)), "ssb_search_final_topn")
+        return out
+
+    def set_init_topn(self, cw):
+        cw = np.ascontiguousarray(cw, np.uint8) if cw is not None else None
+        _lib.check(self.model.lib.ssb_search_set_init_topn(self.ptr, _ptr(cw) if cw is not None else None),
+                   "ssb_search_set_init_topn")
+
     def alignment(self, level):
         """alignment_words/phones/states: int32 [n][5] id start duration score parent."""
         lvl = {"words": 0, "phones": 1, "states": 2}[level]
@@ -1053,7 +1079,9 @@ def align_texts(model, lexicon, feats, texts, **search_cfg):
         c = lexicon.populate(wids, start, dur)
         chains.append(c)
         metas.append((wids, start, dur, c, int(r["hyp_score"])))
-    p2 = align_batch(model, feats, chains, init_active=_left_active(p1) if active else None)
+    carried = [r.get("carried") for r in p1]
+    p2 = align_batch(model, feats, chains, init_active=_left_active(p1) if active else None,
+                     init_topn=carried if all(c is not None for c in carried) else None)
     arrays = model.arrays()
     E = model.n_emit
     out = []

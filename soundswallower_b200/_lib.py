@@ -46,7 +46,8 @@ class AlignIn(C.Structure):
                 ("frame_off", C.POINTER(C.c_int64)), ("phone_off", C.POINTER(C.c_int64)),
                 ("ssid", C.POINTER(C.c_int32)), ("tmat", C.POINTER(C.c_int32)),
                 ("sf", C.POINTER(C.c_int32)), ("ef", C.POINTER(C.c_int32)),
-                ("init_active", C.POINTER(C.c_uint32)), ("compallsen", C.c_int32)]
+                ("init_active", C.POINTER(C.c_uint32)), ("compallsen", C.c_int32),
+                ("init_topn", C.POINTER(C.c_uint8))]
 
 
 class AlignOut(C.Structure):
@@ -74,7 +75,8 @@ class FsgOut(C.Structure):
     _fields_ = [("segs", C.c_void_p), ("n_seg", C.c_void_p), ("hyp_score", C.c_void_p),
                 ("exit_bp", C.c_void_p), ("utt_rv", C.c_void_p), ("n_hist", C.c_void_p),
                 ("n_hmm_eval", C.c_void_p), ("hist9", C.c_void_p), ("kernel_ms", C.c_void_p),
-                ("n_launches", C.c_int32), ("final_active", C.c_void_p), ("n_sen_eval", C.c_void_p)]
+                ("n_launches", C.c_int32), ("final_active", C.c_void_p), ("n_sen_eval", C.c_void_p),
+                ("final_topn", C.c_void_p)]
 
 
 MGAU_FRAME_EVAL = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int16), C.POINTER(C.c_uint8),
@@ -139,7 +141,8 @@ SYMBOLS = [
     "ssb_pipeline_align", "ssb_pipeline_submit", "ssb_pipeline_collect", "ssb_pipeline_set_overlap", "ssb_pipeline_n_launches", "ssb_pipeline_n_chunks", "ssb_pipeline_trace", "ssb_pipeline_free",
     "ssb_score_batch", "ssb_lexicon_basewid", "ssb_fsg_built_is_filler",
     "ssb_state_align_search_init", "ssb_fsg_search_init", "ssb_search_feed", "ssb_search_alignment", "ssb_search_final_active",
-    "ssb_search_set_init_active", "ssb_model_fsg_active_ok", "ssb_align_texts", "ssb_text_align_free",
+    "ssb_search_set_init_active", "ssb_search_final_topn", "ssb_search_set_init_topn",
+    "ssb_model_fsg_active_ok", "ssb_align_texts", "ssb_text_align_free",
     "ssb_text_align_status", "ssb_text_align_hyp", "ssb_text_align_entries", "ssb_text_align_json",
     "ssb_text_align_kernel_ms", "ssb_text_align_render",
     "ssb_topn_batch", "ssb_tc_probe", "ssb_tc_hot_mask", "ssb_fsg_batch", "ssb_hmm_vit_eval",
@@ -244,6 +247,8 @@ def load():
     L.ssb_search_final_active.argtypes = [vp, vp]
     L.ssb_search_set_init_active.argtypes = [vp, vp]
     L.ssb_model_fsg_active_ok.argtypes = [vp]
+    L.ssb_search_final_topn.argtypes = [vp, vp]
+    L.ssb_search_set_init_topn.argtypes = [vp, vp]
     L.ssb_align_texts.restype = vp
     L.ssb_align_texts.argtypes = [vp, vp, vp, vp, P(C.c_char_p), i32, vp, i32, i32]
     L.ssb_text_align_free.restype = None

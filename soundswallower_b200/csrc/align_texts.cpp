@@ -125,6 +125,9 @@ extern "C" ssb_text_align_t *ssb_align_texts(ssb_model_t *m, const ssb_lexicon_t
     ssb_fsg_in_t fin;
     std::vector<int32_t> segs, n_seg(U), hyp_score(U), exit_bp(U), rv1(U);
     std::vector<uint32_t> flags((size_t)U * nw, 0u);
+    // the scorer's carried top-N codewords after pass 1 (PTM / semi-continuous models)
+    const size_t CS = h->kind == SSB_SCORER_CONT ? 0 : (size_t)h->n_mgau * h->n_feat;
+    std::vector<uint8_t> carried((size_t)U * CS * 4, 0);
     float ms1[4] = {0, 0, 0, 0};
     for (int attempt = 0; attempt < 2; ++attempt) {
         memset(&fin, 0, sizeof fin);
@@ -147,6 +150,7 @@ extern "C" ssb_text_align_t *ssb_align_texts(ssb_model_t *m, const ssb_lexicon_t
         fo.utt_rv = rv1.data();
         fo.kernel_ms = ms1;
         fo.final_active = flags.data();
+        fo.final_topn = CS ? carried.data() : nullptr;
         if (ssb_fsg_batch(m, &fin, &fo) != 0)
             return nullptr;
         int need = 0;  // a segmentation longer than max_seg comes back as -length: ask again
@@ -241,6 +245,7 @@ extern "C" ssb_text_align_t *ssb_align_texts(ssb_model_t *m, const ssb_lexicon_t
         ain.sf = sf.data();
         ain.ef = ef.data();
         ain.init_active = fin.active_lists ? flags.data() : nullptr;  // the acmod both passes share
+        ain.init_topn = CS ? carried.data() : nullptr;
         ssb_align_out_t ao;
         memset(&ao, 0, sizeof ao);
         ao.st_start = st_start.data();

@@ -645,7 +645,7 @@ struct ssb_batch_s {
     // K1 over time (topn_fixup.cu): long utterances of a small batch cut into segments
     bool k1_seg = false;
     DevPlan k1_plan{};
-    DBuf d_k1_frame_off, d_k1_ep_off, d_k1_ep_start, d_k1_ep_cbmask, d_seg_utts, d_k1_tie;
+    DBuf d_k1_frame_off, d_k1_ep_off, d_k1_ep_start, d_k1_ep_cbmask, d_seg_utts, d_k1_tie, d_init_topn;
     int n_seg_utts = 0, n_k1_rows = 0;
     int64_t k1_tie_w = 0;
     // timing
@@ -660,7 +660,7 @@ struct ssb_batch_s {
                              &d_usen, &d_st_slot, &d_enter, &st_start, &st_dur, &st_score, &utt_rv,
                              &utt_best, &utt_renorm, &fin_hist, &fin_score, &dense, &best_tmp,
                              &d_k1_frame_off, &d_k1_ep_off, &d_k1_ep_start, &d_k1_ep_cbmask,
-                             &d_seg_utts, &d_k1_tie};
+                             &d_seg_utts, &d_k1_tie, &d_init_topn};
         size_t n = 0;
         for (const DBuf *b : all)
             n += b->cap;
@@ -673,7 +673,8 @@ struct ssb_batch_s {
                        &d_ep_start, &d_ep_cbmask, &d_ep_slot_off, &d_ep_slot, &d_us_off, &d_usen,
                        &d_st_slot, &d_enter, &st_start, &st_dur, &st_score, &utt_rv, &utt_best,
                        &utt_renorm, &fin_hist, &fin_score, &dense, &best_tmp, &d_k1_frame_off,
-                       &d_k1_ep_off, &d_k1_ep_start, &d_k1_ep_cbmask, &d_seg_utts, &d_k1_tie};
+                       &d_k1_ep_off, &d_k1_ep_start, &d_k1_ep_cbmask, &d_seg_utts, &d_k1_tie,
+                       &d_init_topn};
         for (DBuf *b : all)
             b->release();
     }
@@ -1095,6 +1096,16 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
     p.all_active = b->compallsen;
     p.tie_bits = nullptr;
     p.tie_w = 0;
+    p.init_topn = nullptr;
+    if (in->init_topn && U > 0 && CS > 0) {
+        // the top-N lists the scorer carries in from a previous pass on the same decoder
+        if (b->d_init_topn.ensure((size_t)U * CS * 4) != 0)
+            return -1;
+        API_CUDA(cudaMemcpyAsync(b->d_init_topn.p, in->init_topn, (size_t)U * CS * 4,
+                                 cudaMemcpyDefault, st), -1);
+        API_CUDA(cudaStreamSynchronize(st), -1);
+        p.init_topn = b->d_init_topn.as<uchar4>();
+    }
 
     // ---- K1 over time: with few utterances the top-N kernel (thread = utterance) has no rows
     // to fill its CTAs with, so long utterances are cut into segments that are scored
@@ -1162,6 +1173,7 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
                 b->n_seg_utts = (int)seg_utts.size();
                 b->n_k1_rows = (int)kfo.size() - 1;
                 b->k1_plan = p;
+                b->k1_plan.init_topn = nullptr;  // rows are segments; ties are replayed by the fix-up
                 b->k1_plan.n_utts = b->n_k1_rows;
                 b->k1_plan.frame_off = b->d_k1_frame_off.as<int64_t>();
                 b->k1_plan.ep_off = b->d_k1_ep_off.as<int32_t>();
@@ -1639,6 +1651,7 @@ extern "C" int64_t ssb_pipeline_submit(ssb_pipeline_t *p, const ssb_align_in_t *
     }
     const int n_chunks = (int)cut.size() - 1;
     const int nw = (h.n_sen + 31) / 32;
+    const size_t CSb = h.kind == SSB_SCORER_CONT ? 0 : (size_t)h.n_mgau * h.n_feat;
     std::vector<std::unique_ptr<PipeJob>> jobs;
     for (int c = 0; c < n_chunks; ++c) {
         std::unique_ptr<PipeJob> j(new PipeJob);
@@ -1662,6 +1675,7 @@ extern "C" int64_t ssb_pipeline_submit(ssb_pipeline_t *p, const ssb_align_in_t *
         j->in.sf = in->sf ? in->sf + p0 : nullptr;
         j->in.ef = in->ef ? in->ef + p0 : nullptr;
         j->in.init_active = in->init_active ? in->init_active + (size_t)u0 * nw : nullptr;
+        j->in.init_topn = in->init_topn ? in->init_topn + (size_t)u0 * CSb * 4 : nullptr;
         j->out = *out;
         j->out.st_start = out->st_start ? out->st_start + p0 * E : nullptr;
         j->out.st_dur = out->st_dur ? out->st_dur + p0 * E : nullptr;
@@ -2100,7 +2114,8 @@ extern "C" int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out
     if (!b)
         return -1;
     DBuf d_hdr, d_link4, d_flag, d_arc, d_root, d_pnode, d_ctxt, d_ug, d_wsoff, d_ws, d_hist, d_nhist,
-        d_neval, d_frames, d_rv, d_exit, d_score, d_segs, d_nseg, d_awsoff, d_aws, d_tie, d_fact, d_nsen;
+        d_neval, d_frames, d_rv, d_exit, d_score, d_segs, d_nseg, d_awsoff, d_aws, d_tie, d_fact, d_nsen,
+        d_ftopn;
     int rv = -1;
     do {
         if (score_prepare(b, in->feat, in->frame_off, U) != 0)
@@ -2138,6 +2153,9 @@ extern "C" int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out
             plan.tie_bits = d_tie.as<uint32_t>();
             plan.tie_w = tie_w;
         }
+        const size_t ftopn_bytes = (size_t)U * h.n_mgau * h.n_feat * 4;
+        if (out->final_topn && h.kind != SSB_SCORER_CONT && d_ftopn.ensure(std::max<size_t>(ftopn_bytes, 16)))
+            break;
         launch_count(true);
         cudaEventRecord(b->ev[0], st);
         // (the default-mode search replays tie steps from its own carried lists: no fix-up pass)
@@ -2154,7 +2172,8 @@ extern "C" int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out
                                           d_wsoff.as<int64_t>(), d_ws.as<int32_t>(), b->feat.as<float>(),
                                           b->tn_s.as<int4>(), b->tn_c.as<uchar4>(), d_tie.as<uint32_t>(),
                                           G, tie_w, d_awsoff.as<int64_t>(), d_aws.as<int32_t>(),
-                                          d_fact.as<uint32_t>(), d_nsen.as<int64_t>(), U,
+                                          d_fact.as<uint32_t>(), d_nsen.as<int64_t>(),
+                                          out->final_topn ? d_ftopn.as<uchar4>() : nullptr, U,
                                           d_hist.as<int32_t>(), in->hist_cap, tent_cap,
                                           d_nhist.as<int32_t>(), d_neval.as<int64_t>(),
                                           d_frames.as<int32_t>(), d_rv.as<int32_t>(), st) == 0;
@@ -2191,6 +2210,10 @@ extern "C" int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out
         }
         if (!ok)
             break;
+        if (!active && out->final_topn && h.kind != SSB_SCORER_CONT && G > 0
+            && launch_fsg_final_topn_dense(d, b->d_frame_off.as<int64_t>(), U, b->tn_c.as<uchar4>(), G,
+                                           d_ftopn.as<uchar4>(), st) != 0)
+            break;
         cudaEventRecord(b->ev[2], st);
         if (launch_fsg_backtrace(gs, d_ug.as<int32_t>(), 0, U, d_hist.as<int32_t>(), in->hist_cap,
                                  d_nhist.as<int32_t>(), d_frames.as<int32_t>(), d_exit.as<int32_t>(),
@@ -2204,7 +2227,8 @@ extern "C" int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out
             {out->utt_rv, &d_rv, (size_t)U * 4}, {out->n_hist, &d_nhist, (size_t)U * 4},
             {out->n_hmm_eval, &d_neval, (size_t)U * 8}, {out->hist9, &d_hist, hist_ints * 4},
             {active ? (void *)out->final_active : nullptr, &d_fact, (size_t)U * nw_sen * 4},
-            {active ? (void *)out->n_sen_eval : nullptr, &d_nsen, (size_t)U * 8}};
+            {active ? (void *)out->n_sen_eval : nullptr, &d_nsen, (size_t)U * 8},
+            {(h.kind != SSB_SCORER_CONT && G > 0) ? (void *)out->final_topn : nullptr, &d_ftopn, ftopn_bytes}};
         for (auto &c : copies)
             if (c.dst && cudaMemcpyAsync(c.dst, c.src->p, c.bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess)
                 ok = false;
@@ -2227,7 +2251,7 @@ extern "C" int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out
     } while (0);
     DBuf *all[] = {&d_hdr, &d_link4, &d_flag, &d_arc, &d_root, &d_pnode, &d_ctxt, &d_ug, &d_wsoff, &d_ws,
                    &d_hist, &d_nhist, &d_neval, &d_frames, &d_rv, &d_exit, &d_score, &d_segs, &d_nseg,
-                   &d_awsoff, &d_aws, &d_tie, &d_fact, &d_nsen};
+                   &d_awsoff, &d_aws, &d_tie, &d_fact, &d_nsen, &d_ftopn};
     for (DBuf *x : all)
         x->release();
     ssb_batch_free(b);

@@ -96,6 +96,10 @@ struct DevPlan {
     // list it carried in; [n_mgau*n_feat][tie_w] words, zeroed by the caller
     uint32_t *tie_bits;
     int64_t tie_w;
+    // optional: the top-N codewords the scorer carries when the pass starts, [n_utts][CS] (what
+    // a first pass on the same decoder left: the lists are not reset between passes, ref:
+    // src/ptm_mgau.c:426-440); null = the initial lists (codewords 0..N-1)
+    const uchar4 *init_topn;
 };
 
 // ---- kernel launchers (each returns 0 or -1 with the error set) ----
@@ -158,9 +162,13 @@ int launch_fsg_search_active(const DevModel &m, const DevFsgSet &gs, const int64
                              const int32_t *utt_graph, const int64_t *ws_off, int32_t *ws,
                              const float *feat, const int4 *tn_s, const uchar4 *tn_c,
                              const uint32_t *tie, int64_t G, int64_t tie_w, const int64_t *aws_off,
-                             int32_t *aws, uint32_t *final_active, int64_t *n_sen_eval, int n_utts,
+                             int32_t *aws, uint32_t *final_active, int64_t *n_sen_eval,
+                             uchar4 *final_topn, int n_utts,
                              int32_t *hist, int hist_cap, int tent_cap, int32_t *n_hist,
                              int64_t *n_eval, int32_t *frames, int32_t *rv, cudaStream_t st);
+// dense mode: the carried lists after the search are K1's own lists of the last odd frame
+int launch_fsg_final_topn_dense(const DevModel &m, const int64_t *frame_off, int n_utts,
+                                const uchar4 *tn_c, int64_t G, uchar4 *final_topn, cudaStream_t st);
 int launch_fsg_backtrace(const DevFsgSet &gs, const int32_t *utt_graph, int u0, int n_utts,
                          const int32_t *hist, int hist_cap, const int32_t *n_hist,
                          const int32_t *frames, int32_t *exit_bp, int32_t *hyp_score, int32_t *segs,

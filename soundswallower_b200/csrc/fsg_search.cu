@@ -239,6 +239,8 @@ struct FsgScore {            // per-utterance view of the scoring state (every l
     uchar4 *cur_c;           // [CS] codewords of the last scan = the list the reference carries
     uchar4 *cur_n;           // [CS] normalised scores of the frame
     int32_t *last_t;         // [CS] frame of the codebook-stream's last scan (-1: never)
+    uchar4 *snap_c;          // [CS] cur_c / last_t as they stood after the last odd frame: the
+    int32_t *snap_t;         //      reference's history slot 1, which a second pass starts from
     float *sd;               // shared, [128]: exact distances of one codebook-stream
     const uint8_t *lut;      // shared, [256]
 };
@@ -540,6 +542,7 @@ struct FsgActiveArgs {       // mode "compallsen = no"
     int32_t *aws;            // scoring workspace
     uint32_t *final_active;  // [U][(n_sen+31)/32] or null
     int64_t *n_sen_eval;     // [U] or null
+    uchar4 *final_topn;      // [U][CS] or null: the carried top-N codewords after the search
 };
 
 template <bool ACTIVE, bool FIX>
@@ -606,6 +609,10 @@ fsg_search_kernel(DevModel m, DevFsgSet gs, FsgActiveArgs aa, const int64_t *__r
         a += CS;
         q.last_t = a;
         a += CS;
+        q.snap_c = reinterpret_cast<uchar4 *>(a);
+        a += CS;
+        q.snap_t = a;
+        a += CS;
         q.bits = reinterpret_cast<uint32_t *>(a);
         a += nw;
         q.srt = reinterpret_cast<uint16_t *>(a);
@@ -619,6 +626,8 @@ fsg_search_kernel(DevModel m, DevFsgSet gs, FsgActiveArgs aa, const int64_t *__r
         for (int i = lane; i < CS; i += 32) {
             q.cur_c[i] = make_uchar4(0, 1, 2, 3);
             q.last_t[i] = -1;
+            q.snap_c[i] = make_uchar4(0, 1, 2, 3);
+            q.snap_t[i] = -1;
         }
         for (int i = lane; i < nw; i += 32)
             q.bits[i] = 0u;
@@ -659,6 +668,15 @@ fsg_search_kernel(DevModel m, DevFsgSet gs, FsgActiveArgs aa, const int64_t *__r
             int n_ev = 0;
             sbest = score_active_frame<FIX>(m, s, q, t, n_act, lane, n_ev);
             n_sen_eval += n_ev;
+            if (aa.final_topn && t == ((T & 1) ? T - 2 : T - 1)) {
+                // t is the last odd frame: the state of the reference's history slot 1
+                const int CS = m.n_mgau * m.n_feat;
+                for (int i = lane; i < CS; i += 32) {
+                    q.snap_c[i] = q.cur_c[i];
+                    q.snap_t[i] = q.last_t[i];
+                }
+                __syncwarp();
+            }
         }
         // fsg_search_hmm_eval (ref :330-398): the active HMMs in parallel
         int32_t best = WORST_SCORE;
@@ -765,6 +783,62 @@ fsg_search_kernel(DevModel m, DevFsgSet gs, FsgActiveArgs aa, const int64_t *__r
         rv_out[u] = s.overflow ? -2 : 0;
         if (ACTIVE && aa.n_sen_eval)
             aa.n_sen_eval[u] = n_sen_eval;
+    }
+    if (ACTIVE && aa.final_topn) {
+        // What a second pass on the same decoder starts from: frame 0 copies history slot
+        // n_fast_hist-1 = 1 (ref: src/ptm_mgau.c:426-440), i.e. the lists as they stood after the
+        // last ODD frame tl -- the codewords of the last scan up to tl, re-scored and stably
+        // re-sorted by eval_topn on every frame since (replayed from the most recent frame on
+        // which their scores are pairwise distinct: the order is forced there).
+        const int CS = m.n_mgau * m.n_feat, N = m.topn;
+        const int tl = (T & 1) ? T - 2 : T - 1;
+        __syncwarp();
+        for (int cs = lane; cs < CS; cs += 32) {
+            uchar4 c = make_uchar4(0, 1, 2, 3);
+            if (tl >= 0) {
+                c = q.snap_c[cs];
+                const int lt = q.snap_t[cs];
+                if (lt < tl) {
+                    const int cb = cs / m.n_feat, f = cs - cb * m.n_feat;
+                    const int RL = m.rec_len[f], L = m.featlen[f];
+                    const float *rec = m.gau + gau_offset(m, cb, f);
+                    int cc[4] = {c.x, c.y, c.z, c.w};
+                    int tt0 = lt + 1;
+                    for (int tt = tl; tt > lt + 1; --tt) {
+                        const float *xx = q.feat + (int64_t)tt * m.blk + m.featoff[f];
+                        int32_t sc[4];
+                        for (int k = 0; k < N; ++k)
+                            sc[k] = __float2int_rz(fsg_gau_dist(rec + (int64_t)cc[k] * RL, xx, L));
+                        bool distinct = true;
+                        for (int i = 0; i < N; ++i)
+                            for (int j = i + 1; j < N; ++j)
+                                distinct = distinct && sc[i] != sc[j];
+                        if (distinct) {
+                            tt0 = tt;
+                            break;
+                        }
+                    }
+                    for (int tt = tt0; tt <= tl; ++tt) {  // eval_topn: re-score in list order, settle
+                        const float *xx = q.feat + (int64_t)tt * m.blk + m.featoff[f];
+                        int32_t sc[4];
+                        for (int i = 0; i < N; ++i) {
+                            const int32_t v = __float2int_rz(fsg_gau_dist(rec + (int64_t)cc[i] * RL, xx, L));
+                            int j = i;
+                            const int ci = cc[i];
+                            for (; j > 0 && v > sc[j - 1]; --j) {
+                                sc[j] = sc[j - 1];
+                                cc[j] = cc[j - 1];
+                            }
+                            sc[j] = v;
+                            cc[j] = ci;
+                        }
+                    }
+                    c = make_uchar4((unsigned char)cc[0], (unsigned char)cc[1], (unsigned char)cc[2],
+                                    (unsigned char)cc[3]);
+                }
+            }
+            aa.final_topn[(size_t)u * CS + cs] = c;
+        }
     }
     if (ACTIVE && aa.final_active) {
         // acmod's flags as the last frame left them: what the second pass starts from
@@ -882,7 +956,7 @@ size_t fsg_active_ws_ints(const DevModel &m, int n_pnode)
 {
     const size_t nw = (m.n_sen + 31) / 32, CS = (size_t)m.n_mgau * m.n_feat;
     const size_t cap_ev = (3 * (size_t)n_pnode + m.n_sen / 255 + 8 + 1) & ~(size_t)1;
-    size_t n = 4 * CS + CS + CS + CS + nw + cap_ev / 2 + cap_ev / 2 + ((size_t)m.n_sen + 1) / 2;
+    size_t n = 4 * CS + CS + CS + CS + CS + CS + nw + cap_ev / 2 + cap_ev / 2 + ((size_t)m.n_sen + 1) / 2;
     return (n + 3) & ~(size_t)3;  // keeps every utterance's int4 block 16-byte aligned
 }
 
@@ -890,8 +964,8 @@ int launch_fsg_search_active(const DevModel &m, const DevFsgSet &gs, const int64
                              const int32_t *utt_graph, const int64_t *ws_off, int32_t *ws,
                              const float *feat, const int4 *tn_s, const uchar4 *tn_c,
                              const uint32_t *tie, int64_t G, int64_t tie_w, const int64_t *aws_off,
-                             int32_t *aws, uint32_t *final_active, int64_t *n_sen_eval, int n_utts,
-                             int32_t *hist, int hist_cap, int tent_cap, int32_t *n_hist,
+                             int32_t *aws, uint32_t *final_active, int64_t *n_sen_eval,
+                             uchar4 *final_topn, int n_utts, int32_t *hist, int hist_cap, int tent_cap, int32_t *n_hist,
                              int64_t *n_eval, int32_t *frames, int32_t *rv, cudaStream_t st)
 {
     if (n_utts <= 0)
@@ -912,6 +986,7 @@ int launch_fsg_search_active(const DevModel &m, const DevFsgSet &gs, const int64
     aa.aws = aws;
     aa.final_active = final_active;
     aa.n_sen_eval = n_sen_eval;
+    aa.final_topn = final_topn;
     const int wpb = 4;
     if (m.n_feat == 3 && m.topn == 4 && m.n_density == 128)
         fsg_search_kernel<true, true><<<(n_utts + wpb - 1) / wpb, wpb * 32, 0, st>>>(
@@ -921,6 +996,33 @@ int launch_fsg_search_active(const DevModel &m, const DevFsgSet &gs, const int64
         fsg_search_kernel<true, false><<<(n_utts + wpb - 1) / wpb, wpb * 32, 0, st>>>(
             m, gs, aa, frame_off, utt_graph, ws_off, ws, nullptr, 0, 0, n_utts, hist, hist_cap, tent_cap,
             n_hist, n_eval, frames, rv);
+    SSB_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
+__global__ void fsg_final_topn_dense_kernel(DevModel m, const int64_t *__restrict__ frame_off, int n_utts,
+                                            const uchar4 *__restrict__ tn_c, int64_t G,
+                                            uchar4 *__restrict__ final_topn)
+{
+    const int CS = m.n_mgau * m.n_feat;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_utts * CS)
+        return;
+    const int u = (int)(i / CS), cs = (int)(i - (int64_t)u * CS);
+    const int T = (int)(frame_off[u + 1] - frame_off[u]);
+    const int tl = (T & 1) ? T - 2 : T - 1;  // history slot 1 = the last odd frame
+    final_topn[i] = tl >= 0 ? tn_c[(int64_t)cs * G + frame_off[u] + tl] : make_uchar4(0, 1, 2, 3);
+}
+
+int launch_fsg_final_topn_dense(const DevModel &m, const int64_t *frame_off, int n_utts,
+                                const uchar4 *tn_c, int64_t G, uchar4 *final_topn, cudaStream_t st)
+{
+    if (n_utts <= 0)
+        return 0;
+    const int64_t n = (int64_t)n_utts * m.n_mgau * m.n_feat;
+    fsg_final_topn_dense_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m, frame_off, n_utts, tn_c, G,
+                                                                             final_topn);
     SSB_CUDA(cudaGetLastError());
     note_launch();
     return 0;

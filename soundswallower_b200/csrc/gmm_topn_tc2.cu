@@ -270,6 +270,13 @@ gmm_topn_tc2_kernel(DevModel m, DevPlan p, const float *__restrict__ featp, int6
 
     TcTopN<N> tn;
     tn.reset();
+    if (p.init_topn && has_utt) {  // the lists a previous pass left (scores are re-computed)
+        const uchar4 c = p.init_topn[(int64_t)u * gridDim.x + cs];
+        const int cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+            tn.c[k] = cc[k];
+    }
     int t_last = -1;  // last frame on which tn was the reference's exact list
     float4 xn[4];
     int xn_t = -1;    // frame held in xn

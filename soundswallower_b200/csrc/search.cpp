@@ -54,7 +54,8 @@ struct SearchImpl {
     std::vector<std::string> seg_word_store;
     // acmod's active-senone flags: left by the grammar search / found by the aligner
     std::vector<uint32_t> flags;
-    int n_sen = 0;
+    std::vector<uint8_t> carried;  // the scorer's carried top-N codewords ([CS][4]), likewise
+    int n_sen = 0, n_cs = 0;
 };
 
 struct SegImpl {
@@ -117,6 +118,7 @@ int align_finish(ssb_search_t *s)
     in.sf = S->sf.data();
     in.ef = S->ef.data();
     in.init_active = S->flags.empty() ? nullptr : S->flags.data();
+    in.init_topn = S->carried.empty() ? nullptr : S->carried.data();
     std::vector<int32_t> st(ns), du(ns), sc(ns);
     for (int i = 0; i < ns; ++i) {
         st[i] = S->state[i].start;
@@ -316,6 +318,8 @@ int fsg_finish(ssb_search_t *s)
         out.utt_rv = &rv;
         out.n_hist = &n_hist;
         out.final_active = S->flags.data();
+        S->carried.assign((size_t)S->n_cs * 4, 0);
+        out.final_topn = S->n_cs ? S->carried.data() : nullptr;
         if (ssb_fsg_batch(S->m, &in, &out) != 0)
             return -1;
         if (rv != 0) {
@@ -422,6 +426,7 @@ SearchImpl *new_search(int kind, const char *type, const char *name, ssb_model_t
     S->blk = h->blk;
     S->n_emit = h->n_emit;
     S->n_sen = h->n_sen;
+    S->n_cs = h->kind == SSB_SCORER_CONT ? 0 : h->n_mgau * h->n_feat;
     S->type_s = type;
     S->name_s = name ? name : "";
     // search_module_init (ref: src/decoder.c:1276-1307)
@@ -535,6 +540,32 @@ extern "C" int ssb_search_set_init_active(ssb_search_t *s, const uint32_t *bits)
         S->flags.assign(bits, bits + nw);
     else
         S->flags.clear();
+    return 0;
+}
+
+extern "C" int ssb_search_final_topn(const ssb_search_t *s, uint8_t *cw)
+{
+    if (!s || !cw) {
+        set_error("ssb_search_final_topn: bad arguments");
+        return -1;
+    }
+    const SearchImpl *S = reinterpret_cast<const SearchImpl *>(s);
+    for (size_t i = 0; i < (size_t)S->n_cs * 4; ++i)
+        cw[i] = i < S->carried.size() ? S->carried[i] : (uint8_t)(i & 3);
+    return S->n_cs;
+}
+
+extern "C" int ssb_search_set_init_topn(ssb_search_t *s, const uint8_t *cw)
+{
+    if (!s) {
+        set_error("NULL search");
+        return -1;
+    }
+    SearchImpl *S = impl(s);
+    if (cw)
+        S->carried.assign(cw, cw + (size_t)S->n_cs * 4);
+    else
+        S->carried.clear();
     return 0;
 }
 

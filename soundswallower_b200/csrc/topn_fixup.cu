@@ -10,7 +10,8 @@
 //   * a codebook is scanned on every frame from the one it becomes active on (the aligner's
 //     active set only grows, ref: src/state_align_search.c:186-188; compallsen scans
 //     everything), so at a flagged frame t the carried list is the final list of frame t-1;
-//   * on the very first scan the carried list is the initial one (codewords 0..N-1) as
+//   * on the very first scan the carried list is the initial one (codewords 0..N-1, or what a
+//     previous pass left: DevPlan.init_topn) as
 //     eval_topn has re-scored and stably re-sorted it on every frame before (ref :234-237) --
 //     re-played from the most recent frame on which those N scores are pairwise distinct
 //     (their order is forced there), or from the utterance's first frame.
@@ -88,6 +89,13 @@ topn_fixup_kernel(DevModel m, DevPlan p, const int32_t *__restrict__ seg_utts,
             if (lane == 0) {
                 TcTopN<N> tn;
                 tn.reset();
+                if (p.init_topn) {  // the lists a previous pass left
+                    const uchar4 c = p.init_topn[(int64_t)u * gridDim.x + cs];
+                    const int cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+                    for (int k = 0; k < N; ++k)
+                        tn.c[k] = cc[k];
+                }
                 if (t <= a) {
                     int tt0 = 0;
                     for (int tt = t - 1; tt > 0; --tt) {
@@ -95,7 +103,7 @@ topn_fixup_kernel(DevModel m, DevPlan p, const int32_t *__restrict__ seg_utts,
                         int32_t s[N];
 #pragma unroll
                         for (int k = 0; k < N; ++k)
-                            s[k] = __float2int_rz(fix_gau_dist(rec + (int64_t)k * RL, xx, L));
+                            s[k] = __float2int_rz(fix_gau_dist(rec + (int64_t)tn.c[k] * RL, xx, L));
                         bool distinct = true;
 #pragma unroll
                         for (int i = 0; i < N; ++i)

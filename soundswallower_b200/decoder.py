@@ -256,7 +256,9 @@ class Decoder:
             metas.append((wids, c))
         # the aligner starts from the flags the first pass left in acmod
         # (ref: src/state_align_search.c:186-188 never clears them)
-        p2 = align_batch(m, feats, chains, init_active=_left_active([r.p1 for r in results]))
+        carried = [r.p1.get("carried") for r in results]
+        p2 = align_batch(m, feats, chains, init_active=_left_active([r.p1 for r in results]),
+                         init_topn=carried if all(c is not None for c in carried) else None)
         sseq = m.arrays()["sseq"]
         for r, meta, a in zip(results, metas, p2):
             if meta is None or a["rv"] != 0:

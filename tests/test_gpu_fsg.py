@@ -154,6 +154,52 @@ def test_fsg_active_lists_golden(models, golden, fsg_golden, active_golden, lang
     assert np.array_equal(r["segs"][:, 1:], a[name + "_segs"][:, 1:])
 
 
+@pytest.mark.parametrize("lang", ["en-us", "fr-fr"])
+@pytest.mark.parametrize("name", ["align", "mid46", "odd", "wide", "noisy", "tiled"])
+def test_second_pass_inherits_the_scorers_lists(models, oracles, golden, fsg_golden, active_golden, lang, name):
+    """ptm_mgau's top-N lists are not reset between the passes: the grammar search exports the
+    lists the reference is left carrying (history slot 1 = after the last odd frame, re-sorted by
+    eval_topn on every frame since the codebook's last scan) and the aligner starts from them.
+    On en-us mid46 / odd / wide the reference's state scores come out only this way."""
+    m, o, a = models(lang), oracles(lang), active_golden[lang]
+    lx = ssb.Lexicon(m, hmmdir=model_dir(lang))
+    G, feat = active_case(lang, name, golden[lang]["feat"], fsg_golden[lang], a)
+    p1 = ssb.fsg_batch(m, [feat, feat[:-3]], [G], compallsen=False)
+    for f, r in zip((feat, feat[:-3]), p1):     # both frame-count parities
+        assert np.array_equal(r["carried"], o.fsg_search_active(G, f)["carried"].reshape(-1, 4))
+    segs = a[name + "_segs"]
+    segs = segs[segs[:, 0] >= 0]
+    chain = lx.populate(segs[:, 0], segs[:, 1], segs[:, 2] - segs[:, 1] + 1)
+    left = [int(w * 32 + b) for w, x in enumerate(p1[0]["active"]) for b in range(32) if (int(x) >> b) & 1]
+    want = a[name + "_p2_states"]
+    r = ssb.align_batch(m, [feat], [chain], init_active=[left], init_topn=[p1[0]["carried"]])[0]
+    assert r["rv"] == 0 and np.array_equal(np.stack([r["start"], r["dur"], r["score"]], 1), want[:, 1:4])
+    if lang == "en-us" and name in ("mid46", "odd", "wide"):
+        r0 = ssb.align_batch(m, [feat], [chain], init_active=[left])[0]
+        assert not np.array_equal(r0["score"], want[:, 3])
+        # dense first pass (compallsen = yes) exports its lists too: K1's own of the last odd frame
+        d1 = ssb.fsg_batch(m, [feat], [G], compallsen=True)[0]
+        assert d1["carried"].shape == (m.n_mgau * m.n_feat, 4)
+
+
+@pytest.mark.parametrize("seg", [5, 37])
+def test_carried_lists_with_segmented_topn(models, oracles, golden, fsg_golden, active_golden, monkeypatch, seg):
+    """The same hand-over when K1 scores segments independently and the fix-up replays the ties."""
+    m, a = models("en-us"), active_golden["en-us"]
+    lx = ssb.Lexicon(m, hmmdir=model_dir("en-us"))
+    monkeypatch.setenv("SSB_K1_SEG", str(seg))
+    for name in ("mid46", "odd", "wide"):
+        G, feat = active_case("en-us", name, golden["en-us"]["feat"], fsg_golden["en-us"], a)
+        p1 = ssb.fsg_batch(m, [feat], [G], compallsen=False)[0]
+        assert p1["hyp_score"] == int(a[name + "_hyp_score"])
+        segs = a[name + "_segs"]
+        segs = segs[segs[:, 0] >= 0]
+        chain = lx.populate(segs[:, 0], segs[:, 1], segs[:, 2] - segs[:, 1] + 1)
+        left = [int(w * 32 + b) for w, x in enumerate(p1["active"]) for b in range(32) if (int(x) >> b) & 1]
+        r = ssb.align_batch(m, [feat], [chain], init_active=[left], init_topn=[p1["carried"]])[0]
+        assert np.array_equal(np.stack([r["start"], r["dur"], r["score"]], 1), a[name + "_p2_states"][:, 1:4]), name
+
+
 @pytest.mark.parametrize("lang,name", [("fr-fr", "trunc"), ("en-us", "noisy"), ("fr-fr", "tiled")])
 def test_second_pass_starts_from_the_flags_pass_one_left(models, golden, fsg_golden, active_golden, lang, name):
     """decoder_alignment after a default-mode first pass: the aligner never clears acmod's flags

@@ -35,7 +35,7 @@ def test_struct_layouts_match_header():
     assert [f[0] for f in _lib.MgauFuncs._fields_] == ["name", "frame_eval", "transform", "free"]
     assert C.sizeof(_lib.Config) == 64 and _lib.Config.topn_beam.offset == 44
     assert C.sizeof(_lib.FeConfig) == 72
-    assert C.sizeof(_lib.AlignIn) == 80 and C.sizeof(_lib.AlignOut) == 64
+    assert C.sizeof(_lib.AlignIn) == 88 and C.sizeof(_lib.AlignOut) == 64
 
 
 @pytest.mark.parametrize("lang", ["en-us", "fr-fr"])

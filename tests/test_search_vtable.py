@@ -106,6 +106,7 @@ def test_two_pass_through_the_vtables(models, golden, lang):
     p2 = ssb.state_align_search(m, lx, wids, [s[1] for s in seg], [s[2] - s[1] + 1 for s in seg])
     assert np.array_equal(p1.final_active(), fg["align_active"])
     p2.set_init_active(p1.final_active())      # the acmod the two searches share
+    p2.set_init_topn(p1.final_topn())          # ... and the scorer's lists
     assert p2.start() == 0 and p2.forward(feat) == len(feat) and p2.finish() == 0
     assert np.array_equal(p2.alignment("words")[:, :4], g["words"])
     ph = p2.alignment("phones")
@@ -160,3 +161,30 @@ def test_aligner_reports_failure_like_the_reference(models, golden):
     a = ssb.state_align_search(m, lx, wids)
     a.start(); a.forward(g["feat"][:20])
     assert a.finish() == -1 and "Failed to reach final state" in _lib.last_error()
+
+
+@pytest.mark.gpu
+def test_two_pass_hands_over_the_scorers_lists(models, golden):
+    """en-us "mid46": three frames whose Gaussian scores all clamp sit where `go` is first scanned
+    in pass 2, so the reference's state scores depend on the lists pass 1 left in the scorer."""
+    m, g = models("en-us"), golden["en-us"]
+    a = np.load(os.path.join(os.path.dirname(__file__), "golden", "fsg_active_en-us.npz"))
+    lx = ssb.Lexicon(m, hmmdir=model_dir("en-us"))
+    feat = g["feat"].copy()
+    feat[46:49] *= np.float32(3000)
+    want = a["mid46_p2_states"]
+    # search objects
+    p1 = ssb.fsg_search(m, lx, TEXT["en-us"])
+    p1.start(); p1.forward(feat); p1.finish()
+    seg = [s for s in p1.seg() if s[0] != "(NULL)"]
+    p2 = ssb.state_align_search(m, lx, [lx.wordid(s[0]) for s in seg], [s[1] for s in seg],
+                                [s[2] - s[1] + 1 for s in seg])
+    p2.set_init_active(p1.final_active())
+    p2.set_init_topn(p1.final_topn())
+    p2.start(); p2.forward(feat); assert p2.finish() == 0
+    assert np.array_equal(p2.alignment("states"), want)
+    # align_texts (Python) and ssb_align_texts (C)
+    r = ssb.align_texts(m, lx, [feat], [TEXT["en-us"]])[0]
+    assert np.array_equal(r["states"][:, :4], want[:, :4])
+    ta = ssb.TextAlignment(m, lx, [feat], [TEXT["en-us"]], align_level=2)
+    assert np.array_equal(ta.entries(0, "states"), want)

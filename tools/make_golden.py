@@ -185,10 +185,23 @@ def fsg_active_cases(lang, text, feat, jsgf):
     """(name, grammar selection, features) of the default-mode fixtures; the noisy case is
     regenerated from its seed by the tests."""
     rs = np.random.RandomState(1)
+    noisy = feat + rs.randn(*feat.shape).astype(np.float32) * np.float32(0.3)
+    # frames on which every Gaussian score clamps to INT32_MIN, placed where a codebook is first
+    # scanned in the second pass: the lists the first pass left in the scorer decide there
+    # (they are not reset between passes, ref: src/ptm_mgau.c:426-440); "odd" has an odd frame
+    # count, so history slot 1 holds the second-to-last frame's lists
+    mid46 = feat.copy()
+    mid46[46:49] *= np.float32(3000)
+    odd = feat[:-1].copy()
+    odd[46:49] *= np.float32(3000)
+    wide = feat.copy()
+    wide[44:50] *= np.float32(300)
     return [("align", dict(align_text=text), feat), ("jsgf", dict(jsgf=jsgf), feat),
             ("trunc", dict(align_text=text), feat[:150]),
-            ("noisy", dict(align_text=text), feat + rs.randn(*feat.shape).astype(np.float32) * np.float32(0.3)),
-            ("tiled", dict(align_text=" ".join([text] * 2)), np.concatenate([feat, feat]))]
+            ("noisy", dict(align_text=text), noisy),
+            ("tiled", dict(align_text=" ".join([text] * 2)), np.concatenate([feat, feat])),
+            ("mid46", dict(align_text=text), mid46), ("odd", dict(align_text=text), odd),
+            ("wide", dict(align_text=text), wide)]
 
 
 def fsg_active(lang, text, gram):
