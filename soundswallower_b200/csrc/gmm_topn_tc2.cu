@@ -187,7 +187,9 @@ __device__ __forceinline__ void unpack_x(const float4 (&q)[4], float (&x)[TC_L])
     x[12] = q[3].x;
 }
 
-template <int N, bool DEBUG, bool RAW>
+// INIT: start from the lists a previous pass left (DevPlan.init_topn) -- a separate
+// instantiation, because the kernel sits exactly at its 128-register budget
+template <int N, bool DEBUG, bool RAW, bool INIT>
 __global__ void __launch_bounds__(TC2_THREADS, 2)
 gmm_topn_tc2_kernel(DevModel m, DevPlan p, const float *__restrict__ featp, int64_t G,
                     int4 *__restrict__ out_s, uchar4 *__restrict__ out_c, TcDebug dbg)
@@ -270,13 +272,6 @@ gmm_topn_tc2_kernel(DevModel m, DevPlan p, const float *__restrict__ featp, int6
 
     TcTopN<N> tn;
     tn.reset();
-    if (p.init_topn && has_utt) {  // the lists a previous pass left (scores are re-computed)
-        const uchar4 c = p.init_topn[(int64_t)u * gridDim.x + cs];
-        const int cc[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-        for (int k = 0; k < N; ++k)
-            tn.c[k] = cc[k];
-    }
     int t_last = -1;  // last frame on which tn was the reference's exact list
     float4 xn[4];
     int xn_t = -1;    // frame held in xn
@@ -511,6 +506,15 @@ gmm_topn_tc2_kernel(DevModel m, DevPlan p, const float *__restrict__ featp, int6
                     ++n_slow;
                 if (p.tie_bits)
                     atomicOr(&p.tie_bits[(int64_t)cs * p.tie_w + ((g0 + t) >> 5)], 1u << ((g0 + t) & 31));
+                if (INIT && t_last < 0) {
+                    // no exact step yet: the carried list is still the one a previous pass left
+                    // (loaded here, on the cold path: the kernel sits at its register budget)
+                    const uchar4 c = p.init_topn[(int64_t)u * gridDim.x + cs];
+                    const int cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+                    for (int k = 0; k < N; ++k)
+                        tn.c[k] = cc[k];
+                }
 #pragma unroll 1
                 for (int tt = t_last + 1; tt <= t; ++tt) {
                     float xx[TC_L];
@@ -596,17 +600,18 @@ int launch_gmm_topn_tc2(const DevModel &m, const DevPlan &p, const float *feat, 
     const float *src = raw ? feat : featp;
     const size_t smem = sizeof(Tc2Smem) + 1024;
     dim3 grid(m.n_mgau * m.n_feat, (p.n_utts + TC2_THREADS - 1) / TC2_THREADS);
+#define SSB_TC2_(NN, DBG, RW, IN)                                                                 \
+    do {                                                                                          \
+        SSB_DYN_SMEM((gmm_topn_tc2_kernel<NN, DBG, RW, IN>), smem);                               \
+        gmm_topn_tc2_kernel<NN, DBG, RW, IN><<<grid, TC2_THREADS, smem, st>>>(m, p, src, n_frames, \
+                                                                              tn_score, tn_cw, dbg); \
+    } while (0)
 #define SSB_TC2(NN, DBG)                                                                          \
     do {                                                                                          \
-        if (raw) {                                                                                \
-            SSB_DYN_SMEM((gmm_topn_tc2_kernel<NN, DBG, true>), smem);                             \
-            gmm_topn_tc2_kernel<NN, DBG, true><<<grid, TC2_THREADS, smem, st>>>(m, p, src, n_frames, \
-                                                                                tn_score, tn_cw, dbg); \
-        } else {                                                                                  \
-            SSB_DYN_SMEM((gmm_topn_tc2_kernel<NN, DBG, false>), smem);                            \
-            gmm_topn_tc2_kernel<NN, DBG, false><<<grid, TC2_THREADS, smem, st>>>(m, p, src, n_frames, \
-                                                                                 tn_score, tn_cw, dbg); \
-        }                                                                                         \
+        if (raw && !p.init_topn) SSB_TC2_(NN, DBG, true, false);                                  \
+        else if (raw) SSB_TC2_(NN, DBG, true, true);                                              \
+        else if (!p.init_topn) SSB_TC2_(NN, DBG, false, false);                                   \
+        else SSB_TC2_(NN, DBG, false, true);                                                      \
     } while (0)
     switch (m.topn) {
     case 1:
@@ -626,6 +631,7 @@ int launch_gmm_topn_tc2(const DevModel &m, const DevPlan &p, const float *feat, 
         return -1;
     }
 #undef SSB_TC2
+#undef SSB_TC2_
     SSB_CUDA(cudaGetLastError());
     note_launch();
     return 0;
