@@ -39,6 +39,9 @@ int ssb_version(void);
 const char *ssb_last_error(void);
 /* number of visible CUDA devices with compute capability 10.x; 0 if none */
 int ssb_device_count(void);
+/* Device blocks released by one call are kept for the next one (per device, at most
+ * $SSB_DEV_CACHE_GB, default 64; 0 = off); this returns them to the driver. */
+int ssb_device_cache_trim(void);
 
 /* ------------------------------------------------------------------ */
 /* model: loaders + packed device image                                */

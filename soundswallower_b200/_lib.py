@@ -144,7 +144,7 @@ SYMBOLS = [
     "ssb_search_set_init_active", "ssb_search_final_topn", "ssb_search_set_init_topn",
     "ssb_model_fsg_active_ok", "ssb_align_texts", "ssb_text_align_free",
     "ssb_text_align_status", "ssb_text_align_hyp", "ssb_text_align_entries", "ssb_text_align_json",
-    "ssb_text_align_kernel_ms", "ssb_text_align_render",
+    "ssb_text_align_kernel_ms", "ssb_text_align_render", "ssb_device_cache_trim",
     "ssb_topn_batch", "ssb_tc_probe", "ssb_tc_hot_mask", "ssb_fsg_batch", "ssb_hmm_vit_eval",
     "ssb_fe_config_defaults", "ssb_fe_config_from_model", "ssb_frontend_create",
     "ssb_frontend_free", "ssb_frontend_dims", "ssb_frontend_n_frames", "ssb_frontend_tables",

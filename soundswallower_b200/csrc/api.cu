@@ -127,6 +127,17 @@ extern "C" int ssb_device_count(void)
     return ok;
 }
 
+extern "C" int ssb_device_cache_trim(void)
+{
+    DevBlockCache &c = dev_block_cache();
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess)
+        return -1;
+    std::lock_guard<std::mutex> lk(c.mu);
+    c.trim(dev & 15);
+    return 0;
+}
+
 extern "C" void ssb_config_defaults(ssb_config_t *c)
 {
     // ref: include/soundswallower/config_defs.h:78-257
@@ -979,6 +990,9 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
 
     // ---- device buffers; the feature copy starts now and overlaps the planning below
     cudaStream_t st = b->st;
+    // buffers that have to grow go back to the block cache: nothing of the previous run may
+    // still be using them
+    API_CUDA(cudaStreamSynchronize(st), -1);
     const int CS = h.kind == SSB_SCORER_CONT ? 0 : h.n_mgau * h.n_feat;  // no top-N stage
     const int64_t G = b->n_frames;
     if (b->feat.ensure(std::max<size_t>((size_t)G * h.blk * sizeof(float), 16)) != 0
@@ -2249,6 +2263,7 @@ extern "C" int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out
         out->n_launches = launch_count(true);
         rv = 0;
     } while (0);
+    cudaStreamSynchronize(b->st);  // (error paths: nothing may still be running on these buffers)
     DBuf *all[] = {&d_hdr, &d_link4, &d_flag, &d_arc, &d_root, &d_pnode, &d_ctxt, &d_ug, &d_wsoff, &d_ws,
                    &d_hist, &d_nhist, &d_neval, &d_frames, &d_rv, &d_exit, &d_score, &d_segs, &d_nseg,
                    &d_awsoff, &d_aws, &d_tie, &d_fact, &d_nsen, &d_ftopn};
