@@ -862,8 +862,11 @@ void plan_range(const HostModel &h, const ssb_align_in_t *in, const std::vector<
                 }
             if (!grew)
                 continue;
-            if (S.act.size() != before || n_ep == 0)
-                std::sort(S.act.begin(), S.act.end());
+            if (S.act.size() != before || n_ep == 0) {
+                // the list was sorted up to `before`: sort the few newcomers and merge them in
+                std::sort(S.act.begin() + before, S.act.end());
+                std::inplace_merge(S.act.begin(), S.act.begin() + before, S.act.end());
+            }
             const size_t e0 = S.ev.size();
             eval_list_from_sorted(S.act, S.ev);
             S.ev_off.push_back((int32_t)S.ev.size());
