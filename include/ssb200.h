@@ -322,6 +322,13 @@ int ssb_model_fsg_active_ok(const ssb_model_t *m);
 int ssb_hmm_vit_eval(ssb_model_t *m, int32_t n_emit, int32_t tmatid, const uint16_t *senid,
                      const int16_t *senscr, int32_t *st12, int32_t *best);
 
+/* n_cases independent steps on caller-provided transition matrices: tp [n][n_emit][n_emit+1]
+ * (255 = impossible), senscr [n][n_emit] (the scores of the HMM's own states), st12 [n][12]
+ * updated in place, best [n].  n_emit 3 or 5 (hmm_vit_eval_3st_lr / _5st_lr, ref:
+ * src/hmm.c:166-304, 482-567) whatever the model has. */
+int ssb_hmm_vit_eval_tp(ssb_model_t *m, int32_t n_emit, int32_t n_cases, const uint8_t *tp,
+                        const int16_t *senscr, int32_t *st12, int32_t *best);
+
 /* ------------------------------------------------------------------ lexicon (host only)
  * Graph preparation for the chain aligner: pronunciation dictionary + context-dependent phone
  * lookup + the word -> phone-chain expansion.  Word ids are the reference's (main dictionary

@@ -657,6 +657,46 @@ ref_hmm_vit_eval(void *h, int n_emit, int tmatid, const uint16 *senid,
     return best;
 }
 
+/* The same on a caller-provided transition matrix tp[n_emit][n_emit+1] (255 = impossible) and
+ * the n_emit senone scores of the HMM's states: hmm_vit_eval_5st_lr has no bundled model. */
+int
+ref_hmm_vit_eval_tp(void *h, int n_emit, const uint8 *tp, const int16 *senscr, int32 *st)
+{
+    uint8 *rows[8];
+    uint8 **mat[1];
+    uint16 sseq_row[8];
+    uint16 *const sseq[1] = { sseq_row };
+    hmm_context_t *ctx;
+    hmm_t hmm;
+    int32 best;
+    int i;
+    (void)h;
+    if (n_emit < 1 || n_emit > 5)
+        return 0x7fffffff;
+    for (i = 0; i < n_emit; ++i) {
+        rows[i] = (uint8 *)tp + i * (n_emit + 1);
+        sseq_row[i] = (uint16)i;
+    }
+    mat[0] = rows;
+    ctx = hmm_context_init(n_emit, mat, senscr, sseq);
+    hmm_init(ctx, &hmm, FALSE, 0, 0);
+    for (i = 0; i < 5; ++i) {
+        hmm.score[i] = st[i];
+        hmm.history[i] = st[5 + i];
+    }
+    hmm.out_score = st[10];
+    hmm.out_history = st[11];
+    best = hmm_vit_eval(&hmm);
+    for (i = 0; i < 5; ++i) {
+        st[i] = hmm.score[i];
+        st[5 + i] = hmm.history[i];
+    }
+    st[10] = hmm.out_score;
+    st[11] = hmm.out_history;
+    hmm_context_free(ctx);
+    return best;
+}
+
 /* ------------------------------------------------------------------ */
 /* FSG search: flattened graph + history table (for the K4 oracle/kernel) */
 /* ------------------------------------------------------------------ */

@@ -241,6 +241,17 @@ class Ref:
         assert rv >= 0, rv
         return dict(segs=segs[:rv].copy(), hyp_score=int(n_out[4]), n_frames=int(n_out[5]))
 
+    def hmm_vit_eval_tp(self, tp, senscr, st):
+        """hmm_vit_eval on a caller-provided transition matrix [n_emit][n_emit+1] and the n_emit
+        scores of the HMM's own states (3- or 5-state)."""
+        tp = np.ascontiguousarray(tp, np.uint8)
+        n_emit = tp.shape[0]
+        senscr = np.ascontiguousarray(senscr, np.int16)
+        st = np.ascontiguousarray(st, np.int32).copy()
+        best = self.lib.ref_hmm_vit_eval_tp(self.h, n_emit, _p(tp, C.c_uint8), _p(senscr, C.c_int16),
+                                            _p(st, C.c_int32))
+        return best, st
+
     def active_bits(self):
         """(acmod's active-senone flags as uint32 words, senones evaluated by the last fsg search)"""
         out = np.zeros((self.n_sen + 31) // 32, np.uint32)

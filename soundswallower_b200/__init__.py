@@ -634,6 +634,19 @@ TRANSFORMS = {"dct": 0, "legacy": 1, "htk": 2}
 CMN_TYPES = {"none": 0, "batch": 1, "current": 1}
 
 
+def hmm_vit_eval_tp(model, tp, senscr, st):
+    """Many hmm_vit_eval steps on given transition matrices: tp [n][E][E+1] uint8, senscr [n][E],
+    st [n][12]; returns (best [n], new st [n][12]).  E = 3 or 5."""
+    tp = np.ascontiguousarray(tp, np.uint8)
+    n, E = tp.shape[0], tp.shape[1]
+    senscr = np.ascontiguousarray(senscr, np.int16).reshape(n, E)
+    st = np.ascontiguousarray(st, np.int32).reshape(n, 12).copy()
+    best = np.zeros(n, np.int32)
+    _lib.check(model.lib.ssb_hmm_vit_eval_tp(model.h, E, n, _ptr(tp), _ptr(senscr), _ptr(st), _ptr(best)),
+               "ssb_hmm_vit_eval_tp")
+    return best, st
+
+
 class DeviceFeatures:
     """Features of a batch that stayed in HBM (Frontend.run): accepted wherever a list of
     per-utterance feature arrays is (align_batch, fsg_batch, score_batch, StateAlignBatch)."""

@@ -144,7 +144,7 @@ SYMBOLS = [
     "ssb_search_set_init_active", "ssb_search_final_topn", "ssb_search_set_init_topn",
     "ssb_model_fsg_active_ok", "ssb_align_texts", "ssb_text_align_free",
     "ssb_text_align_status", "ssb_text_align_hyp", "ssb_text_align_entries", "ssb_text_align_json",
-    "ssb_text_align_kernel_ms", "ssb_text_align_render", "ssb_device_cache_trim",
+    "ssb_text_align_kernel_ms", "ssb_text_align_render", "ssb_device_cache_trim", "ssb_hmm_vit_eval_tp",
     "ssb_topn_batch", "ssb_tc_probe", "ssb_tc_hot_mask", "ssb_fsg_batch", "ssb_hmm_vit_eval",
     "ssb_fe_config_defaults", "ssb_fe_config_from_model", "ssb_frontend_create",
     "ssb_frontend_free", "ssb_frontend_dims", "ssb_frontend_n_frames", "ssb_frontend_tables",
@@ -223,6 +223,7 @@ def load():
     L.ssb_tc_hot_mask.argtypes = [vp, vp]
     L.ssb_fsg_batch.argtypes = [vp, P(FsgIn), P(FsgOut)]
     L.ssb_hmm_vit_eval.argtypes = [vp, i32, i32, vp, vp, vp, P(i32)]
+    L.ssb_hmm_vit_eval_tp.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     L.ssb_model_kind.argtypes = [vp]
     L.ssb_model_ciphone_str.restype = C.c_char_p
     L.ssb_model_ciphone_str.argtypes = [vp, i32]

@@ -2017,6 +2017,47 @@ extern "C" int ssb_hmm_vit_eval(ssb_model_t *m, int32_t n_emit, int32_t tmatid,
     return rv;
 }
 
+extern "C" int ssb_hmm_vit_eval_tp(ssb_model_t *m, int32_t n_emit, int32_t n_cases, const uint8_t *tp,
+                                   const int16_t *senscr, int32_t *st12, int32_t *best)
+{
+    if (need_device(m) != 0)
+        return -1;
+    if ((n_emit != 3 && n_emit != 5) || n_cases < 0 || (n_cases > 0 && (!tp || !senscr || !st12 || !best))) {
+        set_error("ssb_hmm_vit_eval_tp: bad arguments (3 or 5 emitting states)");
+        return -1;
+    }
+    if (n_cases == 0)
+        return 0;
+    const size_t nt = (size_t)n_cases * n_emit * (n_emit + 1), ns = (size_t)n_cases * n_emit * 2,
+                 nst = (size_t)n_cases * 48, nb = (size_t)n_cases * 4;
+    DBuf a, s, t, o;
+    int rv = -1;
+    do {
+        if (a.ensure(nt) || s.ensure(ns) || t.ensure(nst) || o.ensure(nb))
+            break;
+        if (cudaMemcpy(a.p, tp, nt, cudaMemcpyHostToDevice) != cudaSuccess
+            || cudaMemcpy(s.p, senscr, ns, cudaMemcpyHostToDevice) != cudaSuccess
+            || cudaMemcpy(t.p, st12, nst, cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error("ssb_hmm_vit_eval_tp: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        if (launch_hmm_eval_tp(n_emit, n_cases, a.as<uint8_t>(), s.as<int16_t>(), t.as<int32_t>(),
+                               o.as<int32_t>(), nullptr) != 0)
+            break;
+        if (cudaMemcpy(st12, t.p, nst, cudaMemcpyDeviceToHost) != cudaSuccess
+            || cudaMemcpy(best, o.p, nb, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            set_error("ssb_hmm_vit_eval_tp: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        rv = 0;
+    } while (0);
+    a.release();
+    s.release();
+    t.release();
+    o.release();
+    return rv;
+}
+
 // ------------------------------------------------------------------ FSG search (K4)
 // frames per dense-score slab of the FSG path: whole utterances, <= ~12 GB of int16 scores
 static const int64_t kFsgSlabFrames = 1200000;

@@ -393,6 +393,65 @@ __global__ void hmm_eval_kernel(DevModel m, int n_emit, int tmatid,
     }
 }
 
+// Many independent HMM steps on caller-provided transition matrices (known-answer tests of
+// hmm_step3 / hmm_step5, the 5-state evaluator included: no bundled model has 5-state HMMs).
+// Case i: tp[i][E][E+1], senscr[i][E] (the scores of the HMM's own states), st12[i] in place.
+__global__ void hmm_eval_tp_kernel(int n_emit, int n_cases, const uint8_t *__restrict__ tp,
+                                   const int16_t *__restrict__ senscr, int32_t *st12, int32_t *best)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cases)
+        return;
+    const uint8_t *t = tp + (size_t)i * n_emit * (n_emit + 1);
+    int32_t *st = st12 + (size_t)i * 12;
+    if (n_emit == 3) {
+        int32_t s[3], h[3], o_s = st[10], o_h = st[11];
+        int ss[3];
+        for (int j = 0; j < 3; ++j) {
+            s[j] = st[j];
+            h[j] = st[5 + j];
+            ss[j] = senscr[(size_t)i * 3 + j];
+        }
+        best[i] = hmm_step3(t, ss, s, h, o_s, o_h);
+        for (int j = 0; j < 3; ++j) {
+            st[j] = s[j];
+            st[5 + j] = h[j];
+        }
+        st[10] = o_s;
+        st[11] = o_h;
+    } else {
+        int32_t s[5], h[5], o_s = st[10], o_h = st[11];
+        int ss[5];
+        for (int j = 0; j < 5; ++j) {
+            s[j] = st[j];
+            h[j] = st[5 + j];
+            ss[j] = senscr[(size_t)i * 5 + j];
+        }
+        best[i] = hmm_step5(t, ss, s, h, o_s, o_h);
+        for (int j = 0; j < 5; ++j) {
+            st[j] = s[j];
+            st[5 + j] = h[j];
+        }
+        st[10] = o_s;
+        st[11] = o_h;
+    }
+}
+
+int launch_hmm_eval_tp(int n_emit, int n_cases, const uint8_t *tp, const int16_t *senscr, int32_t *st12,
+                       int32_t *best, cudaStream_t st)
+{
+    if (n_emit != 3 && n_emit != 5) {
+        set_error("hmm_vit_eval: %d emitting states not supported (3 or 5)", n_emit);
+        return -1;
+    }
+    if (n_cases <= 0)
+        return 0;
+    hmm_eval_tp_kernel<<<(n_cases + 127) / 128, 128, 0, st>>>(n_emit, n_cases, tp, senscr, st12, best);
+    SSB_CUDA(cudaGetLastError());
+    note_launch();
+    return 0;
+}
+
 int launch_hmm_eval(const DevModel &m, int n_emit, int tmatid, const uint16_t *senid,
                     const int16_t *senscr, int32_t *st12, int32_t *best, cudaStream_t st)
 {

@@ -184,6 +184,8 @@ int launch_frame_topn(const DevModel &m, const FrameHist &h, int slot, int prev,
 int launch_frame_senones(const DevModel &m, const FrameHist &h, int slot, int do_norm,
                          const uint16_t *act_sen, int n_act, int compallsen, int16_t *senscr,
                          cudaStream_t st);
+int launch_hmm_eval_tp(int n_emit, int n_cases, const uint8_t *tp, const int16_t *senscr, int32_t *st12,
+                       int32_t *best, cudaStream_t st);
 int launch_hmm_eval(const DevModel &m, int n_emit, int tmatid, const uint16_t *senid,
                     const int16_t *senscr, int32_t *st12, int32_t *best, cudaStream_t st);
 

@@ -161,6 +161,18 @@ def test_hmm_vit_eval_known_answers(models, synthetic):
         assert np.array_equal(st, s["hmm_st_out"][i]), i
 
 
+@pytest.mark.parametrize("E", [5, 3])
+def test_hmm_step_on_given_transition_matrices(models, E):
+    """hmm_step5 / hmm_step3 (the device evaluators K3 and K4 are built on) against the
+    reference's hmm_vit_eval_5st_lr / _3st_lr known answers on random left-to-right transition
+    matrices (tests/golden/hmm5.npz): no bundled model has 5-state HMMs."""
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "hmm5.npz"))
+    best, st = ssb.hmm_vit_eval_tp(models("en-us"), g["tp%d" % E], g["senscr%d" % E], g["st_in%d" % E])
+    assert np.array_equal(best, g["best%d" % E])
+    assert np.array_equal(st, g["st_out%d" % E])
+
+
 # ------------------------------------------------------------------ chain alignment
 def _check_against_golden(r, g, mode):
     st = g[mode + "_states"]

@@ -7,7 +7,9 @@ import hashlib
 import numpy as np
 import pytest
 
-from conftest import chain_from_golden, model_dir, model_features, random_chain
+import os
+
+from conftest import GOLDEN, chain_from_golden, model_dir, model_features, random_chain
 
 
 def sha(a):
@@ -155,3 +157,17 @@ def test_oracle_vs_reference_frontend_golden(golden):
     pcm = np.fromfile(os.path.join(DATA, "goforward.raw"), np.int16)
     assert np.array_equal(ref.features_from_pcm(pcm), golden["en-us"]["feat"])
     ref.close()
+
+
+@pytest.mark.parametrize("E", [5, 3])
+def test_hmm_eval_on_given_transition_matrices(oracles, E):
+    """hmm_vit_eval_5st_lr (and _3st_lr) known answers of the reference on random left-to-right
+    transition matrices with impossible arcs, clamps and ties (tests/golden/hmm5.npz): the
+    bundled models only have 3-state HMMs."""
+    o = oracles("en-us")
+    g = np.load(os.path.join(GOLDEN, "hmm5.npz"))
+    for i in range(len(g["best%d" % E])):
+        best, st = o.hmm_eval(E, g["tp%d" % E][i], np.arange(E, dtype=np.uint16), g["senscr%d" % E][i],
+                              g["st_in%d" % E][i])
+        assert best == int(g["best%d" % E][i]), i
+        assert np.array_equal(st, g["st_out%d" % E][i]), i

@@ -181,6 +181,48 @@ def fsg(lang, raw_feat_key, text, gram):
     np.savez_compressed(os.path.join(OUT, "fsg_%s.npz" % lang), **g)
 
 
+def hmm5(n_case=512, seed=55):
+    """hmm_vit_eval_5st_lr / _3st_lr known answers on random left-to-right transition matrices
+    (self loop, next, skip; 255 = impossible) -- no bundled model has 5-state HMMs -> hmm5.npz."""
+    ref = Ref(os.path.join(MODELS, "en-us"))
+    rs = np.random.RandomState(seed)
+    W = -536870912
+    g = {}
+    for E in (5, 3):
+        tps = np.full((n_case, E, E + 1), 255, np.uint8)
+        scr = rs.randint(0, 400, (n_case, E)).astype(np.int16)
+        st_in = np.zeros((n_case, 12), np.int32)
+        st_out = np.zeros((n_case, 12), np.int32)
+        best = np.zeros(n_case, np.int32)
+        for i in range(n_case):
+            for a in range(E):
+                for b in (a, a + 1, a + 2):
+                    if b <= E and rs.rand() > (0.25 if b == a + 2 else 0.03):
+                        tps[i, a, b] = rs.randint(0, 90)
+            st = np.full(12, W, np.int32)
+            st[5:10] = -1
+            st[11] = -1
+            k = rs.randint(0, E + 2)
+            for j in range(min(k, E)):
+                st[j] = -int(rs.randint(0, 50000))
+                st[5 + j] = int(rs.randint(0, 200))
+            if rs.rand() < 0.2:
+                st[rs.randint(0, E)] = W + int(rs.randint(0, 300))   # clamp region
+            if rs.rand() < 0.25 and k >= 2:
+                j = rs.randint(1, min(k, E))
+                st[j] = st[j - 1]                                      # provoke ties
+            if rs.rand() < 0.3:
+                st[10] = -int(rs.randint(0, 50000))
+                st[11] = int(rs.randint(0, 200))
+            st_in[i] = st
+            best[i], st_out[i] = ref.hmm_vit_eval_tp(tps[i], scr[i], st)
+        g.update({"tp%d" % E: tps, "senscr%d" % E: scr, "st_in%d" % E: st_in, "st_out%d" % E: st_out,
+                  "best%d" % E: best})
+        print("hmm", E, "states:", n_case, "cases, best range", best.min(), best.max())
+    ref.close()
+    np.savez_compressed(os.path.join(OUT, "hmm5.npz"), **g)
+
+
 def fsg_active_cases(lang, text, feat, jsgf):
     """(name, grammar selection, features) of the default-mode fixtures; the noisy case is
     regenerated from its seed by the tests."""
@@ -421,6 +463,8 @@ def main():
         return cont()
     if "--lexicon" in sys.argv:
         return lexicon()
+    if "--hmm5" in sys.argv:
+        return hmm5()
     if "--fsg-active" in sys.argv:
         fsg_active("en-us", "go forward ten meters", "goforward.gram")
         return fsg_active("fr-fr", "avance de dix mètres", "goforward_fr.gram")
@@ -431,6 +475,7 @@ def main():
     fsg("fr-fr", "goforward_fr.raw", "avance de dix mètres", "goforward_fr.gram")
     fsg_active("en-us", "go forward ten meters", "goforward.gram")
     fsg_active("fr-fr", "avance de dix mètres", "goforward_fr.gram")
+    hmm5()
     loaders()
     frontend()
     semi()
