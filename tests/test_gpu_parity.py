@@ -609,3 +609,37 @@ def test_segmented_aligner_equals_oracle(models, oracles, golden, monkeypatch, s
         assert r["rv"] == w["rv"] and r["best_score"] == w["best_score"], u
         if w["rv"] == 0:
             assert np.array_equal(r["start"], w["start"]) and np.array_equal(r["score"], w["score"]), u
+
+
+def test_long_two_pass_alignment_from_text(models, oracles, golden):
+    """Both passes on one long utterance through ssb_align_texts: fr-fr, 70 repetitions of the
+    sentence = 16 730 frames, 280 words (more than one max_seg round), a 281-state alignment
+    grammar, K1 scored in segments in both passes.  Against the oracle running the reference's
+    own sequence: default-mode grammar search, pass 1's words and windows, alignment_populate,
+    the aligner starting from the flags and the top-N lists pass 1 left."""
+    m, o = models("fr-fr"), oracles("fr-fr")
+    from conftest import model_dir
+    lx = ssb.Lexicon(m, hmmdir=model_dir("fr-fr"))
+    reps = 70
+    x, _chain = _tiled_fr(golden, reps)
+    text = " ".join(["avance de dix mètres"] * reps)
+    ta = ssb.TextAlignment(m, lx, [x], [text], align_level=2)
+    rv, hyp_score, n_frames = ta.status(0)
+    assert rv == 0 and n_frames == len(x) + 1 and ta.hyp(0) == text
+    G = lx.align_graph(text)
+    p1 = o.fsg_search_active(G, x, cap=1 << 18)
+    assert p1["exit"] > 0 and p1["hyp_score"] == hyp_score
+    seg = ta.entries(0, "seg")
+    assert len(seg) == len(p1["segs"]) > 256
+    assert np.array_equal(seg[:, 1:], p1["segs"][:, 1:])
+    words = p1["segs"][G["link"][p1["segs"][:, 0], 3] >= 0]
+    wids = G["dict_wid"][G["link"][words[:, 0], 3]]
+    c = lx.populate(wids, words[:, 1], words[:, 2] - words[:, 1] + 1)
+    left = [int(w * 32 + b) for w, v in enumerate(p1["active"]) for b in range(32) if (int(v) >> b) & 1]
+    w2 = o.state_align(x, c["ssid"], c["tmat"], c["sf"], c["ef"], init_active=left, init_topn=p1["carried"])
+    assert w2["rv"] == 0
+    st = ta.entries(0, "states")
+    assert np.array_equal(st[:, 1], w2["start"]) and np.array_equal(st[:, 2], w2["dur"])
+    assert np.array_equal(st[:, 3], w2["score"])
+    wd = ta.entries(0, "words")
+    assert len(wd) == len(wids) and wd[0, 1] == 0 and wd[-1, 1] + wd[-1, 2] == len(x)
