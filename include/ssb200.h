@@ -488,7 +488,9 @@ const char *ssb_text_align_json(ssb_text_align_t *r, int32_t u, double start, in
 /* renders the JSON line of every utterance with up to 16 host threads; ssb_text_align_json
  * with the same (start, align_level) then returns the stored lines */
 int ssb_text_align_render(ssb_text_align_t *r, double start, int32_t align_level);
-int ssb_text_align_kernel_ms(const ssb_text_align_t *r, float *ms4); /* pass 1: top-N, mix, search, backtrace */
+/* ms8: [0..3] kernels of pass 1 (top-N, mix, search, backtrace); wall clock of [4] grammars +
+ * first pass, [5] chains on the host, [6] second pass + propagate, [7] the whole call */
+int ssb_text_align_kernel_ms(const ssb_text_align_t *r, float *ms8);
 
 /* ------------------------------------------------------------------ frontend
  * Batched PCM -> MFCC -> CMN -> dynamic features for whole utterances: what

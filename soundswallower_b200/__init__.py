@@ -1180,9 +1180,10 @@ class TextAlignment:
         return j.decode("utf-8") if j is not None else None
 
     def kernel_ms(self):
-        ms = np.zeros(4, np.float32)
+        ms = np.zeros(8, np.float32)
         self.lib.ssb_text_align_kernel_ms(self.r, _ptr(ms))
-        return dict(gmm_topn=float(ms[0]), senone_mix=float(ms[1]), fsg_search=float(ms[2]), backtrace=float(ms[3]))
+        return dict(gmm_topn=float(ms[0]), senone_mix=float(ms[1]), fsg_search=float(ms[2]), backtrace=float(ms[3]),
+                    wall_pass1=float(ms[4]), wall_chains=float(ms[5]), wall_pass2=float(ms[6]), wall_total=float(ms[7]))
 
 
 from .decoder import (Alignment, AlignmentEntry, Decoder, Hyp, Seg, get_audio_data)  # noqa: E402

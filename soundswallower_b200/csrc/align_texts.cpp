@@ -11,6 +11,7 @@
 //   JSON    decoder_result_json                                  ref: src/decoder.c:1339-1593
 // Host code only: every number comes out of the batched kernels.
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -85,6 +86,10 @@ extern "C" ssb_text_align_t *ssb_align_texts(ssb_model_t *m, const ssb_lexicon_t
     if (U == 0)
         return R.release();
 
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&](std::chrono::steady_clock::time_point t) {
+        return (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+    };
     // ---- pass 1: one alignment grammar per distinct transcript
     std::vector<ssb_fsg_built_t *> built;
     std::vector<std::string> built_text;
@@ -121,7 +126,22 @@ extern "C" ssb_text_align_t *ssb_align_texts(ssb_model_t *m, const ssb_lexicon_t
     int max_T = 0;
     for (int u = 0; u < U; ++u)
         max_T = std::max<int64_t>(max_T, frame_off[u + 1] - frame_off[u]);
-    int max_seg = 256;
+    // a segmentation has one entry per word plus the silences / fillers between them (several
+    // per gap are possible; a second round follows if the estimate is too small):
+    // size the buffer from the longest transcript so that the search runs once
+    size_t max_words = 0;
+    for (const std::string &t : built_text) {
+        size_t nwd = 0;
+        bool in_word = false;
+        for (char ch : t) {
+            const bool sp = ch == ' ' || ch == '\t' || ch == '\n' || ch == '\r';
+            if (!sp && !in_word)
+                ++nwd;
+            in_word = !sp;
+        }
+        max_words = std::max(max_words, nwd);
+    }
+    int max_seg = (int)std::max<size_t>(64, 4 * max_words + 64);
     ssb_fsg_in_t fin;
     std::vector<int32_t> segs, n_seg(U), hyp_score(U), exit_bp(U), rv1(U);
     std::vector<uint32_t> flags((size_t)U * nw, 0u);
@@ -162,6 +182,8 @@ extern "C" ssb_text_align_t *ssb_align_texts(ssb_model_t *m, const ssb_lexicon_t
     }
     for (int k = 0; k < 4; ++k)
         R->kernel_ms[k] = ms1[k];
+    R->kernel_ms[4] = since(t_begin);  // wall: grammars + first pass
+    const auto t_chains = std::chrono::steady_clock::now();
 
     // ---- decoder_alignment: words of pass 1 -> chains
     std::vector<int64_t> phone_off(U + 1, 0);
@@ -231,6 +253,8 @@ extern "C" ssb_text_align_t *ssb_align_texts(ssb_model_t *m, const ssb_lexicon_t
         phone_off[u + 1] = phone_off[u] + np;
     }
 
+    R->kernel_ms[5] = since(t_chains);  // wall: chains on the host
+    const auto t_p2 = std::chrono::steady_clock::now();
     // ---- pass 2
     if (align_level && phone_off[U] > 0) {
         std::vector<int32_t> rv2(U, 0), best(U, 0), ren(U, 0);
@@ -296,6 +320,8 @@ extern "C" ssb_text_align_t *ssb_align_texts(ssb_model_t *m, const ssb_lexicon_t
             }
         }
     }
+    R->kernel_ms[6] = since(t_p2);      // wall: second pass + propagate
+    R->kernel_ms[7] = since(t_begin);
     return R.release();
 }
 
@@ -432,11 +458,11 @@ extern "C" int ssb_text_align_render(ssb_text_align_t *r, double start, int32_t 
     return 0;
 }
 
-extern "C" int ssb_text_align_kernel_ms(const ssb_text_align_t *r, float *ms4)
+extern "C" int ssb_text_align_kernel_ms(const ssb_text_align_t *r, float *ms8)
 {
-    if (!r || !ms4)
+    if (!r || !ms8)
         return -1;
-    for (int k = 0; k < 4; ++k)
-        ms4[k] = r->kernel_ms[k];
+    for (int k = 0; k < 8; ++k)
+        ms8[k] = r->kernel_ms[k];
     return 0;
 }
