@@ -280,3 +280,56 @@ CONT_CASES = [  # (tag, write_cont_model keywords)
     ("cont8", dict(n_density=8, seed=9)),
     ("cont3", dict(n_density=3, seed=10)),   # fewer densities than topn: the unsorted "all" list
 ]
+
+
+def write_five_state_model(src, dst, seed=21):
+    """A model directory whose HMMs have FIVE emitting states (hmm_vit_eval_5st_lr; no bundled
+    model has them): the bundled mdef with every senone sequence [a, b, c] stretched to
+    [a, a, b, c, c] and `transition_matrices` replaced by seeded 5 x 6 left-to-right matrices
+    (self loop, next, skip).  Gaussians and mixture weights are the bundled ones."""
+    os.makedirs(dst, exist_ok=True)
+    for name in ("means", "variances", "sendump", "feat_params.json", "noisedict.txt", "dict.txt",
+                 "phoneset.json"):
+        s = os.path.join(src, name)
+        if os.path.exists(s) and not os.path.exists(os.path.join(dst, name)):
+            os.symlink(os.path.abspath(s), os.path.join(dst, name))
+    blob = bytearray(open(os.path.join(src, "mdef"), "rb").read())
+    assert blob[:4] == b"BMDF"
+    fmt_len = struct.unpack_from("<i", blob, 8)[0]
+    hp = 12 + fmt_len
+    h = list(struct.unpack_from("<10i", blob, hp))
+    n_ci, n_phone, n_emit, n_sseq, n_cd = h[0], h[1], h[2], h[6], h[8]
+    assert n_emit == 3
+    p = names = hp + 40
+    for _ in range(n_ci):
+        p = blob.index(b"\0", p) + 1
+    p = names + (((p - names) + 3) & ~3)
+    p += n_cd * 8 + n_phone * 12
+    assert struct.unpack_from("<i", blob, p)[0] == n_sseq * 3
+    sseq = np.frombuffer(bytes(blob[p + 4:p + 4 + n_sseq * 6]), "<u2").reshape(n_sseq, 3)
+    tail = bytes(blob[p + 4 + n_sseq * 6:])
+    s5 = sseq[:, [0, 0, 1, 2, 2]]
+    h[2] = 5
+    struct.pack_into("<10i", blob, hp, *h)
+    out = bytes(blob[:p]) + struct.pack("<i", n_sseq * 5) + np.ascontiguousarray(s5, "<u2").tobytes() + tail
+    with open(os.path.join(dst, "mdef"), "wb") as fh:
+        fh.write(out)
+    # transition matrices [n_tmat][5][6], rows normalised by the loader
+    n_tmat = h[5]
+    rs = np.random.RandomState(seed)
+    tm = np.zeros((n_tmat, 5, 6), "<f4")
+    for t in range(n_tmat):
+        for a in range(5):
+            w = rs.uniform(0.05, 1.0, 3)
+            if rs.rand() < 0.3:
+                w[2] = 0.0                      # no skip arc
+            w /= w.sum()
+            for k, b in enumerate((a, a + 1, a + 2)):
+                if b <= 5:
+                    tm[t, a, b] = w[k]
+    words = np.concatenate([np.array([n_tmat, 5, 6, tm.size], "<i4").view("<u4"), tm.view("<u4").ravel()])
+    with open(os.path.join(dst, "transition_matrices"), "wb") as fh:
+        fh.write(b"s3\nversion 1.0\nchksum0 yes\nendhdr\n" + struct.pack("<I", 0x11223344))
+        fh.write(words.tobytes())
+        fh.write(struct.pack("<I", _s3_checksum(words)))
+    return dst

@@ -223,6 +223,39 @@ def hmm5(n_case=512, seed=55):
     np.savez_compressed(os.path.join(OUT, "hmm5.npz"), **g)
 
 
+def five_state(lang="en-us"):
+    """Forced alignment through the reference on a model whose HMMs have five emitting states
+    (tests/model_variants.py:write_five_state_model): hmm_vit_eval_5st_lr inside
+    state_align_search -> five_state_<lang>.npz."""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import model_variants as mv
+    g0 = np.load(os.path.join(OUT, "align_%s.npz" % lang))
+    feat, words = g0["feat"], g0["words"]
+    rs = np.random.RandomState(5)
+    noisy = feat + rs.randn(*feat.shape).astype(np.float32) * np.float32(0.2)
+    g = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        d = mv.write_five_state_model(os.path.join(MODELS, lang), os.path.join(tmp, "five"))
+        ref = Ref(d)
+        g["tp_sha"] = sha(ref.model_arrays()["tp"])
+        g["sseq_sha"] = sha(ref.model_arrays()["sseq"])
+        for name, f, win in (("win", feat, True), ("nowin", feat, False), ("noisy", noisy, True),
+                             ("short", feat[:120], False)):
+            wids = words[:, 0] if name != "short" else words[:3, 0]
+            st = words[:len(wids), 1] if win else None
+            du = words[:len(wids), 2] if win else None
+            a = ref.state_align(f, wids, st, du, clear_active=True, want_tokens=True)
+            g[name + "_rv"] = np.int32(a["rv"])
+            g[name + "_best"] = np.int32(a["best_score"])
+            g[name + "_states"] = a["states"]
+            g[name + "_phones"] = a["phones"]
+            g[name + "_tokens_sha"] = sha(a["tokens"])
+            print("five-state", lang, name, "rv", a["rv"], "best", a["best_score"], "states", len(a["states"]))
+        ref.close()
+    np.savez_compressed(os.path.join(OUT, "five_state_%s.npz" % lang), **g)
+
+
 def fsg_active_cases(lang, text, feat, jsgf):
     """(name, grammar selection, features) of the default-mode fixtures; the noisy case is
     regenerated from its seed by the tests."""
@@ -465,6 +498,8 @@ def main():
         return lexicon()
     if "--hmm5" in sys.argv:
         return hmm5()
+    if "--five-state" in sys.argv:
+        return five_state()
     if "--fsg-active" in sys.argv:
         fsg_active("en-us", "go forward ten meters", "goforward.gram")
         return fsg_active("fr-fr", "avance de dix mètres", "goforward_fr.gram")
@@ -476,6 +511,7 @@ def main():
     fsg_active("en-us", "go forward ten meters", "goforward.gram")
     fsg_active("fr-fr", "avance de dix mètres", "goforward_fr.gram")
     hmm5()
+    five_state()
     loaders()
     frontend()
     semi()
