@@ -253,7 +253,7 @@ fsg_run(const orc_model_t *m, const orc_fsg_t *g, const int16_t *senscr, int T, 
 {
     static const uint32_t all[4] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu };
     int i, t, E = m->n_emit;
-    if (E != 3)
+    if (E != 3 && E != 5)
         return -1;
     s->m = m;
     s->g = g;
@@ -307,7 +307,7 @@ fsg_run(const orc_model_t *m, const orc_fsg_t *g, const int16_t *senscr, int T, 
             for (i = s->n_act - 1; i >= 0; --i) {
                 int pn = s->act[i];
                 phmm_t *h = &s->h[pn];
-                int32_t sc = orc_hmm_eval(3, m->tp + (size_t)PN(g, pn, 1) * E * (E + 1),
+                int32_t sc = orc_hmm_eval(E, m->tp + (size_t)PN(g, pn, 1) * E * (E + 1),
                                           m->sseq + (size_t)PN(g, pn, 0) * E, ss, h->st);
                 h->bestscore = sc;
                 if (sc > best)

@@ -545,7 +545,7 @@ struct FsgActiveArgs {       // mode "compallsen = no"
     uchar4 *final_topn;      // [U][CS] or null: the carried top-N codewords after the search
 };
 
-template <bool ACTIVE, bool FIX>
+template <bool ACTIVE, bool FIX, bool FIVE>
 __global__ void __launch_bounds__(128)
 fsg_search_kernel(DevModel m, DevFsgSet gs, FsgActiveArgs aa, const int64_t *__restrict__ frame_off,
                   const int32_t *__restrict__ utt_graph, const int64_t *__restrict__ ws_off,
@@ -684,17 +684,22 @@ fsg_search_kernel(DevModel m, DevFsgSet gs, FsgActiveArgs aa, const int64_t *__r
             const int pn = s.act[i];
             int32_t *h = s.phmm + pn * PH;
             const uint16_t *sid = m.sseq + (size_t)s.pnode8[pn * 8 + 0] * E;
-            int32_t sc[3] = {h[0], h[1], h[2]}, hi[3] = {h[5], h[6], h[7]}, o_s = h[10], o_h = h[11];
-            const int sv[3] = {ACTIVE ? (int)(int16_t)(ss[sid[0]] - sbest) : (int)ss[sid[0]],
-                               ACTIVE ? (int)(int16_t)(ss[sid[1]] - sbest) : (int)ss[sid[1]],
-                               ACTIVE ? (int)(int16_t)(ss[sid[2]] - sbest) : (int)ss[sid[2]]};
-            const int32_t b = hmm_step3(m.tp + (size_t)s.pnode8[pn * 8 + 1] * 12, sv, sc, hi, o_s, o_h);
-            h[0] = sc[0];
-            h[1] = sc[1];
-            h[2] = sc[2];
-            h[5] = hi[0];
-            h[6] = hi[1];
-            h[7] = hi[2];
+            constexpr int EN = FIVE ? 5 : 3;  // emitting states (hmm_vit_eval_3st_lr / _5st_lr)
+            int32_t sc[EN], hi[EN], o_s = h[10], o_h = h[11];
+            int sv[EN];
+#pragma unroll
+            for (int j = 0; j < EN; ++j) {
+                sc[j] = h[j];
+                hi[j] = h[5 + j];
+                sv[j] = ACTIVE ? (int)(int16_t)(ss[sid[j]] - sbest) : (int)ss[sid[j]];
+            }
+            const int32_t b = hmm_step<EN>(m.tp + (size_t)s.pnode8[pn * 8 + 1] * EN * (EN + 1), sv, sc, hi,
+                                           o_s, o_h);
+#pragma unroll
+            for (int j = 0; j < EN; ++j) {
+                h[j] = sc[j];
+                h[5 + j] = hi[j];
+            }
             h[10] = o_s;
             h[11] = o_h;
             h[13] = b;
@@ -937,16 +942,21 @@ int launch_fsg_search(const DevModel &m, const DevFsgSet &gs, const int64_t *fra
 {
     if (n_utts <= 0)
         return 0;
-    if (m.n_emit != 3) {
-        set_error("FSG search supports 3-state HMMs, model has %d", m.n_emit);
+    if (m.n_emit != 3 && m.n_emit != 5) {
+        set_error("FSG search supports 3- and 5-state HMMs, model has %d", m.n_emit);
         return -1;
     }
     const int wpb = 4;
     FsgActiveArgs none;
     memset(&none, 0, sizeof none);
-    fsg_search_kernel<false, false><<<(n_utts + wpb - 1) / wpb, wpb * 32, 0, st>>>(
-        m, gs, none, frame_off, utt_graph, ws_off, ws, dense, g0, u0, n_utts, hist, hist_cap, tent_cap,
-        n_hist, n_eval, frames, rv);
+    if (m.n_emit == 3)
+        fsg_search_kernel<false, false, false><<<(n_utts + wpb - 1) / wpb, wpb * 32, 0, st>>>(
+            m, gs, none, frame_off, utt_graph, ws_off, ws, dense, g0, u0, n_utts, hist, hist_cap, tent_cap,
+            n_hist, n_eval, frames, rv);
+    else
+        fsg_search_kernel<false, false, true><<<(n_utts + wpb - 1) / wpb, wpb * 32, 0, st>>>(
+            m, gs, none, frame_off, utt_graph, ws_off, ws, dense, g0, u0, n_utts, hist, hist_cap, tent_cap,
+            n_hist, n_eval, frames, rv);
     SSB_CUDA(cudaGetLastError());
     note_launch();
     return 0;
@@ -970,8 +980,8 @@ int launch_fsg_search_active(const DevModel &m, const DevFsgSet &gs, const int64
 {
     if (n_utts <= 0)
         return 0;
-    if (m.n_emit != 3 || m.kind != SSB_SCORER_PTM || m.n_density > 128 || m.n_mgau > 128) {
-        set_error("FSG search with active lists needs a PTM model with 3-state HMMs, at most 128 "
+    if ((m.n_emit != 3 && m.n_emit != 5) || m.kind != SSB_SCORER_PTM || m.n_density > 128 || m.n_mgau > 128) {
+        set_error("FSG search with active lists needs a PTM model with 3- or 5-state HMMs, at most 128 "
                   "densities and 128 codebooks");
         return -1;
     }
@@ -988,14 +998,17 @@ int launch_fsg_search_active(const DevModel &m, const DevFsgSet &gs, const int64
     aa.n_sen_eval = n_sen_eval;
     aa.final_topn = final_topn;
     const int wpb = 4;
-    if (m.n_feat == 3 && m.topn == 4 && m.n_density == 128)
-        fsg_search_kernel<true, true><<<(n_utts + wpb - 1) / wpb, wpb * 32, 0, st>>>(
-            m, gs, aa, frame_off, utt_graph, ws_off, ws, nullptr, 0, 0, n_utts, hist, hist_cap, tent_cap,
-            n_hist, n_eval, frames, rv);
-    else
-        fsg_search_kernel<true, false><<<(n_utts + wpb - 1) / wpb, wpb * 32, 0, st>>>(
-            m, gs, aa, frame_off, utt_graph, ws_off, ws, nullptr, 0, 0, n_utts, hist, hist_cap, tent_cap,
-            n_hist, n_eval, frames, rv);
+#define SSB_K4(FX, FV)                                                                          \
+    fsg_search_kernel<true, FX, FV><<<(n_utts + wpb - 1) / wpb, wpb * 32, 0, st>>>(                 \
+        m, gs, aa, frame_off, utt_graph, ws_off, ws, nullptr, 0, 0, n_utts, hist, hist_cap, tent_cap, \
+        n_hist, n_eval, frames, rv)
+    const bool fix = m.n_feat == 3 && m.topn == 4 && m.n_density == 128;
+    if (m.n_emit == 3) {
+        if (fix) SSB_K4(true, false); else SSB_K4(false, false);
+    } else {
+        if (fix) SSB_K4(true, true); else SSB_K4(false, true);
+    }
+#undef SSB_K4
     SSB_CUDA(cudaGetLastError());
     note_launch();
     return 0;

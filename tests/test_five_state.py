@@ -67,6 +67,62 @@ def test_loader_and_oracle_on_five_state_model(five, golden):
         assert sha(r["tokens"]) == str(g[name + "_tokens_sha"]), name
 
 
+def _two_pass_inputs(golden):
+    feat = golden["en-us"]["feat"]
+    rs = np.random.RandomState(5)
+    noisy = feat + rs.randn(*feat.shape).astype(np.float32) * np.float32(0.2)
+    return [("fsg", feat), ("fsg_noisy", noisy)]
+
+
+def test_oracle_grammar_search_with_five_state_hmms(five, golden):
+    """fsg_search (default mode) + decoder_alignment on one decoder, 5-state HMMs throughout."""
+    from oracle.oracle import Oracle
+    d, g = five
+    m = ssb.AcousticModel(d, device=-1)
+    lx = ssb.Lexicon(m, hmmdir=d)
+    o = Oracle(d)
+    G = lx.align_graph("go forward ten meters")
+    for name, feat in _two_pass_inputs(golden):
+        p1 = o.fsg_search_active(G, feat)
+        assert p1["rv"] == 0 and np.array_equal(p1["hist"], g[name + "_hist"])
+        assert p1["hyp_score"] == int(g[name + "_hyp_score"]) and p1["n_sen_eval"] == int(g[name + "_n_sen_eval"])
+        assert p1["n_hmm_eval"] == int(g[name + "_n_hmm_eval"]) and np.array_equal(p1["active"], g[name + "_active"])
+        segs = g[name + "_segs"]
+        segs = segs[segs[:, 0] >= 0]
+        c = lx.populate(segs[:, 0], segs[:, 1], segs[:, 2] - segs[:, 1] + 1)
+        left = [int(w * 32 + b) for w, v in enumerate(p1["active"]) for b in range(32) if (int(v) >> b) & 1]
+        r = o.state_align(feat, c["ssid"], c["tmat"], c["sf"], c["ef"], init_active=left, init_topn=p1["carried"])
+        on = r["dur"] > 0
+        want = g[name + "_p2_states"]
+        assert r["rv"] == int(g[name + "_p2_rv"]) == 0
+        assert np.array_equal(np.stack([r["start"], r["dur"], r["score"]], 1)[on], want[on, 1:4])
+
+
+@pytest.mark.gpu
+def test_two_passes_with_five_state_hmms(five, golden):
+    """K4 (active lists, hmm_step5) -> words -> chain_viterbi_kernel<5>, through ssb_fsg_batch /
+    ssb_align_batch and through ssb_align_texts."""
+    d, g = five
+    m = ssb.AcousticModel(d)
+    lx = ssb.Lexicon(m, hmmdir=d)
+    text = "go forward ten meters"
+    G = lx.align_graph(text)
+    inputs = _two_pass_inputs(golden)
+    p1 = ssb.fsg_batch(m, [f for _n, f in inputs], [G], want_hist=True, compallsen=False)
+    ta = ssb.TextAlignment(m, lx, [f for _n, f in inputs], [text] * len(inputs), align_level=2)
+    for u, ((name, feat), r) in enumerate(zip(inputs, p1)):
+        assert r["rv"] == 0 and np.array_equal(r["hist"], g[name + "_hist"]), name
+        assert r["hyp_score"] == int(g[name + "_hyp_score"]) and r["n_sen_eval"] == int(g[name + "_n_sen_eval"])
+        assert r["n_hmm_eval"] == int(g[name + "_n_hmm_eval"]) and np.array_equal(r["active"], g[name + "_active"])
+        assert np.array_equal(r["segs"][:, 1:], g[name + "_segs"][:, 1:])
+        # dense mode searches the same graph with hmm_step5 too
+        assert ssb.fsg_batch(m, [feat], [G])[0]["exit"] > 0
+        want = g[name + "_p2_states"]
+        st = ta.entries(u, "states")
+        assert ta.status(u)[0] == 0 and ta.status(u)[1] == int(g[name + "_hyp_score"])
+        assert np.array_equal(st, want), name     # skipped states keep alignment_populate's values
+
+
 @pytest.mark.gpu
 def test_chain_viterbi_with_five_state_hmms(five, golden):
     """chain_viterbi_kernel<5> + backtrace: state segmentations and the whole token stack."""
@@ -86,5 +142,3 @@ def test_chain_viterbi_with_five_state_hmms(five, golden):
                                golden["en-us"]["words"][:, 2])
     a.start(); a.forward(golden["en-us"]["feat"]); assert a.finish() == 0
     assert np.array_equal(a.alignment("states")[:, :4], g["win_states"][:, :4])   # populate's values kept
-    with pytest.raises(ssb.SsbError, match="3-state"):
-        ssb.fsg_batch(m, [golden["en-us"]["feat"][:20]], [lx.align_graph("go forward")])

@@ -253,6 +253,26 @@ def five_state(lang="en-us"):
             g[name + "_tokens_sha"] = sha(a["tokens"])
             print("five-state", lang, name, "rv", a["rv"], "best", a["best_score"], "states", len(a["states"]))
         ref.close()
+        # both passes in the reference's default mode on one decoder (grammar search with
+        # 5-state HMMs, then decoder_alignment from what it left in acmod and the scorer)
+        text = "go forward ten meters"
+        for name, f in (("fsg", feat), ("fsg_noisy", noisy)):
+            ref = Ref(d, compallsen=False)
+            dd = ref.fsg_decode(f, align_text=text)
+            H = ref.fsg_history()
+            bits, n_sen_eval = ref.active_bits()
+            g[name + "_hist"] = H["hist"]
+            g[name + "_segs"] = dd["segs"]
+            g[name + "_hyp_score"] = np.int32(dd["hyp_score"])
+            g[name + "_n_hmm_eval"] = np.int64(H["n_hmm_eval"])
+            g[name + "_n_sen_eval"] = np.int64(n_sen_eval)
+            g[name + "_active"] = bits
+            segs = dd["segs"][dd["segs"][:, 0] >= 0]
+            a = ref.state_align(f, segs[:, 0], segs[:, 1], segs[:, 2] - segs[:, 1] + 1, clear_active=False)
+            g[name + "_p2_rv"] = np.int32(a["rv"])
+            g[name + "_p2_states"] = a["states"]
+            print("five-state", lang, name, "hist", len(H["hist"]), "hyp", dd["hyp_score"], "p2 rv", a["rv"])
+            ref.close()
     np.savez_compressed(os.path.join(OUT, "five_state_%s.npz" % lang), **g)
 
 
