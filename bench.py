@@ -526,6 +526,23 @@ def main():
                      "mma_tflops_executed": stats["scanned_cb_frames"] * model.n_feat * 3 * 2 * 128 * 32
                                             / (k1_ms * 1e-3) / 1e12,
                      "scalar_equiv_fp32_frac": fp32_ops / (k1_ms * 1e-3) / fp32_peak},
+        "roofline_other": [
+            {"kernel": "chain_viterbi_kernel (K3)", "bound": "hbm", "unit": "GB/s",
+             "achieved": stats["state_frames"] * 10 / (kms["chain_viterbi"] / args.steps * 1e-3) / 1e9,
+             "peak": float(peaks.get("hbm_gbs", 6650.0)),
+             "frac": stats["state_frames"] * 10 / (kms["chain_viterbi"] / args.steps * 1e-3) / 1e9
+                     / float(peaks.get("hbm_gbs", 6650.0)),
+             "note": "ALGORITHMIC bytes: SURVEY 8d's 10 B per state-frame (2 B score in + 8 B token out) x "
+                     "T x chain states; the kernel only writes the evaluated band's tokens (ncu: 1.2 GB of "
+                     "DRAM traffic per launch, profiles/prof_chain_viterbi_r1j.txt) and is issue-bound"},
+            {"kernel": "senone_mix_active_kernel (K2)", "bound": "hbm", "unit": "GB/s",
+             "achieved": (stats["scanned_cb_frames"] * model.n_feat * 20 + stats["state_frames"] * 2)
+                         / (kms["senone_mix"] / args.steps * 1e-3) / 1e9,
+             "peak": float(peaks.get("hbm_gbs", 6650.0)),
+             "frac": (stats["scanned_cb_frames"] * model.n_feat * 20 + stats["state_frames"] * 2)
+                     / (kms["senone_mix"] / args.steps * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6650.0)),
+             "note": "algorithmic bytes: 20 B of top-N list per scanned codebook-stream-frame in + 2 B per "
+                     "state-frame out (ncu: 5.0 + 1.3 GB per launch); integer mixing, issue-bound"}],
         "senone_scores_per_s": stats["active_senone_frames"] / ((kms["gmm_topn"] + kms["senone_mix"]) / args.steps * 1e-3),
         "dp_state_frames_per_s": stats["state_frames"] / (kms["chain_viterbi"] / args.steps * 1e-3),
         "dp_hbm_frac_10B": stats["state_frames"] * 10 / (kms["chain_viterbi"] / args.steps * 1e-3) / 1e9
