@@ -310,6 +310,63 @@ static int model_to_device(ssb_model_s *m)
         if (!(d.gB = to_device(m, gB)) || !(d.gBlo = to_device(m, gBlo))
             || !(d.gAux = to_device(m, gAux)) || !(d.gHot = to_device(m, m->tc_hot)))
             return -1;
+        // ---- frame-tiled kernel (gmm_scan_ft.cu): the same split operands around ONE centre per
+        // stream (the mean of all the stream's means), stored in shared-memory swizzle order
+        if (h.n_feat <= SSB_MAX_FEAT) {
+            std::vector<float> gBft((size_t)CS * 2 * ND * K, 0.f), gAuxFt((size_t)CS * 64, 0.f);
+            for (int f = 0; f < h.n_feat; ++f)
+                for (int j = 0; j < L; ++j) {
+                    double c = 0;
+                    for (int cb = 0; cb < h.n_mgau; ++cb) {
+                        const float *mu = h.mean.data() + h.gau_off[cb * h.n_feat + f];
+                        for (int n = 0; n < ND; ++n)
+                            c += mu[n * L + j];
+                    }
+                    d.ft_centre[f * 16 + j] = (float)(c / ((double)ND * h.n_mgau));
+                }
+            auto swz = [](int n, int k) {  // float index of element (row n, k) in a SWIZZLE_128B tile
+                return ((n >> 3) * 64 + (n & 7) * 8 + ((k >> 2) ^ (n & 7))) * 4 + (k & 3);
+            };
+            for (int cs = 0; cs < CS; ++cs) {
+                const int f = cs % h.n_feat;
+                const float *mu = h.mean.data() + h.gau_off[cs];
+                const float *pv = h.var.data() + h.gau_off[cs];
+                const float *dt = h.det.data() + (size_t)cs * ND;
+                const uint32_t *hot = m->tc_hot.data() + (size_t)cs * 4;
+                float *Bh = gBft.data() + (size_t)cs * 2 * ND * K, *Bl = Bh + ND * K;
+                float *aux = gAuxFt.data() + (size_t)cs * 64;
+                bool any_hot = false;
+                for (int n = 0; n < ND; ++n) {
+                    const bool is_hot = (hot[n >> 5] >> (n & 31)) & 1u;
+                    any_hot = any_hot || is_hot;
+                    double cst = dt[n];
+                    for (int j = 0; j < L; ++j) {
+                        const double mc = (double)mu[n * L + j] - (double)d.ft_centre[f * 16 + j];
+                        const double v = pv[n * L + j];
+                        const float b1 = tf32(2.0 * mc * v), b2 = tf32(-v);
+                        Bh[swz(n, j)] = b1;
+                        Bh[swz(n, L + j)] = b2;
+                        Bl[swz(n, j)] = tf32(2.0 * mc * v - (double)b1);
+                        Bl[swz(n, L + j)] = tf32(-v - (double)b2);
+                        cst -= mc * mc * v;
+                        const int o = is_hot ? 32 : 0;
+                        aux[o + j] = std::max(aux[o + j], std::fabs(b1));
+                        aux[o + 16 + j] = std::max(aux[o + 16 + j], std::fabs(b2));
+                    }
+                    const float hi = tf32(cst);
+                    Bh[swz(n, 26)] = hi;
+                    Bh[swz(n, 27)] = tf32(cst - (double)hi);
+                    const int o = is_hot ? 14 : 13;
+                    aux[o] = std::max(aux[o], (float)std::fabs(cst));
+                }
+                aux[15] = any_hot ? 1.f : 0.f;
+                aux[29] = aux[13];
+                aux[30] = aux[14];
+                aux[31] = aux[15];
+            }
+            if (!(d.gBft = to_device(m, gBft)) || !(d.gAuxFt = to_device(m, gAuxFt)))
+                return -1;
+        }
     }
     std::vector<uint8_t> lut(h.lut8, h.lut8 + 256);
     if (!(d.gau = to_device(m, gau)) || !(d.mixw = to_device(m, h.mixw))
@@ -659,6 +716,10 @@ struct ssb_batch_s {
     DBuf d_k1_frame_off, d_k1_ep_off, d_k1_ep_start, d_k1_ep_cbmask, d_seg_utts, d_k1_tie, d_init_topn;
     int n_seg_utts = 0, n_k1_rows = 0;
     int64_t k1_tie_w = 0;
+    // K1 frame-tiled (gmm_scan_ft.cu): tiles of 128 frames; every tie step goes to the fix-up
+    bool ft = false;
+    int n_tiles = 0;
+    DBuf d_tile_utt, d_tile_t0, d_tile_ctr;
     // timing
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int n_launches = 0;
@@ -671,7 +732,8 @@ struct ssb_batch_s {
                              &d_usen, &d_st_slot, &d_enter, &st_start, &st_dur, &st_score, &utt_rv,
                              &utt_best, &utt_renorm, &fin_hist, &fin_score, &dense, &best_tmp,
                              &d_k1_frame_off, &d_k1_ep_off, &d_k1_ep_start, &d_k1_ep_cbmask,
-                             &d_seg_utts, &d_k1_tie, &d_init_topn};
+                             &d_seg_utts, &d_k1_tie, &d_init_topn, &d_tile_utt, &d_tile_t0,
+                             &d_tile_ctr};
         size_t n = 0;
         for (const DBuf *b : all)
             n += b->cap;
@@ -685,7 +747,7 @@ struct ssb_batch_s {
                        &d_st_slot, &d_enter, &st_start, &st_dur, &st_score, &utt_rv, &utt_best,
                        &utt_renorm, &fin_hist, &fin_score, &dense, &best_tmp, &d_k1_frame_off,
                        &d_k1_ep_off, &d_k1_ep_start, &d_k1_ep_cbmask, &d_seg_utts, &d_k1_tie,
-                       &d_init_topn};
+                       &d_init_topn, &d_tile_utt, &d_tile_t0, &d_tile_ctr};
         for (DBuf *b : all)
             b->release();
     }
@@ -764,6 +826,16 @@ extern "C" int ssb_plan_chain(int32_t np, int32_t T, const int32_t *sf, const in
         }
     plan_enter(np, T, sf, ef, enter);
     return 0;
+}
+
+// K1 kernel choice: the frame-tiled tcgen05 kernel (gmm_scan_ft.cu) unless $SSB_K1 names another
+// one (tc2 / tc1 / fp32: earlier kernels, kept for A/B runs)
+static bool k1_frame_tiled(const DevModel &d)
+{
+    const char *k1 = getenv("SSB_K1");
+    if (k1 && *k1)
+        return strcmp(k1, "ft") == 0 && ft_supported(d);
+    return false;  // TODO default once the parity suite is green
 }
 
 // ---- host planner --------------------------------------------------------------------------
@@ -1130,11 +1202,37 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
     // afterwards (topn_fixup.cu).  $SSB_K1_SEG forces a segment length (tests).
     b->k1_seg = false;
     b->n_seg_utts = 0;
-    {
+    b->ft = false;
+    b->n_tiles = 0;
+    if (k1_frame_tiled(b->m->d) && U > 0 && G > 0) {
+        // frame-tiled K1: every utterance is cut into tiles of 128 frames that are scored
+        // independently; all utterances are candidates for the tie fix-up
+        std::vector<int32_t> tu, tt, all_utts(U);
+        for (int u = 0; u < U; ++u) {
+            all_utts[u] = u;
+            const int T = (int)(b->frame_off[u + 1] - b->frame_off[u]);
+            for (int t0 = 0; t0 < T; t0 += 128) {
+                tu.push_back(u);
+                tt.push_back(t0);
+            }
+        }
+        b->n_tiles = (int)tu.size();
+        b->k1_tie_w = (G + 31) / 32 + 1;
+        if (b->n_tiles > 0) {
+            if (upload(b->d_tile_utt, tu, st) || upload(b->d_tile_t0, tt, st)
+                || upload(b->d_seg_utts, all_utts, st) || b->d_tile_ctr.ensure(16) != 0
+                || b->d_k1_tie.ensure((size_t)CS * b->k1_tie_w * 4 + 16) != 0)
+                return -1;
+            API_CUDA(cudaStreamSynchronize(st), -1);
+            b->ft = true;
+            b->n_seg_utts = U;
+        }
+    }
+    if (!b->ft) {
         const char *force = getenv("SSB_K1_SEG");
         const char *k1 = getenv("SSB_K1");
         int64_t seg = 0;
-        if (tc_supported(b->m->d) && !(k1 && *k1) && h.cfg.ds <= 1 && U > 0 && G > 0) {
+        if (tc_supported(b->m->d) && (!(k1 && *k1) || strcmp(k1, "tc2") == 0) && h.cfg.ds <= 1 && U > 0 && G > 0) {
             if (force && atoll(force) > 0)
                 seg = atoll(force);
             else if (U <= 512 && b->max_T >= 8192)
@@ -1206,7 +1304,8 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
 // the tie flags; when the batch's long utterances were cut into segments the flagged steps are
 // replayed afterwards unless the caller does that itself (`fixup` = false: the grammar search in
 // its default mode never reads them).
-static int batch_topn(ssb_batch_t *b, uint32_t *tie, int64_t tie_w, bool fixup)
+static int batch_topn(ssb_batch_t *b, uint32_t *tie, int64_t tie_w, bool fixup, int exact = 0,
+                      TcDebug dbg = TcDebug{nullptr, nullptr, nullptr})
 {
     const DevModel &d = b->m->d;
     cudaStream_t st = b->st;
@@ -1214,7 +1313,7 @@ static int batch_topn(ssb_batch_t *b, uint32_t *tie, int64_t tie_w, bool fixup)
     if (b->n_utts == 0 || G == 0)
         return 0;
     DevPlan p = b->k1_seg ? b->k1_plan : b->plan;
-    if (b->k1_seg && !tie) {
+    if ((b->k1_seg || b->ft) && !tie) {
         tie = b->d_k1_tie.as<uint32_t>();
         tie_w = b->k1_tie_w;
         if (cudaMemsetAsync(tie, 0, (size_t)d.n_mgau * d.n_feat * tie_w * 4, st) != cudaSuccess) {
@@ -1224,10 +1323,15 @@ static int batch_topn(ssb_batch_t *b, uint32_t *tie, int64_t tie_w, bool fixup)
     }
     p.tie_bits = tie;
     p.tie_w = tie_w;
-    if (launch_gmm_topn(d, p, b->feat.as<float>(), G, b->tn_s.as<int4>(), b->tn_c.as<uchar4>(),
-                        b->featp.as<float>(), st) != 0)
+    if (b->ft) {
+        if (launch_gmm_scan_ft(d, p, b->feat.as<float>(), G, b->tn_s.as<int4>(), b->tn_c.as<uchar4>(),
+                               b->d_tile_utt.as<int32_t>(), b->d_tile_t0.as<int32_t>(), b->n_tiles,
+                               b->d_tile_ctr.as<int>(), exact, dbg, st) != 0)
+            return -1;
+    } else if (launch_gmm_topn(d, p, b->feat.as<float>(), G, b->tn_s.as<int4>(), b->tn_c.as<uchar4>(),
+                               b->featp.as<float>(), st) != 0)
         return -1;
-    if (b->k1_seg && fixup)
+    if ((b->k1_seg || b->ft) && fixup)
         return launch_topn_fixup(d, b->plan, b->d_seg_utts.as<int32_t>(), b->n_seg_utts,
                                  b->feat.as<float>(), G, b->tn_s.as<int4>(), b->tn_c.as<uchar4>(),
                                  tie, tie_w, st);
@@ -1868,7 +1972,19 @@ static int64_t topn_impl(ssb_model_t *m, const float *feat, const int64_t *frame
             break;
         }
         if (!probe) {
-            if (batch_topn(b, nullptr, 0, true) != 0)
+            // exact raw scores (the frame-tiled kernel's production output is scores >> 10 only)
+            if (batch_topn(b, nullptr, 0, true, 1) != 0)
+                break;
+        } else if (b->ft) {
+            if (d_approx.ensure((size_t)G * CS * ND * 4) || d_eps.ensure((size_t)G * CS * 8)
+                || d_cnt.ensure(32))
+                break;
+            cudaMemsetAsync(d_cnt.p, 0, 32, b->st);
+            cudaMemsetAsync(d_eps.p, 0, (size_t)G * CS * 8, b->st);
+            const char *ex = getenv("SSB_FT_EXACT");
+            if (batch_topn(b, nullptr, 0, true, !(ex && *ex == '0'),
+                           TcDebug{d_approx.as<float>(), d_eps.as<float>(),
+                                   d_cnt.as<unsigned long long>()}) != 0)
                 break;
         } else {
             if (!tc_supported(d)) {
@@ -2064,7 +2180,8 @@ static const int64_t kFsgSlabFrames = 1200000;
 
 extern "C" int ssb_model_fsg_active_ok(const ssb_model_t *m)
 {
-    return m && m->device >= 0 && tc_supported(m->d) && !(getenv("SSB_K1") && *getenv("SSB_K1"));
+    const char *k1 = getenv("SSB_K1");  // the earlier A/B kernels do not flag tie steps
+    return m && m->device >= 0 && tc_supported(m->d) && (!(k1 && *k1) || strcmp(k1, "ft") == 0 || strcmp(k1, "tc2") == 0);
 }
 
 extern "C" int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out_t *out)

@@ -59,6 +59,17 @@ struct DevModel {
     const float *gBlo;
     const float *gAux;
     const uint32_t *gHot;
+    // frame-tiled kernel (gmm_scan_ft.cu): ONE centre per stream, so that the A tile of a frame
+    // serves every codebook
+    //   gBft   [cs][2][128][32]  B_hi then B_lo, already in the SWIZZLE_128B shared-memory order
+    //                            (one 32 KB cp.async.bulk per codebook-stream)
+    //   gAuxFt [cs][64]  [0..12] max|2 mu' v|, [16..28] max v over the regular densities;
+    //                    [32..44], [48..60] the same over the hot ones; [13]/[29] max|c| regular,
+    //                    [14]/[30] max|c| hot, [15]/[31] 1.0 if the codebook-stream has hot densities
+    //   ft_centre [feat][16]
+    const float *gBft;
+    const float *gAuxFt;
+    float ft_centre[SSB_MAX_FEAT * 16];
     // scorer family (ssb200.h SSB_SCORER_*): PTM, or the single-codebook semi-continuous one
     // (ref: src/s2_semi_mgau.c) with its per-stream top-N beam
     int32_t kind;
@@ -114,6 +125,17 @@ bool tc_supported(const DevModel &m);
 int launch_gmm_topn_tc(const DevModel &m, const DevPlan &p, const float *feat, int64_t n_frames,
                        int4 *tn_score, uchar4 *tn_cw, float *featp, float *dbg_approx,
                        float *dbg_eps, unsigned long long *dbg_counters, cudaStream_t st);
+// K1, frame-tiled (gmm_scan_ft.cu): tiles of 128 consecutive frames (tile_utt, tile_t0), tie steps
+// flagged in p.tie_bits; scores are stored as (score >> 10) << 10 unless `exact`
+struct TcDebug {
+    float *approx;     // [cs][frame][128] or null
+    float *eps;        // [cs][frame][2]
+    unsigned long long *counters;  // [0] exact evaluations of scan survivors [1] scanned (lane, frame) steps [2] slow-path steps
+};
+bool ft_supported(const DevModel &m);
+int launch_gmm_scan_ft(const DevModel &m, const DevPlan &p, const float *feat, int64_t n_frames,
+                       int4 *tn_score, uchar4 *tn_cw, const int32_t *tile_utt, const int32_t *tile_t0,
+                       int n_tiles, int *tile_counter, int exact, TcDebug dbg, cudaStream_t st);
 // K2 (active lists): normalise, mix, subtract best, gather to chain states.
 // max_union counts the always-zero slot that inactive chain states read.
 int launch_senone_mix_active(const DevModel &m, const DevPlan &p, const int4 *tn_score,

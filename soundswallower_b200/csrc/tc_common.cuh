@@ -35,6 +35,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     // try_wait suspends the thread for a hardware time slice; the iteration cap turns a lost
     // completion (a malformed descriptor, say) into a trap instead of a hung GPU
     const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 22); ++it) {
         uint32_t ok;
         asm volatile(
@@ -190,12 +191,6 @@ struct TcTopN {
             h |= (c[k] == cw);
         return h;
     }
-};
-
-struct TcDebug {
-    float *approx;     // [cs][frame][128] or null
-    float *eps;        // [cs][frame]
-    unsigned long long *counters;  // [0] exact evaluations of scan survivors [1] scanned (lane, frame) steps [2] slow-path steps
 };
 
 // v2 kernel (gmm_topn_tc2.cu); featp = scratch for the re-packed features
