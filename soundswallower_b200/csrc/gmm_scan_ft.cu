@@ -1,68 +1,54 @@
-// gmm_scan_ft.cu -- K1 "frame-tiled": Gaussian top-N of a tile of 128 consecutive frames
-// against every active codebook, one CTA per tile (persistent, tiles handed out by an atomic
-// counter).  Same results as the reference's eval_topn + eval_cb (ref: src/ptm_mgau.c:63-253)
-// wherever integer scores do not tie; tie steps are flagged (DevPlan.tie_bits) for the
-// literal replay (topn_fixup.cu / the grammar search's own replay).
+// gmm_scan_ft.cu -- K1 "frame-tiled": Gaussian top-N of tiles of 128 consecutive frames against
+// every active codebook (persistent CTAs, tile pairs handed out by an atomic counter).  Same
+// results as the reference's eval_topn + eval_cb (ref: src/ptm_mgau.c:63-253) wherever integer
+// scores do not tie; tie steps are flagged (DevPlan.tie_bits) for the literal replay
+// (topn_fixup.cu / the grammar search's own replay).
 //
 // Against gmm_topn_tc2.cu (CTA = codebook-stream x 256 utterances, thread = utterance):
 //   * the MMA's M rows are FRAMES, so the A tile [x', x'^2, 1] (3xTF32 hi / lo split, centred on
-//     one global centre per stream) is built ONCE per tile and shared by all codebooks; it
-//     lives in TENSOR MEMORY (tcgen05.st, A-from-TMEM MMA), not in shared memory;
-//   * B_hi / B_lo of a codebook-stream (32 KB, pre-swizzled in HBM, L2 resident) stream
-//     through a two-slot shared-memory ring filled by cp.async.bulk + mbarrier (TMA warp),
-//     consumed by a single MMA-issuing thread; two accumulators in TMEM let the tensor core
-//     run one codebook ahead of the epilogue;
-//   * the epilogue is warp-specialised: 8 warps, two threads per frame row (64 of the 128
-//     densities each).  One TMEM read-out; group maxima -> N-th largest -> survivor mask
-//     (one FADD + one funnel shift per density); the survivors' screening scores are parked
-//     in a shared-memory stash and picked up by index;
+//     one global centre per stream) is built once per (tile, stream) and shared by all
+//     codebooks; it lives in TENSOR MEMORY (tcgen05.st, A-from-TMEM MMA), not in shared memory;
+//   * a CTA works on TWO tiles (row groups) at a time: B_hi / B_lo of a codebook-stream (32 KB,
+//     pre-swizzled in HBM, L2 resident) travel once per 256 frames through a two-slot
+//     shared-memory ring filled by cp.async.bulk + mbarrier (TMA warp) and are consumed by a
+//     single MMA-issuing thread, one accumulator per row group in TMEM;
+//   * the epilogue is warp-specialised and free of block barriers: 8 warps, thread = frame row,
+//     all 128 densities in registers.  One TMEM read-out; group maxima -> N-th largest ->
+//     survivor mask (one FADD + one funnel shift per density); the row's screening scores are
+//     parked in a private shared-memory stash and the survivors picked up by index, packed with
+//     their index into one sortable 32-bit key, branch-free insertion;
 //   * NO exact evaluation on the common path: if the N+1 best screening scores are separated
 //     by more than the rigorous error bound and none lies within the bound of a 1024-raw-unit
 //     boundary, the list (codewords in order + scores >> 10, which is all that the mixing stage
 //     consumes: ref src/ptm_mgau.c:276-285) is decided.  Otherwise (~13 % of the steps) the row
-//     files the step in a shared-memory queue; the queue is drained by all threads together
-//     (no divergence) with exact evaluations in the reference's operation order.
+//     files the step in its own small queue; a warp works its lanes' queues off together
+//     (exact evaluations in the reference's operation order) when enough lanes have one.
 #include "tc_common.cuh"
 
 namespace ssb {
 
 constexpr int FT_ROWS = 128;
-constexpr int FT_EPI_THREADS = 256;
-constexpr int FT_THREADS = 320;  // 8 epilogue warps + TMA warp + MMA warp
+constexpr int FT_RG = 2;                // row groups (tiles) per CTA
+constexpr int FT_EPI_THREADS = FT_RG * FT_ROWS;
+constexpr int FT_THREADS = FT_EPI_THREADS + 64;  // + TMA warp + MMA warp
 constexpr int FT_NSLOT = 2;
 constexpr int FT_BTILE = TC_ND * TC_K;  // floats of one operand tile (16 KB)
 constexpr int FT_STASH_LD = 132;        // floats per stash row (bank-conflict-free float4 stores)
-constexpr int FT_QCAP = 512;
-constexpr int FT_QWORDS = 5;            // header + 128-bit survivor mask
-constexpr int FT_QDRAIN = 160;          // drain the queue when it holds this many items
-constexpr int FT_MAXCB = 64;            // codebooks a tile can list
+constexpr int FT_MAXCB = 64;            // codebooks a model can have here
 constexpr uint32_t FT_A_COL = 256;      // TMEM columns: accumulators [0,256), A tiles from 256
 
 struct FtSmem {
     float B[FT_NSLOT][2 * FT_BTILE];          // B_hi | B_lo per slot (SWIZZLE_128B, as stored in HBM)
-    float stash[FT_ROWS * FT_STASH_LD];
-    float4 xg[FT_ROWS][2];                    // pair exchange: sorted group maxima
-    float2 xe[FT_ROWS][2];                    //                error-bound partial sums
-    unsigned long long xm[FT_ROWS][2];        //                survivor masks
-    uint32_t q[FT_QCAP][FT_QWORDS];
-    uint64_t b_full[FT_NSLOT], b_empty[FT_NSLOT], acc_full[2], acc_empty[2], a_ready;
+    float stash[FT_EPI_THREADS * FT_STASH_LD];
+    uint64_t b_full[FT_NSLOT], b_empty[FT_NSLOT], acc_full[FT_RG], acc_empty[FT_RG], a_ready[FT_RG];
     uint32_t tmem_base;
-    int q_count;
-    int next_tile;
+    int next_pair;
     int n_cb;
+    uint32_t um[FT_RG][2];                    // codebooks each row group needs (n_mgau <= 64)
     uint8_t cb_list[FT_MAXCB];
-    int16_t cb_r0[FT_MAXCB];
 };
 
 // ---- PTX -----------------------------------------------------------------------------------
-__device__ __forceinline__ void ft_bar_pair(int wq)
-{
-    asm volatile("bar.sync %0, 64;" ::"r"(wq + 1) : "memory");
-}
-__device__ __forceinline__ void ft_bar_epi()
-{
-    asm volatile("bar.sync 5, 256;" ::: "memory");
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -112,6 +98,30 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32])
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 32 accumulator columns of this thread's row, no wait: the values may only be used after
+// FT_TMEM_WAIT32 on the same array (which names the registers, so that nothing is scheduled
+// across it); a second load can be in flight while the first one's values are processed
+#define FT_TMEM_LD32_NOWAIT(taddr, v)                                                                        \
+    asm volatile(                                                                                            \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                            \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                            \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"            \
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),    \
+          "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]),           \
+          "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]),         \
+          "=f"(v[22]), "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]),         \
+          "=f"(v[29]), "=f"(v[30]), "=f"(v[31])                                                              \
+        : "r"(taddr)                                                                                         \
+        : "memory")
+#define FT_TMEM_WAIT32(v)                                                                                    \
+    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                            \
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]),       \
+                   "+f"(v[7]), "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]),   \
+                   "+f"(v[14]), "+f"(v[15]), "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]),             \
+                   "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]),             \
+                   "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])              \
+                 :                                                                                           \
+                 : "memory")
 
 __device__ __forceinline__ float ft_max3(float a, float b, float c)
 {
@@ -119,14 +129,14 @@ __device__ __forceinline__ float ft_max3(float a, float b, float c)
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
 }
-__device__ __forceinline__ float ft_max16(const float (&v)[64], int o)
+__device__ __forceinline__ float ft_max16(const float (&v)[32], int o)
 {
     const float m0 = ft_max3(v[o], v[o + 1], v[o + 2]), m1 = ft_max3(v[o + 3], v[o + 4], v[o + 5]);
     const float m2 = ft_max3(v[o + 6], v[o + 7], v[o + 8]), m3 = ft_max3(v[o + 9], v[o + 10], v[o + 11]);
     const float m4 = ft_max3(v[o + 12], v[o + 13], v[o + 14]);
     return fmaxf(ft_max3(m0, m1, m2), ft_max3(m3, m4, v[o + 15]));
 }
-__device__ __forceinline__ float ft_max16_ex(const float (&v)[64], int o, uint32_t exclude)
+__device__ __forceinline__ float ft_max16_ex(const float (&v)[32], int o, uint32_t exclude)
 {
     float w[16];
 #pragma unroll
@@ -142,14 +152,29 @@ __device__ __forceinline__ float ft_max16_ex(const float (&v)[64], int o, uint32
         b = fminf(a, b);         \
         a = hi_;                 \
     }
-// bit i of the result: v[o + i] >= thr  (sign bit of v - thr, collected by funnel shifts)
-__device__ __forceinline__ uint32_t ft_mask32(const float (&v)[64], int o, float thr)
+// k-th largest (k = 1..4) of 8 values: 19-comparator sorting network, descending
+__device__ __forceinline__ float ft_kth_largest8(float (&g)[8], int k)
 {
-    uint32_t below = 0u;
+    FT_CE(g[0], g[1]) FT_CE(g[2], g[3]) FT_CE(g[4], g[5]) FT_CE(g[6], g[7])
+    FT_CE(g[0], g[2]) FT_CE(g[1], g[3]) FT_CE(g[4], g[6]) FT_CE(g[5], g[7])
+    FT_CE(g[1], g[2]) FT_CE(g[5], g[6]) FT_CE(g[0], g[4]) FT_CE(g[3], g[7])
+    FT_CE(g[1], g[5]) FT_CE(g[2], g[6])
+    FT_CE(g[1], g[4]) FT_CE(g[3], g[6])
+    FT_CE(g[2], g[4]) FT_CE(g[3], g[5])
+    FT_CE(g[3], g[4])
+    return k == 1 ? g[0] : (k == 2 ? g[1] : (k == 3 ? g[2] : g[3]));
+}
+// bit i of the result: v[i] >= thr  (sign bit of v - thr, collected by funnel shifts; two
+// independent chains)
+__device__ __forceinline__ uint32_t ft_mask32(const float (&v)[32], float thr)
+{
+    uint32_t lo = 0u, hi = 0u;
 #pragma unroll
-    for (int i = 31; i >= 0; --i)
-        below = __funnelshift_l(__float_as_uint(__fsub_rn(v[o + i], thr)), below, 1);
-    return ~below;
+    for (int i = 15; i >= 0; --i) {
+        lo = __funnelshift_l(__float_as_uint(__fsub_rn(v[i], thr)), lo, 1);
+        hi = __funnelshift_l(__float_as_uint(__fsub_rn(v[16 + i], thr)), hi, 1);
+    }
+    return ~(lo | (hi << 16));
 }
 
 struct FtArgs {
@@ -159,7 +184,7 @@ struct FtArgs {
     uchar4 *out_c;
     const int32_t *tile_utt, *tile_t0;
     int n_tiles;
-    int *tile_counter;  // zeroed before the launch; tile = gridDim.x + ticket
+    int *tile_counter;  // zeroed before the launch; pair = gridDim.x + ticket
     int exact;          // every step through the exact path: raw scores out (ssb_topn_batch)
     TcDebug dbg;
 };
@@ -188,19 +213,16 @@ __device__ __forceinline__ void ft_store(const FtArgs &a, int cs, int64_t g, con
     a.out_c[(int64_t)cs * a.G + g] = cv;
 }
 
-// One queued step: exact evaluation (the reference's fp32 operation order, no contraction) of
+// One deferred step: exact evaluation (the reference's fp32 operation order, no contraction) of
 // the survivors named by the mask; the N+1 best decide.  Ties -> flagged, list as found.
+// Called with the warp converged; lanes without work pass have = false.
 template <int N, bool DEBUG>
-__device__ __noinline__ void ft_exact_item(const DevModel &m, const DevPlan &p, const FtArgs &a, int cs,
-                                           int64_t g, uint32_t k0, uint32_t k1, uint32_t k2, uint32_t k3)
+__device__ __forceinline__ void ft_exact_step(const DevModel &m, const DevPlan &p, const FtArgs &a, bool have,
+                                              int cs, int64_t g, const float (&x)[TC_L], uint32_t k0,
+                                              uint32_t k1, uint32_t k2, uint32_t k3)
 {
     const int cb = cs / m.n_feat, f = cs - cb * m.n_feat;
     const float *rec = m.gau + gau_offset(m, cb, f);
-    const float *xp = a.feat + g * m.blk + m.featoff[f];
-    float x[TC_L];
-#pragma unroll
-    for (int j = 0; j < TC_L; ++j)
-        x[j] = __ldg(xp + j);
     TcTopN<N + 1> best;
 #pragma unroll
     for (int k = 0; k <= N; ++k) {
@@ -208,19 +230,24 @@ __device__ __noinline__ void ft_exact_item(const DevModel &m, const DevPlan &p, 
         best.c[k] = -1;
     }
     int cnt = 0;
-    uint32_t w[4] = {k0, k1, k2, k3};
-#pragma unroll 1
-    for (int q = 0; q < 4; ++q) {
-        uint32_t bits = w[q];
-        while (bits) {
-            const int cw = q * 32 + __ffs((int)bits) - 1;
-            bits &= bits - 1;
-            const int32_t sc = __float2int_rz(tc_exact_dist(rec + (size_t)cw * TC_RL, x));
-            ++cnt;
-            if (sc >= best.s[N])
-                best.insert(sc, cw);
+    unsigned long long lo = have ? ((unsigned long long)k0 | ((unsigned long long)k1 << 32)) : 0ull;
+    unsigned long long hi = have ? ((unsigned long long)k2 | ((unsigned long long)k3 << 32)) : 0ull;
+    while (lo | hi) {  // ascending density index
+        int cw;
+        if (lo) {
+            cw = __ffsll((long long)lo) - 1;
+            lo &= lo - 1;
+        } else {
+            cw = 63 + __ffsll((long long)hi);
+            hi &= hi - 1;
         }
+        const int32_t sc = __float2int_rz(tc_exact_dist(rec + (size_t)cw * TC_RL, x));
+        ++cnt;
+        if (sc >= best.s[N])
+            best.insert(sc, cw);
     }
+    if (!have)
+        return;
     bool distinct = cnt >= N;
 #pragma unroll
     for (int k = 0; k < N; ++k)
@@ -233,17 +260,6 @@ __device__ __noinline__ void ft_exact_item(const DevModel &m, const DevPlan &p, 
             atomicAdd(&a.dbg.counters[2], 1ull);
     }
     ft_store<N>(a, cs, g, best.s, best.c);
-}
-
-template <int N, bool DEBUG>
-__device__ __forceinline__ void ft_drain(FtSmem &S, const DevModel &m, const DevPlan &p, const FtArgs &a,
-                                         int64_t gtile, int tid, int n)
-{
-    for (int i = tid; i < n; i += FT_EPI_THREADS) {
-        const uint32_t hd = S.q[i][0];
-        ft_exact_item<N, DEBUG>(m, p, a, (int)(hd >> 8), gtile + (int)(hd & 0xffu), S.q[i][1], S.q[i][2],
-                                S.q[i][3], S.q[i][4]);
-    }
 }
 
 template <int N, bool DEBUG>
@@ -260,12 +276,11 @@ gmm_scan_ft_kernel(DevModel m, DevPlan p, FtArgs a)
             mbar_init(&S.b_full[s], 1);
             mbar_init(&S.b_empty[s], 1);
         }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&S.acc_full[s], 1);
-            mbar_init(&S.acc_empty[s], FT_EPI_THREADS / 32);
+        for (int r = 0; r < FT_RG; ++r) {
+            mbar_init(&S.acc_full[r], 1);
+            mbar_init(&S.acc_empty[r], FT_ROWS / 32);
+            mbar_init(&S.a_ready[r], FT_ROWS / 32);
         }
-        mbar_init(&S.a_ready, FT_EPI_THREADS / 32);
-        S.q_count = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -278,60 +293,69 @@ gmm_scan_ft_kernel(DevModel m, DevPlan p, FtArgs a)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = S.tmem_base;
-
-    uint32_t step = 0;      // codebook-stream steps since the kernel began (same in every role)
-    uint32_t tile_it = 0;   // tiles with work this CTA has started (phase of a_ready)
-    int tile = blockIdx.x;
-    while (tile < a.n_tiles) {
-        const int u = a.tile_utt[tile], t0 = a.tile_t0[tile];
-        const int64_t gu = p.frame_off[u];
-        const int T = (int)(p.frame_off[u + 1] - gu);
-        const int nr = min(FT_ROWS, T - t0);
-        const int64_t gtile = gu + t0;
-        // ---- codebooks of the tile: those active on its last frame (the aligner's active set
-        // only grows, ref: src/state_align_search.c:186-188), each from the row it enters on
+    // phase counters, advanced identically by every role
+    uint32_t step = 0;                 // B loads since the kernel began
+    uint32_t acc_it[FT_RG] = {0, 0};   // accumulator hand-overs per row group
+    uint32_t a_it[FT_RG] = {0, 0};     // A tiles built per row group
+    const int n_pairs = (a.n_tiles + FT_RG - 1) / FT_RG;
+    int pair = blockIdx.x;
+    while (pair < n_pairs) {
+        // ---- the pair's tiles; codebooks = union over the epochs that overlap them (the evaluated
+        // list is NOT monotone: the >255-gap bridging senones of acmod_flags2list come and go,
+        // ref: src/acmod.c:968-973); every row then checks its own epoch's mask
+        if (warp < FT_RG) {
+            const int tile = pair * FT_RG + warp;
+            uint32_t um0 = 0u, um1 = 0u;
+            if (tile < a.n_tiles) {
+                const int u = a.tile_utt[tile], t0 = a.tile_t0[tile];
+                const int T = (int)(p.frame_off[u + 1] - p.frame_off[u]);
+                const int nr = min(FT_ROWS, T - t0);
+                if (p.all_active) {
+                    um0 = um1 = 0xffffffffu;
+                } else {
+                    const int e_lo = p.ep_off[u], e_hi = p.ep_off[u + 1];
+                    for (int e = e_lo + lane; e < e_hi; e += 32)
+                        if (p.ep_start[e] <= t0 + nr - 1 && (e + 1 >= e_hi || p.ep_start[e + 1] > t0)) {
+                            um0 |= p.ep_cbmask[(int64_t)e * 8];
+                            um1 |= p.ep_cbmask[(int64_t)e * 8 + 1];
+                        }
+                    um0 = __reduce_or_sync(0xffffffffu, um0);
+                    um1 = __reduce_or_sync(0xffffffffu, um1);
+                }
+                if (m.n_mgau < 32)
+                    um0 &= (1u << m.n_mgau) - 1u;
+                um1 = m.n_mgau > 32 ? (m.n_mgau < 64 ? um1 & ((1u << (m.n_mgau - 32)) - 1u) : um1) : 0u;
+            }
+            if (lane == 0) {
+                S.um[warp][0] = um0;
+                S.um[warp][1] = um1;
+            }
+        }
+        __syncthreads();
         if (warp == 0) {
-            int e_lo = 0, e_hi = 0, e_last = -1;
-            if (!p.all_active) {
-                e_lo = p.ep_off[u];
-                e_hi = p.ep_off[u + 1];
-                for (int e = e_lo; e < e_hi && p.ep_start[e] <= t0 + nr - 1; ++e)
-                    e_last = e;
+            uint32_t w0 = 0u, w1 = 0u;
+            for (int r = 0; r < FT_RG; ++r) {
+                w0 |= S.um[r][0];
+                w1 |= S.um[r][1];
             }
             int n_before = 0;
-            for (int c0 = 0; c0 < m.n_mgau; c0 += 32) {
-                const int cb = c0 + lane;
-                bool on = false;
-                int r0 = 0;
-                if (cb < m.n_mgau) {
-                    if (p.all_active)
-                        on = true;
-                    else if (e_last >= 0
-                             && ((p.ep_cbmask[(int64_t)e_last * 8 + (cb >> 5)] >> (cb & 31)) & 1u)) {
-                        on = true;
-                        for (int e = e_lo; e <= e_last; ++e)
-                            if ((p.ep_cbmask[(int64_t)e * 8 + (cb >> 5)] >> (cb & 31)) & 1u) {
-                                r0 = max(p.ep_start[e] - t0, 0);
-                                break;
-                            }
-                    }
-                }
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                const bool on = ((c0 ? w1 : w0) >> lane) & 1u;
                 const uint32_t bal = __ballot_sync(0xffffffffu, on);
-                if (on) {
-                    const int pos = n_before + __popc(bal & ((1u << lane) - 1u));
-                    if (pos < FT_MAXCB) {
-                        S.cb_list[pos] = (uint8_t)cb;
-                        S.cb_r0[pos] = (int16_t)r0;
-                    }
-                }
+                if (on)
+                    S.cb_list[n_before + __popc(bal & ((1u << lane) - 1u))] = (uint8_t)(c0 + lane);
                 n_before += __popc(bal);
             }
             if (lane == 0)
-                S.n_cb = min(n_before, FT_MAXCB);
+                S.n_cb = n_before;
         }
         __syncthreads();
         const int n_cb = S.n_cb;
-        const uint32_t n_steps = (uint32_t)(n_cb * NF);
+        uint32_t rgm[FT_RG][2];
+        for (int r = 0; r < FT_RG; ++r) {
+            rgm[r][0] = S.um[r][0];
+            rgm[r][1] = S.um[r][1];
+        }
 
         if (warp == FT_EPI_THREADS / 32) {
             // ================= TMA warp: B_hi | B_lo of each listed codebook-stream =================
@@ -349,306 +373,365 @@ gmm_scan_ft_kernel(DevModel m, DevPlan p, FtArgs a)
             }
             __syncwarp();
         } else if (warp == FT_EPI_THREADS / 32 + 1) {
-            // ================= MMA warp: 12 x tcgen05.mma (M128 N128 K8, tf32) per step =================
-            if (lane == 0 && n_steps > 0) {
-                mbar_wait(&S.a_ready, tile_it & 1u);
-                tc_fence_after();
-                uint32_t s = step;
+            // ================= MMA warp: 12 x tcgen05.mma (M128 N128 K8, tf32) per row group and step =================
+            if (lane == 0) {
+                uint32_t s = step, ai[FT_RG] = {acc_it[0], acc_it[1]};
                 for (int f = 0; f < NF; ++f) {
-                    const uint32_t a_hi = tmem + FT_A_COL + (uint32_t)(64 * f), a_lo = a_hi + 32u;
+                    for (int r = 0; r < FT_RG; ++r)
+                        if (rgm[r][0] | rgm[r][1])
+                            mbar_wait(&S.a_ready[r], (a_it[r] + (uint32_t)f) & 1u);
+                    tc_fence_after();
                     for (int i = 0; i < n_cb; ++i, ++s) {
                         const int slot = (int)(s % FT_NSLOT);
-                        const uint32_t accb = s & 1u;
+                        const int cb = S.cb_list[i];
                         mbar_wait(&S.b_full[slot], (s / FT_NSLOT) & 1u);
-                        mbar_wait(&S.acc_empty[accb], ((s >> 1) & 1u) ^ 1u);
-                        tc_fence_after();
                         const uint64_t bhi = umma_desc_sw128(smem_u32(&S.B[slot][0]));
                         const uint64_t blo = umma_desc_sw128(smem_u32(&S.B[slot][FT_BTILE]));
-                        const uint32_t d = tmem + accb * 128u;
+                        for (int r = 0; r < FT_RG; ++r) {
+                            if (!((rgm[r][cb >> 5] >> (cb & 31)) & 1u))
+                                continue;
+                            mbar_wait(&S.acc_empty[r], (ai[r] & 1u) ^ 1u);
+                            tc_fence_after();
+                            const uint32_t a_hi = tmem + FT_A_COL + (uint32_t)(64 * r), a_lo = a_hi + 32u;
+                            const uint32_t d = tmem + (uint32_t)(128 * r);
 #pragma unroll
-                        for (int k = 0; k < TC_K / 8; ++k)
-                            umma_tf32_ts(d, a_hi + (uint32_t)(8 * k), bhi + (uint64_t)(2 * k), k > 0 ? 1u : 0u);
+                            for (int k = 0; k < TC_K / 8; ++k)
+                                umma_tf32_ts(d, a_hi + (uint32_t)(8 * k), bhi + (uint64_t)(2 * k), k > 0 ? 1u : 0u);
 #pragma unroll
-                        for (int k = 0; k < TC_K / 8; ++k)
-                            umma_tf32_ts(d, a_lo + (uint32_t)(8 * k), bhi + (uint64_t)(2 * k), 1u);
+                            for (int k = 0; k < TC_K / 8; ++k)
+                                umma_tf32_ts(d, a_lo + (uint32_t)(8 * k), bhi + (uint64_t)(2 * k), 1u);
 #pragma unroll
-                        for (int k = 0; k < TC_K / 8; ++k)
-                            umma_tf32_ts(d, a_hi + (uint32_t)(8 * k), blo + (uint64_t)(2 * k), 1u);
+                            for (int k = 0; k < TC_K / 8; ++k)
+                                umma_tf32_ts(d, a_hi + (uint32_t)(8 * k), blo + (uint64_t)(2 * k), 1u);
+                            umma_commit(&S.acc_full[r]);
+                            ++ai[r];
+                        }
                         umma_commit(&S.b_empty[slot]);
-                        umma_commit(&S.acc_full[accb]);
                     }
                 }
             }
             __syncwarp();
-        } else if (n_steps > 0) {
-            // ================= epilogue warps =================
-            const int wq = warp & 3, h = warp >> 2, row = wq * 32 + lane;
-            const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-            const bool row_valid = row < nr;
-            const float *xrow = a.feat + (gtile + (row_valid ? row : 0)) * m.blk;
-            // ---- A tiles of the three streams -> TMEM (thread h = 0: hi parts, h = 1: lo parts)
-            for (int f = 0; f < NF; ++f) {
-                float av[32];
-#pragma unroll
-                for (int j = 0; j < TC_L; ++j) {
-                    const float xv = row_valid ? __ldg(xrow + m.featoff[f] + j) : 0.f;
-                    const float xc = __fsub_rn(xv, m.ft_centre[f * 16 + j]);
-                    const float sq = __fmul_rn(xc, xc);
-                    const float xh = to_tf32(xc), sh = to_tf32(sq);
-                    av[j] = h == 0 ? xh : to_tf32(__fsub_rn(xc, xh));
-                    av[TC_L + j] = h == 0 ? sh : to_tf32(__fsub_rn(sq, sh));
-                }
-                av[26] = h == 0 ? 1.f : 0.f;
-                av[27] = h == 0 ? 1.f : 0.f;
-#pragma unroll
-                for (int j = 28; j < 32; ++j)
-                    av[j] = 0.f;
-                tmem_st32(tmem + lane_base + FT_A_COL + (uint32_t)(64 * f + 32 * h), av);
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0)
-                mbar_arrive(&S.a_ready);
-
-            uint32_t s = step;
-            for (int f = 0; f < NF; ++f) {
-                // this thread's half of the error-bound sum: |x'| (h = 0) or x'^2 (h = 1)
-                float ev[TC_L];
-#pragma unroll
-                for (int j = 0; j < TC_L; ++j) {
-                    const float xv = row_valid ? __ldg(xrow + m.featoff[f] + j) : 0.f;
-                    const float xc = __fsub_rn(xv, m.ft_centre[f * 16 + j]);
-                    ev[j] = h == 0 ? fabsf(xc) : __fmul_rn(xc, xc);
-                }
-                for (int i = 0; i < n_cb; ++i, ++s) {
-                    const int cb = S.cb_list[i];
-                    const int cs = cb * NF + f;
-                    const bool active = row_valid && row >= (int)S.cb_r0[i];
-                    const uint32_t accb = s & 1u;
-                    // bound operands of this codebook-stream (L1-resident, 256 B per cs)
-                    const float4 *ax = reinterpret_cast<const float4 *>(m.gAuxFt + (size_t)cs * 64 + 16 * h);
-                    const float4 a0 = __ldg(ax), a1 = __ldg(ax + 1), a2 = __ldg(ax + 2), a3 = __ldg(ax + 3);
-                    const bool has_hot = a3.w != 0.f;
-                    mbar_wait(&S.acc_full[accb], (s >> 1) & 1u);
-                    tc_fence_after();
-                    const bool warp_active = __any_sync(0xffffffffu, active);
-                    float v[64];
-                    if (warp_active) {
-                        float t[32];
-                        tmem_ld32(tmem + lane_base + accb * 128u + (uint32_t)(64 * h), t);
-#pragma unroll
-                        for (int k = 0; k < 32; ++k)
-                            v[k] = t[k];
-                        tmem_ld32(tmem + lane_base + accb * 128u + (uint32_t)(64 * h + 32), t);
-#pragma unroll
-                        for (int k = 0; k < 32; ++k)
-                            v[32 + k] = t[k];
+        } else {
+            // ================= epilogue warps: thread = frame row =================
+            const int rg = warp >> 2, wq = warp & 3, row = wq * 32 + lane;
+            const int tile = pair * FT_RG + rg;
+            if ((rgm[rg][0] | rgm[rg][1]) != 0u) {  // (implies tile < n_tiles)
+                const int u = a.tile_utt[tile], t0 = a.tile_t0[tile];
+                const int64_t gu = p.frame_off[u];
+                const int T = (int)(p.frame_off[u + 1] - gu);
+                const int nr = min(FT_ROWS, T - t0);
+                const int64_t g = gu + t0 + row;
+                const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+                const bool row_valid = row < nr;
+                // active codebooks of this row's epoch
+                uint32_t rm0 = 0u, rm1 = 0u;
+                if (row_valid) {
+                    if (p.all_active) {
+                        rm0 = rm1 = 0xffffffffu;
+                    } else {
+                        int er = -1;
+                        for (int e = p.ep_off[u]; e < p.ep_off[u + 1] && p.ep_start[e] <= t0 + row; ++e)
+                            er = e;
+                        if (er >= 0) {
+                            rm0 = p.ep_cbmask[(int64_t)er * 8];
+                            rm1 = p.ep_cbmask[(int64_t)er * 8 + 1];
+                        }
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0)
-                        mbar_arrive(&S.acc_empty[accb]);
-                    if (warp_active) {
-                        // ---- front: group maxima (regular densities), bound, exchange with the pair
-                        uint32_t hot_lo = 0u, hot_hi = 0u;
-                        float part_hot = 0.f;
-                        float g0, g1, g2, g3;
-                        if (has_hot) {  // uniform per step
-                            hot_lo = __ldg(m.gHot + (size_t)cs * 4 + 2 * h);
-                            hot_hi = __ldg(m.gHot + (size_t)cs * 4 + 2 * h + 1);
-                            g0 = ft_max16_ex(v, 0, hot_lo & 0xffffu);
-                            g1 = ft_max16_ex(v, 16, hot_lo >> 16);
-                            g2 = ft_max16_ex(v, 32, hot_hi & 0xffffu);
-                            g3 = ft_max16_ex(v, 48, hot_hi >> 16);
-                            const float4 *hx = ax + 8;  // + 32 floats: the hot densities' maxima
-                            const float4 b0 = __ldg(hx), b1 = __ldg(hx + 1), b2 = __ldg(hx + 2), b3 = __ldg(hx + 3);
-                            const float hm[13] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w,
-                                                  b2.x, b2.y, b2.z, b2.w, b3.x};
+                }
+                const float *xrow = a.feat + (row_valid ? g : gu + t0) * m.blk;
+                float *srow = &S.stash[(rg * FT_ROWS + row) * FT_STASH_LD];
+                uint32_t ai = acc_it[rg];
+                for (int f = 0; f < NF; ++f) {
+                    // ---- this stream's features; A tile (hi | lo) -> TMEM
+                    float xs[TC_L];
+                    {
+                        float ah[32], al[32], xc[TC_L];
 #pragma unroll
-                            for (int j = 0; j < TC_L; ++j)
-                                part_hot = fmaf(ev[j], hm[j], part_hot);
-                            if (h == 1)
-                                part_hot += a3.z;  // max |c| over the hot densities
-                        } else {
-                            g0 = ft_max16(v, 0);
-                            g1 = ft_max16(v, 16);
-                            g2 = ft_max16(v, 32);
-                            g3 = ft_max16(v, 48);
+                        for (int j = 0; j < TC_L; ++j) {
+                            xs[j] = row_valid ? __ldg(xrow + m.featoff[f] + j) : 0.f;
+                            xc[j] = __fsub_rn(xs[j], m.ft_centre[f * 16 + j]);
+                            const float sq = __fmul_rn(xc[j], xc[j]);
+                            ah[j] = to_tf32(xc[j]);
+                            ah[TC_L + j] = to_tf32(sq);
+                            al[j] = to_tf32(__fsub_rn(xc[j], ah[j]));
+                            al[TC_L + j] = to_tf32(__fsub_rn(sq, ah[TC_L + j]));
                         }
-                        FT_CE(g0, g1) FT_CE(g2, g3) FT_CE(g0, g2) FT_CE(g1, g3) FT_CE(g1, g2)
-                        float part = 0.f;
-                        {
-                            const float rm[13] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w,
-                                                  a2.x, a2.y, a2.z, a2.w, a3.x};
+                        ah[26] = ah[27] = 1.f;
+                        al[26] = al[27] = 0.f;
 #pragma unroll
-                            for (int j = 0; j < TC_L; ++j)
-                                part = fmaf(ev[j], rm[j], part);
-                            if (h == 1)
-                                part += a3.y;  // max |c| over the regular densities
+                        for (int j = 28; j < 32; ++j)
+                            ah[j] = al[j] = 0.f;
+                        // (the row group's MMAs of the previous stream are complete: their last
+                        // accumulator has been read)
+                        tmem_st32(tmem + lane_base + FT_A_COL + (uint32_t)(64 * rg), ah);
+                        tmem_st32(tmem + lane_base + FT_A_COL + (uint32_t)(64 * rg + 32), al);
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0)
+                            mbar_arrive(&S.a_ready[rg]);
+                    }
+                    for (int i = 0; i < n_cb; ++i) {
+                        const int cb = S.cb_list[i];
+                        if (!((rgm[rg][cb >> 5] >> (cb & 31)) & 1u))
+                            continue;  // (uniform for the row group; the MMA warp skips it too)
+                        const int cs = cb * NF + f;
+                        const bool active = ((cb < 32 ? rm0 >> cb : rm1 >> (cb - 32)) & 1u) != 0u;
+                        const float *ax = m.gAuxFt + (size_t)cs * 64;
+                        const bool has_hot = __ldg(ax + 15) != 0.f;
+                        // error bound of the screening scores (2^-18 of the term magnitudes + 4)
+                        float e0 = __ldg(ax + 13), e1 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < TC_L; ++j) {
+                            const float xcj = __fsub_rn(xs[j], m.ft_centre[f * 16 + j]);
+                            e0 = fmaf(fabsf(xcj), __ldg(ax + j), e0);
+                            e1 = fmaf(__fmul_rn(xcj, xcj), __ldg(ax + 16 + j), e1);
                         }
-                        S.xg[row][h] = make_float4(g0, g1, g2, g3);
-                        S.xe[row][h] = make_float2(part, part_hot);
-                        ft_bar_pair(wq);
-                        const float4 og = S.xg[row][1 - h];
-                        const float2 oe = S.xe[row][1 - h];
-                        // N-th largest of the eight group maxima (two sorted quadruples)
-                        float L;
-                        if (N == 4)
-                            L = fmaxf(ft_max3(og.w, fminf(g0, og.z), fminf(g1, og.y)), fmaxf(fminf(g2, og.x), g3));
-                        else if (N == 3)
-                            L = fmaxf(ft_max3(og.z, fminf(g0, og.y), fminf(g1, og.x)), g2);
-                        else if (N == 2)
-                            L = ft_max3(og.y, fminf(g0, og.x), g1);
-                        else
-                            L = fmaxf(g0, og.x);
-                        // split-TF32 products are good to ~2^-20 of the term magnitudes, measured
-                        // worst case 2^-20.4; the bound used is 2^-18 (+4 raw units), as in v2
-                        const float eps = fmaf(part + oe.x, 1.f / 262144.f, 4.f);
-                        const float eps_hot = fmaf(part_hot + oe.y, 1.f / 262144.f, 4.f);
+                        const float eps = fmaf(e0 + e1, 1.f / 262144.f, 4.f);
+                        float eps_hot = 0.f;
+                        uint32_t hot[4] = {0u, 0u, 0u, 0u};
+                        if (has_hot) {  // uniform
+                            float h0 = __ldg(ax + 14), h1 = 0.f;
+#pragma unroll
+                            for (int j = 0; j < TC_L; ++j) {
+                                const float xcj = __fsub_rn(xs[j], m.ft_centre[f * 16 + j]);
+                                h0 = fmaf(fabsf(xcj), __ldg(ax + 32 + j), h0);
+                                h1 = fmaf(__fmul_rn(xcj, xcj), __ldg(ax + 48 + j), h1);
+                            }
+                            eps_hot = fmaf(h0 + h1, 1.f / 262144.f, 4.f);
+                            const uint4 hw = __ldg(reinterpret_cast<const uint4 *>(m.gHot + (size_t)cs * 4));
+                            hot[0] = hw.x;
+                            hot[1] = hw.y;
+                            hot[2] = hw.z;
+                            hot[3] = hw.w;
+                        }
+                        mbar_wait(&S.acc_full[rg], ai & 1u);
+                        ++ai;
+                        tc_fence_after();
+                        const bool warp_active = __any_sync(0xffffffffu, active);
+                        if (!warp_active) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0)
+                                mbar_arrive(&S.acc_empty[rg]);
+                            continue;
+                        }
+                        const uint32_t ta = tmem + lane_base + (uint32_t)(128 * rg);
+                        float va[32], vb[32];
+                        // ---- pass 1 over the accumulator row: group maxima over the regular densities
+                        float gm[8];
+#define FT_GM(v, c)                                                                     \
+    do {                                                                                \
+        if (has_hot) {                                                                  \
+            gm[2 * (c)] = ft_max16_ex(v, 0, hot[c] & 0xffffu);                          \
+            gm[2 * (c) + 1] = ft_max16_ex(v, 16, hot[c] >> 16);                         \
+        } else {                                                                        \
+            gm[2 * (c)] = ft_max16(v, 0);                                               \
+            gm[2 * (c) + 1] = ft_max16(v, 16);                                          \
+        }                                                                               \
+    } while (0)
+                        FT_TMEM_LD32_NOWAIT(ta, va);
+                        FT_TMEM_WAIT32(va);
+                        FT_TMEM_LD32_NOWAIT(ta + 32u, vb);
+                        FT_GM(va, 0);
+                        FT_TMEM_WAIT32(vb);
+                        FT_TMEM_LD32_NOWAIT(ta + 64u, va);
+                        FT_GM(vb, 1);
+                        FT_TMEM_WAIT32(va);
+                        FT_TMEM_LD32_NOWAIT(ta + 96u, vb);
+                        FT_GM(va, 2);
+                        FT_TMEM_WAIT32(vb);
+                        FT_TMEM_LD32_NOWAIT(ta, va);  // (pass 2 starts travelling)
+                        FT_GM(vb, 3);
+#undef FT_GM
+                        const float L = ft_kth_largest8(gm, N);
                         const float thr = L - 2.f * eps - 2.f;
-                        uint32_t mk_lo = ft_mask32(v, 0, thr), mk_hi = ft_mask32(v, 32, thr);
-                        if (has_hot) {
-                            const float thr_hot = L - eps - eps_hot - 2.f;
-                            if (hot_lo)
-                                mk_lo = (mk_lo & ~hot_lo) | (ft_mask32(v, 0, thr_hot) & hot_lo);
-                            if (hot_hi)
-                                mk_hi = (mk_hi & ~hot_hi) | (ft_mask32(v, 32, thr_hot) & hot_hi);
-                        }
-                        if (!active)
-                            mk_lo = mk_hi = 0u;
-                        {
-                            float4 *sp = reinterpret_cast<float4 *>(&S.stash[row * FT_STASH_LD + 64 * h]);
-#pragma unroll
-                            for (int k = 0; k < 16; ++k)
-                                sp[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-                        }
-                        S.xm[row][h] = (unsigned long long)mk_lo | ((unsigned long long)mk_hi << 32);
+                        const float thr_hot = L - eps - eps_hot - 2.f;
+                        // ---- pass 2: survivor masks; chunks with survivors are parked in the stash
+                        uint32_t mk[4];
+#define FT_MK(v, c)                                                                                  \
+    do {                                                                                             \
+        uint32_t mm = ft_mask32(v, thr);                                                             \
+        if (has_hot && hot[c])                                                                       \
+            mm = (mm & ~hot[c]) | (ft_mask32(v, thr_hot) & hot[c]);                                  \
+        mk[c] = active ? mm : 0u;                                                                    \
+        if (__any_sync(0xffffffffu, mk[c] != 0u)) {                                                  \
+            float4 *sp = reinterpret_cast<float4 *>(srow + 32 * (c));                                \
+            _Pragma("unroll") for (int k = 0; k < 8; ++k)                                            \
+                sp[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);             \
+        }                                                                                            \
+        if (DEBUG && active && a.dbg.approx) {                                                       \
+            float *o = a.dbg.approx + ((int64_t)cs * a.G + g) * TC_ND + 32 * (c);                    \
+            _Pragma("unroll") for (int k = 0; k < 32; ++k) o[k] = v[k];                              \
+        }                                                                                            \
+    } while (0)
+                        FT_TMEM_WAIT32(va);
+                        FT_TMEM_LD32_NOWAIT(ta + 32u, vb);
+                        FT_MK(va, 0);
+                        FT_TMEM_WAIT32(vb);
+                        FT_TMEM_LD32_NOWAIT(ta + 64u, va);
+                        FT_MK(vb, 1);
+                        FT_TMEM_WAIT32(va);
+                        FT_TMEM_LD32_NOWAIT(ta + 96u, vb);
+                        FT_MK(va, 2);
+                        FT_TMEM_WAIT32(vb);
+                        // the accumulator has been read: the next codebook's MMAs may overwrite it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0)
+                            mbar_arrive(&S.acc_empty[rg]);
+                        FT_MK(vb, 3);
+#undef FT_MK
                         if (DEBUG && active && a.dbg.approx) {
-                            float *o = a.dbg.approx + (((int64_t)cs * a.G + gtile + row) * TC_ND + 64 * h);
-#pragma unroll
-                            for (int k = 0; k < 64; ++k)
-                                o[k] = v[k];
-                            if (h == 0) {
-                                a.dbg.eps[((int64_t)cs * a.G + gtile + row) * 2] = eps;
-                                a.dbg.eps[((int64_t)cs * a.G + gtile + row) * 2 + 1] = eps_hot;
-                            }
+                            a.dbg.eps[((int64_t)cs * a.G + g) * 2] = eps;
+                            a.dbg.eps[((int64_t)cs * a.G + g) * 2 + 1] = eps_hot;
                         }
-                        ft_bar_pair(wq);
-                        // ---- back: one thread of the pair (alternating) decides the step
-                        if (active && h == (int)(s & 1u)) {
-                            const unsigned long long om = S.xm[row][1 - h];
-                            const unsigned long long mine = (unsigned long long)mk_lo | ((unsigned long long)mk_hi << 32);
-                            unsigned long long mlo = h == 0 ? mine : om, mhi = h == 0 ? om : mine;
-                            const uint32_t k0 = (uint32_t)mlo, k1 = (uint32_t)(mlo >> 32);
-                            const uint32_t k2 = (uint32_t)mhi, k3 = (uint32_t)(mhi >> 32);
-                            bool decided = false;
-                            const int nsurv = __popcll(mlo) + __popcll(mhi);
-                            if (DEBUG && a.dbg.counters)
+                        // ---- the N+2 best survivors: value and index packed in one sortable key
+                        // (the 7 low mantissa bits carry the density index: 2^-16 of the value lost)
+                        {   // (all lanes: the votes below need the whole warp; inactive rows have no survivors)
+                            if (DEBUG && active && a.dbg.counters)
                                 atomicAdd(&a.dbg.counters[1], 1ull);
-                            if (!a.exact && nsurv <= 12) {
-                                float tv[N + 1];
-                                int ti[N + 1];
+                            float tk[N + 2];
 #pragma unroll
-                                for (int k = 0; k <= N; ++k) {
-                                    tv[k] = -3.4028235e38f;
-                                    ti[k] = 0;
-                                }
-                                const float *srow = &S.stash[row * FT_STASH_LD];
-                                while (mlo | mhi) {
-                                    int cw;
-                                    if (mlo) {
-                                        cw = __ffsll((long long)mlo) - 1;
-                                        mlo &= mlo - 1;
-                                    } else {
-                                        cw = 63 + __ffsll((long long)mhi);
-                                        mhi &= mhi - 1;
-                                    }
-                                    const float val = srow[cw];
-                                    if (val > tv[N]) {
-                                        tv[N] = val;
-                                        ti[N] = cw;
+                            for (int k = 0; k < N + 2; ++k)
+                                tk[k] = -3.4028235e38f;
 #pragma unroll
-                                        for (int j = N - 1; j >= 0; --j)
-                                            if (tv[j + 1] > tv[j]) {
-                                                const float fv = tv[j];
-                                                tv[j] = tv[j + 1];
-                                                tv[j + 1] = fv;
-                                                const int iv = ti[j];
-                                                ti[j] = ti[j + 1];
-                                                ti[j + 1] = iv;
-                                            }
+                            for (int c = 0; c < 4; ++c) {
+                                uint32_t w = mk[c];
+                                while (w) {
+                                    const int cw = 32 * c + __ffs((int)w) - 1;
+                                    w &= w - 1u;
+                                    float key = __uint_as_float((__float_as_uint(srow[cw]) & 0xffffff80u) | (uint32_t)cw);
+#pragma unroll
+                                    for (int k = 0; k < N + 2; ++k) {  // branch-free insertion
+                                        const float hi_ = fmaxf(tk[k], key);
+                                        key = fminf(tk[k], key);
+                                        tk[k] = hi_;
                                     }
                                 }
-                                // decided iff the N+1 best are ordered beyond doubt (2 eps + 2 apart)
-                                // and the N best sit clear of every 1024-unit boundary (eps + 2)
-                                bool ok = true;
-                                const float sep = 2.f * eps + 2.f, clr = eps + 2.f;
+                            }
+                            // Which of the N+1 best need their exact score?  Those within the error
+                            // bound of a 1024-unit boundary (their score >> 10 is in doubt) and those
+                            // not separated from a neighbour beyond doubt (their order is).
+                            // |key - score| <= 2^-16 |score|; hot densities carry their own bound.
+                            const float lastv = tk[N + 1] > -1.0e30f ? tk[N + 1] : (tk[N] > -1.0e30f ? tk[N] : tk[N - 1]);
+                            const float qe = fmaxf(fabsf(tk[0]), fabsf(lastv)) * (1.f / 32768.f);
+                            float ek[N + 2];
 #pragma unroll
-                                for (int k = 0; k < N; ++k) {
-                                    ok = ok && (tv[k] - tv[k + 1] > sep);
-                                    const float r = tv[k] * (1.f / 1024.f);
-                                    ok = ok && (fabsf(r - rintf(r)) * 1024.f > clr);
-                                }
+                            for (int k = 0; k < N + 2; ++k) {
+                                ek[k] = eps;
                                 if (has_hot) {
-                                    // a hot density among the candidates carries the larger bound
-#pragma unroll
-                                    for (int k = 0; k <= N; ++k) {
-                                        const uint32_t hw = __ldg(m.gHot + (size_t)cs * 4 + (ti[k] >> 5));
-                                        ok = ok && !((hw >> (ti[k] & 31)) & 1u);
-                                    }
-                                }
-                                if (ok) {
-                                    int32_t qs[N + 1], qc[N + 1];
-#pragma unroll
-                                    for (int k = 0; k <= N; ++k) {
-                                        // (int)d >> 10 of the exact score; stored << 10 (consumers shift)
-                                        qs[k] = (__float2int_rz(tv[k]) >> SENSCR_SHIFT) * 1024;
-                                        qc[k] = ti[k];
-                                    }
-                                    ft_store<N>(a, cs, gtile + row, qs, qc);
-                                    decided = true;
+                                    const int ci = (int)(__float_as_uint(tk[k]) & 127u);
+                                    if ((hot[ci >> 5] >> (ci & 31)) & 1u)
+                                        ek[k] = eps_hot;
                                 }
                             }
-                            if (!decided) {
-                                const int qi = atomicAdd(&S.q_count, 1);
-                                if (qi < FT_QCAP) {
-                                    S.q[qi][0] = (uint32_t)row | ((uint32_t)cs << 8);
-                                    S.q[qi][1] = k0;
-                                    S.q[qi][2] = k1;
-                                    S.q[qi][3] = k2;
-                                    S.q[qi][4] = k3;
+                            uint32_t need = 0u;
+                            bool full = a.exact || !(fabsf(tk[0]) < 1.0e9f) || !(fabsf(lastv) < 1.0e9f);
+                            full = full && active;
+#pragma unroll
+                            for (int k = 0; k <= N; ++k) {
+                                if (k < N) {
+                                    const float r = tk[k] * (1.f / 1024.f);
+                                    if (!(fabsf(r - rintf(r)) * 1024.f > ek[k] + 2.f + qe))
+                                        need |= 1u << k;
+                                    full = full || (active && !(fabsf(tk[k]) >= 1.f));  // (keys near 0 could be flushed)
+                                }
+                                if (k < N && !(tk[k] - tk[k + 1] > ek[k] + ek[k + 1] + 2.f + qe))
+                                    need |= 3u << k;
+                            }
+                            // the (N+2)-th best within reach of the N-th: more than N+1 candidates
+                            // for the list -> every survivor is evaluated (rare)
+                            full = full || (active && !(tk[N - 1] - tk[N + 1] > ek[N - 1] + ek[N + 1] + 2.f + qe));
+                            int32_t fs[N + 1], fc[N + 1];
+#pragma unroll
+                            for (int k = 0; k <= N; ++k) {
+                                fs[k] = tk[k] > -1.0e30f ? __float2int_rz(tk[k]) : INT32_MIN;
+                                fc[k] = (int)(__float_as_uint(tk[k]) & 127u);
+                            }
+                            if (full || !active)
+                                need = 0u;
+                            if (__any_sync(0xffffffffu, need != 0u)) {
+                                const float *rec = m.gau + gau_offset(m, cb, f);
+                                uint32_t nd = need;
+                                while (nd) {
+                                    const int k = __ffs((int)nd) - 1;
+                                    nd &= nd - 1u;
+                                    int cw = fc[0];
+#pragma unroll
+                                    for (int q = 1; q <= N; ++q)
+                                        cw = q == k ? fc[q] : cw;
+                                    const int32_t sc = __float2int_rz(tc_exact_dist(rec + (size_t)cw * TC_RL, xs));
+#pragma unroll
+                                    for (int q = 0; q <= N; ++q)
+                                        fs[q] = q == k ? sc : fs[q];
+                                    if (DEBUG && a.dbg.counters)
+                                        atomicAdd(&a.dbg.counters[0], 1ull);
+                                }
+                                // candidates that were in doubt take their exact places (the others
+                                // are separated from everybody beyond doubt): sort the N+1, descending
+#define FT_CES(i, j)                                                   \
+    if (fs[j] > fs[i]) {                                               \
+        const int32_t ts_ = fs[i], tc_ = fc[i];                        \
+        fs[i] = fs[j];                                                 \
+        fc[i] = fc[j];                                                 \
+        fs[j] = ts_;                                                   \
+        fc[j] = tc_;                                                   \
+    }
+                                if (N == 4) {
+                                    FT_CES(0, 1) FT_CES(3, 4) FT_CES(2, 4) FT_CES(2, 3) FT_CES(1, 4)
+                                    FT_CES(0, 3) FT_CES(0, 2) FT_CES(1, 3) FT_CES(1, 2)
+                                } else if (N == 3) {
+                                    FT_CES(0, 1) FT_CES(2, 3) FT_CES(0, 2) FT_CES(1, 3) FT_CES(1, 2)
+                                } else if (N == 2) {
+                                    FT_CES(0, 1) FT_CES(1, 2) FT_CES(0, 1)
                                 } else {
-                                    ft_exact_item<N, DEBUG>(m, p, a, cs, gtile + row, k0, k1, k2, k3);
+                                    FT_CES(0, 1)
+                                }
+#undef FT_CES
+                                if (need) {
+                                    bool distinct = true;
+#pragma unroll
+                                    for (int k = 0; k < N; ++k)
+                                        distinct = distinct && (fs[k] > fs[k + 1]);
+                                    if (!distinct) {  // exact scores tie: the list depends on the one carried in
+                                        if (p.tie_bits)
+                                            atomicOr(&p.tie_bits[(int64_t)cs * p.tie_w + (g >> 5)], 1u << (g & 31));
+                                        if (DEBUG && a.dbg.counters)
+                                            atomicAdd(&a.dbg.counters[2], 1ull);
+                                    }
                                 }
                             }
-                        }
-                    }
-                    // ---- drain the queue every 4 steps (all epilogue threads, evenly)
-                    if ((i & 3) == 3 || i == n_cb - 1) {
-                        ft_bar_epi();
-                        const int nq = min(S.q_count, FT_QCAP);
-                        const bool last = (i == n_cb - 1) && (f == NF - 1);
-                        if (nq >= FT_QDRAIN || (last && nq > 0)) {
-                            ft_drain<N, DEBUG>(S, m, p, a, gtile, tid, nq);
-                            ft_bar_epi();
-                            if (tid == 0)
-                                S.q_count = 0;
-                            ft_bar_epi();
+                            if (active && !full) {
+                                if (!a.exact) {
+#pragma unroll
+                                    for (int k = 0; k <= N; ++k)
+                                        if (!((need >> k) & 1u))  // (int)d >> 10 of the exact score; stored << 10
+                                            fs[k] = (fs[k] >> SENSCR_SHIFT) * 1024;
+                                }
+                                ft_store<N>(a, cs, g, fs, fc);
+                            }
+                            if (__any_sync(0xffffffffu, full))
+                                ft_exact_step<N, DEBUG>(m, p, a, full, cs, g, xs, mk[0], mk[1], mk[2], mk[3]);
                         }
                     }
                 }
             }
         }
-        step += n_steps;
-        if (n_steps > 0)
-            ++tile_it;
-        // ---- next tile
+        // ---- phase counters, then the next pair
+        for (int r = 0; r < FT_RG; ++r) {
+            const uint32_t w0 = rgm[r][0], w1 = rgm[r][1];
+            if (w0 | w1) {
+                acc_it[r] += (uint32_t)((__popc(w0) + __popc(w1)) * NF);
+                a_it[r] += (uint32_t)NF;
+            }
+        }
+        step += (uint32_t)(n_cb * NF);
         __syncthreads();
         if (tid == 0)
-            S.next_tile = (int)gridDim.x + atomicAdd(a.tile_counter, 1);
+            S.next_pair = (int)gridDim.x + atomicAdd(a.tile_counter, 1);
         __syncthreads();
-        tile = S.next_tile;
+        pair = S.next_pair;
     }
     tc_fence_before();
     __syncthreads();
@@ -674,7 +757,8 @@ int launch_gmm_scan_ft(const DevModel &m, const DevPlan &p, const float *feat, i
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = n_tiles < sms ? n_tiles : sms;
+    const int n_pairs = (n_tiles + FT_RG - 1) / FT_RG;
+    const int grid = n_pairs < sms ? n_pairs : sms;
     SSB_CUDA(cudaMemsetAsync(tile_counter, 0, sizeof(int), st));
     FtArgs a;
     a.feat = feat;

@@ -41,7 +41,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t"
             "}"
             : "=r"(ok)

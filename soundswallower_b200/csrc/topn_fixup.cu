@@ -63,17 +63,7 @@ topn_fixup_kernel(DevModel m, DevPlan p, const int32_t *__restrict__ seg_utts,
     const float *rec = m.gau + gau_offset(m, cb, f);
     const int64_t g0 = p.frame_off[u];
     const int T = (int)(p.frame_off[u + 1] - g0);
-    int a = 0;  // first frame on which this codebook is scanned
-    if (!p.all_active) {
-        a = INT32_MAX;
-        for (int e = p.ep_off[u]; e < p.ep_off[u + 1]; ++e)
-            if ((p.ep_cbmask[(int64_t)e * 8 + (cb >> 5)] >> (cb & 31)) & 1u) {
-                a = p.ep_start[e];
-                break;
-            }
-    }
-    if (a >= T)
-        return;
+    const int e_lo = p.all_active ? 0 : p.ep_off[u], e_hi = p.all_active ? 0 : p.ep_off[u + 1];
     for (int64_t w = g0 >> 5; w <= (g0 + T - 1) >> 5; ++w) {
         uint32_t bits = tie[(int64_t)cs * tie_w + w];
         while (bits) {
@@ -96,9 +86,34 @@ topn_fixup_kernel(DevModel m, DevPlan p, const int32_t *__restrict__ seg_utts,
                     for (int k = 0; k < N; ++k)
                         tn.c[k] = cc[k];
                 }
-                if (t <= a) {
-                    int tt0 = 0;
-                    for (int tt = t - 1; tt > 0; --tt) {
+                // last frame before t on which this codebook was scanned: the frames of the epochs
+                // whose mask holds it (the evaluated list is not monotone -- the >255-gap bridging
+                // senones come and go, ref: src/acmod.c:968-973)
+                int t_prev = p.all_active ? t - 1 : -1;
+                for (int e = e_lo; e < e_hi; ++e) {
+                    const int s0 = p.ep_start[e];
+                    if (s0 >= t)
+                        break;
+                    if ((p.ep_cbmask[(int64_t)e * 8 + (cb >> 5)] >> (cb & 31)) & 1u) {
+                        const int s1 = e + 1 < e_hi ? p.ep_start[e + 1] : T;
+                        t_prev = min(s1, t) - 1;
+                    }
+                }
+                if (t_prev >= 0) {
+                    // the final list of that scan (already replayed if it was flagged itself)
+                    const uchar4 c = tn_c[(int64_t)cs * G + g0 + t_prev];
+                    const int cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+                    for (int k = 0; k < N; ++k)
+                        tn.c[k] = cc[k];
+                }
+                if (t_prev < t - 1) {
+                    // frames t_prev+1 .. t-1 did not scan it: eval_topn re-scored and stably
+                    // re-sorted the carried codewords on each of them (ref :234-237); replayed
+                    // from the most recent frame on which their scores are pairwise distinct
+                    const int lo = t_prev + 1;
+                    int tt0 = lo;
+                    for (int tt = t - 1; tt > lo; --tt) {
                         const float *xx = feat + (g0 + tt) * m.blk + m.featoff[f];
                         int32_t s[N];
 #pragma unroll
@@ -118,12 +133,6 @@ topn_fixup_kernel(DevModel m, DevPlan p, const int32_t *__restrict__ seg_utts,
 #pragma unroll 1
                     for (int tt = tt0; tt < t; ++tt)
                         fix_eval_topn<N>(tn, rec, RL, feat + (g0 + tt) * m.blk + m.featoff[f], L);
-                } else {
-                    const uchar4 c = tn_c[(int64_t)cs * G + g - 1];
-                    const int cc[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-                    for (int k = 0; k < N; ++k)
-                        tn.c[k] = cc[k];
                 }
                 // eval_topn + eval_cb of frame t on the distances held in shared memory
 #pragma unroll 1
