@@ -34,12 +34,14 @@ constexpr int FT_THREADS = FT_EPI_THREADS + 64;  // + TMA warp + MMA warp
 constexpr int FT_NSLOT = 2;
 constexpr int FT_BTILE = TC_ND * TC_K;  // floats of one operand tile (16 KB)
 constexpr int FT_STASH_LD = 132;        // floats per stash row (bank-conflict-free float4 stores)
+constexpr int FT_PQ = 3;                // undecided steps a row can hold
 constexpr int FT_MAXCB = 64;            // codebooks a model can have here
 constexpr uint32_t FT_A_COL = 256;      // TMEM columns: accumulators [0,256), A tiles from 256
 
 struct FtSmem {
     float B[FT_NSLOT][2 * FT_BTILE];          // B_hi | B_lo per slot (SWIZZLE_128B, as stored in HBM)
     float stash[FT_EPI_THREADS * FT_STASH_LD];
+    uint32_t pq[FT_PQ][6][FT_EPI_THREADS];    // per-row queue of undecided steps: cs | need << 16, 5 keys
     uint64_t b_full[FT_NSLOT], b_empty[FT_NSLOT], acc_full[FT_RG], acc_empty[FT_RG], a_ready[FT_RG];
     uint32_t tmem_base;
     int next_pair;
@@ -262,6 +264,75 @@ __device__ __forceinline__ void ft_exact_step(const DevModel &m, const DevPlan &
     ft_store<N>(a, cs, g, best.s, best.c);
 }
 
+// A step whose N+1 best screening scores (keys, descending) do not decide it: the candidates in
+// `need` get their exact score (the reference's fp32 operation order), all N+1 take their
+// places, ties are flagged, the list is stored.  Whole warp; lanes without work pass have = false.
+template <int N, bool DEBUG>
+__device__ __forceinline__ void ft_resolve(const DevModel &m, const DevPlan &p, const FtArgs &a, bool have,
+                                           int cs, int64_t g, const float (&x)[TC_L], uint32_t need,
+                                           const float (&tk)[N + 1])
+{
+    const int cb = cs / m.n_feat, f = cs - cb * m.n_feat;
+    const float *rec = m.gau + gau_offset(m, cb, f);
+    int32_t fs[N + 1], fc[N + 1];
+#pragma unroll
+    for (int k = 0; k <= N; ++k) {
+        fs[k] = tk[k] > -1.0e30f ? __float2int_rz(tk[k]) : INT32_MIN;
+        fc[k] = (int)(__float_as_uint(tk[k]) & 127u);
+    }
+    uint32_t nd = have ? need : 0u;
+    while (nd) {
+        const int k = __ffs((int)nd) - 1;
+        nd &= nd - 1u;
+        int cw = fc[0];
+#pragma unroll
+        for (int q = 1; q <= N; ++q)
+            cw = q == k ? fc[q] : cw;
+        const int32_t sc = __float2int_rz(tc_exact_dist(rec + (size_t)cw * TC_RL, x));
+#pragma unroll
+        for (int q = 0; q <= N; ++q)
+            fs[q] = q == k ? sc : fs[q];
+        if (DEBUG && a.dbg.counters)
+            atomicAdd(&a.dbg.counters[0], 1ull);
+    }
+    if (!have)
+        return;
+    // candidates that were in doubt take their exact places (the others are separated from
+    // everybody beyond doubt): sort the N+1, descending
+#define FT_CES(i, j)                                                   \
+    if (fs[j] > fs[i]) {                                               \
+        const int32_t ts_ = fs[i], tc_ = fc[i];                        \
+        fs[i] = fs[j];                                                 \
+        fc[i] = fc[j];                                                 \
+        fs[j] = ts_;                                                   \
+        fc[j] = tc_;                                                   \
+    }
+    if (N == 4) {
+        FT_CES(0, 1) FT_CES(3, 4) FT_CES(2, 4) FT_CES(2, 3) FT_CES(1, 4)
+        FT_CES(0, 3) FT_CES(0, 2) FT_CES(1, 3) FT_CES(1, 2)
+    } else if (N == 3) {
+        FT_CES(0, 1) FT_CES(2, 3) FT_CES(0, 2) FT_CES(1, 3) FT_CES(1, 2)
+    } else if (N == 2) {
+        FT_CES(0, 1) FT_CES(1, 2) FT_CES(0, 1)
+    } else {
+        FT_CES(0, 1)
+    }
+#undef FT_CES
+    // which entries hold exact scores after the sort?  (exact ones keep their raw value, the
+    // others are stored as (score >> 10) << 10; telling them apart is not needed: both shift right)
+    bool distinct = true;
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+        distinct = distinct && (fs[k] > fs[k + 1]);
+    if (!distinct) {  // exact scores tie: the list depends on the one carried in
+        if (p.tie_bits)
+            atomicOr(&p.tie_bits[(int64_t)cs * p.tie_w + (g >> 5)], 1u << (g & 31));
+        if (DEBUG && a.dbg.counters)
+            atomicAdd(&a.dbg.counters[2], 1ull);
+    }
+    ft_store<N>(a, cs, g, fs, fc);
+}
+
 template <int N, bool DEBUG>
 __global__ void __launch_bounds__(FT_THREADS, 1)
 gmm_scan_ft_kernel(DevModel m, DevPlan p, FtArgs a)
@@ -441,6 +512,8 @@ gmm_scan_ft_kernel(DevModel m, DevPlan p, FtArgs a)
                 const float *xrow = a.feat + (row_valid ? g : gu + t0) * m.blk;
                 float *srow = &S.stash[(rg * FT_ROWS + row) * FT_STASH_LD];
                 uint32_t ai = acc_it[rg];
+                const int qrow = rg * FT_ROWS + row;
+                int pq_n = 0;
                 for (int f = 0; f < NF; ++f) {
                     // ---- this stream's features; A tile (hi | lo) -> TMEM
                     float xs[TC_L];
@@ -477,26 +550,43 @@ gmm_scan_ft_kernel(DevModel m, DevPlan p, FtArgs a)
                             continue;  // (uniform for the row group; the MMA warp skips it too)
                         const int cs = cb * NF + f;
                         const bool active = ((cb < 32 ? rm0 >> cb : rm1 >> (cb - 32)) & 1u) != 0u;
-                        const float *ax = m.gAuxFt + (size_t)cs * 64;
-                        const bool has_hot = __ldg(ax + 15) != 0.f;
+                        const float4 *ax = reinterpret_cast<const float4 *>(m.gAuxFt + (size_t)cs * 64);
                         // error bound of the screening scores (2^-18 of the term magnitudes + 4)
-                        float e0 = __ldg(ax + 13), e1 = 0.f;
+                        float xa[TC_L], xq[TC_L];
 #pragma unroll
                         for (int j = 0; j < TC_L; ++j) {
                             const float xcj = __fsub_rn(xs[j], m.ft_centre[f * 16 + j]);
-                            e0 = fmaf(fabsf(xcj), __ldg(ax + j), e0);
-                            e1 = fmaf(__fmul_rn(xcj, xcj), __ldg(ax + 16 + j), e1);
+                            xa[j] = fabsf(xcj);
+                            xq[j] = __fmul_rn(xcj, xcj);
                         }
-                        const float eps = fmaf(e0 + e1, 1.f / 262144.f, 4.f);
-                        float eps_hot = 0.f;
-                        uint32_t hot[4] = {0u, 0u, 0u, 0u};
-                        if (has_hot) {  // uniform
-                            float h0 = __ldg(ax + 14), h1 = 0.f;
+                        float eps, eps_hot = 0.f;
+                        bool has_hot;
+                        {
+                            const float4 q0 = __ldg(ax), q1 = __ldg(ax + 1), q2 = __ldg(ax + 2), q3 = __ldg(ax + 3);
+                            const float4 r0 = __ldg(ax + 4), r1 = __ldg(ax + 5), r2 = __ldg(ax + 6), r3 = __ldg(ax + 7);
+                            const float m1[13] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x};
+                            const float m2[13] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, r3.x};
+                            float e0 = q3.y, e1 = 0.f;  // q3.y = max |c| over the regular densities
 #pragma unroll
                             for (int j = 0; j < TC_L; ++j) {
-                                const float xcj = __fsub_rn(xs[j], m.ft_centre[f * 16 + j]);
-                                h0 = fmaf(fabsf(xcj), __ldg(ax + 32 + j), h0);
-                                h1 = fmaf(__fmul_rn(xcj, xcj), __ldg(ax + 48 + j), h1);
+                                e0 = fmaf(xa[j], m1[j], e0);
+                                e1 = fmaf(xq[j], m2[j], e1);
+                            }
+                            eps = fmaf(e0 + e1, 1.f / 262144.f, 4.f);
+                            has_hot = q3.w != 0.f;
+                            eps_hot = q3.z;  // max |c| over the hot ones (completed below)
+                        }
+                        uint32_t hot[4] = {0u, 0u, 0u, 0u};
+                        if (has_hot) {  // uniform
+                            const float4 q0 = __ldg(ax + 8), q1 = __ldg(ax + 9), q2 = __ldg(ax + 10), q3 = __ldg(ax + 11);
+                            const float4 r0 = __ldg(ax + 12), r1 = __ldg(ax + 13), r2 = __ldg(ax + 14), r3 = __ldg(ax + 15);
+                            const float m1[13] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x};
+                            const float m2[13] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, r3.x};
+                            float h0 = eps_hot, h1 = 0.f;
+#pragma unroll
+                            for (int j = 0; j < TC_L; ++j) {
+                                h0 = fmaf(xa[j], m1[j], h0);
+                                h1 = fmaf(xq[j], m2[j], h1);
                             }
                             eps_hot = fmaf(h0 + h1, 1.f / 262144.f, 4.f);
                             const uint4 hw = __ldg(reinterpret_cast<const uint4 *>(m.gHot + (size_t)cs * 4));
@@ -587,33 +677,64 @@ gmm_scan_ft_kernel(DevModel m, DevPlan p, FtArgs a)
                             a.dbg.eps[((int64_t)cs * a.G + g) * 2 + 1] = eps_hot;
                         }
                         // ---- the N+2 best survivors: value and index packed in one sortable key
-                        // (the 7 low mantissa bits carry the density index: 2^-16 of the value lost)
+                        // (the 7 low mantissa bits carry the density index: 2^-16 of the value lost).
+                        // Fixed trip count: the first 8 survivors are picked up with all their
+                        // shared-memory loads in flight and sorted by a network; a row with more
+                        // inserts the rest one by one.
+                        float tk[N + 2];
                         {   // (all lanes: the votes below need the whole warp; inactive rows have no survivors)
                             if (DEBUG && active && a.dbg.counters)
                                 atomicAdd(&a.dbg.counters[1], 1ull);
-                            float tk[N + 2];
+                            uint32_t m0 = mk[0], m1 = mk[1], m2 = mk[2], m3 = mk[3];
+                            float k8[8];
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) {
+                                const bool z0 = m0 == 0u, z1 = m1 == 0u, z2 = m2 == 0u;
+                                const uint32_t w = z0 ? (z1 ? (z2 ? m3 : m2) : m1) : m0;
+                                const int base = z0 ? (z1 ? (z2 ? 96 : 64) : 32) : 0;
+                                const uint32_t cl = w & (w - 1u);
+                                const int cw = base + (w ? __ffs((int)w) - 1 : 0);
+                                m0 = z0 ? m0 : cl;
+                                m1 = (z0 && !z1) ? cl : m1;
+                                m2 = (z0 && z1 && !z2) ? cl : m2;
+                                m3 = (z0 && z1 && z2) ? cl : m3;
+                                const float key = __uint_as_float((__float_as_uint(srow[cw]) & 0xffffff80u) | (uint32_t)cw);
+                                k8[it] = w ? key : -3.4028235e38f;
+                            }
+                            FT_CE(k8[0], k8[1]) FT_CE(k8[2], k8[3]) FT_CE(k8[4], k8[5]) FT_CE(k8[6], k8[7])
+                            FT_CE(k8[0], k8[2]) FT_CE(k8[1], k8[3]) FT_CE(k8[4], k8[6]) FT_CE(k8[5], k8[7])
+                            FT_CE(k8[1], k8[2]) FT_CE(k8[5], k8[6]) FT_CE(k8[0], k8[4]) FT_CE(k8[3], k8[7])
+                            FT_CE(k8[1], k8[5]) FT_CE(k8[2], k8[6])
+                            FT_CE(k8[1], k8[4]) FT_CE(k8[3], k8[6])
+                            FT_CE(k8[2], k8[4]) FT_CE(k8[3], k8[5])
+                            FT_CE(k8[3], k8[4])
 #pragma unroll
                             for (int k = 0; k < N + 2; ++k)
-                                tk[k] = -3.4028235e38f;
+                                tk[k] = k8[k];
+                            uint32_t rest[4] = {m0, m1, m2, m3};
+                            if (__any_sync(0xffffffffu, (m0 | m1 | m2 | m3) != 0u)) {
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                uint32_t w = mk[c];
-                                while (w) {
-                                    const int cw = 32 * c + __ffs((int)w) - 1;
-                                    w &= w - 1u;
-                                    float key = __uint_as_float((__float_as_uint(srow[cw]) & 0xffffff80u) | (uint32_t)cw);
+                                for (int c = 0; c < 4; ++c) {
+                                    uint32_t w = rest[c];
+                                    while (w) {
+                                        const int cw = 32 * c + __ffs((int)w) - 1;
+                                        w &= w - 1u;
+                                        const float key = __uint_as_float((__float_as_uint(srow[cw]) & 0xffffff80u) | (uint32_t)cw);
 #pragma unroll
-                                    for (int k = 0; k < N + 2; ++k) {  // branch-free insertion
-                                        const float hi_ = fmaxf(tk[k], key);
-                                        key = fminf(tk[k], key);
-                                        tk[k] = hi_;
+                                        for (int k = N + 1; k >= 1; --k)
+                                            tk[k] = fmaxf(tk[k], fminf(tk[k - 1], key));
+                                        tk[0] = fmaxf(tk[0], key);
                                     }
                                 }
                             }
-                            // Which of the N+1 best need their exact score?  Those within the error
-                            // bound of a 1024-unit boundary (their score >> 10 is in doubt) and those
-                            // not separated from a neighbour beyond doubt (their order is).
-                            // |key - score| <= 2^-16 |score|; hot densities carry their own bound.
+                        }
+                        // Which of the N+1 best need their exact score?  Those within the error
+                        // bound of a 1024-unit boundary (their score >> 10 is in doubt) and those
+                        // not separated from a neighbour beyond doubt (their order is).
+                        // |key - score| <= 2^-16 |score|; hot densities carry their own bound.
+                        uint32_t need = 0u;
+                        bool full;
+                        {
                             const float lastv = tk[N + 1] > -1.0e30f ? tk[N + 1] : (tk[N] > -1.0e30f ? tk[N] : tk[N - 1]);
                             const float qe = fmaxf(fabsf(tk[0]), fabsf(lastv)) * (1.f / 32768.f);
                             float ek[N + 2];
@@ -626,94 +747,101 @@ gmm_scan_ft_kernel(DevModel m, DevPlan p, FtArgs a)
                                         ek[k] = eps_hot;
                                 }
                             }
-                            uint32_t need = 0u;
-                            bool full = a.exact || !(fabsf(tk[0]) < 1.0e9f) || !(fabsf(lastv) < 1.0e9f);
-                            full = full && active;
+                            full = a.exact || !(fabsf(tk[0]) < 1.0e9f) || !(fabsf(lastv) < 1.0e9f);
 #pragma unroll
-                            for (int k = 0; k <= N; ++k) {
-                                if (k < N) {
-                                    const float r = tk[k] * (1.f / 1024.f);
-                                    if (!(fabsf(r - rintf(r)) * 1024.f > ek[k] + 2.f + qe))
-                                        need |= 1u << k;
-                                    full = full || (active && !(fabsf(tk[k]) >= 1.f));  // (keys near 0 could be flushed)
-                                }
-                                if (k < N && !(tk[k] - tk[k + 1] > ek[k] + ek[k + 1] + 2.f + qe))
+                            for (int k = 0; k < N; ++k) {
+                                // distance of the score to the nearest multiple of 1024
+                                const int lowb = __float2int_rz(tk[k]) & 1023;
+                                if (!(__int2float_rn(min(lowb, 1024 - lowb)) > ek[k] + 3.f + qe))
+                                    need |= 1u << k;
+                                full = full || !(fabsf(tk[k]) >= 1.f);  // (keys near 0 could be flushed)
+                                if (!(tk[k] - tk[k + 1] > ek[k] + ek[k + 1] + 2.f + qe))
                                     need |= 3u << k;
                             }
                             // the (N+2)-th best within reach of the N-th: more than N+1 candidates
                             // for the list -> every survivor is evaluated (rare)
-                            full = full || (active && !(tk[N - 1] - tk[N + 1] > ek[N - 1] + ek[N + 1] + 2.f + qe));
+                            full = full || !(tk[N - 1] - tk[N + 1] > ek[N - 1] + ek[N + 1] + 2.f + qe);
+                            full = full && active;
+                            if (full || !active)
+                                need = 0u;
+                        }
+                        if (active && !full && need == 0u) {
+                            // decided by the screening scores alone: (int)d >> 10, stored << 10
                             int32_t fs[N + 1], fc[N + 1];
 #pragma unroll
                             for (int k = 0; k <= N; ++k) {
-                                fs[k] = tk[k] > -1.0e30f ? __float2int_rz(tk[k]) : INT32_MIN;
+                                fs[k] = tk[k] > -1.0e30f ? (__float2int_rz(tk[k]) >> SENSCR_SHIFT) * 1024 : INT32_MIN;
                                 fc[k] = (int)(__float_as_uint(tk[k]) & 127u);
                             }
-                            if (full || !active)
-                                need = 0u;
-                            if (__any_sync(0xffffffffu, need != 0u)) {
-                                const float *rec = m.gau + gau_offset(m, cb, f);
-                                uint32_t nd = need;
-                                while (nd) {
-                                    const int k = __ffs((int)nd) - 1;
-                                    nd &= nd - 1u;
-                                    int cw = fc[0];
-#pragma unroll
-                                    for (int q = 1; q <= N; ++q)
-                                        cw = q == k ? fc[q] : cw;
-                                    const int32_t sc = __float2int_rz(tc_exact_dist(rec + (size_t)cw * TC_RL, xs));
-#pragma unroll
-                                    for (int q = 0; q <= N; ++q)
-                                        fs[q] = q == k ? sc : fs[q];
-                                    if (DEBUG && a.dbg.counters)
-                                        atomicAdd(&a.dbg.counters[0], 1ull);
-                                }
-                                // candidates that were in doubt take their exact places (the others
-                                // are separated from everybody beyond doubt): sort the N+1, descending
-#define FT_CES(i, j)                                                   \
-    if (fs[j] > fs[i]) {                                               \
-        const int32_t ts_ = fs[i], tc_ = fc[i];                        \
-        fs[i] = fs[j];                                                 \
-        fc[i] = fc[j];                                                 \
-        fs[j] = ts_;                                                   \
-        fc[j] = tc_;                                                   \
-    }
-                                if (N == 4) {
-                                    FT_CES(0, 1) FT_CES(3, 4) FT_CES(2, 4) FT_CES(2, 3) FT_CES(1, 4)
-                                    FT_CES(0, 3) FT_CES(0, 2) FT_CES(1, 3) FT_CES(1, 2)
-                                } else if (N == 3) {
-                                    FT_CES(0, 1) FT_CES(2, 3) FT_CES(0, 2) FT_CES(1, 3) FT_CES(1, 2)
-                                } else if (N == 2) {
-                                    FT_CES(0, 1) FT_CES(1, 2) FT_CES(0, 1)
-                                } else {
-                                    FT_CES(0, 1)
-                                }
-#undef FT_CES
-                                if (need) {
-                                    bool distinct = true;
-#pragma unroll
-                                    for (int k = 0; k < N; ++k)
-                                        distinct = distinct && (fs[k] > fs[k + 1]);
-                                    if (!distinct) {  // exact scores tie: the list depends on the one carried in
-                                        if (p.tie_bits)
-                                            atomicOr(&p.tie_bits[(int64_t)cs * p.tie_w + (g >> 5)], 1u << (g & 31));
-                                        if (DEBUG && a.dbg.counters)
-                                            atomicAdd(&a.dbg.counters[2], 1ull);
-                                    }
-                                }
-                            }
-                            if (active && !full) {
-                                if (!a.exact) {
+                            ft_store<N>(a, cs, g, fs, fc);
+                        }
+                        if (__any_sync(0xffffffffu, full))
+                            ft_exact_step<N, DEBUG>(m, p, a, full, cs, g, xs, mk[0], mk[1], mk[2], mk[3]);
+                        // ---- undecided steps wait in the row's queue until the warp has enough of them
+                        {
+                            const bool want_push = need != 0u;
+                            if (__any_sync(0xffffffffu, want_push && pq_n >= FT_PQ)) {
+                                // a full queue: one round first
+                                const bool have = pq_n > 0;
+                                float qk[N + 1];
+                                uint32_t hd = 0u;
+                                if (have) {
+                                    --pq_n;
+                                    hd = S.pq[pq_n][0][qrow];
 #pragma unroll
                                     for (int k = 0; k <= N; ++k)
-                                        if (!((need >> k) & 1u))  // (int)d >> 10 of the exact score; stored << 10
-                                            fs[k] = (fs[k] >> SENSCR_SHIFT) * 1024;
+                                        qk[k] = __uint_as_float(S.pq[pq_n][1 + k][qrow]);
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k <= N; ++k)
+                                        qk[k] = 0.f;
                                 }
-                                ft_store<N>(a, cs, g, fs, fc);
+                                ft_resolve<N, DEBUG>(m, p, a, have, (int)(hd & 0xffffu), g, xs, hd >> 16, qk);
                             }
-                            if (__any_sync(0xffffffffu, full))
-                                ft_exact_step<N, DEBUG>(m, p, a, full, cs, g, xs, mk[0], mk[1], mk[2], mk[3]);
+                            if (want_push) {
+                                S.pq[pq_n][0][qrow] = (uint32_t)cs | (need << 16);
+#pragma unroll
+                                for (int k = 0; k <= N; ++k)
+                                    S.pq[pq_n][1 + k][qrow] = __float_as_uint(tk[k]);
+                                ++pq_n;
+                            }
+                            const uint32_t hv = __ballot_sync(0xffffffffu, pq_n > 0);
+                            if (__popc(hv) >= 26) {
+                                const bool have = pq_n > 0;
+                                float qk[N + 1];
+                                uint32_t hd = 0u;
+                                if (have) {
+                                    --pq_n;
+                                    hd = S.pq[pq_n][0][qrow];
+#pragma unroll
+                                    for (int k = 0; k <= N; ++k)
+                                        qk[k] = __uint_as_float(S.pq[pq_n][1 + k][qrow]);
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k <= N; ++k)
+                                        qk[k] = 0.f;
+                                }
+                                ft_resolve<N, DEBUG>(m, p, a, have, (int)(hd & 0xffffu), g, xs, hd >> 16, qk);
+                            }
                         }
+                    }
+                    // ---- end of the stream: the queues are emptied (xs changes)
+                    while (__any_sync(0xffffffffu, pq_n > 0)) {
+                        const bool have = pq_n > 0;
+                        float qk[N + 1];
+                        uint32_t hd = 0u;
+                        if (have) {
+                            --pq_n;
+                            hd = S.pq[pq_n][0][qrow];
+#pragma unroll
+                            for (int k = 0; k <= N; ++k)
+                                qk[k] = __uint_as_float(S.pq[pq_n][1 + k][qrow]);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k <= N; ++k)
+                                qk[k] = 0.f;
+                        }
+                        ft_resolve<N, DEBUG>(m, p, a, have, (int)(hd & 0xffffu), g, xs, hd >> 16, qk);
                     }
                 }
             }
