@@ -538,8 +538,35 @@ def tc_probe(model, feats):
     return cw, sc, approx, eps, dict(hot=hot, eps_regular=eps2[..., 0], exact_evals=int(cnt[0]), scan_steps=int(cnt[1]), slow_steps=int(cnt[2]))
 
 
-def fsg_batch(model, feats, graphs, utt_graph=None, hist_cap=4096, max_seg=256, want_hist=False,
+def fsg_batch(model, feats, graphs, utt_graph=None, hist_cap=None, max_seg=256, want_hist=False,
               compallsen=True):
+    """fsg_search over a batch: see _fsg_batch_once.  The reference's history table and segment
+    iterator are unbounded (ref: src/fsg_history.c:129-232); here they have capacities, so the
+    call sizes them from the longest utterance (as the C entry points do) and repeats with
+    larger ones when an utterance overflows (rv == -2 / n_seg < 0) instead of reporting a
+    wrong "no hypothesis"."""
+    n_frames = getattr(feats, "frame_off", None)
+    if n_frames is not None:
+        max_T = int(np.max(np.diff(np.asarray(n_frames)))) if len(n_frames) > 1 else 0
+    else:
+        max_T = max([int(np.asarray(f).reshape(-1, model.blk).shape[0]) for f in feats] or [0])
+    cap = int(hist_cap) if hist_cap else max(4096, 8 * max_T)
+    for _attempt in range(6):
+        out = _fsg_batch_once(model, feats, graphs, utt_graph, cap, max_seg, want_hist, compallsen)
+        over_hist = any(r["rv"] == -2 for r in out)
+        over_seg = [-r["n_seg"] for r in out if r["n_seg"] < 0]
+        if not over_hist and not over_seg:
+            return out
+        if over_hist:
+            cap *= 2
+        if over_seg:
+            max_seg = max(max(over_seg), 2 * max_seg)
+    raise SsbError("fsg_batch: history / segment capacity exceeded after 6 attempts "
+                   "(hist_cap %d, max_seg %d)" % (cap, max_seg))
+
+
+def _fsg_batch_once(model, feats, graphs, utt_graph=None, hist_cap=4096, max_seg=256, want_hist=False,
+                    compallsen=True):
     """fsg_search over a batch (first pass / grammar decoding) on dense senone scores.
 
     graphs: list of dicts with the flattened FSG + lextree (keys n_state start final n_ciphone

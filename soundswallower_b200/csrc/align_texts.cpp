@@ -149,7 +149,8 @@ extern "C" ssb_text_align_t *ssb_align_texts(ssb_model_t *m, const ssb_lexicon_t
     const size_t CS = h->kind == SSB_SCORER_CONT ? 0 : (size_t)h->n_mgau * h->n_feat;
     std::vector<uint8_t> carried((size_t)U * CS * 4, 0);
     float ms1[4] = {0, 0, 0, 0};
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    int hist_cap = std::max(4096, 8 * max_T);
+    for (int attempt = 0; attempt < 6; ++attempt) {
         memset(&fin, 0, sizeof fin);
         fin.n_utts = U;
         fin.feat = feat;
@@ -157,7 +158,7 @@ extern "C" ssb_text_align_t *ssb_align_texts(ssb_model_t *m, const ssb_lexicon_t
         fin.n_graphs = (int32_t)graphs.size();
         fin.graphs = graphs.data();
         fin.utt_graph = utt_graph.data();
-        fin.hist_cap = std::max(4096, 8 * max_T);
+        fin.hist_cap = hist_cap;
         fin.max_seg = max_seg;
         fin.active_lists = ssb_model_fsg_active_ok(m);
         segs.assign((size_t)U * max_seg * 5, 0);
@@ -174,11 +175,21 @@ extern "C" ssb_text_align_t *ssb_align_texts(ssb_model_t *m, const ssb_lexicon_t
         if (ssb_fsg_batch(m, &fin, &fo) != 0)
             return nullptr;
         int need = 0;  // a segmentation longer than max_seg comes back as -length: ask again
-        for (int u = 0; u < U; ++u)
+        bool hist_over = false;  // (the reference's history table is unbounded: grow ours)
+        for (int u = 0; u < U; ++u) {
             need = std::max(need, -n_seg[u]);
-        if (need <= max_seg)
+            hist_over = hist_over || rv1[u] == -2;
+        }
+        if (need <= max_seg && !hist_over)
             break;
-        max_seg = need;
+        if (attempt == 5) {
+            ssb::set_error("ssb_align_texts: history / segment capacity exceeded (hist_cap %d, max_seg %d)",
+                           hist_cap, max_seg);
+            return nullptr;
+        }
+        max_seg = std::max(max_seg, need);
+        if (hist_over)
+            hist_cap *= 2;
     }
     for (int k = 0; k < 4; ++k)
         R->kernel_ms[k] = ms1[k];

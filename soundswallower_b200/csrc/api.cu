@@ -1242,11 +1242,15 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
             std::vector<int64_t> kfo(1, 0);
             std::vector<int32_t> kep_off(1, 0), kep_start, seg_utts;
             std::vector<uint32_t> kep_mask;
+            bool any_cut = false;
             for (int u = 0; u < U; ++u) {
                 const int64_t f0 = b->frame_off[u];
                 const int T = (int)(b->frame_off[u + 1] - f0);
                 const bool cut = T > 2 * seg;
-                if (cut)
+                // (rows of the segmented launch start from the initial lists: with lists carried in
+                // from a previous pass the uncut utterances need their tie steps replayed as well)
+                any_cut = any_cut || cut;
+                if (cut || p.init_topn)
                     seg_utts.push_back(u);
                 const int64_t step = cut ? seg : std::max(T, 1);
                 for (int64_t s0 = 0; s0 < std::max(T, 1); s0 += step) {
@@ -1272,7 +1276,7 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
                     kep_off.push_back((int32_t)kep_start.size());
                 }
             }
-            if (!seg_utts.empty()) {
+            if (any_cut) {
                 if (kep_start.empty()) {  // keep the uploads non-empty
                     kep_start.push_back(0);
                     kep_mask.assign(8, 0u);

@@ -592,7 +592,7 @@ fsg_search_kernel(DevModel m, DevFsgSet gs, FsgActiveArgs aa, const int64_t *__r
     long long n_sen_eval = 0;
     if (ACTIVE) {
         const int nw = (m.n_sen + 31) >> 5, CS = m.n_mgau * m.n_feat;
-        const int cap_ev = (3 * NP + m.n_sen / 255 + 8 + 1) & ~1;
+        const int cap_ev = (min(m.n_emit * NP, m.n_sen) + m.n_sen / 255 + 8 + 1) & ~1;  // (one senone per emitting state)
         int32_t *a = aa.aws + aa.aws_off[u];
         q.feat = aa.feat + frame_off[u] * m.blk;
         q.tn_s = aa.tn_s;
@@ -965,7 +965,7 @@ int launch_fsg_search(const DevModel &m, const DevFsgSet &gs, const int64_t *fra
 size_t fsg_active_ws_ints(const DevModel &m, int n_pnode)
 {
     const size_t nw = (m.n_sen + 31) / 32, CS = (size_t)m.n_mgau * m.n_feat;
-    const size_t cap_ev = (3 * (size_t)n_pnode + m.n_sen / 255 + 8 + 1) & ~(size_t)1;
+    const size_t cap_ev = (std::min<size_t>((size_t)m.n_emit * (size_t)n_pnode, (size_t)m.n_sen) + m.n_sen / 255 + 8 + 1) & ~(size_t)1;
     size_t n = 4 * CS + CS + CS + CS + CS + CS + nw + cap_ev / 2 + cap_ev / 2 + ((size_t)m.n_sen + 1) / 2;
     return (n + 3) & ~(size_t)3;  // keeps every utterance's int4 block 16-byte aligned
 }

@@ -267,6 +267,13 @@ static bool read_mdef(HostModel &m, const std::string &path)
         set_error("%s: heterogeneous topologies are not supported", path.c_str());
         return false;
     }
+    // header sanity: every count indexes a table below
+    if (m.n_ciphone <= 0 || m.n_ciphone > 255 || m.n_phone < m.n_ciphone || m.n_emit > 8 || n_sen <= 0
+        || n_sen > 65535 || n_sseq <= 0 || n_cd_tree < 0 || m.n_ci_sen < 0 || m.n_ci_sen > n_sen) {
+        set_error("%s: implausible header (ciphones %d, phones %d, states %d, senones %d, sseq %d, tree %d)",
+                  path.c_str(), m.n_ciphone, m.n_phone, m.n_emit, n_sen, n_sseq, n_cd_tree);
+        return false;
+    }
     size_t names = f.at, p = f.at;
     for (int i = 0; i < m.n_ciphone; ++i) {
         size_t e = p;
@@ -326,6 +333,12 @@ static bool read_mdef(HostModel &m, const std::string &path)
         for (auto &s : m.sseq)
             s = (uint16_t)((s >> 8) | (s << 8));
     m.n_sen = n_sen;
+    for (int i = 0; i < m.n_phone; ++i)
+        if (m.ph_ssid[i] < 0 || m.ph_ssid[i] >= n_sseq || m.ph_tmat[i] < 0 || m.ph_ci[i] >= m.n_ciphone) {
+            set_error("%s: phone %d: ssid %d / tmat %d / ci %d out of range", path.c_str(), i, m.ph_ssid[i],
+                      m.ph_tmat[i], m.ph_ci[i]);
+            return false;
+        }
     // senone -> CI phone of the first phone (in id order) that uses it
     // (ref: src/bin_mdef.c:470-516); this is the PTM senone->codebook map.
     std::vector<int> owner(n_sen, -1);
@@ -336,8 +349,15 @@ static bool read_mdef(HostModel &m, const std::string &path)
                 owner[s] = m.ph_ci[i];
         }
     m.sen2cb.resize(n_sen);
-    for (int s = 0; s < n_sen; ++s)
+    for (int s = 0; s < n_sen; ++s) {
+        if (owner[s] < 0) {
+            // the reference leaves such a senone on codebook -1 and never scores it (no phone
+            // lists it); it cannot be uploaded as an index
+            set_error("%s: senone %d is used by no phone", path.c_str(), s);
+            return false;
+        }
         m.sen2cb[s] = (uint8_t)owner[s];
+    }
     for (int i = 0; i < m.n_ciphone; ++i)
         if (m.ciname[i] == "SIL")
             m.sil = i;
@@ -423,6 +443,10 @@ static bool read_sendump(HostModel &m, const std::string &path)
                           "weight tables", path.c_str(), book[i]);
                 return false;
             }
+    }
+    if (rows <= 0 || cols < n_sen) {
+        set_error("%s: weight rows of %d columns for %d senones", path.c_str(), cols, n_sen);
+        return false;
     }
     const size_t stride = n_bits == 4 ? (size_t)(cols + 1) / 2 : (size_t)cols;
     if (f.left() < stride * rows * n_feat) {
