@@ -254,6 +254,9 @@ def main():
     ap.add_argument("--utts", type=int, default=4096, help="utterances per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--compallsen", action="store_true", help="score every senone every frame")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="config #2 only (skip configs #3, #4, #5 and the compallsen rate)")
+    ap.add_argument("--total-utts", type=int, default=65536, help="config #5: utterances over all GPUs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -434,15 +437,87 @@ def main():
     stream_same = all(np.array_equal(res[k], res_one[k]) for k in ("start", "dur", "score", "rv", "best_score"))
     stream.close()
 
+    # ---- the other BASELINE configs, same run, same clock sampler (tools/bench_configs.py)
+    feat_nbytes = feat_np.nbytes
+    extra = {}
+    c5 = None
+    if not args.no_extra and not args.compallsen:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_configs as bc
+        peaks_x = {}
+        try:
+            peaks_x = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        feat_nbytes = feat_np.nbytes
+        del pinned, feat_np, feats
+        with ClockSampler(local) as clk_x:
+            # config #5: 65 536 utterances, audio + text -> JSON, utt % n_gpu: STRONG scaling
+            pin5 = torch.empty(4096 * 160000, dtype=torch.int16, pin_memory=True).numpy()
+            barrier()
+            c5 = bc.config5_two_pass(ssb, model, total_utts=args.total_utts, rank=rank, world=world,
+                                     chunk=4096, pinned=pin5)
+            barrier()
+            del pin5
+            if world == 1:
+                # compallsen: every senone of every frame (2.1e10 senone scores)
+                Uc = min(U, 1024)
+                fc = np.empty((Uc, FRAMES, model.blk), np.float32)
+                make_config2_batch(g, Uc, seed=1234, out=fc)
+                bcall = ssb.StateAlignBatch(model)
+                bcall.upload_raw(fc.reshape(-1, model.blk), frame_off[:Uc + 1], phone_off[:Uc + 1],
+                                 flat["ssid"][:Uc * len(chain["ssid"])], flat["tmat"][:Uc * len(chain["ssid"])],
+                                 flat["sf"][:Uc * len(chain["ssid"])], flat["ef"][:Uc * len(chain["ssid"])],
+                                 None, True)
+                bcall.run()
+                bcall.run()
+                msc = bcall.kernel_ms()
+                stc = bcall.stats()
+                score_ms = msc["gmm_topn"] + msc["senone_mix"]
+                extra["compallsen"] = {
+                    "workload": "config#2 in compallsen mode: %d x 10 s, all %d senones of every frame "
+                                "(dense int16 scores in slabs of 32768 frames) + gather + state_align"
+                                % (Uc, model.n_sen),
+                    "kernel_ms": msc, "senone_scores": stc["active_senone_frames"],
+                    "senone_scores_per_s": stc["active_senone_frames"] / (score_ms * 1e-3),
+                    "audio_s_per_s": Uc * FRAMES / FRAME_RATE / (msc["total"] * 1e-3),
+                    "roofline": {"bound": "tensor", "unit": "TFLOP/s",
+                                 "achieved": stc["scanned_cb_frames"] * model.n_feat * model.n_density * 2
+                                             * (2 * model.veclen + 1) / (msc["gmm_topn"] * 1e-3) / 1e12,
+                                 "peak": float(peaks_x.get("bf16_tflops_sustained", 1400.0))}}
+                extra["compallsen"]["roofline"]["frac"] = (extra["compallsen"]["roofline"]["achieved"]
+                                                           / extra["compallsen"]["roofline"]["peak"])
+                bcall.close()
+                del fc
+                extra["config3"] = bc.config3(ssb, model, utts=4096, steps=2, peaks=peaks_x)
+                extra["config4"] = bc.config4(ssb, peaks=peaks_x)
+            extra["clocks"] = clk_x.summary()
+
     audio_s = U * FRAMES / FRAME_RATE
-    t_dev = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    t_dev = torch.tensor([dev_ms, e2e_s * 1e3, c5["wall_s"] if c5 else 0.0], dtype=torch.float64, device="cuda")
     # the only exchange of the job: result summaries (failures, a checksum of all segmentations)
     chk = torch.tensor([n_fail, int(res["start"].astype(np.int64).sum() % (1 << 40)),
-                        int(res["dur"].astype(np.int64).sum())], dtype=torch.int64, device="cuda")
+                        int(res["dur"].astype(np.int64).sum()), c5["utts"] if c5 else 0,
+                        c5["aligned"] if c5 else 0, c5["h2d_bytes"] if c5 else 0],
+                       dtype=torch.int64, device="cuda")
     if dist is not None:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
         dist.all_reduce(chk, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_ms_max = float(t_dev[0]), float(t_dev[1])
+    dev_ms_max, e2e_ms_max, c5_wall_max = float(t_dev[0]), float(t_dev[1]), float(t_dev[2])
+    if c5:
+        tot_utts, tot_ok, tot_h2d = int(chk[3]), int(chk[4]), int(chk[5])
+        extra["config5_two_pass"] = {
+            "workload": "config#5: %d utterances of 10 s (16 kHz int16 audio + 12-word transcript) -> the "
+                        "reference CLI's JSON for every utterance: frontend, alignment grammar + first "
+                        "pass (default mode), chains, second pass, decoder_result_json; utterances "
+                        "split utt %% n_gpu, chunks of 4096 per rank (one pool of 4096 distinct noisy "
+                        "utterances sent again for every chunk)" % tot_utts,
+            "scaling": "strong", "n_gpus": world, "utts": tot_utts, "aligned": tot_ok,
+            "wall_s": c5_wall_max, "ms": c5_wall_max * 1e3,
+            "audio_s_per_s": tot_utts * 10.0 / c5_wall_max if c5_wall_max > 0 else None,
+            "h2d_bytes": tot_h2d, "timing": "host wall clock around this rank's chunks (H2D, kernels, host "
+                                            "graph/chain/JSON work, D2H), barrier on both sides, max over ranks",
+            "rank0_last_chunk_pass1_kernel_ms": c5["pass1_kernel_ms_last_chunk"]}
     n_fail = int(chk[0])
     frames_covered = int(chk[2])
     if rank != 0:
@@ -487,7 +562,7 @@ def main():
         "dtype": "f32+i32", "data": "synthetic",
         "config": {"workload": workload, "utts_per_gpu": U, "frames_per_utt": FRAMES,
                    "l2": "inputs (%.0f MB/rank) and per-step intermediates exceed the 126 MB L2; "
-                         "no flush needed" % (feat_np.nbytes / 1e6),
+                         "no flush needed" % (feat_nbytes / 1e6),
                    "failed_alignments": n_fail,
                    "frames_covered_by_state_segments": frames_covered,
                    "frames_total": world * U * FRAMES, "sharding": "utt % n_gpu, no data-path collective"},
@@ -528,13 +603,18 @@ def main():
                      "scalar_equiv_fp32_frac": fp32_ops / (k1_ms * 1e-3) / fp32_peak},
         "roofline_other": [
             {"kernel": "chain_viterbi_kernel (K3)", "bound": "hbm", "unit": "GB/s",
-             "achieved": stats["state_frames"] * 10 / (kms["chain_viterbi"] / args.steps * 1e-3) / 1e9,
+             "achieved": stats["band_state_frames"] * 10 / (kms["chain_viterbi"] / args.steps * 1e-3) / 1e9,
              "peak": float(peaks.get("hbm_gbs", 6650.0)),
-             "frac": stats["state_frames"] * 10 / (kms["chain_viterbi"] / args.steps * 1e-3) / 1e9
+             "frac": stats["band_state_frames"] * 10 / (kms["chain_viterbi"] / args.steps * 1e-3) / 1e9
                      / float(peaks.get("hbm_gbs", 6650.0)),
-             "note": "ALGORITHMIC bytes: SURVEY 8d's 10 B per state-frame (2 B score in + 8 B token out) x "
-                     "T x chain states; the kernel only writes the evaluated band's tokens (ncu: 1.2 GB of "
-                     "DRAM traffic per launch, profiles/prof_chain_viterbi_r1j.txt) and is issue-bound"},
+             "band_state_frames": stats["band_state_frames"], "dense_state_frames": stats["state_frames"],
+             "reference_equivalent_dense_10B_frac": stats["state_frames"] * 10
+                     / (kms["chain_viterbi"] / args.steps * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6650.0)),
+             "note": "bytes = 10 B (2 B score in + 8 B token out, SURVEY 8d) x the state-frames the kernel "
+                     "EVALUATES (the word-window band the planner computed: band_state_frames); the dense "
+                     "T x states count the reference allocates tokens for is reported separately as "
+                     "reference_equivalent_dense_10B_frac and is NOT a bandwidth; the kernel is issue / "
+                     "latency bound (profiles/prof_chain_viterbi_r1j.txt)"},
             {"kernel": "senone_mix_active_kernel (K2)", "bound": "hbm", "unit": "GB/s",
              "achieved": (stats["scanned_cb_frames"] * model.n_feat * 20 + stats["state_frames"] * 2)
                          / (kms["senone_mix"] / args.steps * 1e-3) / 1e9,
@@ -544,11 +624,27 @@ def main():
              "note": "algorithmic bytes: 20 B of top-N list per scanned codebook-stream-frame in + 2 B per "
                      "state-frame out (ncu: 5.0 + 1.3 GB per launch); integer mixing, issue-bound"}],
         "senone_scores_per_s": stats["active_senone_frames"] / ((kms["gmm_topn"] + kms["senone_mix"]) / args.steps * 1e-3),
-        "dp_state_frames_per_s": stats["state_frames"] / (kms["chain_viterbi"] / args.steps * 1e-3),
-        "dp_hbm_frac_10B": stats["state_frames"] * 10 / (kms["chain_viterbi"] / args.steps * 1e-3) / 1e9
+        "dp_state_frames_per_s": stats["band_state_frames"] / (kms["chain_viterbi"] / args.steps * 1e-3),
+        "dp_hbm_frac_10B": stats["band_state_frames"] * 10 / (kms["chain_viterbi"] / args.steps * 1e-3) / 1e9
                            / float(peaks.get("hbm_gbs", 6650.0)),
         "wall_ms_per_step_device_loop": 1e3 * wall_dev / args.steps,
     }
+    for k, v in extra.items():
+        line[k] = v
+    if world == 1 and not args.no_cpu_baseline and extra and cpu_kind() == "reference":
+        import bench_configs as bc
+        cores = host_cores()
+        if "config3" in line:
+            line["config3"]["cpu_baseline"] = bc.cpu_rate("config3", cores, 12)
+        if "config5_two_pass" in line:
+            line["config5_two_pass"]["cpu_baseline"] = bc.cpu_rate("two_pass", cores, 2)
+        if "config4" in line:
+            dt, audio, ok = bc.cpu_config4(2.0)
+            line["config4"]["cpu_baseline"] = {
+                "value": audio / dt, "unit": "audio-s/s", "cores": 1, "kind": "reference",
+                "sample": "second pass of the reference on the first %.0f s of the utterance (the reference "
+                          "is single-threaded per utterance; its token stack for the whole hour would be "
+                          "86 GB), valid=%s" % (audio, ok)}
     if world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
         kind = cpu_kind()

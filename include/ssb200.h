@@ -196,6 +196,10 @@ int ssb_batch_n_launches(const ssb_batch_t *b);
  * [3] scanned codebook-frames [4] device bytes held [5] largest active-senone union
  * [6] longest chain (phones) [7] host microseconds the last upload spent planning */
 int ssb_batch_stats(const ssb_batch_t *b, int64_t *out8);
+/* state-frames the chain Viterbi really evaluates for the uploaded batch: phone i on frames
+ * [enter[i], max(enter[i], ef[i])] (the word-window band; ref: src/state_align_search.c:88-133).
+ * out8[1] of ssb_batch_stats is the dense count T x states the reference allocates tokens for. */
+int64_t ssb_batch_band_state_frames(const ssb_batch_t *b);
 
 /* upload + run + download in one call (the call a host program makes).  A batch of at least
  * two chunks (see ssb_pipeline_create) is routed through a temporary pipeline. */

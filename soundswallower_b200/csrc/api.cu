@@ -695,7 +695,7 @@ struct ssb_batch_s {
     // plan (host)
     int n_utts = 0;
     int64_t n_frames = 0, n_phones = 0, n_states = 0, n_state_frames = 0;
-    int64_t n_active_sen_frames = 0, n_scanned_cb_frames = 0;
+    int64_t n_active_sen_frames = 0, n_scanned_cb_frames = 0, n_band_state_frames = 0;
     int64_t plan_us = 0;  // host time of the last upload's planning + staging calls
     int max_phones = 0, max_union = 0, max_T = 0;
     int compallsen = 0;
@@ -847,7 +847,7 @@ struct PlanPiece {
     std::vector<uint32_t> ep_cbmask;
     std::vector<uint16_t> ep_slot, usen;
     int max_union = 0;
-    int64_t active_sen_frames = 0, scanned_cb_frames = 0;
+    int64_t active_sen_frames = 0, scanned_cb_frames = 0, band_state_frames = 0;
     std::string error;
 };
 
@@ -890,6 +890,10 @@ void plan_range(const HostModel &h, const ssb_align_in_t *in, const std::vector<
         int32_t *enter = enter_all + p0;
         uint16_t *st_slot = st_slot_all + p0 * E;
         plan_enter(np, T, sf, ef, enter);
+        // state-frames the chain Viterbi evaluates: phone i on frames [enter, max(enter, ef)]
+        for (int i = 0; i < np; ++i)
+            if (enter[i] >= 0 && enter[i] < T)
+                out.band_state_frames += (int64_t)E * (std::min<int64_t>(std::max(enter[i], ef[i]), T - 1) - enter[i] + 1);
         if (in->compallsen) {
             out.ep_count.push_back(0);
             out.us_count.push_back(0);
@@ -1128,7 +1132,7 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
     std::vector<int32_t> ep_off(1, 0), ep_start, ep_slot_off(1, 0), us_off(1, 0);
     std::vector<uint32_t> ep_cbmask;
     std::vector<uint16_t> ep_slot, usen;
-    b->n_active_sen_frames = b->n_scanned_cb_frames = 0;
+    b->n_active_sen_frames = b->n_scanned_cb_frames = b->n_band_state_frames = 0;
     for (const PlanPiece &pc : pieces) {
         for (int32_t c : pc.ep_count)
             ep_off.push_back(ep_off.back() + c);
@@ -1142,6 +1146,7 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
         usen.insert(usen.end(), pc.usen.begin(), pc.usen.end());
         b->max_union = std::max(b->max_union, pc.max_union);
         b->n_active_sen_frames += pc.active_sen_frames;
+        b->n_band_state_frames += pc.band_state_frames;
         b->n_scanned_cb_frames += pc.scanned_cb_frames;
     }
     if (ep_slot.size() > (size_t)INT32_MAX - 65536) {
@@ -1526,6 +1531,11 @@ extern "C" int ssb_batch_stats(const ssb_batch_t *b, int64_t *o)
     o[6] = b->max_phones;
     o[7] = b->plan_us;
     return 0;
+}
+
+extern "C" int64_t ssb_batch_band_state_frames(const ssb_batch_t *b)
+{
+    return b ? b->n_band_state_frames : -1;
 }
 
 // ------------------------------------------------------------------ pipeline
