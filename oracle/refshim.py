@@ -11,6 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_SSB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libssref_ssb.so")
 LIB = os.path.join(HERE, "_ref", "libssref.so")
 
 
@@ -25,8 +26,11 @@ def _p(a, t):
 class Ref:
     """One reference decoder_t."""
 
-    def __init__(self, hmmdir, dictfile=None, compallsen=False, samprate=0, loglevel="FATAL"):
-        self.lib = C.CDLL(LIB)
+    def __init__(self, hmmdir, dictfile=None, compallsen=False, samprate=0, loglevel="FATAL", lib=None):
+        # lib: another build of the same sources (oracle/_ref/libssref_ssb.so = the reference linked
+        # against libssb200.so, its scorer replaced through acmod_load_am)
+        self.lib = C.CDLL(lib or LIB)
+        self.external_scorer = lib is not None
         L = self.lib
         L.ref_new.restype = C.c_void_p
         L.ref_new.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p]
@@ -40,6 +44,8 @@ class Ref:
             raise RuntimeError("reference decoder_init failed")
         self.h = C.c_void_p(self.h)
         dims = np.zeros(16, np.int32)
+        if self.external_scorer:
+            return  # (ref_model_dims reads ptm_mgau_t's private fields)
         if L.ref_model_dims(self.h, _p(dims, C.c_int32)) != 0:
             raise RuntimeError("not a PTM model")
         (self.n_mgau, self.n_feat, self.n_density, self.veclen, self.n_sen, self.n_sseq,

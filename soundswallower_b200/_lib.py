@@ -134,7 +134,7 @@ class SegIter(C.Structure):
 SYMBOLS = [
     "ssb_version", "ssb_last_error", "ssb_device_count", "ssb_config_defaults",
     "ssb_model_load", "ssb_model_kind", "ssb_model_ciphone_str", "ssb_model_free", "ssb_model_dims", "ssb_model_copy", "ssb_model_phones",
-    "ssb_mgau_init", "ssb_mgau_frame_eval", "ssb_mgau_reset", "ssb_mgau_free",
+    "ssb_mgau_init", "ssb_mgau_frame_eval", "ssb_mgau_reset", "ssb_mgau_free", "ssb_mgau_own_model",
     "ssb_plan_chain", "ssb_batch_create", "ssb_batch_free", "ssb_batch_upload", "ssb_batch_run",
     "ssb_batch_download", "ssb_batch_debug_tokens", "ssb_batch_kernel_ms",
     "ssb_batch_n_launches", "ssb_batch_stats", "ssb_batch_band_state_frames", "ssb_align_batch", "ssb_pipeline_create",
@@ -189,6 +189,8 @@ def load():
     L.ssb_mgau_reset.restype = None
     L.ssb_mgau_free.argtypes = [P(MgauBase)]
     L.ssb_mgau_free.restype = None
+    L.ssb_mgau_own_model.argtypes = [P(MgauBase), C.c_int]
+    L.ssb_mgau_own_model.restype = None
     L.ssb_plan_chain.argtypes = [i32, i32, vp, vp, vp]
     L.ssb_batch_create.restype = vp
     L.ssb_batch_create.argtypes = [vp, vp]

@@ -501,6 +501,7 @@ static void decode_active(const uint8_t *list, int n, std::vector<uint16_t> &out
 struct ssb_mgau_impl {
     ssb_mgau_t base;  // must be first: {vt, frame_idx}
     ssb_model_t *m;
+    bool owns_model = false;  // ssb_mgau_own_model: freeing the scorer frees the model too
     FrameHist hist;
     DBuf hs[2], hc[2], ha[2], x, senscr, act, raw;
     float *h_x = nullptr;
@@ -585,6 +586,13 @@ extern "C" ssb_mgau_t *ssb_mgau_init(ssb_model_t *m)
     return &g->base;
 }
 
+extern "C" void ssb_mgau_own_model(ssb_mgau_t *gg, int own)
+{
+    ssb_mgau_impl *g = reinterpret_cast<ssb_mgau_impl *>(gg);
+    if (g)
+        g->owns_model = own != 0;
+}
+
 extern "C" void ssb_mgau_reset(ssb_mgau_t *gg)
 {
     ssb_mgau_impl *g = reinterpret_cast<ssb_mgau_impl *>(gg);
@@ -620,7 +628,10 @@ extern "C" void ssb_mgau_free(ssb_mgau_t *gg)
         cudaFreeHost(g->h_cb);
     if (g->st)
         cudaStreamDestroy(g->st);
+    ssb_model_t *owned = g->owns_model ? g->m : nullptr;
     delete g;
+    if (owned)
+        ssb_model_free(owned);
 }
 
 extern "C" int ssb_mgau_frame_eval(ssb_mgau_t *gg, int16_t *senscr, uint8_t *senone_active,
