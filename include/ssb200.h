@@ -378,6 +378,17 @@ typedef struct ssb_fsg_built_s ssb_fsg_built_t;
 /* NULL with "Unknown word ..." when a word of `text` is not in the dictionary */
 ssb_fsg_built_t *ssb_fsg_build_align(const ssb_lexicon_t *lx, const char *text,
                                      const ssb_fsg_config_t *cfg);
+/* Any grammar from its transition list (a compiled JSGF, a .fsg file's TRANSITION lines): what
+ * fsg_model_read_s3file / jsgf_build_fsg hand to decoder_set_fsg (ref: src/fsg_model.c:506-690,
+ * :62-140, :146-213; src/decoder.c:600-645), then the same augmentation + lextree as above.
+ * Transitions in the order the reference would add them (link order decides ties in the search);
+ * word[i] NULL or "" = null transition; prob[i] in (0, 1] is converted as the reference does,
+ * (int32)(logmath_log(p) * lw); null_closure != 0 computes the transitive closure of the null
+ * transitions first (fsg_model_null_trans_closure), as both of the reference's producers do. */
+ssb_fsg_built_t *ssb_fsg_build(const ssb_lexicon_t *lx, int32_t n_state, int32_t start, int32_t final,
+                               int32_t n_trans, const int32_t *from, const int32_t *to,
+                               const float *prob, const char *const *word, int32_t null_closure,
+                               const ssb_fsg_config_t *cfg);
 /* the graph (arrays owned by the object) and its vocabulary: link4[.][3] indexes these words */
 const ssb_fsg_graph_t *ssb_fsg_built_graph(const ssb_fsg_built_t *b);
 int32_t ssb_fsg_built_n_words(const ssb_fsg_built_t *b);

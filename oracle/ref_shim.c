@@ -787,6 +787,18 @@ ref_fsg_prepare(void *h, const char *align_text, const char *jsgf_string)
     return -1;
 }
 
+/* Select the grammar of a text .fsg file (fsg_model_readfile + decoder_set_fsg). */
+int
+ref_fsg_prepare_file(void *h, const char *path)
+{
+    ref_t *r = h;
+    fsg_model_t *fsg = fsg_model_readfile(path, decoder_logmath(r->d),
+                                          config_float(decoder_config(r->d), "lw"));
+    if (fsg == NULL)
+        return -1;
+    return decoder_set_fsg(r->d, fsg);   /* consumes fsg */
+}
+
 /* out: n_state start final n_link n_pnode n_ciphone silcipid beam pbeam wbeam maxhmmpf wip pip */
 int
 ref_fsg_dims(void *h, int32 *out)

@@ -203,12 +203,15 @@ class Ref:
         r.update(rv=rv, best_score=int(n_out[6]), tokens=tokens, senscr=senscr)
         return r
 
-    def fsg_graph(self, align_text=None, jsgf=None):
+    def fsg_graph(self, align_text=None, jsgf=None, fsg_file=None):
         """Select a grammar and return the flattened FSG + lextree the search runs on
         (see ref_fsg_dump in ref_shim.c for the layouts)."""
         L = self.lib
-        rv = L.ref_fsg_prepare(self.h, align_text.encode() if align_text else None,
-                               jsgf.encode() if jsgf else None)
+        if fsg_file:
+            rv = L.ref_fsg_prepare_file(self.h, fsg_file.encode())
+        else:
+            rv = L.ref_fsg_prepare(self.h, align_text.encode() if align_text else None,
+                                   jsgf.encode() if jsgf else None)
         assert rv == 0, rv
         d = np.zeros(16, np.int32)
         assert L.ref_fsg_dims(self.h, _p(d, C.c_int32)) == 0

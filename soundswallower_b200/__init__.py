@@ -25,7 +25,7 @@ MODEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "model")
 
 __all__ = ["AcousticModel", "PtmMgau", "StateAlignBatch", "align_batch", "score_batch",
            "topn_batch", "tc_probe", "fsg_batch", "hmm_vit_eval", "windows", "plan_chain", "propagate", "flags2list", "device_count",
-           "Frontend", "DeviceFeatures", "Lexicon", "align_texts", "SsbError", "Config", "MODEL_DIR", "INT_MAX", "WORST_SCORE"]
+           "Frontend", "DeviceFeatures", "Lexicon", "read_fsg_file", "align_texts", "SsbError", "Config", "MODEL_DIR", "INT_MAX", "WORST_SCORE"]
 
 
 def _ptr(a, t=None):
@@ -894,7 +894,10 @@ def _lexicon_align_graph(self, text, **cfg):
     b = self.lib.ssb_fsg_build_align(self.h, text.encode("utf-8"), C.byref(c))
     if not b:
         raise SsbError("ssb_fsg_build_align: " + _lib.last_error())
-    b = C.c_void_p(b)
+    return _built_graph(self, C.c_void_p(b))
+
+
+def _built_graph(self, b):
     try:
         g = self.lib.ssb_fsg_built_graph(b).contents
 
@@ -924,6 +927,56 @@ def _lexicon_align_graph(self, text, **cfg):
 
 
 Lexicon.align_graph = _lexicon_align_graph
+
+
+def _lexicon_fsg_graph(self, n_state, start, final, transitions, null_closure=True, **cfg):
+    """Any grammar from its transition list [(from, to, prob, word or None), ...] in the order the
+    reference's reader / JSGF compiler adds them (ref: src/fsg_model.c:506-690): decoder_set_fsg's
+    graph, flattened like align_graph's (ssb_fsg_build)."""
+    c = _lib.FsgConfig()
+    self.lib.ssb_fsg_config_defaults(C.byref(c))
+    for k, v in cfg.items():
+        if not hasattr(c, k):
+            raise SsbError("unknown search parameter " + k)
+        setattr(c, k, v)
+    n = len(transitions)
+    fr = np.array([t[0] for t in transitions], np.int32)
+    to = np.array([t[1] for t in transitions], np.int32)
+    pr = np.array([t[2] for t in transitions], np.float32)
+    words = (C.c_char_p * max(n, 1))()
+    for i, t in enumerate(transitions):
+        words[i] = t[3].encode("utf-8") if t[3] else None
+    b = self.lib.ssb_fsg_build(self.h, int(n_state), int(start), int(final), n, _ptr(fr), _ptr(to), _ptr(pr),
+                               words, 1 if null_closure else 0, C.byref(c))
+    if not b:
+        raise SsbError("ssb_fsg_build: " + _lib.last_error())
+    return _built_graph(self, C.c_void_p(b))
+
+
+def read_fsg_file(path):
+    """The reference's text FSG format (ref: src/fsg_model.c:506-690): returns
+    (n_state, start, final, [(from, to, prob, word or None), ...])."""
+    n_state = start = final = None
+    trans = []
+    for ln in open(path, encoding="utf-8"):
+        ln = ln.split("#", 1)[0].split()
+        if not ln:
+            continue
+        k = ln[0]
+        if k in ("NUM_STATES", "N"):
+            n_state = int(ln[1])
+        elif k in ("START_STATE", "S"):
+            start = int(ln[1])
+        elif k in ("FINAL_STATE", "F"):
+            final = int(ln[1])
+        elif k in ("TRANSITION", "T"):
+            trans.append((int(ln[1]), int(ln[2]), float(ln[3]), ln[4] if len(ln) > 4 else None))
+    if None in (n_state, start, final):
+        raise SsbError("%s: not an FSG file" % path)
+    return n_state, start, final, trans
+
+
+Lexicon.fsg_graph = _lexicon_fsg_graph
 
 
 # ---------------------------------------------------------------------------- search drop-in

@@ -152,7 +152,7 @@ SYMBOLS = [
     "ssb_frontend_kernel_ms",
     "ssb_lexicon_load", "ssb_lexicon_free", "ssb_lexicon_size", "ssb_lexicon_wordid",
     "ssb_lexicon_wordstr", "ssb_lexicon_pron", "ssb_lexicon_is_filler", "ssb_chain_populate",
-    "ssb_fsg_config_defaults", "ssb_fsg_build_align", "ssb_fsg_built_graph",
+    "ssb_fsg_config_defaults", "ssb_fsg_build_align", "ssb_fsg_build", "ssb_fsg_built_graph",
     "ssb_fsg_built_n_words", "ssb_fsg_built_word", "ssb_fsg_built_free",
 ]
 
@@ -271,6 +271,8 @@ def load():
     L.ssb_fsg_config_defaults.argtypes = [P(FsgConfig)]
     L.ssb_fsg_build_align.restype = vp
     L.ssb_fsg_build_align.argtypes = [vp, C.c_char_p, P(FsgConfig)]
+    L.ssb_fsg_build.restype = vp
+    L.ssb_fsg_build.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, P(C.c_char_p), i32, P(FsgConfig)]
     L.ssb_fsg_built_graph.restype = P(FsgGraph)
     L.ssb_fsg_built_graph.argtypes = [vp]
     L.ssb_fsg_built_n_words.argtypes = [vp]

@@ -484,6 +484,8 @@ struct FsgWork {
     std::vector<uint8_t> silword, altword;
     std::vector<FLink> pool;
     std::vector<ArcTable> trans;
+    std::vector<ArcTable> ntrans;   // null transitions: one link per (from, to) (ref: src/fsg_model.c:96-140)
+    std::vector<int> nulls;         // the reference's glist of null links, front = newest
 
     int word_add(const std::string &w)
     {
@@ -547,13 +549,63 @@ struct FsgWork {
                         }
                 }
     }
-    // links of state s in fsg_model_arcs order (no null transitions in these grammars)
+    // ref: src/fsg_model.c:96-140 -- 1 = new link, 0 = better probability kept, -1 = nothing changed
+    int null_add(int from, int to, int logp)
+    {
+        if (from == to)
+            return -1;  // self-loop null transitions are redundant
+        if ((int)ntrans.size() < n_state)
+            ntrans.resize(n_state);
+        ArcTable::Ent *e = ntrans[from].find(to);
+        if (e) {
+            FLink &l = pool[e->links[0]];
+            if (l.logp < logp) {
+                l.logp = logp;
+                return 0;
+            }
+            return -1;
+        }
+        e = ntrans[from].enter(to);
+        pool.push_back({from, to, logp, -1});
+        e->links.push_back((int)pool.size() - 1);
+        return 1;
+    }
+    // transitive closure of the null transitions, the reference's sweep order (ref: src/fsg_model.c:
+    // 146-213): the list is walked from its newest entry; links found during a sweep go to the front
+    void null_closure()
+    {
+        if ((int)ntrans.size() < n_state)
+            ntrans.resize(n_state);
+        bool updated;
+        do {
+            updated = false;
+            const std::vector<int> sweep = nulls;  // (additions are seen by the next sweep only)
+            for (int li1 : sweep) {
+                const int from = pool[li1].from, mid = pool[li1].to;
+                for (const auto &bk : ntrans[mid].bucket)
+                    for (const ArcTable::Ent &e2 : bk) {
+                        const int to = pool[e2.links[0]].to;
+                        const int k = null_add(from, to, pool[li1].logp + pool[e2.links[0]].logp);
+                        if (k >= 0) {
+                            updated = true;
+                            if (k > 0)
+                                nulls.insert(nulls.begin(), ntrans[from].find(to)->links[0]);
+                        }
+                    }
+            }
+        } while (updated);
+    }
+    // links of state s in fsg_model_arcs order: word transitions, then null ones (ref :249-300)
     std::vector<int> arcs(int s) const
     {
         std::vector<int> out;
         for (const auto &bk : trans[s].bucket)
             for (const ArcTable::Ent &e : bk)
                 out.insert(out.end(), e.links.begin(), e.links.end());
+        if (s < (int)ntrans.size())
+            for (const auto &bk : ntrans[s].bucket)
+                for (const ArcTable::Ent &e : bk)
+                    out.insert(out.end(), e.links.begin(), e.links.end());
         return out;
     }
 };
@@ -620,9 +672,60 @@ extern "C" ssb_fsg_built_t *ssb_fsg_build_align(const ssb_lexicon_t *lx, const c
         }
     W.n_state = (int)words.size() + 1;
     W.trans.resize(W.n_state);
+    W.ntrans.resize(W.n_state);
     for (size_t i = 0; i < words.size(); ++i)
         W.trans_add((int)i, (int)i + 1, 0, W.word_add(words[i]));
     return fsg_finish(W, 0, (int)words.size());
+}
+
+// A general grammar from its transition list, in the order the reference's reader / JSGF
+// compiler would add them (ref: src/fsg_model.c:506-690 fsg_model_read_s3file, :62-140
+// fsg_model_trans_add / fsg_model_null_trans_add; link order decides ties in the search).
+// word[i] == NULL (or "") is a null transition; prob is the linear transition probability,
+// converted like the reference does: (int32)(logmath_log(p) * lw).
+extern "C" ssb_fsg_built_t *ssb_fsg_build(const ssb_lexicon_t *lx, int32_t n_state, int32_t start,
+                                          int32_t final, int32_t n_trans, const int32_t *from,
+                                          const int32_t *to, const float *prob, const char *const *word,
+                                          int32_t null_closure, const ssb_fsg_config_t *cfg)
+{
+    if (!lx || n_state <= 0 || start < 0 || start >= n_state || final < 0 || final >= n_state || n_trans < 0
+        || (n_trans > 0 && (!from || !to || !prob || !word))) {
+        set_error("ssb_fsg_build: bad arguments");
+        return nullptr;
+    }
+    FsgWork W;
+    W.lx = lx;
+    if (cfg)
+        W.cfg = *cfg;
+    else
+        ssb_fsg_config_defaults(&W.cfg);
+    W.n_state = n_state;
+    W.trans.resize(n_state);
+    W.ntrans.resize(n_state);
+    LogMath lm(lx->h->cfg.logbase);
+    for (int i = 0; i < n_trans; ++i) {
+        if (from[i] < 0 || from[i] >= n_state || to[i] < 0 || to[i] >= n_state) {
+            set_error("ssb_fsg_build: transition %d: state out of range", i);
+            return nullptr;
+        }
+        if (!(prob[i] > 0.f) || prob[i] > 1.f) {
+            set_error("ssb_fsg_build: transition %d: probability %g not in (0, 1]", i, (double)prob[i]);
+            return nullptr;
+        }
+        const int logp = (int32_t)((float)lm.log((double)prob[i], 0) * W.cfg.lw);
+        if (word[i] && word[i][0]) {
+            if (!lx->id.count(word[i])) {
+                set_error("Unknown word %s", word[i]);  // (fsg_search_check_dict, ref: src/fsg_search.c:120-139)
+                return nullptr;
+            }
+            W.trans_add(from[i], to[i], logp, W.word_add(word[i]));
+        } else if (W.null_add(from[i], to[i], logp) == 1) {
+            W.nulls.insert(W.nulls.begin(), W.ntrans[from[i]].find(to[i])->links[0]);
+        }
+    }
+    if (null_closure)
+        W.null_closure();
+    return fsg_finish(W, start, final);
 }
 
 // fsg_search_init's augmentation + fsg_lextree_init, then the flattening
@@ -673,8 +776,8 @@ static ssb_fsg_built_t *fsg_finish(FsgWork &W, int start, int final)
             const FLink &l = W.pool[li];
             link_id[li] = (int)(B->link4.size() / 4);
             B->link4.insert(B->link4.end(), {l.from, l.to, l.logp, l.wid});
-            const bool filler = W.silword[l.wid];
-            const bool single = lx->word[dictwid_of_word[l.wid]].ph.size() == 1;
+            const bool filler = l.wid >= 0 && W.silword[l.wid];
+            const bool single = l.wid >= 0 && lx->word[dictwid_of_word[l.wid]].ph.size() == 1;
             B->link_flag.push_back((uint8_t)(((filler || single) ? 1 : 0) | (filler ? 2 : 0)));
         }
     }
@@ -684,6 +787,8 @@ static ssb_fsg_built_t *fsg_finish(FsgWork &W, int start, int final)
     for (int s = 0; s < NS; ++s)
         for (int li : arcs[s]) {
             const FLink &l = W.pool[li];
+            if (l.wid < 0)
+                continue;
             if (W.silword[l.wid]) {
                 rcb[l.from][sil] = 1;
                 lcb[l.to][sil] = 1;
@@ -694,8 +799,21 @@ static ssb_fsg_built_t *fsg_finish(FsgWork &W, int start, int final)
             }
         }
     std::vector<std::vector<int>> lcl(NS), rcl(NS);
-    for (int s = 0; s < NS; ++s) {
+    for (int s = 0; s < NS; ++s)
         lcb[s][sil] = rcb[s][sil] = 1;
+    // contexts travel across null transitions, one sweep in state / arc order (ref :157-186;
+    // the grammar holds the closure of its null transitions)
+    for (int s = 0; s < NS; ++s)
+        for (int li : arcs[s]) {
+            const FLink &l = W.pool[li];
+            if (l.wid >= 0)
+                continue;
+            for (int i = 0; i < n_ci; ++i) {
+                lcb[l.to][i] |= lcb[l.from][i];
+                rcb[l.from][i] |= rcb[l.to][i];
+            }
+        }
+    for (int s = 0; s < NS; ++s) {
         for (int i = 0; i < n_ci; ++i) {
             if (lcb[s][i])
                 lcl[s].push_back(i);
@@ -722,6 +840,8 @@ static ssb_fsg_built_t *fsg_finish(FsgWork &W, int start, int final)
         auto add_ctxt = [&](int p, int c) { nd[p].ctxt[c >> 5] |= 1u << (c & 31); };
         for (int li : arcs[s]) {
             const FLink &l = W.pool[li];
+            if (l.wid < 0)
+                continue;  // null transitions have no HMMs (the search follows them: null_prop)
             const int32_t dw = dictwid_of_word[l.wid];
             const Word &w = lx->word[dw];
             const int pronlen = (int)w.ph.size();

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import soundswallower_b200 as ssb
-from conftest import GOLDEN, model_features
+from conftest import DATA, GOLDEN, model_features
 from test_oracle_fsg import graph_of
 
 pytestmark = pytest.mark.gpu
@@ -315,3 +315,20 @@ def test_dense_and_aligner_when_scores_tie(models, oracles, golden, kind):
         assert r["rv"] == w["rv"] and r["best_score"] == w["best_score"]
         if w["rv"] == 0:
             assert np.array_equal(r["start"], w["start"]) and np.array_equal(r["score"], w["score"])
+
+
+@pytest.mark.gpu
+def test_fsg_file_grammar_built_in_tree_decodes_like_the_reference(models, golden):
+    """Config #3's kind of grammar without the reference: goforward.fsg's transition list ->
+    ssb_fsg_build -> K4 on dense scores; history table, HMM evaluations, hypothesis score and
+    segmentation equal the reference's on decoder_set_fsg(fsg_model_readfile(...))."""
+    g = np.load(os.path.join(GOLDEN, "fsg_file_en-us.npz"))
+    m = models("en-us")
+    lx = ssb.Lexicon(m, hmmdir=model_dir("en-us"))
+    graph = lx.fsg_graph(*ssb.read_fsg_file(os.path.join(DATA, "goforward.fsg")))
+    r = ssb.fsg_batch(m, [golden["en-us"]["feat"]], [graph], want_hist=True, compallsen=True)[0]
+    assert r["rv"] == 0
+    assert np.array_equal(r["hist"], g["file_hist"])
+    assert r["n_hmm_eval"] == int(g["file_n_hmm_eval"]) and r["hyp_score"] == int(g["file_hyp_score"])
+    assert np.array_equal(r["segs"][:, 1:], g["file_segs"][:, 1:])
+    lx.close()

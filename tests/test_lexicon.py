@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import soundswallower_b200 as ssb
-from conftest import GOLDEN, chain_from_golden, model_dir
+from conftest import DATA, GOLDEN, chain_from_golden, model_dir
 
 
 @pytest.fixture(scope="module")
@@ -138,3 +138,31 @@ def test_align_graphs_agree_with_reference_when_present(lexicons):
             assert all(int(got[k]) == int(want[k]) for k in GRAPH_DIMS), text
             assert all(np.array_equal(got[k], want[k]) for k in GRAPH_KEYS), text
         r.close()
+
+
+# ------------------------------------------------------------------ general grammars (ssb_fsg_build)
+def test_fsg_file_graph_equals_reference():
+    """decoder_set_fsg on tests/data/goforward.fsg (word + null transitions, null closure,
+    silence / filler loops, lextree): ssb_fsg_build's arrays equal the reference's dump
+    (tests/golden/fsg_file_en-us.npz, tools/make_golden.py --fsg-file)."""
+    g = np.load(os.path.join(GOLDEN, "fsg_file_en-us.npz"))
+    m = ssb.AcousticModel(model_dir("en-us"), device=-1)
+    lx = ssb.Lexicon(m, hmmdir=model_dir("en-us"))
+    n_state, start, final, trans = ssb.read_fsg_file(os.path.join(DATA, "goforward.fsg"))
+    assert (n_state, start, final, len(trans)) == (7, 0, 6, 17) and trans[3][3] is None
+    got = lx.fsg_graph(n_state, start, final, trans)
+    for k in ("n_state", "start", "final", "n_ciphone", "sil", "beam", "pbeam", "wbeam", "maxhmmpf"):
+        assert int(got[k]) == int(g["file_" + k]), k
+    for k in GRAPH_KEYS:
+        assert np.array_equal(got[k], g["file_" + k]), k
+    assert (got["link"][:, 3] < 0).sum() == 2          # the two null transitions survive as links
+    with pytest.raises(ssb.SsbError, match="Unknown word"):
+        lx.fsg_graph(2, 0, 1, [(0, 1, 1.0, "xyzzyq")])
+    with pytest.raises(ssb.SsbError, match="probability"):
+        lx.fsg_graph(2, 0, 1, [(0, 1, 0.0, "go")])
+    # a chain of null transitions: the closure adds 0 -> 2
+    c = lx.fsg_graph(4, 0, 3, [(0, 1, 1.0, None), (1, 2, 0.5, None), (2, 3, 1.0, "go")])
+    nulls = {(int(l[0]), int(l[1])) for l in c["link"] if l[3] < 0}
+    assert nulls == {(0, 1), (1, 2), (0, 2)}
+    lx.close()
+    m.close()

@@ -181,6 +181,30 @@ def fsg(lang, raw_feat_key, text, gram):
     np.savez_compressed(os.path.join(OUT, "fsg_%s.npz" % lang), **g)
 
 
+def fsg_file(lang="en-us", fsgfile="goforward.fsg"):
+    """decoder_set_fsg on a text .fsg file (fsg_model_readfile: word + null transitions, null
+    closure): the flattened graph, and the history table / segmentation of the search on the test
+    utterance with dense scores -> fsg_file_<lang>.npz (checks ssb_fsg_build)."""
+    hmm = os.path.join(MODELS, lang)
+    ref = Ref(hmm, compallsen=True)
+    feat = np.load(os.path.join(OUT, "align_%s.npz" % lang))["feat"]
+    path = os.path.join(DATA, fsgfile)
+    g = {}
+    G = ref.fsg_graph(fsg_file=path)
+    for k, v in G.items():
+        g["file_%s" % k] = np.asarray(v)
+    d = ref.fsg_decode(feat)   # (the grammar selected above)
+    H = ref.fsg_history()
+    g["file_hist"] = H["hist"]
+    g["file_segs"] = d["segs"]
+    g["file_n_hmm_eval"] = np.int64(H["n_hmm_eval"])
+    g["file_hyp_score"] = np.int32(H["hyp_score"])
+    print(lang, fsgfile, "pnodes", len(G["pnode"]), "links", len(G["link"]), "hist", len(H["hist"]),
+          "hyp", H["hyp_score"])
+    ref.close()
+    np.savez_compressed(os.path.join(OUT, "fsg_file_%s.npz" % lang), **g)
+
+
 def hmm5(n_case=512, seed=55):
     """hmm_vit_eval_5st_lr / _3st_lr known answers on random left-to-right transition matrices
     (self loop, next, skip; 255 = impossible) -- no bundled model has 5-state HMMs -> hmm5.npz."""
@@ -516,6 +540,8 @@ def main():
         return cont()
     if "--lexicon" in sys.argv:
         return lexicon()
+    if "--fsg-file" in sys.argv:
+        return fsg_file()
     if "--hmm5" in sys.argv:
         return hmm5()
     if "--five-state" in sys.argv:
@@ -530,6 +556,7 @@ def main():
     fsg("fr-fr", "goforward_fr.raw", "avance de dix mètres", "goforward_fr.gram")
     fsg_active("en-us", "go forward ten meters", "goforward.gram")
     fsg_active("fr-fr", "avance de dix mètres", "goforward_fr.gram")
+    fsg_file()
     hmm5()
     five_state()
     loaders()
