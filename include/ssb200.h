@@ -119,7 +119,7 @@ void ssb_mgau_reset(ssb_mgau_t *mgau);
 void ssb_mgau_free(ssb_mgau_t *mgau);
 /* own != 0: the scorer owns its model, ssb_mgau_free (= vt->free, what acmod_free calls, ref:
  * src/acmod.c:278-279) releases both -- the lifetime ptm_mgau_init's object has in the reference
- * (integration/ssb_glue.c: ssb_ptm_mgau_init(acmod_t *)). */
+ * (see integration/ssb_glue.c, the reference-side binding). */
 void ssb_mgau_own_model(ssb_mgau_t *mgau, int own);
 
 /* ------------------------------------------------------------------ */

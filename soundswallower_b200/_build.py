@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libssb200.so")
-SOURCES = ["model.cpp", "lexicon.cpp", "gmm_topn.cu", "gmm_topn_tc.cu", "gmm_topn_tc2.cu", "gmm_scan_ft.cu", "senone_mix.cu", "cont_score.cu", "chain_viterbi.cu", "fsg_search.cu", "topn_fixup.cu", "frontend.cu", "api.cu", "search.cpp", "align_texts.cpp"]
+SOURCES = ["model.cpp", "lexicon.cpp", "gmm_topn.cu", "gmm_topn_tc2.cu", "gmm_scan_ft.cu", "senone_mix.cu", "cont_score.cu", "chain_viterbi.cu", "fsg_search.cu", "topn_fixup.cu", "frontend.cu", "api.cu", "search.cpp", "align_texts.cpp"]
 HEADERS = ["model.h", "device.cuh", "tc_common.cuh", "hmm_step.cuh", os.path.join("..", "..", "include", "ssb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

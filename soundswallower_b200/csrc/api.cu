@@ -840,7 +840,7 @@ extern "C" int ssb_plan_chain(int32_t np, int32_t T, const int32_t *sf, const in
 }
 
 // K1 kernel choice: the frame-tiled tcgen05 kernel (gmm_scan_ft.cu) unless $SSB_K1 names another
-// one (tc2 / tc1 / fp32: earlier kernels, kept for A/B runs)
+// one (tc2 / fp32: kept for A/B runs)
 static bool k1_frame_tiled(const DevModel &d)
 {
     const char *k1 = getenv("SSB_K1");

@@ -356,7 +356,7 @@ int launch_gmm_topn(const DevModel &m, const DevPlan &p, const float *feat, int6
     // default: tensor-core screening kernel (gmm_topn_tc.cu); SSB_K1=fp32 keeps the plain
     // CUDA-core scan below (same results, used for A/B timing and as the generic-shape path)
     const char *force = getenv("SSB_K1");
-    if (tc_supported(m) && !(force && strcmp(force, "fp32") == 0))
+    if (tc_supported(m) && m.ds <= 1 && featp != nullptr && !(force && strcmp(force, "fp32") == 0))
         return launch_gmm_topn_tc(m, p, feat, n_frames, tn_score, tn_cw, featp, nullptr, nullptr,
                                   nullptr, st);
     bool all13 = true;

@@ -637,6 +637,32 @@ int launch_gmm_topn_tc2(const DevModel &m, const DevPlan &p, const float *feat, 
     return 0;
 }
 
+bool tc_supported(const DevModel &m)
+{
+    if (m.n_density != TC_ND || m.gB == nullptr || m.kind != SSB_SCORER_PTM)
+        return false;
+    for (int f = 0; f < m.n_feat; ++f)
+        if (m.featlen[f] != TC_L)
+            return false;
+    return true;
+}
+
+// dispatcher kept from the time when two tensor-core kernels existed (the v1 kernel, single
+// TF32 + carried-list threshold, is gone: 61 ms against 27 ms on config #2)
+int launch_gmm_topn_tc(const DevModel &m, const DevPlan &p, const float *feat, int64_t n_frames,
+                       int4 *tn_score, uchar4 *tn_cw, float *featp, float *dbg_approx,
+                       float *dbg_eps, unsigned long long *dbg_counters, cudaStream_t st)
+{
+    if (p.n_utts == 0 || n_frames == 0)
+        return 0;
+    if (!tc_supported(m) || m.ds > 1 || featp == nullptr) {
+        set_error("tensor-core top-N needs 128 densities, 13-wide streams and ds = 1");
+        return -1;
+    }
+    TcDebug dbg{dbg_approx, dbg_eps, dbg_counters};
+    return launch_gmm_topn_tc2(m, p, feat, n_frames, tn_score, tn_cw, featp, dbg, st);
+}
+
 size_t tc2_featp_bytes(const DevModel &m, int64_t n_frames)
 {
     const char *pk = getenv("SSB_K1_PACK");
