@@ -69,8 +69,16 @@ def test_fsg_ragged_two_grammars(models, oracles, golden, fsg_golden):
 def test_fsg_history_overflow_and_bad_graph(models, golden, fsg_golden):
     m, g = models("en-us"), fsg_golden["en-us"]
     feat = golden["en-us"]["feat"]
-    r = ssb.fsg_batch(m, [feat[:60]], [graph_of(g, "align")], hist_cap=16)[0]
+    # the raw call reports the overflow (rv == -2); the public wrapper repeats with a larger table
+    # (the reference's history is unbounded) and gives the unlimited answer
+    r = ssb._fsg_batch_once(m, [feat[:60]], [graph_of(g, "align")], hist_cap=16)[0]
     assert r["rv"] == -2
+    r = ssb.fsg_batch(m, [feat[:60]], [graph_of(g, "align")], hist_cap=16, want_hist=True)[0]
+    w = ssb.fsg_batch(m, [feat[:60]], [graph_of(g, "align")], want_hist=True)[0]
+    assert r["rv"] == 0 and np.array_equal(r["hist"], w["hist"]) and r["hyp_score"] == w["hyp_score"]
+    # a segmentation longer than max_seg: asked again, not silently empty
+    r = ssb.fsg_batch(m, [feat], [graph_of(g, "align")], max_seg=2)[0]
+    assert r["n_seg"] == len(r["segs"]) > 2
     bad = dict(graph_of(g, "align"))
     bad["pnode"] = bad["pnode"].copy()
     bad["pnode"][3, 0] = m.n_sseq + 5

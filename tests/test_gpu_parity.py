@@ -365,8 +365,8 @@ def test_align_states_off_path_keep_caller_values(models, golden):
     # gmm_topn_tc2, senone_mix, chain_viterbi, backtrace (+ pack_features with SSB_K1_PACK=1,
     # + topn_fixup when segmented)
     # (the frame-tiled K1 always runs the tie fix-up: 5 launches)
-    tc2 = os.environ.get("SSB_K1") == "tc2"
-    assert b.n_launches() == (4 + bool(os.environ.get("SSB_K1_SEG")) + (os.environ.get("SSB_K1_PACK") == "1") if tc2 else 5)
+    ft = os.environ.get("SSB_K1") == "ft"
+    assert b.n_launches() == (5 if ft else 4 + bool(os.environ.get("SSB_K1_SEG")) + (os.environ.get("SSB_K1_PACK") == "1"))
     ms = b.kernel_ms()
     assert ms["total"] > 0
     st = b.stats()
