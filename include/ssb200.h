@@ -208,6 +208,14 @@ int64_t ssb_batch_band_state_frames(const ssb_batch_t *b);
 /* upload + run + download in one call (the call a host program makes).  A batch of at least
  * two chunks (see ssb_pipeline_create) is routed through a temporary pipeline. */
 int ssb_align_batch(ssb_model_t *m, const ssb_align_in_t *in, ssb_align_out_t *out);
+/* The same batch over several GPUs of one box (the path shards by utterance, no
+ * exchange step): models[d] = the model loaded on device d (ssb_config_t.device); one host
+ * thread per GPU takes a contiguous range of utterances with about 1/n of the frames -- slices
+ * of the caller's arrays, nothing is re-packed -- through its own pipeline and writes its part
+ * of `out`.  No collective; results are those of ssb_align_batch on one device.  The debug
+ * outputs (chain_scr, tokens) must be NULL. */
+int ssb_align_batch_multi(ssb_model_t *const *models, int32_t n_models, const ssb_align_in_t *in,
+                          ssb_align_out_t *out);
 
 /* The same call for callers that keep coming back (a server, a long file list): device
  * buffers are kept between calls and a large batch is cut into chunks of whole utterances

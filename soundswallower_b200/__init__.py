@@ -25,7 +25,7 @@ MODEL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "model")
 
 __all__ = ["AcousticModel", "PtmMgau", "StateAlignBatch", "align_batch", "score_batch",
            "topn_batch", "tc_probe", "fsg_batch", "hmm_vit_eval", "windows", "plan_chain", "propagate", "flags2list", "device_count",
-           "Frontend", "DeviceFeatures", "Lexicon", "read_fsg_file", "align_texts", "SsbError", "Config", "MODEL_DIR", "INT_MAX", "WORST_SCORE"]
+           "align_batch_multi", "Frontend", "DeviceFeatures", "Lexicon", "read_fsg_file", "align_texts", "SsbError", "Config", "MODEL_DIR", "INT_MAX", "WORST_SCORE"]
 
 
 def _ptr(a, t=None):
@@ -483,6 +483,18 @@ def align_batch(model, feats, chains, init_active=None, compallsen=False, want_c
     b = _AlignCall(model)
     b.upload(feats, chains, init_active=init_active, compallsen=compallsen, init_topn=init_topn)
     return b.per_utt(b.align(want_chain_scr=want_chain_scr, want_tokens=want_tokens))
+
+
+def align_batch_multi(models, feats, chains, init_active=None, compallsen=False, init_topn=None):
+    """ssb_align_batch_multi: the batch over several GPUs of one box, models[d] loaded on device d
+    (one host thread per GPU inside the C call, contiguous utterance ranges, no collective)."""
+    b = _AlignCall(models[0])
+    b.upload(feats, chains, init_active=init_active, compallsen=compallsen, init_topn=init_topn)
+    o, res = b._align_out(False, False, None)
+    hs = (C.c_void_p * len(models))(*[m.h for m in models])
+    _lib.check(models[0].lib.ssb_align_batch_multi(hs, len(models), C.byref(b._in), C.byref(o)),
+               "ssb_align_batch_multi")
+    return b.per_utt(res)
 
 
 def score_batch(model, feats, want=True):

@@ -17,6 +17,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "device.cuh"
@@ -849,6 +850,23 @@ static bool k1_frame_tiled(const DevModel &d)
     return false;  // TODO default once the parity suite is green
 }
 
+// Planner threads of one batch: the host's cores are shared by the ranks / device threads of a
+// box (8 GPUs x 16 threads on 32 cores cost 5 % end to end in round 1), so: cores / local ranks,
+// at most 16.  $SSB_PLAN_THREADS overrides; torchrun exports LOCAL_WORLD_SIZE;
+// ssb_align_batch_multi sets the divisor for its device threads.
+static std::atomic<int> g_plan_divisor{1};
+static int planner_threads()
+{
+    if (const char *e = getenv("SSB_PLAN_THREADS"))
+        if (atoi(e) > 0)
+            return atoi(e);
+    int div = g_plan_divisor.load();
+    if (const char *e = getenv("LOCAL_WORLD_SIZE"))
+        div = std::max(div, atoi(e));
+    const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+    return std::max(1, std::min(16, hw / std::max(1, div)));
+}
+
 // ---- host planner --------------------------------------------------------------------------
 // Per-utterance plan pieces produced by one worker for a contiguous range of utterances;
 // offsets are local to the piece and rebased when the pieces are concatenated.
@@ -893,6 +911,15 @@ void plan_range(const HostModel &h, const ssb_align_in_t *in, const std::vector<
 {
     const int E = h.n_emit, n_sen = h.n_sen, nw = (n_sen + 31) / 32;
     PlanScratch S(n_sen);
+    // Utterances with the same chain, windows, length and initial flags get the same plan (many
+    // readers of one text, the benchmark's tiled sentence): planned once per worker, then copied.
+    struct Done {
+        int u;
+        size_t ep0, n_ep, sl0, n_sl, us0;
+        int n_us;
+        int64_t act, scan, band;
+    };
+    std::unordered_map<uint64_t, Done> seen;
     for (int u = u0; u < u1; ++u) {
         const int64_t p0 = phone_off[u];
         const int T = (int)(frame_off[u + 1] - frame_off[u]);
@@ -900,6 +927,58 @@ void plan_range(const HostModel &h, const ssb_align_in_t *in, const std::vector<
         const int32_t *ssid = in->ssid + p0, *sf = in->sf + p0, *ef = in->ef + p0;
         int32_t *enter = enter_all + p0;
         uint16_t *st_slot = st_slot_all + p0 * E;
+        uint64_t key = 1469598103934665603ull;
+        auto mix = [&key](const void *ptr, size_t n) {
+            const unsigned char *b = static_cast<const unsigned char *>(ptr);
+            for (size_t i = 0; i < n; ++i)
+                key = (key ^ b[i]) * 1099511628211ull;
+        };
+        mix(&T, sizeof T);
+        mix(&np, sizeof np);
+        mix(ssid, (size_t)np * 4);
+        mix(sf, (size_t)np * 4);
+        mix(ef, (size_t)np * 4);
+        if (in->init_active)
+            mix(in->init_active + (size_t)u * nw, (size_t)nw * 4);
+        if (!in->compallsen) {
+            auto it = seen.find(key);
+            if (it != seen.end()) {
+                const Done &d = it->second;
+                const int64_t q0 = phone_off[d.u];
+                const bool same = (int)(phone_off[d.u + 1] - q0) == np
+                                  && (int)(frame_off[d.u + 1] - frame_off[d.u]) == T
+                                  && std::memcmp(in->ssid + q0, ssid, (size_t)np * 4) == 0
+                                  && std::memcmp(in->sf + q0, sf, (size_t)np * 4) == 0
+                                  && std::memcmp(in->ef + q0, ef, (size_t)np * 4) == 0
+                                  && (!in->init_active
+                                      || std::memcmp(in->init_active + (size_t)d.u * nw,
+                                                     in->init_active + (size_t)u * nw, (size_t)nw * 4) == 0);
+                if (same) {
+                    std::memcpy(enter, enter_all + q0, (size_t)np * 4);
+                    std::memcpy(st_slot, st_slot_all + q0 * E, (size_t)np * E * 2);
+                    // (copy by index: the vectors may reallocate while they grow)
+                    for (size_t k = 0; k < d.n_ep; ++k) {
+                        out.ep_start.push_back(out.ep_start[d.ep0 + k]);
+                        out.ep_slot_len.push_back(out.ep_slot_len[d.ep0 + k]);
+                        for (int w = 0; w < 8; ++w)
+                            out.ep_cbmask.push_back(out.ep_cbmask[(d.ep0 + k) * 8 + w]);
+                    }
+                    for (size_t k = 0; k < d.n_sl; ++k)
+                        out.ep_slot.push_back(out.ep_slot[d.sl0 + k]);
+                    for (int k = 0; k < d.n_us; ++k)
+                        out.usen.push_back(out.usen[d.us0 + k]);
+                    out.ep_count.push_back((int32_t)d.n_ep);
+                    out.us_count.push_back(d.n_us);
+                    out.active_sen_frames += d.act;
+                    out.scanned_cb_frames += d.scan;
+                    out.band_state_frames += d.band;
+                    continue;
+                }
+            }
+        }
+        const size_t rec_ep0 = out.ep_start.size(), rec_sl0 = out.ep_slot.size(), rec_us0 = out.usen.size();
+        const int64_t rec_act = out.active_sen_frames, rec_scan = out.scanned_cb_frames,
+                      rec_band = out.band_state_frames;
         plan_enter(np, T, sf, ef, enter);
         // state-frames the chain Viterbi evaluates: phone i on frames [enter, max(enter, ef)]
         for (int i = 0; i < np; ++i)
@@ -1005,6 +1084,9 @@ void plan_range(const HostModel &h, const ssb_align_in_t *in, const std::vector<
             S.mark[s] = 0;
         for (uint16_t s : S.uni)
             S.umark[s] = 0;
+        seen[key] = Done{u, rec_ep0, out.ep_start.size() - rec_ep0, rec_sl0, out.ep_slot.size() - rec_sl0,
+                         rec_us0, n_us, out.active_sen_frames - rec_act, out.scanned_cb_frames - rec_scan,
+                         out.band_state_frames - rec_band};
     }
 }
 }  // namespace
@@ -1123,7 +1205,7 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
     const auto t_plan0 = std::chrono::steady_clock::now();
     b->enter.assign((size_t)b->n_phones, -1);
     std::vector<uint16_t> st_slot((size_t)b->n_states, 0);
-    int n_workers = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+    int n_workers = planner_threads();
     n_workers = std::max(1, std::min(n_workers, U / 64));
     std::vector<PlanPiece> pieces(n_workers);
     {
@@ -1915,6 +1997,91 @@ extern "C" int ssb_align_batch(ssb_model_t *m, const ssb_align_in_t *in, ssb_ali
         rv = ssb_batch_download(b, out);
     ssb_batch_free(b);
     return rv;
+}
+
+// ------------------------------------------------------------------ several GPUs of one box
+// The path shards by utterance and has no exchange step: one host thread per GPU,
+// each with its device's model, a contiguous range of utterances balanced by frames (slices of
+// the caller's arrays: nothing is copied or re-packed), its own pipeline; results land in the
+// caller's output arrays directly.  No collective.
+extern "C" int ssb_align_batch_multi(ssb_model_t *const *models, int32_t n_models,
+                                     const ssb_align_in_t *in, ssb_align_out_t *out)
+{
+    if (!models || n_models <= 0 || !in || !out || in->n_utts < 0 || (in->n_utts > 0 && (!in->frame_off || !in->phone_off))) {
+        set_error("ssb_align_batch_multi: bad arguments");
+        return -1;
+    }
+    for (int d = 0; d < n_models; ++d)
+        if (!models[d] || models[d]->h.n_emit != models[0]->h.n_emit || models[d]->h.n_sen != models[0]->h.n_sen) {
+            set_error("ssb_align_batch_multi: model %d missing or different from model 0", d);
+            return -1;
+        }
+    if (n_models == 1 || in->n_utts < 2)
+        return ssb_align_batch(models[0], in, out);
+    if (out->chain_scr || out->tokens) {
+        set_error("ssb_align_batch_multi: debug outputs (chain_scr, tokens) are single-device only");
+        return -1;
+    }
+    const int U = in->n_utts, E = models[0]->h.n_emit, nw = (models[0]->h.n_sen + 31) / 32;
+    const int CS = models[0]->h.n_mgau * models[0]->h.n_feat, blk = models[0]->h.blk;
+    // contiguous ranges with about the same number of frames
+    std::vector<int> cut(n_models + 1, U);
+    cut[0] = 0;
+    const int64_t G = in->frame_off[U];
+    for (int d = 1, u = 0; d < n_models; ++d) {
+        while (u < U && in->frame_off[u] < G * d / n_models)
+            ++u;
+        cut[d] = u;
+    }
+    std::vector<int> rv(n_models, 0);
+    std::vector<std::string> err(n_models);
+    std::vector<std::thread> th;
+    g_plan_divisor.store(n_models);
+    for (int d = 0; d < n_models; ++d) {
+        th.emplace_back([&, d] {
+            const int a = cut[d], b = cut[d + 1];
+            if (b <= a)
+                return;
+            const int n = b - a;
+            std::vector<int64_t> fo(n + 1), po(n + 1);
+            for (int i = 0; i <= n; ++i) {
+                fo[i] = in->frame_off[a + i] - in->frame_off[a];
+                po[i] = in->phone_off[a + i] - in->phone_off[a];
+            }
+            const int64_t f0 = in->frame_off[a], p0 = in->phone_off[a];
+            ssb_align_in_t si = *in;
+            si.n_utts = n;
+            si.feat = in->feat + f0 * blk;
+            si.frame_off = fo.data();
+            si.phone_off = po.data();
+            si.ssid = in->ssid + p0;
+            si.tmat = in->tmat + p0;
+            si.sf = in->sf + p0;
+            si.ef = in->ef + p0;
+            si.init_active = in->init_active ? in->init_active + (size_t)a * nw : nullptr;
+            si.init_topn = in->init_topn ? in->init_topn + (size_t)a * CS * 4 : nullptr;
+            ssb_align_out_t so = *out;
+            so.st_start = out->st_start ? out->st_start + p0 * E : nullptr;
+            so.st_dur = out->st_dur ? out->st_dur + p0 * E : nullptr;
+            so.st_score = out->st_score ? out->st_score + p0 * E : nullptr;
+            so.utt_rv = out->utt_rv ? out->utt_rv + a : nullptr;
+            so.utt_best = out->utt_best ? out->utt_best + a : nullptr;
+            so.utt_renorm = out->utt_renorm ? out->utt_renorm + a : nullptr;
+            cudaSetDevice(models[d]->device);
+            rv[d] = ssb_align_batch(models[d], &si, &so);
+            if (rv[d] != 0)
+                err[d] = ssb::last_error();  // (the error text is per thread)
+        });
+    }
+    for (auto &t : th)
+        t.join();
+    g_plan_divisor.store(1);
+    for (int d = 0; d < n_models; ++d)
+        if (rv[d] != 0) {
+            set_error("device %d: %s", models[d]->device, err[d].c_str());
+            return -1;
+        }
+    return 0;
 }
 
 // ------------------------------------------------------------------ dense scoring
