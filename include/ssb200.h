@@ -187,9 +187,13 @@ int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in);
 int ssb_batch_run(ssb_batch_t *b);
 /* device->host copies of the results; synchronises */
 int ssb_batch_download(ssb_batch_t *b, ssb_align_out_t *out);
-/* keep the whole token stack ({-1,-1} where the reference records nothing) so that
- * ssb_batch_download can return it; off by default (only tokens of evaluated states
- * are written).  Call before ssb_batch_run. */
+/* Debug outputs.  By default chain scores and tokens are kept BANDED: every phone keeps only the
+ * frames it can be evaluated on (the reference's dense [T][n_states] token stack is its memory
+ * hazard -- 86 GB for one hour, SURVEY section 5 -- and 98 % of it is never touched inside word
+ * windows), and ssb_batch_download cannot return them.  on & 1: keep the whole dense token stack
+ * ({-1,-1} where the reference records nothing); on & 2: keep the dense chain scores.  Call
+ * before ssb_batch_upload.  (ssb_align_batch / the pipeline do this themselves when the
+ * output struct asks for chain_scr / tokens.) */
 int ssb_batch_debug_tokens(ssb_batch_t *b, int on);
 /* CUDA-event durations (ms) of the kernels of the last ssb_batch_run:
  * [0] gmm_topn [1] senone_mix [2] chain_viterbi [3] backtrace [4] whole run; synchronises */

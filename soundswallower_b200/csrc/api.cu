@@ -711,7 +711,10 @@ struct ssb_batch_s {
     int64_t plan_us = 0;  // host time of the last upload's planning + staging calls
     int max_phones = 0, max_union = 0, max_T = 0;
     int compallsen = 0;
-    bool want_tokens_all = false;
+    bool want_tokens_all = false;  // debug: dense token stack, pre-filled, downloadable
+    bool want_dense = false;       // debug: dense chain scores / tokens (the reference's layout)
+    bool banded = false;           // chain_scr / tokens keep only the evaluated band (DevPlan.banded)
+    int64_t n_band_scr = 0, n_band_tok = 0;
     std::vector<int64_t> frame_off, phone_off, scr_off;
     std::vector<int32_t> enter;
     // device
@@ -732,6 +735,7 @@ struct ssb_batch_s {
     bool ft = false;
     int n_tiles = 0;
     DBuf d_tile_utt, d_tile_t0, d_tile_ctr;
+    DBuf d_scr_boff, d_tok_boff;
     // timing
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int n_launches = 0;
@@ -745,7 +749,7 @@ struct ssb_batch_s {
                              &utt_best, &utt_renorm, &fin_hist, &fin_score, &dense, &best_tmp,
                              &d_k1_frame_off, &d_k1_ep_off, &d_k1_ep_start, &d_k1_ep_cbmask,
                              &d_seg_utts, &d_k1_tie, &d_init_topn, &d_tile_utt, &d_tile_t0,
-                             &d_tile_ctr};
+                             &d_tile_ctr, &d_scr_boff, &d_tok_boff};
         size_t n = 0;
         for (const DBuf *b : all)
             n += b->cap;
@@ -759,7 +763,7 @@ struct ssb_batch_s {
                        &d_st_slot, &d_enter, &st_start, &st_dur, &st_score, &utt_rv, &utt_best,
                        &utt_renorm, &fin_hist, &fin_score, &dense, &best_tmp, &d_k1_frame_off,
                        &d_k1_ep_off, &d_k1_ep_start, &d_k1_ep_cbmask, &d_seg_utts, &d_k1_tie,
-                       &d_init_topn, &d_tile_utt, &d_tile_t0, &d_tile_ctr};
+                       &d_init_topn, &d_tile_utt, &d_tile_t0, &d_tile_ctr, &d_scr_boff, &d_tok_boff};
         for (DBuf *b : all)
             b->release();
     }
@@ -1160,6 +1164,14 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
     }
     b->n_state_frames = b->scr_off[U];
 
+    // chain scores / tokens: banded (only the frames a phone can be evaluated on) unless the caller
+    // wants the reference's dense arrays back (debug outputs) or the scoring path is one that
+    // writes dense rows (compallsen gather, the continuous scorer)
+    {
+        const char *e = getenv("SSB_BANDED");
+        b->banded = !b->want_dense && !b->want_tokens_all && !b->compallsen && h.kind != SSB_SCORER_CONT
+                    && !(e && *e == '0');
+    }
     // ---- device buffers; the feature copy starts now and overlaps the planning below
     cudaStream_t st = b->st;
     // buffers that have to grow go back to the block cache: nothing of the previous run may
@@ -1171,8 +1183,6 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
         || (tc_supported(b->m->d) && b->featp.ensure(std::max<size_t>(tc2_featp_bytes(b->m->d, G), 16)) != 0)
         || b->tn_s.ensure(std::max<size_t>((size_t)G * CS * sizeof(int4), 16)) != 0
         || b->tn_c.ensure(std::max<size_t>((size_t)G * CS * sizeof(uchar4), 16)) != 0
-        || b->chain_scr.ensure(std::max<size_t>((size_t)b->n_state_frames * 2, 16)) != 0
-        || b->tokens.ensure(std::max<size_t>((size_t)b->n_state_frames * sizeof(int2), 16)) != 0
         || b->st_start.ensure(std::max<size_t>((size_t)b->n_states * 4, 16)) != 0
         || b->st_dur.ensure(std::max<size_t>((size_t)b->n_states * 4, 16)) != 0
         || b->st_score.ensure(std::max<size_t>((size_t)b->n_states * 4, 16)) != 0
@@ -1246,6 +1256,43 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
         set_error("active-list plan too large; split the batch");
         return -1;
     }
+    // ---- chain scores and token stack
+    b->n_band_scr = b->n_band_tok = 0;
+    if (b->banded) {
+        std::vector<int64_t> sb((size_t)b->n_phones + 1, 0), tb((size_t)b->n_phones + 1, 0);
+        int64_t ns = 0, nt = 0;
+        for (int u = 0; u < U; ++u) {
+            const int64_t p0 = b->phone_off[u];
+            const int np = (int)(b->phone_off[u + 1] - p0);
+            const int T = (int)(b->frame_off[u + 1] - b->frame_off[u]);
+            for (int i = 0; i < np; ++i) {
+                const int32_t en = b->enter[p0 + i];
+                sb[p0 + i] = ns;
+                tb[p0 + i] = nt;
+                if (en < 0 || T == 0)
+                    continue;
+                const int64_t last = std::min<int64_t>(std::max(en, in->ef[p0 + i]), T - 1);
+                const int64_t first = std::max(en - 1, 0);
+                sb[p0 + i] = ns - (int64_t)en * E;   // virtual bases: element (t, j) at base + t * E + j
+                tb[p0 + i] = nt - first * E;
+                if (en <= T - 1)
+                    ns += (last - en + 1) * E;
+                if (last >= first)
+                    nt += (last - first + 1) * E;
+            }
+        }
+        b->n_band_scr = ns;
+        b->n_band_tok = nt;
+        if (upload(b->d_scr_boff, sb, st) || upload(b->d_tok_boff, tb, st))
+            return -1;
+    }
+    {
+        const size_t n_scr = b->banded ? (size_t)b->n_band_scr : (size_t)b->n_state_frames;
+        const size_t n_tok = b->banded ? (size_t)b->n_band_tok : (size_t)b->n_state_frames;
+        if (b->chain_scr.ensure(std::max<size_t>(n_scr * 2, 16)) != 0
+            || b->tokens.ensure(std::max<size_t>(n_tok * sizeof(int2), 16)) != 0)
+            return -1;
+    }
     std::vector<int32_t> v_ssid(in->ssid, in->ssid + b->n_phones),
         v_tmat(in->tmat, in->tmat + b->n_phones), v_sf(in->sf, in->sf + b->n_phones),
         v_ef(in->ef, in->ef + b->n_phones);
@@ -1281,6 +1328,9 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
     p.st_slot = b->d_st_slot.as<uint16_t>();
     p.enter_plan = b->d_enter.as<int32_t>();
     p.all_active = b->compallsen;
+    p.banded = b->banded ? 1 : 0;
+    p.scr_boff = b->banded ? b->d_scr_boff.as<int64_t>() : nullptr;
+    p.tok_boff = b->banded ? b->d_tok_boff.as<int64_t>() : nullptr;
     p.tie_bits = nullptr;
     p.tie_w = 0;
     p.init_topn = nullptr;
@@ -1555,6 +1605,11 @@ extern "C" int ssb_batch_download(ssb_batch_t *b, ssb_align_out_t *out)
         API_CUDA(cudaMemcpyAsync(out->utt_best, b->utt_best.p, (size_t)U * 4, cudaMemcpyDeviceToHost, st), -1);
     if (U && out->utt_renorm)
         API_CUDA(cudaMemcpyAsync(out->utt_renorm, b->utt_renorm.p, (size_t)U * 4, cudaMemcpyDeviceToHost, st), -1);
+    if (b->banded && b->n_state_frames && (out->chain_scr || out->tokens)) {
+        set_error("dense chain scores / tokens were not kept (banded layout): call "
+                  "ssb_batch_debug_tokens(b, 1) before ssb_batch_upload");
+        return -1;
+    }
     if (b->n_state_frames && out->chain_scr)
         API_CUDA(cudaMemcpyAsync(out->chain_scr, b->chain_scr.p, (size_t)b->n_state_frames * 2,
                                  cudaMemcpyDeviceToHost, st), -1);
@@ -1588,7 +1643,10 @@ extern "C" int ssb_batch_debug_tokens(ssb_batch_t *b, int on)
 {
     if (!b)
         return -1;
-    b->want_tokens_all = on != 0;
+    // bit 0: dense token stack, pre-filled with the reference's 0xff (downloadable);
+    // bit 1: dense chain scores only.  Either keeps the reference's dense [T][states] layout.
+    b->want_tokens_all = (on & 1) != 0;
+    b->want_dense = on != 0;
     return 0;
 }
 
@@ -1710,7 +1768,7 @@ static void pipe_worker(ssb_pipeline_s *p, int li)
             lk.unlock();
             tr[2] = now_ms();
             if (!skip) {
-                ssb_batch_debug_tokens(b, job->out.tokens ? 1 : 0);
+                ssb_batch_debug_tokens(b, (job->out.tokens ? 1 : 0) | (job->out.chain_scr ? 2 : 0));
                 rv = ssb_batch_upload(b, &job->in);
             }
             lk.lock();
@@ -1988,8 +2046,8 @@ extern "C" int ssb_align_batch(ssb_model_t *m, const ssb_align_in_t *in, ssb_ali
     ssb_batch_t *b = ssb_batch_create(m, nullptr);
     if (!b)
         return -1;
-    if (out && out->tokens)
-        ssb_batch_debug_tokens(b, 1);
+    if (out && (out->tokens || out->chain_scr))
+        ssb_batch_debug_tokens(b, (out->tokens ? 1 : 0) | (out->chain_scr ? 2 : 0));
     int rv = ssb_batch_upload(b, in);
     if (rv == 0)
         rv = ssb_batch_run(b);

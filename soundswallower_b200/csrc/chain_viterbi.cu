@@ -148,9 +148,16 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
                     s[j] = sc[j * np + i];
                     h[j] = hi[j * np + i];
                 }
+                if (p.banded) {
+                    const int16_t *sp = chain_scr + p.scr_boff[ph0 + i] + (int64_t)t * E;
 #pragma unroll
-                for (int j = 0; j < E; ++j)
-                    ss[j] = scr_t[i * E + j];
+                    for (int j = 0; j < E; ++j)
+                        ss[j] = sp[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < E; ++j)
+                        ss[j] = scr_t[i * E + j];
+                }
                 int32_t b = hmm_step<E>(m.tp + (size_t)tmat[i] * E * (E + 1), ss, s, h, o_s, o_h);
                 lb = max(lb, b);
 #pragma unroll
@@ -199,10 +206,13 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
                 }
             }
             if (now) {
+                int2 *tk = tok_t + i * E;
+                if (p.banded)
+                    tk = tokens + p.tok_boff[ph0 + i] + (int64_t)t * E;
 #pragma unroll
                 for (int j = 0; j < E; ++j) {
                     const int si = i * E + j;
-                    tok_t[si] = make_int2(hi[j * np + i], sc[j * np + i]);
+                    tk[j] = make_int2(hi[j * np + i], sc[j * np + i]);
                     hi[j * np + i] = si;
                 }
             }
@@ -303,6 +313,8 @@ backtrace_kernel(DevModel m, DevPlan p, const int2 *__restrict__ tokens,
             const bool missing = en < 0 || en > fr + 1 || (en <= fr && fr > max(en, efp));
             if (missing)
                 tk.x = -1;
+            else if (p.banded)
+                tk = tokens[p.tok_boff[p.phone_off[u] + ph] + (int64_t)fr * m.n_emit + (cur_id - ph * m.n_emit)];
             else
                 tk = tok[(int64_t)fr * ns + cur_id];
             event = tk.x != cur_id;

@@ -111,6 +111,17 @@ struct DevPlan {
     // a first pass on the same decoder left: the lists are not reset between passes, ref:
     // src/ptm_mgau.c:426-440); null = the initial lists (codewords 0..N-1)
     const uchar4 *init_topn;
+    // banded layout of chain_scr / tokens (the reference's dense [T][n_states] stack is its memory
+    // hazard: 86 GB for an hour): phone i keeps only the frames it can be
+    // evaluated on, as one contiguous block per phone
+    //   scores: frames [enter[i], last[i]]           at chain_scr + scr_boff[i] + t * E + j
+    //   tokens: frames [max(enter[i]-1, 0), last[i]] at tokens + tok_boff[i] + t * E + j
+    // with last[i] = min(max(enter[i], ef[i]), T-1); the offsets are absolute (whole batch), per
+    // phone, and VIRTUAL: block start minus (first frame) * E, so that no kernel needs the first
+    // frame to address a block
+    int32_t banded;
+    const int64_t *scr_boff;
+    const int64_t *tok_boff;
 };
 
 // ---- kernel launchers (each returns 0 or -1 with the error set) ----

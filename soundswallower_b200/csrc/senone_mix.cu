@@ -121,6 +121,34 @@ senone_mix_active_kernel(DevModel m, DevPlan p, const int4 *__restrict__ tn_s,
     uint32_t okmask = 0;  // bit it: codebook of this lane's it-th codebook-stream is active
     int sl0 = 0, na = 0;
     bool fresh = true;
+    int b_lo = 0, b_hi = -1;  // banded layout: phones [b_lo, b_hi] are evaluated on the warp's frame
+    const int per_round = 32 / m.n_emit;
+    const int lane_ph = (int)((lane + 0.5f) / (float)m.n_emit), lane_j = lane - lane_ph * m.n_emit;
+    if (p.banded) {
+        // first frame of this warp: binary search for the last phone entered by then
+        const int np = ns / m.n_emit, t = t_begin + warp;
+        const int32_t *enter = p.enter_plan + ph0, *ef = p.ef + ph0;
+        int a = 0, b = np;
+        while (a < b) {
+            const int mid = (a + b) >> 1;
+            const int en = enter[mid];
+            if (en >= 0 && en <= t)
+                a = mid + 1;
+            else
+                b = mid;
+        }
+        b_hi = a - 1;
+        a = 0;
+        b = b_hi + 1;
+        while (a < b) {
+            const int mid = (a + b) >> 1;
+            if (max(enter[mid], ef[mid]) >= t)
+                b = mid;
+            else
+                a = mid + 1;
+        }
+        b_lo = a;
+    }
     for (int t = t_begin + warp; t < t_end; t += K2_WARPS) {
         while (e + 1 < e1 && p.ep_start[e + 1] <= t) {
             ++e;
@@ -230,9 +258,34 @@ senone_mix_active_kernel(DevModel m, DevPlan p, const int4 *__restrict__ tn_s,
         // semi-continuous scorer does not normalise over senones)
         {
             const int16_t b16 = (!PTM4 && m.kind == SSB_SCORER_SEMI) ? (int16_t)0 : (int16_t)local_best;
-            int16_t *dst = chain_scr + p.scr_off[u] + (int64_t)t * ns;
-            for (int si = lane; si < ns; si += 32)
-                dst[si] = (int16_t)(wscr[st_slot[si]] - b16);
+            if (!p.banded) {
+                int16_t *dst = chain_scr + p.scr_off[u] + (int64_t)t * ns;
+                for (int si = lane; si < ns; si += 32)
+                    dst[si] = (int16_t)(wscr[st_slot[si]] - b16);
+            } else {
+                // only the phones the chain Viterbi evaluates on frame t: enter[i] <= t <= last[i];
+                // both bounds are non-decreasing along the entered prefix of the chain, and the
+                // warp's frames only go forward: two running pointers
+                const int E = m.n_emit, np = ns / E;
+                const int32_t *enter = p.enter_plan + ph0, *ef = p.ef + ph0;
+                while (b_hi + 1 < np) {
+                    const int en = enter[b_hi + 1];
+                    if (en < 0 || en > t)
+                        break;
+                    ++b_hi;
+                }
+                while (b_lo < b_hi && max(enter[b_lo], ef[b_lo]) < t)
+                    ++b_lo;
+                const int a = b_lo, hiq = b_hi;
+                // lanes = (phone, state) pairs, 32 / E phones per round; virtual block bases
+                // (scr_boff - enter * E) make the address base + t * E + j
+                for (int ph = a + lane_ph; ph <= hiq; ph += per_round)
+                    if (lane < per_round * E) {
+                        const int si = ph * E + lane_j;
+                        chain_scr[p.scr_boff[ph0 + ph] + (int64_t)t * E + lane_j] =
+                            (int16_t)(wscr[st_slot[si]] - b16);
+                    }
+            }
         }
         __syncwarp();
     }
