@@ -31,7 +31,7 @@ int launch_senone_mix_active(const DevModel &m, const DevPlan &p, const int4 *tn
 int launch_chain_viterbi(const DevModel &m, const DevPlan &p, const int16_t *chain_scr,
                          int2 *tokens, int32_t *spill, int64_t spill_stride, int32_t *utt_best,
                          int32_t *utt_renorm, int32_t *fin_hist, int32_t *fin_score,
-                         int max_phones, cudaStream_t st);
+                         int max_phones, int max_band, cudaStream_t st);
 // cont_score.cu: fully continuous models (ref: src/ms_mgau.c:279-368)
 int launch_cont_dense(const DevModel &m, const float *feat, int64_t g0, int64_t n, int16_t *dense,
                       cudaStream_t st);
@@ -709,7 +709,7 @@ struct ssb_batch_s {
     int64_t n_frames = 0, n_phones = 0, n_states = 0, n_state_frames = 0;
     int64_t n_active_sen_frames = 0, n_scanned_cb_frames = 0, n_band_state_frames = 0;
     int64_t plan_us = 0;  // host time of the last upload's planning + staging calls
-    int max_phones = 0, max_union = 0, max_T = 0;
+    int max_phones = 0, max_union = 0, max_T = 0, max_band = 0;
     int compallsen = 0;
     bool want_tokens_all = false;  // debug: dense token stack, pre-filled, downloadable
     bool want_dense = false;       // debug: dense chain scores / tokens (the reference's layout)
@@ -1256,6 +1256,19 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
         set_error("active-list plan too large; split the batch");
         return -1;
     }
+    // widest band of phones alive at once (evaluated, or entering at the end of the frame)
+    b->max_band = 0;
+    for (int u = 0; u < U; ++u) {
+        const int64_t p0 = b->phone_off[u];
+        const int np = (int)(b->phone_off[u + 1] - p0);
+        int lo = 0;
+        for (int i = 0; i < np && b->enter[p0 + i] >= 0; ++i) {
+            const int32_t t = b->enter[p0 + i] - 1;  // phone i enters at the end of frame t
+            while (lo < i && std::max(b->enter[p0 + lo], in->ef[p0 + lo]) < t)
+                ++lo;
+            b->max_band = std::max(b->max_band, i - lo + 1);
+        }
+    }
     // ---- chain scores and token stack
     b->n_band_scr = b->n_band_tok = 0;
     if (b->banded) {
@@ -1552,7 +1565,7 @@ extern "C" int ssb_batch_run(ssb_batch_t *b)
                                  b->spill.as<int32_t>(), b->spill_stride,
                                  b->utt_best.as<int32_t>(), b->utt_renorm.as<int32_t>(),
                                  b->fin_hist.as<int32_t>(), b->fin_score.as<int32_t>(),
-                                 b->max_phones, st) != 0)
+                                 b->max_phones, b->max_band, st) != 0)
             return -1;
     }
     API_CUDA(cudaEventRecord(b->ev[3], st), -1);

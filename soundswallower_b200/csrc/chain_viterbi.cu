@@ -51,7 +51,10 @@ __device__ __forceinline__ void cta_sync(int nwarps)
 
 // Shared (or, for very long chains, global) state of one utterance's chain:
 //   sc[E][np] hi[E][np] osc[np] ohi[np]
-template <int E>
+constexpr int K3_RING = 64;  // ring of HMM states in shared memory (band narrower than this)
+#define IX(i) (RING ? ((i) & (K3_RING - 1)) : (i))
+
+template <int E, bool RING>
 __global__ void __launch_bounds__(1024)
 chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_scr,
                      int2 *__restrict__ tokens, int32_t *__restrict__ spill,
@@ -77,22 +80,27 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
         }
         return;
     }
-    int32_t *st = np <= smem_phones ? sh : spill + (int64_t)u * spill_stride;
-    int32_t *sc = st;                   // [E][np]
-    int32_t *hi = st + (size_t)E * np;  // [E][np]
-    int32_t *osc = hi + (size_t)E * np;
-    int32_t *ohi = osc + np;
+    // RING: only the band of phones that is alive (a word window's worth) is kept, phone i in slot
+    // i mod 64 -- a phone that has left the band is never looked at again (its successor enters
+    // while it is still being evaluated: api.cu plan_enter) -- so that book-length chains run in
+    // shared memory on one warp instead of spilling to L2 behind block barriers
+    int32_t *st = RING ? sh : (np <= smem_phones ? sh : spill + (int64_t)u * spill_stride);
+    const int W = RING ? K3_RING : np;
+    int32_t *sc = st;                  // [E][W]
+    int32_t *hi = st + (size_t)E * W;  // [E][W]
+    int32_t *osc = hi + (size_t)E * W;
+    int32_t *ohi = osc + W;
     const int32_t *enter = p.enter_plan + ph0;
     const int32_t *sf = p.sf + ph0, *ef = p.ef + ph0, *tmat = p.tmat + ph0;
     const int16_t *scr = chain_scr + p.scr_off[u];
     int2 *tok = tokens + p.scr_off[u];
 
     // hmm_clear on every phone, hmm_enter(hmms, 0, 0, 0) (ref: state_align_search.c:46-55)
-    for (int i = threadIdx.x; i < np; i += blockDim.x) {
+    for (int i = threadIdx.x; i < W; i += blockDim.x) {
 #pragma unroll
         for (int j = 0; j < E; ++j) {
-            sc[j * np + i] = WORST_SCORE;
-            hi[j * np + i] = -1;
+            sc[j * W + i] = WORST_SCORE;
+            hi[j * W + i] = -1;
         }
         osc[i] = WORST_SCORE;
         ohi[i] = -1;
@@ -124,13 +132,13 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
         // renormalize_hmms (ref: state_align_search.c:57-64,193-197; hmm.c:150-161):
         // every phone, alive or not, whose scores are above WORST_SCORE
         if (best - 0x300000 < WORST_SCORE) {
-            for (int i = threadIdx.x; i < np; i += blockDim.x) {
+            for (int i = (RING ? lo : 0) + threadIdx.x; i <= (RING ? hiq : np - 1); i += blockDim.x) {
 #pragma unroll
                 for (int j = 0; j < E; ++j)
-                    if (sc[j * np + i] > WORST_SCORE)
-                        sc[j * np + i] -= best;
-                if (osc[i] > WORST_SCORE)
-                    osc[i] -= best;
+                    if (sc[j * W + IX(i)] > WORST_SCORE)
+                        sc[j * W + IX(i)] -= best;
+                if (osc[IX(i)] > WORST_SCORE)
+                    osc[IX(i)] -= best;
             }
             ++n_renorm;
             cta_sync(nwarps);
@@ -141,12 +149,12 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
         int2 *tok_t = tok + (int64_t)t * ns;
         if (lo_alive) {
             for (int i = lo + threadIdx.x; i <= hiq; i += blockDim.x) {
-                int32_t s[E], h[E], o_s = osc[i], o_h = ohi[i];
+                int32_t s[E], h[E], o_s = osc[IX(i)], o_h = ohi[IX(i)];
                 int ss[E];
 #pragma unroll
                 for (int j = 0; j < E; ++j) {
-                    s[j] = sc[j * np + i];
-                    h[j] = hi[j * np + i];
+                    s[j] = sc[j * W + IX(i)];
+                    h[j] = hi[j * W + IX(i)];
                 }
                 if (p.banded) {
                     const int16_t *sp = chain_scr + p.scr_boff[ph0 + i] + (int64_t)t * E;
@@ -162,11 +170,11 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
                 lb = max(lb, b);
 #pragma unroll
                 for (int j = 0; j < E; ++j) {
-                    sc[j * np + i] = s[j];
-                    hi[j * np + i] = h[j];
+                    sc[j * W + IX(i)] = s[j];
+                    hi[j * W + IX(i)] = h[j];
                 }
-                osc[i] = o_s;
-                ohi[i] = o_h;
+                osc[IX(i)] = o_s;
+                ohi[IX(i)] = o_h;
             }
         }
         cta_sync(nwarps);
@@ -181,6 +189,20 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
             while (last_t + 1 < np && enter[last_t + 1] == nf)
                 ++last_t;
         }
+        if (RING && last_t > hiq) {
+            // the slots of the phones entering now: their previous tenants have left the band
+            // (hmm_clear), before anybody reads a neighbour's exit score
+            for (int i = hiq + 1 + threadIdx.x; i <= last_t; i += blockDim.x) {
+#pragma unroll
+                for (int j = 0; j < E; ++j) {
+                    sc[j * W + IX(i)] = WORST_SCORE;
+                    hi[j * W + IX(i)] = -1;
+                }
+                osc[IX(i)] = WORST_SCORE;
+                ohi[IX(i)] = -1;
+            }
+            cta_sync(nwarps);
+        }
         for (int i = first + threadIdx.x; i <= last_t; i += blockDim.x) {
             const bool was_active = i <= hiq;  // evaluated on frame t
             bool now = was_active;             // hmm_frame(hmm) >= t after this step
@@ -189,18 +211,18 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
                 if (!was_active) {
                     // first entry: unconditional, with whatever exit score the previous
                     // phone holds (WORST_SCORE / -1 if it has never been evaluated)
-                    sc[i] = osc[hprev];
-                    hi[i] = ohi[hprev];
+                    sc[IX(i)] = osc[IX(hprev)];
+                    hi[IX(i)] = ohi[IX(hprev)];
                     now = true;
                 } else {
                     const bool prev_eval = hprev >= first && hprev <= hiq;
                     // hmm_frame(prev) == nf: kept by prune_hmms, or entered in this pass
                     const bool prev_nf = (prev_eval && nf <= ef[hprev]) || enter[hprev] == nf;
                     if (prev_nf && nf >= sf[i]) {
-                        const int32_t o = osc[hprev];
-                        if (o > sc[i]) {
-                            sc[i] = o;  // state 0
-                            hi[i] = ohi[hprev];
+                        const int32_t o = osc[IX(hprev)];
+                        if (o > sc[IX(i)]) {
+                            sc[IX(i)] = o;  // state 0
+                            hi[IX(i)] = ohi[IX(hprev)];
                         }
                     }
                 }
@@ -212,8 +234,8 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
 #pragma unroll
                 for (int j = 0; j < E; ++j) {
                     const int si = i * E + j;
-                    tk[j] = make_int2(hi[j * np + i], sc[j * np + i]);
-                    hi[j * np + i] = si;
+                    tk[j] = make_int2(hi[j * W + IX(i)], sc[j * W + IX(i)]);
+                    hi[j * W + IX(i)] = si;
                 }
             }
         }
@@ -222,15 +244,17 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
     if (threadIdx.x == 0) {
         utt_best[u] = best;
         utt_renorm[u] = n_renorm;
-        fin_hist[u] = ohi[np - 1];
-        fin_score[u] = osc[np - 1];
+        // (a last phone that was never entered still holds hmm_clear's values)
+        const bool reached = !RING || (enter[np - 1] >= 0 && enter[np - 1] <= T);
+        fin_hist[u] = reached ? ohi[IX(np - 1)] : -1;
+        fin_score[u] = reached ? osc[IX(np - 1)] : WORST_SCORE;
     }
 }
 
 int launch_chain_viterbi(const DevModel &m, const DevPlan &p, const int16_t *chain_scr,
                          int2 *tokens, int32_t *spill, int64_t spill_stride, int32_t *utt_best,
                          int32_t *utt_renorm, int32_t *fin_hist, int32_t *fin_score,
-                         int max_phones, cudaStream_t st)
+                         int max_phones, int max_band, cudaStream_t st)
 {
     if (p.n_utts == 0)
         return 0;
@@ -241,24 +265,29 @@ int launch_chain_viterbi(const DevModel &m, const DevPlan &p, const int16_t *cha
         return -1;
     }
     // The evaluated band is usually a handful of phones (one word window); a single warp
-    // keeps every step warp-synchronous.  More warps only pay for unconstrained long chains.
-    int threads = max_phones <= 128 ? 32 : (max_phones < 4096 ? 128 : 512);
+    // keeps every step warp-synchronous.  Long chains whose band stays narrow (max_band, from the
+    // planner) run in the shared-memory ring on one warp; more warps only pay for unconstrained
+    // long chains, whose state then lives in shared memory or, beyond 6400 phones, in L2.
+    const bool ring = max_phones > 128 && max_band > 0 && max_band <= K3_RING - 4;
+    int threads = (max_phones <= 128 || ring) ? 32 : (max_phones < 4096 ? 128 : 512);
     const size_t per_phone = (size_t)(2 * E + 2) * sizeof(int32_t);
     int smem_phones = (int)((200 * 1024) / per_phone);
     if (max_phones < smem_phones)
         smem_phones = max_phones;
-    const size_t smem = per_phone * smem_phones;
+    const size_t smem = per_phone * (ring ? K3_RING : smem_phones);
+#define SSB_K3(EE, RR)                                                                               \
+    do {                                                                                             \
+        SSB_DYN_SMEM((chain_viterbi_kernel<EE, RR>), smem);                                          \
+        chain_viterbi_kernel<EE, RR><<<p.n_utts, threads, smem, st>>>(                               \
+            m, p, chain_scr, tokens, spill, spill_stride, utt_best, utt_renorm, fin_hist, fin_score, \
+            smem_phones);                                                                            \
+    } while (0)
     if (E == 3) {
-        SSB_DYN_SMEM((chain_viterbi_kernel<3>), smem);
-        chain_viterbi_kernel<3><<<p.n_utts, threads, smem, st>>>(
-            m, p, chain_scr, tokens, spill, spill_stride, utt_best, utt_renorm, fin_hist,
-            fin_score, smem_phones);
+        if (ring) SSB_K3(3, true); else SSB_K3(3, false);
     } else {
-        SSB_DYN_SMEM((chain_viterbi_kernel<5>), smem);
-        chain_viterbi_kernel<5><<<p.n_utts, threads, smem, st>>>(
-            m, p, chain_scr, tokens, spill, spill_stride, utt_best, utt_renorm, fin_hist,
-            fin_score, smem_phones);
+        if (ring) SSB_K3(5, true); else SSB_K3(5, false);
     }
+#undef SSB_K3
     SSB_CUDA(cudaGetLastError());
     note_launch();
     return 0;

@@ -163,7 +163,7 @@ int launch_gather_chain(const DevModel &m, const DevPlan &p, const int16_t *dens
 int launch_chain_viterbi(const DevModel &m, const DevPlan &p, const int16_t *chain_scr,
                          int2 *tokens, int32_t *spill, int64_t spill_stride, int32_t *utt_best,
                          int32_t *utt_renorm, int32_t *fin_hist, int32_t *fin_score,
-                         int max_phones, cudaStream_t st);
+                         int max_phones, int max_band, cudaStream_t st);
 int launch_backtrace(const DevModel &m, const DevPlan &p, const int2 *tokens,
                      const int32_t *fin_hist, const int32_t *fin_score, int32_t *st_start,
                      int32_t *st_dur, int32_t *st_score, int32_t *utt_rv, cudaStream_t st);
