@@ -121,6 +121,8 @@ void ssb_mgau_free(ssb_mgau_t *mgau);
  * src/acmod.c:278-279) releases both -- the lifetime ptm_mgau_init's object has in the reference
  * (see integration/ssb_glue.c, the reference-side binding). */
 void ssb_mgau_own_model(ssb_mgau_t *mgau, int own);
+/* the model a scorer object was made for (the searches of the same decoder need it) */
+ssb_model_t *ssb_mgau_model(const ssb_mgau_t *mgau);
 
 /* ------------------------------------------------------------------ */
 /* batched path                                                        */
@@ -401,6 +403,12 @@ ssb_fsg_built_t *ssb_fsg_build(const ssb_lexicon_t *lx, int32_t n_state, int32_t
                                int32_t n_trans, const int32_t *from, const int32_t *to,
                                const float *prob, const char *const *word, int32_t null_closure,
                                const ssb_fsg_config_t *cfg);
+/* the same with fsg_link_t.logs2prob values (integers already scaled by lw) instead of linear
+ * probabilities: what an fsg_model_t in memory holds (integration/ssb_glue.c) */
+ssb_fsg_built_t *ssb_fsg_build_logp(const ssb_lexicon_t *lx, int32_t n_state, int32_t start, int32_t final,
+                                    int32_t n_trans, const int32_t *from, const int32_t *to,
+                                    const int32_t *logs2prob, const char *const *word,
+                                    int32_t null_closure, const ssb_fsg_config_t *cfg);
 /* the graph (arrays owned by the object) and its vocabulary: link4[.][3] indexes these words */
 const ssb_fsg_graph_t *ssb_fsg_built_graph(const ssb_fsg_built_t *b);
 int32_t ssb_fsg_built_n_words(const ssb_fsg_built_t *b);

@@ -134,7 +134,7 @@ class SegIter(C.Structure):
 SYMBOLS = [
     "ssb_version", "ssb_last_error", "ssb_device_count", "ssb_config_defaults",
     "ssb_model_load", "ssb_model_kind", "ssb_model_ciphone_str", "ssb_model_free", "ssb_model_dims", "ssb_model_copy", "ssb_model_phones",
-    "ssb_mgau_init", "ssb_mgau_frame_eval", "ssb_mgau_reset", "ssb_mgau_free", "ssb_mgau_own_model",
+    "ssb_mgau_init", "ssb_mgau_frame_eval", "ssb_mgau_reset", "ssb_mgau_free", "ssb_mgau_own_model", "ssb_mgau_model",
     "ssb_plan_chain", "ssb_batch_create", "ssb_batch_free", "ssb_batch_upload", "ssb_batch_run",
     "ssb_batch_download", "ssb_batch_debug_tokens", "ssb_batch_kernel_ms",
     "ssb_batch_n_launches", "ssb_batch_stats", "ssb_batch_band_state_frames", "ssb_align_batch", "ssb_align_batch_multi", "ssb_pipeline_create",
@@ -152,7 +152,7 @@ SYMBOLS = [
     "ssb_frontend_kernel_ms",
     "ssb_lexicon_load", "ssb_lexicon_free", "ssb_lexicon_size", "ssb_lexicon_wordid",
     "ssb_lexicon_wordstr", "ssb_lexicon_pron", "ssb_lexicon_is_filler", "ssb_chain_populate",
-    "ssb_fsg_config_defaults", "ssb_fsg_build_align", "ssb_fsg_build", "ssb_fsg_built_graph",
+    "ssb_fsg_config_defaults", "ssb_fsg_build_align", "ssb_fsg_build", "ssb_fsg_build_logp", "ssb_fsg_built_graph",
     "ssb_fsg_built_n_words", "ssb_fsg_built_word", "ssb_fsg_built_free",
 ]
 

@@ -594,6 +594,12 @@ extern "C" void ssb_mgau_own_model(ssb_mgau_t *gg, int own)
         g->owns_model = own != 0;
 }
 
+extern "C" ssb_model_t *ssb_mgau_model(const ssb_mgau_t *gg)
+{
+    const ssb_mgau_impl *g = reinterpret_cast<const ssb_mgau_impl *>(gg);
+    return g ? g->m : nullptr;
+}
+
 extern "C" void ssb_mgau_reset(ssb_mgau_t *gg)
 {
     ssb_mgau_impl *g = reinterpret_cast<ssb_mgau_impl *>(gg);
@@ -844,14 +850,20 @@ extern "C" int ssb_plan_chain(int32_t np, int32_t T, const int32_t *sf, const in
     return 0;
 }
 
-// K1 kernel choice: the frame-tiled tcgen05 kernel (gmm_scan_ft.cu) unless $SSB_K1 names another
-// one (tc2 / fp32: kept for A/B runs)
-static bool k1_frame_tiled(const DevModel &d)
+// K1 kernel choice.  Two tcgen05 kernels give the same lists:
+//   * gmm_scan_ft.cu (frame-tiled: A tile in tensor memory built once per 128 frames, B streamed
+//     by TMA bulk copies, no exact evaluation on the common path) -- measured faster when every
+//     codebook is scanned (first pass / compallsen: 56 against 84 ms on 4096 x 10 s) and when
+//     lists are carried in from a first pass (no second instantiation at the register limit);
+//   * gmm_topn_tc2.cu (codebook-stream x 256 utterances per CTA, 16 warps per SM) -- measured
+//     faster for the aligner's active lists on short windows (26.5 against 28 ms on config #2).
+// $SSB_K1 = ft / tc2 / fp32 forces one (A/B runs, profiles/prof_gmm_scan_ft_r2*.txt).
+static bool k1_frame_tiled(const DevModel &d, bool all_active, bool carried_lists)
 {
     const char *k1 = getenv("SSB_K1");
     if (k1 && *k1)
         return strcmp(k1, "ft") == 0 && ft_supported(d);
-    return false;  // TODO default once the parity suite is green
+    return ft_supported(d) && (all_active || carried_lists);
 }
 
 // Planner threads of one batch: the host's cores are shared by the ranks / device threads of a
@@ -1365,7 +1377,7 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
     b->n_seg_utts = 0;
     b->ft = false;
     b->n_tiles = 0;
-    if (k1_frame_tiled(b->m->d) && U > 0 && G > 0) {
+    if (k1_frame_tiled(b->m->d, b->compallsen != 0, p.init_topn != nullptr) && U > 0 && G > 0) {
         // frame-tiled K1: every utterance is cut into tiles of 128 frames that are scored
         // independently; all utterances are candidates for the tie fix-up
         std::vector<int32_t> tu, tt, all_utts(U);

@@ -683,13 +683,38 @@ extern "C" ssb_fsg_built_t *ssb_fsg_build_align(const ssb_lexicon_t *lx, const c
 // fsg_model_trans_add / fsg_model_null_trans_add; link order decides ties in the search).
 // word[i] == NULL (or "") is a null transition; prob is the linear transition probability,
 // converted like the reference does: (int32)(logmath_log(p) * lw).
+static ssb_fsg_built_t *fsg_build_impl(const ssb_lexicon_t *lx, int32_t n_state, int32_t start,
+                                       int32_t final, int32_t n_trans, const int32_t *from,
+                                       const int32_t *to, const float *prob, const int32_t *logs2prob,
+                                       const char *const *word, int32_t null_closure,
+                                       const ssb_fsg_config_t *cfg);
+
 extern "C" ssb_fsg_built_t *ssb_fsg_build(const ssb_lexicon_t *lx, int32_t n_state, int32_t start,
                                           int32_t final, int32_t n_trans, const int32_t *from,
                                           const int32_t *to, const float *prob, const char *const *word,
                                           int32_t null_closure, const ssb_fsg_config_t *cfg)
 {
+    return fsg_build_impl(lx, n_state, start, final, n_trans, from, to, prob, nullptr, word, null_closure, cfg);
+}
+
+// the same from an fsg_model_t's own integer scores (fsg_link_t.logs2prob, already scaled by lw)
+extern "C" ssb_fsg_built_t *ssb_fsg_build_logp(const ssb_lexicon_t *lx, int32_t n_state, int32_t start,
+                                               int32_t final, int32_t n_trans, const int32_t *from,
+                                               const int32_t *to, const int32_t *logs2prob,
+                                               const char *const *word, int32_t null_closure,
+                                               const ssb_fsg_config_t *cfg)
+{
+    return fsg_build_impl(lx, n_state, start, final, n_trans, from, to, nullptr, logs2prob, word, null_closure, cfg);
+}
+
+static ssb_fsg_built_t *fsg_build_impl(const ssb_lexicon_t *lx, int32_t n_state, int32_t start,
+                                       int32_t final, int32_t n_trans, const int32_t *from,
+                                       const int32_t *to, const float *prob, const int32_t *logs2prob,
+                                       const char *const *word, int32_t null_closure,
+                                       const ssb_fsg_config_t *cfg)
+{
     if (!lx || n_state <= 0 || start < 0 || start >= n_state || final < 0 || final >= n_state || n_trans < 0
-        || (n_trans > 0 && (!from || !to || !prob || !word))) {
+        || (n_trans > 0 && (!from || !to || (!prob && !logs2prob) || !word))) {
         set_error("ssb_fsg_build: bad arguments");
         return nullptr;
     }
@@ -708,11 +733,15 @@ extern "C" ssb_fsg_built_t *ssb_fsg_build(const ssb_lexicon_t *lx, int32_t n_sta
             set_error("ssb_fsg_build: transition %d: state out of range", i);
             return nullptr;
         }
-        if (!(prob[i] > 0.f) || prob[i] > 1.f) {
+        if (prob && (!(prob[i] > 0.f) || prob[i] > 1.f)) {
             set_error("ssb_fsg_build: transition %d: probability %g not in (0, 1]", i, (double)prob[i]);
             return nullptr;
         }
-        const int logp = (int32_t)((float)lm.log((double)prob[i], 0) * W.cfg.lw);
+        if (!prob && logs2prob[i] > 0) {
+            set_error("ssb_fsg_build: transition %d: log probability %d above 0", i, logs2prob[i]);
+            return nullptr;
+        }
+        const int logp = prob ? (int32_t)((float)lm.log((double)prob[i], 0) * W.cfg.lw) : logs2prob[i];
         if (word[i] && word[i][0]) {
             if (!lx->id.count(word[i])) {
                 set_error("Unknown word %s", word[i]);  // (fsg_search_check_dict, ref: src/fsg_search.c:120-139)
