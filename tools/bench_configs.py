@@ -206,35 +206,66 @@ def config5_two_pass(ssb, model, total_utts=65536, rank=0, world=1, chunk=4096, 
     if max_chunks:
         n_chunks = min(n_chunks, max_chunks)
     flat, n = two_pass_pool(chunk, pinned)
-    lx = ssb.Lexicon(model, hmmdir=hmm)
-    fe = ssb.Frontend(hmm, device=model.device)
     text = " ".join(["go forward ten meters"] * 3)
+    n_workers = max(1, int(os.environ.get("SSB_TWO_PASS_WORKERS", "1")))
 
-    def one(k_utts):
-        off = np.arange(k_utts + 1, dtype=np.int64) * n
-        feats = fe.run_raw(flat[:k_utts * n], off)
-        ta = ssb.TextAlignment(model, lx, feats, [text] * k_utts, align_level=1)
-        ta.render(align_level=1)
-        js0 = ta.json(0, align_level=1)
-        ok = sum(1 for u in range(k_utts) if ta.status(u)[0] == 0)
-        ms1 = ta.kernel_ms()
-        ta.close()
-        return ok, js0, ms1
+    class Worker:
+        """One host thread's objects: while its chunk is in host code (grammars, chains, JSON) the
+        other thread's chunk is on the GPU."""
 
-    one(min(chunk, 256))  # warm-up
-    done, ok_total, js0, ms1 = 0, 0, None, None
-    t0 = time.perf_counter()
+        def __init__(self):
+            self.lx = ssb.Lexicon(model, hmmdir=hmm)
+            self.fe = ssb.Frontend(hmm, device=model.device)
+
+        def one(self, k_utts):
+            off = np.arange(k_utts + 1, dtype=np.int64) * n
+            feats = self.fe.run_raw(flat[:k_utts * n], off)
+            ta = ssb.TextAlignment(model, self.lx, feats, [text] * k_utts, align_level=1)
+            ta.render(align_level=1)
+            js0 = ta.json(0, align_level=1)
+            ok = sum(1 for u in range(k_utts) if ta.status(u)[0] == 0)
+            ms1 = ta.kernel_ms()
+            ta.close()
+            return ok, js0, ms1
+
+        def close(self):
+            self.fe.close()
+            self.lx.close()
+
+    workers = [Worker() for _ in range(n_workers)]
+    for w in workers:
+        w.one(min(chunk, 256))  # warm-up
+    sizes, done = [], 0
     for c in range(n_chunks):
         k = min(chunk, mine - done)
-        ok, js0, ms1 = one(k)
-        ok_total += ok
+        sizes.append(k)
         done += k
+    import concurrent.futures as cf
+    import threading
+    local = threading.local()
+    free = list(workers)
+    lock = threading.Lock()
+
+    def run(k):
+        with lock:
+            w = free.pop()
+        try:
+            return w.one(k)
+        finally:
+            with lock:
+                free.append(w)
+
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(n_workers) as ex:
+        res = list(ex.map(run, sizes))
     wall = time.perf_counter() - t0
-    fe.close()
-    lx.close()
+    for w in workers:
+        w.close()
+    ok_total = sum(r[0] for r in res)
+    js0, ms1 = res[-1][1], res[-1][2]
     return {"utts": done, "aligned": ok_total, "wall_s": wall, "audio_s": done * n / 16000.0,
             "first_json_words": len(json.loads(js0)["w"]) if js0 else 0, "pass1_kernel_ms_last_chunk": ms1,
-            "h2d_bytes": int(done * n * 2)}
+            "h2d_bytes": int(done * n * 2), "host_threads": n_workers}
 
 
 def cpu_two_pass(n_utts):
