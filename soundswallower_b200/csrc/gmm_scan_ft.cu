@@ -743,7 +743,9 @@ gmm_scan_ft_kernel(DevModel m, DevPlan p, FtArgs a)
                                 ek[k] = eps;
                                 if (has_hot) {
                                     const int ci = (int)(__float_as_uint(tk[k]) & 127u);
-                                    if ((hot[ci >> 5] >> (ci & 31)) & 1u)
+                                    const int hq = ci >> 5;  // (select chain: no dynamic register index)
+                                    const uint32_t hw = hq == 0 ? hot[0] : (hq == 1 ? hot[1] : (hq == 2 ? hot[2] : hot[3]));
+                                    if ((hw >> (ci & 31)) & 1u)
                                         ek[k] = eps_hot;
                                 }
                             }
