@@ -312,6 +312,7 @@ def main():
         # keep stdout to the one JSON line: NCCL prints its version banner there otherwise
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     g = np.load(GOLDEN)
