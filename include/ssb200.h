@@ -309,6 +309,10 @@ typedef struct ssb_fsg_in_s {
      * src/fsg_search.c:309-328, 686-690) -- path scores then equal the default CLI's.  PTM
      * models with 128 densities only. */
     int32_t active_lists;
+    /* 1 = the utterances are still running: the hypothesis is the best word exit of the last
+     * frame that has one, whatever state it leads to (fsg_search_hyp before
+     * search_module_finish: find_exit with final = FALSE, ref: src/fsg_search.c:853-924) */
+    int32_t partial;
 } ssb_fsg_in_t;
 
 typedef struct ssb_fsg_out_s {
@@ -424,7 +428,11 @@ void ssb_fsg_built_free(ssb_fsg_built_t *b);
  * (ref: src/decoder.c:935-957) and decoder_end_utt / decoder_hyp / decoder_seg_iter work on
  * them unchanged through the macros of search_module.h.  step() collects the frame's feature
  * vector; finish() runs the utterance through the batched kernels; hyp / seg_iter / the
- * alignment entries are then served from the results. */
+ * alignment entries are then served from the results.  hyp / seg_iter of the grammar search
+ * BETWEEN two steps (the reference answers from its history table as it stands, find_exit with
+ * final = FALSE, ref: src/fsg_search.c:853-960) search the frames collected so far and give what
+ * the reference gives at that frame; the aligner's hyp between steps reads the alignment as
+ * populated, like the reference's (ref: src/state_align_search.c:365-411). */
 typedef struct ssb_search_s ssb_search_t;
 typedef struct ssb_seg_iter_s ssb_seg_iter_t;
 typedef struct ssb_searchfuncs_s { /* searchfuncs_t, ref: search_module.h:72-84 */

@@ -21,6 +21,32 @@
 #include "ssb200.h"
 
 static int g_n_init = 0;
+/* the model the most recent scorers were made from, with the serial number of their creation: a
+ * freed model's address can come back for another model, so the searches' lexicon cache is keyed
+ * by (address, serial) */
+#define GLUE_N_MODELS 64
+static struct { const void *model; int serial; } g_models[GLUE_N_MODELS];
+
+static void
+glue_note_model(const void *sm, int serial)
+{
+    int i, at = serial % GLUE_N_MODELS;
+    for (i = 0; i < GLUE_N_MODELS; ++i)
+        if (g_models[i].model == sm)
+            at = i;
+    g_models[at].model = sm;
+    g_models[at].serial = serial;
+}
+
+static int
+glue_model_serial(const void *sm)
+{
+    int i;
+    for (i = 0; i < GLUE_N_MODELS; ++i)
+        if (g_models[i].model == sm)
+            return g_models[i].serial;
+    return -1;
+}
 
 /* how many scorers this glue has handed to acmod (the test checks the B200 path really ran) */
 int
@@ -58,6 +84,7 @@ ssb_ptm_mgau_init(acmod_t *acmod)
         return NULL;
     }
     ++g_n_init;
+    glue_note_model(sm, g_n_init);
     /* (the model lives as long as the scorer; ssb_mgau_free releases both when the scorer
      * owns it: see ssb_mgau_own_model) */
     ssb_mgau_own_model(g, 1);
@@ -93,9 +120,12 @@ ssb_glue_n_search_init(void)
     return g_n_search_init;
 }
 
-/* one lexicon per scorer model (dictionary + filler dictionary of the decoder's configuration) */
-static ssb_model_t *g_lx_model = NULL;
-static ssb_lexicon_t *g_lx = NULL;
+/* one lexicon per scorer model (dictionary + filler dictionary of the decoder's configuration);
+ * the searches borrow it, so a few are kept: decoders that are alive at the same time (up to
+ * GLUE_N_LX of them) never see theirs freed */
+#define GLUE_N_LX 4
+static struct { ssb_model_t *model; int serial; ssb_lexicon_t *lx; long used; } g_lxs[GLUE_N_LX];
+static long g_lx_clock = 0;
 /* acmod state after the first pass of the decoder's current utterance */
 static uint32_t *g_flags = NULL;
 static uint8_t *g_topn = NULL;
@@ -112,13 +142,23 @@ glue_model(acmod_t *acmod)
 static ssb_lexicon_t *
 glue_lexicon(ssb_model_t *m, config_t *config)
 {
-    if (g_lx && g_lx_model == m)
-        return g_lx;
-    if (g_lx)
-        ssb_lexicon_free(g_lx);
-    g_lx = ssb_lexicon_load(m, config_str(config, "dict"), config_str(config, "fdict"));
-    g_lx_model = m;
-    return g_lx;
+    const int serial = glue_model_serial(m);
+    int i, at = 0;
+    for (i = 0; i < GLUE_N_LX; ++i)
+        if (g_lxs[i].lx && g_lxs[i].model == m && g_lxs[i].serial == serial) {
+            g_lxs[i].used = ++g_lx_clock;
+            return g_lxs[i].lx;
+        }
+    for (i = 1; i < GLUE_N_LX; ++i) /* a free slot, else the least recently used */
+        if (g_lxs[i].lx == NULL ? g_lxs[at].lx != NULL : (g_lxs[at].lx != NULL && g_lxs[i].used < g_lxs[at].used))
+            at = i;
+    if (g_lxs[at].lx)
+        ssb_lexicon_free(g_lxs[at].lx);
+    g_lxs[at].lx = ssb_lexicon_load(m, config_str(config, "dict"), config_str(config, "fdict"));
+    g_lxs[at].model = m;
+    g_lxs[at].serial = serial;
+    g_lxs[at].used = ++g_lx_clock;
+    return g_lxs[at].lx;
 }
 
 /* what acmod_score scores for frame_idx (ref: src/acmod.c:765-802 calc_feat_idx) */

@@ -607,6 +607,62 @@ ref_fsg_decode(void *h, const float *feat, int T, const char *align_text,
     return n;
 }
 
+/* The same decode, asked for its hypothesis BETWEEN steps: after each of stops[0..n_stops)
+ * frames (ascending) decoder_hyp / decoder_seg_iter are called before the next step.  out
+ * [n_stops][2 + 5*maxseg] = hyp score (INT32_MIN when decoder_hyp returns NULL), n segs, then
+ * segs as in ref_fsg_decode; hyps [n_stops][hyp_len] the hypothesis strings.  The utterance is
+ * then run to its end and finished. */
+int
+ref_fsg_partial(void *h, const float *feat, int T, const char *align_text, const int32 *stops,
+                int n_stops, int32 *out, int maxseg, char *hyps, int hyp_len)
+{
+    ref_t *r = h;
+    decoder_t *d = r->d;
+    acmod_t *a = d->acmod;
+    int k = 0, stride = 2 + 5 * maxseg;
+    if (align_text && decoder_set_align_text(d, align_text) < 0)
+        return -1;
+    if (decoder_start_utt(d) < 0)
+        return -1;
+    load_features(r, feat, T);
+    a->state = ACMOD_ENDED;
+    while (a->n_feat_frame > 0) {
+        if (search_module_step(d->search, a->output_frame) < 0)
+            return -1;
+        acmod_advance(a);
+        while (k < n_stops && stops[k] == a->output_frame) {
+            int32 score = 0, *o = out + (size_t)k * stride;
+            const char *hyp = decoder_hyp(d, &score);
+            seg_iter_t *seg;
+            int n = 0;
+            o[0] = hyp ? score : INT32_MIN;
+            hyps[(size_t)k * hyp_len] = 0;
+            if (hyp)
+                strncpy(hyps + (size_t)k * hyp_len, hyp, hyp_len - 1), hyps[(size_t)k * hyp_len + hyp_len - 1] = 0;
+            for (seg = decoder_seg_iter(d); seg; seg = seg_iter_next(seg)) {
+                int sf, ef;
+                int32 ascr, lscr;
+                if (n >= maxseg) {
+                    seg_iter_free(seg);
+                    break;
+                }
+                seg_iter_frames(seg, &sf, &ef);
+                seg_iter_prob(seg, &ascr, &lscr);
+                o[2 + n * 5 + 0] = seg_iter_word(seg) ? dict_wordid(d->dict, seg_iter_word(seg)) : -1;
+                o[2 + n * 5 + 1] = sf;
+                o[2 + n * 5 + 2] = ef;
+                o[2 + n * 5 + 3] = ascr;
+                o[2 + n * 5 + 4] = lscr;
+                ++n;
+            }
+            o[1] = n;
+            ++k;
+        }
+    }
+    search_module_finish(d->search);
+    return k;
+}
+
 /* acmod's active-senone flags as they stand (after an fsg decode in the default mode: the
  * senones of the last frame's active HMMs); out = (n_sen+31)/32 words.  Also the number of
  * senones the last grammar search evaluated (fsgs->n_sen_eval) when it is an fsg search. */

@@ -250,6 +250,28 @@ class Ref:
         assert rv >= 0, rv
         return dict(segs=segs[:rv].copy(), hyp_score=int(n_out[4]), n_frames=int(n_out[5]))
 
+    def fsg_partial(self, feat, align_text, stops, maxseg=64):
+        """decoder_hyp / decoder_seg_iter between steps: after each of `stops` frames.  Returns a
+        list of dicts hyp (str or None), hyp_score, segs [n][5] (wid sf ef ascr lscr)."""
+        feat = np.ascontiguousarray(feat, np.float32)
+        stops = np.ascontiguousarray(stops, np.int32)
+        out = np.zeros((len(stops), 2 + 5 * maxseg), np.int32)
+        hyps = C.create_string_buffer(len(stops) * 512)
+        self.lib.ref_fsg_partial.restype = C.c_int
+        self.lib.ref_fsg_partial.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_char_p,
+                                             C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32), C.c_int,
+                                             C.c_char_p, C.c_int]
+        rv = self.lib.ref_fsg_partial(self.h, _p(feat, C.c_float), feat.shape[0], align_text.encode(),
+                                      _p(stops, C.c_int32), len(stops), _p(out, C.c_int32), maxseg, hyps, 512)
+        assert rv == len(stops), rv
+        res = []
+        for k in range(len(stops)):
+            sc, n = int(out[k, 0]), int(out[k, 1])
+            txt = hyps.raw[k * 512:(k + 1) * 512].split(b"\0")[0].decode()
+            res.append(dict(hyp=None if sc == -2**31 else txt, hyp_score=None if sc == -2**31 else sc,
+                            segs=out[k, 2:2 + 5 * n].reshape(n, 5).copy()))
+        return res
+
     def hmm_vit_eval_tp(self, tp, senscr, st):
         """hmm_vit_eval on a caller-provided transition matrix [n_emit][n_emit+1] and the n_emit
         scores of the HMM's own states (3- or 5-state)."""

@@ -552,7 +552,7 @@ def tc_probe(model, feats):
 
 
 def fsg_batch(model, feats, graphs, utt_graph=None, hist_cap=None, max_seg=256, want_hist=False,
-              compallsen=True):
+              compallsen=True, partial=False):
     """fsg_search over a batch: see _fsg_batch_once.  The reference's history table and segment
     iterator are unbounded (ref: src/fsg_history.c:129-232); here they have capacities, so the
     call sizes them from the longest utterance (as the C entry points do) and repeats with
@@ -565,7 +565,8 @@ def fsg_batch(model, feats, graphs, utt_graph=None, hist_cap=None, max_seg=256, 
         max_T = max([int(np.asarray(f).reshape(-1, model.blk).shape[0]) for f in feats] or [0])
     cap = int(hist_cap) if hist_cap else max(4096, 8 * max_T)
     for _attempt in range(6):
-        out = _fsg_batch_once(model, feats, graphs, utt_graph, cap, max_seg, want_hist, compallsen)
+        out = _fsg_batch_once(model, feats, graphs, utt_graph, cap, max_seg, want_hist, compallsen,
+                              partial)
         over_hist = any(r["rv"] == -2 for r in out)
         over_seg = [-r["n_seg"] for r in out if r["n_seg"] < 0]
         if not over_hist and not over_seg:
@@ -579,7 +580,7 @@ def fsg_batch(model, feats, graphs, utt_graph=None, hist_cap=None, max_seg=256, 
 
 
 def _fsg_batch_once(model, feats, graphs, utt_graph=None, hist_cap=4096, max_seg=256, want_hist=False,
-                    compallsen=True):
+                    compallsen=True, partial=False):
     """fsg_search over a batch (first pass / grammar decoding) on dense senone scores.
 
     graphs: list of dicts with the flattened FSG + lextree (keys n_state start final n_ciphone
@@ -618,6 +619,7 @@ def _fsg_batch_once(model, feats, graphs, utt_graph=None, hist_cap=4096, max_seg
     fin.n_graphs, fin.graphs, fin.utt_graph = len(graphs), garr, ug.ctypes.data
     fin.hist_cap, fin.max_seg = int(hist_cap), int(max_seg)
     fin.active_lists = 0 if compallsen else 1
+    fin.partial = 1 if partial else 0   # hypothesis of a running utterance (find_exit, final = FALSE)
     segs = np.zeros((U, max_seg, 5), np.int32)
     n_seg, score, exit_bp, rv, n_hist = (np.zeros(U, np.int32) for _ in range(5))
     n_eval = np.zeros(U, np.int64)

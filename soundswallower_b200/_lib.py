@@ -68,7 +68,8 @@ class FsgGraph(C.Structure):
 class FsgIn(C.Structure):
     _fields_ = [("n_utts", C.c_int32), ("feat", C.c_void_p), ("frame_off", C.c_void_p),
                 ("n_graphs", C.c_int32), ("graphs", C.POINTER(FsgGraph)), ("utt_graph", C.c_void_p),
-                ("hist_cap", C.c_int32), ("max_seg", C.c_int32), ("active_lists", C.c_int32)]
+                ("hist_cap", C.c_int32), ("max_seg", C.c_int32), ("active_lists", C.c_int32),
+                ("partial", C.c_int32)]
 
 
 class FsgOut(C.Structure):

@@ -1389,6 +1389,51 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
                 tt.push_back(t0);
             }
         }
+        if (getenv("SSB_FT_DIAG") && !b->compallsen) {
+            // row utilisation of the frame-tiled kernel vs a codebook-major arrangement
+            double own = 0, tile_rows = 0, warp_rows = 0, piece_rows = 0, n_runs = 0;
+            for (int u = 0; u < U; ++u) {
+                const int T = (int)(b->frame_off[u + 1] - b->frame_off[u]);
+                std::vector<uint64_t> fm(T, 0);
+                for (int e = ep_off[u]; e < ep_off[u + 1]; ++e) {
+                    const int s = ep_start[e], en = e + 1 < ep_off[u + 1] ? ep_start[e + 1] : T;
+                    const uint64_t mk = (uint64_t)ep_cbmask[(size_t)e * 8] | ((uint64_t)ep_cbmask[(size_t)e * 8 + 1] << 32);
+                    for (int t = std::max(s, 0); t < en && t < T; ++t)
+                        fm[t] = mk;
+                }
+                for (int t = 0; t < T; ++t)
+                    own += __builtin_popcountll(fm[t]);
+                for (int t0 = 0; t0 < T; t0 += 128) {
+                    uint64_t un = 0;
+                    for (int t = t0; t < std::min(T, t0 + 128); ++t)
+                        un |= fm[t];
+                    tile_rows += 128.0 * __builtin_popcountll(un);
+                    for (int w = 0; w < 4; ++w) {
+                        uint64_t wn = 0;
+                        for (int t = t0 + 32 * w; t < std::min(T, t0 + 32 * w + 32); ++t)
+                            wn |= fm[t];
+                        warp_rows += 32.0 * __builtin_popcountll(wn);
+                    }
+                }
+                for (int c = 0; c < 64; ++c) {
+                    int run = 0;
+                    for (int t = 0; t <= T; ++t) {
+                        const bool on = t < T && ((fm[t] >> c) & 1u);
+                        if (on)
+                            ++run;
+                        else if (run) {
+                            piece_rows += 32.0 * ((run + 31) / 32);
+                            n_runs += 1;
+                            run = 0;
+                        }
+                    }
+                }
+            }
+            fprintf(stderr, "[ft diag] frames %lld own cb-rows %.0f (%.2f/frame) tile-union rows %.0f (util %.3f) "
+                            "warp-union rows %.0f (util %.3f) cb-major 32-row pieces %.0f (util %.3f) runs %.0f (mean %.1f)\n",
+                    (long long)G, own, own / (double)G, tile_rows, own / tile_rows, warp_rows, own / warp_rows,
+                    piece_rows, own / piece_rows, n_runs, own / n_runs);
+        }
         b->n_tiles = (int)tu.size();
         b->k1_tie_w = (G + 31) / 32 + 1;
         if (b->n_tiles > 0) {
@@ -2668,7 +2713,7 @@ extern "C" int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out
         if (launch_fsg_backtrace(gs, d_ug.as<int32_t>(), 0, U, d_hist.as<int32_t>(), in->hist_cap,
                                  d_nhist.as<int32_t>(), d_frames.as<int32_t>(), d_exit.as<int32_t>(),
                                  d_score.as<int32_t>(), d_segs.as<int32_t>(), in->max_seg,
-                                 d_nseg.as<int32_t>(), st) != 0)
+                                 d_nseg.as<int32_t>(), in->partial ? 0 : 1, st) != 0)
             break;
         cudaEventRecord(b->ev[3], st);
         struct { void *dst; DBuf *src; size_t bytes; } copies[] = {

@@ -205,7 +205,7 @@ int launch_fsg_final_topn_dense(const DevModel &m, const int64_t *frame_off, int
 int launch_fsg_backtrace(const DevFsgSet &gs, const int32_t *utt_graph, int u0, int n_utts,
                          const int32_t *hist, int hist_cap, const int32_t *n_hist,
                          const int32_t *frames, int32_t *exit_bp, int32_t *hyp_score, int32_t *segs,
-                         int max_seg, int32_t *n_seg, cudaStream_t st);
+                         int max_seg, int32_t *n_seg, int final, cudaStream_t st);
 // single-frame scorer behind the mgau vtable
 struct FrameHist {
     int4 *score[2];    // [CS] per history slot

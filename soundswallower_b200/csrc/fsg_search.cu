@@ -855,13 +855,14 @@ fsg_search_kernel(DevModel m, DevFsgSet gs, FsgActiveArgs aa, const int64_t *__r
     }
 }
 
-// ref: src/fsg_search.c:853-924 (find_exit, final = TRUE) and :1030-1142 (segmentation).
+// ref: src/fsg_search.c:853-924 (find_exit; `final` = 0 while the utterance is running) and
+// :1030-1142 (segmentation).
 // One thread per utterance.  segs [u][max_seg][5] = link sf ef ascr lscr, first word first.
 __global__ void fsg_backtrace_kernel(DevFsgSet gs, const int32_t *__restrict__ utt_graph, int u0,
                                      int n_utts, const int32_t *__restrict__ hist_all, int hist_cap,
                                      const int32_t *__restrict__ n_hist, const int32_t *__restrict__ frames,
                                      int32_t *__restrict__ exit_bp, int32_t *__restrict__ hyp_score,
-                                     int32_t *__restrict__ segs, int max_seg, int32_t *__restrict__ n_seg)
+                                     int32_t *__restrict__ segs, int max_seg, int32_t *__restrict__ n_seg, int final)
 {
     const int u = u0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= u0 + n_utts)
@@ -894,7 +895,7 @@ __global__ void fsg_backtrace_kernel(DevFsgSet gs, const int32_t *__restrict__ u
             break;
         if (score == bestscore && link4[link * 4 + 1] == g->final)
             besthist = bpidx;
-        else if (score > bestscore && link4[link * 4 + 1] == g->final) {
+        else if (score > bestscore && (!final || link4[link * 4 + 1] == g->final)) {
             bestscore = score;
             besthist = bpidx;
         }
@@ -1044,13 +1045,13 @@ int launch_fsg_final_topn_dense(const DevModel &m, const int64_t *frame_off, int
 int launch_fsg_backtrace(const DevFsgSet &gs, const int32_t *utt_graph, int u0, int n_utts,
                          const int32_t *hist, int hist_cap, const int32_t *n_hist,
                          const int32_t *frames, int32_t *exit_bp, int32_t *hyp_score, int32_t *segs,
-                         int max_seg, int32_t *n_seg, cudaStream_t st)
+                         int max_seg, int32_t *n_seg, int final, cudaStream_t st)
 {
     if (n_utts <= 0)
         return 0;
     fsg_backtrace_kernel<<<(n_utts + 63) / 64, 64, 0, st>>>(gs, utt_graph, u0, n_utts, hist, hist_cap,
                                                            n_hist, frames, exit_bp, hyp_score, segs,
-                                                           max_seg, n_seg);
+                                                           max_seg, n_seg, final);
     SSB_CUDA(cudaGetLastError());
     note_launch();
     return 0;

@@ -51,6 +51,7 @@ struct SearchImpl {
     ssb_fsg_built_t *fsg = nullptr;
     std::vector<int32_t> segs;  // [n][5] link sf ef ascr lscr
     int32_t n_seg = 0, hyp_score = 0, exit_bp = 0, n_hist = 0;
+    int result_frames = -1;  // frames the results above were computed on (hyp between two steps)
     std::vector<std::string> seg_word_store;
     // acmod's active-senone flags: left by the grammar search / found by the aligner
     std::vector<uint32_t> flags;
@@ -74,6 +75,7 @@ int search_start(ssb_search_t *s)
     S->n_seg = 0;
     S->exit_bp = 0;
     S->hyp_score = 0;
+    S->result_frames = -1;
     return 0;
 }
 
@@ -225,6 +227,7 @@ const char *align_hyp(ssb_search_t *s, int32_t *out_score)
 }
 
 ssb_seg_iter_t *seg_fill(SegImpl *it);
+bool fsg_have_result(SearchImpl *S);
 
 void seg_free(ssb_seg_iter_t *seg) { delete reinterpret_cast<SegImpl *>(seg); }
 
@@ -272,7 +275,7 @@ ssb_seg_iter_t *seg_fill(SegImpl *it)
 ssb_seg_iter_t *search_seg_iter(ssb_search_t *s)
 {
     SearchImpl *S = impl(s);
-    if (S->kind == 0 ? S->word.empty() : (!S->finished || S->exit_bp <= 0 || S->n_seg <= 0))
+    if (S->kind == 0 ? S->word.empty() : (!fsg_have_result(S) || S->exit_bp <= 0 || S->n_seg <= 0))
         return nullptr;
     SegImpl *it = new SegImpl;
     memset(&it->base, 0, sizeof it->base);
@@ -287,9 +290,11 @@ ssb_seg_iter_t *search_seg_iter(ssb_search_t *s)
 }
 
 // ---- fsg
-int fsg_finish(ssb_search_t *s)
+// The search over the frames collected so far.  partial: the utterance is still running -- the
+// hypothesis is what fsg_search_hyp / fsg_search_seg_iter give between two steps (best word exit
+// of the last frame that has one, final state or not; ref: src/fsg_search.c:853-924, 945-960)
+int fsg_run(SearchImpl *S, bool partial)
 {
-    SearchImpl *S = impl(s);
     const int64_t frame_off[2] = {0, S->n_frames};
     const int32_t utt_graph = 0;
     int max_seg = 256;
@@ -306,6 +311,7 @@ int fsg_finish(ssb_search_t *s)
         in.max_seg = max_seg;
         // the reference's default (compallsen = no) wherever the model allows it
         in.active_lists = ssb_model_fsg_active_ok(S->m);
+        in.partial = partial ? 1 : 0;
         S->flags.assign((size_t)(S->n_sen + 31) / 32, 0u);
         S->segs.assign((size_t)max_seg * 5, 0);
         int32_t n_seg = 0, score = 0, exit_bp = 0, rv = 0, n_hist = 0;
@@ -344,8 +350,30 @@ int fsg_finish(ssb_search_t *s)
         // fsg_model_word_str (ref: include/soundswallower/fsg_model.h:131)
         S->seg_word_store.push_back(wid < 0 ? "(NULL)" : ssb_fsg_built_word(S->fsg, wid, nullptr));
     }
+    S->result_frames = S->n_frames;
+    return 0;
+}
+
+int fsg_finish(ssb_search_t *s)
+{
+    SearchImpl *S = impl(s);
+    if (fsg_run(S, false) != 0)
+        return -1;
     S->finished = true;
     return 0;
+}
+
+// hyp / seg_iter between two steps: the reference answers from its history table as it stands;
+// here the frames collected so far are searched (once per frame count)
+bool fsg_have_result(SearchImpl *S)
+{
+    if (S->finished)
+        return true;
+    if (S->n_frames <= 0)
+        return false;
+    if (S->result_frames != S->n_frames && fsg_run(S, true) != 0)
+        return false;
+    return true;
 }
 
 const char *fsg_hyp(ssb_search_t *s, int32_t *out_score)
@@ -353,7 +381,7 @@ const char *fsg_hyp(ssb_search_t *s, int32_t *out_score)
     // ref: src/fsg_search.c:945-1026 -- words of the best final exit's backtrace, null
     // transitions and fillers left out, base strings of alternate pronunciations
     SearchImpl *S = impl(s);
-    if (!S->finished)
+    if (!fsg_have_result(S))
         return nullptr;
     if (out_score)
         *out_score = S->hyp_score;

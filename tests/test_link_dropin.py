@@ -60,3 +60,24 @@ def test_reference_decoder_runs_on_our_scorer(golden, lang):
     maps = open("/proc/self/maps").read()
     assert "libssb200.so" in maps
     r.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lang", ["en-us", "fr-fr"])
+def test_reference_decoder_asks_our_search_between_steps(golden, lang):
+    """decoder_hyp / decoder_seg_iter of the reference's decoder_t between two
+    search_module_step calls, served by our grammar search through the glue: the unmodified
+    reference's partial hypotheses (tests/golden/fsg_partial.npz)."""
+    if not os.path.exists(refshim.LIB_SSB):
+        pytest.skip("oracle/_ref/libssref_ssb.so not built")
+    pg = np.load(os.path.join(os.path.dirname(__file__), "golden", "fsg_partial.npz"))
+    r = refshim.Ref(model_dir(lang), lib=refshim.LIB_SSB)
+    stops = pg["%s_stops" % lang].tolist()
+    res = r.fsg_partial(golden[lang]["feat"], TEXT[lang], stops)
+    for k, x in enumerate(res):
+        assert (x["hyp"] or "") == str(pg["%s_hyp" % lang][k]), stops[k]
+        if x["hyp"]:
+            assert x["hyp_score"] == int(pg["%s_score" % lang][k]), stops[k]
+        n = int(pg["%s_nseg" % lang][k])
+        assert np.array_equal(x["segs"], pg["%s_segs" % lang][k, :n]), stops[k]
+    r.close()

@@ -122,6 +122,41 @@ def test_two_pass_through_the_vtables(models, golden, lang):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("lang", ["en-us", "fr-fr"])
+def test_hypothesis_between_steps(models, golden, lang):
+    """hyp / seg_iter while the utterance is running: what the reference's decoder_hyp /
+    decoder_seg_iter return between two search steps (find_exit with final = FALSE, ref:
+    src/fsg_search.c:853-960), then the final result after finish()."""
+    m, g = models(lang), golden[lang]
+    pg = np.load(os.path.join(os.path.dirname(__file__), "golden", "fsg_partial.npz"))
+    lx = ssb.Lexicon(m, hmmdir=model_dir(lang))
+    feat = g["feat"]
+    p1 = ssb.fsg_search(m, lx, TEXT[lang])
+    assert p1.start() == 0
+    assert p1.hyp()[0] is None and p1.seg() == []              # nothing yet
+    p1.feed(feat)
+    t = 0
+    for k, stop in enumerate(pg["%s_stops" % lang].tolist()):
+        while t < stop:
+            assert p1.step(t) == 1
+            t += 1
+        hyp, score = p1.hyp()
+        want = str(pg["%s_hyp" % lang][k])
+        assert (hyp or "") == want, (stop, hyp, want)
+        if want:
+            assert score == int(pg["%s_score" % lang][k]), stop
+        n = int(pg["%s_nseg" % lang][k])
+        seg = p1.seg()
+        assert [lx.wordid(s[0]) for s in seg] == pg["%s_segs" % lang][k, :n, 0].tolist(), stop
+        assert np.array_equal(np.array([s[1:] for s in seg], np.int32).reshape(-1, 4),
+                              pg["%s_segs" % lang][k, :n, 1:]), stop
+    assert t == len(feat) and p1.finish() == 0
+    hyp, score = p1.hyp()
+    assert hyp == TEXT[lang] and score == {"en-us": -2761, "fr-fr": -4236}[lang]
+    p1.close()
+
+
+@pytest.mark.gpu
 def test_feature_source_callback_equals_feed(models, golden):
     """The part acmod plays: step(frame_idx) pulls the frame through the callback."""
     m, g = models("en-us"), golden["en-us"]

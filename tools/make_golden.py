@@ -526,6 +526,31 @@ def lexicon():
     np.savez_compressed(os.path.join(OUT, "lexicon.npz"), **g)
 
 
+def fsg_partial():
+    """decoder_hyp / decoder_seg_iter BETWEEN steps of the grammar search (find_exit with final =
+    FALSE, ref: src/fsg_search.c:853-960), default mode, both models -> fsg_partial.npz."""
+    g = {}
+    for lang, text in (("en-us", "go forward ten meters"), ("fr-fr", "avance de dix mètres")):
+        ref = Ref(os.path.join(MODELS, lang))
+        feat = np.load(os.path.join(OUT, "align_%s.npz" % lang))["feat"]
+        T = feat.shape[0]
+        stops = sorted(set([1, 5, 20, 50, 60, 100, 150, 200, 250, T - 1, T]) & set(range(1, T + 1)))
+        res = ref.fsg_partial(feat, text, stops)
+        g["%s_stops" % lang] = np.asarray(stops, np.int32)
+        g["%s_hyp" % lang] = np.asarray([x["hyp"] if x["hyp"] is not None else "" for x in res])
+        g["%s_score" % lang] = np.asarray([x["hyp_score"] if x["hyp_score"] is not None else 0 for x in res], np.int32)
+        segs = np.full((len(stops), 16, 5), -9, np.int32)
+        nseg = np.zeros(len(stops), np.int32)
+        for k, x in enumerate(res):
+            nseg[k] = len(x["segs"])
+            segs[k, :nseg[k]] = x["segs"]
+        g["%s_segs" % lang] = segs
+        g["%s_nseg" % lang] = nseg
+        print(lang, [(t, x["hyp"], x["hyp_score"]) for t, x in zip(stops, res)])
+        ref.close()
+    np.savez_compressed(os.path.join(OUT, "fsg_partial.npz"), **g)
+
+
 def main():
     if not available():
         raise SystemExit("oracle/_ref/libssref.so missing: run `make -C oracle ref` first")
@@ -542,6 +567,8 @@ def main():
         return lexicon()
     if "--fsg-file" in sys.argv:
         return fsg_file()
+    if "--fsg-partial" in sys.argv:
+        return fsg_partial()
     if "--hmm5" in sys.argv:
         return hmm5()
     if "--five-state" in sys.argv:
@@ -557,6 +584,7 @@ def main():
     fsg_active("en-us", "go forward ten meters", "goforward.gram")
     fsg_active("fr-fr", "avance de dix mètres", "goforward_fr.gram")
     fsg_file()
+    fsg_partial()
     hmm5()
     five_state()
     loaders()
