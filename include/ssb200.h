@@ -210,6 +210,10 @@ int ssb_batch_stats(const ssb_batch_t *b, int64_t *out8);
  * [enter[i], max(enter[i], ef[i])] (the word-window band; ref: src/state_align_search.c:88-133).
  * out8[1] of ssb_batch_stats is the dense count T x states the reference allocates tokens for. */
 int64_t ssb_batch_band_state_frames(const ssb_batch_t *b);
+/* chain segments the Viterbi pass of the last upload runs on: chains are cut where one word window
+ * ends exactly where the next begins (the only frame the chain can be crossed on) and the
+ * segments are searched in parallel, with identical results; = n_utts when nothing is cut */
+int32_t ssb_batch_n_segments(const ssb_batch_t *b);
 
 /* upload + run + download in one call (the call a host program makes).  A batch of at least
  * two chunks (see ssb_pipeline_create) is routed through a temporary pipeline. */

@@ -392,7 +392,8 @@ class StateAlignBatch:
         return dict(frames=int(s[0]), state_frames=int(s[1]), active_senone_frames=int(s[2]),
                     scanned_cb_frames=int(s[3]), device_bytes=int(s[4]), max_union=int(s[5]),
                     max_phones=int(s[6]), plan_us=int(s[7]),
-                    band_state_frames=int(self.lib.ssb_batch_band_state_frames(self.b)))
+                    band_state_frames=int(self.lib.ssb_batch_band_state_frames(self.b)),
+                    segments=int(self.lib.ssb_batch_n_segments(self.b)))
 
 
 class _AlignCall(StateAlignBatch):

@@ -138,7 +138,7 @@ SYMBOLS = [
     "ssb_mgau_init", "ssb_mgau_frame_eval", "ssb_mgau_reset", "ssb_mgau_free", "ssb_mgau_own_model", "ssb_mgau_model",
     "ssb_plan_chain", "ssb_batch_create", "ssb_batch_free", "ssb_batch_upload", "ssb_batch_run",
     "ssb_batch_download", "ssb_batch_debug_tokens", "ssb_batch_kernel_ms",
-    "ssb_batch_n_launches", "ssb_batch_stats", "ssb_batch_band_state_frames", "ssb_align_batch", "ssb_align_batch_multi", "ssb_pipeline_create",
+    "ssb_batch_n_launches", "ssb_batch_stats", "ssb_batch_band_state_frames", "ssb_batch_n_segments", "ssb_align_batch", "ssb_align_batch_multi", "ssb_pipeline_create",
     "ssb_pipeline_align", "ssb_pipeline_submit", "ssb_pipeline_collect", "ssb_pipeline_set_overlap", "ssb_pipeline_n_launches", "ssb_pipeline_n_chunks", "ssb_pipeline_trace", "ssb_pipeline_free",
     "ssb_score_batch", "ssb_lexicon_basewid", "ssb_fsg_built_is_filler",
     "ssb_state_align_search_init", "ssb_fsg_search_init", "ssb_search_feed", "ssb_search_alignment", "ssb_search_final_active",
@@ -206,6 +206,8 @@ def load():
     L.ssb_batch_stats.argtypes = [vp, P(i64)]
     L.ssb_batch_band_state_frames.argtypes = [vp]
     L.ssb_batch_band_state_frames.restype = i64
+    L.ssb_batch_n_segments.argtypes = [vp]
+    L.ssb_batch_n_segments.restype = C.c_int32
     L.ssb_align_batch.argtypes = [vp, P(AlignIn), P(AlignOut)]
     L.ssb_align_batch_multi.argtypes = [P(vp), i32, P(AlignIn), P(AlignOut)]
     L.ssb_pipeline_create.restype = vp

@@ -742,6 +742,14 @@ struct ssb_batch_s {
     int n_tiles = 0;
     DBuf d_tile_utt, d_tile_t0, d_tile_ctr;
     DBuf d_scr_boff, d_tok_boff;
+    // chain cutting: K3 + backtrace run on segments of the utterances (cut_chains)
+    bool cut = false, cut_ran = false;  // planned / what the last run used
+    int n_segs = 0, cut_max_phones = 0, cut_max_band = 0;
+    std::vector<int32_t> seg_off;       // [U+1] segments of each utterance
+    std::vector<int64_t> seg_phone_off; // [S+1] (global phone index)
+    DevPlan cut_plan{};
+    DBuf d_seg_frame_off, d_seg_phone_off, d_seg_scr_off, d_seg_enter, d_seg_sf, d_seg_ef, d_seg_scr_boff,
+        d_seg_tok_boff, d_seg_t0, seg_rv, seg_best, seg_renorm, seg_fin_hist, seg_fin_score;
     // timing
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int n_launches = 0;
@@ -755,7 +763,10 @@ struct ssb_batch_s {
                              &utt_best, &utt_renorm, &fin_hist, &fin_score, &dense, &best_tmp,
                              &d_k1_frame_off, &d_k1_ep_off, &d_k1_ep_start, &d_k1_ep_cbmask,
                              &d_seg_utts, &d_k1_tie, &d_init_topn, &d_tile_utt, &d_tile_t0,
-                             &d_tile_ctr, &d_scr_boff, &d_tok_boff};
+                             &d_tile_ctr, &d_scr_boff, &d_tok_boff, &d_seg_frame_off, &d_seg_phone_off,
+                             &d_seg_scr_off, &d_seg_enter, &d_seg_sf, &d_seg_ef, &d_seg_scr_boff,
+                             &d_seg_tok_boff, &d_seg_t0, &seg_rv, &seg_best, &seg_renorm, &seg_fin_hist,
+                             &seg_fin_score};
         size_t n = 0;
         for (const DBuf *b : all)
             n += b->cap;
@@ -769,7 +780,10 @@ struct ssb_batch_s {
                        &d_st_slot, &d_enter, &st_start, &st_dur, &st_score, &utt_rv, &utt_best,
                        &utt_renorm, &fin_hist, &fin_score, &dense, &best_tmp, &d_k1_frame_off,
                        &d_k1_ep_off, &d_k1_ep_start, &d_k1_ep_cbmask, &d_seg_utts, &d_k1_tie,
-                       &d_init_topn, &d_tile_utt, &d_tile_t0, &d_tile_ctr, &d_scr_boff, &d_tok_boff};
+                       &d_init_topn, &d_tile_utt, &d_tile_t0, &d_tile_ctr, &d_scr_boff, &d_tok_boff,
+                       &d_seg_frame_off, &d_seg_phone_off, &d_seg_scr_off, &d_seg_enter, &d_seg_sf,
+                       &d_seg_ef, &d_seg_scr_boff, &d_seg_tok_boff, &d_seg_t0, &seg_rv, &seg_best,
+                       &seg_renorm, &seg_fin_hist, &seg_fin_score};
         for (DBuf *b : all)
             b->release();
     }
@@ -1283,8 +1297,10 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
     }
     // ---- chain scores and token stack
     b->n_band_scr = b->n_band_tok = 0;
+    std::vector<int64_t> sb, tb;
     if (b->banded) {
-        std::vector<int64_t> sb((size_t)b->n_phones + 1, 0), tb((size_t)b->n_phones + 1, 0);
+        sb.assign((size_t)b->n_phones + 1, 0);
+        tb.assign((size_t)b->n_phones + 1, 0);
         int64_t ns = 0, nt = 0;
         for (int u = 0; u < U; ++u) {
             const int64_t p0 = b->phone_off[u];
@@ -1356,6 +1372,7 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
     p.banded = b->banded ? 1 : 0;
     p.scr_boff = b->banded ? b->d_scr_boff.as<int64_t>() : nullptr;
     p.tok_boff = b->banded ? b->d_tok_boff.as<int64_t>() : nullptr;
+    p.seg_t0 = nullptr;
     p.tie_bits = nullptr;
     p.tie_w = 0;
     p.init_topn = nullptr;
@@ -1367,6 +1384,101 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
                                  cudaMemcpyDefault, st), -1);
         API_CUDA(cudaStreamSynchronize(st), -1);
         p.init_topn = b->d_init_topn.as<uchar4>();
+    }
+
+    // ---- chain cutting.  Where one word window ends exactly where the next begins, the chain can
+    // only be crossed on that one frame (prune_hmms / phone_transition, ref: src/
+    // state_align_search.c:88-133): what happens after the cut depends on what happened before
+    // only through the score the first phone is entered with, and integer max-plus arithmetic
+    // is shift invariant -- the phones after the cut see that score as their zero, exactly as
+    // the first phone of an utterance does (hmm_enter(hmms, 0, 0, 0), ref :46-55).  So K3 and the
+    // backtrace run on the SEGMENTS, one warp each, instead of one warp walking 360 000 frames of
+    // an hour-long chain; state scores are differences and come out as they are, start frames are
+    // shifted back by the backtrace, the utterance's best score is the sum of the segments' exit
+    // scores.  Absolute scores matter to the reference in one place, the renormalisation at
+    // best - 0x300000 < WORST_SCORE (ref :193-197): path scores only decrease, so a total above
+    // that line proves no frame was renormalised; otherwise ssb_batch_download runs the uncut
+    // kernels again.  Only with the banded layout (the dense debug stacks hold absolute scores),
+    // and by default only for chains of more than 128 phones ($SSB_K3_CUT = all | 0).
+    b->cut = false;
+    b->n_segs = 0;
+    {
+        const char *e = getenv("SSB_K3_CUT");
+        const bool cut_all = e && strcmp(e, "all") == 0, cut_off = e && *e == '0';
+        if (b->banded && !cut_off && U > 0 && b->n_phones > 0 && (cut_all || b->max_phones > 128)) {
+            std::vector<int64_t> sfo(1, b->frame_off[0]), spo(1, 0), sbo2(sb.begin(), sb.end()), tbo2(tb.begin(), tb.end());
+            std::vector<int32_t> st0, en2(b->enter), sf2(in->sf, in->sf + b->n_phones), ef2(in->ef, in->ef + b->n_phones);
+            b->seg_off.assign(1, 0);
+            b->cut_max_phones = 0;
+            auto shift = [&](int64_t pa, int64_t pb, int32_t t0) {
+                if (t0 == 0)
+                    return;
+                for (int64_t j = pa; j < pb; ++j) {
+                    if (en2[j] >= 0)
+                        en2[j] -= t0;
+                    sf2[j] = (int32_t)std::max<int64_t>((int64_t)sf2[j] - t0, INT32_MIN / 2);
+                    if (ef2[j] < INT32_MAX / 2)
+                        ef2[j] = (int32_t)std::max<int64_t>((int64_t)ef2[j] - t0, INT32_MIN / 2);
+                    sbo2[j] += (int64_t)t0 * E;
+                    tbo2[j] += (int64_t)t0 * E;
+                }
+            };
+            for (int u = 0; u < U; ++u) {
+                const int64_t p0 = b->phone_off[u];
+                const int np = (int)(b->phone_off[u + 1] - p0);
+                const int T = (int)(b->frame_off[u + 1] - b->frame_off[u]);
+                int a = 0;
+                int32_t t0 = 0;
+                if (cut_all || np > 128)
+                    for (int i = 1; i < np; ++i) {
+                        const int32_t s = in->sf[p0 + i];
+                        if (s > t0 && s < T && b->enter[p0 + i] == s && in->ef[p0 + i - 1] == s
+                            && b->enter[p0 + i - 1] >= 0 && b->enter[p0 + i - 1] < s) {
+                            shift(p0 + a, p0 + i, t0);
+                            st0.push_back(t0);
+                            sfo.push_back(b->frame_off[u] + s);
+                            spo.push_back(p0 + i);
+                            b->cut_max_phones = std::max(b->cut_max_phones, i - a);
+                            a = i;
+                            t0 = s;
+                        }
+                    }
+                shift(p0 + a, p0 + np, t0);
+                st0.push_back(t0);
+                sfo.push_back(b->frame_off[u + 1]);
+                spo.push_back(p0 + np);
+                b->cut_max_phones = std::max(b->cut_max_phones, np - a);
+                b->seg_off.push_back((int32_t)st0.size());
+            }
+            const int S = (int)st0.size();
+            if (S > U) {
+                std::vector<int64_t> zero((size_t)S + 1, 0);
+                if (upload(b->d_seg_frame_off, sfo, st) || upload(b->d_seg_phone_off, spo, st)
+                    || upload(b->d_seg_scr_off, zero, st) || upload(b->d_seg_enter, en2, st)
+                    || upload(b->d_seg_sf, sf2, st) || upload(b->d_seg_ef, ef2, st)
+                    || upload(b->d_seg_scr_boff, sbo2, st) || upload(b->d_seg_tok_boff, tbo2, st)
+                    || upload(b->d_seg_t0, st0, st) || b->seg_rv.ensure((size_t)S * 4) != 0
+                    || b->seg_best.ensure((size_t)S * 4) != 0 || b->seg_renorm.ensure((size_t)S * 4) != 0
+                    || b->seg_fin_hist.ensure((size_t)S * 4) != 0 || b->seg_fin_score.ensure((size_t)S * 4) != 0)
+                    return -1;
+                API_CUDA(cudaStreamSynchronize(st), -1);
+                b->cut = true;
+                b->n_segs = S;
+                b->seg_phone_off = spo;
+                b->cut_max_band = std::min(b->max_band, b->cut_max_phones);
+                b->cut_plan = p;
+                b->cut_plan.n_utts = S;
+                b->cut_plan.frame_off = b->d_seg_frame_off.as<int64_t>();
+                b->cut_plan.phone_off = b->d_seg_phone_off.as<int64_t>();
+                b->cut_plan.scr_off = b->d_seg_scr_off.as<int64_t>();
+                b->cut_plan.enter_plan = b->d_seg_enter.as<int32_t>();
+                b->cut_plan.sf = b->d_seg_sf.as<int32_t>();
+                b->cut_plan.ef = b->d_seg_ef.as<int32_t>();
+                b->cut_plan.scr_boff = b->d_seg_scr_boff.as<int64_t>();
+                b->cut_plan.tok_boff = b->d_seg_tok_boff.as<int64_t>();
+                b->cut_plan.seg_t0 = b->d_seg_t0.as<int32_t>();
+            }
+        }
     }
 
     // ---- K1 over time: with few utterances the top-N kernel (thread = utterance) has no rows
@@ -1560,6 +1672,44 @@ static int batch_topn(ssb_batch_t *b, uint32_t *tie, int64_t tie_w, bool fixup, 
     return 0;
 }
 
+// K3 + backtrace of the uploaded batch, on the utterances or (cut) on their segments
+static int run_chain(ssb_batch_t *b, bool cut, bool timed)
+{
+    const DevModel &d = b->m->d;
+    cudaStream_t st = b->st;
+    const int U = b->n_utts;
+    const DevPlan &p = cut ? b->cut_plan : b->plan;
+    if (U > 0) {
+        if (b->want_tokens_all && b->n_state_frames > 0)
+            API_CUDA(cudaMemsetAsync(b->tokens.p, 0xff, (size_t)b->n_state_frames * sizeof(int2), st), -1);
+        if (launch_chain_viterbi(d, p, b->chain_scr.as<int16_t>(), b->tokens.as<int2>(),
+                                 b->spill.as<int32_t>(), b->spill_stride,
+                                 (cut ? b->seg_best : b->utt_best).as<int32_t>(),
+                                 (cut ? b->seg_renorm : b->utt_renorm).as<int32_t>(),
+                                 (cut ? b->seg_fin_hist : b->fin_hist).as<int32_t>(),
+                                 (cut ? b->seg_fin_score : b->fin_score).as<int32_t>(),
+                                 cut ? b->cut_max_phones : b->max_phones, cut ? b->cut_max_band : b->max_band,
+                                 st) != 0)
+            return -1;
+    }
+    if (timed)
+        API_CUDA(cudaEventRecord(b->ev[3], st), -1);
+    if (U > 0) {
+        // duration -1 marks "state not on the best path"
+        if (b->n_states > 0) {
+            API_CUDA(cudaMemsetAsync(b->st_dur.p, 0xff, (size_t)b->n_states * 4, st), -1);
+            // 0x80808080 marks "score never written" (the first state of an utterance)
+            API_CUDA(cudaMemsetAsync(b->st_score.p, 0x80, (size_t)b->n_states * 4, st), -1);
+        }
+        if (launch_backtrace(d, p, b->tokens.as<int2>(), (cut ? b->seg_fin_hist : b->fin_hist).as<int32_t>(),
+                             (cut ? b->seg_fin_score : b->fin_score).as<int32_t>(), b->st_start.as<int32_t>(),
+                             b->st_dur.as<int32_t>(), b->st_score.as<int32_t>(),
+                             (cut ? b->seg_rv : b->utt_rv).as<int32_t>(), st) != 0)
+            return -1;
+    }
+    return 0;
+}
+
 // frames per dense slab in compallsen mode (whole utterances)
 static const int64_t kSlabFrames = 32768;
 
@@ -1615,30 +1765,9 @@ extern "C" int ssb_batch_run(ssb_batch_t *b)
         }
     }
     API_CUDA(cudaEventRecord(b->ev[2], st), -1);
-    if (U > 0) {
-        if (b->want_tokens_all && b->n_state_frames > 0)
-            API_CUDA(cudaMemsetAsync(b->tokens.p, 0xff, (size_t)b->n_state_frames * sizeof(int2), st), -1);
-        if (launch_chain_viterbi(d, p, b->chain_scr.as<int16_t>(), b->tokens.as<int2>(),
-                                 b->spill.as<int32_t>(), b->spill_stride,
-                                 b->utt_best.as<int32_t>(), b->utt_renorm.as<int32_t>(),
-                                 b->fin_hist.as<int32_t>(), b->fin_score.as<int32_t>(),
-                                 b->max_phones, b->max_band, st) != 0)
-            return -1;
-    }
-    API_CUDA(cudaEventRecord(b->ev[3], st), -1);
-    if (U > 0) {
-        // duration -1 marks "state not on the best path"
-        if (b->n_states > 0) {
-            API_CUDA(cudaMemsetAsync(b->st_dur.p, 0xff, (size_t)b->n_states * 4, st), -1);
-            // 0x80808080 marks "score never written" (the first state of an utterance)
-            API_CUDA(cudaMemsetAsync(b->st_score.p, 0x80, (size_t)b->n_states * 4, st), -1);
-        }
-        if (launch_backtrace(d, p, b->tokens.as<int2>(), b->fin_hist.as<int32_t>(),
-                             b->fin_score.as<int32_t>(), b->st_start.as<int32_t>(),
-                             b->st_dur.as<int32_t>(), b->st_score.as<int32_t>(),
-                             b->utt_rv.as<int32_t>(), st) != 0)
-            return -1;
-    }
+    if (run_chain(b, b->cut, true) != 0)
+        return -1;
+    b->cut_ran = b->cut;
     b->n_launches = launch_count(true);
     API_CUDA(cudaEventRecord(b->ev[4], st), -1);
     b->ran = true;
@@ -1660,6 +1789,48 @@ extern "C" int ssb_batch_download(ssb_batch_t *b, ssb_align_out_t *out)
     cudaStream_t st = b->st;
     const int U = b->n_utts;
     const size_t ns = (size_t)b->n_states;
+    // ---- cut chains: the utterances' verdicts from their segments'
+    std::vector<int32_t> c_rv, c_best;
+    if (b->cut_ran && U > 0) {
+        const int S = b->n_segs;
+        std::vector<int32_t> srv(S), sbest(S), sfin(S);
+        API_CUDA(cudaMemcpyAsync(srv.data(), b->seg_rv.p, (size_t)S * 4, cudaMemcpyDeviceToHost, st), -1);
+        API_CUDA(cudaMemcpyAsync(sbest.data(), b->seg_best.p, (size_t)S * 4, cudaMemcpyDeviceToHost, st), -1);
+        API_CUDA(cudaMemcpyAsync(sfin.data(), b->seg_fin_score.p, (size_t)S * 4, cudaMemcpyDeviceToHost, st), -1);
+        API_CUDA(cudaStreamSynchronize(st), -1);
+        c_rv.assign(U, 0);
+        c_best.assign(U, 0);
+        bool renorm = false;
+        for (int u = 0; u < U; ++u) {
+            int64_t total = 0;
+            for (int s = b->seg_off[u]; s < b->seg_off[u + 1]; ++s) {
+                if (srv[s] != 0)
+                    c_rv[u] = -1;
+                if (s + 1 < b->seg_off[u + 1])
+                    total += sfin[s];
+            }
+            const int last = b->seg_off[u + 1] - 1;
+            c_best[u] = (int32_t)(total + sbest[last]);
+            // no frame of the utterance saw best - 0x300000 < WORST_SCORE: scores along a path only
+            // decrease and every frame's best is at least the final path's score
+            if (c_rv[u] == 0 && total + sfin[last] - 0x300000 < (int64_t)WORST_SCORE)
+                renorm = true;
+            // a segment that cannot be crossed: the utterance fails ("Failed to reach final state
+            // in alignment"); what the reference leaves behind then (best score of the last
+            // frame, entries written before the backtrace gave up) comes from the uncut kernels
+            if (c_rv[u] != 0)
+                renorm = true;
+        }
+        if (renorm) {
+            // the reference renormalised somewhere (practically unreachable: ~10^8 frames) or an
+            // utterance failed: the uncut kernels reproduce either
+            if (run_chain(b, false, false) != 0)
+                return -1;
+            b->cut_ran = false;
+            c_rv.clear();
+            c_best.clear();
+        }
+    }
     std::vector<int32_t> s_start, s_dur, s_score;
     if (ns && (out->st_start || out->st_dur || out->st_score)) {
         s_start.resize(ns);
@@ -1669,12 +1840,23 @@ extern "C" int ssb_batch_download(ssb_batch_t *b, ssb_align_out_t *out)
         API_CUDA(cudaMemcpyAsync(s_dur.data(), b->st_dur.p, ns * 4, cudaMemcpyDeviceToHost, st), -1);
         API_CUDA(cudaMemcpyAsync(s_score.data(), b->st_score.p, ns * 4, cudaMemcpyDeviceToHost, st), -1);
     }
-    if (U && out->utt_rv)
-        API_CUDA(cudaMemcpyAsync(out->utt_rv, b->utt_rv.p, (size_t)U * 4, cudaMemcpyDeviceToHost, st), -1);
-    if (U && out->utt_best)
-        API_CUDA(cudaMemcpyAsync(out->utt_best, b->utt_best.p, (size_t)U * 4, cudaMemcpyDeviceToHost, st), -1);
-    if (U && out->utt_renorm)
-        API_CUDA(cudaMemcpyAsync(out->utt_renorm, b->utt_renorm.p, (size_t)U * 4, cudaMemcpyDeviceToHost, st), -1);
+    if (b->cut_ran) {
+        for (int u = 0; u < U; ++u) {
+            if (out->utt_rv)
+                out->utt_rv[u] = c_rv[u];
+            if (out->utt_best)
+                out->utt_best[u] = c_best[u];
+            if (out->utt_renorm)
+                out->utt_renorm[u] = 0;
+        }
+    } else {
+        if (U && out->utt_rv)
+            API_CUDA(cudaMemcpyAsync(out->utt_rv, b->utt_rv.p, (size_t)U * 4, cudaMemcpyDeviceToHost, st), -1);
+        if (U && out->utt_best)
+            API_CUDA(cudaMemcpyAsync(out->utt_best, b->utt_best.p, (size_t)U * 4, cudaMemcpyDeviceToHost, st), -1);
+        if (U && out->utt_renorm)
+            API_CUDA(cudaMemcpyAsync(out->utt_renorm, b->utt_renorm.p, (size_t)U * 4, cudaMemcpyDeviceToHost, st), -1);
+    }
     if (b->banded && b->n_state_frames && (out->chain_scr || out->tokens)) {
         set_error("dense chain scores / tokens were not kept (banded layout): call "
                   "ssb_batch_debug_tokens(b, 1) before ssb_batch_upload");
@@ -1752,6 +1934,11 @@ extern "C" int ssb_batch_stats(const ssb_batch_t *b, int64_t *o)
     o[6] = b->max_phones;
     o[7] = b->plan_us;
     return 0;
+}
+
+extern "C" int32_t ssb_batch_n_segments(const ssb_batch_t *b)
+{
+    return b ? (b->cut ? b->n_segs : b->n_utts) : -1;
 }
 
 extern "C" int64_t ssb_batch_band_state_frames(const ssb_batch_t *b)

@@ -328,6 +328,8 @@ backtrace_kernel(DevModel m, DevPlan p, const int2 *__restrict__ tokens,
     }
     const int32_t *enter = p.enter_plan + p.phone_off[u];
     const int32_t *ef = p.ef + p.phone_off[u];
+    // a segment of a cut chain: frames are reported in the real utterance's numbering
+    const int t0s = p.seg_t0 ? p.seg_t0[u] : 0;
     int32_t cur_id = last_id, last_frame = T;
     int cur_frame = T - 2;
     while (cur_frame >= 0) {
@@ -362,7 +364,7 @@ backtrace_kernel(DevModel m, DevPlan p, const int2 *__restrict__ tokens,
             return;
         }
         if (lane == 0) {
-            st_start[s0 + last_id] = f + 1;
+            st_start[s0 + last_id] = f + 1 + t0s;
             st_dur[s0 + last_id] = last_frame - (f + 1);
             st_score[s0 + last_id] = last_score - nsc;
         }
@@ -372,9 +374,14 @@ backtrace_kernel(DevModel m, DevPlan p, const int2 *__restrict__ tokens,
         cur_frame = f - 1;
     }
     if (lane == 0) {
-        // first state: score left alone by the reference (ref :256-261); report 0
-        st_start[s0] = 0;
+        // first state: score left alone by the reference (ref :256-261); report 0.  The first
+        // state of a later segment of a cut chain is an ordinary state boundary of the whole
+        // utterance: last.score - cur.score with cur = the entry token, whose score is this
+        // segment's zero.
+        st_start[s0] = t0s;
         st_dur[s0] = last_frame;
+        if (t0s > 0)
+            st_score[s0] = last_score;
         utt_rv[u] = 0;
     }
 }

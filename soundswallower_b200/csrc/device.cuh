@@ -122,6 +122,11 @@ struct DevPlan {
     int32_t banded;
     const int64_t *scr_boff;
     const int64_t *tok_boff;
+    // chain cutting (api.cu: cut_chains): the "utterances" of this plan are SEGMENTS of the real
+    // ones -- runs of phones between two points where the chain can only be crossed on one
+    // known frame (a word window ending where the next begins) -- and seg_t0[u] is the frame of
+    // the real utterance the segment starts on; null = the plan's utterances are the real ones
+    const int32_t *seg_t0;
 };
 
 // ---- kernel launchers (each returns 0 or -1 with the error set) ----
