@@ -870,14 +870,21 @@ extern "C" int ssb_plan_chain(int32_t np, int32_t T, const int32_t *sf, const in
 //     codebook is scanned (first pass / compallsen: 56 against 84 ms on 4096 x 10 s) and when
 //     lists are carried in from a first pass (no second instantiation at the register limit);
 //   * gmm_topn_tc2.cu (codebook-stream x 256 utterances per CTA, 16 warps per SM) -- measured
-//     faster for the aligner's active lists on short windows (26.5 against 28 ms on config #2).
+//     faster for the aligner's active lists on big batches (26.5 against 28 ms on config #2).
 // $SSB_K1 = ft / tc2 / fp32 forces one (A/B runs, profiles/prof_gmm_scan_ft_r2*.txt).
-static bool k1_frame_tiled(const DevModel &d, bool all_active, bool carried_lists)
+static bool k1_frame_tiled(const DevModel &d, bool all_active, bool carried_lists, int n_utts)
 {
     const char *k1 = getenv("SSB_K1");
     if (k1 && *k1)
         return strcmp(k1, "ft") == 0 && ft_supported(d);
-    return ft_supported(d) && (all_active || carried_lists);
+    if (const char *seg = getenv("SSB_K1_SEG"))
+        if (atoll(seg) > 0)
+            return false;  // (tests: the segmented tc2 launch)
+    // tc2's rows are utterances, 256 per CTA: below ~1000 utterances its CTAs are mostly idle
+    // lanes (or, for a long recording, a few hundred threads walking thousands of frames each),
+    // while the frame-tiled kernel fills the machine with 128-frame tiles of whatever there is:
+    // K1 of the 1-hour utterance 10.7 -> 2.6 ms
+    return ft_supported(d) && (all_active || carried_lists || n_utts < 1024);
 }
 
 // Planner threads of one batch: the host's cores are shared by the ranks / device threads of a
@@ -1489,7 +1496,7 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
     b->n_seg_utts = 0;
     b->ft = false;
     b->n_tiles = 0;
-    if (k1_frame_tiled(b->m->d, b->compallsen != 0, p.init_topn != nullptr) && U > 0 && G > 0) {
+    if (k1_frame_tiled(b->m->d, b->compallsen != 0, p.init_topn != nullptr, U) && U > 0 && G > 0) {
         // frame-tiled K1: every utterance is cut into tiles of 128 frames that are scored
         // independently; all utterances are candidates for the tie fix-up
         std::vector<int32_t> tu, tt, all_utts(U);

@@ -184,9 +184,12 @@ def _check_against_golden(r, g, mode):
     assert sha(r["tokens"]) == str(g[mode + "_tokens_sha"])
 
 
+@pytest.mark.parametrize("k1", ["", "tc2"])
 @pytest.mark.parametrize("lang", ["en-us", "fr-fr"])
 @pytest.mark.parametrize("mode", ["win", "nowin", "win_call"])
-def test_align_golden(models, golden, lang, mode):
+def test_align_golden(models, golden, lang, mode, k1, monkeypatch):
+    if k1:
+        monkeypatch.setenv("SSB_K1", k1)
     """Windowed / unwindowed, default (active-list) / compallsen scoring, vs the reference's
     own state_align_search run on the same features (tools/make_golden.py)."""
     m, g = models(lang), golden[lang]
@@ -220,8 +223,12 @@ def _random_batch(rs, o, n_utts, max_T=60, max_ph=14):
     return feats, chains
 
 
+@pytest.mark.parametrize("k1", ["", "tc2"])
 @pytest.mark.parametrize("compallsen", [False, True])
-def test_align_random_ragged_batch(models, oracles, compallsen):
+def test_align_random_ragged_batch(models, oracles, compallsen, k1, monkeypatch):
+    # (k1: the kernel a small batch gets by default -- frame-tiled -- and the big batches' tc2)
+    if k1:
+        monkeypatch.setenv("SSB_K1", k1)
     m, o = models("en-us"), oracles("en-us")
     rs = np.random.RandomState(21 + compallsen)
     feats, chains = _random_batch(rs, o, 40)
@@ -365,7 +372,8 @@ def test_align_states_off_path_keep_caller_values(models, golden):
     # gmm_topn_tc2, senone_mix, chain_viterbi, backtrace (+ pack_features with SSB_K1_PACK=1,
     # + topn_fixup when segmented)
     # (the frame-tiled K1 always runs the tie fix-up: 5 launches)
-    ft = os.environ.get("SSB_K1") == "ft"
+    # (small batches take the frame-tiled K1 by default)
+    ft = os.environ.get("SSB_K1", "") in ("", "ft") and not os.environ.get("SSB_K1_SEG")
     assert b.n_launches() == (5 if ft else 4 + bool(os.environ.get("SSB_K1_SEG")) + (os.environ.get("SSB_K1_PACK") == "1"))
     ms = b.kernel_ms()
     assert ms["total"] > 0

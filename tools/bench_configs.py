@@ -119,7 +119,8 @@ def config4(ssb, reps=714, frames_per_rep=504, from_text=True, peaks=None):
            "ms": ms["total"], "kernel_ms": ms, "audio_s_per_s": audio_s / (ms["total"] * 1e-3),
            "e2e_ms": wall * 1e3, "audio_s_per_s_e2e": audio_s / wall, "invariants_ok": ok,
            "device_bytes": st["device_bytes"], "state_frames_dense": st["state_frames"],
-           "band_state_frames": st["band_state_frames"],
+           "band_state_frames": st["band_state_frames"], "chain_segments": st["segments"],
+           "plan_us": st["plan_us"],
            "roofline": {"kernel": "chain_viterbi_kernel (K3)", "bound": "hbm", "unit": "GB/s", "peak": hbm,
                         "achieved": st["band_state_frames"] * 10 / k3 / 1e9,
                         "frac": st["band_state_frames"] * 10 / k3 / 1e9 / hbm,
