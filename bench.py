@@ -306,6 +306,24 @@ def main():
     if not torch.cuda.is_available() or ssb.device_count() == 0:
         raise SystemExit("bench.py needs a B200: the product has no CPU path")
     torch.cuda.set_device(local)
+    # One rank per GPU on a two-socket host: keep the rank's threads -- and with them the pinned
+    # staging buffers it allocates (first touch) -- on the CPUs next to its GPU, so that eight
+    # ranks' H2D copies do not cross the socket interconnect.  ($SSB_BENCH_NUMA=0: leave it alone.)
+    numa_note = None
+    if world > 1 and os.environ.get("SSB_BENCH_NUMA", "1") != "0" and hasattr(os, "sched_setaffinity"):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            ncpu = os.cpu_count() or 1
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+            cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+            cpus &= set(os.sched_getaffinity(0))
+            if cpus and len(cpus) < len(os.sched_getaffinity(0)):
+                os.sched_setaffinity(0, cpus)
+                numa_note = "rank pinned to the %d CPUs local to its GPU" % len(cpus)
+        except Exception as e:  # noqa: BLE001 -- a box without NVML affinity data runs unpinned
+            numa_note = "not pinned (%s)" % type(e).__name__
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -585,6 +603,7 @@ def main():
         "gpu_launches": launches,
         "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items()},
         "clocks": clocks,
+        "host_affinity": numa_note,
         "roofline": {"kernel": "gmm_topn_tc2_kernel (K1: tcgen05 3xTF32 screening GEMM in TMEM + exact "
                                "FP32 survivors + top-N)" if not os.environ.get("SSB_K1") else
                                "K1 variant SSB_K1=%s" % os.environ.get("SSB_K1"),

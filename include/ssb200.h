@@ -607,7 +607,9 @@ int64_t ssb_frontend_run(ssb_frontend_t *fe, const void *pcm, int32_t encoding,
 int ssb_frontend_download(ssb_frontend_t *fe, int64_t *frame_off, float *mfcc, float *feat);
 /* device pointer to feat [frames][3*ncep] of the last run, valid until the next run: may be
  * passed as `feat` of ssb_align_in_t / ssb_fsg_in_t / ssb_score_batch (those accept host or
- * device memory) so that features never visit the host */
+ * device memory) so that features never visit the host.  A frontend created on the default
+ * stream leaves its work queued there (the consumers wait for that stream); one created on a
+ * stream of its own is synchronised by this call. */
 const float *ssb_frontend_feat_device(const ssb_frontend_t *fe);
 /* CUDA-event durations (ms) of the last run: [0] mel spectrum [1] noise tracker
  * [2] cepstrum [3] CMN sums [4] dynamic features [5] whole run incl. the upload */

@@ -2307,6 +2307,8 @@ extern "C" int ssb_align_batch(ssb_model_t *m, const ssb_align_in_t *in, ssb_ali
             return rv;
         }
     }
+    if (need_device(m) != 0)
+        return -1;
     ssb_batch_t *b = ssb_batch_create(m, nullptr);
     if (!b)
         return -1;
@@ -2799,6 +2801,8 @@ extern "C" int ssb_fsg_batch(ssb_model_t *m, const ssb_fsg_in_t *in, ssb_fsg_out
         for (int u = 0; u < U; ++u)
             aws_off[u + 1] = aws_off[u] + (int64_t)fsg_active_ws_ints(m->d, hdr[utt_graph[u]].n_pnode);
     }
+    if (need_device(m) != 0)
+        return -1;
     ssb_batch_t *b = ssb_batch_create(m, nullptr);
     if (!b)
         return -1;

@@ -1216,6 +1216,12 @@ extern "C" const float *ssb_frontend_feat_device(const ssb_frontend_t *fe)
         set_error("ssb_frontend_feat_device: nothing has been run");
         return nullptr;
     }
+    // consumers run on other streams (the one-shot entry points on a stream of their own, ordered
+    // after the legacy default stream only): a frontend on a stream of its own is waited for here
+    if (fe->st != nullptr) {
+        cudaSetDevice(fe->device);
+        cudaStreamSynchronize(fe->st);
+    }
     return fe->feat.as<float>();
 }
 

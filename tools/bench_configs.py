@@ -208,7 +208,7 @@ def config5_two_pass(ssb, model, total_utts=65536, rank=0, world=1, chunk=4096, 
         n_chunks = min(n_chunks, max_chunks)
     flat, n = two_pass_pool(chunk, pinned)
     text = " ".join(["go forward ten meters"] * 3)
-    n_workers = max(1, int(os.environ.get("SSB_TWO_PASS_WORKERS", "1")))
+    n_workers = max(1, int(os.environ.get("SSB_TWO_PASS_WORKERS", "2")))
 
     class Worker:
         """One host thread's objects: while its chunk is in host code (grammars, chains, JSON) the
@@ -216,7 +216,14 @@ def config5_two_pass(ssb, model, total_utts=65536, rank=0, world=1, chunk=4096, 
 
         def __init__(self):
             self.lx = ssb.Lexicon(model, hmmdir=hmm)
-            self.fe = ssb.Frontend(hmm, device=model.device)
+            # (several workers: each frontend on a stream of its own, so that one worker's audio
+            # copy and kernels do not queue behind the other's on the shared default stream)
+            self.stream = None
+            if n_workers > 1:
+                import torch
+                self.stream = torch.cuda.Stream(device=model.device)
+            self.fe = ssb.Frontend(hmm, device=model.device,
+                                   stream=self.stream.cuda_stream if self.stream else None)
 
         def one(self, k_utts):
             off = np.arange(k_utts + 1, dtype=np.int64) * n
