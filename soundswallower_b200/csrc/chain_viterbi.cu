@@ -49,37 +49,73 @@ __device__ __forceinline__ void cta_sync(int nwarps)
         __syncthreads();
 }
 
+// the synchronisation domain of one utterance: a group of L lanes (L < 32), or the CTA
+template <int L>
+__device__ __forceinline__ void group_sync(int nwarps)
+{
+    if (L < 32)
+        __syncwarp();  // (the whole warp: its groups stay converged)
+    else
+        cta_sync(nwarps);
+}
+
+template <int L>
+__device__ __forceinline__ int32_t group_max(int32_t v, int32_t *red, int nwarps)
+{
+    if (L < 32) {
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1)
+            v = max(v, __shfl_xor_sync(0xffffffffu, v, o));  // (xor < L stays inside the group)
+        return v;
+    }
+    return block_max(v, red, nwarps);
+}
+
 // Shared (or, for very long chains, global) state of one utterance's chain:
 //   sc[E][np] hi[E][np] osc[np] ohi[np]
 constexpr int K3_RING = 64;  // ring of HMM states in shared memory (band narrower than this)
 #define IX(i) (RING ? ((i) & (K3_RING - 1)) : (i))
 
-template <int E, bool RING>
-__global__ void __launch_bounds__(1024)
+template <int E, bool RING, int L>
+__global__ void __launch_bounds__(L < 32 ? 128 : 1024)
 chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_scr,
                      int2 *__restrict__ tokens, int32_t *__restrict__ spill,
                      int64_t spill_stride, int32_t *__restrict__ utt_best,
                      int32_t *__restrict__ utt_renorm, int32_t *__restrict__ fin_hist,
                      int32_t *__restrict__ fin_score, int smem_phones)
 {
-    extern __shared__ int32_t sh[];
+    extern __shared__ int32_t sh_all[];
     __shared__ int32_t red[32];
-    const int u = blockIdx.x;
-    const int nwarps = blockDim.x >> 5;
+    // L < 32: a GROUP of L lanes per utterance, 32 / L utterances per warp -- the evaluated band is
+    // a handful of phones, so that a whole warp per utterance leaves most lanes idle.  The groups
+    // of a warp stay CONVERGED (that is the point: one instruction serves four utterances): they
+    // walk the frames in step up to the longest of them, a group past its last frame only
+    // keeps the warp-wide synchronisations company.  L == 32: the CTA.
+    const int tid = L < 32 ? (int)(threadIdx.x % L) : (int)threadIdx.x;
+    const int nthr = L < 32 ? L : (int)blockDim.x;
+    const int u_raw = L < 32 ? (int)(blockIdx.x * (blockDim.x / L) + threadIdx.x / L) : (int)blockIdx.x;
+    const bool live = u_raw < p.n_utts;
+    const int u = live ? u_raw : 0;
+    const int nwarps = L < 32 ? 1 : (int)(blockDim.x >> 5);
+    int32_t *sh = sh_all + (L < 32 ? (size_t)(threadIdx.x / L) * (size_t)smem_phones * (2 * E + 2) : (size_t)0);
     const int64_t g0 = p.frame_off[u];
-    const int T = (int)(p.frame_off[u + 1] - g0);
     const int64_t ph0 = p.phone_off[u];
     const int np = (int)(p.phone_off[u + 1] - ph0);
     const int ns = np * E;
-    if (np == 0) {
-        if (threadIdx.x == 0) {
-            utt_best[u] = 0;
-            utt_renorm[u] = 0;
-            fin_hist[u] = -1;
-            fin_score[u] = WORST_SCORE;
-        }
-        return;
+    const bool valid = live && np > 0;
+    if (live && np == 0 && tid == 0) {
+        utt_best[u] = 0;
+        utt_renorm[u] = 0;
+        fin_hist[u] = -1;
+        fin_score[u] = WORST_SCORE;
     }
+    if (L == 32 && !valid)
+        return;
+    const int T = valid ? (int)(p.frame_off[u + 1] - g0) : 0;
+    int Tloop = T;
+    if (L < 32)
+        for (int o = 16; o > 0; o >>= 1)
+            Tloop = max(Tloop, __shfl_xor_sync(0xffffffffu, Tloop, o));
     // RING: only the band of phones that is alive (a word window's worth) is kept, phone i in slot
     // i mod 64 -- a phone that has left the band is never looked at again (its successor enters
     // while it is still being evaluated: api.cu plan_enter) -- so that book-length chains run in
@@ -96,7 +132,7 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
     int2 *tok = tokens + p.scr_off[u];
 
     // hmm_clear on every phone, hmm_enter(hmms, 0, 0, 0) (ref: state_align_search.c:46-55)
-    for (int i = threadIdx.x; i < W; i += blockDim.x) {
+    for (int i = tid; i < (valid ? W : 0); i += nthr) {
 #pragma unroll
         for (int j = 0; j < E; ++j) {
             sc[j * W + i] = WORST_SCORE;
@@ -105,34 +141,37 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
         osc[i] = WORST_SCORE;
         ohi[i] = -1;
     }
-    cta_sync(nwarps);
-    if (threadIdx.x == 0) {
+    group_sync<L>(nwarps);
+    if (tid == 0 && valid) {
         sc[0] = 0;
         hi[0] = 0;
     }
-    cta_sync(nwarps);
+    group_sync<L>(nwarps);
 
     int32_t best = 0, n_renorm = 0;
     int lo = 0, hiq = 0;  // phones [lo, hiq] are evaluated on frame t
     // the two plan values the band bookkeeping looks at on every frame, kept in registers:
     // the entry frame of the next phone (-1: none / never) and the last frame of phone lo
-    int nx_en = np > 1 ? enter[1] : -1;
-    int lo_end = max(enter[0], ef[0]);
-    for (int t = 0; t < T; ++t) {
+    int nx_en = valid && np > 1 ? enter[1] : -1;
+    int lo_end = valid ? max(enter[0], ef[0]) : 0;
+    for (int t = 0; t < Tloop; ++t) {
         const int nf = t + 1;
-        while (nx_en >= 0 && nx_en <= t) {
-            ++hiq;
-            nx_en = hiq + 1 < np ? enter[hiq + 1] : -1;
+        const bool on = t < T;  // (L < 32: this group's utterance is still running)
+        if (on) {
+            while (nx_en >= 0 && nx_en <= t) {
+                ++hiq;
+                nx_en = hiq + 1 < np ? enter[hiq + 1] : -1;
+            }
+            while (lo < hiq && lo_end < t) {
+                ++lo;
+                lo_end = max(enter[lo], ef[lo]);
+            }
         }
-        while (lo < hiq && lo_end < t) {
-            ++lo;
-            lo_end = max(enter[lo], ef[lo]);
-        }
-        const bool lo_alive = lo_end >= t;  // lo == hiq may have expired too
+        const bool lo_alive = on && lo_end >= t;  // lo == hiq may have expired too
         // renormalize_hmms (ref: state_align_search.c:57-64,193-197; hmm.c:150-161):
         // every phone, alive or not, whose scores are above WORST_SCORE
-        if (best - 0x300000 < WORST_SCORE) {
-            for (int i = (RING ? lo : 0) + threadIdx.x; i <= (RING ? hiq : np - 1); i += blockDim.x) {
+        if (on && best - 0x300000 < WORST_SCORE) {
+            for (int i = (RING ? lo : 0) + tid; i <= (RING ? hiq : np - 1); i += nthr) {
 #pragma unroll
                 for (int j = 0; j < E; ++j)
                     if (sc[j * W + IX(i)] > WORST_SCORE)
@@ -141,14 +180,17 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
                     osc[IX(i)] -= best;
             }
             ++n_renorm;
-            cta_sync(nwarps);
+            if (L == 32)
+                group_sync<L>(nwarps);
         }
+        if (L < 32)
+            group_sync<L>(nwarps);
         // evaluate_hmms (ref :66-86)
         int32_t lb = WORST_SCORE;
         const int16_t *scr_t = scr + (int64_t)t * ns;
         int2 *tok_t = tok + (int64_t)t * ns;
         if (lo_alive) {
-            for (int i = lo + threadIdx.x; i <= hiq; i += blockDim.x) {
+            for (int i = lo + tid; i <= hiq; i += nthr) {
                 int32_t s[E], h[E], o_s = osc[IX(i)], o_h = ohi[IX(i)];
                 int ss[E];
 #pragma unroll
@@ -177,14 +219,18 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
                 ohi[IX(i)] = o_h;
             }
         }
-        cta_sync(nwarps);
-        best = block_max(lb, red, nwarps);
+        group_sync<L>(nwarps);
+        {
+            const int32_t gm = group_max<L>(lb, red, nwarps);
+            if (on)
+                best = gm;
+        }
         // prune_hmms + phone_transition + record_transitions (ref :88-175), one target phone
         // per thread.  Targets: the evaluated band plus every phone the plan enters at nf
         // (several when the reference's transition loop cascades along the chain).
         const int first = lo_alive ? lo : hiq + 1;
-        int last_t = hiq;
-        if (nx_en == nf) {
+        int last_t = on ? hiq : first - 1;
+        if (on && nx_en == nf) {
             ++last_t;
             while (last_t + 1 < np && enter[last_t + 1] == nf)
                 ++last_t;
@@ -192,7 +238,7 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
         if (RING && last_t > hiq) {
             // the slots of the phones entering now: their previous tenants have left the band
             // (hmm_clear), before anybody reads a neighbour's exit score
-            for (int i = hiq + 1 + threadIdx.x; i <= last_t; i += blockDim.x) {
+            for (int i = hiq + 1 + tid; i <= last_t; i += nthr) {
 #pragma unroll
                 for (int j = 0; j < E; ++j) {
                     sc[j * W + IX(i)] = WORST_SCORE;
@@ -201,9 +247,9 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
                 osc[IX(i)] = WORST_SCORE;
                 ohi[IX(i)] = -1;
             }
-            cta_sync(nwarps);
+            group_sync<L>(nwarps);
         }
-        for (int i = first + threadIdx.x; i <= last_t; i += blockDim.x) {
+        for (int i = first + tid; i <= last_t; i += nthr) {
             const bool was_active = i <= hiq;  // evaluated on frame t
             bool now = was_active;             // hmm_frame(hmm) >= t after this step
             if (i > 0) {
@@ -239,9 +285,9 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
                 }
             }
         }
-        cta_sync(nwarps);
+        group_sync<L>(nwarps);
     }
-    if (threadIdx.x == 0) {
+    if (tid == 0 && valid) {
         utt_best[u] = best;
         utt_renorm[u] = n_renorm;
         // (a last phone that was never entered still holds hmm_clear's values)
@@ -274,18 +320,39 @@ int launch_chain_viterbi(const DevModel &m, const DevPlan &p, const int16_t *cha
     int smem_phones = (int)((200 * 1024) / per_phone);
     if (max_phones < smem_phones)
         smem_phones = max_phones;
-    const size_t smem = per_phone * (ring ? K3_RING : smem_phones);
-#define SSB_K3(EE, RR)                                                                               \
+    // Short chains with a narrow band (ordinary sentences with word windows: ~4 phones alive):
+    // 16 lanes per utterance, 8 utterances per 128-thread CTA, instead of a warp each with most of
+    // its lanes idle (config #2: 1.66 -> 1.25 ms; the frame loop stays latency-bound: one dependent
+    // score load per frame).  $SSB_K3_LANES forces 8 / 16 / 32.
+    int lanes = 32;
+    if (!ring && max_phones <= 128 && max_band > 0) {
+        lanes = max_band <= 20 ? 16 : 32;  // (8 measured slower than 16 on config #2: 1.80 / 1.25 / 1.66 ms)
+        if (const char *e = getenv("SSB_K3_LANES"))
+            if (atoi(e) == 8 || atoi(e) == 16 || atoi(e) == 32)
+                lanes = atoi(e);
+    }
+    const int groups = lanes < 32 ? 128 / lanes : 1;
+    const size_t smem = per_phone * (ring ? K3_RING : smem_phones) * groups;
+    const unsigned grid = lanes < 32 ? (unsigned)((p.n_utts + groups - 1) / groups) : (unsigned)p.n_utts;
+    if (lanes < 32)
+        threads = 128;
+#define SSB_K3(EE, RR, LL)                                                                           \
     do {                                                                                             \
-        SSB_DYN_SMEM((chain_viterbi_kernel<EE, RR>), smem);                                          \
-        chain_viterbi_kernel<EE, RR><<<p.n_utts, threads, smem, st>>>(                               \
+        SSB_DYN_SMEM((chain_viterbi_kernel<EE, RR, LL>), smem);                                      \
+        chain_viterbi_kernel<EE, RR, LL><<<grid, threads, smem, st>>>(                               \
             m, p, chain_scr, tokens, spill, spill_stride, utt_best, utt_renorm, fin_hist, fin_score, \
             smem_phones);                                                                            \
     } while (0)
     if (E == 3) {
-        if (ring) SSB_K3(3, true); else SSB_K3(3, false);
+        if (ring) SSB_K3(3, true, 32);
+        else if (lanes == 8) SSB_K3(3, false, 8);
+        else if (lanes == 16) SSB_K3(3, false, 16);
+        else SSB_K3(3, false, 32);
     } else {
-        if (ring) SSB_K3(5, true); else SSB_K3(5, false);
+        if (ring) SSB_K3(5, true, 32);
+        else if (lanes == 8) SSB_K3(5, false, 8);
+        else if (lanes == 16) SSB_K3(5, false, 16);
+        else SSB_K3(5, false, 32);
     }
 #undef SSB_K3
     SSB_CUDA(cudaGetLastError());
