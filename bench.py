@@ -550,15 +550,17 @@ def main():
     except Exception:
         pass
     # DRAM traffic of the dominant kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of
-    # one `ncu --set full` capture of this very launch shape (tools/profile_r1j.sh)
+    # one `ncu --set full` capture of this very launch shape (tools/profile_r2j.sh)
     traffic = None
     try:
         if U == 4096 and not args.compallsen:
             vals = {}
-            for ln in open(os.path.join(ROOT, "profiles", "prof_gmm_topn_r1j.txt")):
+            unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+            for ln in open(os.path.join(ROOT, "profiles", "prof_gmm_topn_r2j.txt")):
                 f = ln.split()
                 if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                    vals[f[0]] = float(f[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[2]]
+                    # (tools/ncu_digest.py prints name unit value, tools/summarise_profiles.py name value unit)
+                    vals[f[0]] = float(f[2]) * unit[f[1]] if f[1] in unit else float(f[1]) * unit[f[2]]
             if len(vals) == 2:
                 traffic = sum(vals.values())
     except Exception:
@@ -610,7 +612,7 @@ def main():
                      "bound": "tensor",
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf, "traffic": traffic,
-                     "traffic_source": "profiles/prof_gmm_topn_r1j.txt (ncu --set full, same launch shape), bytes per launch",
+                     "traffic_source": "profiles/prof_gmm_topn_r2j.txt (ncu --set full, same launch shape, this round's build), bytes per launch",
                      "peak_source": peak_src,
                      "note": "achieved = ALGORITHMIC flops (SURVEY 8d: scanned codebook-frames x 3 streams x "
                              "128 densities x 2(2*13+1)) / CUDA-event time of the kernel; the MMAs actually "
