@@ -298,7 +298,10 @@ int fsg_run(SearchImpl *S, bool partial)
     const int64_t frame_off[2] = {0, S->n_frames};
     const int32_t utt_graph = 0;
     int max_seg = 256;
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    // the reference's history table and segment iterator are unbounded (ref: src/fsg_history.c:
+    // 129-232); here they have capacities, grown and tried again when an utterance exceeds them
+    int hist_cap = std::max(4096, 8 * S->n_frames);
+    for (int attempt = 0; attempt < 8; ++attempt) {
         ssb_fsg_in_t in;
         memset(&in, 0, sizeof in);
         in.n_utts = 1;
@@ -307,7 +310,7 @@ int fsg_run(SearchImpl *S, bool partial)
         in.n_graphs = 1;
         in.graphs = ssb_fsg_built_graph(S->fsg);
         in.utt_graph = &utt_graph;
-        in.hist_cap = std::max(4096, 8 * S->n_frames);
+        in.hist_cap = hist_cap;
         in.max_seg = max_seg;
         // the reference's default (compallsen = no) wherever the model allows it
         in.active_lists = ssb_model_fsg_active_ok(S->m);
@@ -329,10 +332,14 @@ int fsg_run(SearchImpl *S, bool partial)
         if (ssb_fsg_batch(S->m, &in, &out) != 0)
             return -1;
         if (rv != 0) {
+            if (attempt + 1 < 8 && hist_cap < (1 << 28)) {
+                hist_cap *= 2;
+                continue;
+            }
             set_error("fsg search: history overflow (%d entries)", in.hist_cap);
             return -1;
         }
-        if (n_seg < 0 && attempt == 0) {  // segmentation longer than max_seg: ask again
+        if (n_seg < 0 && attempt + 1 < 8) {  // segmentation longer than max_seg: ask again
             max_seg = -n_seg;
             continue;
         }
