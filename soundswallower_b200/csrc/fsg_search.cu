@@ -511,12 +511,8 @@ __device__ int score_active_frame(const DevModel &m, const FsgUtt &s, const FsgS
                 if (k == 0)
                     fden = v;
                 else {
-                    int d = fden - v, r = v;
-                    if (d <= 0) {
-                        d = -d;
-                        r = fden;
-                    }
-                    fden = r - q.lut[d];
+                    // min(a, b) - lut[|a - b|]  (= the reference's branchy form, senone_mix.cu: logadd8)
+                    fden = min(fden, v) - (int)q.lut[__sad(fden, v, 0u)];
                 }
             }
             ascore += fden;

@@ -23,14 +23,13 @@
 
 namespace ssb {
 
+// fast_logmath_add on the 8-bit table (ref: src/ptm_mgau.c:40-56 via logmath's shifted table): the
+// reference keeps the smaller of the two and subtracts table[difference] -- it takes its
+// (mlx > mly) branch only when strictly greater, which for equal values picks the same number --
+// i.e. min(a, b) - lut[|a - b|]: one min, one absolute difference (VABSDIFF), one table read
 __device__ __forceinline__ int logadd8(int a, int b, const uint8_t *lut)
 {
-    int d = a - b, r = b;
-    if (d <= 0) {  // ref takes the (mlx > mly) branch only when strictly greater
-        d = -d;
-        r = a;
-    }
-    return r - lut[d];
+    return min(a, b) - (int)lut[__sad(a, b, 0u)];
 }
 
 // Normalised, clamped scores of one codebook-stream.  For the semi-continuous scorer the
@@ -57,7 +56,13 @@ __device__ __forceinline__ uchar4 norm_scores(const DevModel &m, int f, int nm, 
 
 constexpr int K2_THREADS = 256;
 constexpr int K2_WARPS = K2_THREADS / 32;
-constexpr int K2_CS_PER_LANE = 4;  // codebook-streams per lane: CS <= 128
+constexpr int K2_CS_PER_LANE = 4;
+// resident CTAs per SM the active-list kernel is compiled for: left alone the compiler takes 120
+// registers (2 CTAs per SM, 6.07 ms on config #2); 3 -> 80 registers, no spills, 5.41 ms; 4 -> 64
+// registers with spills, 5.70 ms; 5 -> 6.09 ms
+#ifndef K2_MIN_BLOCKS
+#define K2_MIN_BLOCKS 3
+#endif  // codebook-streams per lane: CS <= 128
 
 // ---------------------------------------------------------------- active lists
 // CTA = (utterance, run of frames); the mixture-weight columns of the utterance's senone
@@ -68,7 +73,7 @@ constexpr int K2_CS_PER_LANE = 4;  // codebook-streams per lane: CS <= 128
 // unused-entry test and no trip-count test in the innermost loop (they cost 2.8 of 11 ms on
 // config #2), no runtime divisions by the stream count.
 template <bool STAGED, bool PTM4>
-__global__ void __launch_bounds__(K2_THREADS)
+__global__ void __launch_bounds__(K2_THREADS, K2_MIN_BLOCKS)
 senone_mix_active_kernel(DevModel m, DevPlan p, const int4 *__restrict__ tn_s,
                          const uchar4 *__restrict__ tn_c, int64_t G, int W, int chunk,
                          int16_t *__restrict__ chain_scr)
