@@ -64,8 +64,18 @@ topn_fixup_kernel(DevModel m, DevPlan p, const int32_t *__restrict__ seg_utts,
     const int64_t g0 = p.frame_off[u];
     const int T = (int)(p.frame_off[u + 1] - g0);
     const int e_lo = p.all_active ? 0 : p.ep_off[u], e_hi = p.all_active ? 0 : p.ep_off[u + 1];
-    for (int64_t w = g0 >> 5; w <= (g0 + T - 1) >> 5; ++w) {
-        uint32_t bits = tie[(int64_t)cs * tie_w + w];
+    // the utterance's flag words, 32 at a time (one coalesced read; a long recording has tens of
+    // thousands of them per codebook-stream and almost all are zero); the flagged steps are then
+    // replayed in time order -- a replay's list is what the next one starts from
+    const int64_t w_lo = g0 >> 5, w_hi = T > 0 ? (g0 + T - 1) >> 5 : w_lo - 1;
+    for (int64_t wb = w_lo; wb <= w_hi; wb += 32) {
+      const uint32_t mine = wb + lane <= w_hi ? tie[(int64_t)cs * tie_w + wb + lane] : 0u;
+      uint32_t nz = __ballot_sync(0xffffffffu, mine != 0u);
+      while (nz) {
+        const int src = __ffs((int)nz) - 1;
+        nz &= nz - 1u;
+        const int64_t w = wb + src;
+        uint32_t bits = __shfl_sync(0xffffffffu, mine, src);
         while (bits) {
             const int64_t g = w * 32 + (__ffs((int)bits) - 1);
             bits &= bits - 1;
@@ -90,14 +100,23 @@ topn_fixup_kernel(DevModel m, DevPlan p, const int32_t *__restrict__ seg_utts,
                 // whose mask holds it (the evaluated list is not monotone -- the >255-gap bridging
                 // senones come and go, ref: src/acmod.c:968-973)
                 int t_prev = p.all_active ? t - 1 : -1;
-                for (int e = e_lo; e < e_hi; ++e) {
-                    const int s0 = p.ep_start[e];
-                    if (s0 >= t)
-                        break;
-                    if ((p.ep_cbmask[(int64_t)e * 8 + (cb >> 5)] >> (cb & 31)) & 1u) {
-                        const int s1 = e + 1 < e_hi ? p.ep_start[e + 1] : T;
-                        t_prev = min(s1, t) - 1;
+                {
+                    // (the last epoch that starts before t and holds the codebook: binary search for
+                    // the first epoch at or after t, then backwards)
+                    int a = e_lo, b = e_hi;
+                    while (a < b) {
+                        const int mid = (a + b) >> 1;
+                        if (p.ep_start[mid] >= t)
+                            b = mid;
+                        else
+                            a = mid + 1;
                     }
+                    for (int e = a - 1; e >= e_lo; --e)
+                        if ((p.ep_cbmask[(int64_t)e * 8 + (cb >> 5)] >> (cb & 31)) & 1u) {
+                            const int s1 = e + 1 < e_hi ? p.ep_start[e + 1] : T;
+                            t_prev = min(s1, t) - 1;
+                            break;
+                        }
                 }
                 if (t_prev >= 0) {
                     // the final list of that scan (already replayed if it was flagged itself)
@@ -179,6 +198,7 @@ topn_fixup_kernel(DevModel m, DevPlan p, const int32_t *__restrict__ seg_utts,
             }
             __syncwarp();
         }
+      }
     }
 }
 
