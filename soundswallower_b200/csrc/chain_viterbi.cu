@@ -76,6 +76,13 @@ __device__ __forceinline__ int32_t group_max(int32_t v, int32_t *red, int nwarps
 constexpr int K3_RING = 64;  // ring of HMM states in shared memory (band narrower than this)
 #define IX(i) (RING ? ((i) & (K3_RING - 1)) : (i))
 
+// int32 words between the shared-memory states of two groups of a warp: the groups' lanes touch the
+// same offsets at the same time, so the regions are staggered by L banks (no two-way conflicts)
+__host__ __device__ inline int k3_group_stride(int words, int lanes)
+{
+    return words + ((lanes - words % 32) + 32) % 32;
+}
+
 template <int E, bool RING, int L>
 __global__ void __launch_bounds__(L < 32 ? 128 : 1024)
 chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_scr,
@@ -97,7 +104,7 @@ chain_viterbi_kernel(DevModel m, DevPlan p, const int16_t *__restrict__ chain_sc
     const bool live = u_raw < p.n_utts;
     const int u = live ? u_raw : 0;
     const int nwarps = L < 32 ? 1 : (int)(blockDim.x >> 5);
-    int32_t *sh = sh_all + (L < 32 ? (size_t)(threadIdx.x / L) * (size_t)smem_phones * (2 * E + 2) : (size_t)0);
+    int32_t *sh = sh_all + (L < 32 ? (size_t)(threadIdx.x / L) * (size_t)k3_group_stride(smem_phones * (2 * E + 2), L) : (size_t)0);
     const int64_t g0 = p.frame_off[u];
     const int64_t ph0 = p.phone_off[u];
     const int np = (int)(p.phone_off[u + 1] - ph0);
@@ -332,7 +339,8 @@ int launch_chain_viterbi(const DevModel &m, const DevPlan &p, const int16_t *cha
                 lanes = atoi(e);
     }
     const int groups = lanes < 32 ? 128 / lanes : 1;
-    const size_t smem = per_phone * (ring ? K3_RING : smem_phones) * groups;
+    const size_t smem = lanes < 32 ? (size_t)k3_group_stride(smem_phones * (2 * E + 2), lanes) * 4 * groups
+                                   : per_phone * (ring ? K3_RING : smem_phones);
     const unsigned grid = lanes < 32 ? (unsigned)((p.n_utts + groups - 1) / groups) : (unsigned)p.n_utts;
     if (lanes < 32)
         threads = 128;
