@@ -105,3 +105,55 @@ def test_unwindowed_long_chain_is_not_cut(models, oracles, golden):
     chain = dict(chain, sf=chain["sf"] * 0, ef=chain["ef"] * 0 + ssb.INT_MAX)
     _, st = _run(m, [x], [chain])
     assert st["segments"] == 1
+
+
+@pytest.mark.parametrize("lanes", ["8", "16", "32"])
+def test_lane_groups_and_cuts_on_french(models, oracles, monkeypatch, lanes):
+    """K3 with 8 / 16 / 32 lanes per utterance (several utterances per warp, kept converged), every
+    cut made, fr-fr, ragged lengths so that the groups of a warp finish at different frames."""
+    monkeypatch.setenv("SSB_K3_CUT", "all")
+    monkeypatch.setenv("SSB_K3_LANES", lanes)
+    m, o = models("fr-fr"), oracles("fr-fr")
+    rs = np.random.RandomState(31 + int(lanes))
+    arrays = o.model_arrays()
+    feats, chains = [], []
+    for u in range(37):
+        T = int(rs.randint(30, 200))
+        feats.append(model_features(rs, arrays, T))
+        chains.append(random_chain(rs, o, int(rs.randint(1, 26)), T, windowed=u % 4 != 0))
+    res, st = _run(m, feats, chains)
+    assert st["segments"] > len(feats)
+    n_ok, _ = _check(o, feats, chains, res)
+    assert n_ok >= 12
+
+
+def test_cut_chains_with_five_state_hmms(tmp_path_factory, golden, monkeypatch):
+    """The synthetic 5-state model (skip arcs: states off the best path keep the caller's values):
+    cut and uncut give the same entries, and they are the oracle's."""
+    import model_variants as mv
+    from conftest import model_dir
+    from oracle.oracle import Oracle
+    d = mv.write_five_state_model(model_dir("en-us"), str(tmp_path_factory.mktemp("five_cut") / "five"))
+    m = ssb.AcousticModel(d, device=0)
+    o = Oracle(d)
+    lx = ssb.Lexicon(m, hmmdir=d)
+    g = golden["en-us"]
+    words = g["words"]
+    chain = lx.populate(words[:, 0], words[:, 1], words[:, 2])
+    rs = np.random.RandomState(8)
+    feats = [g["feat"], g["feat"] + rs.randn(*g["feat"].shape).astype(np.float32) * np.float32(0.2)]
+    chains = [dict(ssid=chain["ssid"], tmat=chain["tmat"], sf=chain["sf"], ef=chain["ef"])] * 2
+    out = {}
+    for mode in ("all", "0"):
+        monkeypatch.setenv("SSB_K3_CUT", mode)
+        out[mode], st = _run(m, feats, chains)
+        assert (st["segments"] > 2) == (mode == "all")
+    for u, (f, c) in enumerate(zip(feats, chains)):
+        w = o.state_align(f, c["ssid"], c["tmat"], c["sf"], c["ef"])
+        for mode in ("all", "0"):
+            r = out[mode][u]
+            assert r["rv"] == w["rv"] == 0 and r["best_score"] == w["best_score"], (u, mode)
+            for k in ("start", "dur", "score"):
+                assert np.array_equal(r[k], w[k]), (u, mode, k)
+    lx.close()
+    m.close()
