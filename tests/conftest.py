@@ -27,6 +27,9 @@ def _has_gpu():
     # (a library that does not load -- stale build, missing symbol -- must fail the run, not skip
     # every GPU test: only "no device" is a reason to skip)
     import soundswallower_b200 as ssb
+    from soundswallower_b200 import _build, _lib
+    if not os.path.exists(_lib.LIB_PATH):   # a fresh checkout: compile first (nvcc needs no GPU)
+        _build.build_lib()
     return ssb.device_count() > 0
 
 
