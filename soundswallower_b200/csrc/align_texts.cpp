@@ -196,19 +196,20 @@ extern "C" ssb_text_align_t *ssb_align_texts(ssb_model_t *m, const ssb_lexicon_t
     R->kernel_ms[4] = since(t_begin);  // wall: grammars + first pass
     const auto t_chains = std::chrono::steady_clock::now();
 
-    // ---- decoder_alignment: words of pass 1 -> chains
+    // ---- decoder_alignment: words of pass 1 -> chains.  Per utterance (worker threads), then the
+    // batch arrays by concatenation.
     std::vector<int64_t> phone_off(U + 1, 0);
     std::vector<int32_t> ssid, tmat, sf, ef, st_start, st_dur, st_score;
-    std::vector<std::vector<int32_t>> ci_u(U), parent_u(U), wid_u(U);
-    for (int u = 0; u < U; ++u) {
+    std::vector<std::vector<int32_t>> ci_u(U), parent_u(U), wid_u(U), ssid_u(U), tmat_u(U);
+    std::vector<uint8_t> failed(U, 0);
+    auto chain_of = [&](int u) {
         UttResult &r = R->utt[u];
         r.n_frames = (int32_t)(frame_off[u + 1] - frame_off[u]) + 1;  // decoder_n_frames (ref :1247-1250)
         r.hyp_score = hyp_score[u];
         const ssb_fsg_built_t *b = built[utt_graph[u]];
         const ssb_fsg_graph_t &g = graphs[utt_graph[u]];
-        phone_off[u + 1] = phone_off[u];
         if (rv1[u] != 0 || exit_bp[u] <= 0 || n_seg[u] <= 0)
-            continue;  // no hypothesis: "does not match the grammar"
+            return;  // no hypothesis: "does not match the grammar"
         std::vector<int32_t> wstart, wdur;
         for (int i = 0; i < n_seg[u]; ++i) {
             const int32_t *sg = &segs[((size_t)u * max_seg + i) * 5];
@@ -231,37 +232,82 @@ extern "C" ssb_text_align_t *ssb_align_texts(ssb_model_t *m, const ssb_lexicon_t
         }
         r.rv = 0;
         if (!align_level || wid_u[u].empty())
-            continue;
+            return;
         const int nwd = (int)wid_u[u].size();
         const int32_t np = ssb_chain_populate(lx, wid_u[u].data(), nwd, nullptr, nullptr, nullptr, nullptr, 0);
-        if (np < 0)
-            return nullptr;
-        const size_t p0 = ssid.size();
-        ssid.resize(p0 + np);
-        tmat.resize(p0 + np);
+        if (np < 0) {
+            failed[u] = 1;
+            return;
+        }
+        ssid_u[u].resize(np);
+        tmat_u[u].resize(np);
         ci_u[u].resize(np);
         parent_u[u].resize(np);
         if (np > 0
-            && ssb_chain_populate(lx, wid_u[u].data(), nwd, &ssid[p0], &tmat[p0], ci_u[u].data(),
-                                  parent_u[u].data(), np) != np)
-            return nullptr;
+            && ssb_chain_populate(lx, wid_u[u].data(), nwd, ssid_u[u].data(), tmat_u[u].data(), ci_u[u].data(),
+                                  parent_u[u].data(), np) != np) {
+            failed[u] = 1;
+            return;
+        }
         for (int i = 0; i < nwd; ++i)
             r.word.push_back(Ent{wid_u[u][i], wstart[i], wdur[i], 0, -1});
+        r.phone.reserve(np);
+        r.state.reserve((size_t)np * E);
         for (int i = 0; i < np; ++i) {
             const Ent &w = r.word[parent_u[u][i]];
-            // ref: src/state_align_search.c:464-471
-            sf.push_back(w.start > 0 ? w.start : 0);
-            ef.push_back(w.dur > 0 ? w.start + w.dur : INT_MAX);
             r.phone.push_back(Ent{ci_u[u][i], w.start, w.dur, 0, parent_u[u][i]});
-            for (int j = 0; j < E; ++j) {
+            for (int j = 0; j < E; ++j)
                 // what alignment_populate leaves in the state entries (ref: src/ps_alignment.c:237-240)
-                r.state.push_back(Ent{h->sseq[(size_t)ssid[p0 + i] * E + j], w.start, w.dur, 0, i});
-                st_start.push_back(w.start);
-                st_dur.push_back(w.dur);
-                st_score.push_back(0);
-            }
+                r.state.push_back(Ent{h->sseq[(size_t)ssid_u[u][i] * E + j], w.start, w.dur, 0, i});
         }
-        phone_off[u + 1] = phone_off[u] + np;
+    };
+    {
+        const int nt = std::max(1, std::min<int>({16, (int)std::thread::hardware_concurrency(), U / 64}));
+        auto work = [&](int t) {
+            for (int u = t; u < U; u += nt)
+                chain_of(u);
+        };
+        if (nt == 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nt; ++t)
+                th.emplace_back(work, t);
+            for (auto &x : th)
+                x.join();
+        }
+    }
+    {
+        size_t np_total = 0;
+        for (int u = 0; u < U; ++u) {
+            if (failed[u])
+                return nullptr;  // (ssb_chain_populate has set the error)
+            np_total += ssid_u[u].size();
+        }
+        ssid.reserve(np_total);
+        tmat.reserve(np_total);
+        sf.reserve(np_total);
+        ef.reserve(np_total);
+        st_start.reserve(np_total * E);
+        st_dur.reserve(np_total * E);
+        st_score.assign(np_total * E, 0);
+        for (int u = 0; u < U; ++u) {
+            const UttResult &r = R->utt[u];
+            const size_t np = ssid_u[u].size();
+            ssid.insert(ssid.end(), ssid_u[u].begin(), ssid_u[u].end());
+            tmat.insert(tmat.end(), tmat_u[u].begin(), tmat_u[u].end());
+            for (size_t i = 0; i < np; ++i) {
+                const Ent &w = r.word[parent_u[u][i]];
+                // ref: src/state_align_search.c:464-471
+                sf.push_back(w.start > 0 ? w.start : 0);
+                ef.push_back(w.dur > 0 ? w.start + w.dur : INT_MAX);
+                for (int j = 0; j < E; ++j) {
+                    st_start.push_back(w.start);
+                    st_dur.push_back(w.dur);
+                }
+            }
+            phone_off[u + 1] = phone_off[u] + (int64_t)np;
+        }
     }
 
     R->kernel_ms[5] = since(t_chains);  // wall: chains on the host
@@ -291,13 +337,13 @@ extern "C" ssb_text_align_t *ssb_align_texts(ssb_model_t *m, const ssb_lexicon_t
         ao.utt_renorm = ren.data();
         if (ssb_align_batch(m, &ain, &ao) != 0)
             return nullptr;
-        for (int u = 0; u < U; ++u) {
+        auto finish_of = [&](int u) {
             UttResult &r = R->utt[u];
             if (r.rv != 0 || r.state.empty())
-                continue;
+                return;
             if (rv2[u] != 0) {
                 r.rv = -2;  // "Failed to reach final state in alignment"
-                continue;
+                return;
             }
             const size_t s0 = (size_t)phone_off[u] * E;
             for (size_t i = 0; i < r.state.size(); ++i) {
@@ -329,6 +375,20 @@ extern "C" ssb_text_align_t *ssb_align_texts(ssb_model_t *m, const ssb_lexicon_t
                 w.score += p.score;
                 last = p.parent;
             }
+        };
+        const int nt = std::max(1, std::min<int>({16, (int)std::thread::hardware_concurrency(), U / 64}));
+        auto work = [&](int t) {
+            for (int u = t; u < U; u += nt)
+                finish_of(u);
+        };
+        if (nt == 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nt; ++t)
+                th.emplace_back(work, t);
+            for (auto &x : th)
+                x.join();
         }
     }
     R->kernel_ms[6] = since(t_p2);      // wall: second pass + propagate
