@@ -552,12 +552,21 @@ def main():
     # DRAM traffic of the dominant kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of
     # one `ncu --set full` capture of this very launch shape (tools/profile_r2j.sh r2k)
     traffic = None
+    # ... and, from the same capture, what the kernel keeps busy: it is bound by issue slots of
+    # the integer / FP32 epilogue, not by the tensor pipe the roofline below is stated against
+    ncu_pct = {"smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_slots_pct",
+               "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pipe_pct",
+               "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
+               "smsp__inst_executed.sum": "warp_instructions"}
+    ncu_k1 = {}
     try:
         if U == 4096 and not args.compallsen:
             vals = {}
             unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
             for ln in open(os.path.join(ROOT, "profiles", "prof_gmm_topn_r2k.txt")):
                 f = ln.split()
+                if len(f) >= 3 and f[0] in ncu_pct:
+                    ncu_k1[ncu_pct[f[0]]] = float(f[2] if f[1] in ("%", "inst") else f[1])
                 if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                     # (tools/ncu_digest.py prints name unit value, tools/summarise_profiles.py name value unit)
                     vals[f[0]] = float(f[2]) * unit[f[1]] if f[1] in unit else float(f[1]) * unit[f[2]]
@@ -611,7 +620,7 @@ def main():
                                "K1 variant SSB_K1=%s" % os.environ.get("SSB_K1"),
                      "bound": "tensor",
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": achieved_tf / peak_tf, "traffic": traffic,
+                     "frac": achieved_tf / peak_tf, "traffic": traffic, "ncu": ncu_k1 or None,
                      "traffic_source": "profiles/prof_gmm_topn_r2k.txt (ncu --set full, same launch shape, this round's build), bytes per launch",
                      "peak_source": peak_src,
                      "note": "achieved = ALGORITHMIC flops (SURVEY 8d: scanned codebook-frames x 3 streams x "
