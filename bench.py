@@ -550,7 +550,7 @@ def main():
     except Exception:
         pass
     # DRAM traffic of the dominant kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of
-    # one `ncu --set full` capture of this very launch shape (tools/profile_r2j.sh r2k)
+    # one `ncu --set full` capture of this very launch shape (tools/profile_r2j.sh r2l)
     traffic = None
     # ... and, from the same capture, what the kernel keeps busy: it is bound by issue slots of
     # the integer / FP32 epilogue, not by the tensor pipe the roofline below is stated against
@@ -563,7 +563,7 @@ def main():
         if U == 4096 and not args.compallsen:
             vals = {}
             unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-            for ln in open(os.path.join(ROOT, "profiles", "prof_gmm_topn_r2k.txt")):
+            for ln in open(os.path.join(ROOT, "profiles", "prof_gmm_topn_r2l.txt")):
                 f = ln.split()
                 if len(f) >= 3 and f[0] in ncu_pct:
                     ncu_k1[ncu_pct[f[0]]] = float(f[2] if f[1] in ("%", "inst") else f[1])
@@ -621,7 +621,7 @@ def main():
                      "bound": "tensor",
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": achieved_tf / peak_tf, "traffic": traffic, "ncu": ncu_k1 or None,
-                     "traffic_source": "profiles/prof_gmm_topn_r2k.txt (ncu --set full, same launch shape, this round's build), bytes per launch",
+                     "traffic_source": "profiles/prof_gmm_topn_r2l.txt (ncu --set full, same launch shape, this round's build), bytes per launch",
                      "peak_source": peak_src,
                      "note": "achieved = ALGORITHMIC flops (SURVEY 8d: scanned codebook-frames x 3 streams x "
                              "128 densities x 2(2*13+1)) / CUDA-event time of the kernel; the MMAs actually "
