@@ -77,11 +77,11 @@ __device__ __forceinline__ int find_utt(const int64_t *off, int n, int64_t x)
 __global__ void __launch_bounds__(256)
 fe_melspec_kernel(FeDev fe, const void *__restrict__ pcm, int enc,
                   const int64_t *__restrict__ samp_off, const int64_t *__restrict__ frame_off,
-                  int n_utts, int64_t n_frames, double *__restrict__ mel)
+                  int n_utts, int64_t fr_base, int64_t n_frames, double *__restrict__ mel)
 {
     extern __shared__ double fe_sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t fr = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    const int64_t fr = fr_base + (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;  // frames [fr_base, n_frames)
     if (fr >= n_frames)
         return;
     const int n = fe.fft_size, m = fe.fft_order, fs = fe.frame_size;
@@ -194,13 +194,13 @@ template <int LR>
 __global__ void __launch_bounds__(256)
 fe_melspec_reg_kernel(FeDev fe, const void *__restrict__ pcm, int enc,
                       const int64_t *__restrict__ samp_off,
-                      const int64_t *__restrict__ frame_off, int n_utts, int64_t n_frames,
-                      double *__restrict__ mel)
+                      const int64_t *__restrict__ frame_off, int n_utts, int64_t fr_base,
+                      int64_t n_frames, double *__restrict__ mel)
 {
     constexpr int R = 1 << LR, NN = 32 * R, M = 5 + LR, LDW = NN + NN / 16;
     extern __shared__ double fe_sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t fr = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    const int64_t fr = fr_base + (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;  // frames [fr_base, n_frames)
     if (fr >= n_frames)
         return;
     double *x = fe_sm + (size_t)warp * LDW;
@@ -777,6 +777,11 @@ struct ssb_frontend_s {
     int32_t n_utts = 0;
     int64_t n_frames = 0;
     cudaEvent_t ev[7] = {};
+    // the audio travels in pieces on a stream of its own; the mel spectrum of a piece starts when
+    // the piece has landed, under the copy of the next one
+    static constexpr int kPieces = 4;
+    cudaStream_t copy_st = nullptr;
+    cudaEvent_t ev_piece[kPieces] = {}, ev_free = nullptr;
     bool have_ev = false, ran = false;
     bool force_generic = false;  // SSB_FE=generic: the shared-memory-only mel spectrum kernel
 };
@@ -999,6 +1004,13 @@ extern "C" ssb_frontend_t *ssb_frontend_create(const ssb_fe_config_t *c, int dev
     for (auto &ev : fe->ev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess)
             return fail("cudaEventCreate", e);
+    for (auto &ev : fe->ev_piece)
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess)
+            return fail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&fe->ev_free, cudaEventDisableTiming)) != cudaSuccess)
+        return fail("cudaEventCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&fe->copy_st, cudaStreamNonBlocking)) != cudaSuccess)
+        return fail("cudaStreamCreate", e);
     fe->have_ev = true;
     // two fft_size arrays of doubles per warp, 64 KB per CTA (8 warps up to 512 points)
     e = cudaFuncSetAttribute(fe_melspec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1016,9 +1028,18 @@ extern "C" void ssb_frontend_free(ssb_frontend_t *fe)
         cudaSetDevice(fe->device);
         if (fe->ran)
             cudaStreamSynchronize(fe->st);
-        if (fe->have_ev)
-            for (auto &ev : fe->ev)
+        if (fe->copy_st) {
+            cudaStreamSynchronize(fe->copy_st);
+            cudaStreamDestroy(fe->copy_st);
+        }
+        for (auto &ev : fe->ev)
+            if (ev)
                 cudaEventDestroy(ev);
+        for (auto &ev : fe->ev_piece)
+            if (ev)
+                cudaEventDestroy(ev);
+        if (fe->ev_free)
+            cudaEventDestroy(fe->ev_free);
         for (DBuf *b : {&fe->tables, &fe->pcm, &fe->samp_off, &fe->frame_off, &fe->mel, &fe->mfcc,
                         &fe->feat, &fe->mean, &fe->scale})
             b->release();
@@ -1121,37 +1142,67 @@ extern "C" int64_t ssb_frontend_run(ssb_frontend_t *fe, const void *pcm, int32_t
     cudaStream_t st = fe->st;
     launch_count(true);
     API_CUDA(cudaEventRecord(fe->ev[0], st), -1);
-    if (S > 0)
-        API_CUDA(cudaMemcpyAsync(fe->pcm.p, pcm, (size_t)S * ssz, cudaMemcpyDefault, st), -1);
     const int64_t zero = 0;
     API_CUDA(cudaMemcpyAsync(fe->samp_off.p, U > 0 ? samp_off : &zero, (size_t)(U + 1) * 8,
                              cudaMemcpyHostToDevice, st), -1);
     API_CUDA(cudaMemcpyAsync(fe->frame_off.p, fe->h_frame_off.data(), (size_t)(U + 1) * 8,
                              cudaMemcpyHostToDevice, st), -1);
+    // pieces of whole utterances with about equal sample counts (one piece for small inputs)
+    int piece_u[ssb_frontend_s::kPieces + 1];
+    int n_pieces = (S * (int64_t)ssz >= (64 << 20) && U >= 2 * ssb_frontend_s::kPieces) ? ssb_frontend_s::kPieces : 1;
+    piece_u[0] = 0;
+    for (int k = 1; k < n_pieces; ++k) {
+        const int64_t want = S * k / n_pieces;
+        int u = piece_u[k - 1];
+        while (u < U && samp_off[u] < want)
+            ++u;
+        piece_u[k] = std::max(u, piece_u[k - 1]);
+    }
+    piece_u[n_pieces] = U;
+    if (n_pieces > 1) {
+        // the copy stream may not overwrite the buffer while earlier work on `st` still reads it
+        API_CUDA(cudaEventRecord(fe->ev_free, st), -1);
+        API_CUDA(cudaStreamWaitEvent(fe->copy_st, fe->ev_free, 0), -1);
+    }
     API_CUDA(cudaEventRecord(fe->ev[1], st), -1);
     const int64_t *d_so = fe->samp_off.as<int64_t>(), *d_fo = fe->frame_off.as<int64_t>();
-    if (G > 0) {
-        const bool reg = !h.c.remove_dc && !fe->force_generic
-                         && (h.fft_size == 256 || h.fft_size == 512 || h.fft_size == 1024);
+    const bool reg = !h.c.remove_dc && !fe->force_generic
+                     && (h.fft_size == 256 || h.fft_size == 512 || h.fft_size == 1024);
+    for (int k = 0; k < n_pieces; ++k) {
+        const int u0 = piece_u[k], u1 = piece_u[k + 1];
+        if (u1 <= u0)
+            continue;
+        const int64_t s0 = samp_off[u0], s1 = samp_off[u1];
+        cudaStream_t cs = n_pieces > 1 ? fe->copy_st : st;
+        if (s1 > s0)
+            API_CUDA(cudaMemcpyAsync(fe->pcm.as<char>() + (size_t)s0 * ssz, (const char *)pcm + (size_t)s0 * ssz,
+                                     (size_t)(s1 - s0) * ssz, cudaMemcpyDefault, cs), -1);
+        if (n_pieces > 1) {
+            API_CUDA(cudaEventRecord(fe->ev_piece[k], cs), -1);
+            API_CUDA(cudaStreamWaitEvent(st, fe->ev_piece[k], 0), -1);
+        }
+        const int64_t f0 = fe->h_frame_off[u0], f1 = fe->h_frame_off[u1];
+        if (f1 <= f0)
+            continue;
         if (reg) {  // register-resident first stages
             const int warps = h.fft_size == 1024 ? 4 : 8;
-            const int64_t blocks = (G + warps - 1) / warps;
+            const int64_t blocks = (f1 - f0 + warps - 1) / warps;
             const size_t smem = (size_t)warps * (h.fft_size + h.fft_size / 16) * 8;
             double *mel = fe->mel.as<double>();
             if (h.fft_size == 256)
                 fe_melspec_reg_kernel<3><<<(unsigned)blocks, warps * 32, smem, st>>>(
-                    fe->d, fe->pcm.p, encoding, d_so, d_fo, U, G, mel);
+                    fe->d, fe->pcm.p, encoding, d_so, d_fo, U, f0, f1, mel);
             else if (h.fft_size == 512)
                 fe_melspec_reg_kernel<4><<<(unsigned)blocks, warps * 32, smem, st>>>(
-                    fe->d, fe->pcm.p, encoding, d_so, d_fo, U, G, mel);
+                    fe->d, fe->pcm.p, encoding, d_so, d_fo, U, f0, f1, mel);
             else
                 fe_melspec_reg_kernel<5><<<(unsigned)blocks, warps * 32, smem, st>>>(
-                    fe->d, fe->pcm.p, encoding, d_so, d_fo, U, G, mel);
+                    fe->d, fe->pcm.p, encoding, d_so, d_fo, U, f0, f1, mel);
         } else {  // any power of two up to 2048, per-frame DC removal
             const int warps = std::max(1, std::min(8, kMelSmem / (2 * h.fft_size * 8)));
-            const int64_t blocks = (G + warps - 1) / warps;
+            const int64_t blocks = (f1 - f0 + warps - 1) / warps;
             fe_melspec_kernel<<<(unsigned)blocks, warps * 32, (size_t)warps * 2 * h.fft_size * 8,
-                                st>>>(fe->d, fe->pcm.p, encoding, d_so, d_fo, U, G,
+                                st>>>(fe->d, fe->pcm.p, encoding, d_so, d_fo, U, f0, f1,
                                       fe->mel.as<double>());
         }
         note_launch();
