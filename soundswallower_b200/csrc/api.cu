@@ -1458,7 +1458,10 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
                 b->seg_off.push_back((int32_t)st0.size());
             }
             const int S = (int)st0.size();
-            if (S > U) {
+            // (a segment too long for shared memory would index the per-utterance spill area by its
+            // segment number: such batches stay uncut)
+            const int smem_cap = (int)((200 * 1024) / ((size_t)(2 * E + 2) * 4));
+            if (S > U && b->cut_max_phones <= smem_cap) {
                 std::vector<int64_t> zero((size_t)S + 1, 0);
                 if (upload(b->d_seg_frame_off, sfo, st) || upload(b->d_seg_phone_off, spo, st)
                     || upload(b->d_seg_scr_off, zero, st) || upload(b->d_seg_enter, en2, st)
