@@ -1406,13 +1406,15 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
     // best - 0x300000 < WORST_SCORE (ref :193-197): path scores only decrease, so a total above
     // that line proves no frame was renormalised; otherwise ssb_batch_download runs the uncut
     // kernels again.  Only with the banded layout (the dense debug stacks hold absolute scores),
-    // and by default only for chains of more than 128 phones ($SSB_K3_CUT = all | 0).
+    // and by default for chains of more than 128 phones and for batches of fewer than 512 utterances
+    // ($SSB_K3_CUT = all | 0).
     b->cut = false;
     b->n_segs = 0;
     {
         const char *e = getenv("SSB_K3_CUT");
         const bool cut_all = e && strcmp(e, "all") == 0, cut_off = e && *e == '0';
-        if (b->banded && !cut_off && U > 0 && b->n_phones > 0 && (cut_all || b->max_phones > 128)) {
+        const bool few = U < 512;  // a batch that leaves the GPU idle: every cut adds a warp of work in flight
+        if (b->banded && !cut_off && U > 0 && b->n_phones > 0 && (cut_all || few || b->max_phones > 128)) {
             std::vector<int64_t> sfo(1, b->frame_off[0]), spo(1, 0), sbo2(sb.begin(), sb.end()), tbo2(tb.begin(), tb.end());
             std::vector<int32_t> st0, en2(b->enter), sf2(in->sf, in->sf + b->n_phones), ef2(in->ef, in->ef + b->n_phones);
             b->seg_off.assign(1, 0);
@@ -1436,7 +1438,7 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
                 const int T = (int)(b->frame_off[u + 1] - b->frame_off[u]);
                 int a = 0;
                 int32_t t0 = 0;
-                if (cut_all || np > 128)
+                if (cut_all || few || np > 128)
                     for (int i = 1; i < np; ++i) {
                         const int32_t s = in->sf[p0 + i];
                         if (s > t0 && s < T && b->enter[p0 + i] == s && in->ef[p0 + i - 1] == s
