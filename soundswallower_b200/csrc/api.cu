@@ -1710,6 +1710,9 @@ static int run_chain(ssb_batch_t *b, bool cut, bool timed)
         // duration -1 marks "state not on the best path"
         if (b->n_states > 0) {
             API_CUDA(cudaMemsetAsync(b->st_dur.p, 0xff, (size_t)b->n_states * 4, st), -1);
+            // (start frames of states off the path are never read back into the caller's arrays;
+            // zeroed so that the download copies initialised memory)
+            API_CUDA(cudaMemsetAsync(b->st_start.p, 0, (size_t)b->n_states * 4, st), -1);
             // 0x80808080 marks "score never written" (the first state of an utterance)
             API_CUDA(cudaMemsetAsync(b->st_score.p, 0x80, (size_t)b->n_states * 4, st), -1);
         }
