@@ -66,6 +66,27 @@ static void hyp_item(std::string &out, double b, double d, double p, const char 
 
 extern "C" void ssb_text_align_free(ssb_text_align_t *r) { delete r; }
 
+// fn(u) for every utterance, on up to 16 host threads (utterances are independent; one thread per
+// 64 utterances at least, so that small batches stay on the caller's thread)
+template <class F>
+static void for_each_utt(int U, F fn)
+{
+    const int nt = std::max(1, std::min<int>({16, (int)std::thread::hardware_concurrency(), U / 64}));
+    auto work = [&](int t) {
+        for (int u = t; u < U; u += nt)
+            fn(u);
+    };
+    if (nt == 1) {
+        work(0);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t)
+        th.emplace_back(work, t);
+    for (auto &x : th)
+        x.join();
+}
+
 extern "C" ssb_text_align_t *ssb_align_texts(ssb_model_t *m, const ssb_lexicon_t *lx, const float *feat,
                                              const int64_t *frame_off, const char *const *texts,
                                              int32_t n_utts, const ssb_fsg_config_t *cfg,
@@ -261,22 +282,7 @@ extern "C" ssb_text_align_t *ssb_align_texts(ssb_model_t *m, const ssb_lexicon_t
                 r.state.push_back(Ent{h->sseq[(size_t)ssid_u[u][i] * E + j], w.start, w.dur, 0, i});
         }
     };
-    {
-        const int nt = std::max(1, std::min<int>({16, (int)std::thread::hardware_concurrency(), U / 64}));
-        auto work = [&](int t) {
-            for (int u = t; u < U; u += nt)
-                chain_of(u);
-        };
-        if (nt == 1) {
-            work(0);
-        } else {
-            std::vector<std::thread> th;
-            for (int t = 0; t < nt; ++t)
-                th.emplace_back(work, t);
-            for (auto &x : th)
-                x.join();
-        }
-    }
+    for_each_utt(U, chain_of);
     {
         size_t np_total = 0;
         for (int u = 0; u < U; ++u) {
@@ -376,20 +382,7 @@ extern "C" ssb_text_align_t *ssb_align_texts(ssb_model_t *m, const ssb_lexicon_t
                 last = p.parent;
             }
         };
-        const int nt = std::max(1, std::min<int>({16, (int)std::thread::hardware_concurrency(), U / 64}));
-        auto work = [&](int t) {
-            for (int u = t; u < U; u += nt)
-                finish_of(u);
-        };
-        if (nt == 1) {
-            work(0);
-        } else {
-            std::vector<std::thread> th;
-            for (int t = 0; t < nt; ++t)
-                th.emplace_back(work, t);
-            for (auto &x : th)
-                x.join();
-        }
+        for_each_utt(U, finish_of);
     }
     R->kernel_ms[6] = since(t_p2);      // wall: second pass + propagate
     R->kernel_ms[7] = since(t_begin);
@@ -512,20 +505,7 @@ extern "C" int ssb_text_align_render(ssb_text_align_t *r, double start, int32_t 
         return -1;
     }
     const int U = (int)r->utt.size();
-    const int nt = std::max(1, std::min<int>({16, (int)std::thread::hardware_concurrency(), U / 64}));
-    auto work = [&](int t) {
-        for (int u = t; u < U; u += nt)
-            ssb_text_align_json(r, u, start, align_level);
-    };
-    if (nt == 1) {
-        work(0);
-    } else {
-        std::vector<std::thread> th;
-        for (int t = 0; t < nt; ++t)
-            th.emplace_back(work, t);
-        for (auto &x : th)
-            x.join();
-    }
+    for_each_utt(U, [&](int u) { ssb_text_align_json(r, u, start, align_level); });
     return 0;
 }
 
