@@ -746,7 +746,6 @@ struct ssb_batch_s {
     bool cut = false, cut_ran = false;  // planned / what the last run used
     int n_segs = 0, cut_max_phones = 0, cut_max_band = 0;
     std::vector<int32_t> seg_off;       // [U+1] segments of each utterance
-    std::vector<int64_t> seg_phone_off; // [S+1] (global phone index)
     DevPlan cut_plan{};
     DBuf d_seg_frame_off, d_seg_phone_off, d_seg_scr_off, d_seg_enter, d_seg_sf, d_seg_ef, d_seg_scr_boff,
         d_seg_tok_boff, d_seg_t0, seg_rv, seg_best, seg_renorm, seg_fin_hist, seg_fin_score;
@@ -1476,7 +1475,6 @@ extern "C" int ssb_batch_upload(ssb_batch_t *b, const ssb_align_in_t *in)
                 API_CUDA(cudaStreamSynchronize(st), -1);
                 b->cut = true;
                 b->n_segs = S;
-                b->seg_phone_off = spo;
                 b->cut_max_band = std::min(b->max_band, b->cut_max_phones);
                 b->cut_plan = p;
                 b->cut_plan.n_utts = S;
